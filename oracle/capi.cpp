@@ -1,0 +1,240 @@
+// ORACLE (test infrastructure, not product code).  C entry points over the CPU restatement so
+// that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can drive it with ctypes.
+// All field elements cross this boundary in CANONICAL form.  Nothing under ziren_b200/ links,
+// imports or calls this library.
+#include "prover.h"
+#include <cstdlib>
+#include <cstring>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace zko;
+
+static thread_local std::string g_err;
+static int fail(const std::exception& e) { g_err = e.what(); return 1; }
+
+static Matrix mat_from(const u32* p, size_t h, size_t w) {
+  Matrix m(h, w);
+  for (size_t i = 0; i < h * w; i++) m.v[i] = F(p[i]);
+  return m;
+}
+static E e_from(const u32* p) { return E(F(p[0]), F(p[1]), F(p[2]), F(p[3])); }
+static void e_to(const E& e, u32* p) { for (int i = 0; i < 4; i++) p[i] = e.c[i].v; }
+
+extern "C" {
+
+const char* zko_last_error() { return g_err.c_str(); }
+int zko_num_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void zko_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+void zko_poseidon2_permute(u32* s) {
+  F st[16];
+  for (int i = 0; i < 16; i++) st[i] = F(s[i]);
+  poseidon2_permute(st);
+  for (int i = 0; i < 16; i++) s[i] = st[i].v;
+}
+void zko_poseidon2_permute_batch(u32* s, size_t n) {
+#pragma omp parallel for schedule(static)
+  for (size_t k = 0; k < n; k++) zko_poseidon2_permute(s + 16 * k);
+}
+void zko_hash(const u32* in, size_t n, u32* out) {
+  std::vector<F> v(n);
+  for (size_t i = 0; i < n; i++) v[i] = F(in[i]);
+  Digest d = sponge_hash(v.data(), n);
+  for (int i = 0; i < 8; i++) out[i] = d[i].v;
+}
+void zko_compress(const u32* l, const u32* r, u32* out) {
+  Digest a, b;
+  for (int i = 0; i < 8; i++) { a[i] = F(l[i]); b[i] = F(r[i]); }
+  Digest d = compress2(a, b);
+  for (int i = 0; i < 8; i++) out[i] = d[i].v;
+}
+void zko_ef_mul(const u32* a, const u32* b, u32* out) { e_to(e_from(a) * e_from(b), out); }
+void zko_ef_inv(const u32* a, u32* out) { e_to(einv(e_from(a)), out); }
+u32 zko_two_adic_generator(unsigned bits) { return two_adic_generator(bits).v; }
+
+void zko_dft(u32* data, size_t h, size_t w, int inverse) {
+  Matrix m = mat_from(data, h, w);
+  dft_rows(m, inverse != 0);
+  for (size_t i = 0; i < h * w; i++) data[i] = m.v[i].v;
+}
+// out: (h << added_bits) x w, rows bit-reversed (the committed layout)
+void zko_coset_lde(const u32* in, size_t h, size_t w, unsigned added_bits, u32 shift, u32* out) {
+  Matrix r = coset_lde_bitrev(mat_from(in, h, w), added_bits, F(shift));
+  for (size_t i = 0; i < r.v.size(); i++) out[i] = r.v[i].v;
+}
+// Merkle root over matrices as given (no LDE): MerkleTreeMmcs::commit
+void zko_mmcs_root(int nmats, const u32* const* mats, const size_t* heights, const size_t* widths, u32* root) {
+  MerkleTree t;
+  for (int i = 0; i < nmats; i++) t.mats.push_back(mat_from(mats[i], heights[i], widths[i]));
+  t.build();
+  for (int i = 0; i < 8; i++) root[i] = t.root[i].v;
+}
+// TwoAdicFriPcs::commit root: LDE (shift GENERATOR/domain_shift) + Merkle
+void zko_pcs_commit_root(int nmats, const u32* const* mats, const size_t* heights, const size_t* widths,
+                         const u32* domain_shifts, unsigned log_blowup, u32* root) {
+  FriConfig cfg; cfg.log_blowup = log_blowup;
+  std::vector<std::pair<Domain, Matrix>> in;
+  for (int i = 0; i < nmats; i++)
+    in.push_back({Domain{log2_strict(heights[i]), F(domain_shifts ? domain_shifts[i] : 1)}, mat_from(mats[i], heights[i], widths[i])});
+  auto cd = pcs_commit(in, cfg);
+  for (int i = 0; i < 8; i++) root[i] = cd->commit()[i].v;
+}
+// one FRI fold step on m EF values (bit-reversed order), optional add of beta^2 * ro_next
+void zko_fri_fold(const u32* in, size_t m, const u32* beta, const u32* ro_next, u32* out) {
+  unsigned lm = log2_strict(m);
+  F g = two_adic_generator(lm);
+  E b = e_from(beta), b2 = b * b;
+  for (size_t i = 0; i < m / 2; i++) {
+    E r = fold_pair(e_from(in + 8 * i), e_from(in + 8 * i + 4), fpow(g, bitrev(2 * i, lm)), b);
+    if (ro_next) r += b2 * e_from(ro_next + 4 * i);
+    e_to(r, out + 4 * i);
+  }
+}
+// challenger script: ops[i] = 0 observe(vals[i]) | 1 sample -> out | 2 sample_bits(vals[i]) -> out
+void zko_challenger_script(u32* state34, const u32* ops, const u32* vals, size_t n, u32* out) {
+  Challenger ch; ch.from_words(state34);
+  size_t o = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (ops[i] == 0) ch.observe(F(vals[i]));
+    else if (ops[i] == 1) out[o++] = ch.sample().v;
+    else out[o++] = ch.sample_bits(vals[i]);
+  }
+  ch.to_words(state34);
+}
+u32 zko_grind(u32* state34, unsigned bits) {
+  Challenger ch; ch.from_words(state34);
+  F w = ch.grind(bits);
+  ch.to_words(state34);
+  return w.v;
+}
+
+// ---- machine level ------------------------------------------------------------------------------
+void* zko_machine_new(const u32* desc, size_t n) {
+  try { return new Machine(parse_machine(desc, n)); } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+void zko_machine_free(void* m) { delete (Machine*)m; }
+int zko_chip_info(void* m_, const char* name, u32* out /* perm_width_ef, num_constraints, lqd */) {
+  const Chip* c = ((Machine*)m_)->find(name);
+  if (!c) return 1;
+  out[0] = (u32)c->perm_width_ef(); out[1] = (u32)c->num_constraints(); out[2] = c->log_quotient_degree;
+  return 0;
+}
+
+void* zko_setup(void* m_, int n, const char* const* names, const u32* const* ptrs, const size_t* heights,
+                const size_t* widths, u32 pc_start, const u32* init_gsum, u32* commit_out) {
+  try {
+    std::vector<std::pair<std::string, Matrix>> prep;
+    for (int i = 0; i < n; i++) prep.push_back({names[i], mat_from(ptrs[i], heights[i], widths[i])});
+    F gs[14];
+    for (int i = 0; i < 14; i++) gs[i] = F(init_gsum ? init_gsum[i] : 0);
+    auto pk = setup(*(Machine*)m_, std::move(prep), F(pc_start), gs);
+    if (commit_out) for (int i = 0; i < 8; i++) commit_out[i] = pk->commit[i].v;
+    return pk.release();
+  } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+void zko_pk_free(void* pk) { delete (ProvingKey*)pk; }
+// the challenger every shard proof starts from: fresh challenger after pk.observe_into
+void zko_pk_initial_challenger(void* pk, u32* state34) {
+  Challenger ch;
+  ((ProvingKey*)pk)->observe_into(ch);
+  ch.to_words(state34);
+}
+
+// commit + open of one shard.  challenger34 is in/out (a clone of the post-observe_into state).
+int zko_prove_shard(void* m_, void* pk_, int n, const char* const* names, const u32* const* ptrs,
+                    const size_t* heights, const size_t* widths, const u32* pv, size_t npv, u32* challenger34,
+                    u32** out_words, size_t* out_len) {
+  try {
+    const Machine& m = *(Machine*)m_;
+    std::vector<std::pair<std::string, Matrix>> tr;
+    for (int i = 0; i < n; i++) tr.push_back({names[i], mat_from(ptrs[i], heights[i], widths[i])});
+    std::vector<F> pvs(npv);
+    for (size_t i = 0; i < npv; i++) pvs[i] = F(pv[i]);
+    auto sd = commit(m, std::move(tr), pvs);
+    Challenger ch; ch.from_words(challenger34);
+    auto proof = open(m, *(ProvingKey*)pk_, *sd, ch);
+    ch.to_words(challenger34);
+    std::vector<u32> w = serialize_proof(*proof);
+    *out_words = (u32*)malloc(w.size() * 4);
+    memcpy(*out_words, w.data(), w.size() * 4);
+    *out_len = w.size();
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+// main commitment only (MachineProver::commit)
+int zko_commit_shard(void* m_, int n, const char* const* names, const u32* const* ptrs, const size_t* heights,
+                     const size_t* widths, u32* commit_out) {
+  try {
+    std::vector<std::pair<std::string, Matrix>> tr;
+    for (int i = 0; i < n; i++) tr.push_back({names[i], mat_from(ptrs[i], heights[i], widths[i])});
+    auto sd = commit(*(Machine*)m_, std::move(tr), {});
+    for (int i = 0; i < 8; i++) commit_out[i] = sd->main_data->commit()[i].v;
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+void zko_free(void* p) { free(p); }
+
+// returns 0 when the proof verifies; otherwise 1 and zko_last_error() says why
+int zko_verify_shard(void* m_, void* pk_, const u32* proof_words, size_t n, const u32* challenger34) {
+  try {
+    ShardProof p = parse_proof(proof_words, n);
+    VerifyingKey vk = vk_from_pk(*(ProvingKey*)pk_);
+    Challenger ch; ch.from_words(challenger34);
+    std::string err = verify_shard(*(Machine*)m_, vk, ch, p);
+    if (!err.empty()) { g_err = err; return 1; }
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+// ---- stage hooks for kernel-level parity tests ----------------------------------------------------
+int zko_permutation_trace(void* m_, const char* chip, const u32* prep, const u32* main, size_t height,
+                          const u32* alpha, const u32* beta, u32* out, u32* local_sum) {
+  try {
+    const Chip* c = ((Machine*)m_)->find(chip);
+    if (!c) throw std::runtime_error("unknown chip");
+    Matrix pm, mm = mat_from(main, height, c->main_width);
+    if (prep) pm = mat_from(prep, height, c->prep_width);
+    E ls;
+    Matrix r = generate_permutation_trace(*c, prep ? &pm : nullptr, mm, e_from(alpha), e_from(beta), ls);
+    for (size_t i = 0; i < r.v.size(); i++) out[i] = r.v[i].v;
+    e_to(ls, local_sum);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+// LDE inputs are the committed (bit-reversed) matrices of height n << log_blowup; out is Q x 4 natural order
+int zko_quotient_values(void* m_, const char* chip, unsigned log_n, const u32* prep_lde, const u32* main_lde,
+                        const u32* perm_lde, const u32* perm_alpha, const u32* perm_beta, const u32* local_sum,
+                        const u32* global_sum, const u32* alpha, const u32* pub, size_t npub, u32* out) {
+  try {
+    const Machine& m = *(Machine*)m_;
+    const Chip* c = m.find(chip);
+    if (!c) throw std::runtime_error("unknown chip");
+    size_t H = (size_t)1 << (log_n + m.cfg.log_blowup);
+    Matrix pl, ml = mat_from(main_lde, H, c->main_width), el = mat_from(perm_lde, H, 4 * c->perm_width_ef());
+    if (prep_lde) pl = mat_from(prep_lde, H, c->prep_width);
+    F gs[14];
+    for (int i = 0; i < 14; i++) gs[i] = F(global_sum[i]);
+    std::vector<F> pubv(npub + 1);
+    for (size_t i = 0; i < npub; i++) pubv[i] = F(pub[i]);
+    std::vector<E> q = quotient_values(*c, log_n, prep_lde ? &pl : nullptr, ml, el, e_from(perm_alpha), e_from(perm_beta),
+                                       e_from(local_sum), gs, e_from(alpha), pubv.data());
+    for (size_t i = 0; i < q.size(); i++) e_to(q[i], out + 4 * i);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+"""ctypes bindings of the CPU oracle (oracle/libzkoracle.so) and of the reference-header shim
+(oracle/_ref/libzkref.so).  TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs.  Canonical-form uint32 everywhere."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+u32p = C.POINTER(C.c_uint32)
+
+
+def build(quiet: bool = True):
+    subprocess.run(["make", "-C", _DIR], check=True, stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _load(path):
+    if not os.path.exists(path):
+        build()
+    return C.CDLL(path)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _load(os.path.join(_DIR, "libzkoracle.so"))
+        _lib.zko_last_error.restype = C.c_char_p
+        _lib.zko_machine_new.restype = C.c_void_p
+        _lib.zko_setup.restype = C.c_void_p
+        _lib.zko_two_adic_generator.restype = C.c_uint32
+        _lib.zko_grind.restype = C.c_uint32
+    return _lib
+
+
+def ref_lib():
+    """The reference's own kb31_t / Poseidon2 C++ headers behind a C shim; None if not built."""
+    p = os.path.join(_DIR, "_ref", "libzkref.so")
+    if not os.path.exists(p):
+        return None
+    l = C.CDLL(p)
+    for f in ("ref_kb31_mul", "ref_kb31_add", "ref_kb31_sub", "ref_kb31_inv", "ref_kb31_to_monty", "ref_kb31_from_monty"):
+        getattr(l, f).restype = C.c_uint32
+        getattr(l, f).argtypes = [C.c_uint32] * (1 if f.endswith(("inv", "monty")) else 2)
+    return l
+
+
+def _a(x):
+    return np.ascontiguousarray(x, dtype=np.uint32)
+
+
+def _p(x):
+    return x.ctypes.data_as(u32p)
+
+
+def err():
+    return lib().zko_last_error().decode()
+
+
+def num_threads():
+    return lib().zko_num_threads()
+
+
+def set_num_threads(n):
+    lib().zko_set_num_threads(int(n))
+
+
+def permute(state):
+    s = _a(state).copy()
+    lib().zko_poseidon2_permute(_p(s))
+    return s
+
+
+def permute_batch(states):
+    s = _a(states).copy()
+    lib().zko_poseidon2_permute_batch(_p(s), C.c_size_t(s.size // 16))
+    return s
+
+
+def hash(x):
+    x = _a(x)
+    out = np.zeros(8, np.uint32)
+    lib().zko_hash(_p(x), C.c_size_t(x.size), _p(out))
+    return out
+
+
+def compress(l, r):
+    l, r = _a(l), _a(r)
+    out = np.zeros(8, np.uint32)
+    lib().zko_compress(_p(l), _p(r), _p(out))
+    return out
+
+
+def ef_mul(a, b):
+    a, b = _a(a), _a(b)
+    out = np.zeros(4, np.uint32)
+    lib().zko_ef_mul(_p(a), _p(b), _p(out))
+    return out
+
+
+def ef_inv(a):
+    a = _a(a)
+    out = np.zeros(4, np.uint32)
+    lib().zko_ef_inv(_p(a), _p(out))
+    return out
+
+
+def two_adic_generator(bits):
+    return lib().zko_two_adic_generator(C.c_uint(bits))
+
+
+def dft(mat, inverse=False):
+    m = _a(mat).copy()
+    lib().zko_dft(_p(m), C.c_size_t(m.shape[0]), C.c_size_t(m.shape[1]), C.c_int(int(inverse)))
+    return m
+
+
+def coset_lde(mat, added_bits=1, shift=3):
+    m = _a(mat)
+    out = np.zeros((m.shape[0] << added_bits, m.shape[1]), np.uint32)
+    lib().zko_coset_lde(_p(m), C.c_size_t(m.shape[0]), C.c_size_t(m.shape[1]), C.c_uint(added_bits), C.c_uint32(shift), _p(out))
+    return out
+
+
+def _mat_args(mats):
+    mats = [_a(m) for m in mats]
+    n = len(mats)
+    ptrs = (u32p * n)(*[_p(m) for m in mats])
+    hs = (C.c_size_t * n)(*[m.shape[0] for m in mats])
+    ws = (C.c_size_t * n)(*[m.shape[1] for m in mats])
+    return mats, n, ptrs, hs, ws
+
+
+def mmcs_root(mats):
+    mats, n, ptrs, hs, ws = _mat_args(mats)
+    out = np.zeros(8, np.uint32)
+    lib().zko_mmcs_root(C.c_int(n), ptrs, hs, ws, _p(out))
+    return out
+
+
+def pcs_commit_root(mats, shifts=None, log_blowup=1):
+    mats, n, ptrs, hs, ws = _mat_args(mats)
+    out = np.zeros(8, np.uint32)
+    sh = _a(shifts) if shifts is not None else None
+    lib().zko_pcs_commit_root(C.c_int(n), ptrs, hs, ws, _p(sh) if sh is not None else None, C.c_uint(log_blowup), _p(out))
+    return out
+
+
+def fri_fold(vals, beta, ro_next=None):
+    v = _a(vals)
+    m = v.size // 4
+    out = np.zeros((m // 2, 4), np.uint32)
+    b = _a(beta)
+    r = _a(ro_next) if ro_next is not None else None
+    lib().zko_fri_fold(_p(v), C.c_size_t(m), _p(b), _p(r) if r is not None else None, _p(out))
+    return out
+
+
+def challenger_script(state34, ops, vals):
+    st, ops, vals = _a(state34).copy(), _a(ops), _a(vals)
+    out = np.zeros(int((ops != 0).sum()) + 1, np.uint32)
+    lib().zko_challenger_script(_p(st), _p(ops), _p(vals), C.c_size_t(ops.size), _p(out))
+    return st, out[:-1]
+
+
+def grind(state34, bits):
+    st = _a(state34).copy()
+    w = lib().zko_grind(_p(st), C.c_uint(bits))
+    return st, w
+
+
+def _named(named):
+    names = [n.encode() for n in named]
+    mats, n, ptrs, hs, ws = _mat_args(list(named.values()))
+    cn = (C.c_char_p * n)(*names)
+    return mats, n, cn, ptrs, hs, ws
+
+
+class OracleMachine:
+    def __init__(self, machine):
+        d = _a(machine.descriptor())
+        self.h = lib().zko_machine_new(_p(d), C.c_size_t(d.size))
+        if not self.h:
+            raise RuntimeError("oracle: " + err())
+        self.machine = machine
+        self.pk = None
+
+    def chip_info(self, name):
+        out = np.zeros(3, np.uint32)
+        assert lib().zko_chip_info(C.c_void_p(self.h), name.encode(), _p(out)) == 0
+        return dict(perm_width_ef=int(out[0]), num_constraints=int(out[1]), log_quotient_degree=int(out[2]))
+
+    def setup(self, prep: dict, pc_start=0, init_gsum=None):
+        mats, n, cn, ptrs, hs, ws = _named(prep)
+        commit = np.zeros(8, np.uint32)
+        gs = _a(init_gsum) if init_gsum is not None else np.zeros(14, np.uint32)
+        self.pk = lib().zko_setup(C.c_void_p(self.h), C.c_int(n), cn, ptrs, hs, ws, C.c_uint32(pc_start), _p(gs), _p(commit))
+        if not self.pk:
+            raise RuntimeError("oracle: " + err())
+        return commit
+
+    def initial_challenger(self):
+        st = np.zeros(34, np.uint32)
+        lib().zko_pk_initial_challenger(C.c_void_p(self.pk), _p(st))
+        return st
+
+    def commit_shard(self, traces: dict):
+        mats, n, cn, ptrs, hs, ws = _named(traces)
+        out = np.zeros(8, np.uint32)
+        if lib().zko_commit_shard(C.c_void_p(self.h), C.c_int(n), cn, ptrs, hs, ws, _p(out)):
+            raise RuntimeError("oracle: " + err())
+        return out
+
+    def prove_shard(self, traces: dict, public_values, challenger=None):
+        mats, n, cn, ptrs, hs, ws = _named(traces)
+        pv = _a(public_values)
+        st = _a(challenger).copy() if challenger is not None else self.initial_challenger()
+        outp, outn = u32p(), C.c_size_t()
+        rc = lib().zko_prove_shard(C.c_void_p(self.h), C.c_void_p(self.pk), C.c_int(n), cn, ptrs, hs, ws, _p(pv),
+                                   C.c_size_t(pv.size), _p(st), C.byref(outp), C.byref(outn))
+        if rc:
+            raise RuntimeError("oracle: " + err())
+        proof = np.ctypeslib.as_array(outp, shape=(outn.value,)).copy()
+        lib().zko_free(outp)
+        return proof, st
+
+    def verify_shard(self, proof, challenger=None):
+        p = _a(proof)
+        st = _a(challenger) if challenger is not None else self.initial_challenger()
+        rc = lib().zko_verify_shard(C.c_void_p(self.h), C.c_void_p(self.pk), _p(p), C.c_size_t(p.size), _p(st))
+        return (rc == 0), (err() if rc else "")
+
+    def permutation_trace(self, chip, prep, main, alpha, beta):
+        main = _a(main)
+        info = self.chip_info(chip)
+        out = np.zeros((main.shape[0], 4 * info["perm_width_ef"]), np.uint32)
+        ls = np.zeros(4, np.uint32)
+        pp = _a(prep) if prep is not None else None
+        a, b = _a(alpha), _a(beta)
+        rc = lib().zko_permutation_trace(C.c_void_p(self.h), chip.encode(), _p(pp) if pp is not None else None, _p(main),
+                                         C.c_size_t(main.shape[0]), _p(a), _p(b), _p(out), _p(ls))
+        if rc:
+            raise RuntimeError("oracle: " + err())
+        return out, ls
+
+    def quotient_values(self, chip, log_n, prep_lde, main_lde, perm_lde, perm_alpha, perm_beta, local_sum, global_sum,
+                        alpha, pub):
+        info = self.chip_info(chip)
+        q = 1 << (log_n + info["log_quotient_degree"])
+        out = np.zeros((q, 4), np.uint32)
+        pl = _a(prep_lde) if prep_lde is not None else None
+        ml, el = _a(main_lde), _a(perm_lde)
+        args = [_a(x) for x in (perm_alpha, perm_beta, local_sum, global_sum, alpha, pub)]
+        rc = lib().zko_quotient_values(C.c_void_p(self.h), chip.encode(), C.c_uint(log_n), _p(pl) if pl is not None else None,
+                                       _p(ml), _p(el), *[_p(x) for x in args[:5]], _p(args[5]), C.c_size_t(args[5].size), _p(out))
+        if rc:
+            raise RuntimeError("oracle: " + err())
+        return out

@@ -1,0 +1,37 @@
+"""KoalaBear helpers for host-side test/bench data (numpy, uint64 intermediates).
+
+p = 2^31 - 2^24 + 1.  In-memory form at the C ABI is Montgomery with R = 2^32, the representation
+of `KoalaBear` inside the reference's `RowMajorMatrix<Val>` (the in-tree C++ reinterpret-casts
+it to `kb31_t`, crates/core/machine/cpp/extern.cpp:12; constants kb31_t.hpp:27-34).
+"""
+import numpy as np
+
+P = 0x7F000001
+R_MOD_P = (1 << 32) % P          # 0x1fffffe
+R_INV = pow(R_MOD_P, P - 2, P)
+
+
+def to_monty(x) -> np.ndarray:
+    x = np.asarray(x, dtype=np.uint64)
+    return ((x << np.uint64(32)) % np.uint64(P)).astype(np.uint32)
+
+
+def from_monty(x) -> np.ndarray:
+    x = np.asarray(x, dtype=np.uint64)
+    return ((x * np.uint64(R_INV)) % np.uint64(P)).astype(np.uint32)
+
+
+def mul(a, b) -> np.ndarray:
+    return ((np.asarray(a, dtype=np.uint64) * np.asarray(b, dtype=np.uint64)) % np.uint64(P)).astype(np.uint32)
+
+
+def add(a, b) -> np.ndarray:
+    return ((np.asarray(a, dtype=np.uint64) + np.asarray(b, dtype=np.uint64)) % np.uint64(P)).astype(np.uint32)
+
+
+def sub(a, b) -> np.ndarray:
+    return ((np.asarray(a, dtype=np.uint64) + np.uint64(P) - np.asarray(b, dtype=np.uint64)) % np.uint64(P)).astype(np.uint32)
+
+
+def random_elements(rng: np.random.Generator, shape) -> np.ndarray:
+    return rng.integers(0, P, size=shape, dtype=np.uint32)

@@ -1,0 +1,249 @@
+"""Synthetic machines and shard traces with the reference's shapes.
+
+No guest ELF can be built in this environment (no MIPS/Rust toolchain), so benchmark and test
+shards are synthetic: satisfiable AIRs whose table names, heights and per-row column budgets
+follow the reference (crates/core/executor/src/artifacts/mips_costs.json — cost = P + M + 4E + 4Q
+per crates/stark/src/chip.rs:154-163 — and crates/core/machine/src/shape/maximal_shapes.json),
+filled from a seeded RNG.  Structure mirrors the real machine: a preprocessed byte/range table
+and a preprocessed program table that receive lookups from the execution tables, one
+global-scope table whose last 14 columns carry the septic digest, public values.
+
+Small real AIR: Fibonacci with public values, crates/stark/src/stark_testing.rs:25-61.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import field as kb
+from .air import (KIND_BYTE, KIND_GLOBAL, KIND_MEMORY, KIND_PROGRAM, SCOPE_GLOBAL, Chip, Machine)
+
+P = kb.P
+RANGE_BITS = 16  # the reference's Byte table has 2^16 rows
+
+
+@dataclass
+class WideSpec:
+    """A 'wide' execution table: `groups` column groups (a,b,c,d,e,r) with a*b=c, c*d=e,
+    the first `lookups` groups send r to the byte table, `extra` unconstrained columns.
+    `counter`: group 0's `a` starts at public value 0 and increments (transition constraint) and
+    is looked up in the program table.  `global_scope`: 14 trailing digest columns."""
+    name: str
+    log_height: int
+    groups: int
+    lookups: int
+    extra: int = 0
+    counter: bool = False
+    global_scope: bool = False
+
+    @property
+    def width(self) -> int:
+        return 6 * self.groups + self.extra + (14 if self.global_scope else 0)
+
+
+def _wide_chip(s: WideSpec) -> Chip:
+    def ev(b):
+        for g in range(s.groups):
+            a, bb, c, d, e, r = (b.main(6 * g + k) for k in range(6))
+            b.assert_zero(a * bb - c)
+            b.assert_zero(c * d - e)
+            if g < s.lookups:
+                b.send(KIND_BYTE, [r], 1)
+        if s.counter:
+            a0 = b.main(0)
+            b.when_first_row().assert_eq(a0, b.pub(0))
+            b.when_transition().assert_eq(b.main(0, next=True), a0 + 1)
+            b.send(KIND_PROGRAM, [a0], 1)
+        if s.global_scope:
+            b.send(KIND_GLOBAL, [b.main(1)], 1, scope=SCOPE_GLOBAL)
+    return Chip(s.name, 0, s.width, ev, global_scope=s.global_scope)
+
+
+def _wide_trace(s: WideSpec, rng: np.random.Generator, pv0: int) -> np.ndarray:
+    n = 1 << s.log_height
+    t = np.empty((n, s.width), dtype=np.uint32)
+    for g in range(s.groups):
+        a = kb.random_elements(rng, n)
+        if g == 0 and s.counter:
+            a = ((np.arange(n, dtype=np.uint64) + np.uint64(pv0)) % np.uint64(P)).astype(np.uint32)
+        bb, d = kb.random_elements(rng, n), kb.random_elements(rng, n)
+        c = kb.mul(a, bb)
+        t[:, 6 * g + 0], t[:, 6 * g + 1], t[:, 6 * g + 2] = a, bb, c
+        t[:, 6 * g + 3], t[:, 6 * g + 4] = d, kb.mul(c, d)
+        t[:, 6 * g + 5] = rng.integers(0, 1 << RANGE_BITS, size=n, dtype=np.uint32)
+    rest = s.width - 6 * s.groups
+    if rest:
+        t[:, 6 * s.groups:] = kb.random_elements(rng, (n, rest))
+    return t
+
+
+def _byte_chip() -> Chip:
+    def ev(b):
+        b.receive(KIND_BYTE, [b.prep(0)], b.main(0))
+    return Chip("Byte", 1, 1, ev, local_only=True)
+
+
+def _program_chip() -> Chip:
+    def ev(b):
+        b.receive(KIND_PROGRAM, [b.prep(0)], b.main(0))
+    return Chip("Program", 2, 1, ev, local_only=True)
+
+
+def _fib_chip() -> Chip:
+    # stark_testing.rs:35-61, public values at offsets 1..3, plus a send of every row
+    def ev(b):
+        left, right = b.main(0), b.main(1)
+        nl, nr = b.main(0, next=True), b.main(1, next=True)
+        b.when_first_row().assert_eq(left, b.pub(1))
+        b.when_first_row().assert_eq(right, b.pub(2))
+        b.when_transition().assert_eq(right, nl)
+        b.when_transition().assert_eq(left + right, nr)
+        b.when_last_row().assert_eq(right, b.pub(3))
+        b.send(KIND_MEMORY, [left, right], 1)
+    return Chip("Fibonacci", 0, 2, ev)
+
+
+def _sink_chip() -> Chip:
+    def ev(b):
+        b.receive(KIND_MEMORY, [b.main(0), b.main(1)], b.main(2))
+    return Chip("Sink", 0, 3, ev, local_only=True)
+
+
+class ShardCase:
+    """A machine plus one satisfiable shard: preprocessed traces, main traces, public values.
+    Traces are row-major uint32 arrays in CANONICAL form; use `.monty()` for the C ABI."""
+
+    def __init__(self, machine: Machine, prep: dict, traces: dict, public_values: np.ndarray, cycles: int):
+        self.machine, self.prep, self.traces = machine, prep, traces
+        self.public_values, self.cycles = public_values, cycles
+
+    @property
+    def cells(self) -> int:
+        tot = 0
+        for name, t in self.traces.items():
+            tot += t.shape[0] * self.machine.chip(name).cost
+        return tot
+
+    @property
+    def trace_bytes(self) -> int:
+        return sum(4 * t.size for t in self.traces.values())
+
+
+def build_case(wides: list[WideSpec], *, with_fib: int | None = None, seed: int = 0xC0FFEE,
+               num_queries: int = 84, pow_bits: int = 16, cycles: int | None = None) -> ShardCase:
+    """Assemble a machine from wide tables (+ optional Fibonacci/Sink pair of log height
+    `with_fib`) and generate one balanced shard."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pv = np.zeros(8, dtype=np.uint32)
+    chips, traces, prep = [], {}, {}
+    counter_specs = [w for w in wides if w.counter]
+    assert len(counter_specs) <= 1
+    byte_counts = np.zeros(1 << RANGE_BITS, dtype=np.uint64)
+    for w in wides:
+        chips.append(_wide_chip(w))
+        t = _wide_trace(w, rng, int(pv[0]))
+        if w.global_scope:
+            t[-1, -14:] = kb.random_elements(rng, 14)
+        traces[w.name] = t
+        for g in range(w.lookups):
+            byte_counts += np.bincount(t[:, 6 * g + 5], minlength=1 << RANGE_BITS).astype(np.uint64)
+    chips.append(_byte_chip())
+    prep["Byte"] = np.arange(1 << RANGE_BITS, dtype=np.uint32).reshape(-1, 1)
+    traces["Byte"] = (byte_counts % np.uint64(P)).astype(np.uint32).reshape(-1, 1)
+    if counter_specs:
+        n = 1 << counter_specs[0].log_height
+        chips.append(_program_chip())
+        pt = np.empty((n, 2), dtype=np.uint32)
+        pt[:, 0] = np.arange(n, dtype=np.uint32)
+        pt[:, 1] = kb.random_elements(rng, n)
+        prep["Program"] = pt
+        traces["Program"] = np.ones((n, 1), dtype=np.uint32)
+    if with_fib is not None:
+        n = 1 << with_fib
+        a, b_ = 0, 1
+        rows = np.empty((n, 2), dtype=np.uint32)
+        for i in range(n):
+            rows[i] = (a, b_)
+            a, b_ = b_, (a + b_) % P
+        pv[1], pv[2], pv[3] = 0, 1, rows[-1, 1]
+        chips.append(_fib_chip())
+        traces["Fibonacci"] = rows
+        chips.append(_sink_chip())
+        sink = np.zeros((2 * n, 3), dtype=np.uint32)
+        perm = rng.permutation(n)
+        sink[:n, :2] = rows[perm]
+        sink[:n, 2] = 1
+        traces["Sink"] = sink
+    machine = Machine(chips, num_pv_elts=4, num_queries=num_queries, pow_bits=pow_bits)
+    if cycles is None:
+        cycles = (1 << counter_specs[0].log_height) if counter_specs else 0
+    return ShardCase(machine, prep, traces, pv, cycles)
+
+
+def tune_wide(name: str, log_height: int, cost: int, lookups: int, **kw) -> WideSpec:
+    """Pick (groups, extra) so that the table's per-row cost P+M+4E+4Q matches `cost`
+    (mips_costs.json) for the given number of byte lookups."""
+    n_lk = lookups + (1 if kw.get("counter") else 0)
+    e = -(-n_lk // 2) + 1
+    m = cost - 4 * e - 8 - (14 if kw.get("global_scope") else 0)
+    groups = max(lookups, m // 6, 1)
+    extra = max(0, m - 6 * groups)
+    return WideSpec(name, log_height, groups, lookups, extra, **kw)
+
+
+# -- named workloads ---------------------------------------------------------------------------
+def mini_case(seed: int = 1, **kw) -> ShardCase:
+    """Tiny machine covering every structural feature (used by parity tests)."""
+    wides = [WideSpec("Cpu", 6, 3, 3, 2, counter=True), WideSpec("AddSub", 5, 2, 1, 0),
+             WideSpec("Global", 4, 1, 1, 1, global_scope=True)]
+    kw.setdefault("num_queries", 8)
+    kw.setdefault("pow_bits", 4)
+    return build_case(wides, with_fib=4, seed=seed, **kw)
+
+
+def fibonacci_core_case(log_cpu: int = 16, seed: int = 0xC0FFEE, **kw) -> ShardCase:
+    """S1 'fib-2^16' (SURVEY.md §8d): a single small core shard."""
+    h = log_cpu
+    wides = [tune_wide("Cpu", h, 119, 10, counter=True), tune_wide("AddSub", h - 1, 47, 4),
+             tune_wide("Lt", h - 2, 52, 4), tune_wide("Branch", h - 3, 90, 6),
+             tune_wide("MemoryInstrs", h - 4, 115, 8), tune_wide("Global", h - 4, 115, 6, global_scope=True),
+             tune_wide("MemoryLocal", h - 6, 100, 6)]
+    return build_case(wides, seed=seed, **kw)
+
+
+# maximal_shapes.json["21"][1]
+_CORE21 = {"Cpu": 21, "AddSub": 20, "MemoryInstrs": 19, "Bitwise": 19, "Lt": 18, "ShiftRight": 18, "Global": 18,
+           "Branch": 17, "ShiftLeft": 16, "MemoryLocal": 15, "MovCond": 15, "Jump": 15, "Mul": 13,
+           "SyscallInstrs": 12, "SyscallCore": 12, "MiscInstrs": 8, "CloClz": 8, "DivRem": 4}
+_COSTS = {"Cpu": 119, "AddSub": 47, "MemoryInstrs": 115, "Bitwise": 42, "Lt": 52, "ShiftRight": 131, "Global": 115,
+          "Branch": 90, "ShiftLeft": 68, "MemoryLocal": 100, "MovCond": 48, "Jump": 82, "Mul": 110,
+          "SyscallInstrs": 97, "SyscallCore": 39, "MiscInstrs": 152, "CloClz": 41, "DivRem": 162,
+          "KeccakSponge": 4259}
+_LOOKUPS = {"Cpu": 10, "AddSub": 4, "MemoryInstrs": 8, "Bitwise": 4, "Lt": 4, "ShiftRight": 8, "Global": 6,
+            "Branch": 6, "ShiftLeft": 6, "MemoryLocal": 6, "MovCond": 4, "Jump": 6, "Mul": 8, "SyscallInstrs": 6,
+            "SyscallCore": 3, "MiscInstrs": 8, "CloClz": 3, "DivRem": 10, "KeccakSponge": 40}
+
+
+def core_case(log_cpu: int = 21, seed: int = 0xC0FFEE, **kw) -> ShardCase:
+    """S3 'core-2^21' tendermint-like maximal shard, scaled by log_cpu (heights shift together)."""
+    d = 21 - log_cpu
+    wides = []
+    for name, lh in _CORE21.items():
+        lh = max(4, lh - d)
+        wides.append(tune_wide(name, lh, _COSTS[name], _LOOKUPS[name], counter=(name == "Cpu"),
+                               global_scope=(name == "Global")))
+    return build_case(wides, seed=seed, **kw)
+
+
+def keccak_case(log_cpu: int = 20, log_keccak: int | None = None, seed: int = 0xC0FFEE, **kw) -> ShardCase:
+    """S2 'keccak-2^20': a core shard whose area is dominated by the KeccakSponge precompile table
+    (4259 columns per row).  Default keccak height = cpu height - 2."""
+    lk = log_cpu - 2 if log_keccak is None else log_keccak
+    h = log_cpu
+    wides = [tune_wide("Cpu", h, 119, 10, counter=True), tune_wide("AddSub", h - 1, 47, 4),
+             tune_wide("MemoryInstrs", h - 2, 115, 8), tune_wide("Bitwise", h - 2, 42, 4),
+             tune_wide("Global", h - 3, 115, 6, global_scope=True), tune_wide("MemoryLocal", h - 5, 100, 6),
+             tune_wide("SyscallInstrs", h - 8, 97, 6), tune_wide("SyscallCore", h - 8, 39, 3),
+             tune_wide("KeccakSponge", lk, 4259, 40)]
+    return build_case(wides, seed=seed, **kw)
