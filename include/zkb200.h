@@ -1,0 +1,146 @@
+/* zkb200 — C ABI of the B200 STARK shard prover (libzkb200.so).
+ *
+ * Drop-in boundary for ONE path of ProjectZKM/Ziren: `MachineProver::{setup, commit, open}` for
+ * `SC = KoalaBearPoseidon2` (trait: crates/stark/src/prover.rs:30-184; CPU implementation it
+ * replaces: crates/stark/src/prover.rs:202-694; selected through ZKMProverComponents,
+ * crates/prover/src/components.rs:6-35).  Host Rust keeps MIPS execution, trace generation and
+ * shard scheduling and calls through this header; INTEGRATION.md shows the `extern "C"` block and
+ * the `impl MachineProver for B200Prover` shim.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success, non-zero on error, and
+ *     `zkb200_last_error(ctx)` describes the failure (MachineProver::Error).
+ *   - TRACE MATRICES are row-major `height x width` arrays of uint32 in MONTGOMERY form
+ *     (R = 2^32, p = 2^31 - 2^24 + 1): the in-memory layout of `RowMajorMatrix<KoalaBear>`, so the
+ *     Rust side passes `trace.values.as_ptr()` without conversion.  Pointers may be host
+ *     (pageable or pinned) or device memory; the library detects which.
+ *   - everything SMALL crosses in CANONICAL form (residues 0..p-1): commitments, public values,
+ *     challenger state, pc_start, cumulative sums and the proof ("ZKPF").
+ *   - a context is bound to one GPU; calls on one context are serialised internally, so commit/open
+ *     may be invoked from several host threads (prove.rs:487-521 does).
+ *
+ * Machine descriptor "ZKMD" (uint32 words) — chips as data, the export of a SymbolicAirBuilder
+ * walk (crates/stark/src/machine.rs:377-389) plus each chip's sends/receives
+ * (crates/stark/src/lookup/lookup.rs:10-19):
+ *   0x444d4b5a, 1, n_chips, num_pv_elts, log_blowup, num_queries, pow_bits, then per chip:
+ *     name_len, name bytes (LE packed, padded to words),
+ *     prep_width, main_width, log_quotient_degree, local_only, commit_scope_is_global,
+ *     n_sends, n_receives, n_nodes, n_constraints,
+ *     lookups (sends then receives): kind, scope (0 local / 1 global), n_values,
+ *         multiplicity VPC, n_values x VPC;  VPC = constant, n_terms, n_terms x (is_main, column, weight)
+ *     nodes: n_nodes x (op, a, b), topologically ordered, ops:
+ *         0 CONST(a)  1 MAIN(col a, row offset b)  2 PREP(col a, row offset b)  3 PUBLIC(a)
+ *         4 IS_FIRST_ROW  5 IS_LAST_ROW  6 IS_TRANSITION  7 ADD  8 SUB  9 MUL  10 NEG
+ *     constraints: n_constraints x node id, in `assert_zero` order.
+ *   The LogUp constraints (crates/stark/src/permutation.rs:205-347) are derived from the lookups.
+ *
+ * Proof encoding "ZKPF" (uint32 words, canonical) — the fields of ShardProof
+ * (crates/stark/src/types.rs:76-83) and of Plonky3's FriProof:
+ *   0x46504b5a, 1, main_commit[8], permutation_commit[8], quotient_commit[8],
+ *   n_chips, per chip in shard order (height desc, name asc = chip_ordering):
+ *       name, log_degree, prep_w, main_w, perm_w (= 4E), n_quotient_chunks,
+ *       preprocessed local[prep_w] next[prep_w], main local/next, permutation local/next  (EF = 4 words),
+ *       quotient[n_chunks][4] EF, global_cumulative_sum[14], local_cumulative_sum EF
+ *   n_public_values, public_values[]
+ *   n_commit_phase_commits, commits[8] each, final_poly EF, pow_witness, n_queries, per query:
+ *       n_rounds, per round: n_matrices, per matrix: width, opened row[width]; path_len, path[8] each
+ *       n_layers, per layer: sibling_value EF, path_len, path[8] each
+ *   pow_witness is the SMALLEST valid witness (the reference takes any: rayon find_any).
+ *
+ * Challenger image (34 words, canonical): sponge_state[16], n_inputs, input_buffer[8],
+ *   n_outputs, output_buffer[8] — the fields of DuplexChallenger<Val, Perm, 16, 8>.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zkb200_ctx zkb200_ctx;     /* MachineProver instance on one GPU */
+typedef struct zkb200_pk zkb200_pk;       /* MachineProver::DeviceProvingKey */
+typedef struct zkb200_shard zkb200_shard; /* ShardMainData<SC, DeviceMatrix, DeviceProverData> */
+
+typedef struct {
+  const char* name;      /* chip name (MachineAir::name) */
+  const uint32_t* data;  /* row-major height x width, Montgomery; host or device pointer */
+  size_t height;         /* power of two */
+  size_t width;
+} zkb200_trace;
+
+/* MachineProver::new(machine) — crates/stark/src/prover.rs:43.  `desc` is a ZKMD descriptor. */
+int zkb200_ctx_create(int device, const uint32_t* desc, size_t n_words, zkb200_ctx** out);
+void zkb200_ctx_destroy(zkb200_ctx* ctx);
+/* error text of the last failed call on this context (or of ctx_create when ctx is NULL) */
+const char* zkb200_last_error(zkb200_ctx* ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is issued on */
+void* zkb200_ctx_stream(zkb200_ctx* ctx);
+
+/* MachineProver::setup + pk_to_device — prover.rs:49-63, machine.rs:352-459: commit the
+ * preprocessed traces, keep traces + LDEs + tree on the device.  init_global_sum: 14 words. */
+int zkb200_setup(zkb200_ctx* ctx, const zkb200_trace* prep, int n, uint32_t pc_start,
+                 const uint32_t* init_global_sum, uint32_t commit_out[8], zkb200_pk** out);
+void zkb200_pk_free(zkb200_pk* pk);
+/* MachineProvingKey::observe_into on a fresh challenger — prover.rs:714-721 */
+int zkb200_pk_initial_challenger(const zkb200_pk* pk, uint32_t challenger[34]);
+
+/* MachineProver::commit — prover.rs:258-292: sort by (height desc, name), LDE + Merkle. */
+int zkb200_commit(zkb200_ctx* ctx, const zkb200_trace* traces, int n, const uint32_t* public_values,
+                  size_t n_public_values, uint32_t commit_out[8], zkb200_shard** out);
+void zkb200_shard_free(zkb200_shard* shard);
+
+/* MachineProver::open — prover.rs:298-653.  `challenger` (in/out) is the per-shard clone of the
+ * post-observe_into challenger.  The proof buffer is malloc'ed; release with zkb200_free. */
+int zkb200_open(zkb200_ctx* ctx, const zkb200_pk* pk, zkb200_shard* shard, uint32_t challenger[34],
+                uint32_t** proof_words, size_t* n_words);
+/* commit + open of one record (the body of MachineProver::prove's loop, prover.rs:681-688) */
+int zkb200_prove_shard(zkb200_ctx* ctx, const zkb200_pk* pk, const zkb200_trace* traces, int n,
+                       const uint32_t* public_values, size_t n_public_values, uint32_t challenger[34],
+                       uint32_t** proof_words, size_t* n_words);
+void zkb200_free(void* p);
+
+/* per-stage device times (ms) of the last zkb200_open when profiling is on; returns the number of
+ * stages; names/ms may be NULL to query the count */
+void zkb200_set_profile(zkb200_ctx* ctx, int on);
+int zkb200_last_stage_times(zkb200_ctx* ctx, const char** names, float* ms, int cap);
+
+/* ---- kernel-level entry points (tests, micro-benchmarks, ncu captures) -------------------------
+ * All matrices here are DEVICE pointers, COLUMN-MAJOR (column c at data + c*height), Montgomery. */
+/* K1: out (n<<log_blowup) x width = evaluations on shift*K, rows bit-reversed */
+int zkb200_coset_lde(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, size_t width,
+                     unsigned log_blowup, uint32_t shift_canonical);
+/* K1: plain DFT, natural order in; bitrev_out selects the output row order */
+int zkb200_ntt(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, size_t width, int inverse,
+               int bitrev_out);
+/* K2: MMCS root (canonical) over matrices as given */
+int zkb200_mmcs_root(zkb200_ctx* ctx, const uint32_t* const* mats, const unsigned* log_heights, const size_t* widths,
+                     int n, uint32_t root_out[8]);
+/* K2: n Poseidon2 permutations in place, states row-major n x 16 */
+int zkb200_poseidon2_permute_batch(zkb200_ctx* ctx, uint32_t* states, size_t n);
+/* K5: LogUp permutation trace of one chip; out n x 4E column-major, local_sum canonical[4] */
+int zkb200_permutation_trace(zkb200_ctx* ctx, const char* chip, const uint32_t* prep, const uint32_t* main_trace,
+                             size_t height, const uint32_t alpha[4], const uint32_t beta[4], uint32_t* out,
+                             uint32_t local_sum_out[4]);
+/* K3: quotient chunks of one chip from committed LDEs; challenges/sums canonical; pub on host.
+ * out: 2^lqd chunk matrices, each n x 4 column-major */
+int zkb200_quotient(zkb200_ctx* ctx, const char* chip, unsigned log_n, const uint32_t* prep_lde,
+                    const uint32_t* main_lde, const uint32_t* perm_lde, const uint32_t perm_alpha[4],
+                    const uint32_t perm_beta[4], const uint32_t local_sum[4], const uint32_t global_sum[14],
+                    const uint32_t alpha[4], const uint32_t* public_values, size_t n_public_values, uint32_t* out);
+/* K4c: one FRI fold of m EF values (component-major [4][m]); ro_next may be NULL */
+int zkb200_fri_fold(zkb200_ctx* ctx, const uint32_t* in, size_t m, const uint32_t beta[4], const uint32_t* ro_next,
+                    uint32_t* out);
+/* K4d: smallest proof-of-work witness for a challenger image */
+int zkb200_grind(zkb200_ctx* ctx, const uint32_t challenger[34], unsigned bits, uint32_t* witness_out);
+/* layout helpers on the context stream: row-major <-> column-major, canonical <-> Montgomery */
+int zkb200_transpose(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t height, size_t width, int to_colmajor);
+int zkb200_convert(zkb200_ctx* ctx, uint32_t* data, size_t n, int to_montgomery);
+int zkb200_sync(zkb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

@@ -1,0 +1,239 @@
+// extern "C" surface of libzkb200.so — see include/zkb200.h for the contract.
+#include "../../include/zkb200.h"
+#include <cstdlib>
+#include "layout.h"
+#include "logup.h"
+#include "open.h"
+#include "prover.h"
+#include "quotient.h"
+
+using namespace zkb;
+
+struct zkb200_ctx { Ctx c; };
+struct zkb200_pk { Pk* p; };
+struct zkb200_shard { Shard* s; };
+
+static thread_local std::string g_create_err;
+
+template <class F>
+static int guarded(zkb200_ctx* ctx, F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    if (ctx) ctx->c.err = e.what(); else g_create_err = e.what();
+    cudaGetLastError();
+    return 1;
+  }
+}
+
+static std::vector<TraceIn> to_traces(const zkb200_trace* t, int n) {
+  std::vector<TraceIn> v;
+  for (int i = 0; i < n; i++) v.push_back(TraceIn{t[i].name, t[i].data, t[i].height, t[i].width});
+  return v;
+}
+static Ef ef_from_canon(const uint32_t* w) { Ef e; for (int i = 0; i < 4; i++) e.c[i] = fp_from_canonical(w[i]); return e; }
+
+extern "C" {
+
+int zkb200_ctx_create(int device, const uint32_t* desc, size_t n_words, zkb200_ctx** out) {
+  *out = nullptr;
+  zkb200_ctx* ctx = new zkb200_ctx();
+  int rc = guarded(nullptr, [&] { ctx->c.init(device, desc, n_words); });
+  if (rc) { delete ctx; return rc; }
+  *out = ctx;
+  return 0;
+}
+void zkb200_ctx_destroy(zkb200_ctx* ctx) {
+  if (!ctx) return;
+  ctx->c.destroy();
+  delete ctx;
+}
+const char* zkb200_last_error(zkb200_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
+void* zkb200_ctx_stream(zkb200_ctx* ctx) { return (void*)ctx->c.stream; }
+
+int zkb200_setup(zkb200_ctx* ctx, const zkb200_trace* prep, int n, uint32_t pc_start, const uint32_t* init_global_sum,
+                 uint32_t commit_out[8], zkb200_pk** out) {
+  return guarded(ctx, [&] {
+    Pk* pk = prover_setup(ctx->c, to_traces(prep, n), pc_start, init_global_sum);
+    if (commit_out) memcpy(commit_out, pk->commit_canon, 32);
+    *out = new zkb200_pk{pk};
+  });
+}
+void zkb200_pk_free(zkb200_pk* pk) {
+  if (!pk) return;
+  if (pk->p) { cudaSetDevice(pk->p->ctx->device); delete pk->p; }
+  delete pk;
+}
+int zkb200_pk_initial_challenger(const zkb200_pk* pk, uint32_t challenger[34]) {
+  Challenger ch;
+  for (int i = 0; i < 8; i++) ch.observe_canonical(pk->p->commit_canon[i]);
+  ch.observe_canonical(pk->p->pc_start);
+  for (int i = 0; i < 14; i++) ch.observe_canonical(pk->p->init_global_sum[i]);
+  ch.observe(fp_zero());
+  ch.store(challenger);
+  return 0;
+}
+
+int zkb200_commit(zkb200_ctx* ctx, const zkb200_trace* traces, int n, const uint32_t* pv, size_t npv, uint32_t commit_out[8],
+                  zkb200_shard** out) {
+  return guarded(ctx, [&] {
+    Shard* s = prover_commit(ctx->c, to_traces(traces, n), pv, npv);
+    if (commit_out) for (int i = 0; i < 8; i++) commit_out[i] = fp_to_canonical(fp_raw(s->main.root[i]));
+    *out = new zkb200_shard{s};
+  });
+}
+void zkb200_shard_free(zkb200_shard* sh) {
+  if (!sh) return;
+  if (sh->s) { cudaSetDevice(sh->s->ctx->device); delete sh->s; }
+  delete sh;
+}
+
+int zkb200_open(zkb200_ctx* ctx, const zkb200_pk* pk, zkb200_shard* shard, uint32_t challenger[34], uint32_t** proof_words,
+                size_t* n_words) {
+  return guarded(ctx, [&] {
+    std::vector<u32> w = prover_open(ctx->c, *pk->p, *shard->s, challenger);
+    *proof_words = (uint32_t*)malloc(w.size() * 4);
+    memcpy(*proof_words, w.data(), w.size() * 4);
+    *n_words = w.size();
+  });
+}
+int zkb200_prove_shard(zkb200_ctx* ctx, const zkb200_pk* pk, const zkb200_trace* traces, int n, const uint32_t* pv, size_t npv,
+                       uint32_t challenger[34], uint32_t** proof_words, size_t* n_words) {
+  zkb200_shard* sh = nullptr;
+  int rc = zkb200_commit(ctx, traces, n, pv, npv, nullptr, &sh);
+  if (rc) return rc;
+  rc = zkb200_open(ctx, pk, sh, challenger, proof_words, n_words);
+  zkb200_shard_free(sh);
+  return rc;
+}
+void zkb200_free(void* p) { free(p); }
+
+void zkb200_set_profile(zkb200_ctx* ctx, int on) { ctx->c.profile = on != 0; }
+int zkb200_last_stage_times(zkb200_ctx* ctx, const char** names, float* ms, int cap) {
+  int n = (int)ctx->c.stage_ms.size();
+  for (int i = 0; i < n && i < cap; i++) {
+    if (names) names[i] = ctx->c.stage_ms[i].first.c_str();
+    if (ms) ms[i] = ctx->c.stage_ms[i].second;
+  }
+  return n;
+}
+
+// ---- kernel-level entry points ----------------------------------------------------------------
+int zkb200_coset_lde(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, size_t width, unsigned log_blowup,
+                     uint32_t shift) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    if (log_n + log_blowup > 24) throw std::runtime_error("zkb200: LDE height exceeds 2^24");
+    size_t n = (size_t)1 << log_n;
+    coset_lde_batch(ctx->c.tables, in, n, out, n << log_blowup, log_n, width, log_blowup, fp_from_canonical(shift), ctx->c.stream);
+  });
+}
+int zkb200_ntt(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, size_t width, int inverse, int bitrev_out) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    if (log_n > 24) throw std::runtime_error("zkb200: NTT size exceeds 2^24");
+    ntt_batch(ctx->c.tables, in, out, log_n, width, inverse != 0, bitrev_out != 0, ctx->c.stream);
+  });
+}
+int zkb200_mmcs_root(zkb200_ctx* ctx, const uint32_t* const* mats, const unsigned* log_heights, const size_t* widths, int n,
+                     uint32_t root_out[8]) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    ctx->c.arena.reset();
+    std::vector<MatRef> refs;
+    for (int i = 0; i < n; i++) refs.push_back(MatRef{mats[i], (u32)widths[i], log_heights[i]});
+    DigestLayers layers;
+    merkle_build(refs, ctx->c.arena, layers, ctx->c.d_small, ctx->c.stream);
+    ZKB_CUDA(cudaMemcpyAsync(ctx->c.h_small, ctx->c.d_small, 32, cudaMemcpyDeviceToHost, ctx->c.stream));
+    ZKB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    for (int i = 0; i < 8; i++) root_out[i] = fp_to_canonical(fp_raw(ctx->c.h_small[i]));
+  });
+}
+int zkb200_poseidon2_permute_batch(zkb200_ctx* ctx, uint32_t* states, size_t n) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    permute_batch(states, n, ctx->c.stream);
+  });
+}
+int zkb200_permutation_trace(zkb200_ctx* ctx, const char* chip, const uint32_t* prep, const uint32_t* main_trace, size_t height,
+                             const uint32_t alpha[4], const uint32_t beta[4], uint32_t* out, uint32_t local_sum_out[4]) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    const ChipInfo* c = ctx->c.machine.find(chip);
+    if (!c) throw std::runtime_error(std::string("zkb200: unknown chip ") + chip);
+    permutation_trace(ctx->c.machine, *c, prep, main_trace, height, ef_from_canon(alpha), ef_from_canon(beta), out, ctx->c.d_small,
+                      ctx->c.stream);
+    ZKB_CUDA(cudaMemcpyAsync(ctx->c.h_small, ctx->c.d_small, 16, cudaMemcpyDeviceToHost, ctx->c.stream));
+    ZKB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    for (int i = 0; i < 4; i++) local_sum_out[i] = fp_to_canonical(fp_raw(ctx->c.h_small[i]));
+  });
+}
+int zkb200_quotient(zkb200_ctx* ctx, const char* chip, unsigned log_n, const uint32_t* prep_lde, const uint32_t* main_lde,
+                    const uint32_t* perm_lde, const uint32_t perm_alpha[4], const uint32_t perm_beta[4], const uint32_t local_sum[4],
+                    const uint32_t global_sum[14], const uint32_t alpha[4], const uint32_t* pv, size_t npv, uint32_t* out) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    ctx->c.arena.reset();
+    const ChipInfo* c = ctx->c.machine.find(chip);
+    if (!c) throw std::runtime_error(std::string("zkb200: unknown chip ") + chip);
+    std::vector<u32> pvm(npv ? npv : 1, 0);
+    for (size_t i = 0; i < npv; i++) pvm[i] = fp_from_canonical(pv[i]).v;
+    QuotientInputs in;
+    in.prep_lde = prep_lde; in.main_lde = main_lde; in.perm_lde = perm_lde;
+    in.lde_h = (size_t)1 << (log_n + ctx->c.machine.log_blowup);
+    in.log_n = log_n;
+    in.perm_alpha = ef_from_canon(perm_alpha); in.perm_beta = ef_from_canon(perm_beta);
+    in.local_sum = ef_from_canon(local_sum); in.alpha = ef_from_canon(alpha);
+    for (int i = 0; i < 14; i++) in.global_sum[i] = fp_from_canonical(global_sum[i]).v;
+    in.pub_dev = ctx->c.arena.push(pvm.data(), pvm.size());
+    quotient_values(ctx->c.machine, *c, ctx->c.tables, in, out, ctx->c.stream);
+    ZKB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  });
+}
+int zkb200_fri_fold(zkb200_ctx* ctx, const uint32_t* in, size_t m, const uint32_t beta[4], const uint32_t* ro_next, uint32_t* out) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    fri_fold(ctx->c.tables, in, m, ef_from_canon(beta), ro_next, out, ctx->c.stream);
+  });
+}
+int zkb200_grind(zkb200_ctx* ctx, const uint32_t challenger[34], unsigned bits, uint32_t* witness_out) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    Challenger ch;
+    ch.load(challenger);
+    u32 st[16];
+    for (int i = 0; i < 16; i++) st[i] = ch.state[i].v;
+    for (unsigned i = 0; i < ch.n_in; i++) st[i] = ch.in_buf[i].v;
+    *witness_out = grind_witness(st, ch.n_in, bits, ctx->c.d_small + 8192, ctx->c.stream);
+  });
+}
+int zkb200_transpose(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t height, size_t width, int to_colmajor) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    if (to_colmajor) transpose_to_colmajor(in, out, height, width, ctx->c.stream);
+    else transpose_to_rowmajor(in, out, height, width, ctx->c.stream);
+  });
+}
+int zkb200_convert(zkb200_ctx* ctx, uint32_t* data, size_t n, int to_montgomery) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    if (to_montgomery) to_monty_inplace(data, n, ctx->c.stream);
+    else from_monty_inplace(data, n, ctx->c.stream);
+  });
+}
+int zkb200_sync(zkb200_ctx* ctx) {
+  return guarded(ctx, [&] { ZKB_CUDA(cudaSetDevice(ctx->c.device)); ZKB_CUDA(cudaStreamSynchronize(ctx->c.stream)); });
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// Shared host-side plumbing of libzkb200: error handling, stream-ordered device memory,
+// a parameter arena for small host->device tables, and the column-major device matrix.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "kb31.cuh"
+
+namespace zkb {
+
+#define ZKB_CUDA(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " +    \
+                               __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")");        \
+  } while (0)
+
+#define ZKB_CHECK_LAUNCH() ZKB_CUDA(cudaGetLastError())
+
+// Device buffer on the context stream (cudaMallocAsync pool keeps freed blocks cached).
+struct DevBuf {
+  u32* p = nullptr;
+  size_t words = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf() {}
+  DevBuf(size_t n_words, cudaStream_t s) : words(n_words), stream(s) {
+    if (n_words) ZKB_CUDA(cudaMallocAsync((void**)&p, n_words * sizeof(u32), s));
+  }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), words(o.words), stream(o.stream) { o.p = nullptr; o.words = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; words = o.words; stream = o.stream; o.p = nullptr; o.words = 0; }
+    return *this;
+  }
+  void release() {
+    if (p) { cudaFreeAsync(p, stream); p = nullptr; }
+    words = 0;
+  }
+  ~DevBuf() { release(); }
+};
+
+// Column-major device matrix: element (r, c) at d[c * height + r].  Columns are the polynomials,
+// so NTTs run over contiguous memory and row-wise kernels (leaf hashing, constraint evaluation)
+// read with one thread per row fully coalesced.
+struct DevMat {
+  DevBuf buf;
+  size_t height = 0, width = 0;
+  u32* d() const { return buf.p; }
+  DevMat() {}
+  DevMat(size_t h, size_t w, cudaStream_t s) : buf(h * w, s), height(h), width(w) {}
+};
+
+// Bump arena for small tables handed to kernels (matrix lists, opening schedules...):
+// written into pinned host memory, copied in-stream, recycled when the owner knows the stream
+// has drained.
+struct ParamArena {
+  char* host = nullptr;
+  char* dev = nullptr;
+  size_t cap = 0, used = 0;
+  cudaStream_t stream = nullptr;
+  void init(size_t bytes, cudaStream_t s) {
+    cap = bytes; stream = s;
+    ZKB_CUDA(cudaMallocHost((void**)&host, bytes));
+    ZKB_CUDA(cudaMalloc((void**)&dev, bytes));
+  }
+  void destroy() {
+    if (host) cudaFreeHost(host);
+    if (dev) cudaFree(dev);
+    host = dev = nullptr;
+  }
+  void reset() { used = 0; }
+  template <class T>
+  T* push(const T* data, size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    if (used + bytes > cap) throw std::runtime_error("zkb200: parameter arena exhausted");
+    memcpy(host + used, data, n * sizeof(T));
+    ZKB_CUDA(cudaMemcpyAsync(dev + used, host + used, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+    T* r = (T*)(dev + used);
+    used += bytes;
+    return r;
+  }
+};
+
+static inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace zkb

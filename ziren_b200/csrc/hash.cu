@@ -1,0 +1,285 @@
+// K2: Poseidon2 sponge / compression kernels and the Merkle (MMCS) tree build.
+// One thread owns one row (leaf) or one tree node: the 16-word state lives in registers,
+// column-major matrices make every load of a warp one contiguous 128 B segment, digest layers
+// are stored word-major (SoA) so that the two children of a node are one 8-byte load.
+#include "hash.h"
+#include <algorithm>
+#include <map>
+
+namespace zkb {
+
+static const u32 P2_RC_CANON[30][16] = {
+#include "p2_rc.inc"
+};
+
+static P2Consts make_consts() {
+  P2Consts c;
+  auto m = [](u32 x) { return fp_from_canonical(x % KB_P).v; };
+  for (int r = 0; r < 4; r++)
+    for (int i = 0; i < 16; i++) { c.ext[r][i] = m(P2_RC_CANON[r][i]); c.ext[4 + r][i] = m(P2_RC_CANON[17 + r][i]); }
+  for (int r = 0; r < 13; r++) c.in[r] = m(P2_RC_CANON[4 + r][0]);
+  const u32 P = KB_P;
+  const u32 diag[16] = {P - 2, 1, 2, (P + 1) >> 1, 3, 4, (P - 1) >> 1, P - 3, P - 4, P - ((P - 1) >> 8),
+                        P - ((P - 1) >> 3), P - 127, (P - 1) >> 8, (P - 1) >> 3, (P - 1) >> 4, 127};
+  for (int i = 0; i < 16; i++) c.diag[i] = m(diag[i]);
+  return c;
+}
+const P2Consts& p2_host_consts() {
+  static const P2Consts c = make_consts();
+  return c;
+}
+
+__constant__ P2Consts d_p2;
+
+void p2_upload_constants() {
+  ZKB_CUDA(cudaMemcpyToSymbol(d_p2, &p2_host_consts(), sizeof(P2Consts)));
+}
+
+__device__ __forceinline__ void p2_permute_dev(Fp* s) { p2_permute_with(s, d_p2); }
+
+// ---- leaf hashing: PaddingFreeSponge over the concatenated rows of same-height matrices ----
+__device__ __forceinline__ void sponge_rows(const MatRef* __restrict__ mats, int nmats, size_t height, size_t r, Fp* st) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) st[i] = fp_zero();
+  int mi = 0;
+  u32 col = 0;
+  // skip empty matrices
+  while (mi < nmats && mats[mi].width == 0) mi++;
+  while (mi < nmats) {
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (mi < nmats) {
+        st[i] = fp_raw(mats[mi].ptr[(size_t)col * height + r]);
+        any = true;
+        col++;
+        while (mi < nmats && col >= mats[mi].width) { mi++; col = 0; }
+      }
+    }
+    if (any) p2_permute_dev(st);
+  }
+}
+
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const MatRef* __restrict__ mats, int nmats, size_t height,
+                                                        u32* __restrict__ out) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= height) return;
+  Fp st[16];
+  sponge_rows(mats, nmats, height, r, st);
+#pragma unroll
+  for (int j = 0; j < 8; j++) out[j * height + r] = st[j].v;
+}
+
+// next[i] = compress(prev[2i], prev[2i+1]); optionally then compress(., hash(rows i of `mats`))
+__global__ void __launch_bounds__(128) compress_kernel(const u32* __restrict__ prev, u32* __restrict__ next, size_t m,
+                                                       const MatRef* __restrict__ mats, int nmats) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  Fp st[16];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    uint2 pr = reinterpret_cast<const uint2*>(prev + j * 2 * m)[i];
+    st[j] = fp_raw(pr.x);
+    st[8 + j] = fp_raw(pr.y);
+  }
+  p2_permute_dev(st);
+  if (nmats > 0) {
+    Fp h[16];
+    sponge_rows(mats, nmats, m, i, h);
+#pragma unroll
+    for (int j = 0; j < 8; j++) st[8 + j] = h[j];
+    p2_permute_dev(st);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) next[j * m + i] = st[j].v;
+}
+
+// The top of a tree (<= 512 nodes wide, no injections) in one CTA: levels separated by
+// __syncthreads instead of kernel launches.  layers are consecutive SoA blocks in `buf`.
+__global__ void __launch_bounds__(256) compress_top_kernel(u32* buf, size_t off_first, size_t m_first, int nlevels) {
+  size_t off_prev = off_first, m = m_first;   // prev layer has 2m nodes
+  for (int l = 0; l < nlevels; l++) {
+    const u32* prev = buf + off_prev;
+    u32* next = buf + off_prev + 16 * m;
+    for (size_t i = threadIdx.x; i < m; i += blockDim.x) {
+      Fp st[16];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        st[j] = fp_raw(prev[j * 2 * m + 2 * i]);
+        st[8 + j] = fp_raw(prev[j * 2 * m + 2 * i + 1]);
+      }
+      p2_permute_dev(st);
+#pragma unroll
+      for (int j = 0; j < 8; j++) next[j * m + i] = st[j].v;
+    }
+    __syncthreads();
+    off_prev += 16 * m;
+    m >>= 1;
+  }
+}
+
+static void alloc_layers(DigestLayers& out, unsigned max_log, cudaStream_t s) {
+  out.offset.clear(); out.count.clear();
+  size_t total = 0;
+  for (unsigned l = 0; l <= max_log; l++) {
+    size_t cnt = (size_t)1 << (max_log - l);
+    out.offset.push_back(total);
+    out.count.push_back(cnt);
+    total += 8 * cnt;
+  }
+  out.buf = DevBuf(total, s);
+}
+
+// layers 1..max_log from the leaf layer; `groups` = matrices to inject, keyed by log height
+static void build_upper(DigestLayers& out, unsigned max_log, const std::map<unsigned, std::vector<MatRef>>& groups,
+                        std::map<unsigned, const MatRef*>& dev_groups, u32* root_dev, cudaStream_t s) {
+  unsigned l = 1;
+  while (l <= max_log) {
+    size_t m = out.count[l];
+    unsigned lh = max_log - l;
+    bool inject = groups.count(lh) != 0;
+    if (!inject && m <= 512) {
+      // run as many injection-free levels as possible inside one CTA
+      unsigned l2 = l;
+      while (l2 <= max_log && groups.count(max_log - l2) == 0) l2++;
+      compress_top_kernel<<<1, 256, 0, s>>>(out.buf.p, out.offset[l - 1], m, (int)(l2 - l));
+      ZKB_CHECK_LAUNCH();
+      l = l2;
+      continue;
+    }
+    compress_kernel<<<ceil_div(m, 128), 128, 0, s>>>(out.layer(l - 1), out.layer(l), m, inject ? dev_groups[lh] : nullptr,
+                                                     inject ? (int)groups.at(lh).size() : 0);
+    ZKB_CHECK_LAUNCH();
+    l++;
+  }
+  ZKB_CUDA(cudaMemcpyAsync(root_dev, out.layer(max_log), 8 * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+}
+
+void merkle_build(const std::vector<MatRef>& mats, ParamArena& arena, DigestLayers& out, u32* root_dev, cudaStream_t s) {
+  unsigned max_log = 0;
+  for (auto& m : mats) max_log = std::max(max_log, m.log_height);
+  // group by height, list order preserved
+  std::map<unsigned, std::vector<MatRef>> groups;
+  for (auto& m : mats) groups[m.log_height].push_back(m);
+  std::map<unsigned, const MatRef*> dev_groups;
+  for (auto& g : groups) dev_groups[g.first] = arena.push(g.second.data(), g.second.size());
+  alloc_layers(out, max_log, s);
+  size_t h = (size_t)1 << max_log;
+  leaf_hash_kernel<<<ceil_div(h, 128), 128, 0, s>>>(dev_groups[max_log], (int)groups[max_log].size(), h, out.layer(0));
+  ZKB_CHECK_LAUNCH();
+  std::map<unsigned, std::vector<MatRef>> inj = groups;
+  inj.erase(max_log);
+  build_upper(out, max_log, inj, dev_groups, root_dev, s);
+}
+
+// FRI commit-phase layer: leaves are the pairs (e_{2i}, e_{2i+1}) of the folded vector flattened
+// to 8 base elements (ExtensionMmcs over a width-2 EF matrix) -> exactly one permutation per leaf.
+__global__ void __launch_bounds__(128) fri_leaf_kernel(const u32* __restrict__ folded, size_t m, u32* __restrict__ out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t half = m >> 1;
+  if (i >= half) return;
+  Fp st[16];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    uint2 pr = reinterpret_cast<const uint2*>(folded + (size_t)c * m)[i];
+    st[c] = fp_raw(pr.x);
+    st[4 + c] = fp_raw(pr.y);
+  }
+#pragma unroll
+  for (int j = 8; j < 16; j++) st[j] = fp_zero();
+  p2_permute_dev(st);
+#pragma unroll
+  for (int j = 0; j < 8; j++) out[j * half + i] = st[j].v;
+}
+void fri_commit_layer(const u32* folded, size_t m, DigestLayers& out, u32* root_dev, cudaStream_t s) {
+  const size_t half = m >> 1;
+  unsigned max_log = log2_exact(half);
+  alloc_layers(out, max_log, s);
+  fri_leaf_kernel<<<ceil_div(half, 128), 128, 0, s>>>(folded, m, out.layer(0));
+  ZKB_CHECK_LAUNCH();
+  std::map<unsigned, std::vector<MatRef>> none;
+  std::map<unsigned, const MatRef*> none_dev;
+  build_upper(out, max_log, none, none_dev, root_dev, s);
+}
+
+__global__ void permute_batch_kernel(u32* states, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp st[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) st[j] = fp_raw(states[16 * i + j]);
+  p2_permute_dev(st);
+#pragma unroll
+  for (int j = 0; j < 16; j++) states[16 * i + j] = st[j].v;
+}
+void permute_batch(u32* states, size_t n, cudaStream_t s) {
+  if (!n) return;
+  permute_batch_kernel<<<ceil_div(n, 128), 128, 0, s>>>(states, n);
+  ZKB_CHECK_LAUNCH();
+}
+
+// ---- proof-of-work grinding ---------------------------------------------------------------------
+struct GrindArgs { u32 st[16]; };
+__global__ void grind_kernel(GrindArgs a, unsigned n_in, u32 mask, u32 base, u32* result) {
+  u32 w = base + blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= KB_P) return;
+  Fp st[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) st[j] = fp_raw(a.st[j]);
+  Fp wm = fp_from_canonical(w);
+#pragma unroll
+  for (int j = 0; j < 8; j++) if (j == (int)n_in) st[j] = wm;
+  p2_permute_dev(st);
+  if ((fp_to_canonical(st[7]) & mask) == 0) atomicMin(result, w);
+}
+u32 grind_witness(const u32 st[16], unsigned n_in, unsigned bits, u32* scratch_dev, cudaStream_t s) {
+  GrindArgs a;
+  memcpy(a.st, st, sizeof(a.st));
+  const u32 mask = (1u << bits) - 1;
+  const u32 batch = 1u << 20;
+  u32 init = 0xffffffffu, found = 0xffffffffu;
+  ZKB_CUDA(cudaMemcpyAsync(scratch_dev, &init, 4, cudaMemcpyHostToDevice, s));
+  for (u64 base = 0; base < KB_P; base += batch) {
+    grind_kernel<<<batch / 256, 256, 0, s>>>(a, n_in, mask, (u32)base, scratch_dev);
+    ZKB_CHECK_LAUNCH();
+    ZKB_CUDA(cudaMemcpyAsync(&found, scratch_dev, 4, cudaMemcpyDeviceToHost, s));
+    ZKB_CUDA(cudaStreamSynchronize(s));
+    if (found != 0xffffffffu) return found;
+  }
+  throw std::runtime_error("zkb200: proof-of-work witness not found");
+}
+
+// ---- host challenger ------------------------------------------------------------------------------
+void Challenger::duplexing() {
+  for (unsigned i = 0; i < n_in; i++) state[i] = in_buf[i];
+  n_in = 0;
+  p2_permute_host(state);
+  for (int i = 0; i < 8; i++) out_buf[i] = state[i];
+  n_out = 8;
+}
+void Challenger::observe(Fp v) {
+  n_out = 0;
+  in_buf[n_in++] = v;
+  if (n_in == 8) duplexing();
+}
+Fp Challenger::sample() {
+  if (n_in != 0 || n_out == 0) duplexing();
+  return out_buf[--n_out];
+}
+void Challenger::load(const u32* w) {
+  for (int i = 0; i < 16; i++) state[i] = fp_from_canonical(w[i]);
+  n_in = w[16];
+  for (int i = 0; i < 8; i++) in_buf[i] = fp_from_canonical(w[17 + i]);
+  n_out = w[25];
+  for (int i = 0; i < 8; i++) out_buf[i] = fp_from_canonical(w[26 + i]);
+  if (n_in > 8 || n_out > 8) throw std::runtime_error("zkb200: malformed challenger state");
+}
+void Challenger::store(u32* w) const {
+  for (int i = 0; i < 16; i++) w[i] = fp_to_canonical(state[i]);
+  w[16] = n_in;
+  for (int i = 0; i < 8; i++) w[17 + i] = i < (int)n_in ? fp_to_canonical(in_buf[i]) : 0;
+  w[25] = n_out;
+  for (int i = 0; i < 8; i++) w[26 + i] = i < (int)n_out ? fp_to_canonical(out_buf[i]) : 0;
+}
+
+}  // namespace zkb

@@ -1,0 +1,62 @@
+// K2: Poseidon2 Merkle-tree (MMCS) build, batched permutation, proof-of-work grinding, and the
+// host-side duplex challenger.  Replaces [P3-upstream] MerkleTreeMmcs::commit / PaddingFreeSponge /
+// TruncatedPermutation / DuplexChallenger as reached from TwoAdicFriPcs::commit and the FRI commit
+// phase (reference call sites crates/stark/src/prover.rs:277,403,497,547; structure pinned by
+// crates/recursion/circuit/src/fri.rs:363-405, hash.rs:40-80, challenger.rs:60-233).
+#pragma once
+#include "common.h"
+#include "poseidon2.cuh"
+
+namespace zkb {
+
+struct MatRef {
+  const u32* ptr;   // column-major
+  u32 width;
+  u32 log_height;
+};
+
+void p2_upload_constants();  // once per device
+
+// Digest layers of one commitment, each SoA: word j of node i at layer[j * count + i].
+struct DigestLayers {
+  DevBuf buf;
+  std::vector<size_t> offset;  // per layer, in words
+  std::vector<size_t> count;   // nodes per layer; layer 0 = leaves
+  u32* layer(size_t l) const { return buf.p + offset[l]; }
+};
+
+// Build the tree over column-major matrices of power-of-two heights (leaf = sponge over the
+// concatenated rows of the tallest matrices in list order; shorter ones injected on the way up).
+// `mats_dev` is the same list in device memory.  Root (Montgomery) is written to root_dev[8].
+void merkle_build(const std::vector<MatRef>& mats, ParamArena& arena, DigestLayers& out, u32* root_dev, cudaStream_t s);
+
+// Tree over one FRI commit-phase layer: folded = m EF values, component-major [4][m].
+void fri_commit_layer(const u32* folded, size_t m, DigestLayers& out, u32* root_dev, cudaStream_t s);
+
+void permute_batch(u32* states, size_t n, cudaStream_t s);   // n x 16 row-major Montgomery states
+
+// Smallest witness w (canonical) with sample_bits(bits) == 0 after observing w.
+// st: sponge state (Montgomery) with the pending inputs already written to st[0..n_in).
+u32 grind_witness(const u32 st[16], unsigned n_in, unsigned bits, u32* scratch_dev, cudaStream_t s);
+
+// DuplexChallenger<KoalaBear, Poseidon2, 16, 8> on the host (Montgomery residues internally).
+struct Challenger {
+  Fp state[16];
+  Fp in_buf[8];
+  Fp out_buf[8];
+  unsigned n_in = 0, n_out = 0;
+  Challenger() { for (auto& x : state) x = fp_zero(); }
+  void duplexing();
+  void observe(Fp v);
+  void observe_canonical(u32 v) { observe(fp_from_canonical(v)); }
+  void observe_digest(const u32* d_monty) { for (int i = 0; i < 8; i++) observe(fp_raw(d_monty[i])); }
+  void observe_ext(const Ef& e) { for (int i = 0; i < 4; i++) observe(e.c[i]); }
+  Fp sample();
+  Ef sample_ext() { Ef e; for (int i = 0; i < 4; i++) e.c[i] = sample(); return e; }
+  u32 sample_bits(unsigned bits) { return fp_to_canonical(sample()) & ((1u << bits) - 1); }
+  // 34-word canonical image: state[16], n_in, in[8], n_out, out[8]
+  void load(const u32* w);
+  void store(u32* w) const;
+};
+
+}  // namespace zkb

@@ -1,0 +1,37 @@
+// K1: batched KoalaBear NTT / coset low-degree extension over column-major matrices.
+// Replaces [P3-upstream] Radix2DitParallel::coset_lde_batch + bit_reverse_rows as called from
+// TwoAdicFriPcs::commit (reference call sites crates/stark/src/prover.rs:277,403,497 and
+// crates/stark/src/machine.rs:416-417).
+#pragma once
+#include "common.h"
+
+namespace zkb {
+
+struct NttTables {
+  u32* tw_lo = nullptr;  // w^e, e in [0, 4096)           (w = generator of the 2^24 subgroup)
+  u32* tw_hi = nullptr;  // w^(4096 e), e in [0, 4096)
+  void init(cudaStream_t s);
+  void destroy();
+};
+
+// Coset LDE of every column: in = evaluations over H_n in natural order (col-major n x w,
+// column stride in_stride), out = evaluations over shift * K_{n << log_blowup} stored
+// BIT-REVERSED by row (col-major, column stride out_stride).  Montgomery residues.
+void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* out, size_t out_stride,
+                     unsigned log_n, size_t width, unsigned log_blowup, Fp shift, cudaStream_t s);
+
+// Plain DFT of every column, natural order in; out natural (bitrev_out = false) or bit-reversed.
+void ntt_batch(const NttTables& tb, const u32* in, u32* out, unsigned log_n, size_t width, bool inverse,
+               bool bitrev_out, cudaStream_t s);
+
+#if defined(__CUDACC__)
+// w^E for E in [0, 2^24) from the two-level table (w generates the 2^24 subgroup)
+__device__ __forceinline__ Fp tw_pow2(const u32* __restrict__ lo, const u32* __restrict__ hi, u32 E) {
+  return fp_raw(__ldg(hi + (E >> 12))) * fp_raw(__ldg(lo + (E & 4095u)));
+}
+#endif
+
+// element-wise helpers used by the PCS
+void bitrev_rows(const u32* in, u32* out, unsigned log_n, size_t width, cudaStream_t s);
+
+}  // namespace zkb

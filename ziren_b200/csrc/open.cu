@@ -1,0 +1,204 @@
+#include "open.h"
+
+namespace zkb {
+
+__global__ void bary_weights_kernel(const u32* tw_lo, const u32* tw_hi, unsigned log_n, Ef zp, Ef scale, u32* out) {
+  const size_t n = (size_t)1 << log_n;
+  size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (pos >= n) return;
+  u32 i = bitrev32((u32)pos, log_n);
+  Fp h = tw_pow2(tw_lo, tw_hi, i << (24 - log_n));
+  Ef w = (ef_inv(zp - h) * h) * scale;
+#pragma unroll
+  for (int c = 0; c < 4; c++) out[(size_t)c * n + pos] = w.c[c].v;
+}
+void bary_weights(const NttTables& tb, unsigned log_n, const Ef& z, u32* out, cudaStream_t s) {
+  const size_t n = (size_t)1 << log_n;
+  // z' = z / g;  scale = (z'^n - 1) / n
+  Ef zp = z * fp_inv(fp_from_canonical(KB_GEN));
+  Ef zn = zp;
+  for (unsigned i = 0; i < log_n; i++) zn *= zn;
+  Ef scale = (zn - fp_one()) * fp_inv(fp_from_canonical((u32)(n % KB_P)));
+  bary_weights_kernel<<<ceil_div(n, 128), 128, 0, s>>>(tb.tw_lo, tb.tw_hi, log_n, zp, scale, out);
+  ZKB_CHECK_LAUNCH();
+}
+
+// ---- column evaluation --------------------------------------------------------------------------
+constexpr int EC_COLS = 8;       // columns per CTA
+constexpr int EC_THREADS = 256;
+
+template <int NPT>
+__global__ void __launch_bounds__(EC_THREADS) eval_columns_kernel(const u32* __restrict__ lde, size_t H, size_t n, size_t W,
+                                                                  const u32* __restrict__ w0, const u32* __restrict__ w1,
+                                                                  u32* __restrict__ partial, size_t rows_per_split) {
+  const size_t c0 = (size_t)blockIdx.x * EC_COLS;
+  const size_t r_begin = (size_t)blockIdx.y * rows_per_split;
+  size_t r_end = r_begin + rows_per_split;
+  if (r_end > n) r_end = n;
+  Ef acc[NPT][EC_COLS];
+#pragma unroll
+  for (int p = 0; p < NPT; p++)
+#pragma unroll
+    for (int c = 0; c < EC_COLS; c++) acc[p][c] = ef_zero();
+  for (size_t r = r_begin + threadIdx.x; r < r_end; r += EC_THREADS) {
+    Ef wv[NPT];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      wv[0].c[k] = fp_raw(w0[(size_t)k * n + r]);
+      if (NPT > 1) wv[NPT - 1].c[k] = fp_raw(w1[(size_t)k * n + r]);
+    }
+#pragma unroll
+    for (int c = 0; c < EC_COLS; c++) {
+      if (c0 + c < W) {
+        Fp x = fp_raw(lde[(c0 + c) * H + r]);
+#pragma unroll
+        for (int p = 0; p < NPT; p++) acc[p][c] += wv[p] * x;
+      }
+    }
+  }
+  // block reduction: warp shuffle, then across warps through shared memory
+  __shared__ u32 sh[EC_THREADS / 32][NPT * EC_COLS * 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int p = 0; p < NPT; p++)
+#pragma unroll
+    for (int c = 0; c < EC_COLS; c++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        Fp v = acc[p][c].c[k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v = v + fp_raw(__shfl_xor_sync(0xffffffffu, v.v, d));
+        if (lane == 0) sh[warp][(p * EC_COLS + c) * 4 + k] = v.v;
+      }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NPT * EC_COLS * 4; idx += EC_THREADS) {
+    Fp v = fp_zero();
+    for (int wv = 0; wv < EC_THREADS / 32; wv++) v = v + fp_raw(sh[wv][idx]);
+    int p = idx / (EC_COLS * 4), c = (idx / 4) % EC_COLS, k = idx % 4;
+    if (c0 + c < W) partial[(((size_t)blockIdx.y * NPT + p) * W + c0 + c) * 4 + k] = v.v;
+  }
+}
+__global__ void sum_partials_kernel(const u32* partial, size_t count, int nsplit, u32* out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Fp v = fp_zero();
+  for (int s = 0; s < nsplit; s++) v = v + fp_raw(partial[(size_t)s * count + i]);
+  out[i] = v.v;
+}
+void eval_columns(const u32* lde, size_t H, size_t n, size_t W, const u32* w0, const u32* w1, int npoints, u32* out,
+                  cudaStream_t s) {
+  if (!W) return;
+  const unsigned colblocks = ceil_div(W, EC_COLS);
+  size_t nsplit = 1;
+  if (colblocks < 296) nsplit = (296 + colblocks - 1) / colblocks;
+  size_t max_split = n / 1024 ? n / 1024 : 1;
+  if (nsplit > max_split) nsplit = max_split;
+  size_t rows_per_split = (n + nsplit - 1) / nsplit;
+  const size_t count = (size_t)npoints * W * 4;
+  DevBuf partial(nsplit > 1 ? nsplit * count : 0, s);
+  u32* dst = nsplit > 1 ? partial.p : out;
+  dim3 grid(colblocks, (unsigned)nsplit);
+  if (npoints == 1) eval_columns_kernel<1><<<grid, EC_THREADS, 0, s>>>(lde, H, n, W, w0, w0, dst, rows_per_split);
+  else eval_columns_kernel<2><<<grid, EC_THREADS, 0, s>>>(lde, H, n, W, w0, w1, dst, rows_per_split);
+  ZKB_CHECK_LAUNCH();
+  if (nsplit > 1) {
+    sum_partials_kernel<<<ceil_div(count, 256), 256, 0, s>>>(partial.p, count, (int)nsplit, out);
+    ZKB_CHECK_LAUNCH();
+  }
+}
+
+__global__ void inv_denoms_kernel(const u32* tw_lo, const u32* tw_hi, unsigned log_h, Ef z, Fp gen, u32* out) {
+  const size_t H = (size_t)1 << log_h;
+  size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (pos >= H) return;
+  u32 i = bitrev32((u32)pos, log_h);
+  Fp x = gen * tw_pow2(tw_lo, tw_hi, i << (24 - log_h));
+  Ef d = ef_inv(z - x);
+#pragma unroll
+  for (int c = 0; c < 4; c++) out[(size_t)c * H + pos] = d.c[c].v;
+}
+void inv_denominators(const NttTables& tb, unsigned log_h, const Ef& z, u32* out, cudaStream_t s) {
+  const size_t H = (size_t)1 << log_h;
+  inv_denoms_kernel<<<ceil_div(H, 128), 128, 0, s>>>(tb.tw_lo, tb.tw_hi, log_h, z, fp_from_canonical(KB_GEN), out);
+  ZKB_CHECK_LAUNCH();
+}
+
+__global__ void ef_powers_kernel(Ef alpha, size_t count, u32* out) {
+  size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  Ef p = ef_pow(alpha, j);
+  uint4 v = make_uint4(p.c[0].v, p.c[1].v, p.c[2].v, p.c[3].v);
+  reinterpret_cast<uint4*>(out)[j] = v;
+}
+void ef_powers(const Ef& alpha, size_t count, u32* out, cudaStream_t s) {
+  if (!count) return;
+  ef_powers_kernel<<<ceil_div(count, 128), 128, 0, s>>>(alpha, count, out);
+  ZKB_CHECK_LAUNCH();
+}
+
+// ---- reduced openings ---------------------------------------------------------------------------
+__device__ __forceinline__ Ef ldg_ef(const u32* p, size_t j) {
+  uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + j);
+  Ef e; e.c[0] = fp_raw(v.x); e.c[1] = fp_raw(v.y); e.c[2] = fp_raw(v.z); e.c[3] = fp_raw(v.w);
+  return e;
+}
+// rys[pt] = sum_j alpha^j ys[pt][j]   (one CTA per point)
+__global__ void __launch_bounds__(256) reduce_ys_kernel(const u32* ys, const u32* apow, size_t W, u32* rys) {
+  const u32* y = ys + (size_t)blockIdx.x * W * 4;
+  Ef acc = ef_zero();
+  for (size_t j = threadIdx.x; j < W; j += blockDim.x) acc += ldg_ef(apow, j) * ldg_ef(y, j);
+  __shared__ u32 sh[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    Fp v = acc.c[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = v + fp_raw(__shfl_xor_sync(0xffffffffu, v.v, d));
+    if (lane == 0) sh[warp][k] = v.v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    Fp v = fp_zero();
+    for (int w = 0; w < 8; w++) v = v + fp_raw(sh[w][threadIdx.x]);
+    rys[blockIdx.x * 4 + threadIdx.x] = v.v;
+  }
+}
+template <int NPT>
+__global__ void __launch_bounds__(128) reduce_matrix_kernel(const u32* __restrict__ lde, size_t H, size_t W,
+                                                            const u32* __restrict__ apow, const u32* __restrict__ rys,
+                                                            Ef off0, Ef off1, const u32* __restrict__ invden0,
+                                                            const u32* __restrict__ invden1, u32* __restrict__ ro) {
+  size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (x >= H) return;
+  Ef acc = ef_zero();
+  for (size_t j = 0; j < W; j++) acc += ldg_ef(apow, j) * fp_raw(lde[j * H + x]);
+  Ef r;
+#pragma unroll
+  for (int c = 0; c < 4; c++) r.c[c] = fp_raw(ro[(size_t)c * H + x]);
+  {
+    Ef d;
+#pragma unroll
+    for (int c = 0; c < 4; c++) d.c[c] = fp_raw(invden0[(size_t)c * H + x]);
+    r += off0 * ((ldg_ef(rys, 0) - acc) * d);
+  }
+  if (NPT > 1) {
+    Ef d;
+#pragma unroll
+    for (int c = 0; c < 4; c++) d.c[c] = fp_raw(invden1[(size_t)c * H + x]);
+    r += off1 * ((ldg_ef(rys, 1) - acc) * d);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) ro[(size_t)c * H + x] = r.c[c].v;
+}
+void reduce_matrix(const u32* lde, size_t H, size_t W, const u32* apow, const u32* ys, int npoints, const Ef& off0,
+                   const Ef& off1, const u32* invden0, const u32* invden1, u32* ro, cudaStream_t s) {
+  if (!W) return;
+  DevBuf rys(8, s);
+  reduce_ys_kernel<<<npoints, 256, 0, s>>>(ys, apow, W, rys.p);
+  ZKB_CHECK_LAUNCH();
+  if (npoints == 1) reduce_matrix_kernel<1><<<ceil_div(H, 128), 128, 0, s>>>(lde, H, W, apow, rys.p, off0, off1, invden0, invden0, ro);
+  else reduce_matrix_kernel<2><<<ceil_div(H, 128), 128, 0, s>>>(lde, H, W, apow, rys.p, off0, off1, invden0, invden1, ro);
+  ZKB_CHECK_LAUNCH();
+}
+
+}  // namespace zkb

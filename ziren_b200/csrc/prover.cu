@@ -1,0 +1,508 @@
+// Shard prover orchestration on one GPU (see prover.h).  All numeric work is in the kernels of
+// ntt.cu / hash.cu / logup.cu / quotient.cu / open.cu / fri.cu; this file sequences them on the
+// context stream, runs the duplex challenger on the host between stages (the transcript order of
+// crates/stark/src/prover.rs:298-653) and packs the "ZKPF" proof.
+#include "prover.h"
+#include <algorithm>
+#include <array>
+#include <map>
+#include "layout.h"
+#include "logup.h"
+#include "open.h"
+#include "quotient.h"
+
+namespace zkb {
+
+void Ctx::init(int dev, const u32* desc, size_t n) {
+  device = dev;
+  ZKB_CUDA(cudaSetDevice(dev));
+  machine.parse(desc, n);
+  ZKB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  // keep freed blocks in the stream-ordered pool: shard proofs reuse the same sizes
+  cudaMemPool_t pool;
+  ZKB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  unsigned long long thr = ~0ull;
+  ZKB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  machine.upload();
+  tables.init(stream);
+  p2_upload_constants();
+  arena.init(8u << 20, stream);
+  ZKB_CUDA(cudaMalloc((void**)&d_small, 1 << 16));
+  ZKB_CUDA(cudaMallocHost((void**)&h_small, 1 << 16));
+  ZKB_CUDA(cudaStreamSynchronize(stream));
+}
+void Ctx::destroy() {
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  machine.destroy();
+  tables.destroy();
+  arena.destroy();
+  if (d_small) cudaFree(d_small);
+  if (h_small) cudaFreeHost(h_small);
+  if (stream) cudaStreamDestroy(stream);
+  stream = nullptr;
+}
+
+struct StageTimer {
+  Ctx& ctx; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+  StageTimer(Ctx& c, const char* n) : ctx(c), name(n) {
+    if (ctx.profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx.stream); }
+  }
+  ~StageTimer() {
+    if (ctx.profile) {
+      cudaEventRecord(b, ctx.stream); cudaEventSynchronize(b);
+      float ms = 0; cudaEventElapsedTime(&ms, a, b);
+      ctx.stage_ms.push_back({name, ms});
+      cudaEventDestroy(a); cudaEventDestroy(b);
+    }
+  }
+};
+
+DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w) {
+  DevMat m(h, w, ctx.stream);
+  if (h * w == 0) return m;
+  cudaPointerAttributes attr;
+  bool on_device = false;
+  if (cudaPointerGetAttributes(&attr, data) == cudaSuccess) on_device = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+  else cudaGetLastError();
+  if (on_device) {
+    transpose_to_colmajor(data, m.d(), h, w, ctx.stream);
+  } else {
+    DevBuf stage(h * w, ctx.stream);
+    ZKB_CUDA(cudaMemcpyAsync(stage.p, data, h * w * sizeof(u32), cudaMemcpyHostToDevice, ctx.stream));
+    transpose_to_colmajor(stage.p, m.d(), h, w, ctx.stream);
+  }
+  return m;
+}
+
+// TwoAdicFriPcs::commit: coset LDE (shift GENERATOR / domain_shift) of every matrix + MMCS tree.
+void pcs_commit(Ctx& ctx, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out) {
+  const unsigned lb = ctx.machine.log_blowup;
+  std::vector<MatRef> refs;
+  out.ldes.clear(); out.log_n.clear();
+  Fp gen = fp_from_canonical(KB_GEN);
+  for (size_t i = 0; i < traces.size(); i++) {
+    const DevMat& t = traces[i];
+    unsigned ln = log2_exact(t.height);
+    if (((size_t)1 << ln) != t.height) throw std::runtime_error("zkb200: trace height is not a power of two");
+    if (ln + lb > 24) throw std::runtime_error("zkb200: LDE height exceeds the field's two-adicity (2^24)");
+    DevMat lde(t.height << lb, t.width, ctx.stream);
+    Fp shift = gen * fp_inv(domain_shifts[i]);
+    coset_lde_batch(ctx.tables, t.d(), t.height, lde.d(), lde.height, ln, t.width, lb, shift, ctx.stream);
+    refs.push_back(MatRef{lde.d(), (u32)t.width, ln + lb});
+    out.ldes.push_back(std::move(lde));
+    out.log_n.push_back(ln);
+  }
+  merkle_build(refs, ctx.arena, out.layers, ctx.d_small, ctx.stream);
+  ZKB_CUDA(cudaMemcpyAsync(ctx.h_small, ctx.d_small, 32, cudaMemcpyDeviceToHost, ctx.stream));
+  ZKB_CUDA(cudaStreamSynchronize(ctx.stream));
+  memcpy(out.root, ctx.h_small, 32);
+  out.log_max_height = 0;
+  for (auto& r : refs) out.log_max_height = std::max(out.log_max_height, r.log_height);
+}
+
+static void sort_traces(std::vector<TraceIn>& v) {
+  std::stable_sort(v.begin(), v.end(), [](const TraceIn& a, const TraceIn& b) {
+    if (a.height != b.height) return a.height > b.height;
+    return a.name < b.name;
+  });
+}
+
+Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, const u32* init_gsum) {
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  ZKB_CUDA(cudaSetDevice(ctx.device));
+  ctx.arena.reset();
+  std::unique_ptr<Pk> pk(new Pk());
+  pk->ctx = &ctx;
+  std::vector<TraceIn> prep = prep_in;
+  sort_traces(prep);
+  std::vector<Fp> shifts;
+  for (auto& t : prep) {
+    const ChipInfo* c = ctx.machine.find(t.name);
+    if (!c) throw std::runtime_error("zkb200: setup: unknown chip " + t.name);
+    if (c->prep_width != t.width) throw std::runtime_error("zkb200: setup: preprocessed width mismatch for " + t.name);
+    pk->names.push_back(t.name);
+    pk->local_only.push_back(c->local_only);
+    pk->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width));
+    shifts.push_back(fp_one());
+  }
+  if (!prep.empty()) {
+    pcs_commit(ctx, pk->traces, shifts, pk->data);
+    for (int i = 0; i < 8; i++) pk->commit_canon[i] = fp_to_canonical(fp_raw(pk->data.root[i]));
+  }
+  pk->pc_start = pc_start;
+  for (int i = 0; i < 14; i++) pk->init_global_sum[i] = init_gsum ? init_gsum[i] : 0;
+  ZKB_CUDA(cudaStreamSynchronize(ctx.stream));
+  return pk.release();
+}
+
+Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32* pv, size_t npv) {
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  ZKB_CUDA(cudaSetDevice(ctx.device));
+  ctx.arena.reset();
+  std::unique_ptr<Shard> sh(new Shard());
+  sh->ctx = &ctx;
+  std::vector<TraceIn> traces = traces_in;
+  sort_traces(traces);
+  std::vector<Fp> shifts;
+  for (auto& t : traces) {
+    const ChipInfo* c = ctx.machine.find(t.name);
+    if (!c) throw std::runtime_error("zkb200: commit: unknown chip " + t.name);
+    if (c->main_width != t.width) throw std::runtime_error("zkb200: commit: main width mismatch for " + t.name);
+    sh->names.push_back(t.name);
+    sh->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width));
+    shifts.push_back(fp_one());
+  }
+  if (traces.empty()) throw std::runtime_error("zkb200: commit: no traces");
+  pcs_commit(ctx, sh->traces, shifts, sh->main);
+  sh->public_values.assign(pv, pv + npv);
+  return sh.release();
+}
+
+// ---- proof packing ------------------------------------------------------------------------------
+namespace {
+struct Writer {
+  std::vector<u32> w;
+  void put(u32 x) { w.push_back(x); }
+  void put_fp(Fp x) { w.push_back(fp_to_canonical(x)); }
+  void put_ef(const Ef& e) { for (int i = 0; i < 4; i++) put_fp(e.c[i]); }
+  void put_digest_monty(const u32* d) { for (int i = 0; i < 8; i++) put_fp(fp_raw(d[i])); }
+  void str(const std::string& s) {
+    put((u32)s.size());
+    for (size_t i = 0; i < s.size(); i += 4) {
+      u32 x = 0;
+      for (size_t b = 0; b < 4 && i + b < s.size(); b++) x |= (u32)(unsigned char)s[i + b] << (8 * b);
+      put(x);
+    }
+  }
+  size_t reserve(size_t n) { size_t at = w.size(); w.resize(at + n, 0); return at; }
+};
+
+struct OpenMat {           // one matrix of one round in the opening
+  const DevMat* lde;
+  unsigned log_h;          // LDE log height
+  unsigned log_n;
+  int npoints;             // 1: zeta; 2: zeta and zeta * g_n
+  size_t ys_off;           // word offset of [npoints][W] EF in the opened-values buffer
+  size_t alpha_off;        // num_reduced[log_h] before this matrix
+};
+}  // namespace
+
+std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger34) {
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  ZKB_CUDA(cudaSetDevice(ctx.device));
+  ctx.arena.reset();
+  ctx.stage_ms.clear();
+  cudaStream_t s = ctx.stream;
+  const MachineInfo& M = ctx.machine;
+  const unsigned lb = M.log_blowup;
+  const size_t nc = sh.names.size();
+  std::vector<const ChipInfo*> chips;
+  std::vector<unsigned> logn;
+  for (size_t i = 0; i < nc; i++) { chips.push_back(M.find(sh.names[i])); logn.push_back(log2_exact(sh.traces[i].height)); }
+  if (sh.public_values.size() < M.num_pv_elts) throw std::runtime_error("zkb200: open: fewer public values than num_pv_elts");
+  for (auto& name : pk.names) if (std::find(sh.names.begin(), sh.names.end(), name) == sh.names.end())
+    throw std::runtime_error("zkb200: open: preprocessed chip " + name + " missing from shard");
+
+  Challenger ch;
+  ch.load(challenger34);
+  for (u32 i = 0; i < M.num_pv_elts; i++) ch.observe_canonical(sh.public_values[i]);
+  ch.observe_digest(sh.main.root);
+  const Ef perm_alpha = ch.sample_ext(), perm_beta = ch.sample_ext();
+
+  // public values on the device (Montgomery)
+  std::vector<u32> pv_m(std::max<size_t>(sh.public_values.size(), 1), 0);
+  for (size_t i = 0; i < sh.public_values.size(); i++) pv_m[i] = fp_from_canonical(sh.public_values[i] % KB_P).v;
+  const u32* pv_dev = ctx.arena.push(pv_m.data(), pv_m.size());
+
+  // ---- permutation traces (K5) + commit -----------------------------------------------------
+  std::vector<DevMat> perm_traces;
+  std::vector<Ef> local_sums(nc);
+  std::vector<std::array<u32, 14>> global_sums(nc);   // Montgomery
+  {
+    StageTimer tm(ctx, "permutation_trace");
+    // sums land in d_small: per chip 4 words local + 14 words global
+    if (nc > 200) throw std::runtime_error("zkb200: too many chips in shard");
+    std::vector<GatherJob> jobs;
+    for (size_t i = 0; i < nc; i++) {
+      int pi = pk.index_of(sh.names[i]);
+      const DevMat* prep = pi >= 0 ? &pk.traces[pi] : nullptr;
+      if (prep && prep->height != sh.traces[i].height) throw std::runtime_error("zkb200: preprocessed and main have different heights: " + sh.names[i]);
+      const size_t n = sh.traces[i].height;
+      DevMat pt(n, 4 * chips[i]->perm_width_ef(), s);
+      u32* sums = ctx.d_small + 4096 + i * 4;   // Montgomery scratch, converted by the gather below
+      permutation_trace(M, *chips[i], prep ? prep->d() : nullptr, sh.traces[i].d(), n, perm_alpha, perm_beta, pt.d(), sums, s);
+      jobs.push_back(GatherJob{sums, 1, 4, (u32)(i * 18)});
+      if (chips[i]->global_scope)
+        jobs.push_back(GatherJob{sh.traces[i].d() + (sh.traces[i].width - 14) * n + (n - 1), n, 14, (u32)(i * 18 + 4)});
+      perm_traces.push_back(std::move(pt));
+    }
+    ZKB_CUDA(cudaMemsetAsync(ctx.d_small, 0, nc * 18 * 4, s));
+    const GatherJob* jd = ctx.arena.push(jobs.data(), jobs.size());
+    gather_canonical(jd, jobs.size(), ctx.d_small, s);
+    ZKB_CUDA(cudaMemcpyAsync(ctx.h_small, ctx.d_small, nc * 18 * 4, cudaMemcpyDeviceToHost, s));
+    ZKB_CUDA(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < nc; i++) {
+      const u32* w = ctx.h_small + i * 18;   // canonical
+      for (int c = 0; c < 4; c++) local_sums[i].c[c] = fp_from_canonical(w[c]);
+      for (int k = 0; k < 14; k++) global_sums[i][k] = fp_from_canonical(w[4 + k]).v;
+    }
+  }
+  Commit perm_commit;
+  {
+    StageTimer tm(ctx, "commit_permutation");
+    std::vector<Fp> shifts(nc, fp_one());
+    pcs_commit(ctx, perm_traces, shifts, perm_commit);
+  }
+  perm_traces.clear();
+  ch.observe_digest(perm_commit.root);
+  for (size_t i = 0; i < nc; i++) {
+    ch.observe_ext(local_sums[i]);
+    for (int k = 0; k < 14; k++) ch.observe(fp_raw(global_sums[i][k]));
+  }
+
+  // ---- quotient (K3) + commit ---------------------------------------------------------------
+  const Ef alpha = ch.sample_ext();
+  std::vector<DevMat> quot_chunks;
+  std::vector<Fp> quot_shifts;
+  {
+    StageTimer tm(ctx, "quotient");
+    for (size_t i = 0; i < nc; i++) {
+      const unsigned lqd = chips[i]->log_quotient_degree;
+      const size_t n = (size_t)1 << logn[i], nchunks = (size_t)1 << lqd;
+      DevBuf q(nchunks * 4 * n, s);
+      QuotientInputs in;
+      int pi = pk.index_of(sh.names[i]);
+      in.prep_lde = pi >= 0 ? pk.data.ldes[pi].d() : nullptr;
+      in.main_lde = sh.main.ldes[i].d();
+      in.perm_lde = perm_commit.ldes[i].d();
+      in.lde_h = n << lb;
+      in.log_n = logn[i];
+      in.perm_alpha = perm_alpha; in.perm_beta = perm_beta; in.local_sum = local_sums[i]; in.alpha = alpha;
+      memcpy(in.global_sum, global_sums[i].data(), sizeof(in.global_sum));
+      in.pub_dev = pv_dev;
+      quotient_values(M, *chips[i], ctx.tables, in, q.p, s);
+      Fp gq = two_adic_generator(logn[i] + lqd);
+      for (size_t j = 0; j < nchunks; j++) {
+        DevMat cm(n, 4, s);
+        ZKB_CUDA(cudaMemcpyAsync(cm.d(), q.p + j * 4 * n, 4 * n * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+        quot_chunks.push_back(std::move(cm));
+        quot_shifts.push_back(fp_from_canonical(KB_GEN) * fp_pow(gq, j));
+      }
+    }
+  }
+  Commit quot_commit;
+  {
+    StageTimer tm(ctx, "commit_quotient");
+    pcs_commit(ctx, quot_chunks, quot_shifts, quot_commit);
+  }
+  quot_chunks.clear();
+  ch.observe_digest(quot_commit.root);
+  const Ef zeta = ch.sample_ext();
+
+  // ---- opening (K4a/K4b) ----------------------------------------------------------------------
+  struct Round { const Commit* c; std::vector<OpenMat> mats; };
+  std::vector<Round> rounds;
+  size_t ys_words = 0;
+  size_t num_reduced[32] = {0};
+  size_t max_w = 1;
+  auto add_round = [&](const Commit* c, const std::vector<int>& npts) {
+    Round r; r.c = c;
+    for (size_t i = 0; i < c->ldes.size(); i++) {
+      OpenMat m;
+      m.lde = &c->ldes[i]; m.log_n = c->log_n[i]; m.log_h = c->log_n[i] + lb; m.npoints = npts[i];
+      m.ys_off = ys_words; ys_words += (size_t)m.npoints * m.lde->width * 4;
+      m.alpha_off = num_reduced[m.log_h];
+      num_reduced[m.log_h] += (size_t)m.npoints * m.lde->width;
+      max_w = std::max(max_w, m.lde->width);
+      r.mats.push_back(m);
+    }
+    rounds.push_back(std::move(r));
+  };
+  if (!pk.data.empty()) { std::vector<int> np; for (size_t i = 0; i < pk.names.size(); i++) np.push_back(pk.local_only[i] ? 1 : 2); add_round(&pk.data, np); }
+  { std::vector<int> np; for (size_t i = 0; i < nc; i++) np.push_back(chips[i]->local_only ? 1 : 2); add_round(&sh.main, np); }
+  add_round(&perm_commit, std::vector<int>(nc, 2));
+  add_round(&quot_commit, std::vector<int>(quot_commit.ldes.size(), 1));
+  const size_t main_round = pk.data.empty() ? 0 : 1;
+
+  const Ef alpha_fri = ch.sample_ext();
+  unsigned log_gmax = 0;
+  for (auto& r : rounds) log_gmax = std::max(log_gmax, r.c->log_max_height);
+
+  DevBuf ys_dev(std::max<size_t>(ys_words, 1), s);
+  std::vector<DevBuf> ro(32);
+  {
+    StageTimer tm(ctx, "open_reduce");
+    DevBuf apow(4 * max_w, s);
+    ef_powers(alpha_fri, max_w, apow.p, s);
+    // group by LDE height so that barycentric weights and inverse denominators are built once
+    for (unsigned lh = lb; lh <= log_gmax; lh++) {
+      bool any = false, any2 = false;
+      for (auto& r : rounds) for (auto& m : r.mats) if (m.log_h == lh) { any = true; if (m.npoints == 2) any2 = true; }
+      if (!any) continue;
+      const unsigned ln = lh - lb;
+      const size_t n = (size_t)1 << ln, H = (size_t)1 << lh;
+      const Ef znext = zeta * two_adic_generator(ln);
+      DevBuf w0(4 * n, s), w1(any2 ? 4 * n : 0, s), d0(4 * H, s), d1(any2 ? 4 * H : 0, s);
+      bary_weights(ctx.tables, ln, zeta, w0.p, s);
+      inv_denominators(ctx.tables, lh, zeta, d0.p, s);
+      if (any2) { bary_weights(ctx.tables, ln, znext, w1.p, s); inv_denominators(ctx.tables, lh, znext, d1.p, s); }
+      ro[lh] = DevBuf(4 * H, s);
+      ZKB_CUDA(cudaMemsetAsync(ro[lh].p, 0, 4 * H * sizeof(u32), s));
+      for (auto& r : rounds) for (auto& m : r.mats) {
+        if (m.log_h != lh || m.lde->width == 0) continue;
+        const size_t W = m.lde->width;
+        u32* ys = ys_dev.p + m.ys_off;
+        eval_columns(m.lde->d(), H, n, W, w0.p, w1.p, m.npoints, ys, s);
+        Ef off0 = ef_pow(alpha_fri, m.alpha_off), off1 = ef_pow(alpha_fri, m.alpha_off + W);
+        reduce_matrix(m.lde->d(), H, W, apow.p, ys, m.npoints, off0, off1, d0.p, d1.p, ro[lh].p, s);
+      }
+    }
+  }
+
+  // ---- FRI commit phase (K4c) -------------------------------------------------------------------
+  struct FriLayer { DevBuf folded; size_t m; DigestLayers tree; u32 root[8]; };
+  std::vector<FriLayer> fri_layers;
+  Ef final_poly;
+  {
+    StageTimer tm(ctx, "fri_commit_phase");
+    DevBuf cur = std::move(ro[log_gmax]);
+    size_t m = (size_t)1 << log_gmax;
+    const size_t blowup = (size_t)1 << lb;
+    while (m > blowup) {
+      FriLayer L;
+      L.m = m;
+      fri_commit_layer(cur.p, m, L.tree, ctx.d_small, s);
+      ZKB_CUDA(cudaMemcpyAsync(ctx.h_small, ctx.d_small, 32, cudaMemcpyDeviceToHost, s));
+      ZKB_CUDA(cudaStreamSynchronize(s));
+      memcpy(L.root, ctx.h_small, 32);
+      ch.observe_digest(L.root);
+      const Ef beta = ch.sample_ext();
+      const unsigned lnext = log2_exact(m) - 1;
+      DevBuf next(4 * (m >> 1), s);
+      fri_fold(ctx.tables, cur.p, m, beta, ro[lnext].p, next.p, s);
+      L.folded = std::move(cur);
+      cur = std::move(next);
+      fri_layers.push_back(std::move(L));
+      m >>= 1;
+    }
+    // `cur` holds blowup evaluations of a constant polynomial
+    ZKB_CUDA(cudaMemcpyAsync(ctx.h_small, cur.p, 4 * m * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    ZKB_CUDA(cudaStreamSynchronize(s));
+    for (int c = 0; c < 4; c++) final_poly.c[c] = fp_raw(ctx.h_small[c * m]);
+    for (size_t i = 1; i < m; i++)
+      for (int c = 0; c < 4; c++)
+        if (ctx.h_small[c * m + i] != final_poly.c[c].v) throw std::runtime_error("zkb200: FRI final polynomial is not constant (unsatisfied constraints?)");
+  }
+  ch.observe_ext(final_poly);
+
+  // ---- proof of work (K4d) ------------------------------------------------------------------
+  u32 pow_witness = 0;
+  {
+    StageTimer tm(ctx, "grind");
+    u32 st[16];
+    for (int i = 0; i < 16; i++) st[i] = ch.state[i].v;
+    for (unsigned i = 0; i < ch.n_in; i++) st[i] = ch.in_buf[i].v;
+    pow_witness = grind_witness(st, ch.n_in, M.pow_bits, ctx.d_small + 8192, s);
+    ch.observe_canonical(pow_witness);
+    if (ch.sample_bits(M.pow_bits) != 0) throw std::runtime_error("zkb200: grinding produced an invalid witness");
+  }
+
+  // ---- assemble the proof; query openings are gathered on the device (K4e) ----------------------
+  std::vector<u32> ys_host(ys_words);
+  if (ys_words) ZKB_CUDA(cudaMemcpyAsync(ys_host.data(), ys_dev.p, ys_words * sizeof(u32), cudaMemcpyDeviceToHost, s));
+  ZKB_CUDA(cudaStreamSynchronize(s));
+  auto ys_at = [&](const OpenMat& m, int pt, size_t col) {
+    const u32* p = ys_host.data() + m.ys_off + ((size_t)pt * m.lde->width + col) * 4;
+    Ef e; for (int c = 0; c < 4; c++) e.c[c] = fp_raw(p[c]);
+    return e;
+  };
+
+  Writer o;
+  o.put(0x46504b5au); o.put(1);
+  o.put_digest_monty(sh.main.root); o.put_digest_monty(perm_commit.root); o.put_digest_monty(quot_commit.root);
+  o.put((u32)nc);
+  size_t qidx = 0;
+  for (size_t i = 0; i < nc; i++) {
+    const ChipInfo& c = *chips[i];
+    o.str(c.name);
+    o.put(logn[i]);
+    o.put(c.prep_width); o.put(c.main_width); o.put(4 * c.perm_width_ef()); o.put(1u << c.log_quotient_degree);
+    auto put_opened = [&](const OpenMat* m, size_t width) {
+      for (int pt = 0; pt < 2; pt++)
+        for (size_t col = 0; col < width; col++) {
+          if (m && pt < m->npoints) o.put_ef(ys_at(*m, pt, col));
+          else o.put_ef(ef_zero());
+        }
+    };
+    int pi = pk.index_of(c.name);
+    put_opened(pi >= 0 ? &rounds[0].mats[pi] : nullptr, pi >= 0 ? c.prep_width : 0);
+    put_opened(&rounds[main_round].mats[i], c.main_width);
+    put_opened(&rounds[main_round + 1].mats[i], 4 * c.perm_width_ef());
+    for (u32 j = 0; j < (1u << c.log_quotient_degree); j++, qidx++)
+      for (size_t col = 0; col < 4; col++) o.put_ef(ys_at(rounds[main_round + 2].mats[qidx], 0, col));
+    for (int k = 0; k < 14; k++) o.put_fp(fp_raw(global_sums[i][k]));
+    o.put_ef(local_sums[i]);
+  }
+  o.put((u32)sh.public_values.size());
+  for (u32 x : sh.public_values) o.put(x);
+  o.put((u32)fri_layers.size());
+  for (auto& L : fri_layers) o.put_digest_monty(L.root);
+  o.put_ef(final_poly);
+  o.put(pow_witness);
+  o.put(M.num_queries);
+
+  std::vector<GatherJob> jobs;
+  {
+    StageTimer tm(ctx, "query_openings");
+    for (u32 q = 0; q < M.num_queries; q++) {
+      const size_t index = ch.sample_bits(log_gmax);
+      o.put((u32)rounds.size());
+      for (auto& r : rounds) {
+        const unsigned lmax = r.c->log_max_height;
+        const size_t ridx = index >> (log_gmax - lmax);
+        o.put((u32)r.mats.size());
+        for (auto& m : r.mats) {
+          const size_t W = m.lde->width, H = m.lde->height;
+          const size_t row = ridx >> (lmax - m.log_h);
+          o.put((u32)W);
+          size_t at = o.reserve(W);
+          if (W) jobs.push_back(GatherJob{m.lde->d() + row, H, (u32)W, (u32)at});
+        }
+        o.put(lmax);
+        for (unsigned l = 0; l < lmax; l++) {
+          size_t at = o.reserve(8);
+          size_t node = (ridx >> l) ^ 1;
+          jobs.push_back(GatherJob{r.c->layers.layer(l) + node, r.c->layers.count[l], 8, (u32)at});
+        }
+      }
+      o.put((u32)fri_layers.size());
+      for (size_t li = 0; li < fri_layers.size(); li++) {
+        const FriLayer& L = fri_layers[li];
+        const size_t idx_i = index >> li, pair = idx_i >> 1, sib = idx_i ^ 1;
+        size_t at = o.reserve(4);
+        jobs.push_back(GatherJob{L.folded.p + sib, L.m, 4, (u32)at});
+        const unsigned depth = (unsigned)L.tree.count.size() - 1;
+        o.put(depth);
+        for (unsigned l = 0; l < depth; l++) {
+          size_t a2 = o.reserve(8);
+          size_t node = (pair >> l) ^ 1;
+          jobs.push_back(GatherJob{L.tree.layer(l) + node, L.tree.count[l], 8, (u32)a2});
+        }
+      }
+    }
+    if (o.w.size() >= (1ull << 32)) throw std::runtime_error("zkb200: proof too large");
+    // gather straight into a device image of the proof, then overlay the gathered words
+    DevBuf jobs_dev((jobs.size() * sizeof(GatherJob) + 3) / 4 + 1, s);
+    DevBuf img(o.w.size(), s);
+    ZKB_CUDA(cudaMemcpyAsync(jobs_dev.p, jobs.data(), jobs.size() * sizeof(GatherJob), cudaMemcpyHostToDevice, s));
+    ZKB_CUDA(cudaMemcpyAsync(img.p, o.w.data(), o.w.size() * sizeof(u32), cudaMemcpyHostToDevice, s));
+    gather_canonical(reinterpret_cast<const GatherJob*>(jobs_dev.p), jobs.size(), img.p, s);
+    ZKB_CUDA(cudaMemcpyAsync(o.w.data(), img.p, o.w.size() * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    ZKB_CUDA(cudaStreamSynchronize(s));
+  }
+  ch.store(challenger34);
+  return std::move(o.w);
+}
+
+}  // namespace zkb

@@ -1,0 +1,80 @@
+// Host orchestration of the shard prover on one GPU: the device-side counterpart of the
+// reference's MachineProver implementation (crates/stark/src/prover.rs:30-184 trait,
+// :258-292 commit, :298-653 open) and of StarkMachine::setup (crates/stark/src/machine.rs:352-459).
+#pragma once
+#include <mutex>
+#include <string>
+#include <vector>
+#include "common.h"
+#include "fri.h"
+#include "hash.h"
+#include "machine.h"
+#include "ntt.h"
+
+namespace zkb {
+
+// One committed batch of matrices: the device image of Plonky3's PcsProverData
+// (bit-reversed coset LDEs + Merkle digest layers).
+struct Commit {
+  std::vector<DevMat> ldes;          // column-major, height n << log_blowup
+  std::vector<unsigned> log_n;       // trace log-heights
+  DigestLayers layers;
+  u32 root[8] = {0};                 // Montgomery
+  unsigned log_max_height = 0;       // of the LDEs
+  bool empty() const { return ldes.empty(); }
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  MachineInfo machine;
+  NttTables tables;
+  ParamArena arena;
+  u32* d_small = nullptr;            // small device scratch (roots, sums)
+  u32* h_small = nullptr;            // pinned mirror
+  std::mutex mu;                     // commit/open may be called from several host threads
+  std::string err;
+  // statistics of the last open(): kernel-stage timings (ms) when profiling is enabled
+  bool profile = false;
+  std::vector<std::pair<std::string, float>> stage_ms;
+  unsigned long long launches = 0;
+
+  void init(int device, const u32* desc, size_t n);
+  void destroy();
+};
+
+struct TraceIn { std::string name; const u32* data; size_t height, width; };   // row-major Montgomery; host or device pointer
+
+struct Pk {
+  Ctx* ctx = nullptr;
+  std::vector<std::string> names;      // (height desc, name asc)
+  std::vector<DevMat> traces;          // preprocessed traces, column-major
+  std::vector<bool> local_only;
+  Commit data;
+  u32 commit_canon[8] = {0};
+  u32 pc_start = 0;                    // canonical
+  u32 init_global_sum[14] = {0};       // canonical
+  int index_of(const std::string& n) const {
+    for (size_t i = 0; i < names.size(); i++) if (names[i] == n) return (int)i;
+    return -1;
+  }
+};
+
+struct Shard {
+  Ctx* ctx = nullptr;
+  std::vector<std::string> names;      // (height desc, name asc)
+  std::vector<DevMat> traces;          // main traces, column-major
+  Commit main;
+  std::vector<u32> public_values;      // canonical
+};
+
+Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep, u32 pc_start, const u32* init_gsum);
+Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces, const u32* pv, size_t npv);
+// consumes nothing; caller frees the shard.  challenger34: canonical image, in/out.
+std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& shard, u32* challenger34);
+
+// building blocks shared with the micro entry points
+DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w);
+void pcs_commit(Ctx& ctx, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out);
+
+}  // namespace zkb
