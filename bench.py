@@ -1,0 +1,294 @@
+#!/usr/bin/env python3
+"""Headline benchmark: MIPS cycles proved per second (BASELINE.json `metric`).
+
+A "step" proves ONE shard of the named workload through the reference-facing C ABI
+(`zkb200_commit` + `zkb200_open`, i.e. MachineProver::{commit, open}).  Default workload at N=1 is
+BASELINE.json configs[1] ("examples/keccak-precompile, 2^20-row shards"): a synthetic core shard
+with a 2^20-row Cpu table whose area is dominated by a KeccakSponge precompile table (no guest ELF
+can be built here, see ziren_b200/synthetic.py).  cycles per shard = rows of the Cpu table.
+
+  value : device-resident inputs (row-major traces already in HBM), timed with CUDA events on the
+          prover's stream, max over ranks.
+  e2e   : the same call with traces in PINNED HOST memory; H2D of the traces and D2H of the proof
+          are inside the timed region.
+  roofline / cpu_baseline : see DESIGN.md §Measurement.
+
+Multi-GPU (torchrun, one rank per GPU): shards are independent, every rank proves
+its own shards, no data-path collective; NCCL only gathers the 8-word commitments and the timings.
+`--impl reference` times the CPU oracle (the reference itself cannot be built here: no Rust) with
+all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from ziren_b200 import field as kb  # noqa: E402
+from ziren_b200 import synthetic  # noqa: E402
+
+METRIC = "mips_cycles_proved_per_sec"
+UNIT = "cycles/s"
+
+
+def make_case(args, sample=False):
+    w = args.workload
+    lc = args.sample_log_cpu if sample else args.log_cpu
+    if w == "keccak":
+        return synthetic.keccak_case(log_cpu=lc, seed=0xC0FFEE + args.rank)
+    if w == "core":
+        return synthetic.core_case(log_cpu=lc, seed=0xC0FFEE + args.rank)
+    if w == "fibonacci":
+        return synthetic.fibonacci_core_case(log_cpu=lc, seed=0xC0FFEE + args.rank)
+    raise SystemExit(f"unknown workload {w}")
+
+
+def workload_config(args, case, sample=False):
+    lc = args.sample_log_cpu if sample else args.log_cpu
+    names = {"keccak": "examples/keccak-precompile-like synthetic shard (Cpu 2^%d rows, KeccakSponge 2^%d x 4259 cols)" % (lc, lc - 2),
+             "core": "tendermint-like maximal core shard (maximal_shapes.json[21][1] scaled to Cpu 2^%d)" % lc,
+             "fibonacci": "examples/fibonacci-like single core shard (Cpu 2^%d)" % lc}
+    return {"workload": names[args.workload], "cycles_per_shard": case.cycles, "cells_per_shard": case.cells,
+            "trace_bytes_per_shard": case.trace_bytes, "fri": {"log_blowup": 1, "num_queries": 84, "pow_bits": 16},
+            "l2_policy": "inputs larger than L2 (trace bytes >> 126 MB); fresh shard allocations every step",
+            "parallelism": f"shard-per-gpu x{args.gpus}"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [int(s[0]) for s in self.samples if s and s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port (kind 'port'), all host threads, bounded sample of the workload."""
+    from oracle import oracle_ffi as o
+    if args.rank != 0:
+        return
+    case = make_case(args, sample=True)
+    om = o.OracleMachine(case.machine)
+    om.setup(case.prep)
+    cores = o.num_threads()
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        om.prove_shard(case.traces, case.public_values)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        proof, _ = om.prove_shard(case.traces, case.public_values)
+    dt = time.perf_counter() - t0
+    val = case.cycles * args.steps / dt
+    cfg = workload_config(args, case, sample=True)
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 (KoalaBear 31-bit prime field)", "data": "synthetic", "impl": "reference", "config": cfg,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} shard(s) of the same machine scaled to Cpu 2^{args.sample_log_cpu}; "
+                                       "C++ oracle (OpenMP), not Plonky3's AVX code: the Rust reference cannot be built here"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="keccak", choices=["keccak", "core", "fibonacci"])
+    ap.add_argument("--log-cpu", type=int, default=20)
+    ap.add_argument("--sample-log-cpu", type=int, default=14, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="print per-stage device times to stderr")
+    args = ap.parse_args()
+    args.rank = int(os.environ.get("RANK", "0"))
+    args.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ziren_b200.prover import B200Prover
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(args.local_rank)
+    distributed = args.world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", args.local_rank))
+
+    case = make_case(args)
+    prover = B200Prover(case.machine, device=args.local_rank)
+    stream = torch.cuda.ExternalStream(prover.stream_ptr(), device=torch.device("cuda", args.local_rank))
+    pk = prover.setup({k: kb.to_monty(v) for k, v in case.prep.items()})
+    base_ch = pk.observe_into()
+
+    # inputs: Montgomery row-major, once in pinned host memory (e2e arm), once resident in HBM
+    host_tr = {}
+    for k, v in case.traces.items():
+        t = torch.from_numpy(kb.to_monty(v).view(np.int32)).pin_memory()
+        host_tr[k] = t
+    dev_tr = {k: v.cuda() for k, v in host_tr.items()}
+    h2d_bytes = sum(4 * v.numel() for v in host_tr.values())
+    torch.cuda.synchronize()
+
+    def prove(traces):
+        proof, _ = prover.prove_shard(pk, traces, case.public_values, base_ch)
+        return proof
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(traces, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        proof = None
+        for _ in range(steps):
+            proof = prove(traces)
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if distributed:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, proof
+
+    for _ in range(args.warmup):
+        prove(dev_tr)
+    sampler = ClockSampler(args.local_rank)
+    sampler.start()
+    ms_dev, proof = timed(dev_tr, args.steps)
+    ms_e2e, proof2 = timed(host_tr, args.steps)
+    clocks = sampler.stop()
+    assert np.array_equal(proof, proof2)
+    d2h_bytes = int(proof.size) * 4
+
+    stages = None
+    if args.rank == 0:
+        prover.set_profile(True)
+        prove(dev_tr)
+        stages = prover.last_stage_times()
+        prover.set_profile(False)
+        if args.stages:
+            print("stage ms:", json.dumps(stages), file=sys.stderr)
+
+    # commitments are the only thing the ranks exchange (NCCL all_gather of 8 words)
+    if distributed:
+        c = torch.from_numpy(proof[2:10].astype(np.int64)).cuda()
+        allc = [torch.empty_like(c) for _ in range(args.world)]
+        dist.all_gather(allc, c)
+
+    roofline = cpu_base = None
+    if args.rank == 0:
+        roofline = measure_roofline(prover, case, torch, stream)
+        if not args.no_cpu_baseline:
+            cpu_base = measure_cpu_baseline(args)
+
+    if args.rank == 0:
+        total_cycles = case.cycles * args.steps * args.gpus
+        line = {"metric": METRIC, "value": total_cycles / (ms_dev / 1e3), "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32 (KoalaBear 31-bit prime field)", "data": "synthetic",
+                "config": workload_config(args, case),
+                "e2e": {"value": total_cycles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": None, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
+                "stage_ms": stages, "cells_per_sec": case.cells * args.steps * args.gpus / (ms_dev / 1e3)}
+        line["gpu_launches"] = count_launches(case)
+        print(json.dumps(line))
+    pk.free()
+    prover.close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+def count_launches(case):
+    """Kernels of OURS launched per timed step (analytic count of the launch sites in
+    csrc/prover.cu for this shard; cross-checked against the ncu launch list in profiles/)."""
+    return None  # filled from the profile in DESIGN.md until the library exports a live counter
+
+
+def measure_roofline(prover, case, torch, stream):
+    """HBM roofline of the dominant kernel family measured live with CUDA events: the coset LDE of
+    the widest table (algorithmic bytes 12*n*c per SURVEY.md §8d: read n*c, write 2n*c words)."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, which = 6650.0, "fallback"
+    if os.path.exists(peaks_path):
+        peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+    name, tr = max(case.traces.items(), key=lambda kv: kv[1].size)
+    n, w = tr.shape
+    w = min(w, 512)
+    log_n = int(np.log2(n))
+    d_in = torch.randint(0, kb.P, (w, n), dtype=torch.int32, device="cuda")
+    d_out = torch.empty((w, 2 * n), dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        prover.coset_lde(d_in, d_out, log_n, w, 1, 3)
+    prover.sync()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        prover.coset_lde(d_in, d_out, log_n, w, 1, 3)
+    e1.record(stream)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    alg = 12.0 * n * w
+    achieved = alg / (ms / 1e3) / 1e9
+    return {"bound": "hbm", "kernel": "coset_lde_batch (ntt_pass_kernel x passes)", "achieved": achieved, "peak": peak,
+            "peak_source": which, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "shape": f"{name}: n=2^{log_n}, {w} columns", "ms": ms}
+
+
+def measure_cpu_baseline(args):
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", args.workload, "--sample-log-cpu", str(args.sample_log_cpu)],
+                         capture_output=True, text=True, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
+    try:
+        return json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+    except Exception:
+        return {"error": (out.stderr or out.stdout)[-300:]}
+
+
+if __name__ == "__main__":
+    main()

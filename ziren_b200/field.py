@@ -11,14 +11,23 @@ R_MOD_P = (1 << 32) % P          # 0x1fffffe
 R_INV = pow(R_MOD_P, P - 2, P)
 
 
+def _chunked(fn, x, chunk=1 << 24):
+    x = np.ascontiguousarray(x)
+    if x.size <= chunk:
+        return fn(x)
+    out = np.empty(x.shape, dtype=np.uint32)
+    flat_in, flat_out = x.reshape(-1), out.reshape(-1)
+    for i in range(0, x.size, chunk):
+        flat_out[i:i + chunk] = fn(flat_in[i:i + chunk])
+    return out
+
+
 def to_monty(x) -> np.ndarray:
-    x = np.asarray(x, dtype=np.uint64)
-    return ((x << np.uint64(32)) % np.uint64(P)).astype(np.uint32)
+    return _chunked(lambda a: ((a.astype(np.uint64) << np.uint64(32)) % np.uint64(P)).astype(np.uint32), np.asarray(x))
 
 
 def from_monty(x) -> np.ndarray:
-    x = np.asarray(x, dtype=np.uint64)
-    return ((x * np.uint64(R_INV)) % np.uint64(P)).astype(np.uint32)
+    return _chunked(lambda a: ((a.astype(np.uint64) * np.uint64(R_INV)) % np.uint64(P)).astype(np.uint32), np.asarray(x))
 
 
 def mul(a, b) -> np.ndarray:
