@@ -132,6 +132,10 @@ def main():
     ap.add_argument("--log-cpu", type=int, default=20)
     ap.add_argument("--sample-log-cpu", type=int, default=14, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=2,
+                    help="host threads calling commit/open concurrently in the e2e arm (the reference keeps "
+                         "shard_batch_size shards in flight, prove.rs:487-521): uploads of one shard overlap the open of another")
     ap.add_argument("--stages", action="store_true", help="print per-stage device times to stderr")
     args = ap.parse_args()
     args.rank = int(os.environ.get("RANK", "0"))
@@ -177,13 +181,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(traces, steps):
+    def timed(traces, steps, nthreads=1):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        proof = None
-        for _ in range(steps):
-            proof = prove(traces)
+        proofs = [None] * steps
+        if nthreads <= 1:
+            for i in range(steps):
+                proofs[i] = prove(traces)
+        else:
+            def worker(t):
+                for i in range(t, steps, nthreads):
+                    proofs[i] = prove(traces)
+            ths = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        proof = proofs[-1]
+        prover.sync()
         e1.record(stream)
         e1.synchronize()
         barrier()
@@ -199,7 +215,8 @@ def main():
     sampler = ClockSampler(args.local_rank)
     sampler.start()
     ms_dev, proof = timed(dev_tr, args.steps)
-    ms_e2e, proof2 = timed(host_tr, args.steps)
+    timed(host_tr, max(args.warmup, args.e2e_threads), args.e2e_threads)      # warm the staging/pool paths of the e2e arm
+    ms_e2e, proof2 = timed(host_tr, args.steps, args.e2e_threads)
     clocks = sampler.stop()
     assert np.array_equal(proof, proof2)
     d2h_bytes = int(proof.size) * 4
@@ -221,7 +238,8 @@ def main():
 
     roofline = cpu_base = None
     if args.rank == 0:
-        roofline = measure_roofline(prover, case, torch, stream)
+        if not args.no_roofline:
+            roofline = measure_roofline(prover, case, torch, stream)
         if not args.no_cpu_baseline:
             cpu_base = measure_cpu_baseline(args)
 
@@ -232,7 +250,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32 (KoalaBear 31-bit prime field)", "data": "synthetic",
                 "config": workload_config(args, case),
                 "e2e": {"value": total_cycles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
+                        "host_threads_in_flight": args.e2e_threads},
                 "gpu_launches": None, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
                 "stage_ms": stages, "cells_per_sec": case.cells * args.steps * args.gpus / (ms_dev / 1e3)}
         line["gpu_launches"] = count_launches(case)

@@ -74,7 +74,7 @@ typedef struct {
 /* MachineProver::new(machine) — crates/stark/src/prover.rs:43.  `desc` is a ZKMD descriptor. */
 int zkb200_ctx_create(int device, const uint32_t* desc, size_t n_words, zkb200_ctx** out);
 void zkb200_ctx_destroy(zkb200_ctx* ctx);
-/* error text of the last failed call on this context (or of ctx_create when ctx is NULL) */
+/* error text of the last failed call made by the calling host thread (ctx may be NULL) */
 const char* zkb200_last_error(zkb200_ctx* ctx);
 /* the CUDA stream (cudaStream_t) all work of this context is issued on */
 void* zkb200_ctx_stream(zkb200_ctx* ctx);

@@ -13,7 +13,8 @@ struct zkb200_ctx { Ctx c; };
 struct zkb200_pk { Pk* p; };
 struct zkb200_shard { Shard* s; };
 
-static thread_local std::string g_create_err;
+// MachineProver::Error text of the last failed call made by THIS host thread
+static thread_local std::string g_err;
 
 template <class F>
 static int guarded(zkb200_ctx* ctx, F&& f) {
@@ -21,7 +22,7 @@ static int guarded(zkb200_ctx* ctx, F&& f) {
     f();
     return 0;
   } catch (const std::exception& e) {
-    if (ctx) ctx->c.err = e.what(); else g_create_err = e.what();
+    g_err = e.what();
     cudaGetLastError();
     return 1;
   }
@@ -49,7 +50,7 @@ void zkb200_ctx_destroy(zkb200_ctx* ctx) {
   ctx->c.destroy();
   delete ctx;
 }
-const char* zkb200_last_error(zkb200_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
+const char* zkb200_last_error(zkb200_ctx* ctx) { (void)ctx; return g_err.c_str(); }
 void* zkb200_ctx_stream(zkb200_ctx* ctx) { return (void*)ctx->c.stream; }
 
 int zkb200_setup(zkb200_ctx* ctx, const zkb200_trace* prep, int n, uint32_t pc_start, const uint32_t* init_global_sum,

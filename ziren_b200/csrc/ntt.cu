@@ -1,23 +1,25 @@
-// K1: batched KoalaBear NTT / coset LDE, column-major.
+// K1: batched KoalaBear NTT / coset LDE over column-major matrices.
 //
-// A transform of length N = 2^logN is a sequence of PASSES; each pass runs small NTTs of size
-// 2^K inside shared-memory tiles (2^K slots x T neighbouring offsets of one column) and applies
-// the four-step twiddle w_L^(i*t) that links it to the next level.  Three pass kinds:
-//   DIF        natural -> bit-reversed, in place         (inverse transform of the evaluations)
-//   DIT        bit-reversed -> natural, in place         (forward transform, inner levels)
-//   DIT_FINAL  last forward level, stores BIT-REVERSED   (the committed LDE row order)
-// so the LDE never needs a separate permutation or transpose pass: evaluations (natural)
-// --DIF,w^-1--> coefficients (bit-reversed) --scale by shift^i / n on load, DIT--> coset
-// evaluations written straight into their bit-reversed rows.  Columns are processed in chunks
-// sized to stay L2-resident (126 MB on B200) between the passes.
+// A transform of length n = 2^(K1+K2) is TWO levels (four-step): a STRIDED level of 2^K1-point
+// NTTs over elements 2^K2 apart, and a CONTIGUOUS level of 2^K2-point NTTs, linked by the twiddle
+// w_n^(k1*t).  Each level runs inside shared-memory tiles; inside a tile every thread keeps 16
+// elements in registers and performs radix-2..16 butterfly rounds there (<= 3 shared-memory round
+// trips for 2^12 points).  The coset LDE is three launches per column chunk and never needs a
+// separate bit-reversal, transpose or scaling pass:
+//   A  strided DIF (inverse twiddles)                       evaluations      -> half-transformed
+//   B  contiguous DIF  ->  x shift_c^i / n  ->  contiguous DIT, once per coset c (fused in smem)
+//   C  strided DIT with the BIT-REVERSED store of the committed row order
+// (n <= 2^12: B alone, storing bit-reversed).  Column chunks are sized so that the traffic
+// between A, B and C stays in the 126 MB L2: HBM sees ~ read n + write 2n per column.
 #include "ntt.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace zkb {
 
 static constexpr int TW_SPLIT = 12;
-static constexpr int MAX_TILE_LOG = 13;   // 8192 elements = 32 KB (+ padding) per CTA
-static constexpr int NTT_THREADS = 256;
+static constexpr int KMAX = 12;             // largest in-tile transform
+static constexpr int ELEMS_PER_THREAD = 16;
 
 __global__ void tw_init_kernel(u32* lo, u32* hi) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -26,214 +28,441 @@ __global__ void tw_init_kernel(u32* lo, u32* hi) {
   lo[i] = fp_pow(w, (u64)i).v;
   hi[i] = fp_pow(w, (u64)i << TW_SPLIT).v;
 }
+// Shoup pair of a Montgomery-form constant c: (w, w') with w = canonical(c), w' = floor(w 2^32 / p).
+// For any 32-bit a:  a*w - umulhi(a, w')*p  lies in [0, 2p) and is = a*w (mod p); with `a` a
+// Montgomery residue the product is again a Montgomery residue.
+__device__ __forceinline__ uint2 shoup_pair(Fp c) {
+  u32 w = fp_to_canonical(c);
+  return make_uint2(w, (u32)((((u64)w) << 32) / KB_P));
+}
+__device__ __forceinline__ Fp shoup_mul(u32 a, uint2 w) {
+  u32 q = __umulhi(a, w.y);
+  u32 r = a * w.x - q * KB_P;
+  u32 t = r - KB_P;
+  return fp_raw(t < r ? t : r);
+}
+
+// small[dir][K] : w_{2^K}^(+-e), e < 2^(K-1), as Shoup pairs (K <= KMAX_TAB)
+static constexpr int KMAX_TAB = 12;
+__global__ void small_tw_kernel(uint2* out, const u32* lo, const u32* hi) {
+  // layout: for dir in {fwd, inv}: for K in 1..12: 2^(K-1) entries at offset (2^(K-1) - 1)
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 per_dir = (1u << KMAX_TAB) - 1;
+  if (i >= 2 * per_dir) return;
+  u32 dir = i / per_dir, r = i % per_dir;
+  int K = 32 - __clz(r + 1);            // r in [2^(K-1)-1, 2^K-1)
+  u32 e = r - ((1u << (K - 1)) - 1);
+  u32 E = e << (24 - K);
+  if (dir) E = (0u - E) & ((1u << 24) - 1);
+  out[i] = shoup_pair(tw_pow2(lo, hi, E));
+}
 void NttTables::init(cudaStream_t s) {
   ZKB_CUDA(cudaMalloc((void**)&tw_lo, sizeof(u32) << TW_SPLIT));
   ZKB_CUDA(cudaMalloc((void**)&tw_hi, sizeof(u32) << TW_SPLIT));
   tw_init_kernel<<<(1 << TW_SPLIT) / 256, 256, 0, s>>>(tw_lo, tw_hi);
   ZKB_CHECK_LAUNCH();
+  const u32 cnt = 2 * ((1u << KMAX_TAB) - 1);
+  ZKB_CUDA(cudaMalloc((void**)&small_tw, cnt * sizeof(uint2)));
+  small_tw_kernel<<<ceil_div(cnt, 256), 256, 0, s>>>((uint2*)small_tw, tw_lo, tw_hi);
+  ZKB_CHECK_LAUNCH();
 }
 void NttTables::destroy() {
   if (tw_lo) cudaFree(tw_lo);
   if (tw_hi) cudaFree(tw_hi);
-  tw_lo = tw_hi = nullptr;
+  if (small_tw) cudaFree(small_tw);
+  for (auto& kv : four_step) cudaFree(kv.second);
+  for (auto& kv : scale_cache) cudaFree(kv.second);
+  four_step.clear(); scale_cache.clear(); scale_cache_bytes = 0;
+  tw_lo = tw_hi = nullptr; small_tw = nullptr;
 }
 
-// w^E for E in [0, 2^24)
-__device__ __forceinline__ Fp tw_pow(const u32* __restrict__ lo, const u32* __restrict__ hi, u32 E) {
-  return fp_raw(__ldg(hi + (E >> TW_SPLIT))) * fp_raw(__ldg(lo + (E & ((1u << TW_SPLIT) - 1))));
+// four-step twiddle of the element stored at position o*S + t of a 2^(K1+K2) column:
+// w_n^(+-bitrev_K1(o) * t), as a Shoup pair, indexed by the position itself (coalesced, L2-resident)
+__global__ void four_step_kernel(uint2* out, int K1, int logS, int inverse, const u32* lo, const u32* hi) {
+  const u32 logn = K1 + logS;
+  size_t pos = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (pos >= ((size_t)1 << logn)) return;
+  u32 o = (u32)(pos >> logS), t = (u32)pos & ((1u << logS) - 1);
+  u32 e = (bitrev32(o, K1) * t) & ((1u << logn) - 1);
+  u32 E = e << (24 - logn);
+  if (inverse) E = (0u - E) & ((1u << 24) - 1);
+  out[pos] = shoup_pair(tw_pow2(lo, hi, E));
+}
+const void* NttTables::four_step_table(int K1, int logS, bool inverse, cudaStream_t s) const {
+  const int key = ((K1 + logS) << 1) | (inverse ? 1 : 0);
+  auto it = four_step.find(key);
+  if (it != four_step.end()) return it->second;
+  const size_t n = (size_t)1 << (K1 + logS);
+  void* p = nullptr;
+  ZKB_CUDA(cudaMalloc(&p, n * sizeof(uint2)));
+  four_step_kernel<<<ceil_div(n, 256), 256, 0, s>>>((uint2*)p, K1, logS, inverse ? 1 : 0, tw_lo, tw_hi);
+  ZKB_CHECK_LAUNCH();
+  four_step[key] = p;
+  return p;
 }
 
-enum PassKind { PASS_DIF = 0, PASS_DIT = 1, PASS_DIT_FINAL = 2 };
+// ---- in-register butterfly rounds --------------------------------------------------------------
+// x[m] holds slot (base | m << lo) of a 2^K-point transform; bl = base & (2^lo - 1).
+// tw[e] = w_{2^K}^(+-e), e < 2^(K-1).
+template <int R, bool DIF>
+__device__ __forceinline__ void butterflies(Fp* x, u32 bl, int lo, int K, const uint2* __restrict__ tw) {
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    const int lh = DIF ? (R - 1 - j) : j;   // log2(half) in m-space
+    const int sh = K - 1 - lo - lh;         // slot-space half is 2^(lo+lh)
+    const u32 tbase = bl << sh;
+#pragma unroll
+    for (int p = 0; p < (1 << (R - 1)); p++) {
+      const int k = p & ((1 << lh) - 1);
+      const int m0 = ((p >> lh) << (lh + 1)) | k;
+      const int m1 = m0 + (1 << lh);
+      const uint2 w = tw[tbase + ((u32)k << (lo + sh))];
+      if (DIF) {
+        Fp a = x[m0], b = x[m1];
+        x[m0] = a + b;
+        x[m1] = shoup_mul(a.v - b.v + KB_P, w);     // a - b + p in (0, 2p): any u32 is fine
+      } else {
+        Fp t = shoup_mul(x[m1].v, w);
+        x[m1] = x[m0] - t;
+        x[m0] = x[m0] + t;
+      }
+    }
+  }
+}
 
-struct PassArgs {
-  const u32* in;
-  u32* out;
-  size_t in_stride, out_stride;  // elements between columns
-  const u32* tw_lo;
-  const u32* tw_hi;
-  const u32* scale_a;            // optional load scaling: f(p) = a[p & mask] * b[p >> split]
-  const u32* scale_b;
-  int scale_split;
-  int K, logS, logT, logN;
-  int kind, inverse, contig;
+// One round over bits [lo, lo+R) of the slot index for the whole tile held in `sm`.
+// Layouts: strided tiles  addr(slot, q) = slot * (T+1) + q           (lanes run along q)
+//          contig tiles   addr(slot, q) = q * ldg + slot + slot/8    (lanes run along slot)
+template <int R, bool DIF, bool CONTIG>
+__device__ __forceinline__ void tile_round(u32* sm, int K, int logT, int lo, const uint2* __restrict__ tw, u32 ldg) {
+  constexpr int G = ELEMS_PER_THREAD >> R;   // groups per thread
+  const u32 T = 1u << logT;
+  const u32 ngroups = 1u << (K - R + logT);
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    u32 gi = g * blockDim.x + threadIdx.x;
+    if (gi >= ngroups) break;
+    u32 rest, q;
+    if (CONTIG) { rest = gi & ((1u << (K - R)) - 1); q = gi >> (K - R); }
+    else { q = gi & (T - 1); rest = gi >> logT; }
+    const u32 bl = rest & ((1u << lo) - 1);
+    const u32 base = ((rest >> lo) << (lo + R)) | bl;
+    Fp x[1 << R];
+#pragma unroll
+    for (int m = 0; m < (1 << R); m++) {
+      u32 slot = base | ((u32)m << lo);
+      x[m] = fp_raw(sm[CONTIG ? (q * ldg + slot + (slot >> 3)) : (slot * (T + 1) + q)]);
+    }
+    butterflies<R, DIF>(x, bl, lo, K, tw);
+#pragma unroll
+    for (int m = 0; m < (1 << R); m++) {
+      u32 slot = base | ((u32)m << lo);
+      sm[CONTIG ? (q * ldg + slot + (slot >> 3)) : (slot * (T + 1) + q)] = x[m].v;
+    }
+  }
+}
+
+// full 2^K-point transform of every (q) of the tile: DIF natural -> bit-reversed slots,
+// DIT bit-reversed -> natural slots.  Rounds of radix <= 16, evenly split.
+template <bool DIF, bool CONTIG>
+__device__ __forceinline__ void tile_transform(u32* sm, int K, int logT, const uint2* __restrict__ tw, u32 ldg) {
+  const int nr = (K + 3) / 4;
+  int done = 0;
+  for (int r = 0; r < nr; r++) {
+    const int R = K / nr + (r < K % nr ? 1 : 0);
+    const int lo = DIF ? (K - done - R) : done;
+    switch (R) {
+      case 1: tile_round<1, DIF, CONTIG>(sm, K, logT, lo, tw, ldg); break;
+      case 2: tile_round<2, DIF, CONTIG>(sm, K, logT, lo, tw, ldg); break;
+      case 3: tile_round<3, DIF, CONTIG>(sm, K, logT, lo, tw, ldg); break;
+      default: tile_round<4, DIF, CONTIG>(sm, K, logT, lo, tw, ldg); break;
+    }
+    done += R;
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void fill_small_twiddles(uint2* tw, int K, bool inverse, const uint2* __restrict__ small_tw) {
+  const u32 half = 1u << (K - 1);
+  const uint2* src = small_tw + (inverse ? ((1u << KMAX_TAB) - 1) : 0) + (half - 1);
+  for (u32 m = threadIdx.x; m < half; m += blockDim.x) tw[m] = src[m];
+}
+
+// ---- strided level -----------------------------------------------------------------------------
+struct StridedArgs {
+  const u32* in; u32* out;
+  size_t in_stride, out_stride;      // elements between columns
+  const uint2* small_tw;
+  const uint2* four;                 // four-step twiddles indexed by element position
+  int K, logS, logT;                 // n = 2^(K+logS)
+  int inverse;
+  int final_dit;                     // 0: DIF with post-twiddle, in-place positions
+                                     // 1: DIT (pre-twiddle) storing bit-reversed positions
+  size_t out_coset_stride;           // final_dit: blockIdx.z selects the coset block of in/out
+  size_t in_coset_stride;
 };
 
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassArgs a) {
-  extern __shared__ u32 smem[];
+__global__ void __launch_bounds__(1024, 1) ntt_strided_kernel(StridedArgs a) {
+  extern __shared__ __align__(16) u32 smem[];
   const int K = a.K, logT = a.logT, logS = a.logS;
   const u32 nslot = 1u << K, T = 1u << logT;
-  const u32 half_n = nslot >> 1;
-  u32* tw = smem;                      // 2^(K-1) small twiddles
-  u32* data = smem + (half_n ? half_n : 1);
-  const u32 row = a.contig ? (nslot + 1) : (T + 1);   // padded leading dimension
+  uint2* tw = reinterpret_cast<uint2*>(smem);
+  u32* data = smem + nslot;           // 2^(K-1) uint2 twiddles = nslot words
   const u32 tile_elems = nslot << logT;
-  const u32* __restrict__ in = a.in + (size_t)blockIdx.y * a.in_stride;
-  u32* __restrict__ out = a.out + (size_t)blockIdx.y * a.out_stride;
-  const u32 logL = K + logS;
-  const u32 mask24 = (1u << 24) - 1;
+  const u32* __restrict__ in = a.in + (size_t)blockIdx.y * a.in_stride + (size_t)blockIdx.z * a.in_coset_stride;
+  u32* __restrict__ out = a.out + (size_t)blockIdx.y * a.out_stride + (size_t)blockIdx.z * a.out_coset_stride;
+  fill_small_twiddles(tw, K, a.inverse, a.small_tw);
+  const u32 t0 = blockIdx.x << logT;   // offsets t0 .. t0+T-1
 
-  // small twiddles w_{2^K}^(+-m)
-  for (u32 m = threadIdx.x; m < half_n; m += blockDim.x) {
-    u32 E = m << (24 - K);
-    if (a.inverse) E = (0u - E) & mask24;
-    tw[m] = tw_pow(a.tw_lo, a.tw_hi, E).v;
-  }
-
-  // tile origin: flat offset index f0 = tile * T enumerates (sub-problem, t) pairs
-  const u32 f0 = blockIdx.x << logT;
-  u32 base, t0;
-  if (a.contig) { base = f0 << K; t0 = 0; }            // S == 1: T consecutive groups
-  else { u32 sub = f0 >> logS; t0 = f0 & ((1u << logS) - 1); base = (sub << logL) + t0; }
-
-  // ---- load (+ optional scaling, + pre-twiddle for DIT kinds) ----
-  for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
-    u32 j, q, pos;
-    if (a.contig) { j = i & (nslot - 1); q = i >> K; pos = base + i; }
-    else { q = i & (T - 1); j = i >> logT; pos = base + (j << logS) + q; }
-    Fp v = fp_raw(in[pos]);
-    if (a.scale_a) {
-      Fp f = fp_raw(__ldg(a.scale_a + (pos & ((1u << a.scale_split) - 1)))) * fp_raw(__ldg(a.scale_b + (pos >> a.scale_split)));
-      v = v * f;
-    }
-    u32 slot = j;
-    if (a.kind != PASS_DIF) {
-      u32 ilo = bitrev32(j, K);
-      u32 t = a.contig ? 0 : (t0 + q);
-      if (logS) {
-        u32 e = (ilo * t) & ((1u << logL) - 1);
-        u32 E = e << (24 - logL);
-        if (a.inverse) E = (0u - E) & mask24;
-        v = v * tw_pow(a.tw_lo, a.tw_hi, E);
+  // loads are issued in batches of 8 per thread so that 8 independent requests are in flight
+#pragma unroll
+  for (int h = 0; h < ELEMS_PER_THREAD; h += 8) {
+    u32 v[8];
+    uint2 w[8];
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const u32 i = (h + it) * blockDim.x + threadIdx.x;
+      if (i < tile_elems) {
+        const size_t pos = ((size_t)(i >> logT) << logS) + t0 + (i & (T - 1));
+        v[it] = in[pos];
+        if (a.final_dit) w[it] = __ldg(a.four + pos);
       }
-      if (a.kind == PASS_DIT_FINAL) slot = ilo;
     }
-    data[a.contig ? (q * row + slot) : (slot * row + q)] = v.v;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const u32 i = (h + it) * blockDim.x + threadIdx.x;
+      if (i < tile_elems) {
+        const u32 q = i & (T - 1), j = i >> logT;
+        u32 x = v[it], slot = j;
+        if (a.final_dit) { x = shoup_mul(x, w[it]).v; slot = bitrev32(j, K); }
+        data[slot * (T + 1) + q] = x;
+      }
+    }
   }
   __syncthreads();
+  // both kinds run the DIF network: natural slots in, bit-reversed slots out
+  tile_transform<true, false>(data, K, logT, tw, 0);
 
-  // ---- butterfly network over the slot dimension ----
-  const u32 n_bf = half_n << logT;
-  const bool dif = (a.kind != PASS_DIT);
-  for (int s = 0; s < K; s++) {
-    const u32 lh = dif ? (K - 1 - s) : s;       // log2(half)
-    const u32 half = 1u << lh;
-    for (u32 i = threadIdx.x; i < n_bf; i += blockDim.x) {
-      u32 bf, q;
-      if (a.contig) { bf = i & (half_n - 1); q = i >> (K - 1); }
-      else { q = i & (T - 1); bf = i >> logT; }
-      u32 k = bf & (half - 1);
-      u32 j0 = ((bf >> lh) << (lh + 1)) + k, j1 = j0 + half;
-      u32 i0 = a.contig ? (q * row + j0) : (j0 * row + q);
-      u32 i1 = a.contig ? (q * row + j1) : (j1 * row + q);
-      Fp w = fp_raw(tw[k << (K - 1 - lh)]);
-      Fp x = fp_raw(data[i0]), y = fp_raw(data[i1]);
-      if (dif) { data[i0] = (x + y).v; data[i1] = ((x - y) * w).v; }
-      else { Fp yw = y * w; data[i0] = (x + yw).v; data[i1] = (x - yw).v; }
+  if (a.final_dit) {
+    // slot o holds k_hi = bitrev_K(o); natural index k_hi*S + t lands at bitrev_logS(t) * 2^K + o
+    for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
+      const u32 o = i & (nslot - 1), q = i >> K;
+      const size_t pos = ((size_t)bitrev32(t0 + q, logS) << K) + o;
+      out[pos] = data[o * (T + 1) + q];
+    }
+  } else {
+#pragma unroll
+    for (int h = 0; h < ELEMS_PER_THREAD; h += 8) {
+      uint2 w[8];
+#pragma unroll
+      for (int it = 0; it < 8; it++) {
+        const u32 i = (h + it) * blockDim.x + threadIdx.x;
+        if (i < tile_elems) w[it] = __ldg(a.four + (((size_t)(i >> logT) << logS) + t0 + (i & (T - 1))));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; it++) {
+        const u32 i = (h + it) * blockDim.x + threadIdx.x;
+        if (i < tile_elems) {
+          const u32 q = i & (T - 1), o = i >> logT;
+          out[((size_t)o << logS) + t0 + q] = shoup_mul(data[o * (T + 1) + q], w[it]).v;
+        }
+      }
+    }
+  }
+}
+
+// ---- contiguous level (optionally fused inverse -> scale -> forward per coset) --------------------
+struct ContigArgs {
+  const u32* in; u32* out;
+  size_t in_stride, out_stride;      // elements between columns
+  const uint2* small_tw;
+  int K, logT, logn;                 // groups of 2^K contiguous elements; column length 2^logn
+  u32 total_groups;                  // ncols * 2^(logn-K)
+  int mode;                          // 0: DIF only (inverse flag applies)
+                                     // 1: DIF(inverse) -> scale_c -> DIT(forward), per coset
+  int inverse;
+  int ncoset;
+  int bitrev_store;                  // mode 1, single level (K == logn): store bit-reversed rows
+  const uint2* scale;                // per coset: n Shoup pairs, shift_c^bitrev(p) / n at position p
+  size_t out_coset_stride;           // element offset between coset outputs
+};
+
+__global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
+  extern __shared__ __align__(16) u32 smem[];
+  const int K = a.K, logT = a.logT;
+  const u32 nslot = 1u << K, T = 1u << logT;
+  const u32 ldg = nslot + (nslot >> 3) + 1;
+  uint2* tw_a = reinterpret_cast<uint2*>(smem);            // first transform's twiddles (nslot words)
+  uint2* tw_b = reinterpret_cast<uint2*>(smem + nslot);    // forward twiddles for the fused DIT
+  u32* bufA = smem + 2 * nslot;
+  u32* bufB = bufA + (size_t)T * ldg;
+  const u32 tile_elems = nslot << logT;
+  const int sub_bits = a.logn - K;                 // groups per column = 2^sub_bits
+  fill_small_twiddles(tw_a, K, a.mode == 1 ? true : (a.inverse != 0), a.small_tw);
+  if (a.mode == 1) fill_small_twiddles(tw_b, K, false, a.small_tw);
+  const u32 f0 = blockIdx.x << logT;
+
+#pragma unroll
+  for (int h = 0; h < ELEMS_PER_THREAD; h += 8) {
+    u32 v[8];
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const u32 i = (h + it) * blockDim.x + threadIdx.x;
+      v[it] = 0;
+      if (i < tile_elems) {
+        const u32 slot = i & (nslot - 1), f = f0 + (i >> K);
+        if (f < a.total_groups) v[it] = a.in[(size_t)(f >> sub_bits) * a.in_stride + ((size_t)(f & ((1u << sub_bits) - 1)) << K) + slot];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const u32 i = (h + it) * blockDim.x + threadIdx.x;
+      if (i < tile_elems) { const u32 slot = i & (nslot - 1), q = i >> K; bufA[q * ldg + slot + (slot >> 3)] = v[it]; }
+    }
+  }
+  __syncthreads();
+  tile_transform<true, true>(bufA, K, logT, tw_a, ldg);
+
+  if (a.mode == 0) {
+    for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
+      const u32 slot = i & (nslot - 1), q = i >> K;
+      const u32 f = f0 + q;
+      if (f >= a.total_groups) continue;
+      const size_t col = f >> sub_bits, sub = f & ((1u << sub_bits) - 1);
+      a.out[col * a.out_stride + (sub << K) + slot] = bufA[q * ldg + slot + (slot >> 3)];
+    }
+    return;
+  }
+
+  for (int c = 0; c < a.ncoset; c++) {
+    const uint2* __restrict__ sc = a.scale + ((size_t)c << a.logn);
+    // coefficient at bit-reversed position p gets shift_c^bitrev(p) / n
+#pragma unroll
+    for (int h = 0; h < ELEMS_PER_THREAD; h += 8) {
+      uint2 w[8];
+#pragma unroll
+      for (int it = 0; it < 8; it++) {
+        const u32 i = (h + it) * blockDim.x + threadIdx.x;
+        if (i < tile_elems) w[it] = __ldg(sc + ((((f0 + (i >> K)) & ((1u << sub_bits) - 1)) << K) + (i & (nslot - 1))));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; it++) {
+        const u32 i = (h + it) * blockDim.x + threadIdx.x;
+        if (i < tile_elems) {
+          const u32 slot = i & (nslot - 1), q = i >> K;
+          const u32 ad = q * ldg + slot + (slot >> 3);
+          bufB[ad] = shoup_mul(bufA[ad], w[it]).v;
+        }
+      }
+    }
+    __syncthreads();
+    tile_transform<false, true>(bufB, K, logT, tw_b, ldg);
+    u32* __restrict__ outc = a.out + (size_t)c * a.out_coset_stride;
+    for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
+      const u32 o = i & (nslot - 1), q = i >> K;
+      const u32 f = f0 + q;
+      if (f >= a.total_groups) continue;
+      const size_t col = f >> sub_bits, sub = f & ((1u << sub_bits) - 1);
+      // bit-reversed store only happens when the whole column is one group
+      const u32 src = a.bitrev_store ? bitrev32(o, K) : o;
+      outc[col * a.out_stride + (sub << K) + o] = bufB[q * ldg + src + (src >> 3)];
     }
     __syncthreads();
   }
-
-  // ---- store (+ post-twiddle for DIF) ----
-  if (a.kind == PASS_DIT_FINAL) {
-    // slot o holds output k_hi = bitrev_K(o); natural index k_hi * S + t lands at
-    // bitrev_logN = bitrev_logS(t) * 2^K + o  -> contiguous runs over o
-    for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
-      u32 o = i & (nslot - 1), q = i >> K;
-      u32 t = a.contig ? 0 : (t0 + q);
-      u32 pos = (bitrev32(t, logS) << K) + o;
-      if (a.contig) pos += (f0 + q) << K;  // only reachable with a single group (logS == 0, logN == K)
-      out[pos] = data[a.contig ? (q * row + o) : (o * row + q)];
-    }
-  } else {
-    for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
-      u32 o, q, pos;
-      if (a.contig) { o = i & (nslot - 1); q = i >> K; pos = base + i; }
-      else { q = i & (T - 1); o = i >> logT; pos = base + (o << logS) + q; }
-      Fp v = fp_raw(data[a.contig ? (q * row + o) : (o * row + q)]);
-      if (a.kind == PASS_DIF && logS) {
-        u32 k1 = bitrev32(o, K);
-        u32 e = (k1 * (t0 + q)) & ((1u << logL) - 1);
-        u32 E = e << (24 - logL);
-        if (a.inverse) E = (0u - E) & mask24;
-        v = v * tw_pow(a.tw_lo, a.tw_hi, E);
-      }
-      out[pos] = v.v;
-    }
-  }
 }
 
-static void launch_pass(const NttTables& tb, const u32* in, size_t in_stride, u32* out, size_t out_stride,
-                        size_t ncols, int logN, int K, int logS, int kind, bool inverse, const u32* scale_a,
-                        const u32* scale_b, int scale_split, cudaStream_t s) {
-  PassArgs a;
+// ---- launch helpers ------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+static void split_levels(int logn, int& K1, int& K2) {
+  if (logn <= KMAX) { K1 = 0; K2 = logn; return; }
+  K2 = (logn + 1) / 2;
+  K1 = logn - K2;
+  if (K2 > KMAX) throw std::runtime_error("zkb200: NTT size out of range");
+}
+
+static void launch_strided(const NttTables& tb, const u32* in, size_t in_stride, u32* out, size_t out_stride, size_t ncols,
+                           int K, int logS, bool inverse, bool final_dit, int ncoset, size_t in_coset_stride,
+                           size_t out_coset_stride, cudaStream_t s) {
+  StridedArgs a;
   a.in = in; a.out = out; a.in_stride = in_stride; a.out_stride = out_stride;
-  a.tw_lo = tb.tw_lo; a.tw_hi = tb.tw_hi;
-  a.scale_a = scale_a; a.scale_b = scale_b; a.scale_split = scale_split;
-  a.K = K; a.logS = logS; a.logN = logN; a.kind = kind; a.inverse = inverse ? 1 : 0;
-  const int log_groups = logN - K;        // number of (sub, t) pairs per column
-  a.contig = (logS == 0) ? 1 : 0;
-  int logT = MAX_TILE_LOG - K;
+  a.small_tw = (const uint2*)tb.small_tw;
+  a.four = (const uint2*)tb.four_step_table(K, logS, inverse, s);
+  a.K = K; a.logS = logS; a.inverse = inverse ? 1 : 0; a.final_dit = final_dit ? 1 : 0;
+  a.in_coset_stride = in_coset_stride; a.out_coset_stride = out_coset_stride;
+  int logT = 14 - K;                             // 16384 elements per tile, 32 offsets for K <= 9
+  if (logT > 5) logT = 5;
+  if (logT > logS) logT = logS;
   if (logT < 0) logT = 0;
-  if (a.contig) { if (logT > log_groups) logT = log_groups; if (kind == PASS_DIT_FINAL) logT = 0; }
-  else if (logT > logS) logT = logS;
   a.logT = logT;
-  size_t row = a.contig ? ((1u << K) + 1) : ((1u << logT) + 1);
-  size_t rows = a.contig ? (1u << logT) : (1u << K);
-  size_t smem = (((1u << K) >> 1) + 1 + row * rows) * sizeof(u32);
-  dim3 grid(1u << (log_groups - logT), (unsigned)ncols);
-  ntt_pass_kernel<<<grid, NTT_THREADS, smem, s>>>(a);
+  const size_t tile_elems = (size_t)1 << (K + logT);
+  unsigned threads = (unsigned)std::max<size_t>(32, tile_elems / ELEMS_PER_THREAD);
+  size_t smem = (((size_t)1 << K) + ((size_t)1 << K) * (((size_t)1 << logT) + 1)) * sizeof(u32);
+  static bool attr_done = false;
+  if (!attr_done) {
+    ZKB_CUDA(cudaFuncSetAttribute(ntt_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  dim3 grid(1u << (logS - logT), (unsigned)ncols, (unsigned)ncoset);
+  ntt_strided_kernel<<<grid, threads, smem, s>>>(a);
   ZKB_CHECK_LAUNCH();
 }
 
-// split logN into pass sizes, each <= 8 bits, as evenly as possible (first entries larger)
-static std::vector<int> plan_passes(int logN) {
-  std::vector<int> ks;
-  if (logN == 0) return ks;
-  int np = (logN + 7) / 8;
-  for (int i = 0; i < np; i++) ks.push_back(logN / np + (i < logN % np ? 1 : 0));
-  return ks;
-}
-
-// DIF transform (natural -> bit-reversed) of ncols columns; first pass in -> out, rest in place
-static void run_dif(const NttTables& tb, const u32* in, size_t in_stride, u32* out, size_t out_stride, size_t ncols,
-                    int logN, bool inverse, cudaStream_t s) {
-  std::vector<int> ks = plan_passes(logN);
-  int logL = logN;
-  for (size_t p = 0; p < ks.size(); p++) {
-    int K = ks[p], logS = logL - K;
-    launch_pass(tb, p == 0 ? in : out, p == 0 ? in_stride : out_stride, out, out_stride, ncols, logN, K, logS, PASS_DIF,
-                inverse, nullptr, nullptr, 0, s);
-    logL = logS;
+static void launch_contig(const NttTables& tb, ContigArgs a, size_t ncols, cudaStream_t s) {
+  a.small_tw = (const uint2*)tb.small_tw;
+  const int K = a.K;
+  const size_t groups = ncols << (a.logn - K);
+  a.total_groups = (u32)groups;
+  int logT = 13 - K;
+  if (logT < 0) logT = 0;
+  while (logT > 0 && ((size_t)1 << logT) > groups) logT--;
+  a.logT = logT;
+  const size_t tile_elems = (size_t)1 << (K + logT);
+  unsigned threads = (unsigned)std::max<size_t>(32, tile_elems / ELEMS_PER_THREAD);
+  const size_t ldg = ((size_t)1 << K) + (((size_t)1 << K) >> 3) + 1;
+  size_t smem = (((size_t)2 << K) + ((size_t)(a.mode == 1 ? 2 : 1) << logT) * ldg) * sizeof(u32);
+  static bool attr_done = false;
+  if (!attr_done) {
+    ZKB_CUDA(cudaFuncSetAttribute(ntt_contig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
   }
+  unsigned grid = (unsigned)((groups + ((size_t)1 << logT) - 1) >> logT);
+  ntt_contig_kernel<<<grid, threads, smem, s>>>(a);
+  ZKB_CHECK_LAUNCH();
 }
 
-// DIT transform (bit-reversed -> bit-reversed store) with optional load scaling:
-// in -> (scratch, in place) -> out.  `scratch` must hold ncols columns (stride scratch_stride).
-static void run_dit_bitrev_out(const NttTables& tb, const u32* in, size_t in_stride, u32* scratch, size_t scratch_stride,
-                               u32* out, size_t out_stride, size_t ncols, int logN, bool inverse, const u32* scale_a,
-                               const u32* scale_b, int scale_split, cudaStream_t s) {
-  std::vector<int> ks = plan_passes(logN);
-  // DIT runs the levels bottom-up: contiguous groups first, the stride-N/2^K level last
-  std::reverse(ks.begin(), ks.end());
-  int logS = 0;
-  for (size_t p = 0; p < ks.size(); p++) {
-    int K = ks[p];
-    bool last = (p + 1 == ks.size());
-    const u32* src = p == 0 ? in : scratch;
-    size_t src_stride = p == 0 ? in_stride : scratch_stride;
-    launch_pass(tb, src, src_stride, last ? out : scratch, last ? out_stride : scratch_stride, ncols, logN, K, logS,
-                last ? PASS_DIT_FINAL : PASS_DIT, inverse, p == 0 ? scale_a : nullptr, p == 0 ? scale_b : nullptr,
-                scale_split, s);
-    logS += K;
+// scale[c][p] = shift_c^bitrev(p) / n as Shoup pairs; output block c holds coset shift * w_N^bitrev(c)
+__global__ void scale_table_kernel(uint2* out, int logn, int log_blowup, Fp shift, Fp ninv, Fp wN) {
+  const size_t n = (size_t)1 << logn;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= (n << log_blowup)) return;
+  u32 c = (u32)(i >> logn), p = (u32)i & (u32)(n - 1);
+  Fp sh = shift * fp_pow(wN, bitrev32(c, log_blowup));
+  out[i] = shoup_pair(ninv * fp_pow(sh, bitrev32(p, logn)));
+}
+const void* NttTables::scale_table(unsigned log_n, unsigned log_blowup, Fp shift, cudaStream_t s) const {
+  const u64 key = ((u64)shift.v << 16) | (log_n << 4) | log_blowup;
+  auto it = scale_cache.find(key);
+  if (it != scale_cache.end()) return it->second;
+  const size_t count = (size_t)1 << (log_n + log_blowup);
+  if (scale_cache_bytes + count * sizeof(uint2) > ((size_t)1 << 30)) {
+    // callers only hold a table for the duration of stream-ordered launches: drain before freeing
+    ZKB_CUDA(cudaStreamSynchronize(s));
+    for (auto& kv : scale_cache) cudaFree(kv.second);
+    scale_cache.clear(); scale_cache_bytes = 0;
   }
-}
-
-// scale tables for "coefficient at bit-reversed position p gets c * shift^bitrev(p)"
-__global__ void scale_tables_kernel(u32* a, u32* b, int logn, int split, Fp shift, Fp c) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  u32 na = 1u << split, nb = 1u << (logn - split);
-  if (i < na) a[i] = (c * fp_pow(shift, (u64)bitrev32(i, split) << (logn - split))).v;
-  if (i < nb) b[i] = fp_pow(shift, (u64)bitrev32(i, logn - split)).v;
+  void* p = nullptr;
+  ZKB_CUDA(cudaMalloc(&p, count * sizeof(uint2)));
+  Fp ninv = fp_inv(fp_from_canonical((u32)(((size_t)1 << log_n) % KB_P)));
+  scale_table_kernel<<<ceil_div(count, 256), 256, 0, s>>>((uint2*)p, (int)log_n, (int)log_blowup, shift, ninv,
+                                                         two_adic_generator(log_n + log_blowup));
+  ZKB_CHECK_LAUNCH();
+  scale_cache[key] = p;
+  scale_cache_bytes += count * sizeof(uint2);
+  return p;
 }
 
 void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* out, size_t out_stride,
@@ -241,44 +470,40 @@ void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* 
   if (width == 0) return;
   const size_t n = (size_t)1 << log_n;
   const unsigned ncoset = 1u << log_blowup;
-  const int split = (int)(log_n + 1) / 2;
-  // per-coset scale tables
-  DevBuf tabs(((size_t)ncoset) * (((size_t)1 << split) + ((size_t)1 << (log_n - split))), s);
-  const size_t tab_sz = ((size_t)1 << split) + ((size_t)1 << (log_n - split));
-  Fp ninv = fp_inv(fp_from_canonical((u32)(n % KB_P)));
-  Fp wN = two_adic_generator(log_n + log_blowup);
-  for (unsigned c = 0; c < ncoset; c++) {
-    Fp sh = shift * fp_pow(wN, c);
-    u32* ta = tabs.p + c * tab_sz;
-    u32* tbp = ta + ((size_t)1 << split);
-    unsigned cnt = 1u << (split > (int)log_n - split ? split : (int)log_n - split);
-    scale_tables_kernel<<<ceil_div(cnt, 256), 256, 0, s>>>(ta, tbp, (int)log_n, split, sh, ninv);
-    ZKB_CHECK_LAUNCH();
+  if (log_n == 0) {
+    for (unsigned c = 0; c < ncoset; c++)
+      ZKB_CUDA(cudaMemcpy2DAsync(out + c, out_stride * 4, in, in_stride * 4, 4, width, cudaMemcpyDeviceToDevice, s));
+    return;
   }
-  // column chunks of ~32 MB so that pass-to-pass traffic stays in L2
-  size_t chunk = ((size_t)1 << 23) >> log_n;
+  int K1, K2;
+  split_levels((int)log_n, K1, K2);
+  const uint2* scale = (const uint2*)tb.scale_table(log_n, log_blowup, shift, s);
+  // column chunks: keep the A->B->C intermediates L2-resident
+  const size_t chunk_elems = (size_t)1 << std::min(30, std::max(10, env_int("ZKB200_NTT_CHUNK_LOG", 22)));
+  size_t chunk = chunk_elems >> log_n;
   if (chunk < 1) chunk = 1;
   if (chunk > width) chunk = width;
   if (chunk > 32768) chunk = 32768;
-  DevBuf coef(chunk * n, s), scratch(chunk * n, s);
+  const bool two_level = K1 > 0;
+  DevBuf half(two_level ? chunk * n : 0, s), xbuf(two_level ? chunk * n * ncoset : 0, s);
   for (size_t c0 = 0; c0 < width; c0 += chunk) {
-    size_t nc = width - c0 < chunk ? width - c0 : chunk;
-    if (log_n == 0) {
-      // constant columns: every coset evaluation equals the single value
-      for (unsigned c = 0; c < ncoset; c++)
-        ZKB_CUDA(cudaMemcpy2DAsync(out + c0 * out_stride + c, out_stride * 4, in + c0 * in_stride, in_stride * 4, 4, nc,
-                                   cudaMemcpyDeviceToDevice, s));
+    const size_t nc = width - c0 < chunk ? width - c0 : chunk;
+    ContigArgs b;
+    b.K = K2; b.logn = (int)log_n; b.mode = 1; b.inverse = 1; b.ncoset = (int)ncoset;
+    b.scale = scale;
+    if (!two_level) {
+      b.in = in + c0 * in_stride; b.in_stride = in_stride;
+      b.out = out + c0 * out_stride; b.out_stride = out_stride; b.out_coset_stride = n;
+      b.bitrev_store = 1;
+      launch_contig(tb, b, nc, s);
       continue;
     }
-    run_dif(tb, in + c0 * in_stride, in_stride, coef.p, n, nc, (int)log_n, true, s);
-    for (unsigned c = 0; c < ncoset; c++) {
-      u32* ta = tabs.p + c * tab_sz;
-      u32* tbp = ta + ((size_t)1 << split);
-      // coset c (shift * w_N^c) lives in block bitrev(c) of the bit-reversed output
-      size_t blk = bitrev32(c, log_blowup);
-      run_dit_bitrev_out(tb, coef.p, n, scratch.p, n, out + c0 * out_stride + blk * n, out_stride, nc, (int)log_n, false,
-                         ta, tbp, split, s);
-    }
+    launch_strided(tb, in + c0 * in_stride, in_stride, half.p, n, nc, K1, K2, true, false, 1, 0, 0, s);
+    b.in = half.p; b.in_stride = n;
+    b.out = xbuf.p; b.out_stride = n; b.out_coset_stride = chunk * n;
+    b.bitrev_store = 0;
+    launch_contig(tb, b, nc, s);
+    launch_strided(tb, xbuf.p, n, out + c0 * out_stride, out_stride, nc, K1, K2, false, true, (int)ncoset, chunk * n, n, s);
   }
 }
 
@@ -311,15 +536,23 @@ void ntt_batch(const NttTables& tb, const u32* in, u32* out, unsigned log_n, siz
   if (!width) return;
   const size_t n = (size_t)1 << log_n;
   if (log_n == 0) { ZKB_CUDA(cudaMemcpyAsync(out, in, width * 4, cudaMemcpyDeviceToDevice, s)); return; }
+  int K1, K2;
+  split_levels((int)log_n, K1, K2);
   for (size_t c0 = 0; c0 < width; c0 += 32768) {
     size_t nc = width - c0 < 32768 ? width - c0 : 32768;
-    if (bitrev_out) {
-      run_dif(tb, in + c0 * n, n, out + c0 * n, n, nc, (int)log_n, inverse, s);
-    } else {
-      DevBuf tmp(nc * n, s);
-      run_dif(tb, in + c0 * n, n, tmp.p, n, nc, (int)log_n, inverse, s);
-      bitrev_rows(tmp.p, out + c0 * n, log_n, nc, s);
+    DevBuf tmp(bitrev_out ? 0 : nc * n, s);
+    u32* dst = bitrev_out ? out + c0 * n : tmp.p;
+    const u32* src = in + c0 * n;
+    if (K1 > 0) {
+      launch_strided(tb, src, n, dst, n, nc, K1, K2, inverse, false, 1, 0, 0, s);
+      src = dst;
     }
+    ContigArgs b;
+    b.in = src; b.in_stride = n; b.out = dst; b.out_stride = n; b.out_coset_stride = 0;
+    b.K = K2; b.logn = (int)log_n; b.mode = 0; b.inverse = inverse ? 1 : 0; b.ncoset = 1; b.bitrev_store = 0;
+    b.scale = nullptr;
+    launch_contig(tb, b, nc, s);
+    if (!bitrev_out) bitrev_rows(tmp.p, out + c0 * n, log_n, nc, s);
   }
   if (inverse) {
     Fp ninv = fp_inv(fp_from_canonical((u32)(n % KB_P)));

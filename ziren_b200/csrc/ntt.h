@@ -3,6 +3,7 @@
 // TwoAdicFriPcs::commit (reference call sites crates/stark/src/prover.rs:277,403,497 and
 // crates/stark/src/machine.rs:416-417).
 #pragma once
+#include <map>
 #include "common.h"
 
 namespace zkb {
@@ -10,8 +11,14 @@ namespace zkb {
 struct NttTables {
   u32* tw_lo = nullptr;  // w^e, e in [0, 4096)           (w = generator of the 2^24 subgroup)
   u32* tw_hi = nullptr;  // w^(4096 e), e in [0, 4096)
+  void* small_tw = nullptr;                       // Shoup pairs of w_{2^K}^(+-e), K <= 12
+  mutable std::map<int, void*> four_step;         // per (log n, direction): four-step twiddles by position
+  mutable std::map<u64, void*> scale_cache;       // per (log n, blow-up, shift): coset scale factors by position
+  mutable size_t scale_cache_bytes = 0;
   void init(cudaStream_t s);
   void destroy();
+  const void* four_step_table(int K1, int logS, bool inverse, cudaStream_t s) const;
+  const void* scale_table(unsigned log_n, unsigned log_blowup, Fp shift, cudaStream_t s) const;
 };
 
 // Coset LDE of every column: in = evaluations over H_n in natural order (col-major n x w,

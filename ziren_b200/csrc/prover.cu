@@ -18,11 +18,16 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
   ZKB_CUDA(cudaSetDevice(dev));
   machine.parse(desc, n);
   ZKB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  ZKB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
   // keep freed blocks in the stream-ordered pool: shard proofs reuse the same sizes
   cudaMemPool_t pool;
   ZKB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
   unsigned long long thr = ~0ull;
   ZKB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  // never let the pool make the copy stream wait for the compute stream (or vice versa) just to
+  // recycle a block: a fresh block is cheaper than losing the upload/compute overlap
+  int no = 0;
+  ZKB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &no));
   machine.upload();
   tables.init(stream);
   p2_upload_constants();
@@ -40,7 +45,8 @@ void Ctx::destroy() {
   if (d_small) cudaFree(d_small);
   if (h_small) cudaFreeHost(h_small);
   if (stream) cudaStreamDestroy(stream);
-  stream = nullptr;
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  stream = copy_stream = nullptr;
 }
 
 struct StageTimer {
@@ -58,19 +64,22 @@ struct StageTimer {
   }
 };
 
-DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w) {
-  DevMat m(h, w, ctx.stream);
+// Row-major host/device matrix -> column-major device matrix, issued on stream `on`.  The result
+// is released on the compute stream, so `on` must be joined into it before first use.
+DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream_t on) {
+  DevMat m(h, w, on);
+  m.buf.stream = ctx.stream;
   if (h * w == 0) return m;
   cudaPointerAttributes attr;
   bool on_device = false;
   if (cudaPointerGetAttributes(&attr, data) == cudaSuccess) on_device = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
   else cudaGetLastError();
   if (on_device) {
-    transpose_to_colmajor(data, m.d(), h, w, ctx.stream);
+    transpose_to_colmajor(data, m.d(), h, w, on);
   } else {
-    DevBuf stage(h * w, ctx.stream);
-    ZKB_CUDA(cudaMemcpyAsync(stage.p, data, h * w * sizeof(u32), cudaMemcpyHostToDevice, ctx.stream));
-    transpose_to_colmajor(stage.p, m.d(), h, w, ctx.stream);
+    DevBuf stage(h * w, on);
+    ZKB_CUDA(cudaMemcpyAsync(stage.p, data, h * w * sizeof(u32), cudaMemcpyHostToDevice, on));
+    transpose_to_colmajor(stage.p, m.d(), h, w, on);
   }
   return m;
 }
@@ -123,7 +132,7 @@ Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, co
     if (c->prep_width != t.width) throw std::runtime_error("zkb200: setup: preprocessed width mismatch for " + t.name);
     pk->names.push_back(t.name);
     pk->local_only.push_back(c->local_only);
-    pk->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width));
+    pk->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width, ctx.stream));
     shifts.push_back(fp_one());
   }
   if (!prep.empty()) {
@@ -137,23 +146,37 @@ Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, co
 }
 
 Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32* pv, size_t npv) {
-  std::lock_guard<std::mutex> lock(ctx.mu);
   ZKB_CUDA(cudaSetDevice(ctx.device));
-  ctx.arena.reset();
   std::unique_ptr<Shard> sh(new Shard());
   sh->ctx = &ctx;
   std::vector<TraceIn> traces = traces_in;
   sort_traces(traces);
+  if (traces.empty()) throw std::runtime_error("zkb200: commit: no traces");
   std::vector<Fp> shifts;
   for (auto& t : traces) {
     const ChipInfo* c = ctx.machine.find(t.name);
     if (!c) throw std::runtime_error("zkb200: commit: unknown chip " + t.name);
     if (c->main_width != t.width) throw std::runtime_error("zkb200: commit: main width mismatch for " + t.name);
-    sh->names.push_back(t.name);
-    sh->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width));
-    shifts.push_back(fp_one());
   }
-  if (traces.empty()) throw std::runtime_error("zkb200: commit: no traces");
+  // Phase 1 (copy stream, its own lock): host->device upload + layout change.  Another host
+  // thread may hold the compute stream (open of the previous shard) meanwhile, the way the
+  // reference keeps several shards in flight (crates/core/machine/src/utils/prove.rs:487-521).
+  cudaEvent_t uploaded;
+  ZKB_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+  {
+    std::lock_guard<std::mutex> lock(ctx.copy_mu);
+    for (auto& t : traces) {
+      sh->names.push_back(t.name);
+      sh->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width, ctx.copy_stream));
+      shifts.push_back(fp_one());
+    }
+    ZKB_CUDA(cudaEventRecord(uploaded, ctx.copy_stream));
+  }
+  // Phase 2 (compute stream): LDE + Merkle tree
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  ctx.arena.reset();
+  ZKB_CUDA(cudaStreamWaitEvent(ctx.stream, uploaded, 0));
+  cudaEventDestroy(uploaded);
   pcs_commit(ctx, sh->traces, shifts, sh->main);
   sh->public_values.assign(pv, pv + npv);
   return sh.release();

@@ -27,6 +27,8 @@ struct Commit {
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host->device uploads + layout change, overlaps the compute stream
+  std::mutex copy_mu;
   MachineInfo machine;
   NttTables tables;
   ParamArena arena;
@@ -74,7 +76,7 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces, const u32* pv
 std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& shard, u32* challenger34);
 
 // building blocks shared with the micro entry points
-DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w);
+DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream_t on);
 void pcs_commit(Ctx& ctx, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out);
 
 }  // namespace zkb
