@@ -58,7 +58,7 @@ def workload_config(args, case, sample=False):
     return {"workload": names[args.workload], "cycles_per_shard": case.cycles, "cells_per_shard": case.cells,
             "trace_bytes_per_shard": case.trace_bytes, "fri": {"log_blowup": 1, "num_queries": 84, "pow_bits": 16},
             "l2_policy": "inputs larger than L2 (trace bytes >> 126 MB); fresh shard allocations every step",
-            "parallelism": f"shard-per-gpu x{args.gpus}"}
+            "parallelism": f"shard-per-gpu x{args.gpus}", "shards_in_flight_per_gpu": {"value": args.value_threads, "e2e": args.e2e_threads}}
 
 
 class ClockSampler:
@@ -103,6 +103,7 @@ def run_reference(args):
     case = make_case(args, sample=True)
     om = o.OracleMachine(case.machine)
     om.setup(case.prep)
+    o.set_num_threads(os.cpu_count())     # torchrun exports OMP_NUM_THREADS=1; use every host core
     cores = o.num_threads()
     for _ in range(args.warmup if args.warmup < 1 else 1):
         om.prove_shard(case.traces, case.public_values)
@@ -133,6 +134,8 @@ def main():
     ap.add_argument("--sample-log-cpu", type=int, default=14, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--value-threads", type=int, default=2,
+                    help="host threads proving device-resident shards concurrently in the `value` arm (compute lanes)")
     ap.add_argument("--e2e-threads", type=int, default=2,
                     help="host threads calling commit/open concurrently in the e2e arm (the reference keeps "
                          "shard_batch_size shards in flight, prove.rs:487-521): uploads of one shard overlap the open of another")
@@ -214,7 +217,9 @@ def main():
         prove(dev_tr)
     sampler = ClockSampler(args.local_rank)
     sampler.start()
-    ms_dev, proof = timed(dev_tr, args.steps)
+    if args.value_threads > 1:
+        timed(dev_tr, args.value_threads, args.value_threads)
+    ms_dev, proof = timed(dev_tr, args.steps, args.value_threads)
     timed(host_tr, max(args.warmup, args.e2e_threads), args.e2e_threads)      # warm the staging/pool paths of the e2e arm
     ms_e2e, proof2 = timed(host_tr, args.steps, args.e2e_threads)
     clocks = sampler.stop()

@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libzkb200.so")
+LIB_PATH = os.environ.get("ZKB200_LIB", os.path.join(_DIR, "libzkb200.so"))   # override: A/B builds of the same ABI
 
 u32p = C.POINTER(C.c_uint32)
 

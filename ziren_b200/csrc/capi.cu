@@ -51,7 +51,7 @@ void zkb200_ctx_destroy(zkb200_ctx* ctx) {
   delete ctx;
 }
 const char* zkb200_last_error(zkb200_ctx* ctx) { (void)ctx; return g_err.c_str(); }
-void* zkb200_ctx_stream(zkb200_ctx* ctx) { return (void*)ctx->c.stream; }
+void* zkb200_ctx_stream(zkb200_ctx* ctx) { return (void*)ctx->c.lanes[0].stream; }
 
 int zkb200_setup(zkb200_ctx* ctx, const zkb200_trace* prep, int n, uint32_t pc_start, const uint32_t* init_global_sum,
                  uint32_t commit_out[8], zkb200_pk** out) {
@@ -124,64 +124,64 @@ int zkb200_last_stage_times(zkb200_ctx* ctx, const char** names, float* ms, int 
 int zkb200_coset_lde(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, size_t width, unsigned log_blowup,
                      uint32_t shift) {
   return guarded(ctx, [&] {
-    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
     if (log_n + log_blowup > 24) throw std::runtime_error("zkb200: LDE height exceeds 2^24");
     size_t n = (size_t)1 << log_n;
-    coset_lde_batch(ctx->c.tables, in, n, out, n << log_blowup, log_n, width, log_blowup, fp_from_canonical(shift), ctx->c.stream);
+    coset_lde_batch(ctx->c.tables, in, n, out, n << log_blowup, log_n, width, log_blowup, fp_from_canonical(shift), ctx->c.lanes[0].stream);
   });
 }
 int zkb200_ntt(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, size_t width, int inverse, int bitrev_out) {
   return guarded(ctx, [&] {
-    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
     if (log_n > 24) throw std::runtime_error("zkb200: NTT size exceeds 2^24");
-    ntt_batch(ctx->c.tables, in, out, log_n, width, inverse != 0, bitrev_out != 0, ctx->c.stream);
+    ntt_batch(ctx->c.tables, in, out, log_n, width, inverse != 0, bitrev_out != 0, ctx->c.lanes[0].stream);
   });
 }
 int zkb200_mmcs_root(zkb200_ctx* ctx, const uint32_t* const* mats, const unsigned* log_heights, const size_t* widths, int n,
                      uint32_t root_out[8]) {
   return guarded(ctx, [&] {
-    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
-    ctx->c.arena.reset();
+    ctx->c.lanes[0].arena.reset();
     std::vector<MatRef> refs;
     for (int i = 0; i < n; i++) refs.push_back(MatRef{mats[i], (u32)widths[i], log_heights[i]});
     DigestLayers layers;
-    merkle_build(refs, ctx->c.arena, layers, ctx->c.d_small, ctx->c.stream);
-    ZKB_CUDA(cudaMemcpyAsync(ctx->c.h_small, ctx->c.d_small, 32, cudaMemcpyDeviceToHost, ctx->c.stream));
-    ZKB_CUDA(cudaStreamSynchronize(ctx->c.stream));
-    for (int i = 0; i < 8; i++) root_out[i] = fp_to_canonical(fp_raw(ctx->c.h_small[i]));
+    merkle_build(refs, ctx->c.lanes[0].arena, layers, ctx->c.lanes[0].d_small, ctx->c.lanes[0].stream);
+    ZKB_CUDA(cudaMemcpyAsync(ctx->c.lanes[0].h_small, ctx->c.lanes[0].d_small, 32, cudaMemcpyDeviceToHost, ctx->c.lanes[0].stream));
+    ZKB_CUDA(cudaStreamSynchronize(ctx->c.lanes[0].stream));
+    for (int i = 0; i < 8; i++) root_out[i] = fp_to_canonical(fp_raw(ctx->c.lanes[0].h_small[i]));
   });
 }
 int zkb200_poseidon2_permute_batch(zkb200_ctx* ctx, uint32_t* states, size_t n) {
   return guarded(ctx, [&] {
-    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
-    permute_batch(states, n, ctx->c.stream);
+    permute_batch(states, n, ctx->c.lanes[0].stream);
   });
 }
 int zkb200_permutation_trace(zkb200_ctx* ctx, const char* chip, const uint32_t* prep, const uint32_t* main_trace, size_t height,
                              const uint32_t alpha[4], const uint32_t beta[4], uint32_t* out, uint32_t local_sum_out[4]) {
   return guarded(ctx, [&] {
-    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
     const ChipInfo* c = ctx->c.machine.find(chip);
     if (!c) throw std::runtime_error(std::string("zkb200: unknown chip ") + chip);
-    permutation_trace(ctx->c.machine, *c, prep, main_trace, height, ef_from_canon(alpha), ef_from_canon(beta), out, ctx->c.d_small,
-                      ctx->c.stream);
-    ZKB_CUDA(cudaMemcpyAsync(ctx->c.h_small, ctx->c.d_small, 16, cudaMemcpyDeviceToHost, ctx->c.stream));
-    ZKB_CUDA(cudaStreamSynchronize(ctx->c.stream));
-    for (int i = 0; i < 4; i++) local_sum_out[i] = fp_to_canonical(fp_raw(ctx->c.h_small[i]));
+    permutation_trace(ctx->c.machine, *c, prep, main_trace, height, ef_from_canon(alpha), ef_from_canon(beta), out, ctx->c.lanes[0].d_small,
+                      ctx->c.lanes[0].stream);
+    ZKB_CUDA(cudaMemcpyAsync(ctx->c.lanes[0].h_small, ctx->c.lanes[0].d_small, 16, cudaMemcpyDeviceToHost, ctx->c.lanes[0].stream));
+    ZKB_CUDA(cudaStreamSynchronize(ctx->c.lanes[0].stream));
+    for (int i = 0; i < 4; i++) local_sum_out[i] = fp_to_canonical(fp_raw(ctx->c.lanes[0].h_small[i]));
   });
 }
 int zkb200_quotient(zkb200_ctx* ctx, const char* chip, unsigned log_n, const uint32_t* prep_lde, const uint32_t* main_lde,
                     const uint32_t* perm_lde, const uint32_t perm_alpha[4], const uint32_t perm_beta[4], const uint32_t local_sum[4],
                     const uint32_t global_sum[14], const uint32_t alpha[4], const uint32_t* pv, size_t npv, uint32_t* out) {
   return guarded(ctx, [&] {
-    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
-    ctx->c.arena.reset();
+    ctx->c.lanes[0].arena.reset();
     const ChipInfo* c = ctx->c.machine.find(chip);
     if (!c) throw std::runtime_error(std::string("zkb200: unknown chip ") + chip);
     std::vector<u32> pvm(npv ? npv : 1, 0);
@@ -193,48 +193,48 @@ int zkb200_quotient(zkb200_ctx* ctx, const char* chip, unsigned log_n, const uin
     in.perm_alpha = ef_from_canon(perm_alpha); in.perm_beta = ef_from_canon(perm_beta);
     in.local_sum = ef_from_canon(local_sum); in.alpha = ef_from_canon(alpha);
     for (int i = 0; i < 14; i++) in.global_sum[i] = fp_from_canonical(global_sum[i]).v;
-    in.pub_dev = ctx->c.arena.push(pvm.data(), pvm.size());
-    quotient_values(ctx->c.machine, *c, ctx->c.tables, in, out, ctx->c.stream);
-    ZKB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    in.pub_dev = ctx->c.lanes[0].arena.push(pvm.data(), pvm.size());
+    quotient_values(ctx->c.machine, *c, ctx->c.tables, in, out, ctx->c.lanes[0].stream);
+    ZKB_CUDA(cudaStreamSynchronize(ctx->c.lanes[0].stream));
   });
 }
 int zkb200_fri_fold(zkb200_ctx* ctx, const uint32_t* in, size_t m, const uint32_t beta[4], const uint32_t* ro_next, uint32_t* out) {
   return guarded(ctx, [&] {
-    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
-    fri_fold(ctx->c.tables, in, m, ef_from_canon(beta), ro_next, out, ctx->c.stream);
+    fri_fold(ctx->c.tables, in, m, ef_from_canon(beta), ro_next, out, ctx->c.lanes[0].stream);
   });
 }
 int zkb200_grind(zkb200_ctx* ctx, const uint32_t challenger[34], unsigned bits, uint32_t* witness_out) {
   return guarded(ctx, [&] {
-    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
     Challenger ch;
     ch.load(challenger);
     u32 st[16];
     for (int i = 0; i < 16; i++) st[i] = ch.state[i].v;
     for (unsigned i = 0; i < ch.n_in; i++) st[i] = ch.in_buf[i].v;
-    *witness_out = grind_witness(st, ch.n_in, bits, ctx->c.d_small + 8192, ctx->c.stream);
+    *witness_out = grind_witness(st, ch.n_in, bits, ctx->c.lanes[0].d_small + 8192, ctx->c.lanes[0].stream);
   });
 }
 int zkb200_transpose(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t height, size_t width, int to_colmajor) {
   return guarded(ctx, [&] {
-    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
-    if (to_colmajor) transpose_to_colmajor(in, out, height, width, ctx->c.stream);
-    else transpose_to_rowmajor(in, out, height, width, ctx->c.stream);
+    if (to_colmajor) transpose_to_colmajor(in, out, height, width, ctx->c.lanes[0].stream);
+    else transpose_to_rowmajor(in, out, height, width, ctx->c.lanes[0].stream);
   });
 }
 int zkb200_convert(zkb200_ctx* ctx, uint32_t* data, size_t n, int to_montgomery) {
   return guarded(ctx, [&] {
-    std::lock_guard<std::mutex> lock(ctx->c.mu);
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
-    if (to_montgomery) to_monty_inplace(data, n, ctx->c.stream);
-    else from_monty_inplace(data, n, ctx->c.stream);
+    if (to_montgomery) to_monty_inplace(data, n, ctx->c.lanes[0].stream);
+    else from_monty_inplace(data, n, ctx->c.lanes[0].stream);
   });
 }
 int zkb200_sync(zkb200_ctx* ctx) {
-  return guarded(ctx, [&] { ZKB_CUDA(cudaSetDevice(ctx->c.device)); ZKB_CUDA(cudaStreamSynchronize(ctx->c.stream)); });
+  return guarded(ctx, [&] { ZKB_CUDA(cudaSetDevice(ctx->c.device)); ZKB_CUDA(cudaDeviceSynchronize()); });
 }
 
 }  // extern "C"

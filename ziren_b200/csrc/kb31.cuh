@@ -32,18 +32,49 @@ KB_HD Fp fp_raw(u32 v) { Fp r; r.v = v; return r; }
 KB_HD Fp fp_zero() { return fp_raw(0); }
 KB_HD Fp fp_one() { return fp_raw(KB_ONE); }
 
+// m = lo * p^-1 mod 2^32.  p^-1 = 2^31 + 2^24 + 1, so on the device the product is two
+// shift-adds on the ALU pipe instead of an IMAD on the (saturated) FMA-heavy pipe.
+KB_HD u32 mont_m(u32 lo) {
+#if defined(__CUDA_ARCH__) && !defined(ZKB_MONT_IMAD)
+  return lo + (lo << 24) + (lo << 31);
+#else
+  return lo * KB_PINV;
+#endif
+}
 KB_HD u32 mont_reduce(u64 x) {
   // x < p * 2^32.  m = x * p^-1 mod 2^32;  (x - m*p) / 2^32  in (-p, p)
   u32 lo = (u32)x, hi = (u32)(x >> 32);
-  u32 m = lo * KB_PINV;
+  u32 m = mont_m(lo);
 #if defined(__CUDA_ARCH__)
   u32 mp = __umulhi(m, KB_P);
 #else
   u32 mp = (u32)(((u64)m * KB_P) >> 32);
 #endif
-  u32 r = hi - mp;
-  return hi < mp ? r + KB_P : r;
+  u32 r = hi - mp;      // wraps high when negative
+  u32 t = r + KB_P;
+  return t < r ? t : r;  // umin(r, r + p): one fused add-min on sm_100
 }
+// same reduction without the final correction: result in (0, 2p), congruent to x / 2^32
+KB_HD u32 mont_reduce_lazy(u64 x) {
+  u32 lo = (u32)x, hi = (u32)(x >> 32);
+  u32 m = mont_m(lo);
+#if defined(__CUDA_ARCH__)
+  u32 mp = __umulhi(m, KB_P);
+#else
+  u32 mp = (u32)(((u64)m * KB_P) >> 32);
+#endif
+  return hi - mp + KB_P;
+}
+// reduction of a sum of up to four products of residues (x < 4 p^2 < 2 p 2^32): one conditional
+// subtraction of p * 2^32 on the high word, then the usual reduction
+KB_HD u32 mont_reduce_wide(u64 x) {
+  u32 hi = (u32)(x >> 32);
+  u32 h2 = hi - KB_P;
+  hi = h2 < hi ? h2 : hi;
+  return mont_reduce(((u64)hi << 32) | (u32)x);
+}
+// a * b with a < 2p, b < p (product < p * 2^32)
+KB_HD u32 mont_mul_raw(u32 a, u32 b) { return mont_reduce((u64)a * b); }
 KB_HD Fp operator*(Fp a, Fp b) { return fp_raw(mont_reduce((u64)a.v * b.v)); }
 KB_HD Fp operator+(Fp a, Fp b) {
   u32 s = a.v + b.v;
@@ -97,6 +128,23 @@ KB_HD Ef operator*(const Ef& a, const Ef& b) {
   r.c[3] = a.c[0] * b.c[3] + a.c[1] * b.c[2] + a.c[2] * b.c[1] + a.c[3] * b.c[0];
   return r;
 }
+// Lazy EF accumulator: sums of (EF x base) products kept as raw 64-bit sums, reduced every
+// fourth product.  acc.add(w, x) costs 4 multiply-accumulates instead of 4 modular multiply-adds.
+struct EfAcc {
+  u64 raw[4];
+  Fp tot[4];
+  int n;
+  KB_HD void clear() { for (int i = 0; i < 4; i++) { raw[i] = 0; tot[i] = fp_raw(0); } n = 0; }
+  KB_HD void flush() {
+    for (int i = 0; i < 4; i++) { tot[i] = tot[i] + fp_raw(mont_reduce_wide(raw[i])); raw[i] = 0; }
+    n = 0;
+  }
+  KB_HD void add(const Ef& w, Fp x) {
+    for (int i = 0; i < 4; i++) raw[i] += (u64)w.c[i].v * x.v;
+    if (++n == 4) flush();
+  }
+  KB_HD Ef value() { if (n) flush(); Ef r; for (int i = 0; i < 4; i++) r.c[i] = tot[i]; return r; }
+};
 KB_HD Ef& operator+=(Ef& a, const Ef& b) { a = a + b; return a; }
 KB_HD Ef& operator-=(Ef& a, const Ef& b) { a = a - b; return a; }
 KB_HD Ef& operator*=(Ef& a, const Ef& b) { a = a * b; return a; }

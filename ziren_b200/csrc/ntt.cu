@@ -89,6 +89,7 @@ __global__ void four_step_kernel(uint2* out, int K1, int logS, int inverse, cons
   out[pos] = shoup_pair(tw_pow2(lo, hi, E));
 }
 const void* NttTables::four_step_table(int K1, int logS, bool inverse, cudaStream_t s) const {
+  std::lock_guard<std::mutex> lock(mu);
   const int key = ((K1 + logS) << 1) | (inverse ? 1 : 0);
   auto it = four_step.find(key);
   if (it != four_step.end()) return it->second;
@@ -97,26 +98,29 @@ const void* NttTables::four_step_table(int K1, int logS, bool inverse, cudaStrea
   ZKB_CUDA(cudaMalloc(&p, n * sizeof(uint2)));
   four_step_kernel<<<ceil_div(n, 256), 256, 0, s>>>((uint2*)p, K1, logS, inverse ? 1 : 0, tw_lo, tw_hi);
   ZKB_CHECK_LAUNCH();
+  ZKB_CUDA(cudaStreamSynchronize(s));   // published to every lane: must be complete
   four_step[key] = p;
   return p;
 }
 
 // ---- in-register butterfly rounds --------------------------------------------------------------
-// x[m] holds slot (base | m << lo) of a 2^K-point transform; bl = base & (2^lo - 1).
-// tw[e] = w_{2^K}^(+-e), e < 2^(K-1).
-template <int R, bool DIF>
-__device__ __forceinline__ void butterflies(Fp* x, u32 bl, int lo, int K, const uint2* __restrict__ tw) {
+// Everything about a round is a compile-time constant (transform size 2^K, radix 2^R, bit offset
+// LO), so twiddle indices and element offsets fold into immediates.
+// x[m] holds slot (base | m << LO) of a 2^K-point transform; bl = base & (2^LO - 1).
+// tw[e] = Shoup pair of w_{2^K}^(+-e), e < 2^(K-1).
+template <int K, int R, int LO, bool DIF>
+__device__ __forceinline__ void butterflies(Fp* x, u32 bl, const uint2* __restrict__ tw) {
 #pragma unroll
   for (int j = 0; j < R; j++) {
     const int lh = DIF ? (R - 1 - j) : j;   // log2(half) in m-space
-    const int sh = K - 1 - lo - lh;         // slot-space half is 2^(lo+lh)
+    const int sh = K - 1 - LO - lh;         // slot-space half is 2^(LO+lh)
     const u32 tbase = bl << sh;
 #pragma unroll
     for (int p = 0; p < (1 << (R - 1)); p++) {
       const int k = p & ((1 << lh) - 1);
       const int m0 = ((p >> lh) << (lh + 1)) | k;
       const int m1 = m0 + (1 << lh);
-      const uint2 w = tw[tbase + ((u32)k << (lo + sh))];
+      const uint2 w = tw[tbase + ((u32)k << (LO + sh))];
       if (DIF) {
         Fp a = x[m0], b = x[m1];
         x[m0] = a + b;
@@ -130,11 +134,16 @@ __device__ __forceinline__ void butterflies(Fp* x, u32 bl, int lo, int K, const 
   }
 }
 
-// One round over bits [lo, lo+R) of the slot index for the whole tile held in `sm`.
-// Layouts: strided tiles  addr(slot, q) = slot * (T+1) + q           (lanes run along q)
-//          contig tiles   addr(slot, q) = q * ldg + slot + slot/8    (lanes run along slot)
-template <int R, bool DIF, bool CONTIG>
-__device__ __forceinline__ void tile_round(u32* sm, int K, int logT, int lo, const uint2* __restrict__ tw, u32 ldg) {
+// Shared-memory layouts.  Strided tiles: row = slot, 2^logT offsets per row, XOR-swizzled so that
+// both "lanes along q" and "lanes along slot" accesses are conflict-free without padding:
+//   saddr(slot, q) = slot * T + (q ^ (slot & (T-1)))
+// Contiguous tiles: one row per group, addr = q * ldg + slot + slot/8 (lanes run along slot).
+__device__ __forceinline__ u32 saddr(u32 slot, u32 q, int logT) { return (slot << logT) + (q ^ (slot & ((1u << logT) - 1))); }
+__device__ __forceinline__ u32 caddr(u32 slot, u32 q, u32 ldg) { return q * ldg + slot + (slot >> 3); }
+
+// One round over bits [LO, LO+R) of the slot index for the whole tile held in `sm`.
+template <int K, int R, int LO, bool DIF, bool CONTIG>
+__device__ __forceinline__ void tile_round(u32* sm, int logT, const uint2* __restrict__ tw, u32 ldg) {
   constexpr int G = ELEMS_PER_THREAD >> R;   // groups per thread
   const u32 T = 1u << logT;
   const u32 ngroups = 1u << (K - R + logT);
@@ -145,45 +154,49 @@ __device__ __forceinline__ void tile_round(u32* sm, int K, int logT, int lo, con
     u32 rest, q;
     if (CONTIG) { rest = gi & ((1u << (K - R)) - 1); q = gi >> (K - R); }
     else { q = gi & (T - 1); rest = gi >> logT; }
-    const u32 bl = rest & ((1u << lo) - 1);
-    const u32 base = ((rest >> lo) << (lo + R)) | bl;
+    const u32 bl = rest & ((1u << LO) - 1);
+    const u32 base = ((rest >> LO) << (LO + R)) | bl;
     Fp x[1 << R];
 #pragma unroll
     for (int m = 0; m < (1 << R); m++) {
-      u32 slot = base | ((u32)m << lo);
-      x[m] = fp_raw(sm[CONTIG ? (q * ldg + slot + (slot >> 3)) : (slot * (T + 1) + q)]);
+      const u32 slot = base | ((u32)m << LO);
+      x[m] = fp_raw(sm[CONTIG ? caddr(slot, q, ldg) : saddr(slot, q, logT)]);
     }
-    butterflies<R, DIF>(x, bl, lo, K, tw);
+    butterflies<K, R, LO, DIF>(x, bl, tw);
 #pragma unroll
     for (int m = 0; m < (1 << R); m++) {
-      u32 slot = base | ((u32)m << lo);
-      sm[CONTIG ? (q * ldg + slot + (slot >> 3)) : (slot * (T + 1) + q)] = x[m].v;
+      const u32 slot = base | ((u32)m << LO);
+      sm[CONTIG ? caddr(slot, q, ldg) : saddr(slot, q, logT)] = x[m].v;
     }
   }
 }
+
+// rounds of radix <= 16, evenly split: R_r = K/nr + (r < K%nr)
+__host__ __device__ constexpr int round_bits(int K, int r) { return K / ((K + 3) / 4) + (r < K % ((K + 3) / 4) ? 1 : 0); }
 
 // full 2^K-point transform of every (q) of the tile: DIF natural -> bit-reversed slots,
-// DIT bit-reversed -> natural slots.  Rounds of radix <= 16, evenly split.
-template <bool DIF, bool CONTIG>
-__device__ __forceinline__ void tile_transform(u32* sm, int K, int logT, const uint2* __restrict__ tw, u32 ldg) {
-  const int nr = (K + 3) / 4;
-  int done = 0;
-  for (int r = 0; r < nr; r++) {
-    const int R = K / nr + (r < K % nr ? 1 : 0);
-    const int lo = DIF ? (K - done - R) : done;
-    switch (R) {
-      case 1: tile_round<1, DIF, CONTIG>(sm, K, logT, lo, tw, ldg); break;
-      case 2: tile_round<2, DIF, CONTIG>(sm, K, logT, lo, tw, ldg); break;
-      case 3: tile_round<3, DIF, CONTIG>(sm, K, logT, lo, tw, ldg); break;
-      default: tile_round<4, DIF, CONTIG>(sm, K, logT, lo, tw, ldg); break;
-    }
-    done += R;
+// DIT bit-reversed -> natural slots.
+template <int K, bool DIF, bool CONTIG>
+__device__ __forceinline__ void tile_transform(u32* sm, int logT, const uint2* __restrict__ tw, u32 ldg) {
+  constexpr int NR = (K + 3) / 4;
+  constexpr int R0 = round_bits(K, 0);
+  tile_round<K, R0, DIF ? K - R0 : 0, DIF, CONTIG>(sm, logT, tw, ldg);
+  __syncthreads();
+  if constexpr (NR > 1) {
+    constexpr int R1 = round_bits(K, 1);
+    tile_round<K, R1, DIF ? K - R0 - R1 : R0, DIF, CONTIG>(sm, logT, tw, ldg);
     __syncthreads();
+    if constexpr (NR > 2) {
+      constexpr int R2 = round_bits(K, 2);
+      tile_round<K, R2, DIF ? K - R0 - R1 - R2 : R0 + R1, DIF, CONTIG>(sm, logT, tw, ldg);
+      __syncthreads();
+    }
   }
 }
 
-__device__ __forceinline__ void fill_small_twiddles(uint2* tw, int K, bool inverse, const uint2* __restrict__ small_tw) {
-  const u32 half = 1u << (K - 1);
+template <int K>
+__device__ __forceinline__ void fill_small_twiddles(uint2* tw, bool inverse, const uint2* __restrict__ small_tw) {
+  constexpr u32 half = 1u << (K - 1);
   const uint2* src = small_tw + (inverse ? ((1u << KMAX_TAB) - 1) : 0) + (half - 1);
   for (u32 m = threadIdx.x; m < half; m += blockDim.x) tw[m] = src[m];
 }
@@ -194,7 +207,7 @@ struct StridedArgs {
   size_t in_stride, out_stride;      // elements between columns
   const uint2* small_tw;
   const uint2* four;                 // four-step twiddles indexed by element position
-  int K, logS, logT;                 // n = 2^(K+logS)
+  int logS, logT;                    // n = 2^(K+logS)
   int inverse;
   int final_dit;                     // 0: DIF with post-twiddle, in-place positions
                                      // 1: DIT (pre-twiddle) storing bit-reversed positions
@@ -202,16 +215,18 @@ struct StridedArgs {
   size_t in_coset_stride;
 };
 
+template <int K>
 __global__ void __launch_bounds__(1024, 1) ntt_strided_kernel(StridedArgs a) {
   extern __shared__ __align__(16) u32 smem[];
-  const int K = a.K, logT = a.logT, logS = a.logS;
-  const u32 nslot = 1u << K, T = 1u << logT;
+  const int logT = a.logT, logS = a.logS;
+  constexpr u32 nslot = 1u << K;
+  const u32 T = 1u << logT;
   uint2* tw = reinterpret_cast<uint2*>(smem);
   u32* data = smem + nslot;           // 2^(K-1) uint2 twiddles = nslot words
   const u32 tile_elems = nslot << logT;
   const u32* __restrict__ in = a.in + (size_t)blockIdx.y * a.in_stride + (size_t)blockIdx.z * a.in_coset_stride;
   u32* __restrict__ out = a.out + (size_t)blockIdx.y * a.out_stride + (size_t)blockIdx.z * a.out_coset_stride;
-  fill_small_twiddles(tw, K, a.inverse, a.small_tw);
+  fill_small_twiddles<K>(tw, a.inverse, a.small_tw);
   const u32 t0 = blockIdx.x << logT;   // offsets t0 .. t0+T-1
 
   // loads are issued in batches of 8 per thread so that 8 independent requests are in flight
@@ -235,20 +250,20 @@ __global__ void __launch_bounds__(1024, 1) ntt_strided_kernel(StridedArgs a) {
         const u32 q = i & (T - 1), j = i >> logT;
         u32 x = v[it], slot = j;
         if (a.final_dit) { x = shoup_mul(x, w[it]).v; slot = bitrev32(j, K); }
-        data[slot * (T + 1) + q] = x;
+        data[saddr(slot, q, logT)] = x;
       }
     }
   }
   __syncthreads();
   // both kinds run the DIF network: natural slots in, bit-reversed slots out
-  tile_transform<true, false>(data, K, logT, tw, 0);
+  tile_transform<K, true, false>(data, logT, tw, 0);
 
   if (a.final_dit) {
     // slot o holds k_hi = bitrev_K(o); natural index k_hi*S + t lands at bitrev_logS(t) * 2^K + o
     for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
       const u32 o = i & (nslot - 1), q = i >> K;
       const size_t pos = ((size_t)bitrev32(t0 + q, logS) << K) + o;
-      out[pos] = data[o * (T + 1) + q];
+      out[pos] = data[saddr(o, q, logT)];
     }
   } else {
 #pragma unroll
@@ -264,7 +279,7 @@ __global__ void __launch_bounds__(1024, 1) ntt_strided_kernel(StridedArgs a) {
         const u32 i = (h + it) * blockDim.x + threadIdx.x;
         if (i < tile_elems) {
           const u32 q = i & (T - 1), o = i >> logT;
-          out[((size_t)o << logS) + t0 + q] = shoup_mul(data[o * (T + 1) + q], w[it]).v;
+          out[((size_t)o << logS) + t0 + q] = shoup_mul(data[saddr(o, q, logT)], w[it]).v;
         }
       }
     }
@@ -287,19 +302,21 @@ struct ContigArgs {
   size_t out_coset_stride;           // element offset between coset outputs
 };
 
+template <int K>
 __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
   extern __shared__ __align__(16) u32 smem[];
-  const int K = a.K, logT = a.logT;
-  const u32 nslot = 1u << K, T = 1u << logT;
-  const u32 ldg = nslot + (nslot >> 3) + 1;
+  const int logT = a.logT;
+  constexpr u32 nslot = 1u << K;
+  const u32 T = 1u << logT;
+  constexpr u32 ldg = nslot + (nslot >> 3) + 1;
   uint2* tw_a = reinterpret_cast<uint2*>(smem);            // first transform's twiddles (nslot words)
   uint2* tw_b = reinterpret_cast<uint2*>(smem + nslot);    // forward twiddles for the fused DIT
   u32* bufA = smem + 2 * nslot;
   u32* bufB = bufA + (size_t)T * ldg;
   const u32 tile_elems = nslot << logT;
   const int sub_bits = a.logn - K;                 // groups per column = 2^sub_bits
-  fill_small_twiddles(tw_a, K, a.mode == 1 ? true : (a.inverse != 0), a.small_tw);
-  if (a.mode == 1) fill_small_twiddles(tw_b, K, false, a.small_tw);
+  fill_small_twiddles<K>(tw_a, a.mode == 1 ? true : (a.inverse != 0), a.small_tw);
+  if (a.mode == 1) fill_small_twiddles<K>(tw_b, false, a.small_tw);
   const u32 f0 = blockIdx.x << logT;
 
 #pragma unroll
@@ -317,11 +334,11 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
 #pragma unroll
     for (int it = 0; it < 8; it++) {
       const u32 i = (h + it) * blockDim.x + threadIdx.x;
-      if (i < tile_elems) { const u32 slot = i & (nslot - 1), q = i >> K; bufA[q * ldg + slot + (slot >> 3)] = v[it]; }
+      if (i < tile_elems) bufA[caddr(i & (nslot - 1), i >> K, ldg)] = v[it];
     }
   }
   __syncthreads();
-  tile_transform<true, true>(bufA, K, logT, tw_a, ldg);
+  tile_transform<K, true, true>(bufA, logT, tw_a, ldg);
 
   if (a.mode == 0) {
     for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
@@ -329,7 +346,7 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
       const u32 f = f0 + q;
       if (f >= a.total_groups) continue;
       const size_t col = f >> sub_bits, sub = f & ((1u << sub_bits) - 1);
-      a.out[col * a.out_stride + (sub << K) + slot] = bufA[q * ldg + slot + (slot >> 3)];
+      a.out[col * a.out_stride + (sub << K) + slot] = bufA[caddr(slot, q, ldg)];
     }
     return;
   }
@@ -349,14 +366,13 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
       for (int it = 0; it < 8; it++) {
         const u32 i = (h + it) * blockDim.x + threadIdx.x;
         if (i < tile_elems) {
-          const u32 slot = i & (nslot - 1), q = i >> K;
-          const u32 ad = q * ldg + slot + (slot >> 3);
+          const u32 ad = caddr(i & (nslot - 1), i >> K, ldg);
           bufB[ad] = shoup_mul(bufA[ad], w[it]).v;
         }
       }
     }
     __syncthreads();
-    tile_transform<false, true>(bufB, K, logT, tw_b, ldg);
+    tile_transform<K, false, true>(bufB, logT, tw_b, ldg);
     u32* __restrict__ outc = a.out + (size_t)c * a.out_coset_stride;
     for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
       const u32 o = i & (nslot - 1), q = i >> K;
@@ -365,7 +381,7 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
       const size_t col = f >> sub_bits, sub = f & ((1u << sub_bits) - 1);
       // bit-reversed store only happens when the whole column is one group
       const u32 src = a.bitrev_store ? bitrev32(o, K) : o;
-      outc[col * a.out_stride + (sub << K) + o] = bufB[q * ldg + src + (src >> 3)];
+      outc[col * a.out_stride + (sub << K) + o] = bufB[caddr(src, q, ldg)];
     }
     __syncthreads();
   }
@@ -391,7 +407,7 @@ static void launch_strided(const NttTables& tb, const u32* in, size_t in_stride,
   a.in = in; a.out = out; a.in_stride = in_stride; a.out_stride = out_stride;
   a.small_tw = (const uint2*)tb.small_tw;
   a.four = (const uint2*)tb.four_step_table(K, logS, inverse, s);
-  a.K = K; a.logS = logS; a.inverse = inverse ? 1 : 0; a.final_dit = final_dit ? 1 : 0;
+  a.logS = logS; a.inverse = inverse ? 1 : 0; a.final_dit = final_dit ? 1 : 0;
   a.in_coset_stride = in_coset_stride; a.out_coset_stride = out_coset_stride;
   int logT = 14 - K;                             // 16384 elements per tile, 32 offsets for K <= 9
   if (logT > 5) logT = 5;
@@ -400,14 +416,23 @@ static void launch_strided(const NttTables& tb, const u32* in, size_t in_stride,
   a.logT = logT;
   const size_t tile_elems = (size_t)1 << (K + logT);
   unsigned threads = (unsigned)std::max<size_t>(32, tile_elems / ELEMS_PER_THREAD);
-  size_t smem = (((size_t)1 << K) + ((size_t)1 << K) * (((size_t)1 << logT) + 1)) * sizeof(u32);
-  static bool attr_done = false;
-  if (!attr_done) {
-    ZKB_CUDA(cudaFuncSetAttribute(ntt_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
+  size_t smem = (((size_t)1 << K) + ((size_t)1 << (K + logT))) * sizeof(u32);
   dim3 grid(1u << (logS - logT), (unsigned)ncols, (unsigned)ncoset);
-  ntt_strided_kernel<<<grid, threads, smem, s>>>(a);
+  static bool attr_done[KMAX + 1] = {false};
+#define ZKB_STRIDED_CASE(KK)                                                                                              \
+  case KK:                                                                                                                \
+    if (!attr_done[KK]) {                                                                                                 \
+      ZKB_CUDA(cudaFuncSetAttribute(ntt_strided_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));    \
+      attr_done[KK] = true;                                                                                               \
+    }                                                                                                                     \
+    ntt_strided_kernel<KK><<<grid, threads, smem, s>>>(a);                                                                \
+    break;
+  switch (K) {
+    ZKB_STRIDED_CASE(1) ZKB_STRIDED_CASE(2) ZKB_STRIDED_CASE(3) ZKB_STRIDED_CASE(4) ZKB_STRIDED_CASE(5) ZKB_STRIDED_CASE(6)
+    ZKB_STRIDED_CASE(7) ZKB_STRIDED_CASE(8) ZKB_STRIDED_CASE(9) ZKB_STRIDED_CASE(10) ZKB_STRIDED_CASE(11) ZKB_STRIDED_CASE(12)
+    default: throw std::runtime_error("zkb200: strided NTT level out of range");
+  }
+#undef ZKB_STRIDED_CASE
   ZKB_CHECK_LAUNCH();
 }
 
@@ -424,13 +449,22 @@ static void launch_contig(const NttTables& tb, ContigArgs a, size_t ncols, cudaS
   unsigned threads = (unsigned)std::max<size_t>(32, tile_elems / ELEMS_PER_THREAD);
   const size_t ldg = ((size_t)1 << K) + (((size_t)1 << K) >> 3) + 1;
   size_t smem = (((size_t)2 << K) + ((size_t)(a.mode == 1 ? 2 : 1) << logT) * ldg) * sizeof(u32);
-  static bool attr_done = false;
-  if (!attr_done) {
-    ZKB_CUDA(cudaFuncSetAttribute(ntt_contig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
-  }
   unsigned grid = (unsigned)((groups + ((size_t)1 << logT) - 1) >> logT);
-  ntt_contig_kernel<<<grid, threads, smem, s>>>(a);
+  static bool attr_done[KMAX + 1] = {false};
+#define ZKB_CONTIG_CASE(KK)                                                                                               \
+  case KK:                                                                                                                \
+    if (!attr_done[KK]) {                                                                                                 \
+      ZKB_CUDA(cudaFuncSetAttribute(ntt_contig_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));     \
+      attr_done[KK] = true;                                                                                               \
+    }                                                                                                                     \
+    ntt_contig_kernel<KK><<<grid, threads, smem, s>>>(a);                                                                 \
+    break;
+  switch (K) {
+    ZKB_CONTIG_CASE(1) ZKB_CONTIG_CASE(2) ZKB_CONTIG_CASE(3) ZKB_CONTIG_CASE(4) ZKB_CONTIG_CASE(5) ZKB_CONTIG_CASE(6)
+    ZKB_CONTIG_CASE(7) ZKB_CONTIG_CASE(8) ZKB_CONTIG_CASE(9) ZKB_CONTIG_CASE(10) ZKB_CONTIG_CASE(11) ZKB_CONTIG_CASE(12)
+    default: throw std::runtime_error("zkb200: contiguous NTT level out of range");
+  }
+#undef ZKB_CONTIG_CASE
   ZKB_CHECK_LAUNCH();
 }
 
@@ -444,13 +478,14 @@ __global__ void scale_table_kernel(uint2* out, int logn, int log_blowup, Fp shif
   out[i] = shoup_pair(ninv * fp_pow(sh, bitrev32(p, logn)));
 }
 const void* NttTables::scale_table(unsigned log_n, unsigned log_blowup, Fp shift, cudaStream_t s) const {
+  std::lock_guard<std::mutex> lock(mu);
   const u64 key = ((u64)shift.v << 16) | (log_n << 4) | log_blowup;
   auto it = scale_cache.find(key);
   if (it != scale_cache.end()) return it->second;
   const size_t count = (size_t)1 << (log_n + log_blowup);
   if (scale_cache_bytes + count * sizeof(uint2) > ((size_t)1 << 30)) {
     // callers only hold a table for the duration of stream-ordered launches: drain before freeing
-    ZKB_CUDA(cudaStreamSynchronize(s));
+    ZKB_CUDA(cudaDeviceSynchronize());
     for (auto& kv : scale_cache) cudaFree(kv.second);
     scale_cache.clear(); scale_cache_bytes = 0;
   }
@@ -460,6 +495,7 @@ const void* NttTables::scale_table(unsigned log_n, unsigned log_blowup, Fp shift
   scale_table_kernel<<<ceil_div(count, 256), 256, 0, s>>>((uint2*)p, (int)log_n, (int)log_blowup, shift, ninv,
                                                          two_adic_generator(log_n + log_blowup));
   ZKB_CHECK_LAUNCH();
+  ZKB_CUDA(cudaStreamSynchronize(s));
   scale_cache[key] = p;
   scale_cache_bytes += count * sizeof(uint2);
   return p;

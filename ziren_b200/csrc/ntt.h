@@ -4,6 +4,7 @@
 // crates/stark/src/machine.rs:416-417).
 #pragma once
 #include <map>
+#include <mutex>
 #include "common.h"
 
 namespace zkb {
@@ -15,6 +16,7 @@ struct NttTables {
   mutable std::map<int, void*> four_step;         // per (log n, direction): four-step twiddles by position
   mutable std::map<u64, void*> scale_cache;       // per (log n, blow-up, shift): coset scale factors by position
   mutable size_t scale_cache_bytes = 0;
+  mutable std::mutex mu;                          // tables are shared by the compute lanes
   void init(cudaStream_t s);
   void destroy();
   const void* four_step_table(int K1, int logS, bool inverse, cudaStream_t s) const;

@@ -40,19 +40,36 @@ __global__ void __launch_bounds__(EC_THREADS) eval_columns_kernel(const u32* __r
   for (int p = 0; p < NPT; p++)
 #pragma unroll
     for (int c = 0; c < EC_COLS; c++) acc[p][c] = ef_zero();
-  for (size_t r = r_begin + threadIdx.x; r < r_end; r += EC_THREADS) {
-    Ef wv[NPT];
+  // four rows per iteration: the four products of a component are summed raw in 64 bits
+  // (4 p^2 < 2^64) and reduced once
+  for (size_t rb = r_begin + threadIdx.x; rb < r_end; rb += 4 * EC_THREADS) {
+    u32 wv[4][NPT][4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      wv[0].c[k] = fp_raw(w0[(size_t)k * n + r]);
-      if (NPT > 1) wv[NPT - 1].c[k] = fp_raw(w1[(size_t)k * n + r]);
+    for (int u = 0; u < 4; u++) {
+      const size_t r = rb + (size_t)u * EC_THREADS;
+      const bool ok = r < r_end;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        wv[u][0][k] = ok ? w0[(size_t)k * n + r] : 0;
+        if (NPT > 1) wv[u][NPT - 1][k] = ok ? w1[(size_t)k * n + r] : 0;
+      }
     }
 #pragma unroll
     for (int c = 0; c < EC_COLS; c++) {
       if (c0 + c < W) {
-        Fp x = fp_raw(lde[(c0 + c) * H + r]);
+        u32 x[4];
 #pragma unroll
-        for (int p = 0; p < NPT; p++) acc[p][c] += wv[p] * x;
+        for (int u = 0; u < 4; u++) {
+          const size_t r = rb + (size_t)u * EC_THREADS;
+          x[u] = r < r_end ? lde[(c0 + c) * H + r] : 0;
+        }
+#pragma unroll
+        for (int p = 0; p < NPT; p++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            u64 s = (u64)wv[0][p][k] * x[0] + (u64)wv[1][p][k] * x[1] + (u64)wv[2][p][k] * x[2] + (u64)wv[3][p][k] * x[3];
+            acc[p][c].c[k] += fp_raw(mont_reduce_wide(s));
+          }
       }
     }
   }
@@ -170,8 +187,10 @@ __global__ void __launch_bounds__(128) reduce_matrix_kernel(const u32* __restric
                                                             const u32* __restrict__ invden1, u32* __restrict__ ro) {
   size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (x >= H) return;
-  Ef acc = ef_zero();
-  for (size_t j = 0; j < W; j++) acc += ldg_ef(apow, j) * fp_raw(lde[j * H + x]);
+  EfAcc lazy;
+  lazy.clear();
+  for (size_t j = 0; j < W; j++) lazy.add(ldg_ef(apow, j), fp_raw(lde[j * H + x]));
+  Ef acc = lazy.value();
   Ef r;
 #pragma unroll
   for (int c = 0; c < 4; c++) r.c[c] = fp_raw(ro[(size_t)c * H + x]);

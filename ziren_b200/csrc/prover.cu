@@ -5,6 +5,7 @@
 #include "prover.h"
 #include <algorithm>
 #include <array>
+#include <cstdlib>
 #include <map>
 #include "layout.h"
 #include "logup.h"
@@ -15,9 +16,10 @@ namespace zkb {
 
 void Ctx::init(int dev, const u32* desc, size_t n) {
   device = dev;
+  if (const char* e = getenv("ZKB200_LANES")) active_lanes = std::max(1, std::min(NUM_LANES, atoi(e)));
   ZKB_CUDA(cudaSetDevice(dev));
   machine.parse(desc, n);
-  ZKB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  for (auto& L : lanes) ZKB_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
   ZKB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
   // keep freed blocks in the stream-ordered pool: shard proofs reuse the same sizes
   cudaMemPool_t pool;
@@ -28,35 +30,54 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
   // recycle a block: a fresh block is cheaper than losing the upload/compute overlap
   int no = 0;
   ZKB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &no));
+  // Prime the pool: growing it (cuMemCreate/cuMemMap of GBs) in the middle of a proof costs up to
+  // seconds, so reserve the physical memory once.  ZKB200_POOL_GB overrides (0 disables).
+  {
+    size_t free_b = 0, total_b = 0;
+    ZKB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t want = std::min<size_t>((size_t)64 << 30, free_b / 2);
+    if (const char* e = getenv("ZKB200_POOL_GB")) want = std::min<size_t>((size_t)atol(e) << 30, free_b * 9 / 10);
+    if (want) {
+      void* p = nullptr;
+      ZKB_CUDA(cudaMallocAsync(&p, want, lanes[0].stream));
+      ZKB_CUDA(cudaFreeAsync(p, lanes[0].stream));
+      ZKB_CUDA(cudaStreamSynchronize(lanes[0].stream));
+    }
+  }
   machine.upload();
-  tables.init(stream);
+  tables.init(lanes[0].stream);
   p2_upload_constants();
-  arena.init(8u << 20, stream);
-  ZKB_CUDA(cudaMalloc((void**)&d_small, 1 << 16));
-  ZKB_CUDA(cudaMallocHost((void**)&h_small, 1 << 16));
-  ZKB_CUDA(cudaStreamSynchronize(stream));
+  for (auto& L : lanes) {
+    L.arena.init(8u << 20, L.stream);
+    ZKB_CUDA(cudaMalloc((void**)&L.d_small, 1 << 16));
+    ZKB_CUDA(cudaMallocHost((void**)&L.h_small, 1 << 16));
+  }
+  ZKB_CUDA(cudaStreamSynchronize(lanes[0].stream));
 }
 void Ctx::destroy() {
   cudaSetDevice(device);
-  if (stream) cudaStreamSynchronize(stream);
+  cudaDeviceSynchronize();
   machine.destroy();
   tables.destroy();
-  arena.destroy();
-  if (d_small) cudaFree(d_small);
-  if (h_small) cudaFreeHost(h_small);
-  if (stream) cudaStreamDestroy(stream);
+  for (auto& L : lanes) {
+    L.arena.destroy();
+    if (L.d_small) cudaFree(L.d_small);
+    if (L.h_small) cudaFreeHost(L.h_small);
+    if (L.stream) cudaStreamDestroy(L.stream);
+    L.stream = nullptr; L.d_small = nullptr; L.h_small = nullptr;
+  }
   if (copy_stream) cudaStreamDestroy(copy_stream);
-  stream = copy_stream = nullptr;
+  copy_stream = nullptr;
 }
 
 struct StageTimer {
-  Ctx& ctx; const char* name; cudaEvent_t a = nullptr, b = nullptr;
-  StageTimer(Ctx& c, const char* n) : ctx(c), name(n) {
-    if (ctx.profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, ctx.stream); }
+  Ctx& ctx; cudaStream_t stream; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+  StageTimer(Ctx& c, Lane& L, const char* n) : ctx(c), stream(L.stream), name(n) {
+    if (ctx.profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, stream); }
   }
   ~StageTimer() {
     if (ctx.profile) {
-      cudaEventRecord(b, ctx.stream); cudaEventSynchronize(b);
+      cudaEventRecord(b, stream); cudaEventSynchronize(b);
       float ms = 0; cudaEventElapsedTime(&ms, a, b);
       ctx.stage_ms.push_back({name, ms});
       cudaEventDestroy(a); cudaEventDestroy(b);
@@ -66,9 +87,10 @@ struct StageTimer {
 
 // Row-major host/device matrix -> column-major device matrix, issued on stream `on`.  The result
 // is released on the compute stream, so `on` must be joined into it before first use.
-DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream_t on) {
+DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream_t on, cudaStream_t free_on) {
+  (void)ctx;
   DevMat m(h, w, on);
-  m.buf.stream = ctx.stream;
+  m.buf.stream = free_on;
   if (h * w == 0) return m;
   cudaPointerAttributes attr;
   bool on_device = false;
@@ -85,7 +107,7 @@ DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream
 }
 
 // TwoAdicFriPcs::commit: coset LDE (shift GENERATOR / domain_shift) of every matrix + MMCS tree.
-void pcs_commit(Ctx& ctx, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out) {
+void pcs_commit(Ctx& ctx, Lane& L, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out) {
   const unsigned lb = ctx.machine.log_blowup;
   std::vector<MatRef> refs;
   out.ldes.clear(); out.log_n.clear();
@@ -95,17 +117,17 @@ void pcs_commit(Ctx& ctx, std::vector<DevMat>& traces, const std::vector<Fp>& do
     unsigned ln = log2_exact(t.height);
     if (((size_t)1 << ln) != t.height) throw std::runtime_error("zkb200: trace height is not a power of two");
     if (ln + lb > 24) throw std::runtime_error("zkb200: LDE height exceeds the field's two-adicity (2^24)");
-    DevMat lde(t.height << lb, t.width, ctx.stream);
+    DevMat lde(t.height << lb, t.width, L.stream);
     Fp shift = gen * fp_inv(domain_shifts[i]);
-    coset_lde_batch(ctx.tables, t.d(), t.height, lde.d(), lde.height, ln, t.width, lb, shift, ctx.stream);
+    coset_lde_batch(ctx.tables, t.d(), t.height, lde.d(), lde.height, ln, t.width, lb, shift, L.stream);
     refs.push_back(MatRef{lde.d(), (u32)t.width, ln + lb});
     out.ldes.push_back(std::move(lde));
     out.log_n.push_back(ln);
   }
-  merkle_build(refs, ctx.arena, out.layers, ctx.d_small, ctx.stream);
-  ZKB_CUDA(cudaMemcpyAsync(ctx.h_small, ctx.d_small, 32, cudaMemcpyDeviceToHost, ctx.stream));
-  ZKB_CUDA(cudaStreamSynchronize(ctx.stream));
-  memcpy(out.root, ctx.h_small, 32);
+  merkle_build(refs, L.arena, out.layers, L.d_small, L.stream);
+  ZKB_CUDA(cudaMemcpyAsync(L.h_small, L.d_small, 32, cudaMemcpyDeviceToHost, L.stream));
+  ZKB_CUDA(cudaStreamSynchronize(L.stream));
+  memcpy(out.root, L.h_small, 32);
   out.log_max_height = 0;
   for (auto& r : refs) out.log_max_height = std::max(out.log_max_height, r.log_height);
 }
@@ -118,9 +140,10 @@ static void sort_traces(std::vector<TraceIn>& v) {
 }
 
 Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, const u32* init_gsum) {
-  std::lock_guard<std::mutex> lock(ctx.mu);
   ZKB_CUDA(cudaSetDevice(ctx.device));
-  ctx.arena.reset();
+  LaneGuard guard(ctx);
+  Lane& L = *guard.lane;
+  L.arena.reset();
   std::unique_ptr<Pk> pk(new Pk());
   pk->ctx = &ctx;
   std::vector<TraceIn> prep = prep_in;
@@ -132,16 +155,16 @@ Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, co
     if (c->prep_width != t.width) throw std::runtime_error("zkb200: setup: preprocessed width mismatch for " + t.name);
     pk->names.push_back(t.name);
     pk->local_only.push_back(c->local_only);
-    pk->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width, ctx.stream));
+    pk->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width, L.stream, L.stream));
     shifts.push_back(fp_one());
   }
   if (!prep.empty()) {
-    pcs_commit(ctx, pk->traces, shifts, pk->data);
+    pcs_commit(ctx, L, pk->traces, shifts, pk->data);
     for (int i = 0; i < 8; i++) pk->commit_canon[i] = fp_to_canonical(fp_raw(pk->data.root[i]));
   }
   pk->pc_start = pc_start;
   for (int i = 0; i < 14; i++) pk->init_global_sum[i] = init_gsum ? init_gsum[i] : 0;
-  ZKB_CUDA(cudaStreamSynchronize(ctx.stream));
+  ZKB_CUDA(cudaStreamSynchronize(L.stream));
   return pk.release();
 }
 
@@ -167,17 +190,18 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     std::lock_guard<std::mutex> lock(ctx.copy_mu);
     for (auto& t : traces) {
       sh->names.push_back(t.name);
-      sh->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width, ctx.copy_stream));
+      sh->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width, ctx.copy_stream, ctx.lanes[0].stream));
       shifts.push_back(fp_one());
     }
     ZKB_CUDA(cudaEventRecord(uploaded, ctx.copy_stream));
   }
-  // Phase 2 (compute stream): LDE + Merkle tree
-  std::lock_guard<std::mutex> lock(ctx.mu);
-  ctx.arena.reset();
-  ZKB_CUDA(cudaStreamWaitEvent(ctx.stream, uploaded, 0));
+  // Phase 2 (a compute lane): LDE + Merkle tree
+  LaneGuard guard(ctx);
+  Lane& L = *guard.lane;
+  L.arena.reset();
+  ZKB_CUDA(cudaStreamWaitEvent(L.stream, uploaded, 0));
   cudaEventDestroy(uploaded);
-  pcs_commit(ctx, sh->traces, shifts, sh->main);
+  pcs_commit(ctx, L, sh->traces, shifts, sh->main);
   sh->public_values.assign(pv, pv + npv);
   return sh.release();
 }
@@ -212,11 +236,12 @@ struct OpenMat {           // one matrix of one round in the opening
 }  // namespace
 
 std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger34) {
-  std::lock_guard<std::mutex> lock(ctx.mu);
   ZKB_CUDA(cudaSetDevice(ctx.device));
-  ctx.arena.reset();
-  ctx.stage_ms.clear();
-  cudaStream_t s = ctx.stream;
+  LaneGuard guard(ctx);
+  Lane& L = *guard.lane;
+  L.arena.reset();
+  if (ctx.profile) ctx.stage_ms.clear();
+  cudaStream_t s = L.stream;
   const MachineInfo& M = ctx.machine;
   const unsigned lb = M.log_blowup;
   const size_t nc = sh.names.size();
@@ -236,14 +261,14 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
   // public values on the device (Montgomery)
   std::vector<u32> pv_m(std::max<size_t>(sh.public_values.size(), 1), 0);
   for (size_t i = 0; i < sh.public_values.size(); i++) pv_m[i] = fp_from_canonical(sh.public_values[i] % KB_P).v;
-  const u32* pv_dev = ctx.arena.push(pv_m.data(), pv_m.size());
+  const u32* pv_dev = L.arena.push(pv_m.data(), pv_m.size());
 
   // ---- permutation traces (K5) + commit -----------------------------------------------------
   std::vector<DevMat> perm_traces;
   std::vector<Ef> local_sums(nc);
   std::vector<std::array<u32, 14>> global_sums(nc);   // Montgomery
   {
-    StageTimer tm(ctx, "permutation_trace");
+    StageTimer tm(ctx, L, "permutation_trace");
     // sums land in d_small: per chip 4 words local + 14 words global
     if (nc > 200) throw std::runtime_error("zkb200: too many chips in shard");
     std::vector<GatherJob> jobs;
@@ -253,29 +278,29 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
       if (prep && prep->height != sh.traces[i].height) throw std::runtime_error("zkb200: preprocessed and main have different heights: " + sh.names[i]);
       const size_t n = sh.traces[i].height;
       DevMat pt(n, 4 * chips[i]->perm_width_ef(), s);
-      u32* sums = ctx.d_small + 4096 + i * 4;   // Montgomery scratch, converted by the gather below
+      u32* sums = L.d_small + 4096 + i * 4;   // Montgomery scratch, converted by the gather below
       permutation_trace(M, *chips[i], prep ? prep->d() : nullptr, sh.traces[i].d(), n, perm_alpha, perm_beta, pt.d(), sums, s);
       jobs.push_back(GatherJob{sums, 1, 4, (u32)(i * 18)});
       if (chips[i]->global_scope)
         jobs.push_back(GatherJob{sh.traces[i].d() + (sh.traces[i].width - 14) * n + (n - 1), n, 14, (u32)(i * 18 + 4)});
       perm_traces.push_back(std::move(pt));
     }
-    ZKB_CUDA(cudaMemsetAsync(ctx.d_small, 0, nc * 18 * 4, s));
-    const GatherJob* jd = ctx.arena.push(jobs.data(), jobs.size());
-    gather_canonical(jd, jobs.size(), ctx.d_small, s);
-    ZKB_CUDA(cudaMemcpyAsync(ctx.h_small, ctx.d_small, nc * 18 * 4, cudaMemcpyDeviceToHost, s));
+    ZKB_CUDA(cudaMemsetAsync(L.d_small, 0, nc * 18 * 4, s));
+    const GatherJob* jd = L.arena.push(jobs.data(), jobs.size());
+    gather_canonical(jd, jobs.size(), L.d_small, s);
+    ZKB_CUDA(cudaMemcpyAsync(L.h_small, L.d_small, nc * 18 * 4, cudaMemcpyDeviceToHost, s));
     ZKB_CUDA(cudaStreamSynchronize(s));
     for (size_t i = 0; i < nc; i++) {
-      const u32* w = ctx.h_small + i * 18;   // canonical
+      const u32* w = L.h_small + i * 18;   // canonical
       for (int c = 0; c < 4; c++) local_sums[i].c[c] = fp_from_canonical(w[c]);
       for (int k = 0; k < 14; k++) global_sums[i][k] = fp_from_canonical(w[4 + k]).v;
     }
   }
   Commit perm_commit;
   {
-    StageTimer tm(ctx, "commit_permutation");
+    StageTimer tm(ctx, L, "commit_permutation");
     std::vector<Fp> shifts(nc, fp_one());
-    pcs_commit(ctx, perm_traces, shifts, perm_commit);
+    pcs_commit(ctx, L, perm_traces, shifts, perm_commit);
   }
   perm_traces.clear();
   ch.observe_digest(perm_commit.root);
@@ -289,7 +314,7 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
   std::vector<DevMat> quot_chunks;
   std::vector<Fp> quot_shifts;
   {
-    StageTimer tm(ctx, "quotient");
+    StageTimer tm(ctx, L, "quotient");
     for (size_t i = 0; i < nc; i++) {
       const unsigned lqd = chips[i]->log_quotient_degree;
       const size_t n = (size_t)1 << logn[i], nchunks = (size_t)1 << lqd;
@@ -316,8 +341,8 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
   }
   Commit quot_commit;
   {
-    StageTimer tm(ctx, "commit_quotient");
-    pcs_commit(ctx, quot_chunks, quot_shifts, quot_commit);
+    StageTimer tm(ctx, L, "commit_quotient");
+    pcs_commit(ctx, L, quot_chunks, quot_shifts, quot_commit);
   }
   quot_chunks.clear();
   ch.observe_digest(quot_commit.root);
@@ -355,7 +380,7 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
   DevBuf ys_dev(std::max<size_t>(ys_words, 1), s);
   std::vector<DevBuf> ro(32);
   {
-    StageTimer tm(ctx, "open_reduce");
+    StageTimer tm(ctx, L, "open_reduce");
     DevBuf apow(4 * max_w, s);
     ef_powers(alpha_fri, max_w, apow.p, s);
     // group by LDE height so that barycentric weights and inverse denominators are built once
@@ -388,45 +413,45 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
   std::vector<FriLayer> fri_layers;
   Ef final_poly;
   {
-    StageTimer tm(ctx, "fri_commit_phase");
+    StageTimer tm(ctx, L, "fri_commit_phase");
     DevBuf cur = std::move(ro[log_gmax]);
     size_t m = (size_t)1 << log_gmax;
     const size_t blowup = (size_t)1 << lb;
     while (m > blowup) {
-      FriLayer L;
-      L.m = m;
-      fri_commit_layer(cur.p, m, L.tree, ctx.d_small, s);
-      ZKB_CUDA(cudaMemcpyAsync(ctx.h_small, ctx.d_small, 32, cudaMemcpyDeviceToHost, s));
+      FriLayer FL;
+      FL.m = m;
+      fri_commit_layer(cur.p, m, FL.tree, L.d_small, s);
+      ZKB_CUDA(cudaMemcpyAsync(L.h_small, L.d_small, 32, cudaMemcpyDeviceToHost, s));
       ZKB_CUDA(cudaStreamSynchronize(s));
-      memcpy(L.root, ctx.h_small, 32);
-      ch.observe_digest(L.root);
+      memcpy(FL.root, L.h_small, 32);
+      ch.observe_digest(FL.root);
       const Ef beta = ch.sample_ext();
       const unsigned lnext = log2_exact(m) - 1;
       DevBuf next(4 * (m >> 1), s);
       fri_fold(ctx.tables, cur.p, m, beta, ro[lnext].p, next.p, s);
-      L.folded = std::move(cur);
+      FL.folded = std::move(cur);
       cur = std::move(next);
-      fri_layers.push_back(std::move(L));
+      fri_layers.push_back(std::move(FL));
       m >>= 1;
     }
     // `cur` holds blowup evaluations of a constant polynomial
-    ZKB_CUDA(cudaMemcpyAsync(ctx.h_small, cur.p, 4 * m * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    ZKB_CUDA(cudaMemcpyAsync(L.h_small, cur.p, 4 * m * sizeof(u32), cudaMemcpyDeviceToHost, s));
     ZKB_CUDA(cudaStreamSynchronize(s));
-    for (int c = 0; c < 4; c++) final_poly.c[c] = fp_raw(ctx.h_small[c * m]);
+    for (int c = 0; c < 4; c++) final_poly.c[c] = fp_raw(L.h_small[c * m]);
     for (size_t i = 1; i < m; i++)
       for (int c = 0; c < 4; c++)
-        if (ctx.h_small[c * m + i] != final_poly.c[c].v) throw std::runtime_error("zkb200: FRI final polynomial is not constant (unsatisfied constraints?)");
+        if (L.h_small[c * m + i] != final_poly.c[c].v) throw std::runtime_error("zkb200: FRI final polynomial is not constant (unsatisfied constraints?)");
   }
   ch.observe_ext(final_poly);
 
   // ---- proof of work (K4d) ------------------------------------------------------------------
   u32 pow_witness = 0;
   {
-    StageTimer tm(ctx, "grind");
+    StageTimer tm(ctx, L, "grind");
     u32 st[16];
     for (int i = 0; i < 16; i++) st[i] = ch.state[i].v;
     for (unsigned i = 0; i < ch.n_in; i++) st[i] = ch.in_buf[i].v;
-    pow_witness = grind_witness(st, ch.n_in, M.pow_bits, ctx.d_small + 8192, s);
+    pow_witness = grind_witness(st, ch.n_in, M.pow_bits, L.d_small + 8192, s);
     ch.observe_canonical(pow_witness);
     if (ch.sample_bits(M.pow_bits) != 0) throw std::runtime_error("zkb200: grinding produced an invalid witness");
   }
@@ -470,14 +495,14 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
   o.put((u32)sh.public_values.size());
   for (u32 x : sh.public_values) o.put(x);
   o.put((u32)fri_layers.size());
-  for (auto& L : fri_layers) o.put_digest_monty(L.root);
+  for (auto& fl : fri_layers) o.put_digest_monty(fl.root);
   o.put_ef(final_poly);
   o.put(pow_witness);
   o.put(M.num_queries);
 
   std::vector<GatherJob> jobs;
   {
-    StageTimer tm(ctx, "query_openings");
+    StageTimer tm(ctx, L, "query_openings");
     for (u32 q = 0; q < M.num_queries; q++) {
       const size_t index = ch.sample_bits(log_gmax);
       o.put((u32)rounds.size());
@@ -501,16 +526,16 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
       }
       o.put((u32)fri_layers.size());
       for (size_t li = 0; li < fri_layers.size(); li++) {
-        const FriLayer& L = fri_layers[li];
+        const FriLayer& FL = fri_layers[li];
         const size_t idx_i = index >> li, pair = idx_i >> 1, sib = idx_i ^ 1;
         size_t at = o.reserve(4);
-        jobs.push_back(GatherJob{L.folded.p + sib, L.m, 4, (u32)at});
-        const unsigned depth = (unsigned)L.tree.count.size() - 1;
+        jobs.push_back(GatherJob{FL.folded.p + sib, FL.m, 4, (u32)at});
+        const unsigned depth = (unsigned)FL.tree.count.size() - 1;
         o.put(depth);
         for (unsigned l = 0; l < depth; l++) {
           size_t a2 = o.reserve(8);
           size_t node = (pair >> l) ^ 1;
-          jobs.push_back(GatherJob{L.tree.layer(l) + node, L.tree.count[l], 8, (u32)a2});
+          jobs.push_back(GatherJob{FL.tree.layer(l) + node, FL.tree.count[l], 8, (u32)a2});
         }
       }
     }

@@ -24,17 +24,26 @@ struct Commit {
   bool empty() const { return ldes.empty(); }
 };
 
-struct Ctx {
-  int device = 0;
+// A compute lane: one stream with its own scratch.  commit/open calls from different host threads
+// run on different lanes, so the phases of one shard that leave the SMs idle (FRI commit phase,
+// grinding, host round trips) and kernels bound by different pipes overlap with another shard's.
+struct Lane {
   cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;   // host->device uploads + layout change, overlaps the compute stream
-  std::mutex copy_mu;
-  MachineInfo machine;
-  NttTables tables;
   ParamArena arena;
   u32* d_small = nullptr;            // small device scratch (roots, sums)
   u32* h_small = nullptr;            // pinned mirror
-  std::mutex mu;                     // commit/open may be called from several host threads
+  std::mutex mu;
+};
+constexpr int NUM_LANES = 2;
+
+struct Ctx {
+  int device = 0;
+  Lane lanes[NUM_LANES];
+  int active_lanes = NUM_LANES;         // ZKB200_LANES=1 serialises all compute on one stream
+  cudaStream_t copy_stream = nullptr;   // host->device uploads + layout change, overlaps the compute lanes
+  std::mutex copy_mu;
+  MachineInfo machine;
+  NttTables tables;
   std::string err;
   // statistics of the last open(): kernel-stage timings (ms) when profiling is enabled
   bool profile = false;
@@ -76,7 +85,18 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces, const u32* pv
 std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& shard, u32* challenger34);
 
 // building blocks shared with the micro entry points
-DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream_t on);
-void pcs_commit(Ctx& ctx, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out);
+DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream_t on, cudaStream_t free_on);
+void pcs_commit(Ctx& ctx, Lane& L, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out);
+
+// picks a free lane (or waits for lane 0) and holds it
+struct LaneGuard {
+  Lane* lane;
+  explicit LaneGuard(Ctx& ctx) : lane(nullptr) {
+    for (int i = 0; i < ctx.active_lanes && !lane; i++) if (ctx.lanes[i].mu.try_lock()) lane = &ctx.lanes[i];
+    if (!lane) { ctx.lanes[0].mu.lock(); lane = &ctx.lanes[0]; }
+  }
+  ~LaneGuard() { lane->mu.unlock(); }
+  LaneGuard(const LaneGuard&) = delete;
+};
 
 }  // namespace zkb

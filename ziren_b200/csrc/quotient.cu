@@ -48,12 +48,15 @@ __device__ __forceinline__ Ef load_apow(const u32* ap, u32 k) {
   return e;
 }
 
+constexpr int QCHUNK = 1024;   // 12 KB of bytecode per stage
+
 template <int NREGS>
 __global__ void __launch_bounds__(128) quotient_kernel(QuotArgs a) {
   const u32 lq = a.log_n + a.lqd;
   const size_t Q = (size_t)1 << lq;
-  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (t >= Q) return;
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const bool active = t < Q;
+  if (!active) t = Q - 1;          // keep every thread in the barriers below; result discarded
   const u32 i = bitrev32((u32)t, lq);
   const size_t tn = bitrev32((u32)((i + (1u << a.lqd)) & (Q - 1)), lq);
 
@@ -65,9 +68,22 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotArgs a) {
   Fp is_first = zh * (inv12 * d2), is_last = zh * (inv12 * d1), is_trans = d2;
 
   Fp regs[NREGS];
-  Ef acc = ef_zero();
-  for (u32 pc = a.code_begin; pc < a.code_end; pc++) {
-    Instr ins = a.code[pc];
+  EfAcc lazy;     // base-field constraints: alpha-power x value, reduced every fourth assert
+  lazy.clear();
+  // the bytecode is staged through shared memory in chunks: every thread runs the same
+  // instruction stream, so one cooperative copy replaces a dependent global load per instruction
+  __shared__ Instr sh_code[QCHUNK];
+  for (u32 cbase = a.code_begin; cbase < a.code_end; cbase += QCHUNK) {
+  const u32 cn = min((u32)QCHUNK, a.code_end - cbase);
+  __syncthreads();
+  {
+    const u32* src = reinterpret_cast<const u32*>(a.code + cbase);
+    u32* dstw = reinterpret_cast<u32*>(sh_code);
+    for (u32 w = threadIdx.x; w < 3 * cn; w += blockDim.x) dstw[w] = __ldg(src + w);
+  }
+  __syncthreads();
+  for (u32 pc = 0; pc < cn; pc++) {
+    Instr ins = sh_code[pc];
     const u32 op = ins.op_dst >> 24, dst = ins.op_dst & 0xffffffu;
     Fp v;
     switch (op) {
@@ -83,13 +99,15 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotArgs a) {
       case N_MUL: v = regs[ins.a] * regs[ins.b]; break;
       case N_NEG: v = -regs[ins.a]; break;
       default: {  // OP_ASSERT
-        acc += load_apow(a.alpha_pow, ins.b) * regs[ins.a];
+        lazy.add(load_apow(a.alpha_pow, ins.b), regs[ins.a]);
         continue;
       }
     }
     regs[dst] = v;
   }
+  }
 
+  Ef acc = lazy.value();
   // permutation constraints (permutation.rs:205-347)
   u32 k = a.n_air;
   if (a.ew) {
@@ -137,8 +155,10 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotArgs a) {
   // chunk j = i mod 2^lqd, row k = i >> lqd (quotient_domain.split_evals, prover.rs:477-488)
   const size_t n = (size_t)1 << a.log_n;
   u32* o = a.out + (size_t)(i & ((1u << a.lqd) - 1)) * 4 * n + (i >> a.lqd);
+  if (active) {
 #pragma unroll
-  for (int c = 0; c < 4; c++) o[(size_t)c * n] = q.c[c].v;
+    for (int c = 0; c < 4; c++) o[(size_t)c * n] = q.c[c].v;
+  }
 }
 
 __global__ void alpha_pow_kernel(u32* out, u32 C, Ef alpha) {
