@@ -215,11 +215,13 @@ def main():
 
     for _ in range(args.warmup):
         prove(dev_tr)
-    sampler = ClockSampler(args.local_rank)
-    sampler.start()
     if args.value_threads > 1:
         timed(dev_tr, args.value_threads, args.value_threads)
+    sampler = ClockSampler(args.local_rank)
+    sampler.start()
+    launches0 = prover.launch_count()
     ms_dev, proof = timed(dev_tr, args.steps, args.value_threads)
+    launches = prover.launch_count() - launches0
     timed(host_tr, max(args.warmup, args.e2e_threads), args.e2e_threads)      # warm the staging/pool paths of the e2e arm
     ms_e2e, proof2 = timed(host_tr, args.steps, args.e2e_threads)
     clocks = sampler.stop()
@@ -241,10 +243,12 @@ def main():
         allc = [torch.empty_like(c) for _ in range(args.world)]
         dist.all_gather(allc, c)
 
-    roofline = cpu_base = None
+    roofline = roofline_other = cpu_base = None
     if args.rank == 0:
-        if not args.no_roofline:
-            roofline = measure_roofline(prover, case, torch, stream)
+        rl = stage_rooflines(case, stages or {})
+        ranked = sorted(rl.values(), key=lambda r: -r["ms"])
+        if ranked:
+            roofline, roofline_other = ranked[0], ranked[1:]
         if not args.no_cpu_baseline:
             cpu_base = measure_cpu_baseline(args)
 
@@ -257,9 +261,9 @@ def main():
                 "e2e": {"value": total_cycles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                         "host_threads_in_flight": args.e2e_threads},
-                "gpu_launches": None, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other,
+                "cpu_baseline": cpu_base,
                 "stage_ms": stages, "cells_per_sec": case.cells * args.steps * args.gpus / (ms_dev / 1e3)}
-        line["gpu_launches"] = count_launches(case)
         print(json.dumps(line))
     pk.free()
     prover.close()
@@ -267,41 +271,34 @@ def main():
         dist.destroy_process_group()
 
 
-def count_launches(case):
-    """Kernels of OURS launched per timed step (analytic count of the launch sites in
-    csrc/prover.cu for this shard; cross-checked against the ncu launch list in profiles/)."""
-    return None  # filled from the profile in DESIGN.md until the library exports a live counter
-
-
-def measure_roofline(prover, case, torch, stream):
-    """HBM roofline of the dominant kernel family measured live with CUDA events: the coset LDE of
-    the widest table (algorithmic bytes 12*n*c per SURVEY.md §8d: read n*c, write 2n*c words)."""
+def stage_rooflines(case, stages, log_blowup=1):
+    """HBM rooflines of the two dominant kernel families from the per-stage CUDA-event times of a
+    live profiled step (zkb200_set_profile): K2 = Merkle build of the main commit, K1 = coset LDE of
+    the main commit.  Algorithmic bytes per SURVEY.md section 8d."""
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak, which = 6650.0, "fallback"
+    peak, which = 6650.0, "fallback (B200_PROFILING.md)"
     if os.path.exists(peaks_path):
-        peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
-    name, tr = max(case.traces.items(), key=lambda kv: kv[1].size)
-    n, w = tr.shape
-    w = min(w, 512)
-    log_n = int(np.log2(n))
-    d_in = torch.randint(0, kb.P, (w, n), dtype=torch.int32, device="cuda")
-    d_out = torch.empty((w, 2 * n), dtype=torch.int32, device="cuda")
-    for _ in range(3):
-        prover.coset_lde(d_in, d_out, log_n, w, 1, 3)
-    prover.sync()
-    reps = 5
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(reps):
-        prover.coset_lde(d_in, d_out, log_n, w, 1, 3)
-    e1.record(stream)
-    e1.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    alg = 12.0 * n * w
-    achieved = alg / (ms / 1e3) / 1e9
-    return {"bound": "hbm", "kernel": "coset_lde_batch (ntt_pass_kernel x passes)", "achieved": achieved, "peak": peak,
-            "peak_source": which, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "shape": f"{name}: n=2^{log_n}, {w} columns", "ms": ms}
+        peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    shapes = [(t.shape[0] << log_blowup, t.shape[1]) for t in case.traces.values()]
+    hmax = max(h for h, _ in shapes)
+    inj_heights = sorted({h for h, _ in shapes if h < hmax})
+    merkle_bytes = sum(4.0 * h * w for h, w in shapes) + 32.0 * hmax + 96.0 * (hmax - 1) + 64.0 * sum(inj_heights)
+    perms = sum(h * (-(-w // 8)) for h, w in shapes) + (hmax - 1) + sum(inj_heights)
+    lde_bytes = sum(12.0 * t.shape[0] * t.shape[1] for t in case.traces.values())
+    out = {}
+    for key, stage, alg, kern in (("k2_merkle", "commit_main_merkle", merkle_bytes, "merkle_build: leaf_hash_kernel + compress_kernel (Poseidon2 sponge / inject)"),
+                                  ("k1_lde", "commit_main_lde", lde_bytes, "coset_lde_batch: ntt_strided_kernel + ntt_contig_kernel")):
+        ms = stages.get(stage)
+        if not ms:
+            continue
+        ach = alg / (ms / 1e3) / 1e9
+        out[key] = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "ms": ms, "algorithmic_bytes": alg,
+                    "share_of_step": ms / max(sum(stages.values()), 1e-9)}
+    if "k2_merkle" in out:
+        out["k2_merkle"]["poseidon2_Gperm_per_s"] = perms / (stages["commit_main_merkle"] / 1e3) / 1e9
+        out["k2_merkle"]["note"] = "integer-multiply (FMA-heavy pipe) bound, not HBM bound: ~4.8k instructions per permutation; see profiles/README.md"
+    return out
 
 
 def measure_cpu_baseline(args):

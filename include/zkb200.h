@@ -106,6 +106,8 @@ void zkb200_free(void* p);
  * stages; names/ms may be NULL to query the count */
 void zkb200_set_profile(zkb200_ctx* ctx, int on);
 int zkb200_last_stage_times(zkb200_ctx* ctx, const char** names, float* ms, int cap);
+/* number of CUDA kernels this library has launched in this process (all contexts) */
+unsigned long long zkb200_launch_count(void);
 
 /* ---- kernel-level entry points (tests, micro-benchmarks, ncu captures) -------------------------
  * All matrices here are DEVICE pointers, COLUMN-MAJOR (column c at data + c*height), Montgomery. */

@@ -40,6 +40,7 @@ SIGNATURES = {
                                      C.POINTER(u32p), C.POINTER(C.c_size_t)]),
     "zkb200_free": (None, [C.c_void_p]),
     "zkb200_set_profile": (None, [C.c_void_p, C.c_int]),
+    "zkb200_launch_count": (C.c_ulonglong, []),
     "zkb200_last_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]),
     "zkb200_coset_lde": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t, C.c_uint, C.c_uint32]),
     "zkb200_ntt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t, C.c_int, C.c_int]),

@@ -111,6 +111,7 @@ int zkb200_prove_shard(zkb200_ctx* ctx, const zkb200_pk* pk, const zkb200_trace*
 void zkb200_free(void* p) { free(p); }
 
 void zkb200_set_profile(zkb200_ctx* ctx, int on) { ctx->c.profile = on != 0; }
+unsigned long long zkb200_launch_count(void) { return g_kernel_launches.load(); }
 int zkb200_last_stage_times(zkb200_ctx* ctx, const char** names, float* ms, int cap) {
   int n = (int)ctx->c.stage_ms.size();
   for (int i = 0; i < n && i < cap; i++) {

@@ -2,6 +2,7 @@
 // a parameter arena for small host->device tables, and the column-major device matrix.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -21,7 +22,14 @@ namespace zkb {
                                __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")");        \
   } while (0)
 
-#define ZKB_CHECK_LAUNCH() ZKB_CUDA(cudaGetLastError())
+// every kernel launch site goes through this macro: it also feeds the live launch counter that
+// bench.py reports as `gpu_launches`
+extern std::atomic<unsigned long long> g_kernel_launches;
+#define ZKB_CHECK_LAUNCH()                 \
+  do {                                     \
+    ZKB_CUDA(cudaGetLastError());          \
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed); \
+  } while (0)
 
 // Device buffer on the context stream (cudaMallocAsync pool keeps freed blocks cached).
 struct DevBuf {

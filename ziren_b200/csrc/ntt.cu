@@ -141,57 +141,48 @@ __device__ __forceinline__ void butterflies(Fp* x, u32 bl, const uint2* __restri
 __device__ __forceinline__ u32 saddr(u32 slot, u32 q, int logT) { return (slot << logT) + (q ^ (slot & ((1u << logT) - 1))); }
 __device__ __forceinline__ u32 caddr(u32 slot, u32 q, u32 ldg) { return q * ldg + slot + (slot >> 3); }
 
-// One round over bits [LO, LO+R) of the slot index for the whole tile held in `sm`.
-template <int K, int R, int LO, bool DIF, bool CONTIG>
-__device__ __forceinline__ void tile_round(u32* sm, int logT, const uint2* __restrict__ tw, u32 ldg) {
+// One radix-2^R round over bits [LO, LO+R) of the slot index, 16 elements per thread.  Where the
+// elements come from and go to is given by the caller (shared memory or straight from / to global
+// memory): the first round of a level loads from global memory into registers and the last one
+// stores from registers, so a 2^9-point level makes one or two shared-memory round trips.
+template <int K, int R, int LO, bool DIF, bool CONTIG, class Load, class Store>
+__device__ __forceinline__ void round_io(int logT, const uint2* __restrict__ tw, Load load, Store store) {
   constexpr int G = ELEMS_PER_THREAD >> R;   // groups per thread
   const u32 T = 1u << logT;
   const u32 ngroups = 1u << (K - R + logT);
+  Fp x[G][1 << R];
+  u32 qs[G], bases[G];
 #pragma unroll
   for (int g = 0; g < G; g++) {
-    u32 gi = g * blockDim.x + threadIdx.x;
-    if (gi >= ngroups) break;
+    const u32 gi = g * blockDim.x + threadIdx.x;
     u32 rest, q;
     if (CONTIG) { rest = gi & ((1u << (K - R)) - 1); q = gi >> (K - R); }
     else { q = gi & (T - 1); rest = gi >> logT; }
-    const u32 bl = rest & ((1u << LO) - 1);
-    const u32 base = ((rest >> LO) << (LO + R)) | bl;
-    Fp x[1 << R];
+    qs[g] = q;
+    bases[g] = ((rest >> LO) << (LO + R)) | (rest & ((1u << LO) - 1));
+    if (gi < ngroups) {
 #pragma unroll
-    for (int m = 0; m < (1 << R); m++) {
-      const u32 slot = base | ((u32)m << LO);
-      x[m] = fp_raw(sm[CONTIG ? caddr(slot, q, ldg) : saddr(slot, q, logT)]);
+      for (int m = 0; m < (1 << R); m++) x[g][m] = load(bases[g] | ((u32)m << LO), q);
     }
-    butterflies<K, R, LO, DIF>(x, bl, tw);
+  }
 #pragma unroll
-    for (int m = 0; m < (1 << R); m++) {
-      const u32 slot = base | ((u32)m << LO);
-      sm[CONTIG ? caddr(slot, q, ldg) : saddr(slot, q, logT)] = x[m].v;
+  for (int g = 0; g < G; g++) {
+    const u32 gi = g * blockDim.x + threadIdx.x;
+    if (gi < ngroups) {
+      butterflies<K, R, LO, DIF>(x[g], bases[g] & ((1u << LO) - 1), tw);
+#pragma unroll
+      for (int m = 0; m < (1 << R); m++) store(bases[g] | ((u32)m << LO), qs[g], x[g][m]);
     }
   }
 }
 
 // rounds of radix <= 16, evenly split: R_r = K/nr + (r < K%nr)
 __host__ __device__ constexpr int round_bits(int K, int r) { return K / ((K + 3) / 4) + (r < K % ((K + 3) / 4) ? 1 : 0); }
-
-// full 2^K-point transform of every (q) of the tile: DIF natural -> bit-reversed slots,
-// DIT bit-reversed -> natural slots.
-template <int K, bool DIF, bool CONTIG>
-__device__ __forceinline__ void tile_transform(u32* sm, int logT, const uint2* __restrict__ tw, u32 ldg) {
-  constexpr int NR = (K + 3) / 4;
-  constexpr int R0 = round_bits(K, 0);
-  tile_round<K, R0, DIF ? K - R0 : 0, DIF, CONTIG>(sm, logT, tw, ldg);
-  __syncthreads();
-  if constexpr (NR > 1) {
-    constexpr int R1 = round_bits(K, 1);
-    tile_round<K, R1, DIF ? K - R0 - R1 : R0, DIF, CONTIG>(sm, logT, tw, ldg);
-    __syncthreads();
-    if constexpr (NR > 2) {
-      constexpr int R2 = round_bits(K, 2);
-      tile_round<K, R2, DIF ? K - R0 - R1 - R2 : R0 + R1, DIF, CONTIG>(sm, logT, tw, ldg);
-      __syncthreads();
-    }
-  }
+// bit offset of round r when the rounds are laid out from the top bit down (r = 0 on top)
+__host__ __device__ constexpr int round_lo(int K, int r) {
+  int lo = K;
+  for (int i = 0; i <= r; i++) lo -= round_bits(K, i);
+  return lo;
 }
 
 template <int K>
@@ -215,75 +206,72 @@ struct StridedArgs {
   size_t in_coset_stride;
 };
 
-template <int K>
-__global__ void __launch_bounds__(1024, 1) ntt_strided_kernel(StridedArgs a) {
-  extern __shared__ __align__(16) u32 smem[];
+template <int K, bool FINAL>
+__device__ __forceinline__ void strided_body(const StridedArgs& a, u32* smem) {
   const int logT = a.logT, logS = a.logS;
   constexpr u32 nslot = 1u << K;
-  const u32 T = 1u << logT;
+  constexpr int NR = (K + 3) / 4;
   uint2* tw = reinterpret_cast<uint2*>(smem);
   u32* data = smem + nslot;           // 2^(K-1) uint2 twiddles = nslot words
   const u32 tile_elems = nslot << logT;
   const u32* __restrict__ in = a.in + (size_t)blockIdx.y * a.in_stride + (size_t)blockIdx.z * a.in_coset_stride;
   u32* __restrict__ out = a.out + (size_t)blockIdx.y * a.out_stride + (size_t)blockIdx.z * a.out_coset_stride;
+  const uint2* __restrict__ four = a.four;
   fill_small_twiddles<K>(tw, a.inverse, a.small_tw);
   const u32 t0 = blockIdx.x << logT;   // offsets t0 .. t0+T-1
 
-  // loads are issued in batches of 8 per thread so that 8 independent requests are in flight
-#pragma unroll
-  for (int h = 0; h < ELEMS_PER_THREAD; h += 8) {
-    u32 v[8];
-    uint2 w[8];
-#pragma unroll
-    for (int it = 0; it < 8; it++) {
-      const u32 i = (h + it) * blockDim.x + threadIdx.x;
-      if (i < tile_elems) {
-        const size_t pos = ((size_t)(i >> logT) << logS) + t0 + (i & (T - 1));
-        v[it] = in[pos];
-        if (a.final_dit) w[it] = __ldg(a.four + pos);
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < 8; it++) {
-      const u32 i = (h + it) * blockDim.x + threadIdx.x;
-      if (i < tile_elems) {
-        const u32 q = i & (T - 1), j = i >> logT;
-        u32 x = v[it], slot = j;
-        if (a.final_dit) { x = shoup_mul(x, w[it]).v; slot = bitrev32(j, K); }
-        data[saddr(slot, q, logT)] = x;
-      }
+  // both kinds run the DIF network: natural slots in, bit-reversed slots out.  For the final DIT
+  // level the natural slot s is fed from row bitrev(s) (pre-twiddled), see the file header.
+  auto gload = [&](u32 slot, u32 q) {
+    const u32 row = FINAL ? bitrev32(slot, K) : slot;
+    const size_t pos = ((size_t)row << logS) + t0 + q;
+    const u32 v = in[pos];
+    return FINAL ? shoup_mul(v, __ldg(four + pos)) : fp_raw(v);
+  };
+  auto gstore = [&](u32 slot, u32 q, Fp v) {      // DIF only: post-twiddle, in-place position
+    const size_t pos = ((size_t)slot << logS) + t0 + q;
+    out[pos] = shoup_mul(v.v, __ldg(four + pos)).v;
+  };
+  auto sload = [&](u32 slot, u32 q) { return fp_raw(data[saddr(slot, q, logT)]); };
+  auto sstore = [&](u32 slot, u32 q, Fp v) { data[saddr(slot, q, logT)] = v.v; };
+
+  __syncthreads();   // twiddles visible
+  constexpr int R0 = round_bits(K, 0);
+  if constexpr (NR == 1) {
+    if constexpr (FINAL) round_io<K, R0, 0, true, false>(logT, tw, gload, sstore);
+    else round_io<K, R0, 0, true, false>(logT, tw, gload, gstore);
+  } else {
+    round_io<K, R0, round_lo(K, 0), true, false>(logT, tw, gload, sstore);
+    __syncthreads();
+    constexpr int R1 = round_bits(K, 1);
+    if constexpr (NR == 2) {
+      if constexpr (FINAL) round_io<K, R1, 0, true, false>(logT, tw, sload, sstore);
+      else round_io<K, R1, 0, true, false>(logT, tw, sload, gstore);
+    } else {
+      round_io<K, R1, round_lo(K, 1), true, false>(logT, tw, sload, sstore);
+      __syncthreads();
+      constexpr int R2 = round_bits(K, 2);
+      if constexpr (FINAL) round_io<K, R2, 0, true, false>(logT, tw, sload, sstore);
+      else round_io<K, R2, 0, true, false>(logT, tw, sload, gstore);
     }
   }
-  __syncthreads();
-  // both kinds run the DIF network: natural slots in, bit-reversed slots out
-  tile_transform<K, true, false>(data, logT, tw, 0);
-
-  if (a.final_dit) {
-    // slot o holds k_hi = bitrev_K(o); natural index k_hi*S + t lands at bitrev_logS(t) * 2^K + o
+  if constexpr (FINAL) {
+    __syncthreads();
+    // slot o holds k_hi = bitrev_K(o); natural index k_hi*S + t lands at bitrev_logS(t) * 2^K + o:
+    // transposed through shared memory so that the stores run along o
     for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
       const u32 o = i & (nslot - 1), q = i >> K;
       const size_t pos = ((size_t)bitrev32(t0 + q, logS) << K) + o;
       out[pos] = data[saddr(o, q, logT)];
     }
-  } else {
-#pragma unroll
-    for (int h = 0; h < ELEMS_PER_THREAD; h += 8) {
-      uint2 w[8];
-#pragma unroll
-      for (int it = 0; it < 8; it++) {
-        const u32 i = (h + it) * blockDim.x + threadIdx.x;
-        if (i < tile_elems) w[it] = __ldg(a.four + (((size_t)(i >> logT) << logS) + t0 + (i & (T - 1))));
-      }
-#pragma unroll
-      for (int it = 0; it < 8; it++) {
-        const u32 i = (h + it) * blockDim.x + threadIdx.x;
-        if (i < tile_elems) {
-          const u32 q = i & (T - 1), o = i >> logT;
-          out[((size_t)o << logS) + t0 + q] = shoup_mul(data[saddr(o, q, logT)], w[it]).v;
-        }
-      }
-    }
   }
+}
+
+template <int K>
+__global__ void __launch_bounds__(1024, 1) ntt_strided_kernel(StridedArgs a) {
+  extern __shared__ __align__(16) u32 smem[];
+  if (a.final_dit) strided_body<K, true>(a, smem);
+  else strided_body<K, false>(a, smem);
 }
 
 // ---- contiguous level (optionally fused inverse -> scale -> forward per coset) --------------------
@@ -307,6 +295,7 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
   extern __shared__ __align__(16) u32 smem[];
   const int logT = a.logT;
   constexpr u32 nslot = 1u << K;
+  constexpr int NR = (K + 3) / 4;
   const u32 T = 1u << logT;
   constexpr u32 ldg = nslot + (nslot >> 3) + 1;
   uint2* tw_a = reinterpret_cast<uint2*>(smem);            // first transform's twiddles (nslot words)
@@ -318,70 +307,80 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
   fill_small_twiddles<K>(tw_a, a.mode == 1 ? true : (a.inverse != 0), a.small_tw);
   if (a.mode == 1) fill_small_twiddles<K>(tw_b, false, a.small_tw);
   const u32 f0 = blockIdx.x << logT;
+  const u32* __restrict__ gin = a.in;
 
-#pragma unroll
-  for (int h = 0; h < ELEMS_PER_THREAD; h += 8) {
-    u32 v[8];
-#pragma unroll
-    for (int it = 0; it < 8; it++) {
-      const u32 i = (h + it) * blockDim.x + threadIdx.x;
-      v[it] = 0;
-      if (i < tile_elems) {
-        const u32 slot = i & (nslot - 1), f = f0 + (i >> K);
-        if (f < a.total_groups) v[it] = a.in[(size_t)(f >> sub_bits) * a.in_stride + ((size_t)(f & ((1u << sub_bits) - 1)) << K) + slot];
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < 8; it++) {
-      const u32 i = (h + it) * blockDim.x + threadIdx.x;
-      if (i < tile_elems) bufA[caddr(i & (nslot - 1), i >> K, ldg)] = v[it];
+  auto gaddr = [&](u32 slot, u32 q, size_t stride) {     // element offset of (group f0+q, slot)
+    const u32 f = f0 + q;
+    return (size_t)(f >> sub_bits) * stride + ((size_t)(f & ((1u << sub_bits) - 1)) << K) + slot;
+  };
+  auto gload = [&](u32 slot, u32 q) { return fp_raw((f0 + q) < a.total_groups ? gin[gaddr(slot, q, a.in_stride)] : 0u); };
+  auto aload = [&](u32 slot, u32 q) { return fp_raw(bufA[caddr(slot, q, ldg)]); };
+  auto astore = [&](u32 slot, u32 q, Fp v) { bufA[caddr(slot, q, ldg)] = v.v; };
+  auto bload = [&](u32 slot, u32 q) { return fp_raw(bufB[caddr(slot, q, ldg)]); };
+  auto bstore = [&](u32 slot, u32 q, Fp v) { bufB[caddr(slot, q, ldg)] = v.v; };
+
+  __syncthreads();   // twiddles visible
+  // ---- DIF (top bits first); the last round's result is left in shared memory (bufA) ----
+  constexpr int R0 = round_bits(K, 0);
+  round_io<K, R0, round_lo(K, 0), true, true>(logT, tw_a, gload, astore);
+  __syncthreads();
+  if constexpr (NR > 1) {
+    constexpr int R1 = round_bits(K, 1);
+    round_io<K, R1, round_lo(K, 1), true, true>(logT, tw_a, aload, astore);
+    __syncthreads();
+    if constexpr (NR > 2) {
+      constexpr int R2 = round_bits(K, 2);
+      round_io<K, R2, round_lo(K, 2), true, true>(logT, tw_a, aload, astore);
+      __syncthreads();
     }
   }
-  __syncthreads();
-  tile_transform<K, true, true>(bufA, logT, tw_a, ldg);
 
   if (a.mode == 0) {
     for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
       const u32 slot = i & (nslot - 1), q = i >> K;
-      const u32 f = f0 + q;
-      if (f >= a.total_groups) continue;
-      const size_t col = f >> sub_bits, sub = f & ((1u << sub_bits) - 1);
-      a.out[col * a.out_stride + (sub << K) + slot] = bufA[caddr(slot, q, ldg)];
+      if (f0 + q >= a.total_groups) continue;
+      a.out[gaddr(slot, q, a.out_stride)] = bufA[caddr(slot, q, ldg)];
     }
     return;
   }
 
   for (int c = 0; c < a.ncoset; c++) {
     const uint2* __restrict__ sc = a.scale + ((size_t)c << a.logn);
-    // coefficient at bit-reversed position p gets shift_c^bitrev(p) / n
-#pragma unroll
-    for (int h = 0; h < ELEMS_PER_THREAD; h += 8) {
-      uint2 w[8];
-#pragma unroll
-      for (int it = 0; it < 8; it++) {
-        const u32 i = (h + it) * blockDim.x + threadIdx.x;
-        if (i < tile_elems) w[it] = __ldg(sc + ((((f0 + (i >> K)) & ((1u << sub_bits) - 1)) << K) + (i & (nslot - 1))));
-      }
-#pragma unroll
-      for (int it = 0; it < 8; it++) {
-        const u32 i = (h + it) * blockDim.x + threadIdx.x;
-        if (i < tile_elems) {
-          const u32 ad = caddr(i & (nslot - 1), i >> K, ldg);
-          bufB[ad] = shoup_mul(bufA[ad], w[it]).v;
-        }
+    u32* __restrict__ outc = a.out + (size_t)c * a.out_coset_stride;
+    // coefficient at bit-reversed position p gets shift_c^bitrev(p) / n, folded into the load of
+    // the first DIT round (bottom bits), which reads the coefficients from bufA
+    auto cload = [&](u32 slot, u32 q) {
+      const u32 sub = (f0 + q) & ((1u << sub_bits) - 1);
+      return shoup_mul(bufA[caddr(slot, q, ldg)], __ldg(sc + (((size_t)sub << K) + slot)));
+    };
+    auto gstore = [&](u32 slot, u32 q, Fp v) { if (f0 + q < a.total_groups) outc[gaddr(slot, q, a.out_stride)] = v.v; };
+    // ---- DIT: the same bit ranges bottom-up; the last round stores straight to global memory ----
+    constexpr int RL = round_bits(K, NR - 1);
+    if constexpr (NR == 1) {
+      if (a.bitrev_store) round_io<K, RL, 0, false, true>(logT, tw_b, cload, bstore);
+      else round_io<K, RL, 0, false, true>(logT, tw_b, cload, gstore);
+    } else {
+      round_io<K, RL, 0, false, true>(logT, tw_b, cload, bstore);
+      __syncthreads();
+      if constexpr (NR == 2) {
+        if (a.bitrev_store) round_io<K, R0, round_lo(K, 0), false, true>(logT, tw_b, bload, bstore);
+        else round_io<K, R0, round_lo(K, 0), false, true>(logT, tw_b, bload, gstore);
+      } else {
+        constexpr int R1 = round_bits(K, 1);
+        round_io<K, R1, round_lo(K, 1), false, true>(logT, tw_b, bload, bstore);
+        __syncthreads();
+        if (a.bitrev_store) round_io<K, R0, round_lo(K, 0), false, true>(logT, tw_b, bload, bstore);
+        else round_io<K, R0, round_lo(K, 0), false, true>(logT, tw_b, bload, gstore);
       }
     }
-    __syncthreads();
-    tile_transform<K, false, true>(bufB, logT, tw_b, ldg);
-    u32* __restrict__ outc = a.out + (size_t)c * a.out_coset_stride;
-    for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
-      const u32 o = i & (nslot - 1), q = i >> K;
-      const u32 f = f0 + q;
-      if (f >= a.total_groups) continue;
-      const size_t col = f >> sub_bits, sub = f & ((1u << sub_bits) - 1);
-      // bit-reversed store only happens when the whole column is one group
-      const u32 src = a.bitrev_store ? bitrev32(o, K) : o;
-      outc[col * a.out_stride + (sub << K) + o] = bufB[caddr(src, q, ldg)];
+    if (a.bitrev_store) {
+      // single level (the whole column is one group): rows leave in bit-reversed order
+      __syncthreads();
+      for (u32 i = threadIdx.x; i < tile_elems; i += blockDim.x) {
+        const u32 o = i & (nslot - 1), q = i >> K;
+        if (f0 + q >= a.total_groups) continue;
+        outc[gaddr(o, q, a.out_stride)] = bufB[caddr(bitrev32(o, K), q, ldg)];
+      }
     }
     __syncthreads();
   }

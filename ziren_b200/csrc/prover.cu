@@ -14,6 +14,8 @@
 
 namespace zkb {
 
+std::atomic<unsigned long long> g_kernel_launches{0};
+
 void Ctx::init(int dev, const u32* desc, size_t n) {
   device = dev;
   if (const char* e = getenv("ZKB200_LANES")) active_lanes = std::max(1, std::min(NUM_LANES, atoi(e)));
@@ -107,11 +109,13 @@ DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream
 }
 
 // TwoAdicFriPcs::commit: coset LDE (shift GENERATOR / domain_shift) of every matrix + MMCS tree.
-void pcs_commit(Ctx& ctx, Lane& L, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out) {
+void pcs_commit(Ctx& ctx, Lane& L, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out,
+                const char* lde_stage, const char* merkle_stage) {
   const unsigned lb = ctx.machine.log_blowup;
   std::vector<MatRef> refs;
   out.ldes.clear(); out.log_n.clear();
   Fp gen = fp_from_canonical(KB_GEN);
+  std::unique_ptr<StageTimer> tm(lde_stage ? new StageTimer(ctx, L, lde_stage) : nullptr);
   for (size_t i = 0; i < traces.size(); i++) {
     const DevMat& t = traces[i];
     unsigned ln = log2_exact(t.height);
@@ -124,9 +128,11 @@ void pcs_commit(Ctx& ctx, Lane& L, std::vector<DevMat>& traces, const std::vecto
     out.ldes.push_back(std::move(lde));
     out.log_n.push_back(ln);
   }
+  tm.reset(merkle_stage ? new StageTimer(ctx, L, merkle_stage) : nullptr);
   merkle_build(refs, L.arena, out.layers, L.d_small, L.stream);
   ZKB_CUDA(cudaMemcpyAsync(L.h_small, L.d_small, 32, cudaMemcpyDeviceToHost, L.stream));
   ZKB_CUDA(cudaStreamSynchronize(L.stream));
+  tm.reset();
   memcpy(out.root, L.h_small, 32);
   out.log_max_height = 0;
   for (auto& r : refs) out.log_max_height = std::max(out.log_max_height, r.log_height);
@@ -159,7 +165,7 @@ Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, co
     shifts.push_back(fp_one());
   }
   if (!prep.empty()) {
-    pcs_commit(ctx, L, pk->traces, shifts, pk->data);
+    pcs_commit(ctx, L, pk->traces, shifts, pk->data, nullptr, nullptr);
     for (int i = 0; i < 8; i++) pk->commit_canon[i] = fp_to_canonical(fp_raw(pk->data.root[i]));
   }
   pk->pc_start = pc_start;
@@ -199,9 +205,13 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
   LaneGuard guard(ctx);
   Lane& L = *guard.lane;
   L.arena.reset();
-  ZKB_CUDA(cudaStreamWaitEvent(L.stream, uploaded, 0));
+  if (ctx.profile) ctx.stage_ms.clear();
+  {
+    StageTimer tm(ctx, L, "commit_main_wait_upload");
+    ZKB_CUDA(cudaStreamWaitEvent(L.stream, uploaded, 0));
+  }
   cudaEventDestroy(uploaded);
-  pcs_commit(ctx, L, sh->traces, shifts, sh->main);
+  pcs_commit(ctx, L, sh->traces, shifts, sh->main, "commit_main_lde", "commit_main_merkle");
   sh->public_values.assign(pv, pv + npv);
   return sh.release();
 }
@@ -240,7 +250,6 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
   LaneGuard guard(ctx);
   Lane& L = *guard.lane;
   L.arena.reset();
-  if (ctx.profile) ctx.stage_ms.clear();
   cudaStream_t s = L.stream;
   const MachineInfo& M = ctx.machine;
   const unsigned lb = M.log_blowup;
@@ -298,9 +307,8 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
   }
   Commit perm_commit;
   {
-    StageTimer tm(ctx, L, "commit_permutation");
     std::vector<Fp> shifts(nc, fp_one());
-    pcs_commit(ctx, L, perm_traces, shifts, perm_commit);
+    pcs_commit(ctx, L, perm_traces, shifts, perm_commit, "commit_permutation_lde", "commit_permutation_merkle");
   }
   perm_traces.clear();
   ch.observe_digest(perm_commit.root);
@@ -341,8 +349,7 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
   }
   Commit quot_commit;
   {
-    StageTimer tm(ctx, L, "commit_quotient");
-    pcs_commit(ctx, L, quot_chunks, quot_shifts, quot_commit);
+    pcs_commit(ctx, L, quot_chunks, quot_shifts, quot_commit, "commit_quotient_lde", "commit_quotient_merkle");
   }
   quot_chunks.clear();
   ch.observe_digest(quot_commit.root);

@@ -86,7 +86,8 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& shard, u32* challeng
 
 // building blocks shared with the micro entry points
 DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream_t on, cudaStream_t free_on);
-void pcs_commit(Ctx& ctx, Lane& L, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out);
+void pcs_commit(Ctx& ctx, Lane& L, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out,
+                const char* lde_stage, const char* merkle_stage);
 
 // picks a free lane (or waits for lane 0) and holds it
 struct LaneGuard {

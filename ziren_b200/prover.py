@@ -175,6 +175,11 @@ class B200Prover:
         return [self.prove_shard(pk, tr, pv, base)[0] for tr, pv in records]
 
     # -- profiling ------------------------------------------------------------------------------
+    @staticmethod
+    def launch_count() -> int:
+        """CUDA kernels launched by libzkb200 in this process so far."""
+        return int(_ffi.lib().zkb200_launch_count())
+
     def set_profile(self, on: bool):
         _ffi.lib().zkb200_set_profile(self._h, int(on))
 

@@ -130,8 +130,27 @@ class ShardCase:
         return sum(4 * t.size for t in self.traces.values())
 
 
+def _plain_chip(name: str) -> Chip:
+    """No lookups at all and degree 2: log_quotient_degree 0, zero-width permutation trace."""
+    def ev(b):
+        x, y, z = b.main(0), b.main(1), b.main(2)
+        b.assert_zero(x * y - z)
+        b.when_transition().assert_eq(b.main(0, next=True), x + 2)
+    return Chip(name, 0, 3, ev)
+
+
+def _plain_trace(rng, log_height: int) -> np.ndarray:
+    n = 1 << log_height
+    t = np.empty((n, 3), dtype=np.uint32)
+    t[:, 0] = ((np.arange(n, dtype=np.uint64) * 2 + 5) % P).astype(np.uint32)
+    t[:, 1] = kb.random_elements(rng, n)
+    t[:, 2] = kb.mul(t[:, 0], t[:, 1])
+    return t
+
+
 def build_case(wides: list[WideSpec], *, with_fib: int | None = None, seed: int = 0xC0FFEE,
-               num_queries: int = 84, pow_bits: int = 16, cycles: int | None = None) -> ShardCase:
+               num_queries: int = 84, pow_bits: int = 16, cycles: int | None = None, log_blowup: int = 1,
+               plain: list[tuple[str, int]] = ()) -> ShardCase:
     """Assemble a machine from wide tables (+ optional Fibonacci/Sink pair of log height
     `with_fib`) and generate one balanced shard."""
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -175,7 +194,10 @@ def build_case(wides: list[WideSpec], *, with_fib: int | None = None, seed: int 
         sink[:n, :2] = rows[perm]
         sink[:n, 2] = 1
         traces["Sink"] = sink
-    machine = Machine(chips, num_pv_elts=4, num_queries=num_queries, pow_bits=pow_bits)
+    for name, lh in plain:
+        chips.append(_plain_chip(name))
+        traces[name] = _plain_trace(rng, lh)
+    machine = Machine(chips, num_pv_elts=4, num_queries=num_queries, pow_bits=pow_bits, log_blowup=log_blowup)
     if cycles is None:
         cycles = (1 << counter_specs[0].log_height) if counter_specs else 0
     return ShardCase(machine, prep, traces, pv, cycles)
@@ -200,6 +222,15 @@ def mini_case(seed: int = 1, **kw) -> ShardCase:
     kw.setdefault("num_queries", 8)
     kw.setdefault("pow_bits", 4)
     return build_case(wides, with_fib=4, seed=seed, **kw)
+
+
+def edge_case(seed: int = 7, **kw) -> ShardCase:
+    """Edge shapes: chips with no lookups (log_quotient_degree 0, zero-width permutation matrices,
+    one of them alone at its height), tiny tables (2^1 rows), equal heights ordered by name."""
+    wides = [WideSpec("Cpu", 5, 2, 2, 1, counter=True), WideSpec("Alu", 5, 1, 1, 0)]
+    kw.setdefault("num_queries", 6)
+    kw.setdefault("pow_bits", 3)
+    return build_case(wides, seed=seed, plain=[("PlainA", 7), ("PlainB", 5), ("PlainTiny", 1)], **kw)
 
 
 def fibonacci_core_case(log_cpu: int = 16, seed: int = 0xC0FFEE, **kw) -> ShardCase:
