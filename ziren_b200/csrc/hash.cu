@@ -22,6 +22,7 @@ static P2Consts make_consts() {
   const u32 diag[16] = {P - 2, 1, 2, (P + 1) >> 1, 3, 4, (P - 1) >> 1, P - 3, P - 4, P - ((P - 1) >> 8),
                         P - ((P - 1) >> 3), P - 127, (P - 1) >> 8, (P - 1) >> 3, (P - 1) >> 4, 127};
   for (int i = 0; i < 16; i++) c.diag[i] = m(diag[i]);
+  c.big = 0xffffffffu;
   return c;
 }
 const P2Consts& p2_host_consts() {

@@ -81,6 +81,16 @@ KB_HD Fp operator+(Fp a, Fp b) {
   u32 t = s - KB_P;
   return fp_raw(t < s ? t : s);  // umin(s, s - p): s - p wraps high when s < p
 }
+// Modular add whose first step is written as min(a + b, big) with big = 0xffffffff read at run
+// time: a no-op mathematically, but it makes the compiler emit the fused add-min (ALU pipe) instead
+// of IMAD.IADD on the FMA-heavy pipe, which Poseidon2 saturates with its multiplies
+// (profiles/README.md, "pipe steering").
+KB_HD Fp fp_add_alu(Fp a, Fp b, u32 big) {
+  u32 s = a.v + b.v;
+  s = s < big ? s : big;
+  u32 t = s - KB_P;
+  return fp_raw(t < s ? t : s);
+}
 KB_HD Fp operator-(Fp a, Fp b) {
   u32 s = a.v - b.v;
   u32 t = s + KB_P;

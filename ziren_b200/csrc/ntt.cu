@@ -21,6 +21,11 @@ static constexpr int TW_SPLIT = 12;
 static constexpr int KMAX = 12;             // largest in-tile transform
 static constexpr int ELEMS_PER_THREAD = 16;
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 __global__ void tw_init_kernel(u32* lo, u32* hi) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (1 << TW_SPLIT)) return;
@@ -120,7 +125,8 @@ __device__ __forceinline__ void butterflies(Fp* x, u32 bl, const uint2* __restri
       const int k = p & ((1 << lh) - 1);
       const int m0 = ((p >> lh) << (lh + 1)) | k;
       const int m1 = m0 + (1 << lh);
-      const uint2 w = tw[tbase + ((u32)k << (LO + sh))];
+      const u32 e = tbase + ((u32)k << (LO + sh));
+      const uint2 w = tw[e + (e >> 4)];          // padded: strided twiddle reads stay conflict-free
       if (DIF) {
         Fp a = x[m0], b = x[m1];
         x[m0] = a + b;
@@ -189,8 +195,10 @@ template <int K>
 __device__ __forceinline__ void fill_small_twiddles(uint2* tw, bool inverse, const uint2* __restrict__ small_tw) {
   constexpr u32 half = 1u << (K - 1);
   const uint2* src = small_tw + (inverse ? ((1u << KMAX_TAB) - 1) : 0) + (half - 1);
-  for (u32 m = threadIdx.x; m < half; m += blockDim.x) tw[m] = src[m];
+  for (u32 m = threadIdx.x; m < half; m += blockDim.x) tw[m + (m >> 4)] = src[m];
 }
+// words of shared memory taken by one padded twiddle table of a 2^K-point transform
+__host__ __device__ constexpr u32 tw_words(int K) { return ((1u << K) + ((1u << K) >> 4) + 4) & ~3u; }
 
 // ---- strided level -----------------------------------------------------------------------------
 struct StridedArgs {
@@ -212,7 +220,7 @@ __device__ __forceinline__ void strided_body(const StridedArgs& a, u32* smem) {
   constexpr u32 nslot = 1u << K;
   constexpr int NR = (K + 3) / 4;
   uint2* tw = reinterpret_cast<uint2*>(smem);
-  u32* data = smem + nslot;           // 2^(K-1) uint2 twiddles = nslot words
+  u32* data = smem + tw_words(K);
   const u32 tile_elems = nslot << logT;
   const u32* __restrict__ in = a.in + (size_t)blockIdx.y * a.in_stride + (size_t)blockIdx.z * a.in_coset_stride;
   u32* __restrict__ out = a.out + (size_t)blockIdx.y * a.out_stride + (size_t)blockIdx.z * a.out_coset_stride;
@@ -298,9 +306,9 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
   constexpr int NR = (K + 3) / 4;
   const u32 T = 1u << logT;
   constexpr u32 ldg = nslot + (nslot >> 3) + 1;
-  uint2* tw_a = reinterpret_cast<uint2*>(smem);            // first transform's twiddles (nslot words)
-  uint2* tw_b = reinterpret_cast<uint2*>(smem + nslot);    // forward twiddles for the fused DIT
-  u32* bufA = smem + 2 * nslot;
+  uint2* tw_a = reinterpret_cast<uint2*>(smem);                  // first transform's twiddles
+  uint2* tw_b = reinterpret_cast<uint2*>(smem + tw_words(K));    // forward twiddles for the fused DIT
+  u32* bufA = smem + 2 * tw_words(K);
   u32* bufB = bufA + (size_t)T * ldg;
   const u32 tile_elems = nslot << logT;
   const int sub_bits = a.logn - K;                 // groups per column = 2^sub_bits
@@ -387,10 +395,6 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
 }
 
 // ---- launch helpers ------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
 
 static void split_levels(int logn, int& K1, int& K2) {
   if (logn <= KMAX) { K1 = 0; K2 = logn; return; }
@@ -408,14 +412,15 @@ static void launch_strided(const NttTables& tb, const u32* in, size_t in_stride,
   a.four = (const uint2*)tb.four_step_table(K, logS, inverse, s);
   a.logS = logS; a.inverse = inverse ? 1 : 0; a.final_dit = final_dit ? 1 : 0;
   a.in_coset_stride = in_coset_stride; a.out_coset_stride = out_coset_stride;
-  int logT = 14 - K;                             // 16384 elements per tile, 32 offsets for K <= 9
+  static const int tile_log = env_int("ZKB200_NTT_STRIDED_TILE_LOG", 13);
+  int logT = tile_log - K;                       // 8192 elements (512 threads) per tile: two CTAs per SM
   if (logT > 5) logT = 5;
   if (logT > logS) logT = logS;
   if (logT < 0) logT = 0;
   a.logT = logT;
   const size_t tile_elems = (size_t)1 << (K + logT);
   unsigned threads = (unsigned)std::max<size_t>(32, tile_elems / ELEMS_PER_THREAD);
-  size_t smem = (((size_t)1 << K) + ((size_t)1 << (K + logT))) * sizeof(u32);
+  size_t smem = ((size_t)tw_words(K) + ((size_t)1 << (K + logT))) * sizeof(u32);
   dim3 grid(1u << (logS - logT), (unsigned)ncols, (unsigned)ncoset);
   static bool attr_done[KMAX + 1] = {false};
 #define ZKB_STRIDED_CASE(KK)                                                                                              \
@@ -440,14 +445,15 @@ static void launch_contig(const NttTables& tb, ContigArgs a, size_t ncols, cudaS
   const int K = a.K;
   const size_t groups = ncols << (a.logn - K);
   a.total_groups = (u32)groups;
-  int logT = 13 - K;
+  static const int ctile_log = env_int("ZKB200_NTT_CONTIG_TILE_LOG", 12);
+  int logT = ctile_log - K;
   if (logT < 0) logT = 0;
   while (logT > 0 && ((size_t)1 << logT) > groups) logT--;
   a.logT = logT;
   const size_t tile_elems = (size_t)1 << (K + logT);
   unsigned threads = (unsigned)std::max<size_t>(32, tile_elems / ELEMS_PER_THREAD);
   const size_t ldg = ((size_t)1 << K) + (((size_t)1 << K) >> 3) + 1;
-  size_t smem = (((size_t)2 << K) + ((size_t)(a.mode == 1 ? 2 : 1) << logT) * ldg) * sizeof(u32);
+  size_t smem = ((size_t)2 * tw_words(K) + ((size_t)(a.mode == 1 ? 2 : 1) << logT) * ldg) * sizeof(u32);
   unsigned grid = (unsigned)((groups + ((size_t)1 << logT) - 1) >> logT);
   static bool attr_done[KMAX + 1] = {false};
 #define ZKB_CONTIG_CASE(KK)                                                                                               \
@@ -513,8 +519,10 @@ void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* 
   int K1, K2;
   split_levels((int)log_n, K1, K2);
   const uint2* scale = (const uint2*)tb.scale_table(log_n, log_blowup, shift, s);
-  // column chunks: keep the A->B->C intermediates L2-resident
-  const size_t chunk_elems = (size_t)1 << std::min(30, std::max(10, env_int("ZKB200_NTT_CHUNK_LOG", 22)));
+  // column chunks bound the scratch (n x chunk x (1 + cosets) words).  The kernels are
+  // instruction-issue bound, not bandwidth bound, so large chunks (fewer, fuller launches) beat
+  // L2-resident ones: measured 3.3 ms at 2^26 vs 4.3 ms at 2^22 for 2^18 x 512 (profiles/README.md)
+  const size_t chunk_elems = (size_t)1 << std::min(30, std::max(10, env_int("ZKB200_NTT_CHUNK_LOG", 26)));
   size_t chunk = chunk_elems >> log_n;
   if (chunk < 1) chunk = 1;
   if (chunk > width) chunk = width;
