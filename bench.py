@@ -134,9 +134,9 @@ def main():
     ap.add_argument("--sample-log-cpu", type=int, default=14, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--value-threads", type=int, default=2,
+    ap.add_argument("--value-threads", type=int, default=3,
                     help="host threads proving device-resident shards concurrently in the `value` arm (compute lanes)")
-    ap.add_argument("--e2e-threads", type=int, default=2,
+    ap.add_argument("--e2e-threads", type=int, default=4,
                     help="host threads calling commit/open concurrently in the e2e arm (the reference keeps "
                          "shard_batch_size shards in flight, prove.rs:487-521): uploads of one shard overlap the open of another")
     ap.add_argument("--stages", action="store_true", help="print per-stage device times to stderr")
@@ -167,9 +167,11 @@ def main():
 
     # inputs: Montgomery row-major, once in pinned host memory (e2e arm), once resident in HBM
     host_tr = {}
-    for k, v in case.traces.items():
-        t = torch.from_numpy(kb.to_monty(v).view(np.int32)).pin_memory()
-        host_tr[k] = t
+    cfg = workload_config(args, case)
+    cells, shapes = case.cells, {k: v.shape for k, v in case.traces.items()}
+    for k in list(case.traces):
+        host_tr[k] = torch.from_numpy(kb.to_monty(case.traces[k]).view(np.int32)).pin_memory()
+        case.traces[k] = None          # the canonical copy is not needed any more (host RAM at 8 ranks)
     dev_tr = {k: v.cuda() for k, v in host_tr.items()}
     h2d_bytes = sum(4 * v.numel() for v in host_tr.values())
     torch.cuda.synchronize()
@@ -245,7 +247,7 @@ def main():
 
     roofline = roofline_other = cpu_base = None
     if args.rank == 0:
-        rl = stage_rooflines(case, stages or {})
+        rl = stage_rooflines(shapes, stages or {})
         ranked = sorted(rl.values(), key=lambda r: -r["ms"])
         if ranked:
             roofline, roofline_other = ranked[0], ranked[1:]
@@ -257,13 +259,13 @@ def main():
         line = {"metric": METRIC, "value": total_cycles / (ms_dev / 1e3), "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32 (KoalaBear 31-bit prime field)", "data": "synthetic",
-                "config": workload_config(args, case),
+                "config": cfg,
                 "e2e": {"value": total_cycles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                         "host_threads_in_flight": args.e2e_threads},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other,
                 "cpu_baseline": cpu_base,
-                "stage_ms": stages, "cells_per_sec": case.cells * args.steps * args.gpus / (ms_dev / 1e3)}
+                "stage_ms": stages, "cells_per_sec": cells * args.steps * args.gpus / (ms_dev / 1e3)}
         print(json.dumps(line))
     pk.free()
     prover.close()
@@ -271,7 +273,7 @@ def main():
         dist.destroy_process_group()
 
 
-def stage_rooflines(case, stages, log_blowup=1):
+def stage_rooflines(trace_shapes, stages, log_blowup=1):
     """HBM rooflines of the two dominant kernel families from the per-stage CUDA-event times of a
     live profiled step (zkb200_set_profile): K2 = Merkle build of the main commit, K1 = coset LDE of
     the main commit.  Algorithmic bytes per SURVEY.md section 8d."""
@@ -279,12 +281,12 @@ def stage_rooflines(case, stages, log_blowup=1):
     peak, which = 6650.0, "fallback (B200_PROFILING.md)"
     if os.path.exists(peaks_path):
         peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    shapes = [(t.shape[0] << log_blowup, t.shape[1]) for t in case.traces.values()]
+    shapes = [(h << log_blowup, w) for h, w in trace_shapes.values()]
     hmax = max(h for h, _ in shapes)
     inj_heights = sorted({h for h, _ in shapes if h < hmax})
     merkle_bytes = sum(4.0 * h * w for h, w in shapes) + 32.0 * hmax + 96.0 * (hmax - 1) + 64.0 * sum(inj_heights)
     perms = sum(h * (-(-w // 8)) for h, w in shapes) + (hmax - 1) + sum(inj_heights)
-    lde_bytes = sum(12.0 * t.shape[0] * t.shape[1] for t in case.traces.values())
+    lde_bytes = sum(12.0 * h * w for h, w in trace_shapes.values())
     out = {}
     for key, stage, alg, kern in (("k2_merkle", "commit_main_merkle", merkle_bytes, "merkle_build: leaf_hash_kernel + compress_kernel (Poseidon2 sponge / inject)"),
                                   ("k1_lde", "commit_main_lde", lde_bytes, "coset_lde_batch: ntt_strided_kernel + ntt_contig_kernel")):

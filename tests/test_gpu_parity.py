@@ -291,6 +291,28 @@ def test_concurrent_shards_are_independent(torch, mini, oracle):
     pk.free()
 
 
+@pytest.mark.parametrize("which", ["core", "compress", "keccak"])
+def test_reference_shapes_bit_exact(torch, oracle, which):
+    """the other BASELINE.json configs as parity cases at a size the oracle proves in seconds:
+    tendermint-like maximal core shape (18 execution tables + Byte + Program), recursion-compress
+    shape (Poseidon2Wide 313 columns), keccak-precompile shape (4167-column table)"""
+    from ziren_b200.prover import B200Prover
+    case = {"core": lambda: synthetic.core_case(log_cpu=9, seed=31, num_queries=5, pow_bits=6),
+            "compress": lambda: synthetic.compress_case(log_max=9, seed=32, num_queries=5, pow_bits=6),
+            "keccak": lambda: synthetic.keccak_case(log_cpu=8, seed=33, num_queries=5, pow_bits=6)}[which]()
+    prover = B200Prover(case.machine)
+    om = oracle.OracleMachine(case.machine)
+    om.setup(case.prep)
+    want, _ = om.prove_shard(case.traces, case.public_values)
+    pk = prover.setup({k: kb.to_monty(v) for k, v in case.prep.items()})
+    got, _ = prover.prove_shard(pk, {k: kb.to_monty(v) for k, v in case.traces.items()}, case.public_values)
+    assert np.array_equal(got, want)
+    ok, err = om.verify_shard(got)
+    assert ok, err
+    pk.free()
+    prover.close()
+
+
 def test_large_shard_is_accepted_by_the_verifier(torch, oracle):
     """Size-independent property at a size the CPU oracle cannot re-prove in test time: a
     keccak-precompile-like shard (Cpu 2^17 rows, KeccakSponge 2^15 x 4167 columns, 168 M cells, the

@@ -37,7 +37,7 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
   {
     size_t free_b = 0, total_b = 0;
     ZKB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t want = std::min<size_t>((size_t)64 << 30, free_b / 2);
+    size_t want = std::min<size_t>((size_t)112 << 30, free_b / 10 * 7);
     if (const char* e = getenv("ZKB200_POOL_GB")) want = std::min<size_t>((size_t)atol(e) << 30, free_b * 9 / 10);
     if (want) {
       void* p = nullptr;

@@ -34,12 +34,12 @@ struct Lane {
   u32* h_small = nullptr;            // pinned mirror
   std::mutex mu;
 };
-constexpr int NUM_LANES = 2;
+constexpr int NUM_LANES = 4;
 
 struct Ctx {
   int device = 0;
   Lane lanes[NUM_LANES];
-  int active_lanes = NUM_LANES;         // ZKB200_LANES=1 serialises all compute on one stream
+  int active_lanes = 3;                 // ZKB200_LANES=1 serialises all compute on one stream
   cudaStream_t copy_stream = nullptr;   // host->device uploads + layout change, overlaps the compute lanes
   std::mutex copy_mu;
   MachineInfo machine;

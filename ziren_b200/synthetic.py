@@ -278,3 +278,23 @@ def keccak_case(log_cpu: int = 20, log_keccak: int | None = None, seed: int = 0x
              tune_wide("SyscallInstrs", h - 8, 97, 6), tune_wide("SyscallCore", h - 8, 39, 3),
              tune_wide("KeccakSponge", lk, 4259, 40)]
     return build_case(wides, seed=seed, **kw)
+
+
+# recursion "compress" machine (BASELINE.json configs[4]); heights = shrink_shape of
+# crates/recursion/core/src/machine.rs:155-172, main widths: Poseidon2Wide 313 and BatchFRI 13 from
+# the reference (poseidon2_wide/columns/permutation.rs:22-34, chips/batch_fri.rs:39-56), the others
+# are stand-ins of plausible size (the real widths need the Rust derive macros).
+_COMPRESS = {"MemoryVar": (18, 8, 2), "Select": (18, 12, 2), "MemoryConst": (17, 6, 1), "BatchFRI": (17, 13, 2),
+             "BaseAlu": (17, 12, 2), "ExpReverseBitsLen": (17, 12, 2), "Poseidon2Wide": (16, 313, 8), "ExtAlu": (15, 24, 3),
+             "PublicValues": (4, 30, 1)}
+
+
+def compress_case(log_max: int = 18, seed: int = 0xC0FFEE, **kw) -> ShardCase:
+    """S5 'compress': one inner proof of the recursion machine, scaled so that the tallest table
+    has 2^log_max rows."""
+    d = 18 - log_max
+    wides = []
+    for name, (lh, width, lookups) in _COMPRESS.items():
+        groups = max(lookups, width // 6, 1)
+        wides.append(WideSpec(name, max(2, lh - d), groups, lookups, max(0, width - 6 * groups)))
+    return build_case(wides, seed=seed, cycles=0, **kw)
