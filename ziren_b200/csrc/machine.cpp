@@ -73,8 +73,9 @@ void MachineInfo::parse(const u32* words, size_t n) {
   }
 }
 
-// Lower one chip's constraint DAG to interpreter bytecode with linear-scan register reuse.
-static void lower_chip(ChipInfo& c, std::vector<Instr>& code) {
+// Lower one chip's constraint DAG to interpreter bytecode: leaves become tagged operands, inner
+// nodes get registers by linear scan, a SUB that is only asserted becomes ASSERT_SUB.
+static void lower_chip(ChipInfo& c, std::vector<Instr>& code, std::vector<u32>& consts) {
   const size_t nn = c.nodes.size();
   std::vector<char> reach(nn, 0);
   for (u32 k : c.constraints) reach[k] = 1;
@@ -83,8 +84,7 @@ static void lower_chip(ChipInfo& c, std::vector<Instr>& code) {
     const HostNode& nd = c.nodes[i];
     if (nd.op >= N_ADD) { reach[nd.a] = 1; if (nd.op != N_NEG) reach[nd.b] = 1; }
   }
-  // number of remaining consumers per node (ops only; asserts are emitted right after the definition)
-  std::vector<u32> uses(nn, 0);
+  std::vector<u32> uses(nn, 0);   // remaining consumers among op nodes
   for (size_t i = 0; i < nn; i++) {
     if (!reach[i]) continue;
     const HostNode& nd = c.nodes[i];
@@ -96,37 +96,54 @@ static void lower_chip(ChipInfo& c, std::vector<Instr>& code) {
   std::vector<int> reg(nn, -1);
   std::vector<u32> free_regs;
   u32 n_regs = 0;
+  c.const_begin = (u32)consts.size();
   auto alloc = [&]() { if (!free_regs.empty()) { u32 r = free_regs.back(); free_regs.pop_back(); return r; } return n_regs++; };
-  auto emit = [&](u32 op, u32 dst, u32 a, u32 b) { code.push_back(Instr{(op << 24) | dst, a, b}); };
-  auto materialize = [&](u32 id) {
-    if (reg[id] >= 0) return;
-    const HostNode& nd = c.nodes[id];
-    u32 r = alloc();
-    reg[id] = (int)r;
-    u32 a = nd.a;
-    if (nd.op == N_CONST) a = fp_from_canonical(nd.a % KB_P).v;
-    emit(nd.op, r, a, nd.b);
-    for (u32 k : asserts_of[id]) emit(OP_ASSERT, 0, r, k);
+  auto emit = [&](u32 op, u32 dst, u32 a, u32 b, u32 k) { code.push_back(Instr{(op << 24) | dst, a, b, k}); };
+  auto tag = [](u32 kind, u32 idx) {
+    if (idx >= (1u << 29)) throw std::runtime_error("zkb200: operand index out of range");
+    return (kind << 29) | idx;
   };
-  auto release = [&](u32 id) { if (--uses[id] == 0) { free_regs.push_back((u32)reg[id]); } };
+  auto operand = [&](u32 id) -> u32 {
+    const HostNode& nd = c.nodes[id];
+    switch (nd.op) {
+      case N_CONST: consts.push_back(fp_from_canonical(nd.a % KB_P).v); return tag(O_CONST, (u32)consts.size() - 1);
+      case N_MAIN: return tag(nd.b ? O_MAIN_NEXT : O_MAIN, nd.a);
+      case N_PREP: return tag(nd.b ? O_PREP_NEXT : O_PREP, nd.a);
+      case N_PUB: return tag(O_PUB, nd.a);
+      case N_IS_FIRST: return tag(O_SEL, 0);
+      case N_IS_LAST: return tag(O_SEL, 1);
+      case N_IS_TRANS: return tag(O_SEL, 2);
+      default:
+        if (reg[id] < 0) throw std::runtime_error("zkb200: internal: operand used before definition");
+        return tag(O_REG, (u32)reg[id]);
+    }
+  };
+  auto release = [&](u32 id) {
+    if (c.nodes[id].op < N_ADD) return;          // leaves hold no register
+    if (--uses[id] == 0) free_regs.push_back((u32)reg[id]);
+  };
   c.code_begin = (u32)code.size();
   for (size_t i = 0; i < nn; i++) {
     if (!reach[i]) continue;
     const HostNode& nd = c.nodes[i];
     if (nd.op < N_ADD) {
-      // leaves are materialised lazily at first use; a leaf asserted directly has no consumer
-      if (uses[i] == 0) { materialize((u32)i); free_regs.push_back((u32)reg[i]); }
+      for (u32 k : asserts_of[i]) emit(I_ASSERT, 0, operand((u32)i), 0, k);
       continue;
     }
-    materialize(nd.a);
-    if (nd.op != N_NEG) materialize(nd.b);
-    u32 ra = (u32)reg[nd.a], rb = nd.op != N_NEG ? (u32)reg[nd.b] : 0;
+    const u32 oa = operand(nd.a), ob = nd.op != N_NEG ? operand(nd.b) : 0;
+    if (nd.op == N_SUB && uses[i] == 0) {
+      // only asserted: fold the subtraction into the assert
+      for (u32 k : asserts_of[i]) emit(I_ASSERT_SUB, 0, oa, ob, k);
+      release(nd.a); release(nd.b);
+      continue;
+    }
     release(nd.a);
     if (nd.op != N_NEG) release(nd.b);
-    u32 r = alloc();
+    const u32 r = alloc();
     reg[i] = (int)r;
-    emit(nd.op, r, ra, rb);
-    for (u32 k : asserts_of[i]) emit(OP_ASSERT, 0, r, k);
+    const u32 op = nd.op == N_ADD ? I_ADD : nd.op == N_SUB ? I_SUB : nd.op == N_MUL ? I_MUL : I_NEG;
+    emit(op, r, oa, ob, 0);
+    for (u32 k : asserts_of[i]) emit(I_ASSERT, 0, tag(O_REG, r), 0, k);
     if (uses[i] == 0) free_regs.push_back(r);
   }
   c.code_end = (u32)code.size();
@@ -138,6 +155,7 @@ void MachineInfo::upload() {
   std::vector<DevVPC> vpcs;
   std::vector<DevLookup> lookups;
   std::vector<Instr> code;
+  std::vector<u32> consts;
   auto add_vpc = [&](const HostVPC& v) {
     DevVPC d;
     d.constant = fp_from_canonical(v.const_canon % KB_P).v;
@@ -162,7 +180,7 @@ void MachineInfo::upload() {
       lookups.push_back(d);
     }
     c.dev_lookup_end = (u32)lookups.size();
-    lower_chip(c, code);
+    lower_chip(c, code, consts);
   }
   auto up = [](auto*& dptr, const auto& v) {
     using T = typename std::remove_reference<decltype(v)>::type::value_type;
@@ -174,6 +192,7 @@ void MachineInfo::upload() {
   up(d_vpcs, vpcs);
   up(d_lookups, lookups);
   up(d_code, code);
+  up(d_consts, consts);
 }
 
 void MachineInfo::destroy() {
@@ -181,6 +200,8 @@ void MachineInfo::destroy() {
   if (d_vpcs) cudaFree(d_vpcs);
   if (d_lookups) cudaFree(d_lookups);
   if (d_code) cudaFree(d_code);
+  if (d_consts) cudaFree(d_consts);
+  d_consts = nullptr;
   d_terms = nullptr; d_vpcs = nullptr; d_lookups = nullptr; d_code = nullptr;
 }
 

@@ -25,18 +25,18 @@ struct DevTerm { u32 col; u32 w; };                 // col: bit 31 set = main tr
 struct DevVPC { u32 constant; u32 term_begin, term_end; };
 struct DevLookup { u32 kind; u32 is_send; u32 mult_vpc; u32 value_begin, value_end; };   // kind Montgomery
 
-// Bytecode of the constraint interpreter: registers hold base-field values.
-//   op  | meaning
-//   0   | r[dst] = const imm (Montgomery, in `a`)
-//   1   | r[dst] = main[a] at row offset b (0 local, 1 next)
-//   2   | r[dst] = prep[a] at row offset b
-//   3   | r[dst] = public value a
-//   4-6 | r[dst] = is_first / is_last / is_transition
-//   7-9 | r[dst] = r[a] (+,-,*) r[b]
-//   10  | r[dst] = -r[a]
-//   11  | assert_zero(r[a]): acc += alpha_pow[next++] * r[a]
-struct Instr { u32 op_dst; u32 a, b; };             // op in the top 8 bits of op_dst, dst in the low 24
-constexpr u32 OP_ASSERT = 11;
+// Bytecode of the constraint interpreter (K3).  16-byte instructions {op|dst, a, b, c}; operands
+// are tagged references, so trace columns, public values, selectors and constants are read where
+// they are used instead of through separate load instructions:
+//   operand = kind << 29 | index     kind 0 register, 1 main local col, 2 main next col,
+//                                         3 prep local col, 4 prep next col, 5 constant-pool slot,
+//                                         6 public value, 7 selector (0 first, 1 last, 2 transition)
+//   op 0 ADD  1 SUB  2 MUL : r[dst] = a (op) b          3 NEG : r[dst] = -a
+//   op 4 ASSERT            : acc += alpha_pow[c] * a     (assert_zero, folder.rs:79-84)
+//   op 5 ASSERT_SUB        : acc += alpha_pow[c] * (a - b)   (assert_eq / "x*y - z" in one step)
+struct Instr { u32 op_dst; u32 a, b, c; };
+enum InstrOp : u32 { I_ADD = 0, I_SUB = 1, I_MUL = 2, I_NEG = 3, I_ASSERT = 4, I_ASSERT_SUB = 5 };
+enum OperandKind : u32 { O_REG = 0, O_MAIN = 1, O_MAIN_NEXT = 2, O_PREP = 3, O_PREP_NEXT = 4, O_CONST = 5, O_PUB = 6, O_SEL = 7 };
 
 struct ChipInfo {
   std::string name;
@@ -61,6 +61,7 @@ struct ChipInfo {
   u32 max_values = 0;                             // longest lookup tuple
   u32 code_begin = 0, code_end = 0;               // range in the machine-wide Instr table
   u32 n_regs = 0;
+  u32 const_begin = 0;                            // first slot of this chip in the constant pool
 };
 
 struct MachineInfo {
@@ -72,6 +73,7 @@ struct MachineInfo {
   DevVPC* d_vpcs = nullptr;
   DevLookup* d_lookups = nullptr;
   Instr* d_code = nullptr;
+  u32* d_consts = nullptr;      // constant pool, Montgomery
 
   void parse(const u32* words, size_t n);
   void upload();       // lower + copy tables to the current device

@@ -16,6 +16,7 @@ struct QuotArgs {
   const Instr* code; u32 code_begin, code_end, n_air;
   const DevTerm* terms; const DevVPC* vpcs; const DevLookup* lookups; u32 lk_begin, lk_end;
   const u32* alpha_pow;   // [C][4] Montgomery: alpha^(C-1-k)
+  const u32* consts;      // constant pool (Montgomery)
   const u32* pub;
   const u32* tw_lo; const u32* tw_hi;
   Ef perm_alpha, local_sum;
@@ -48,7 +49,7 @@ __device__ __forceinline__ Ef load_apow(const u32* ap, u32 k) {
   return e;
 }
 
-constexpr int QCHUNK = 1024;   // 12 KB of bytecode per stage
+constexpr int QCHUNK = 1024;   // 16 KB of bytecode per stage
 
 template <int NREGS>
 __global__ void __launch_bounds__(128) quotient_kernel(QuotArgs a) {
@@ -70,41 +71,46 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotArgs a) {
   Fp regs[NREGS];
   EfAcc lazy;     // base-field constraints: alpha-power x value, reduced every fourth assert
   lazy.clear();
+  // operands are tagged references (machine.h): registers, trace columns at the local / next
+  // row, constants, public values, selectors
+  auto fetch = [&](u32 o) -> Fp {
+    const u32 idx = o & 0x1fffffffu;
+    switch (o >> 29) {
+      case O_REG: return regs[idx];
+      case O_MAIN: return fp_raw(a.main_[(size_t)idx * a.H + t]);
+      case O_MAIN_NEXT: return fp_raw(a.main_[(size_t)idx * a.H + tn]);
+      case O_PREP: return fp_raw(a.prep[(size_t)idx * a.H + t]);
+      case O_PREP_NEXT: return fp_raw(a.prep[(size_t)idx * a.H + tn]);
+      case O_CONST: return fp_raw(__ldg(a.consts + idx));
+      case O_PUB: return fp_raw(__ldg(a.pub + idx));
+      default: return idx == 0 ? is_first : idx == 1 ? is_last : is_trans;
+    }
+  };
   // the bytecode is staged through shared memory in chunks: every thread runs the same
   // instruction stream, so one cooperative copy replaces a dependent global load per instruction
-  __shared__ Instr sh_code[QCHUNK];
+  __shared__ uint4 sh_code[QCHUNK];
   for (u32 cbase = a.code_begin; cbase < a.code_end; cbase += QCHUNK) {
-  const u32 cn = min((u32)QCHUNK, a.code_end - cbase);
-  __syncthreads();
-  {
-    const u32* src = reinterpret_cast<const u32*>(a.code + cbase);
-    u32* dstw = reinterpret_cast<u32*>(sh_code);
-    for (u32 w = threadIdx.x; w < 3 * cn; w += blockDim.x) dstw[w] = __ldg(src + w);
-  }
-  __syncthreads();
-  for (u32 pc = 0; pc < cn; pc++) {
-    Instr ins = sh_code[pc];
-    const u32 op = ins.op_dst >> 24, dst = ins.op_dst & 0xffffffu;
-    Fp v;
-    switch (op) {
-      case N_CONST: v = fp_raw(ins.a); break;
-      case N_MAIN: v = fp_raw(a.main_[(size_t)ins.a * a.H + (ins.b ? tn : t)]); break;
-      case N_PREP: v = fp_raw(a.prep[(size_t)ins.a * a.H + (ins.b ? tn : t)]); break;
-      case N_PUB: v = fp_raw(__ldg(a.pub + ins.a)); break;
-      case N_IS_FIRST: v = is_first; break;
-      case N_IS_LAST: v = is_last; break;
-      case N_IS_TRANS: v = is_trans; break;
-      case N_ADD: v = regs[ins.a] + regs[ins.b]; break;
-      case N_SUB: v = regs[ins.a] - regs[ins.b]; break;
-      case N_MUL: v = regs[ins.a] * regs[ins.b]; break;
-      case N_NEG: v = -regs[ins.a]; break;
-      default: {  // OP_ASSERT
-        lazy.add(load_apow(a.alpha_pow, ins.b), regs[ins.a]);
-        continue;
-      }
+    const u32 cn = min((u32)QCHUNK, a.code_end - cbase);
+    __syncthreads();
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(a.code + cbase);
+      for (u32 w = threadIdx.x; w < cn; w += blockDim.x) sh_code[w] = __ldg(src + w);
     }
-    regs[dst] = v;
-  }
+    __syncthreads();
+    for (u32 pc = 0; pc < cn; pc++) {
+      const uint4 ins = sh_code[pc];
+      const u32 op = ins.x >> 24, dst = ins.x & 0xffffffu;
+      if (op == I_ASSERT) { lazy.add(load_apow(a.alpha_pow, ins.w), fetch(ins.y)); continue; }
+      if (op == I_ASSERT_SUB) { lazy.add(load_apow(a.alpha_pow, ins.w), fetch(ins.y) - fetch(ins.z)); continue; }
+      const Fp x = fetch(ins.y);
+      Fp v;
+      if (op == I_NEG) v = -x;
+      else {
+        const Fp y = fetch(ins.z);
+        v = op == I_ADD ? x + y : op == I_SUB ? x - y : x * y;
+      }
+      regs[dst] = v;
+    }
   }
 
   Ef acc = lazy.value();
@@ -183,7 +189,7 @@ void quotient_values(const MachineInfo& m, const ChipInfo& chip, const NttTables
   if (a.lqd > 4) throw std::runtime_error("zkb200: log_quotient_degree > 4 unsupported");
   a.code = m.d_code; a.code_begin = chip.code_begin; a.code_end = chip.code_end; a.n_air = (u32)chip.constraints.size();
   a.terms = m.d_terms; a.vpcs = m.d_vpcs; a.lookups = m.d_lookups; a.lk_begin = chip.dev_lookup_begin; a.lk_end = chip.dev_lookup_end;
-  a.pub = in.pub_dev; a.tw_lo = tb.tw_lo; a.tw_hi = tb.tw_hi;
+  a.pub = in.pub_dev; a.consts = m.d_consts; a.tw_lo = tb.tw_lo; a.tw_hi = tb.tw_hi;
   a.perm_alpha = in.perm_alpha; a.local_sum = in.local_sum;
   a.bpow[0] = ef_one();
   for (int i = 1; i < 17; i++) a.bpow[i] = a.bpow[i - 1] * in.perm_beta;
