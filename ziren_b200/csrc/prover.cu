@@ -187,28 +187,49 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     if (!c) throw std::runtime_error("zkb200: commit: unknown chip " + t.name);
     if (c->main_width != t.width) throw std::runtime_error("zkb200: commit: main width mismatch for " + t.name);
   }
-  // Phase 1 (copy stream, its own lock): host->device upload + layout change.  Another host
-  // thread may hold the compute stream (open of the previous shard) meanwhile, the way the
+  // Phase 1 (copy stream, its own lock): host->device DMA only, so the copy engine is never held
+  // up waiting for SM slots.  Other host threads may hold the compute lanes meanwhile, the way the
   // reference keeps several shards in flight (crates/core/machine/src/utils/prove.rs:487-521).
+  struct Staged { const u32* src; DevBuf stage; };   // src: row-major device pointer to transpose from
+  std::vector<Staged> staged;
   cudaEvent_t uploaded;
   ZKB_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
   {
     std::lock_guard<std::mutex> lock(ctx.copy_mu);
     for (auto& t : traces) {
-      sh->names.push_back(t.name);
-      sh->traces.push_back(upload_colmajor(ctx, t.data, t.height, t.width, ctx.copy_stream, ctx.lanes[0].stream));
-      shifts.push_back(fp_one());
+      Staged st;
+      st.src = t.data;
+      cudaPointerAttributes attr;
+      bool on_device = false;
+      if (cudaPointerGetAttributes(&attr, t.data) == cudaSuccess) on_device = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+      else cudaGetLastError();
+      if (!on_device && t.height * t.width) {
+        st.stage = DevBuf(t.height * t.width, ctx.copy_stream);
+        ZKB_CUDA(cudaMemcpyAsync(st.stage.p, t.data, t.height * t.width * sizeof(u32), cudaMemcpyHostToDevice, ctx.copy_stream));
+        st.src = st.stage.p;
+      }
+      staged.push_back(std::move(st));
     }
     ZKB_CUDA(cudaEventRecord(uploaded, ctx.copy_stream));
   }
-  // Phase 2 (a compute lane): LDE + Merkle tree
+  // Phase 2 (a compute lane): layout change, LDE + Merkle tree
   LaneGuard guard(ctx);
   Lane& L = *guard.lane;
   L.arena.reset();
   if (ctx.profile) ctx.stage_ms.clear();
   {
-    StageTimer tm(ctx, L, "commit_main_wait_upload");
+    StageTimer tm(ctx, L, "commit_main_wait_upload_transpose");
     ZKB_CUDA(cudaStreamWaitEvent(L.stream, uploaded, 0));
+    for (size_t i = 0; i < traces.size(); i++) {
+      const TraceIn& t = traces[i];
+      DevMat m(t.height, t.width, L.stream);
+      if (t.height * t.width) transpose_to_colmajor(staged[i].src, m.d(), t.height, t.width, L.stream);
+      staged[i].stage.stream = L.stream;     // released in lane order, after the transpose
+      staged[i].stage.release();
+      sh->names.push_back(t.name);
+      sh->traces.push_back(std::move(m));
+      shifts.push_back(fp_one());
+    }
   }
   cudaEventDestroy(uploaded);
   pcs_commit(ctx, L, sh->traces, shifts, sh->main, "commit_main_lde", "commit_main_merkle");
