@@ -71,9 +71,10 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const MatRef* __restrict
   for (int j = 0; j < 8; j++) out[j * height + r] = st[j].v;
 }
 
-// next[i] = compress(prev[2i], prev[2i+1]); optionally then compress(., hash(rows i of `mats`))
+// next[i] = compress(prev[2i], prev[2i+1]); optionally then compress(., inject[i]) where inject holds
+// the row digests of the matrices of this height (hashed by leaf_hash_kernel, word-major)
 __global__ void __launch_bounds__(128) compress_kernel(const u32* __restrict__ prev, u32* __restrict__ next, size_t m,
-                                                       const MatRef* __restrict__ mats, int nmats) {
+                                                       const u32* __restrict__ inject) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= m) return;
   Fp st[16];
@@ -84,15 +85,38 @@ __global__ void __launch_bounds__(128) compress_kernel(const u32* __restrict__ p
     st[8 + j] = fp_raw(pr.y);
   }
   p2_permute_dev(st);
-  if (nmats > 0) {
-    Fp h[16];
-    sponge_rows(mats, nmats, m, i, h);
+  if (inject) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) st[8 + j] = h[j];
+    for (int j = 0; j < 8; j++) st[8 + j] = fp_raw(inject[j * m + i]);
     p2_permute_dev(st);
   }
 #pragma unroll
   for (int j = 0; j < 8; j++) next[j * m + i] = st[j].v;
+}
+
+// The row-hashing kernel runs one long-lived thread per row (hundreds of permutations), so a
+// partially filled last wave costs real time: 2^19 rows are 4096 CTAs = 1.73 waves at 16 CTAs/SM
+// but 1.98 waves at 14.  Pick the residency (12..16 CTAs per SM, enforced through a dynamic
+// shared-memory reservation) whose last wave is fullest.
+static size_t leaf_smem_for(size_t nblocks) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int best_b = 16;
+  double best_eff = 0;
+  for (int b = 16; b >= 12; b--) {
+    double waves = (double)nblocks / ((double)sms * b);
+    double eff = waves / (double)(size_t)(waves + 0.999999);
+    if (waves <= 1.0) eff = 1.0;
+    if (eff > best_eff + 0.02) { best_eff = eff; best_b = b; }
+  }
+  if (best_b == 16) return 0;
+  return ((size_t)227 * 1024 / best_b - 1024) & ~(size_t)1023;   // leaves room for exactly best_b CTAs
+}
+static void launch_leaf_hash(const MatRef* mats_dev, int nmats, size_t height, u32* out, cudaStream_t s) {
+  const unsigned nblocks = ceil_div(height, 128);
+  leaf_hash_kernel<<<nblocks, 128, leaf_smem_for(nblocks), s>>>(mats_dev, nmats, height, out);
+  ZKB_CHECK_LAUNCH();
 }
 
 // The top of a tree (<= 512 nodes wide, no injections) in one CTA: levels separated by
@@ -148,8 +172,9 @@ static void build_upper(DigestLayers& out, unsigned max_log, const std::map<unsi
       l = l2;
       continue;
     }
-    compress_kernel<<<ceil_div(m, 128), 128, 0, s>>>(out.layer(l - 1), out.layer(l), m, inject ? dev_groups[lh] : nullptr,
-                                                     inject ? (int)groups.at(lh).size() : 0);
+    DevBuf inj(inject ? 8 * m : 0, s);
+    if (inject) launch_leaf_hash(dev_groups[lh], (int)groups.at(lh).size(), m, inj.p, s);
+    compress_kernel<<<ceil_div(m, 128), 128, 0, s>>>(out.layer(l - 1), out.layer(l), m, inject ? inj.p : nullptr);
     ZKB_CHECK_LAUNCH();
     l++;
   }
@@ -166,8 +191,7 @@ void merkle_build(const std::vector<MatRef>& mats, ParamArena& arena, DigestLaye
   for (auto& g : groups) dev_groups[g.first] = arena.push(g.second.data(), g.second.size());
   alloc_layers(out, max_log, s);
   size_t h = (size_t)1 << max_log;
-  leaf_hash_kernel<<<ceil_div(h, 128), 128, 0, s>>>(dev_groups[max_log], (int)groups[max_log].size(), h, out.layer(0));
-  ZKB_CHECK_LAUNCH();
+  launch_leaf_hash(dev_groups[max_log], (int)groups[max_log].size(), h, out.layer(0), s);
   std::map<unsigned, std::vector<MatRef>> inj = groups;
   inj.erase(max_log);
   build_upper(out, max_log, inj, dev_groups, root_dev, s);

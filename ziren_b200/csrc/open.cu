@@ -24,7 +24,7 @@ void bary_weights(const NttTables& tb, unsigned log_n, const Ef& z, u32* out, cu
 }
 
 // ---- column evaluation --------------------------------------------------------------------------
-constexpr int EC_COLS = 8;       // columns per CTA
+constexpr int EC_COLS = 4;       // columns per CTA
 constexpr int EC_THREADS = 256;
 
 template <int NPT>
@@ -187,10 +187,33 @@ __global__ void __launch_bounds__(128) reduce_matrix_kernel(const u32* __restric
                                                             const u32* __restrict__ invden1, u32* __restrict__ ro) {
   size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (x >= H) return;
-  EfAcc lazy;
-  lazy.clear();
-  for (size_t j = 0; j < W; j++) lazy.add(ldg_ef(apow, j), fp_raw(lde[j * H + x]));
-  Ef acc = lazy.value();
+  // eight columns per iteration: the eight loads are independent and issued together, and every
+  // group of four products is reduced once (4 p^2 < 2^64)
+  Ef acc = ef_zero();
+  size_t j = 0;
+  for (; j + 8 <= W; j += 8) {
+    u32 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = lde[(j + u) * H + x];
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      u64 s[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const Ef a = ldg_ef(apow, j + 4 * g + u);
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[k] += (u64)a.c[k].v * v[4 * g + u];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc.c[k] += fp_raw(mont_reduce_wide(s[k]));
+    }
+  }
+  if (j < W) {
+    EfAcc lazy;
+    lazy.clear();
+    for (; j < W; j++) lazy.add(ldg_ef(apow, j), fp_raw(lde[j * H + x]));
+    acc += lazy.value();
+  }
   Ef r;
 #pragma unroll
   for (int c = 0; c < 4; c++) r.c[c] = fp_raw(ro[(size_t)c * H + x]);
