@@ -247,16 +247,18 @@ def test_fibonacci_core_shard_bit_exact(torch, oracle, seed, log_cpu):
     prover.close()
 
 
-@pytest.mark.parametrize("which", ["edge", "edge_blowup2", "mini_blowup2", "mini_blowup3"])
+@pytest.mark.parametrize("which", ["edge", "edge_blowup2", "mini_blowup2", "mini_blowup3", "noprep"])
 def test_edge_machines_bit_exact(torch, oracle, which):
     """chips without lookups (log_quotient_degree 0, zero-width permutation matrices), 2-row tables,
+    a machine without any preprocessed table (empty proving-key commitment),
     FRI blow-up 4 and 8 (the reference's compressed()/ultra_compressed() configs,
     crates/stark/src/kb31_poseidon2.rs:217-241)."""
     from ziren_b200.prover import B200Prover
     case = {"edge": lambda: synthetic.edge_case(),
             "edge_blowup2": lambda: synthetic.edge_case(log_blowup=2),
             "mini_blowup2": lambda: synthetic.mini_case(seed=9, log_blowup=2, num_queries=5),
-            "mini_blowup3": lambda: synthetic.mini_case(seed=10, log_blowup=3, num_queries=4)}[which]()
+            "mini_blowup3": lambda: synthetic.mini_case(seed=10, log_blowup=3, num_queries=4),
+            "noprep": lambda: synthetic.noprep_case()}[which]()
     prover = B200Prover(case.machine)
     om = oracle.OracleMachine(case.machine)
     om.setup(case.prep)

@@ -9,8 +9,10 @@
 //   A  strided DIF (inverse twiddles)                       evaluations      -> half-transformed
 //   B  contiguous DIF  ->  x shift_c^i / n  ->  contiguous DIT, once per coset c (fused in smem)
 //   C  strided DIT with the BIT-REVERSED store of the committed row order
-// (n <= 2^12: B alone, storing bit-reversed).  Column chunks are sized so that the traffic
-// between A, B and C stays in the 126 MB L2: HBM sees ~ read n + write 2n per column.
+// (n <= 2^12: B alone, storing bit-reversed).  The first radix round of a level reads straight from
+// global memory and the last one writes straight to it.  The kernels are bound by integer
+// instruction issue, not by HBM (profiles/README.md), so columns are processed in large chunks
+// (2^26 elements) that keep every launch several waves deep rather than L2-sized ones.
 #include "ntt.h"
 #include <algorithm>
 #include <cstdlib>

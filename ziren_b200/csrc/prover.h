@@ -44,7 +44,6 @@ struct Ctx {
   std::mutex copy_mu;
   MachineInfo machine;
   NttTables tables;
-  std::string err;
   // statistics of the last open(): kernel-stage timings (ms) when profiling is enabled
   bool profile = false;
   std::vector<std::pair<std::string, float>> stage_ms;

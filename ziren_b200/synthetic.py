@@ -233,6 +233,30 @@ def edge_case(seed: int = 7, **kw) -> ShardCase:
     return build_case(wides, seed=seed, plain=[("PlainA", 7), ("PlainB", 5), ("PlainTiny", 1)], **kw)
 
 
+def noprep_case(seed: int = 5, **kw) -> ShardCase:
+    """A machine with NO preprocessed table at all (empty proving-key commitment, three opening
+    rounds instead of four): Fibonacci + Sink + two plain chips."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    kw.setdefault("num_queries", 5)
+    kw.setdefault("pow_bits", 3)
+    n = 1 << 5
+    a, b_ = 0, 1
+    rows = np.empty((n, 2), dtype=np.uint32)
+    for i in range(n):
+        rows[i] = (a, b_)
+        a, b_ = b_, (a + b_) % P
+    pv = np.zeros(8, dtype=np.uint32)
+    pv[1], pv[2], pv[3] = 0, 1, rows[-1, 1]
+    sink = np.zeros((n, 3), dtype=np.uint32)
+    sink[:, :2] = rows[rng.permutation(n)]
+    sink[:, 2] = 1
+    chips = [_fib_chip(), _sink_chip(), _plain_chip("PlainA"), _plain_chip("PlainB")]
+    traces = {"Fibonacci": rows, "Sink": sink, "PlainA": _plain_trace(rng, 6), "PlainB": _plain_trace(rng, 3)}
+    machine = Machine(chips, num_pv_elts=4, num_queries=kw["num_queries"], pow_bits=kw["pow_bits"],
+                      log_blowup=kw.get("log_blowup", 1))
+    return ShardCase(machine, {}, traces, pv, 0)
+
+
 def fibonacci_core_case(log_cpu: int = 16, seed: int = 0xC0FFEE, **kw) -> ShardCase:
     """S1 'fib-2^16' (SURVEY.md §8d): a single small core shard."""
     h = log_cpu
