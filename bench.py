@@ -288,7 +288,7 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1):
     perms = sum(h * (-(-w // 8)) for h, w in shapes) + (hmax - 1) + sum(inj_heights)
     lde_bytes = sum(12.0 * h * w for h, w in trace_shapes.values())
     out = {}
-    for key, stage, alg, kern in (("k2_merkle", "commit_main_merkle", merkle_bytes, "merkle_build: leaf_hash_kernel + compress_kernel (Poseidon2 sponge / inject)"),
+    for key, stage, alg, kern in (("k2_merkle", "commit_main_merkle", merkle_bytes, "merkle_build: leaf_hash_kernel (Poseidon2 sponge over the rows of every height) + compress_kernel"),
                                   ("k1_lde", "commit_main_lde", lde_bytes, "coset_lde_batch: ntt_strided_kernel + ntt_contig_kernel")):
         ms = stages.get(stage)
         if not ms:
