@@ -251,7 +251,7 @@ def main():
         ranked = sorted(rl.values(), key=lambda r: -r["ms"])
         if ranked:
             roofline, roofline_other = ranked[0], ranked[1:]
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.world == 1:      # reported at N=1 only (other ranks would contend for the cores)
             cpu_base = measure_cpu_baseline(args)
 
     if args.rank == 0:
@@ -270,6 +270,7 @@ def main():
     pk.free()
     prover.close()
     if distributed:
+        dist.barrier()          # ranks leave together (rank 0 may still have been timing the CPU baseline)
         dist.destroy_process_group()
 
 
