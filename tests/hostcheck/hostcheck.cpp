@@ -1,0 +1,58 @@
+// Host build of the product's arithmetic headers (ziren_b200/csrc/kb31.cuh, poseidon2.cuh): the
+// device kernels run exactly these expressions, so the CPU suite can pin them against the golden
+// vectors and the oracle without a GPU.  Test infrastructure only (built by tests/test_host_logic.py).
+#include "poseidon2.cuh"
+#include <vector>
+
+namespace zkb {
+const P2Consts& p2_host_consts() {
+  static const P2Consts c = p2_make_consts();
+  return c;
+}
+}  // namespace zkb
+using namespace zkb;
+
+extern "C" {
+// canonical in / out, n states of 16 words
+void hostcheck_permute(uint32_t* st, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Fp s[16];
+    for (int j = 0; j < 16; j++) s[j] = fp_from_canonical(st[16 * i + j]);
+    p2_permute_host(s);
+    for (int j = 0; j < 16; j++) st[16 * i + j] = fp_to_canonical(s[j]);
+  }
+}
+// op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 to_monty(a), 5 halve(a); canonical in / out except op 4
+void hostcheck_field(int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Fp x = fp_from_canonical(a[i]), y = fp_from_canonical(b ? b[i] : 0);
+    switch (op) {
+      case 0: out[i] = fp_to_canonical(x * y); break;
+      case 1: out[i] = fp_to_canonical(x + y); break;
+      case 2: out[i] = fp_to_canonical(x - y); break;
+      case 3: out[i] = fp_to_canonical(fp_inv(x)); break;
+      case 4: out[i] = x.v; break;
+      case 5: out[i] = fp_to_canonical(fp_halve(x)); break;
+    }
+  }
+}
+// EF4 product, canonical coefficients
+void hostcheck_ef_mul(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Ef x, y;
+  for (int i = 0; i < 4; i++) { x.c[i] = fp_from_canonical(a[i]); y.c[i] = fp_from_canonical(b[i]); }
+  Ef z = x * y;
+  for (int i = 0; i < 4; i++) out[i] = fp_to_canonical(z.c[i]);
+}
+// lazy accumulation path used by the opening / quotient kernels: sum_i w_i * x_i (EF x base)
+void hostcheck_efacc(const uint32_t* w, const uint32_t* x, size_t n, uint32_t* out) {
+  EfAcc acc;
+  acc.clear();
+  for (size_t i = 0; i < n; i++) {
+    Ef e;
+    for (int j = 0; j < 4; j++) e.c[j] = fp_from_canonical(w[4 * i + j]);
+    acc.add(e, fp_from_canonical(x[i]));
+  }
+  Ef r = acc.value();
+  for (int j = 0; j < 4; j++) out[j] = fp_to_canonical(r.c[j]);
+}
+}

@@ -8,25 +8,8 @@
 
 namespace zkb {
 
-static const u32 P2_RC_CANON[30][16] = {
-#include "p2_rc.inc"
-};
-
-static P2Consts make_consts() {
-  P2Consts c;
-  auto m = [](u32 x) { return fp_from_canonical(x % KB_P).v; };
-  for (int r = 0; r < 4; r++)
-    for (int i = 0; i < 16; i++) { c.ext[r][i] = m(P2_RC_CANON[r][i]); c.ext[4 + r][i] = m(P2_RC_CANON[17 + r][i]); }
-  for (int r = 0; r < 13; r++) c.in[r] = m(P2_RC_CANON[4 + r][0]);
-  const u32 P = KB_P;
-  const u32 diag[16] = {P - 2, 1, 2, (P + 1) >> 1, 3, 4, (P - 1) >> 1, P - 3, P - 4, P - ((P - 1) >> 8),
-                        P - ((P - 1) >> 3), P - 127, (P - 1) >> 8, (P - 1) >> 3, (P - 1) >> 4, 127};
-  for (int i = 0; i < 16; i++) c.diag[i] = m(diag[i]);
-  c.big = 0xffffffffu;
-  return c;
-}
 const P2Consts& p2_host_consts() {
-  static const P2Consts c = make_consts();
+  static const P2Consts c = p2_make_consts();
   return c;
 }
 
@@ -44,24 +27,37 @@ __device__ __forceinline__ void sponge_rows(const MatRef* __restrict__ mats, int
   for (int i = 0; i < 16; i++) st[i] = fp_zero();
   int mi = 0;
   u32 col = 0;
-  // skip empty matrices
-  while (mi < nmats && mats[mi].width == 0) mi++;
+  while (mi < nmats && mats[mi].width == 0) mi++;   // skip empty matrices
   while (mi < nmats) {
-    bool any = false;
+    // whole 8-column chunks inside the current matrix: eight strided loads and a permutation
+    const u32 w = mats[mi].width;
+    const u32* __restrict__ p = mats[mi].ptr + (size_t)col * height + r;
+    while (col + 8 <= w) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) st[i] = fp_raw(p[(size_t)i * height]);
+      p += 8 * height;
+      col += 8;
+      p2_permute_dev(st);
+    }
+    if (col == w) {
+      col = 0;
+      do { mi++; } while (mi < nmats && mats[mi].width == 0);
+      continue;
+    }
+    // ragged chunk: the rate block spans the end of this matrix (and maybe whole narrow ones)
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       if (mi < nmats) {
         st[i] = fp_raw(mats[mi].ptr[(size_t)col * height + r]);
-        any = true;
         col++;
         while (mi < nmats && col >= mats[mi].width) { mi++; col = 0; }
       }
     }
-    if (any) p2_permute_dev(st);
+    p2_permute_dev(st);
   }
 }
 
-__global__ void __launch_bounds__(128) leaf_hash_kernel(const MatRef* __restrict__ mats, int nmats, size_t height,
+__global__ void __launch_bounds__(128, 16) leaf_hash_kernel(const MatRef* __restrict__ mats, int nmats, size_t height,
                                                         u32* __restrict__ out) {
   size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (r >= height) return;

@@ -32,38 +32,34 @@ KB_HD Fp fp_raw(u32 v) { Fp r; r.v = v; return r; }
 KB_HD Fp fp_zero() { return fp_raw(0); }
 KB_HD Fp fp_one() { return fp_raw(KB_ONE); }
 
-// m = lo * p^-1 mod 2^32.  p^-1 = 2^31 + 2^24 + 1, so on the device the product is two
-// shift-adds on the ALU pipe instead of an IMAD on the (saturated) FMA-heavy pipe.
-KB_HD u32 mont_m(u32 lo) {
-#if defined(__CUDA_ARCH__) && !defined(ZKB_MONT_IMAD)
-  return lo + (lo << 24) + (lo << 31);
+// 32 x 32 -> 64 product as one mul.wide (IMAD.WIDE): from C the compiler may widen an operand that
+// came out of a 64-bit shift and emit a 64 x 64 product with stray zero-word adds
+KB_HD u64 mul_wide(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+  u64 r;
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+  return r;
 #else
-  return lo * KB_PINV;
+  return (u64)a * b;
 #endif
+}
+// Montgomery reduction in the "plus" form: m = -x * p^-1 mod 2^32 makes x + m*p a multiple of 2^32,
+// so the quotient is the high word of one multiply-accumulate (IMAD.HI with the 64-bit addend)
+// and no separate subtraction is needed.  x < p * 2^32  =>  (x + m*p) / 2^32 in [0, 2p).
+constexpr u32 KB_NPINV = 0x7effffffu;   // -p^-1 mod 2^32
+KB_HD u32 mont_reduce_lazy(u64 x) {
+#if defined(__CUDA_ARCH__)
+  u32 m;   // kept a 32-bit multiply: left to the compiler it becomes a 64-bit product plus mask
+  asm("mul.lo.u32 %0, %1, %2;" : "=r"(m) : "r"((u32)x), "r"(KB_NPINV));
+#else
+  u32 m = (u32)x * KB_NPINV;
+#endif
+  return (u32)((x + (u64)m * KB_P) >> 32);
 }
 KB_HD u32 mont_reduce(u64 x) {
-  // x < p * 2^32.  m = x * p^-1 mod 2^32;  (x - m*p) / 2^32  in (-p, p)
-  u32 lo = (u32)x, hi = (u32)(x >> 32);
-  u32 m = mont_m(lo);
-#if defined(__CUDA_ARCH__)
-  u32 mp = __umulhi(m, KB_P);
-#else
-  u32 mp = (u32)(((u64)m * KB_P) >> 32);
-#endif
-  u32 r = hi - mp;      // wraps high when negative
-  u32 t = r + KB_P;
-  return t < r ? t : r;  // umin(r, r + p): one fused add-min on sm_100
-}
-// same reduction without the final correction: result in (0, 2p), congruent to x / 2^32
-KB_HD u32 mont_reduce_lazy(u64 x) {
-  u32 lo = (u32)x, hi = (u32)(x >> 32);
-  u32 m = mont_m(lo);
-#if defined(__CUDA_ARCH__)
-  u32 mp = __umulhi(m, KB_P);
-#else
-  u32 mp = (u32)(((u64)m * KB_P) >> 32);
-#endif
-  return hi - mp + KB_P;
+  u32 r = mont_reduce_lazy(x);
+  u32 t = r - KB_P;
+  return t < r ? t : r;  // umin(r, r - p): one fused add-min on sm_100
 }
 // reduction of a sum of up to four products of residues (x < 4 p^2 < 2 p 2^32): one conditional
 // subtraction of p * 2^32 on the high word, then the usual reduction
@@ -74,8 +70,8 @@ KB_HD u32 mont_reduce_wide(u64 x) {
   return mont_reduce(((u64)hi << 32) | (u32)x);
 }
 // a * b with a < 2p, b < p (product < p * 2^32)
-KB_HD u32 mont_mul_raw(u32 a, u32 b) { return mont_reduce((u64)a * b); }
-KB_HD Fp operator*(Fp a, Fp b) { return fp_raw(mont_reduce((u64)a.v * b.v)); }
+KB_HD u32 mont_mul_raw(u32 a, u32 b) { return mont_reduce(mul_wide(a, b)); }
+KB_HD Fp operator*(Fp a, Fp b) { return fp_raw(mont_reduce(mul_wide(a.v, b.v))); }
 KB_HD Fp operator+(Fp a, Fp b) {
   u32 s = a.v + b.v;
   u32 t = s - KB_P;
