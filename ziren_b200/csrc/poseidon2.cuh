@@ -48,11 +48,11 @@ const P2Consts& p2_host_consts();
 // 12 column-sum adds, 44 M4 adds, in this order of preference) go to the heavy pipe;
 // -1 leaves the choice to ptxas
 #ifndef ZKB_P2_NH
-#define ZKB_P2_NH 16
+#define ZKB_P2_NH -1
 #endif
 // internal rounds: 1 = all pipe-neutral adds on the heavy pipe, 0 = all on the ALU pipe, -1 = ptxas
 #ifndef ZKB_P2_INT_HEAVY
-#define ZKB_P2_INT_HEAVY 1
+#define ZKB_P2_INT_HEAVY -1
 #endif
 
 // a + b mod p, pinned to a pipe (mode 1 heavy, 0 ALU, -1 unpinned)
