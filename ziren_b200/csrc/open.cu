@@ -1,4 +1,5 @@
 #include "open.h"
+#include <algorithm>
 
 namespace zkb {
 
@@ -106,8 +107,29 @@ void eval_columns(const u32* lde, size_t H, size_t n, size_t W, const u32* w0, c
                   cudaStream_t s) {
   if (!W) return;
   const unsigned colblocks = ceil_div(W, EC_COLS);
+  // Row splits: enough CTAs to fill the GPU, and for large grids the split count (<= 8) whose last
+  // wave is fullest (every CTA does the same work, so a ragged last wave is lost time: the
+  // 1042-CTA keccak matrix runs 3.5 waves unsplit)
+  static int slots_per_sm[2] = {0, 0};
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slots_per_sm[0], eval_columns_kernel<1>, EC_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slots_per_sm[1], eval_columns_kernel<2>, EC_THREADS, 0);
+  }
+  const size_t slots = (size_t)sms * std::max(1, slots_per_sm[npoints == 1 ? 0 : 1]);
   size_t nsplit = 1;
-  if (colblocks < 296) nsplit = (296 + colblocks - 1) / colblocks;
+  if (colblocks < slots) nsplit = (slots + colblocks - 1) / colblocks;
+  else {
+    double best = 0;
+    for (size_t k = 1; k <= 8; k++) {
+      const double waves = (double)(colblocks * k) / (double)slots;
+      const double eff = waves / (double)(size_t)(waves + 0.999999);
+      if (eff > best + 0.02) { best = eff; nsplit = k; }
+    }
+  }
   size_t max_split = n / 1024 ? n / 1024 : 1;
   if (nsplit > max_split) nsplit = max_split;
   size_t rows_per_split = (n + nsplit - 1) / nsplit;
