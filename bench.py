@@ -289,6 +289,11 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1):
     perms = sum(h * (-(-w // 8)) for h, w in shapes) + (hmax - 1) + sum(inj_heights)
     lde_bytes = sum(12.0 * h * w for h, w in trace_shapes.values())
     out = {}
+    # DRAM traffic / algorithmic bytes of the family's kernels, from the committed `ncu --set full`
+    # captures (profiles/r01_ncu_full_summary_v2.txt): leaf_hash_kernel 2^19 x 512 moves 1.0926 GB for
+    # 1.0905 GB algorithmic; the three launches of one 2^18 x 256 LDE chunk move 2.306 GB for 0.805 GB
+    # (the A->B->C intermediates go through HBM at this chunk size)
+    ncu_ratio = {"k2_merkle": 1.0019, "k1_lde": 2.864}
     for key, stage, alg, kern in (("k2_merkle", "commit_main_merkle", merkle_bytes, "merkle_build: leaf_hash_kernel (Poseidon2 sponge over the rows of every height) + compress_kernel"),
                                   ("k1_lde", "commit_main_lde", lde_bytes, "coset_lde_batch: ntt_strided_kernel + ntt_contig_kernel")):
         ms = stages.get(stage)
@@ -296,11 +301,13 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1):
             continue
         ach = alg / (ms / 1e3) / 1e9
         out[key] = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "ms": ms, "algorithmic_bytes": alg,
+                    "frac": ach / peak, "traffic": alg * ncu_ratio[key],
+                    "traffic_source": "algorithmic bytes x the dram__bytes ratio of the ncu --set full capture under profiles/",
+                    "ms": ms, "algorithmic_bytes": alg,
                     "share_of_step": ms / max(sum(stages.values()), 1e-9)}
     if "k2_merkle" in out:
         out["k2_merkle"]["poseidon2_Gperm_per_s"] = perms / (stages["commit_main_merkle"] / 1e3) / 1e9
-        out["k2_merkle"]["note"] = "integer-multiply (FMA-heavy pipe) bound, not HBM bound: ~4.8k instructions per permutation; see profiles/README.md"
+        out["k2_merkle"]["note"] = "integer-issue bound, not HBM bound: ~4.3k instructions per permutation, IMAD.WIDE/IMAD.HI cost 4-5.5 issue cycles per warp (profiles/r01_pipe_probe.jsonl); see profiles/README.md"
     return out
 
 
