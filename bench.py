@@ -38,6 +38,31 @@ METRIC = "mips_cycles_proved_per_sec"
 UNIT = "cycles/s"
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """At N > 1 every rank stages 5 GB per shard from pinned host memory: keep the rank's threads
+    and its pinned pages on the NUMA node its GPU hangs off (first-touch placement), so the ranks do
+    not all pull their uploads through one socket.  Best effort: returns the CPU list it bound to."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 4:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
 def make_case(args, sample=False):
     w = args.workload
     lc = args.sample_log_cpu if sample else args.log_cpu
@@ -156,6 +181,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(args.local_rank)
     distributed = args.world > 1
+    numa_cpus = bind_to_gpu_numa_node(torch, args.local_rank) if distributed else None
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", args.local_rank))
 
@@ -168,6 +194,8 @@ def main():
     # inputs: Montgomery row-major, once in pinned host memory (e2e arm), once resident in HBM
     host_tr = {}
     cfg = workload_config(args, case)
+    if numa_cpus:
+        cfg["host_numa_binding"] = "each rank bound to its GPU's local_cpulist (rank 0: %s)" % numa_cpus
     cells, shapes = case.cells, {k: v.shape for k, v in case.traces.items()}
     for k in list(case.traces):
         host_tr[k] = torch.from_numpy(kb.to_monty(case.traces[k]).view(np.int32)).pin_memory()
