@@ -137,6 +137,25 @@ int zkb200_fri_fold(zkb200_ctx* ctx, const uint32_t* in, size_t m, const uint32_
                     uint32_t* out);
 /* K4d: smallest proof-of-work witness for a challenger image */
 int zkb200_grind(zkb200_ctx* ctx, const uint32_t challenger[34], unsigned bits, uint32_t* witness_out);
+/* ---- trace generation ---------------------------------------------
+ * MachineAir::generate_trace of the core ALU chips AddSub, Bitwise, Lt, ShiftLeft, ShiftRight and
+ * CloClz (crates/core/machine/src/alu/{add_sub,bitwise,lt,sll,sr,clo_clz}/mod.rs; the reference's
+ * own C++ twins are crates/core/machine/include/*.hpp behind cpp/extern.cpp:15-80): one event per
+ * row in event order, then the chip's padding rows up to 2^log_height (next_power_of_two /
+ * fixed_log2_rows, crates/core/machine/src/utils/mod.rs:101-125, is the caller's choice).
+ * `events` is the record's Vec<AluEvent> as it lies in memory (#[repr(C)],
+ * crates/core/executor/src/events/instr.rs:11-26), host or device; `out` is DEVICE memory of
+ * 2^log_height x width words, Montgomery, row-major (col_major = 0: the RowMajorMatrix layout
+ * zkb200_commit takes) or column-major (col_major = 1: the layout of the kernel-level entry points). */
+typedef struct {
+  uint32_t pc, next_pc;
+  uint8_t opcode;        /* Opcode as #[repr(u8)], crates/core/executor/src/opcode.rs:25-89 */
+  uint32_t hi, a, b, c;
+} zkb200_alu_event;
+/* NUM_*_COLS of the chip, -1 if this library has no row filler for it */
+int zkb200_alu_trace_width(const char* chip);
+int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const zkb200_alu_event* events, size_t n_events,
+                              unsigned log_height, uint32_t* out, int col_major);
 /* layout helpers on the context stream: row-major <-> column-major, canonical <-> Montgomery */
 int zkb200_transpose(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t height, size_t width, int to_colmajor);
 int zkb200_convert(zkb200_ctx* ctx, uint32_t* data, size_t n, int to_montgomery);

@@ -3,6 +3,7 @@
 // All field elements cross this boundary in CANONICAL form.  Nothing under ziren_b200/ links,
 // imports or calls this library.
 #include "prover.h"
+#include "tracegen.h"
 #include <cstdlib>
 #include <cstring>
 #ifdef _OPENMP
@@ -235,6 +236,22 @@ int zko_quotient_values(void* m_, const char* chip, unsigned log_n, const u32* p
     for (size_t i = 0; i < q.size(); i++) e_to(q[i], out + 4 * i);
     return 0;
   } catch (const std::exception& e) { return fail(e); }
+}
+
+// trace generation of the core ALU chips (tracegen.h): events n x 7 words {pc, next_pc, opcode, hi, a, b, c},
+// out height x width row-major canonical
+int zko_alu_width(int chip) { return chip >= 0 && chip < T_NCHIPS ? ALU_WIDTHS[chip] : -1; }
+int zko_alu_trace(int chip, const u32* ev, size_t n, size_t height, u32* out) {
+  try {
+    std::vector<AluEvent> e(n);
+    for (size_t i = 0; i < n; i++)
+      e[i] = AluEvent{ev[7 * i], ev[7 * i + 1], ev[7 * i + 2] & 0xff, ev[7 * i + 3], ev[7 * i + 4], ev[7 * i + 5], ev[7 * i + 6]};
+    alu_trace(chip, e.data(), n, height, out);
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return 1;
+  }
 }
 
 }  // extern "C"

@@ -50,6 +50,46 @@ def ref_lib():
     return l
 
 
+def ref_core_lib():
+    """The reference's own ALU row fillers (crates/core/machine/include/*.hpp) behind a C shim; None if not built."""
+    p = os.path.join(_DIR, "_ref", "libzkref_core.so")
+    if not os.path.exists(p):
+        return None
+    l = C.CDLL(p)
+    l.ref_alu_num_cols.restype = C.c_uint
+    return l
+
+
+ALU_CHIPS = ("AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz")
+
+
+def alu_width(chip):
+    return lib().zko_alu_width(ALU_CHIPS.index(chip))
+
+
+def alu_trace(chip, events, height):
+    """events: (n, 7) uint32 {pc, next_pc, opcode, hi, a, b, c}; returns (height, width) canonical rows."""
+    ev = _a(events).reshape(-1, 7)
+    w = alu_width(chip)
+    out = np.zeros((int(height), w), np.uint32)
+    if lib().zko_alu_trace(ALU_CHIPS.index(chip), _p(ev), C.c_size_t(ev.shape[0]), C.c_size_t(int(height)), _p(out)):
+        raise RuntimeError(err())
+    return out
+
+
+def ref_alu_rows(chip, events):
+    """Rows of the reference's own C++ event_to_row (Montgomery words), or None without oracle/_ref."""
+    l = ref_core_lib()
+    if l is None:
+        return None
+    ev = _a(events).reshape(-1, 7)
+    cid = ALU_CHIPS.index(chip)
+    out = np.zeros((ev.shape[0], l.ref_alu_num_cols(cid)), np.uint32)
+    if l.ref_alu_event_to_rows(cid, _p(ev), C.c_size_t(ev.shape[0]), _p(out)):
+        raise RuntimeError("reference row filler failed")
+    return out
+
+
 def _a(x):
     return np.ascontiguousarray(x, dtype=np.uint32)
 

@@ -1,0 +1,55 @@
+// Drives the reference's own ALU row fillers (crates/core/machine/include/*.hpp, the C++ the
+// reference's `sys` feature calls from generate_trace, crates/core/machine/cpp/extern.cpp:15-80)
+// so that tests can compare our trace generation with it.  Test infrastructure only.
+#include <cassert>
+#include <algorithm>
+#include <cstring>
+#include "zkm-core-machine-sys-cbindgen.hpp"
+#include "kb31_t.hpp"
+#include "add_sub.hpp"
+#include "bitwise.hpp"
+#include "lt.hpp"
+#include "shift_left.hpp"
+#include "shift_right.hpp"
+#include "clo_clz.hpp"
+
+using namespace zkm_core_machine_sys;
+
+template <class Cols> static constexpr size_t ncols() { return sizeof(Cols) / sizeof(kb31_t); }
+
+extern "C" {
+// chip: 0 AddSub, 1 Bitwise, 2 Lt, 3 ShiftLeft, 4 ShiftRight, 5 CloClz
+unsigned ref_alu_num_cols(int chip) {
+  switch (chip) {
+    case 0: return ncols<AddSubCols<kb31_t>>();
+    case 1: return ncols<BitwiseCols<kb31_t>>();
+    case 2: return ncols<LtCols<kb31_t>>();
+    case 3: return ncols<ShiftLeftCols<kb31_t>>();
+    case 4: return ncols<ShiftRightCols<kb31_t>>();
+    case 5: return ncols<CloClzCols<kb31_t>>();
+  }
+  return 0;
+}
+// events: n records of 7 words {pc, next_pc, opcode, hi, a, b, c}; rows: n x num_cols, zero-initialised here,
+// Montgomery words exactly as the reference leaves them in the trace
+int ref_alu_event_to_rows(int chip, const uint32_t* ev, size_t n, uint32_t* rows) {
+  const unsigned w = ref_alu_num_cols(chip);
+  if (!w) return 1;
+  std::memset(rows, 0, n * w * sizeof(uint32_t));
+  for (size_t i = 0; i < n; i++) {
+    AluEvent e;
+    e.pc = ev[7 * i]; e.next_pc = ev[7 * i + 1]; e.opcode = (Opcode)ev[7 * i + 2]; e.hi = ev[7 * i + 3];
+    e.a = ev[7 * i + 4]; e.b = ev[7 * i + 5]; e.c = ev[7 * i + 6];
+    uint32_t* r = rows + i * w;
+    switch (chip) {
+      case 0: add_sub::event_to_row<kb31_t>(e, *reinterpret_cast<AddSubCols<kb31_t>*>(r)); break;
+      case 1: bitwise::event_to_row<kb31_t>(e, *reinterpret_cast<BitwiseCols<kb31_t>*>(r)); break;
+      case 2: lt::event_to_row<kb31_t>(e, *reinterpret_cast<LtCols<kb31_t>*>(r)); break;
+      case 3: shift_left::event_to_row<kb31_t>(e, *reinterpret_cast<ShiftLeftCols<kb31_t>*>(r)); break;
+      case 4: shift_right::event_to_row<kb31_t>(e, *reinterpret_cast<ShiftRightCols<kb31_t>*>(r)); break;
+      case 5: clo_clz::event_to_row<kb31_t>(e, *reinterpret_cast<CloClzCols<kb31_t>*>(r)); break;
+    }
+  }
+  return 0;
+}
+}

@@ -1,0 +1,114 @@
+// Stand-in for the header cbindgen generates in the reference's Rust build
+// (crates/core/machine/build.rs:94-180); that build cannot run here (no Rust toolchain).  It
+// declares, with the field order of the Rust #[repr(C)] definitions cited below, the layout types
+// the reference's ALU row fillers (crates/core/machine/include/{add_sub,bitwise,lt,shift_left,
+// shift_right,clo_clz}.hpp) name, plus the names utils.hpp mentions in signatures.  This file is
+// ours; the reference's headers are compiled from where they lie under /root/reference.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace zkm_core_machine_sys {
+
+constexpr size_t BYTE_SIZE = 8;        // crates/core/machine/src/alu/sll/mod.rs (BYTE_SIZE)
+constexpr size_t WORD_SIZE = 4;        // crates/primitives/src/consts.rs:5
+constexpr size_t LONG_WORD_SIZE = 8;   // crates/primitives/src/consts.rs:6
+constexpr size_t PRODUCT_SIZE = 8;     // crates/core/machine/src/alu/mul/mod.rs:64
+
+// crates/core/executor/src/opcode.rs:25-89 (#[repr(u8)])
+enum class Opcode : uint8_t {
+  ADD = 0, SUB = 1, MUL = 2, MULT = 3, MULTU = 4, DIV = 5, DIVU = 6, MOD = 7, MODU = 8, SLL = 9, SRL = 10, SRA = 11,
+  ROR = 12, SLT = 13, SLTU = 14, AND = 15, OR = 16, XOR = 17, NOR = 18, CLZ = 19, CLO = 20,
+  BEQ = 21, BGEZ = 22, BGTZ = 23, BLEZ = 24, BLTZ = 25, BNE = 26, Jump = 27, Jumpi = 28, JumpDirect = 29, SYSCALL = 30,
+  LB = 31, LBU = 32, LH = 33, LHU = 34, LW = 35, LWL = 36, LWR = 37, LL = 38, SB = 39, SH = 40, SW = 41, SWL = 42,
+  SWR = 43, SC = 44, INS = 45, MADDU = 46, MSUBU = 47, MADD = 48, MSUB = 49, MEQ = 50, MNE = 51, WSBH = 52, EXT = 53,
+  TEQ = 54, SEXT = 55, UNIMPL = 0xff,
+};
+enum class SyscallCode : uint32_t { HALT = 0 };   // only named by utils.hpp:to_syscall_id
+
+// crates/core/executor/src/events/instr.rs:11-26 (#[repr(C)])
+struct AluEvent {
+  uint32_t pc;
+  uint32_t next_pc;
+  Opcode opcode;
+  uint32_t hi;
+  uint32_t a;
+  uint32_t b;
+  uint32_t c;
+};
+
+template <class T> struct Word { T _0[WORD_SIZE]; };   // crates/stark/src/word.rs:21
+
+// operation helpers utils.hpp takes by reference (crates/core/machine/src/operations/*.rs)
+template <class T> struct KoalaBearWordRangeChecker {
+  T most_sig_byte_decomp[8];
+  T and_most_sig_byte_decomp_0_to_2, and_most_sig_byte_decomp_0_to_3, and_most_sig_byte_decomp_0_to_4,
+      and_most_sig_byte_decomp_0_to_5, and_most_sig_byte_decomp_0_to_6, and_most_sig_byte_decomp_0_to_7;
+};
+template <class T> struct IsZeroOperation { T inverse; T result; };
+template <class T> struct IsZeroWordOperation {
+  IsZeroOperation<T> is_zero_byte[WORD_SIZE];
+  T is_lower_half_zero, is_upper_half_zero, result;
+};
+template <class T> struct IsEqualWordOperation { IsZeroWordOperation<T> is_diff_zero; };
+template <class T> struct AddDoubleOperation { Word<T> value; Word<T> value_hi; T carry[7]; };
+template <class T> struct AddOperation { Word<T> value; T carry[3]; };   // operations/add.rs:13-19
+
+// crates/core/machine/src/alu/add_sub/mod.rs:43-65
+template <class T> struct AddSubCols {
+  T pc, next_pc;
+  AddOperation<T> add_operation;
+  Word<T> operand_1, operand_2;
+  T is_add, is_sub;
+};
+// crates/core/machine/src/alu/bitwise/mod.rs (BitwiseCols)
+template <class T> struct BitwiseCols {
+  T pc, next_pc;
+  Word<T> a, b, c;
+  T is_nor, is_xor, is_or, is_and;
+};
+// crates/core/machine/src/alu/lt/mod.rs (LtCols)
+template <class T> struct LtCols {
+  T pc, next_pc, is_slt, is_sltu;
+  Word<T> a, b, c;
+  T byte_flags[4];
+  T b_masked, c_masked, not_eq_inv;
+  T msb_b, msb_c, bit_b, bit_c;
+  T sltu, is_comp_eq, is_sign_eq;
+  T comparison_bytes[2];
+};
+// crates/core/machine/src/alu/sll/mod.rs (ShiftLeftCols)
+template <class T> struct ShiftLeftCols {
+  T pc, next_pc;
+  Word<T> a, b, c;
+  T c_least_sig_byte[BYTE_SIZE];
+  T shift_by_n_bits[BYTE_SIZE];
+  T bit_shift_multiplier;
+  T bit_shift_result[WORD_SIZE];
+  T bit_shift_result_carry[WORD_SIZE];
+  T shift_by_n_bytes[WORD_SIZE];
+  T is_real;
+};
+// crates/core/machine/src/alu/sr/mod.rs (ShiftRightCols)
+template <class T> struct ShiftRightCols {
+  T pc, next_pc;
+  Word<T> b, c;
+  T shift_by_n_bits[BYTE_SIZE];
+  T shift_by_n_bytes[WORD_SIZE];
+  T byte_shift_result[LONG_WORD_SIZE];
+  T bit_shift_result[LONG_WORD_SIZE];
+  T shr_carry_output_carry[LONG_WORD_SIZE];
+  T shr_carry_output_shifted_byte[LONG_WORD_SIZE];
+  T b_msb;
+  T c_least_sig_byte[BYTE_SIZE];
+  T is_srl, is_ror, is_sra;
+  T is_real;
+};
+// crates/core/machine/src/alu/clo_clz/mod.rs (CloClzCols)
+template <class T> struct CloClzCols {
+  T pc, next_pc;
+  Word<T> a, b, bb;
+  T is_bb_zero, is_clz, is_real;
+};
+
+}  // namespace zkm_core_machine_sys

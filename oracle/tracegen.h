@@ -1,0 +1,158 @@
+// CPU restatement of the core ALU chips' trace generation — TEST
+// INFRASTRUCTURE, the checker for ziren_b200/csrc/tracegen.cu, never the thing shipped or measured.
+// Plain per-byte loops in canonical form (the CUDA path uses branch-free word arithmetic on
+// Montgomery residues), each function following the reference's Rust generate_trace / event_to_row:
+//   AddSub     crates/core/machine/src/alu/add_sub/mod.rs:94-123, :152-171; operations/add.rs:23-47
+//   Bitwise    crates/core/machine/src/alu/bitwise/mod.rs:90-119 (rows), event_to_row below it
+//   Lt         crates/core/machine/src/alu/lt/mod.rs:120-148 (rows), event_to_row below it
+//   ShiftLeft  crates/core/machine/src/alu/sll/mod.rs:130-178
+//   ShiftRight crates/core/machine/src/alu/sr/mod.rs:163-193, event_to_row below it
+//   CloClz     crates/core/machine/src/alu/clo_clz/mod.rs:100-166
+// Pinned against the reference's own C++ row fillers (crates/core/machine/include/*.hpp compiled
+// into oracle/_ref/libzkref_core.so) and the golden rows generated from them
+// (tests/golden/alu_rows.json).
+#pragma once
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+#include "kb.h"
+
+namespace zko {
+
+struct AluEvent { u32 pc, next_pc, opcode, hi, a, b, c; };
+enum { T_ADDSUB = 0, T_BITWISE, T_LT, T_SLL, T_SR, T_CLOCLZ, T_NCHIPS };
+static const int ALU_WIDTHS[T_NCHIPS] = {19, 18, 32, 44, 67, 17};
+enum { K_ADD = 0, K_SUB = 1, K_SLL = 9, K_SRL = 10, K_SRA = 11, K_ROR = 12, K_SLT = 13, K_SLTU = 14, K_AND = 15, K_OR = 16,
+       K_XOR = 17, K_NOR = 18, K_CLZ = 19, K_CLO = 20 };
+
+struct RowWriter {
+  u32* r;
+  int at = 0;
+  void put(u32 canonical) { r[at++] = canonical % P; }
+  void flag(bool b) { r[at++] = b ? 1 : 0; }
+  void bytes(const unsigned char* b, int n) { for (int i = 0; i < n; i++) put(b[i]); }
+  void word(u32 v) { unsigned char b[4]; for (int i = 0; i < 4; i++) b[i] = (unsigned char)(v >> (8 * i)); bytes(b, 4); }
+};
+
+static inline void alu_row(int chip, const AluEvent& e, u32* row) {
+  RowWriter w{row};
+  unsigned char a[4], b[4], c[4];
+  for (int i = 0; i < 4; i++) { a[i] = (unsigned char)(e.a >> (8 * i)); b[i] = (unsigned char)(e.b >> (8 * i)); c[i] = (unsigned char)(e.c >> (8 * i)); }
+  w.put(e.pc); w.put(e.next_pc);
+  switch (chip) {
+    case T_ADDSUB: {
+      const bool is_add = e.opcode == K_ADD;
+      const u32 x = is_add ? e.b : e.a, y = e.c;
+      w.word(x + y);
+      unsigned carry = 0;
+      for (int i = 0; i < 3; i++) {
+        carry = (((x >> (8 * i)) & 0xff) + ((y >> (8 * i)) & 0xff) + carry) > 0xff;
+        w.flag(carry);
+      }
+      w.word(x); w.word(y);
+      w.flag(is_add); w.flag(e.opcode == K_SUB);
+      break;
+    }
+    case T_BITWISE:
+      w.bytes(a, 4); w.bytes(b, 4); w.bytes(c, 4);
+      w.flag(e.opcode == K_NOR); w.flag(e.opcode == K_XOR); w.flag(e.opcode == K_OR); w.flag(e.opcode == K_AND);
+      break;
+    case T_LT: {
+      const bool slt = e.opcode == K_SLT;
+      w.flag(slt); w.flag(e.opcode == K_SLTU);
+      w.bytes(a, 4); w.bytes(b, 4); w.bytes(c, 4);
+      unsigned char bc[4], cc[4];
+      memcpy(bc, b, 4); memcpy(cc, c, 4);
+      const unsigned char mb = b[3] & 0x7f, mc = c[3] & 0x7f;
+      if (slt) { bc[3] = mb; cc[3] = mc; }
+      u32 flags[4] = {0, 0, 0, 0}, cmp[2] = {0, 0}, inv = 0;
+      bool sltu = false, eq = true;
+      for (int i = 3; i >= 0; i--) {
+        if (bc[i] != cc[i]) {
+          flags[i] = 1; eq = false;
+          sltu = bc[i] < cc[i];
+          inv = finv(F(bc[i]) - F(cc[i])).v;
+          cmp[0] = bc[i]; cmp[1] = cc[i];
+          break;
+        }
+      }
+      for (int i = 0; i < 4; i++) w.put(flags[i]);
+      w.put(mb); w.put(mc); w.put(inv);
+      const u32 msb_b = b[3] >> 7, msb_c = c[3] >> 7;
+      w.put(msb_b); w.put(msb_c); w.put(msb_b * (slt ? 1 : 0)); w.put(msb_c * (slt ? 1 : 0));
+      w.flag(sltu); w.flag(eq); w.flag(slt ? msb_b == msb_c : true);
+      w.put(cmp[0]); w.put(cmp[1]);
+      break;
+    }
+    case T_SLL: {
+      w.bytes(a, 4); w.bytes(b, 4); w.bytes(c, 4);
+      for (int i = 0; i < 8; i++) w.flag((e.c >> i) & 1);
+      const u32 nbits = e.c % 8, nbytes = (e.c & 31) / 8, mult = 1u << nbits;
+      for (u32 i = 0; i < 8; i++) w.flag(nbits == i);
+      w.put(mult);
+      u32 carry = 0, res[4], car[4];
+      for (int i = 0; i < 4; i++) { u32 v = b[i] * mult + carry; carry = v / 256; res[i] = v % 256; car[i] = carry; }
+      for (int i = 0; i < 4; i++) w.put(res[i]);
+      for (int i = 0; i < 4; i++) w.put(car[i]);
+      for (u32 i = 0; i < 4; i++) w.flag(nbytes == i);
+      w.flag(true);
+      break;
+    }
+    case T_SR: {
+      w.bytes(b, 4); w.bytes(c, 4);
+      const u32 n = e.c % 32, nbytes = n / 8, nbits = n % 8;
+      for (u32 i = 0; i < 8; i++) w.flag(nbits == i);
+      for (u32 i = 0; i < 4; i++) w.flag(nbytes == i);
+      unsigned char ext[8];
+      for (int i = 0; i < 4; i++) ext[i] = b[i];
+      for (int i = 4; i < 8; i++) ext[i] = e.opcode == K_SRA ? ((b[3] >> 7) ? 0xff : 0) : e.opcode == K_ROR ? b[i - 4] : 0;
+      unsigned char by[8] = {0};
+      for (u32 i = 0; i + nbytes < 8; i++) by[i] = ext[i + nbytes];
+      unsigned char out[8], cars[8], shifted[8];
+      u32 last = 0;
+      for (int i = 7; i >= 0; i--) {
+        const unsigned char sh = nbits ? (unsigned char)(by[i] >> nbits) : by[i];
+        const unsigned char ca = nbits ? (unsigned char)(by[i] & ((1u << nbits) - 1)) : 0;
+        cars[i] = ca; shifted[i] = sh;
+        out[i] = (unsigned char)((sh + last * (1u << (8 - nbits))) & 0xff);
+        last = ca;
+      }
+      w.bytes(by, 8); w.bytes(out, 8); w.bytes(cars, 8); w.bytes(shifted, 8);
+      w.put(b[3] >> 7);
+      for (int i = 0; i < 8; i++) w.flag((e.c >> i) & 1);
+      w.flag(e.opcode == K_SRL); w.flag(e.opcode == K_ROR); w.flag(e.opcode == K_SRA);
+      w.flag(true);
+      break;
+    }
+    case T_CLOCLZ: {
+      const bool clz = e.opcode == K_CLZ;
+      const u32 bb = clz ? e.b : 0xffffffffu - e.b;
+      w.bytes(a, 4); w.bytes(b, 4); w.word(bb);
+      w.flag(bb == 0); w.flag(clz); w.flag(true);
+      break;
+    }
+    default: throw std::runtime_error("oracle: unknown ALU chip");
+  }
+  if (w.at != ALU_WIDTHS[chip]) throw std::runtime_error("oracle: ALU row width mismatch");
+}
+
+static inline void alu_padding_row(int chip, u32* row) {
+  const int w = ALU_WIDTHS[chip];
+  for (int i = 0; i < w; i++) row[i] = 0;
+  if (chip == T_SLL) { row[22] = 1; row[30] = 1; row[39] = 1; }   // shift_by_n_bits[0], multiplier, shift_by_n_bytes[0]
+  if (chip == T_SR) { row[10] = 1; row[18] = 1; }                  // shift_by_n_bits[0], shift_by_n_bytes[0]
+  if (chip == T_CLOCLZ) { row[2] = 32; row[14] = 1; }              // a = 32, is_bb_zero
+}
+
+// height x width row-major canonical trace: events in order, then padding rows
+static inline void alu_trace(int chip, const AluEvent* ev, size_t n, size_t height, u32* out) {
+  if (chip < 0 || chip >= T_NCHIPS) throw std::runtime_error("oracle: unknown ALU chip");
+  if (n > height) throw std::runtime_error("oracle: more events than rows");
+  const int w = ALU_WIDTHS[chip];
+  for (size_t i = 0; i < height; i++) {
+    if (i < n) alu_row(chip, ev[i], out + i * w);
+    else alu_padding_row(chip, out + i * w);
+  }
+}
+
+}  // namespace zko

@@ -2,6 +2,7 @@
 // device kernels run exactly these expressions, so the CPU suite can pin them against the golden
 // vectors and the oracle without a GPU.  Test infrastructure only (built by tests/test_host_logic.py).
 #include "poseidon2.cuh"
+#include "tracegen.cuh"
 #include <vector>
 
 namespace zkb {
@@ -55,4 +56,19 @@ void hostcheck_efacc(const uint32_t* w, const uint32_t* x, size_t n, uint32_t* o
   Ef r = acc.value();
   for (int j = 0; j < 4; j++) out[j] = fp_to_canonical(r.c[j]);
 }
+// the product's ALU row fillers (csrc/tracegen.cuh) on the host: events n x 7 words, out height x width
+// row-major Montgomery, padding rows past the last event
+int hostcheck_alu_rows(int chip, const uint32_t* ev, size_t n, size_t height, uint32_t* out) {
+  if (chip < 0 || chip >= ALU_NCHIPS || n > height) return 1;
+  static u32 inv255[256];
+  static bool init = false;
+  if (!init) { alu_build_inv255(inv255); init = true; }
+  const int w = alu_width(chip);
+  for (size_t i = 0; i < height; i++) {
+    if (i < n) fill_alu_row(chip, alu_event_from_words(ev + 7 * i), out + i * w, inv255);
+    else fill_alu_padding(chip, out + i * w);
+  }
+  return 0;
+}
+int hostcheck_alu_width(int chip) { return alu_width(chip); }
 }

@@ -18,19 +18,6 @@ GOLD = json.load(open(os.path.join(HERE, "golden", "ref_vectors.json")))
 P = kb.P
 
 
-@pytest.fixture(scope="module")
-def host():
-    src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
-    out_dir = os.path.join(HERE, "hostcheck", "_build")
-    os.makedirs(out_dir, exist_ok=True)
-    so = os.path.join(out_dir, "libhostcheck.so")
-    csrc = os.path.join(ROOT, "ziren_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("kb31.cuh", "poseidon2.cuh", "p2_rc.inc")]
-    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + csrc, "-x", "c++", src, "-o", so])
-    return ctypes.CDLL(so)
-
-
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 

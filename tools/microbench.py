@@ -19,7 +19,9 @@ from ziren_b200 import synthetic  # noqa: E402
 from ziren_b200.prover import B200Prover  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("what", choices=["lde", "ntt", "mmcs", "permute"])
+ap.add_argument("what", choices=["lde", "ntt", "mmcs", "permute", "tracegen"])
+ap.add_argument("--chip", default="ShiftRight", help="tracegen: AddSub, Bitwise, Lt, ShiftLeft, ShiftRight or CloClz")
+ap.add_argument("--col-major", action="store_true", help="tracegen: write the column-major layout")
 ap.add_argument("--log-n", type=int, default=18)
 ap.add_argument("--width", type=int, default=512)
 ap.add_argument("--reps", type=int, default=5)
@@ -59,12 +61,22 @@ elif args.what == "mmcs":
     d_in = torch.randint(0, kb.P, (w, n), dtype=torch.int32, device="cuda")
     ms = timed(lambda: prover.mmcs_root([d_in], [args.log_n], [w]))
     alg = 4.0 * n * w + 32.0 * n + 96.0 * (n - 1)
+elif args.what == "tracegen":
+    from ziren_b200 import tracegen as tg
+    w = tg.width(args.chip)
+    ev = tg.synthetic_events(args.chip, n - 77, seed=1)
+    d_ev = torch.from_numpy(ev.view(np.int32)).cuda()
+    d_out = torch.empty((n * w,), dtype=torch.int32, device="cuda")
+    ms = timed(lambda: prover.generate_alu_trace(args.chip, d_ev, args.log_n, d_out, col_major=args.col_major))
+    alg = 28.0 * (n - 77) + 4.0 * n * w          # one event read, one row written
 else:
     d_in = torch.randint(0, kb.P, (n, 16), dtype=torch.int32, device="cuda")
     ms = timed(lambda: (prover.poseidon2_permute_batch(d_in, n), prover.sync()))
     alg = 128.0 * n
 gbs = alg / (ms / 1e3) / 1e9
 out = {"what": args.what, "log_n": args.log_n, "width": w, "ms": ms, "algorithmic_GB": alg / 1e9, "GB/s": gbs, "frac_of_measured_hbm": gbs / PEAK}
+if args.what == "tracegen":
+    out.update({"chip": args.chip, "width": w, "layout": "column-major" if args.col_major else "row-major", "Grows/s": n / (ms / 1e3) / 1e9})
 if args.what in ("mmcs", "permute"):
     perms = n * (-(-w // 8)) + (n - 1) if args.what == "mmcs" else n
     out["Gperm/s"] = perms / (ms / 1e3) / 1e9

@@ -53,6 +53,8 @@ SIGNATURES = {
     "zkb200_grind": (C.c_int, [C.c_void_p, u32p, C.c_uint, u32p]),
     "zkb200_transpose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]),
     "zkb200_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "zkb200_alu_trace_width": (C.c_int, [C.c_char_p]),
+    "zkb200_generate_alu_trace": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_int]),
     "zkb200_sync": (C.c_int, [C.c_void_p]),
 }
 

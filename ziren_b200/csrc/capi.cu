@@ -6,6 +6,7 @@
 #include "open.h"
 #include "prover.h"
 #include "quotient.h"
+#include "tracegen.h"
 
 using namespace zkb;
 
@@ -232,6 +233,38 @@ int zkb200_convert(zkb200_ctx* ctx, uint32_t* data, size_t n, int to_montgomery)
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
     if (to_montgomery) to_monty_inplace(data, n, ctx->c.lanes[0].stream);
     else from_monty_inplace(data, n, ctx->c.lanes[0].stream);
+  });
+}
+int zkb200_alu_trace_width(const char* chip) {
+  const int id = alu_chip_by_name(chip);
+  return id < 0 ? -1 : alu_width(id);
+}
+int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const zkb200_alu_event* events, size_t n_events,
+                              unsigned log_height, uint32_t* out, int col_major) {
+  return guarded(ctx, [&] {
+    static_assert(sizeof(zkb200_alu_event) == 28, "AluEvent is seven 32-bit words");
+    const int id = alu_chip_by_name(chip);
+    if (id < 0) throw std::runtime_error(std::string("zkb200: generate_alu_trace: no row filler for chip ") + chip);
+    if (log_height > 30) throw std::runtime_error("zkb200: generate_alu_trace: log_height out of range");
+    const size_t height = (size_t)1 << log_height;
+    if (n_events > height) throw std::runtime_error("zkb200: generate_alu_trace: more events than rows (fixed log2 rows is too small)");
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    cudaStream_t s = ctx->c.lanes[0].stream;
+    const u32* ev = reinterpret_cast<const u32*>(events);
+    DevBuf staged;
+    cudaPointerAttributes attr;
+    bool on_device = false;
+    if (n_events && cudaPointerGetAttributes(&attr, events) == cudaSuccess)
+      on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    else cudaGetLastError();
+    if (n_events && !on_device) {
+      staged = DevBuf(n_events * 7, s);
+      ZKB_CUDA(cudaMemcpyAsync(staged.p, events, n_events * 28, cudaMemcpyHostToDevice, s));
+      ev = staged.p;
+    }
+    alu_trace(id, ev, n_events, height, out, col_major != 0, s);
+    ZKB_CUDA(cudaStreamSynchronize(s));
   });
 }
 int zkb200_sync(zkb200_ctx* ctx) {

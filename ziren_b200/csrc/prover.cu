@@ -3,6 +3,7 @@
 // context stream, runs the duplex challenger on the host between stages (the transcript order of
 // crates/stark/src/prover.rs:298-653) and packs the "ZKPF" proof.
 #include "prover.h"
+#include "tracegen.h"
 #include <algorithm>
 #include <array>
 #include <cstdlib>
@@ -49,6 +50,7 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
   machine.upload();
   tables.init(lanes[0].stream);
   p2_upload_constants();
+  tracegen_upload_constants();
   for (auto& L : lanes) {
     L.arena.init(8u << 20, L.stream);
     ZKB_CUDA(cudaMalloc((void**)&L.d_small, 1 << 16));

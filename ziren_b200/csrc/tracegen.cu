@@ -1,0 +1,72 @@
+// K6: event -> row kernels for the core ALU chips.  One thread fills one row into a shared-memory
+// tile (row stride odd, so that the column-wise read-back is conflict-free); the CTA then stores
+// the tile with fully coalesced writes in either layout: its 128 rows are one contiguous block of
+// the row-major matrix, and 128 consecutive elements of every column of the column-major one.
+// HBM-bound by construction: 28 bytes read and 4 * width bytes written per row.
+#include "tracegen.h"
+#include <cstring>
+
+namespace zkb {
+
+__constant__ u32 d_inv255[256];
+
+void tracegen_upload_constants() {
+  u32 h[256];
+  alu_build_inv255(h);
+  ZKB_CUDA(cudaMemcpyToSymbol(d_inv255, h, sizeof(h)));
+}
+
+constexpr int TG_ROWS = 128;   // rows per CTA = threads per CTA
+
+template <int CHIP>
+__global__ void __launch_bounds__(TG_ROWS) alu_rows_kernel(const u32* __restrict__ events, size_t n, size_t height,
+                                                           u32* __restrict__ out, int col_major) {
+  constexpr int W = alu_width(CHIP);
+  constexpr int WP = W | 1;
+  __shared__ u32 ev_s[TG_ROWS * 7];
+  __shared__ u32 tile[TG_ROWS * WP];
+  const size_t row0 = (size_t)blockIdx.x * TG_ROWS;
+  // the CTA's events are 7 * 128 consecutive words: coalesced load, then one record per thread
+  const size_t ev_words = row0 < n ? (n - row0 < TG_ROWS ? (n - row0) * 7 : (size_t)TG_ROWS * 7) : 0;
+  for (u32 i = threadIdx.x; i < ev_words; i += TG_ROWS) ev_s[i] = events[row0 * 7 + i];
+  __syncthreads();
+  u32* r = tile + threadIdx.x * WP;
+  if (row0 + threadIdx.x < n) fill_alu_row(CHIP, alu_event_from_words(ev_s + 7 * threadIdx.x), r, d_inv255);
+  else fill_alu_padding(CHIP, r);
+  __syncthreads();
+  const size_t rows = height - row0 < TG_ROWS ? height - row0 : TG_ROWS;
+  if (col_major) {
+    if (threadIdx.x < rows) {
+#pragma unroll 4
+      for (int c = 0; c < W; c++) out[(size_t)c * height + row0 + threadIdx.x] = tile[threadIdx.x * WP + c];
+    }
+  } else {
+    u32* dst = out + row0 * W;
+    for (u32 i = threadIdx.x; i < rows * W; i += TG_ROWS) dst[i] = tile[(i / W) * WP + (i % W)];
+  }
+}
+
+void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* out, bool col_major, cudaStream_t s) {
+  if (!height) return;
+  if (n > height) throw std::runtime_error("zkb200: alu_trace: more events than rows");
+  const unsigned grid = ceil_div(height, TG_ROWS);
+  const int cm = col_major ? 1 : 0;
+  switch (chip) {
+    case ALU_ADDSUB: alu_rows_kernel<ALU_ADDSUB><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_BITWISE: alu_rows_kernel<ALU_BITWISE><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_LT: alu_rows_kernel<ALU_LT><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_SLL: alu_rows_kernel<ALU_SLL><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_SR: alu_rows_kernel<ALU_SR><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_CLOCLZ: alu_rows_kernel<ALU_CLOCLZ><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    default: throw std::runtime_error("zkb200: alu_trace: unknown chip");
+  }
+  ZKB_CHECK_LAUNCH();
+}
+
+int alu_chip_by_name(const char* name) {
+  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz"};
+  for (int i = 0; i < ALU_NCHIPS; i++) if (!strcmp(name, names[i])) return i;
+  return -1;
+}
+
+}  // namespace zkb

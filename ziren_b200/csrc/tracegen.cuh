@@ -1,0 +1,193 @@
+// Row fillers of the core ALU chips (trace generation on the GPU).
+// One AluEvent (crates/core/executor/src/events/instr.rs:11-26) becomes one row of the chip's
+// RowMajorMatrix; the column order is the #[repr(C)] order of the chip's column struct.  What each
+// column holds follows the chips' event_to_row (Rust, cited per chip) and its C++ twin
+// crates/core/machine/include/*.hpp that the reference's `sys` feature calls; the formulation
+// here is branch-free word arithmetic (carries, shifts and byte compares on whole 32/64-bit
+// words) instead of the reference's per-byte loops.  Host and device run the same code
+// (tests/hostcheck compiles it for the CPU and compares with the reference's C++).
+#pragma once
+#include "kb31.cuh"
+
+namespace zkb {
+
+enum AluChip : int { ALU_ADDSUB = 0, ALU_BITWISE = 1, ALU_LT = 2, ALU_SLL = 3, ALU_SR = 4, ALU_CLOCLZ = 5, ALU_NCHIPS = 6 };
+// opcodes as numbered by crates/core/executor/src/opcode.rs:25-49 (#[repr(u8)])
+enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_ROR = 12, OP_SLT = 13, OP_SLTU = 14,
+             OP_AND = 15, OP_OR = 16, OP_XOR = 17, OP_NOR = 18, OP_CLZ = 19, OP_CLO = 20 };
+
+KB_HD constexpr int alu_width(int chip) {
+  return chip == ALU_ADDSUB ? 19 : chip == ALU_BITWISE ? 18 : chip == ALU_LT ? 32 : chip == ALU_SLL ? 44 : chip == ALU_SR ? 67 : 17;
+}
+
+// AluEvent as laid out by #[repr(C)]: seven 32-bit words, the opcode in the low byte of word 2
+struct AluEv { u32 pc, next_pc, opcode, hi, a, b, c; };
+KB_HD AluEv alu_event_from_words(const u32* w) {
+  AluEv e;
+  e.pc = w[0]; e.next_pc = w[1]; e.opcode = w[2] & 0xffu; e.hi = w[3]; e.a = w[4]; e.b = w[5]; e.c = w[6];
+  return e;
+}
+
+KB_HD u32 tg_top_bit(u32 x) {                                 // index of the highest set bit, x != 0
+#if defined(__CUDA_ARCH__)
+  return 31u - (u32)__clz((int)x);
+#else
+  return 31u - (u32)__builtin_clz(x);
+#endif
+}
+KB_HD u32 tg_f(u32 x) { return fp_from_canonical(x).v; }      // F::from_canonical_u32 (x < p)
+KB_HD u32 tg_b(bool x) { return x ? KB_ONE : 0u; }            // F::from_bool
+KB_HD void tg_word(u32* r, u32 v) {                           // Word::from(u32): little-endian bytes
+  r[0] = tg_f(v & 0xffu); r[1] = tg_f((v >> 8) & 0xffu); r[2] = tg_f((v >> 16) & 0xffu); r[3] = tg_f(v >> 24);
+}
+KB_HD void tg_long(u32* r, u64 v) { tg_word(r, (u32)v); tg_word(r + 4, (u32)(v >> 32)); }
+KB_HD void tg_onehot(u32* r, int n, u32 hot) { for (int i = 0; i < n; i++) r[i] = tg_b((u32)i == hot); }
+KB_HD void tg_bits(u32* r, int n, u32 v) { for (int i = 0; i < n; i++) r[i] = tg_b((v >> i) & 1u); }
+
+// AddSubChip::event_to_row, crates/core/machine/src/alu/add_sub/mod.rs:152-171; AddOperation::populate,
+// operations/add.rs:23-47.  Columns: pc, next_pc, add_operation{value[4], carry[3]}, operand_1[4],
+// operand_2[4], is_add, is_sub.
+KB_HD void fill_add_sub(const AluEv& e, u32* r) {
+  const bool is_add = e.opcode == OP_ADD;
+  const u32 x = is_add ? e.b : e.a, y = e.c;
+  r[0] = tg_f(e.pc); r[1] = tg_f(e.next_pc);
+  tg_word(r + 2, x + y);
+  // carry out of the low 1, 2, 3 bytes
+  r[6] = tg_b(((x & 0xffu) + (y & 0xffu)) >> 8);
+  r[7] = tg_b(((x & 0xffffu) + (y & 0xffffu)) >> 16);
+  r[8] = tg_b(((x & 0xffffffu) + (y & 0xffffffu)) >> 24);
+  tg_word(r + 9, x);
+  tg_word(r + 13, y);
+  r[17] = tg_b(is_add);
+  r[18] = tg_b(e.opcode == OP_SUB);
+}
+
+// BitwiseChip::event_to_row, crates/core/machine/src/alu/bitwise/mod.rs.  Columns: pc, next_pc, a[4],
+// b[4], c[4], is_nor, is_xor, is_or, is_and.
+KB_HD void fill_bitwise(const AluEv& e, u32* r) {
+  r[0] = tg_f(e.pc); r[1] = tg_f(e.next_pc);
+  tg_word(r + 2, e.a); tg_word(r + 6, e.b); tg_word(r + 10, e.c);
+  r[14] = tg_b(e.opcode == OP_NOR); r[15] = tg_b(e.opcode == OP_XOR);
+  r[16] = tg_b(e.opcode == OP_OR); r[17] = tg_b(e.opcode == OP_AND);
+}
+
+// LtChip::event_to_row, crates/core/machine/src/alu/lt/mod.rs.  Columns: pc, next_pc, is_slt, is_sltu,
+// a[4], b[4], c[4], byte_flags[4], b_masked, c_masked, not_eq_inv, msb_b, msb_c, bit_b, bit_c, sltu,
+// is_comp_eq, is_sign_eq, comparison_bytes[2].  inv255[d] = 1/d (Montgomery) for d = 1..255.
+KB_HD void fill_lt(const AluEv& e, u32* r, const u32* inv255) {
+  const bool slt = e.opcode == OP_SLT;
+  r[0] = tg_f(e.pc); r[1] = tg_f(e.next_pc);
+  r[2] = tg_b(slt); r[3] = tg_b(e.opcode == OP_SLTU);
+  tg_word(r + 4, e.a); tg_word(r + 8, e.b); tg_word(r + 12, e.c);
+  // SLT compares with the sign bits cleared (they are handled by bit_b / bit_c)
+  const u32 bc = slt ? e.b & 0x7fffffffu : e.b, cc = slt ? e.c & 0x7fffffffu : e.c;
+  const u32 diff = bc ^ cc;
+  u32 hot = 4, bb = 0, cb = 0, inv = 0;
+  if (diff) {
+    // most significant differing byte
+    hot = tg_top_bit(diff) >> 3;
+    bb = (bc >> (8 * hot)) & 0xffu;
+    cb = (cc >> (8 * hot)) & 0xffu;
+    inv = bb > cb ? inv255[bb - cb] : KB_P - inv255[cb - bb];
+  }
+  tg_onehot(r + 16, 4, hot);
+  r[20] = tg_f((e.b >> 24) & 0x7fu); r[21] = tg_f((e.c >> 24) & 0x7fu);
+  r[22] = inv;
+  const u32 msb_b = e.b >> 31, msb_c = e.c >> 31;
+  r[23] = tg_b(msb_b); r[24] = tg_b(msb_c);
+  r[25] = tg_b(msb_b && slt); r[26] = tg_b(msb_c && slt);
+  r[27] = tg_b(bc < cc);
+  r[28] = tg_b(diff == 0);
+  r[29] = tg_b(!slt || msb_b == msb_c);
+  r[30] = tg_f(bb); r[31] = tg_f(cb);
+}
+
+// ShiftLeft::event_to_row, crates/core/machine/src/alu/sll/mod.rs.  Columns: pc, next_pc, a[4], b[4],
+// c[4], c_least_sig_byte[8], shift_by_n_bits[8], bit_shift_multiplier, bit_shift_result[4],
+// bit_shift_result_carry[4], shift_by_n_bytes[4], is_real.
+KB_HD void fill_shift_left(const AluEv& e, u32* r) {
+  r[0] = tg_f(e.pc); r[1] = tg_f(e.next_pc);
+  tg_word(r + 2, e.a); tg_word(r + 6, e.b); tg_word(r + 10, e.c);
+  tg_bits(r + 14, 8, e.c);
+  const u32 nbits = e.c & 7u, nbytes = (e.c & 31u) >> 3;
+  tg_onehot(r + 22, 8, nbits);
+  r[30] = tg_f(1u << nbits);
+  // b * 2^nbits byte by byte: result bytes are those of the 64-bit shift, the carry after byte i
+  // is what the low i+1 bytes push beyond them
+  const u64 sh = (u64)e.b << nbits;
+  tg_word(r + 31, (u32)sh);
+  for (int i = 0; i < 4; i++) {
+    const u64 low = (u64)(i == 3 ? e.b : (e.b & ((1u << (8 * (i + 1))) - 1u))) << nbits;
+    r[35 + i] = tg_f((u32)(low >> (8 * (i + 1))));
+  }
+  tg_onehot(r + 39, 4, nbytes);
+  r[43] = KB_ONE;
+}
+
+// ShiftRightChip::event_to_row, crates/core/machine/src/alu/sr/mod.rs.  Columns: pc, next_pc, b[4], c[4],
+// shift_by_n_bits[8], shift_by_n_bytes[4], byte_shift_result[8], bit_shift_result[8],
+// shr_carry_output_carry[8], shr_carry_output_shifted_byte[8], b_msb, c_least_sig_byte[8], is_srl,
+// is_ror, is_sra, is_real.
+KB_HD void fill_shift_right(const AluEv& e, u32* r) {
+  r[0] = tg_f(e.pc); r[1] = tg_f(e.next_pc);
+  tg_word(r + 2, e.b); tg_word(r + 6, e.c);
+  const u32 nbits = e.c & 7u, nbytes = (e.c & 31u) >> 3;
+  tg_onehot(r + 10, 8, nbits);
+  tg_onehot(r + 18, 4, nbytes);
+  // the operand widened to 64 bits: sign-extended (SRA), doubled (ROR) or zero-extended
+  u64 wide = e.b;
+  if (e.opcode == OP_SRA) wide = (u64)(int64_t)(int32_t)e.b;
+  else if (e.opcode == OP_ROR) wide |= (u64)e.b << 32;
+  const u64 by_bytes = wide >> (8 * nbytes);
+  tg_long(r + 22, by_bytes);
+  tg_long(r + 30, by_bytes >> nbits);
+  // per byte: the bits shifted out (carry) and what stays (shifted byte)
+  const u64 ones = 0x0101010101010101ull;
+  const u64 carry_mask = ones * ((1u << nbits) - 1u);
+  tg_long(r + 38, by_bytes & carry_mask);
+  tg_long(r + 46, (by_bytes >> nbits) & (ones * (0xffu >> nbits)));
+  r[54] = tg_b(e.b >> 31);
+  tg_bits(r + 55, 8, e.c);
+  r[63] = tg_b(e.opcode == OP_SRL); r[64] = tg_b(e.opcode == OP_ROR); r[65] = tg_b(e.opcode == OP_SRA);
+  r[66] = KB_ONE;
+}
+
+// CloClzChip::generate_trace, crates/core/machine/src/alu/clo_clz/mod.rs:105-122.  Columns: pc, next_pc,
+// a[4], b[4], bb[4], is_bb_zero, is_clz, is_real.
+KB_HD void fill_clo_clz(const AluEv& e, u32* r) {
+  const bool clz = e.opcode == OP_CLZ;
+  const u32 bb = clz ? e.b : ~e.b;
+  r[0] = tg_f(e.pc); r[1] = tg_f(e.next_pc);
+  tg_word(r + 2, e.a); tg_word(r + 6, e.b); tg_word(r + 10, bb);
+  r[14] = tg_b(bb == 0); r[15] = tg_b(clz); r[16] = KB_ONE;
+}
+
+// Rows past the last event (generate_trace of each chip): zeros, except the dummy rows that keep the
+// shift and count-leading chips' constraints satisfied (sll/mod.rs:160-173, sr/mod.rs:184-187,
+// clo_clz/mod.rs:150-163).
+KB_HD void fill_alu_padding(int chip, u32* r) {
+  const int w = alu_width(chip);
+  for (int i = 0; i < w; i++) r[i] = 0;
+  if (chip == ALU_SLL) { r[22] = KB_ONE; r[30] = KB_ONE; r[39] = KB_ONE; }
+  if (chip == ALU_SR) { r[10] = KB_ONE; r[18] = KB_ONE; }
+  if (chip == ALU_CLOCLZ) { tg_word(r + 2, 32); r[14] = KB_ONE; }
+}
+
+KB_HD void fill_alu_row(int chip, const AluEv& e, u32* r, const u32* inv255) {
+  switch (chip) {
+    case ALU_ADDSUB: fill_add_sub(e, r); break;
+    case ALU_BITWISE: fill_bitwise(e, r); break;
+    case ALU_LT: fill_lt(e, r, inv255); break;
+    case ALU_SLL: fill_shift_left(e, r); break;
+    case ALU_SR: fill_shift_right(e, r); break;
+    default: fill_clo_clz(e, r); break;
+  }
+}
+
+// 1/d for d = 0..255 in Montgomery form (entry 0 unused)
+inline void alu_build_inv255(u32* out) {
+  out[0] = 0;
+  for (u32 d = 1; d < 256; d++) out[d] = fp_inv(fp_from_canonical(d)).v;
+}
+
+}  // namespace zkb

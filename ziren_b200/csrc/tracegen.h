@@ -1,0 +1,17 @@
+// Trace generation on the GPU for the core ALU chips.
+#pragma once
+#include "common.h"
+#include "tracegen.cuh"
+
+namespace zkb {
+
+void tracegen_upload_constants();   // once per device: the 1/d table of the Lt chip
+
+// events: n records of 28 bytes (#[repr(C)] AluEvent) in DEVICE memory; out: height x width words,
+// row-major (the RowMajorMatrix layout zkb200_commit takes) or column-major (the layout every kernel
+// of this library works in).  Rows >= n are the chip's padding rows.
+void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* out, bool col_major, cudaStream_t s);
+
+int alu_chip_by_name(const char* name);   // MachineAir::name -> AluChip, -1 if not an ALU chip handled here
+
+}  // namespace zkb

@@ -241,3 +241,13 @@ class B200Prover:
 
     def convert(self, data, n, to_montgomery=True):
         self._check(_ffi.lib().zkb200_convert(self._h, _data_ptr(data), n, int(to_montgomery)))
+
+    # ---- trace generation ----------------------------------------------
+    def generate_alu_trace(self, chip: str, events, log_height: int, out, col_major: bool = False):
+        """`MachineAir::generate_trace` of an ALU chip (AddSub, Bitwise, Lt, ShiftLeft, ShiftRight,
+        CloClz) on the GPU.  `events`: the record's `Vec<AluEvent>` as (n, 7) uint32 words (numpy or a
+        CUDA tensor, see ziren_b200/tracegen.py); `out`: CUDA tensor of 2^log_height x width words."""
+        n = int(_shape(events)[0]) if len(_shape(events)) else 0
+        self._check(_ffi.lib().zkb200_generate_alu_trace(self._h, chip.encode(), _data_ptr(events) if n else None, n,
+                                                         int(log_height), _data_ptr(out), int(col_major)))
+

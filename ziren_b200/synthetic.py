@@ -322,3 +322,119 @@ def compress_case(log_max: int = 18, seed: int = 0xC0FFEE, **kw) -> ShardCase:
         groups = max(lookups, width // 6, 1)
         wides.append(WideSpec(name, max(2, lh - d), groups, lookups, max(0, width - 6 * groups)))
     return build_case(wides, seed=seed, cycles=0, **kw)
+
+
+# ---- real ALU chips (trace generation) ------------------------------------
+# The arithmetic constraints of two reference chips restated in the AirBuilder, so that traces made by
+# `zkb200_generate_alu_trace` can be proved and verified.  Their lookups (receive_instruction, byte
+# range checks) need the Cpu and Byte tables of the full MIPS machine and are left out: these chips
+# carry the chips' polynomial identities only.
+
+def _assert_bool(b, x):
+    b.assert_zero(x * (x - 1))
+
+
+def _add_sub_chip() -> Chip:
+    """AddSubChip::eval crates/core/machine/src/alu/add_sub/mod.rs:196-250 with AddOperation::eval
+    crates/core/machine/src/operations/add.rs:57-94; columns of AddSubCols (add_sub/mod.rs:43-65)."""
+    def ev(b):
+        value = [b.main(2 + i) for i in range(4)]
+        carry = [b.main(6 + i) for i in range(3)]
+        x = [b.main(9 + i) for i in range(4)]
+        y = [b.main(13 + i) for i in range(4)]
+        is_add, is_sub = b.main(17), b.main(18)
+        is_real = is_add + is_sub
+        real = b.when(is_real)
+        over = [x[0] + y[0] - value[0]] + [x[i] + y[i] - value[i] + carry[i - 1] for i in (1, 2, 3)]
+        real.assert_zero(over[3] * (over[3] - 256))
+        for i in range(3):
+            real.assert_zero(carry[i] * (over[i] - 256))
+        for i in range(3):
+            real.assert_zero((carry[i] - 1) * over[i])
+        for i in range(3):
+            real.assert_zero(carry[i] * (carry[i] - 1))
+        real.assert_zero(is_real * (is_real - 1))
+        _assert_bool(b, is_add)
+        _assert_bool(b, is_sub)
+        _assert_bool(b, is_real)
+    return Chip("AddSub", 0, 19, ev, local_only=True)
+
+
+def _shift_left_chip() -> Chip:
+    """ShiftLeft::eval crates/core/machine/src/alu/sll/mod.rs:285-410; columns of ShiftLeftCols."""
+    def ev(b):
+        a = [b.main(2 + i) for i in range(4)]
+        bb = [b.main(6 + i) for i in range(4)]
+        c = [b.main(10 + i) for i in range(4)]
+        c_bits = [b.main(14 + i) for i in range(8)]
+        by_bits = [b.main(22 + i) for i in range(8)]
+        mult = b.main(30)
+        res = [b.main(31 + i) for i in range(4)]
+        car = [b.main(35 + i) for i in range(4)]
+        by_bytes = [b.main(39 + i) for i in range(4)]
+        total = c_bits[0]
+        for i in range(1, 8):
+            total = total + c_bits[i] * (1 << i)
+        b.assert_eq(total, c[0])
+        nbits = c_bits[0] + c_bits[1] * 2 + c_bits[2] * 4
+        for i in range(8):
+            b.when(by_bits[i]).assert_eq(nbits, i)
+        for i in range(8):
+            b.when(by_bits[i]).assert_eq(mult, 1 << i)
+        for i in range(4):
+            v = bb[i] * mult - car[i] * 256
+            if i > 0:
+                v = v + car[i - 1]
+            b.assert_eq(res[i], v)
+        nbytes = c_bits[3] + c_bits[4] * 2
+        for i in range(4):
+            b.when(by_bytes[i]).assert_eq(nbytes, i)
+        for k in range(4):
+            sh = b.when(by_bytes[k])
+            for i in range(4):
+                if i < k:
+                    sh.assert_eq(a[i], 0)
+                else:
+                    sh.assert_eq(a[i], res[i - k])
+        for bit in c_bits:
+            _assert_bool(b, bit)
+        for s in by_bits:
+            _assert_bool(b, s)
+        tot = by_bits[0]
+        for s in by_bits[1:]:
+            tot = tot + s
+        b.assert_eq(tot, 1)
+        for s in by_bytes:
+            _assert_bool(b, s)
+        tot = by_bytes[0]
+        for s in by_bytes[1:]:
+            tot = tot + s
+        b.assert_eq(tot, 1)
+        _assert_bool(b, b.main(43))
+    return Chip("ShiftLeft", 0, 44, ev, local_only=True)
+
+
+def alu_case(traces: dict, *, with_lookup_pair: bool = True, **kw) -> ShardCase:
+    """`traces`: {"AddSub": rows, "ShiftLeft": rows} in canonical form, as produced by trace generation.
+    with_lookup_pair adds the Fibonacci/Sink pair so that the shard also has permutation traces (the two
+    ALU chips alone have no lookups here)."""
+    chips = [_add_sub_chip(), _shift_left_chip()]
+    traces = dict(traces)
+    pv = np.zeros(8, dtype=np.uint32)
+    if with_lookup_pair:
+        n = 1 << 5
+        a, b_ = 0, 1
+        rows = np.empty((n, 2), dtype=np.uint32)
+        for i in range(n):
+            rows[i] = (a, b_)
+            a, b_ = b_, (a + b_) % P
+        pv[1], pv[2], pv[3] = 0, 1, rows[-1, 1]
+        sink = np.zeros((n, 3), dtype=np.uint32)
+        sink[:, :2] = rows[::-1]
+        sink[:, 2] = 1
+        chips += [_fib_chip(), _sink_chip()]
+        traces["Fibonacci"], traces["Sink"] = rows, sink
+    machine = Machine(chips, num_pv_elts=4, num_queries=kw.get("num_queries", 8), pow_bits=kw.get("pow_bits", 4),
+                      log_blowup=kw.get("log_blowup", 1))
+    cycles = sum(int(traces[k].shape[0]) for k in ("AddSub", "ShiftLeft") if k in traces)
+    return ShardCase(machine, {}, traces, pv, cycles)

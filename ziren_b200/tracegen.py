@@ -1,0 +1,99 @@
+"""Host side of GPU trace generation for the core ALU chips: the chip
+table, the `AluEvent` record layout and the padded height rule, mirroring what the Rust host keeps
+when it hands a record's event vectors to `zkb200_generate_alu_trace` (include/zkb200.h).
+
+Reference: `AluEvent` crates/core/executor/src/events/instr.rs:11-26 (#[repr(C)]: seven 32-bit
+words, the #[repr(u8)] opcode in the low byte of the third); `next_power_of_two`
+crates/core/machine/src/utils/mod.rs:101-125; chips crates/core/machine/src/alu/*/mod.rs."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import field as kb
+
+# MachineAir::name -> (NUM_*_COLS, opcodes the chip receives, crates/core/executor/src/opcode.rs:25-49)
+OPCODES = {"ADD": 0, "SUB": 1, "SLL": 9, "SRL": 10, "SRA": 11, "ROR": 12, "SLT": 13, "SLTU": 14, "AND": 15, "OR": 16,
+           "XOR": 17, "NOR": 18, "CLZ": 19, "CLO": 20}
+ALU_CHIPS = {
+    "AddSub": (19, ("ADD", "SUB")),
+    "Bitwise": (18, ("AND", "OR", "XOR", "NOR")),
+    "Lt": (32, ("SLT", "SLTU")),
+    "ShiftLeft": (44, ("SLL",)),
+    "ShiftRight": (67, ("SRL", "SRA", "ROR")),
+    "CloClz": (17, ("CLZ", "CLO")),
+}
+EVENT_WORDS = 7          # pc, next_pc, opcode, hi, a, b, c
+EVENT_BYTES = 28
+
+
+def width(chip: str) -> int:
+    return ALU_CHIPS[chip][0]
+
+
+def padded_log_height(n_events: int, fixed_log2_rows: int | None = None) -> int:
+    """`next_power_of_two(n, fixed_log2_rows)`: at least 16 rows, or the shape's fixed height."""
+    if fixed_log2_rows is not None:
+        if n_events > (1 << fixed_log2_rows):
+            raise ValueError(f"fixed log2 rows is too small: got {n_events}, expected {1 << fixed_log2_rows}")
+        return fixed_log2_rows
+    return max(4, int(n_events - 1).bit_length() if n_events > 1 else 0)
+
+
+def _alu_result(op: np.ndarray, b: np.ndarray, c: np.ndarray) -> np.ndarray:
+    """`a` of well-formed events (what the MIPS executor would have recorded)."""
+    b64, c64 = b.astype(np.uint64), c.astype(np.uint64)
+    sh = c64 & np.uint64(31)
+    sb, sc = b.astype(np.int32), c.astype(np.int32)
+    out = np.zeros_like(b64)
+    m32 = np.uint64(0xFFFFFFFF)
+
+    def put(name, val):
+        sel = op == OPCODES[name]
+        out[sel] = val[sel] & m32
+
+    put("ADD", b64 + c64)
+    put("SUB", b64 - c64)
+    put("SLL", b64 << sh)
+    put("SRL", b64 >> sh)
+    put("SRA", (sb.astype(np.int64) >> sh.astype(np.int64)).astype(np.uint64))
+    put("ROR", (b64 >> sh) | (b64 << (np.uint64(32) - sh)))
+    put("SLT", (sb < sc).astype(np.uint64))
+    put("SLTU", (b < c).astype(np.uint64))
+    put("AND", b64 & c64)
+    put("OR", b64 | c64)
+    put("XOR", b64 ^ c64)
+    put("NOR", ~(b64 | c64))
+    clz = np.array([32 - int(x).bit_length() for x in b], dtype=np.uint64) if b.size else np.zeros(0, np.uint64)
+    clo = np.array([32 - int(x ^ 0xFFFFFFFF).bit_length() for x in b], dtype=np.uint64) if b.size else np.zeros(0, np.uint64)
+    put("CLZ", clz)
+    put("CLO", clo)
+    return out.astype(np.uint32)
+
+
+EDGE_OPERANDS = np.array([0, 1, 7, 8, 9, 31, 32, 33, 0x7F, 0x80, 0xFF, 0x100, 0x7FFF, 0x8000, 0xFFFF, 0x10000, 0x7FFFFF, 0x800000,
+                          0xFFFFFF, 0x1000000, 0x7FFFFFFF, 0x80000000, 0x80000001, 0xFFFFFFFE, 0xFFFFFFFF], dtype=np.uint32)
+
+
+def synthetic_events(chip: str, n: int, seed: int = 0, edges: bool = True) -> np.ndarray:
+    """n well-formed events of the chip as (n, 7) uint32 words: seeded uniform operands, the first rows
+    replaced by every pair of edge operands (byte boundaries, sign bits, equal and near-equal words)."""
+    rng = np.random.default_rng(0xA1E00 + seed)
+    ev = np.zeros((n, EVENT_WORDS), np.uint32)
+    ev[:, 0] = rng.integers(0, kb.P, n) & ~np.uint32(3)
+    ev[:, 1] = ev[:, 0] + 4
+    ev[:, 2] = rng.choice([OPCODES[o] for o in ALU_CHIPS[chip][1]], n)
+    ev[:, 3] = 0
+    ev[:, 5] = rng.integers(0, 1 << 32, n, dtype=np.uint64)
+    ev[:, 6] = rng.integers(0, 1 << 32, n, dtype=np.uint64)
+    if edges:
+        m = len(EDGE_OPERANDS)
+        k = min(n, m * m)
+        idx = np.arange(k)
+        ev[:k, 5] = EDGE_OPERANDS[idx // m]
+        ev[:k, 6] = EDGE_OPERANDS[idx % m]
+        lo, hi = k, min(n, k + 256)
+        ev[lo:hi, 6] = ev[lo:hi, 5]                                                  # equal operands
+        lo2, hi2 = hi, min(n, hi + 256)
+        ev[lo2:hi2, 6] = ev[lo2:hi2, 5] ^ (np.uint32(1) << rng.integers(0, 32, hi2 - lo2).astype(np.uint32))   # one bit apart
+    ev[:, 4] = _alu_result(ev[:, 2], ev[:, 5], ev[:, 6])
+    return ev
