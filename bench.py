@@ -183,6 +183,8 @@ def main():
     distributed = args.world > 1
     numa_cpus = bind_to_gpu_numa_node(torch, args.local_rank) if distributed else None
     if distributed:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is VERSION/INFO: keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", args.local_rank))
 
     case = make_case(args)

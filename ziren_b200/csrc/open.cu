@@ -1,5 +1,6 @@
 #include "open.h"
 #include <algorithm>
+#include <mutex>
 
 namespace zkb {
 
@@ -112,13 +113,15 @@ void eval_columns(const u32* lde, size_t H, size_t n, size_t W, const u32* w0, c
   // 1042-CTA keccak matrix runs 3.5 waves unsplit)
   static int slots_per_sm[2] = {0, 0};
   static int sms = 0;
-  if (!sms) {
+  static std::once_flag once;       // several host threads open shards concurrently
+  std::call_once(once, [] {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slots_per_sm[0], eval_columns_kernel<1>, EC_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slots_per_sm[1], eval_columns_kernel<2>, EC_THREADS, 0);
-  }
+    if (sms <= 0) sms = 148;
+  });
   const size_t slots = (size_t)sms * std::max(1, slots_per_sm[npoints == 1 ? 0 : 1]);
   size_t nsplit = 1;
   if (colblocks < slots) nsplit = (slots + colblocks - 1) / colblocks;
