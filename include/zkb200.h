@@ -138,13 +138,16 @@ int zkb200_fri_fold(zkb200_ctx* ctx, const uint32_t* in, size_t m, const uint32_
 /* K4d: smallest proof-of-work witness for a challenger image */
 int zkb200_grind(zkb200_ctx* ctx, const uint32_t challenger[34], unsigned bits, uint32_t* witness_out);
 /* ---- trace generation ---------------------------------------------
- * MachineAir::generate_trace of the core ALU chips AddSub, Bitwise, Lt, ShiftLeft, ShiftRight and
- * CloClz (crates/core/machine/src/alu/{add_sub,bitwise,lt,sll,sr,clo_clz}/mod.rs; the reference's
- * own C++ twins are crates/core/machine/include/*.hpp behind cpp/extern.cpp:15-80): one event per
- * row in event order, then the chip's padding rows up to 2^log_height (next_power_of_two /
+ * MachineAir::generate_trace of the core ALU chips AddSub, Bitwise, Lt, ShiftLeft, ShiftRight, CloClz
+ * (crates/core/machine/src/alu/{add_sub,bitwise,lt,sll,sr,clo_clz}/mod.rs) and of the control-flow
+ * chips Branch and Jump (crates/core/machine/src/control_flow/{branch,jump}/trace.rs); the reference's
+ * own C++ twins are crates/core/machine/include/*.hpp behind cpp/extern.cpp:15-90.  One event per row
+ * in event order, then the chip's padding rows up to 2^log_height (next_power_of_two /
  * fixed_log2_rows, crates/core/machine/src/utils/mod.rs:101-125, is the caller's choice).
- * `events` is the record's Vec<AluEvent> as it lies in memory (#[repr(C)],
- * crates/core/executor/src/events/instr.rs:11-26), host or device; `out` is DEVICE memory of
+ * `events` is the record's event vector as it lies in memory, host or device: 28-byte #[repr(C)]
+ * records, `AluEvent` {pc, next_pc, opcode, hi, a, b, c} for the ALU chips and `BranchEvent` /
+ * `JumpEvent` {pc, next_pc, next_next_pc, opcode, a, b, c} for Branch / Jump
+ * (crates/core/executor/src/events/instr.rs:11-26, :160-217).  `out` is DEVICE memory of
  * 2^log_height x width words, Montgomery, row-major (col_major = 0: the RowMajorMatrix layout
  * zkb200_commit takes) or column-major (col_major = 1: the layout of the kernel-level entry points). */
 typedef struct {
@@ -152,9 +155,15 @@ typedef struct {
   uint8_t opcode;        /* Opcode as #[repr(u8)], crates/core/executor/src/opcode.rs:25-89 */
   uint32_t hi, a, b, c;
 } zkb200_alu_event;
+typedef struct {
+  uint32_t pc, next_pc, next_next_pc;
+  uint8_t opcode;
+  uint32_t a, b, c;
+} zkb200_flow_event;     /* BranchEvent / JumpEvent */
 /* NUM_*_COLS of the chip, -1 if this library has no row filler for it */
 int zkb200_alu_trace_width(const char* chip);
-int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const zkb200_alu_event* events, size_t n_events,
+/* events: zkb200_alu_event[] or, for "Branch" / "Jump", zkb200_flow_event[] */
+int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* events, size_t n_events,
                               unsigned log_height, uint32_t* out, int col_major);
 /* layout helpers on the context stream: row-major <-> column-major, canonical <-> Montgomery */
 int zkb200_transpose(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t height, size_t width, int to_colmajor);

@@ -245,7 +245,9 @@ int zko_alu_trace(int chip, const u32* ev, size_t n, size_t height, u32* out) {
   try {
     std::vector<AluEvent> e(n);
     for (size_t i = 0; i < n; i++)
-      e[i] = AluEvent{ev[7 * i], ev[7 * i + 1], ev[7 * i + 2] & 0xff, ev[7 * i + 3], ev[7 * i + 4], ev[7 * i + 5], ev[7 * i + 6]};
+      e[i] = AluEvent{ev[7 * i], ev[7 * i + 1], ev[7 * i + 2], ev[7 * i + 3], ev[7 * i + 4], ev[7 * i + 5], ev[7 * i + 6]};
+    // the #[repr(u8)] opcode is the low byte of its word: word 2 of an AluEvent, word 3 of a Branch/JumpEvent
+    for (auto& x : e) { if (chip == T_BRANCH || chip == T_JUMP) x.hi &= 0xff; else x.opcode &= 0xff; }
     alu_trace(chip, e.data(), n, height, out);
     return 0;
   } catch (const std::exception& ex) {

@@ -60,7 +60,7 @@ def ref_core_lib():
     return l
 
 
-ALU_CHIPS = ("AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz")
+ALU_CHIPS = ("AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump")
 
 
 def alu_width(chip):
@@ -68,7 +68,8 @@ def alu_width(chip):
 
 
 def alu_trace(chip, events, height):
-    """events: (n, 7) uint32 {pc, next_pc, opcode, hi, a, b, c}; returns (height, width) canonical rows."""
+    """events: (n, 7) uint32, {pc, next_pc, opcode, hi, a, b, c} (AluEvent) or {pc, next_pc, next_next_pc, opcode,
+    a, b, c} (Branch / Jump); returns (height, width) canonical rows."""
     ev = _a(events).reshape(-1, 7)
     w = alu_width(chip)
     out = np.zeros((int(height), w), np.uint32)

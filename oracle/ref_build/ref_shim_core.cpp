@@ -12,13 +12,15 @@
 #include "shift_left.hpp"
 #include "shift_right.hpp"
 #include "clo_clz.hpp"
+#include "branch.hpp"
+#include "jump.hpp"
 
 using namespace zkm_core_machine_sys;
 
 template <class Cols> static constexpr size_t ncols() { return sizeof(Cols) / sizeof(kb31_t); }
 
 extern "C" {
-// chip: 0 AddSub, 1 Bitwise, 2 Lt, 3 ShiftLeft, 4 ShiftRight, 5 CloClz
+// chip: 0 AddSub, 1 Bitwise, 2 Lt, 3 ShiftLeft, 4 ShiftRight, 5 CloClz, 6 Branch, 7 Jump
 unsigned ref_alu_num_cols(int chip) {
   switch (chip) {
     case 0: return ncols<AddSubCols<kb31_t>>();
@@ -27,10 +29,13 @@ unsigned ref_alu_num_cols(int chip) {
     case 3: return ncols<ShiftLeftCols<kb31_t>>();
     case 4: return ncols<ShiftRightCols<kb31_t>>();
     case 5: return ncols<CloClzCols<kb31_t>>();
+    case 6: return ncols<BranchColumns<kb31_t>>();
+    case 7: return ncols<JumpColumns<kb31_t>>();
   }
   return 0;
 }
-// events: n records of 7 words {pc, next_pc, opcode, hi, a, b, c}; rows: n x num_cols, zero-initialised here,
+// events: n records of 7 words, AluEvent {pc, next_pc, opcode, hi, a, b, c} for chips 0-5,
+// BranchEvent / JumpEvent {pc, next_pc, next_next_pc, opcode, a, b, c} for chips 6-7; rows: n x num_cols, zero-initialised here,
 // Montgomery words exactly as the reference leaves them in the trace
 int ref_alu_event_to_rows(int chip, const uint32_t* ev, size_t n, uint32_t* rows) {
   const unsigned w = ref_alu_num_cols(chip);
@@ -41,6 +46,8 @@ int ref_alu_event_to_rows(int chip, const uint32_t* ev, size_t n, uint32_t* rows
     e.pc = ev[7 * i]; e.next_pc = ev[7 * i + 1]; e.opcode = (Opcode)ev[7 * i + 2]; e.hi = ev[7 * i + 3];
     e.a = ev[7 * i + 4]; e.b = ev[7 * i + 5]; e.c = ev[7 * i + 6];
     uint32_t* r = rows + i * w;
+    BranchEvent be{ev[7 * i], ev[7 * i + 1], ev[7 * i + 2], (Opcode)ev[7 * i + 3], ev[7 * i + 4], ev[7 * i + 5], ev[7 * i + 6]};
+    JumpEvent je{be.pc, be.next_pc, be.next_next_pc, be.opcode, be.a, be.b, be.c};
     switch (chip) {
       case 0: add_sub::event_to_row<kb31_t>(e, *reinterpret_cast<AddSubCols<kb31_t>*>(r)); break;
       case 1: bitwise::event_to_row<kb31_t>(e, *reinterpret_cast<BitwiseCols<kb31_t>*>(r)); break;
@@ -48,6 +55,8 @@ int ref_alu_event_to_rows(int chip, const uint32_t* ev, size_t n, uint32_t* rows
       case 3: shift_left::event_to_row<kb31_t>(e, *reinterpret_cast<ShiftLeftCols<kb31_t>*>(r)); break;
       case 4: shift_right::event_to_row<kb31_t>(e, *reinterpret_cast<ShiftRightCols<kb31_t>*>(r)); break;
       case 5: clo_clz::event_to_row<kb31_t>(e, *reinterpret_cast<CloClzCols<kb31_t>*>(r)); break;
+      case 6: branch::event_to_row<kb31_t>(be, *reinterpret_cast<BranchColumns<kb31_t>*>(r)); break;
+      case 7: jump::event_to_row<kb31_t>(je, *reinterpret_cast<JumpColumns<kb31_t>*>(r)); break;
     }
   }
   return 0;

@@ -1,8 +1,8 @@
 // Stand-in for the header cbindgen generates in the reference's Rust build
 // (crates/core/machine/build.rs:94-180); that build cannot run here (no Rust toolchain).  It
 // declares, with the field order of the Rust #[repr(C)] definitions cited below, the layout types
-// the reference's ALU row fillers (crates/core/machine/include/{add_sub,bitwise,lt,shift_left,
-// shift_right,clo_clz}.hpp) name, plus the names utils.hpp mentions in signatures.  This file is
+// the reference's ALU and control-flow row fillers (crates/core/machine/include/{add_sub,bitwise,lt,
+// shift_left,shift_right,clo_clz,branch,jump}.hpp) name, plus the names utils.hpp mentions in signatures.  This file is
 // ours; the reference's headers are compiled from where they lie under /root/reference.
 #pragma once
 #include <cstddef>
@@ -36,6 +36,10 @@ struct AluEvent {
   uint32_t b;
   uint32_t c;
 };
+
+// crates/core/executor/src/events/instr.rs:160-217 (#[repr(C)])
+struct BranchEvent { uint32_t pc, next_pc, next_next_pc; Opcode opcode; uint32_t a, b, c; };
+struct JumpEvent { uint32_t pc, next_pc, next_next_pc; Opcode opcode; uint32_t a, b, c; };
 
 template <class T> struct Word { T _0[WORD_SIZE]; };   // crates/stark/src/word.rs:21
 
@@ -109,6 +113,30 @@ template <class T> struct CloClzCols {
   T pc, next_pc;
   Word<T> a, b, bb;
   T is_bb_zero, is_clz, is_real;
+};
+
+// crates/core/machine/src/control_flow/branch/columns.rs (BranchColumns)
+template <class T> struct BranchColumns {
+  T pc;
+  Word<T> next_pc;
+  KoalaBearWordRangeChecker<T> next_pc_range_checker;
+  Word<T> target_pc;
+  Word<T> next_next_pc;
+  KoalaBearWordRangeChecker<T> next_next_pc_range_checker;
+  Word<T> op_a_value, op_b_value, op_c_value;
+  T is_beq, is_bne, is_bltz, is_blez, is_bgtz, is_bgez;
+  T is_branching, a_gt_b, a_lt_b;
+};
+// crates/core/machine/src/control_flow/jump/columns.rs (JumpColumns)
+template <class T> struct JumpColumns {
+  T pc;
+  Word<T> next_pc;
+  KoalaBearWordRangeChecker<T> next_pc_range_checker;
+  Word<T> next_next_pc;
+  KoalaBearWordRangeChecker<T> next_next_pc_range_checker;
+  Word<T> op_a_value, op_b_value, op_c_value;
+  T is_jump, is_jumpi, is_jumpdirect;
+  KoalaBearWordRangeChecker<T> op_a_range_checker;
 };
 
 }  // namespace zkm_core_machine_sys

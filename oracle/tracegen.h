@@ -8,6 +8,9 @@
 //   ShiftLeft  crates/core/machine/src/alu/sll/mod.rs:130-178
 //   ShiftRight crates/core/machine/src/alu/sr/mod.rs:163-193, event_to_row below it
 //   CloClz     crates/core/machine/src/alu/clo_clz/mod.rs:100-166
+//   Branch     crates/core/machine/src/control_flow/branch/trace.rs:45-137 (columns.rs)
+//   Jump       crates/core/machine/src/control_flow/jump/trace.rs:45-113 (columns.rs)
+//   range checker  crates/core/machine/src/operations/koala_bear_word.rs:35-49
 // Pinned against the reference's own C++ row fillers (crates/core/machine/include/*.hpp compiled
 // into oracle/_ref/libzkref_core.so) and the golden rows generated from them
 // (tests/golden/alu_rows.json).
@@ -20,10 +23,13 @@
 namespace zko {
 
 struct AluEvent { u32 pc, next_pc, opcode, hi, a, b, c; };
-enum { T_ADDSUB = 0, T_BITWISE, T_LT, T_SLL, T_SR, T_CLOCLZ, T_NCHIPS };
-static const int ALU_WIDTHS[T_NCHIPS] = {19, 18, 32, 44, 67, 17};
+// the same seven words read as BranchEvent / JumpEvent {pc, next_pc, next_next_pc, opcode, a, b, c}
+struct FlowEvent { u32 pc, next_pc, next_next_pc, opcode, a, b, c; };
+enum { T_ADDSUB = 0, T_BITWISE, T_LT, T_SLL, T_SR, T_CLOCLZ, T_BRANCH, T_JUMP, T_NCHIPS };
+static const int ALU_WIDTHS[T_NCHIPS] = {19, 18, 32, 44, 67, 17, 62, 66};
 enum { K_ADD = 0, K_SUB = 1, K_SLL = 9, K_SRL = 10, K_SRA = 11, K_ROR = 12, K_SLT = 13, K_SLTU = 14, K_AND = 15, K_OR = 16,
-       K_XOR = 17, K_NOR = 18, K_CLZ = 19, K_CLO = 20 };
+       K_XOR = 17, K_NOR = 18, K_CLZ = 19, K_CLO = 20, K_BEQ = 21, K_BGEZ = 22, K_BGTZ = 23, K_BLEZ = 24, K_BLTZ = 25, K_BNE = 26,
+       K_JUMP = 27, K_JUMPI = 28, K_JUMPDIRECT = 29 };
 
 struct RowWriter {
   u32* r;
@@ -32,7 +38,47 @@ struct RowWriter {
   void flag(bool b) { r[at++] = b ? 1 : 0; }
   void bytes(const unsigned char* b, int n) { for (int i = 0; i < n; i++) put(b[i]); }
   void word(u32 v) { unsigned char b[4]; for (int i = 0; i < 4; i++) b[i] = (unsigned char)(v >> (8 * i)); bytes(b, 4); }
+  // KoalaBearWordRangeChecker::populate
+  void range_checker(u32 v) {
+    u32 bit[8];
+    for (int i = 0; i < 8; i++) { bit[i] = (v >> (24 + i)) & 1; put(bit[i]); }
+    u32 acc = bit[0] * bit[1];
+    put(acc);
+    for (int i = 2; i <= 6; i++) { acc *= bit[i]; put(acc); }
+  }
 };
+
+static inline void flow_row(int chip, const FlowEvent& e, u32* row) {
+  RowWriter w{row};
+  w.put(e.pc);
+  if (chip == T_BRANCH) {
+    w.word(e.next_pc); w.range_checker(e.next_pc);
+    w.word(e.next_pc + e.c);
+    w.word(e.next_next_pc); w.range_checker(e.next_next_pc);
+    w.word(e.a); w.word(e.b); w.word(e.c);
+    w.flag(e.opcode == K_BEQ); w.flag(e.opcode == K_BNE); w.flag(e.opcode == K_BLTZ);
+    w.flag(e.opcode == K_BLEZ); w.flag(e.opcode == K_BGTZ); w.flag(e.opcode == K_BGEZ);
+    const bool eq = e.a == e.b, lt = (int32_t)e.a < (int32_t)e.b, gt = (int32_t)e.a > (int32_t)e.b;
+    bool taken = false;
+    switch (e.opcode) {
+      case K_BEQ: taken = eq; break;
+      case K_BNE: taken = !eq; break;
+      case K_BLTZ: taken = lt; break;
+      case K_BLEZ: taken = lt || eq; break;
+      case K_BGTZ: taken = gt; break;
+      case K_BGEZ: taken = eq || gt; break;
+      default: break;
+    }
+    w.flag(taken); w.flag(gt); w.flag(lt);
+  } else {
+    w.word(e.next_pc); w.range_checker(e.next_pc);
+    w.word(e.next_next_pc); w.range_checker(e.next_next_pc);
+    w.word(e.a); w.word(e.b); w.word(e.c);
+    w.flag(e.opcode == K_JUMP); w.flag(e.opcode == K_JUMPI); w.flag(e.opcode == K_JUMPDIRECT);
+    w.range_checker(e.a);
+  }
+  if (w.at != ALU_WIDTHS[chip]) throw std::runtime_error("oracle: control-flow row width mismatch");
+}
 
 static inline void alu_row(int chip, const AluEvent& e, u32* row) {
   RowWriter w{row};
@@ -150,8 +196,10 @@ static inline void alu_trace(int chip, const AluEvent* ev, size_t n, size_t heig
   if (n > height) throw std::runtime_error("oracle: more events than rows");
   const int w = ALU_WIDTHS[chip];
   for (size_t i = 0; i < height; i++) {
-    if (i < n) alu_row(chip, ev[i], out + i * w);
-    else alu_padding_row(chip, out + i * w);
+    if (i >= n) alu_padding_row(chip, out + i * w);
+    else if (chip == T_BRANCH || chip == T_JUMP)
+      flow_row(chip, FlowEvent{ev[i].pc, ev[i].next_pc, ev[i].opcode, ev[i].hi, ev[i].a, ev[i].b, ev[i].c}, out + i * w);
+    else alu_row(chip, ev[i], out + i * w);
   }
 }
 

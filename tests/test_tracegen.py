@@ -82,11 +82,15 @@ def test_padded_height_rule():
 def test_synthetic_events_are_well_formed():
     for chip in CHIPS:
         ev = tg.synthetic_events(chip, 2000, seed=5)
-        assert set(np.unique(ev[:, 2])) <= {tg.OPCODES[o] for o in tg.ALU_CHIPS[chip][1]}
-        assert (ev[:, 0] < kb.P).all() and (ev[:, 1] < kb.P).all()
+        opcode_word = 3 if chip in tg.FLOW_CHIPS else 2          # BranchEvent / JumpEvent vs AluEvent
+        assert set(np.unique(ev[:, opcode_word]).tolist()) <= {tg.OPCODES[o] for o in tg.ALU_CHIPS[chip][1]}
+        assert (ev[:, 0] < kb.P).all() and np.array_equal(ev[:, 1], ev[:, 0] + 4)
     ev = tg.synthetic_events("AddSub", 2000, seed=5)
     add = ev[:, 2] == 0
     assert np.array_equal(ev[add, 4], ev[add, 5] + ev[add, 6]) and np.array_equal(ev[~add, 4], ev[~add, 5] - ev[~add, 6])
+    ev = tg.synthetic_events("Branch", 2000, seed=5)
+    taken = ev[:, 2] != ev[:, 1] + 4
+    assert 0.3 < taken.mean() < 0.7 and np.array_equal(ev[taken, 2], ev[taken, 1] + ev[taken, 6])
 
 
 def _alu_traces(oracle, n_add=1000, n_sll=300, seed=4):

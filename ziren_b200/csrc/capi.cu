@@ -239,10 +239,10 @@ int zkb200_alu_trace_width(const char* chip) {
   const int id = alu_chip_by_name(chip);
   return id < 0 ? -1 : alu_width(id);
 }
-int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const zkb200_alu_event* events, size_t n_events,
+int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* events, size_t n_events,
                               unsigned log_height, uint32_t* out, int col_major) {
   return guarded(ctx, [&] {
-    static_assert(sizeof(zkb200_alu_event) == 28, "AluEvent is seven 32-bit words");
+    static_assert(sizeof(zkb200_alu_event) == 28 && sizeof(zkb200_flow_event) == 28, "event records are seven 32-bit words");
     const int id = alu_chip_by_name(chip);
     if (id < 0) throw std::runtime_error(std::string("zkb200: generate_alu_trace: no row filler for chip ") + chip);
     if (log_height > 30) throw std::runtime_error("zkb200: generate_alu_trace: log_height out of range");

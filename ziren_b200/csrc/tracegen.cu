@@ -1,4 +1,4 @@
-// K6: event -> row kernels for the core ALU chips.  One thread fills one row into a shared-memory
+// K6: event -> row kernels for the core ALU and control-flow chips (seven-word event records).  One thread fills one row into a shared-memory
 // tile (row stride odd, so that the column-wise read-back is conflict-free); the CTA then stores
 // the tile with fully coalesced writes in either layout: its 128 rows are one contiguous block of
 // the row-major matrix, and 128 consecutive elements of every column of the column-major one.
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(TG_ROWS) alu_rows_kernel(const u32* __restrict
   for (u32 i = threadIdx.x; i < ev_words; i += TG_ROWS) ev_s[i] = events[row0 * 7 + i];
   __syncthreads();
   u32* r = tile + threadIdx.x * WP;
-  if (row0 + threadIdx.x < n) fill_alu_row(CHIP, alu_event_from_words(ev_s + 7 * threadIdx.x), r, d_inv255);
+  if (row0 + threadIdx.x < n) fill_alu_row(CHIP, ev_s + 7 * threadIdx.x, r, d_inv255);
   else fill_alu_padding(CHIP, r);
   __syncthreads();
   const size_t rows = height - row0 < TG_ROWS ? height - row0 : TG_ROWS;
@@ -58,13 +58,15 @@ void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* ou
     case ALU_SLL: alu_rows_kernel<ALU_SLL><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     case ALU_SR: alu_rows_kernel<ALU_SR><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     case ALU_CLOCLZ: alu_rows_kernel<ALU_CLOCLZ><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_BRANCH: alu_rows_kernel<ALU_BRANCH><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_JUMP: alu_rows_kernel<ALU_JUMP><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     default: throw std::runtime_error("zkb200: alu_trace: unknown chip");
   }
   ZKB_CHECK_LAUNCH();
 }
 
 int alu_chip_by_name(const char* name) {
-  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz"};
+  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump"};
   for (int i = 0; i < ALU_NCHIPS; i++) if (!strcmp(name, names[i])) return i;
   return -1;
 }

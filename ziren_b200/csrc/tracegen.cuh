@@ -11,13 +11,16 @@
 
 namespace zkb {
 
-enum AluChip : int { ALU_ADDSUB = 0, ALU_BITWISE = 1, ALU_LT = 2, ALU_SLL = 3, ALU_SR = 4, ALU_CLOCLZ = 5, ALU_NCHIPS = 6 };
+enum AluChip : int { ALU_ADDSUB = 0, ALU_BITWISE = 1, ALU_LT = 2, ALU_SLL = 3, ALU_SR = 4, ALU_CLOCLZ = 5, ALU_BRANCH = 6, ALU_JUMP = 7,
+                     ALU_NCHIPS = 8 };
 // opcodes as numbered by crates/core/executor/src/opcode.rs:25-49 (#[repr(u8)])
 enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_ROR = 12, OP_SLT = 13, OP_SLTU = 14,
-             OP_AND = 15, OP_OR = 16, OP_XOR = 17, OP_NOR = 18, OP_CLZ = 19, OP_CLO = 20 };
+             OP_AND = 15, OP_OR = 16, OP_XOR = 17, OP_NOR = 18, OP_CLZ = 19, OP_CLO = 20, OP_BEQ = 21, OP_BGEZ = 22, OP_BGTZ = 23,
+             OP_BLEZ = 24, OP_BLTZ = 25, OP_BNE = 26, OP_JUMP = 27, OP_JUMPI = 28, OP_JUMPDIRECT = 29 };
 
 KB_HD constexpr int alu_width(int chip) {
-  return chip == ALU_ADDSUB ? 19 : chip == ALU_BITWISE ? 18 : chip == ALU_LT ? 32 : chip == ALU_SLL ? 44 : chip == ALU_SR ? 67 : 17;
+  return chip == ALU_ADDSUB ? 19 : chip == ALU_BITWISE ? 18 : chip == ALU_LT ? 32 : chip == ALU_SLL ? 44 : chip == ALU_SR ? 67
+       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : 66;
 }
 
 // AluEvent as laid out by #[repr(C)]: seven 32-bit words, the opcode in the low byte of word 2
@@ -162,6 +165,58 @@ KB_HD void fill_clo_clz(const AluEv& e, u32* r) {
   r[14] = tg_b(bb == 0); r[15] = tg_b(clz); r[16] = KB_ONE;
 }
 
+// BranchEvent / JumpEvent (crates/core/executor/src/events/instr.rs:160-217, #[repr(C)]): seven words
+// {pc, next_pc, next_next_pc, opcode, a, b, c}
+struct FlowEv { u32 pc, next_pc, next_next_pc, opcode, a, b, c; };
+KB_HD FlowEv flow_event_from_words(const u32* w) {
+  FlowEv e;
+  e.pc = w[0]; e.next_pc = w[1]; e.next_next_pc = w[2]; e.opcode = w[3] & 0xffu; e.a = w[4]; e.b = w[5]; e.c = w[6];
+  return e;
+}
+// KoalaBearWordRangeChecker::populate, crates/core/machine/src/operations/koala_bear_word.rs:35-49: the bits
+// of the most significant byte and the running conjunction of its low 2..7 bits (14 columns)
+KB_HD void tg_range_checker(u32* r, u32 v) {
+  const u32 top = v >> 24;
+  tg_bits(r, 8, top);
+  for (u32 j = 2; j <= 7; j++) r[6 + j] = tg_b((top & ((1u << j) - 1u)) == (1u << j) - 1u);
+}
+// BranchChip::event_to_row, crates/core/machine/src/control_flow/branch/trace.rs:94-137.  Columns
+// (columns.rs): pc, next_pc[4], next_pc_range_checker[14], target_pc[4], next_next_pc[4],
+// next_next_pc_range_checker[14], op_a_value[4], op_b_value[4], op_c_value[4], is_beq, is_bne, is_bltz,
+// is_blez, is_bgtz, is_bgez, is_branching, a_gt_b, a_lt_b.
+KB_HD void fill_branch(const FlowEv& e, u32* r) {
+  r[0] = tg_f(e.pc);
+  tg_word(r + 1, e.next_pc);
+  tg_range_checker(r + 5, e.next_pc);
+  tg_word(r + 19, e.next_pc + e.c);
+  tg_word(r + 23, e.next_next_pc);
+  tg_range_checker(r + 27, e.next_next_pc);
+  tg_word(r + 41, e.a); tg_word(r + 45, e.b); tg_word(r + 49, e.c);
+  const u32 op = e.opcode;
+  r[53] = tg_b(op == OP_BEQ); r[54] = tg_b(op == OP_BNE); r[55] = tg_b(op == OP_BLTZ);
+  r[56] = tg_b(op == OP_BLEZ); r[57] = tg_b(op == OP_BGTZ); r[58] = tg_b(op == OP_BGEZ);
+  const bool eq = e.a == e.b, lt = (int32_t)e.a < (int32_t)e.b, gt = (int32_t)e.a > (int32_t)e.b;
+  // taken when the relation the opcode names holds between a and b
+  const bool want_eq = op == OP_BEQ || op == OP_BLEZ || op == OP_BGEZ;
+  const bool want_lt = op == OP_BLTZ || op == OP_BLEZ || op == OP_BNE;
+  const bool want_gt = op == OP_BGTZ || op == OP_BGEZ || op == OP_BNE;
+  r[59] = tg_b((want_eq && eq) || (want_lt && lt) || (want_gt && gt));
+  r[60] = tg_b(gt); r[61] = tg_b(lt);
+}
+// JumpChip::event_to_row, crates/core/machine/src/control_flow/jump/trace.rs:94-113.  Columns: pc, next_pc[4],
+// next_pc_range_checker[14], next_next_pc[4], next_next_pc_range_checker[14], op_a_value[4], op_b_value[4],
+// op_c_value[4], is_jump, is_jumpi, is_jumpdirect, op_a_range_checker[14].
+KB_HD void fill_jump(const FlowEv& e, u32* r) {
+  r[0] = tg_f(e.pc);
+  tg_word(r + 1, e.next_pc);
+  tg_range_checker(r + 5, e.next_pc);
+  tg_word(r + 19, e.next_next_pc);
+  tg_range_checker(r + 23, e.next_next_pc);
+  tg_word(r + 37, e.a); tg_word(r + 41, e.b); tg_word(r + 45, e.c);
+  r[49] = tg_b(e.opcode == OP_JUMP); r[50] = tg_b(e.opcode == OP_JUMPI); r[51] = tg_b(e.opcode == OP_JUMPDIRECT);
+  tg_range_checker(r + 52, e.a);
+}
+
 // Rows past the last event (generate_trace of each chip): zeros, except the dummy rows that keep the
 // shift and count-leading chips' constraints satisfied (sll/mod.rs:160-173, sr/mod.rs:184-187,
 // clo_clz/mod.rs:150-163).
@@ -173,14 +228,17 @@ KB_HD void fill_alu_padding(int chip, u32* r) {
   if (chip == ALU_CLOCLZ) { tg_word(r + 2, 32); r[14] = KB_ONE; }
 }
 
-KB_HD void fill_alu_row(int chip, const AluEv& e, u32* r, const u32* inv255) {
+// w: the event's seven words as they lie in the record's event vector
+KB_HD void fill_alu_row(int chip, const u32* w, u32* r, const u32* inv255) {
   switch (chip) {
-    case ALU_ADDSUB: fill_add_sub(e, r); break;
-    case ALU_BITWISE: fill_bitwise(e, r); break;
-    case ALU_LT: fill_lt(e, r, inv255); break;
-    case ALU_SLL: fill_shift_left(e, r); break;
-    case ALU_SR: fill_shift_right(e, r); break;
-    default: fill_clo_clz(e, r); break;
+    case ALU_ADDSUB: fill_add_sub(alu_event_from_words(w), r); break;
+    case ALU_BITWISE: fill_bitwise(alu_event_from_words(w), r); break;
+    case ALU_LT: fill_lt(alu_event_from_words(w), r, inv255); break;
+    case ALU_SLL: fill_shift_left(alu_event_from_words(w), r); break;
+    case ALU_SR: fill_shift_right(alu_event_from_words(w), r); break;
+    case ALU_CLOCLZ: fill_clo_clz(alu_event_from_words(w), r); break;
+    case ALU_BRANCH: fill_branch(flow_event_from_words(w), r); break;
+    default: fill_jump(flow_event_from_words(w), r); break;
   }
 }
 

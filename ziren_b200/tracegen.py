@@ -1,4 +1,4 @@
-"""Host side of GPU trace generation for the core ALU chips: the chip
+"""Host side of GPU trace generation for the core ALU and control-flow chips: the chip
 table, the `AluEvent` record layout and the padded height rule, mirroring what the Rust host keeps
 when it hands a record's event vectors to `zkb200_generate_alu_trace` (include/zkb200.h).
 
@@ -13,7 +13,8 @@ from . import field as kb
 
 # MachineAir::name -> (NUM_*_COLS, opcodes the chip receives, crates/core/executor/src/opcode.rs:25-49)
 OPCODES = {"ADD": 0, "SUB": 1, "SLL": 9, "SRL": 10, "SRA": 11, "ROR": 12, "SLT": 13, "SLTU": 14, "AND": 15, "OR": 16,
-           "XOR": 17, "NOR": 18, "CLZ": 19, "CLO": 20}
+           "XOR": 17, "NOR": 18, "CLZ": 19, "CLO": 20, "BEQ": 21, "BGEZ": 22, "BGTZ": 23, "BLEZ": 24, "BLTZ": 25, "BNE": 26,
+           "Jump": 27, "Jumpi": 28, "JumpDirect": 29}
 ALU_CHIPS = {
     "AddSub": (19, ("ADD", "SUB")),
     "Bitwise": (18, ("AND", "OR", "XOR", "NOR")),
@@ -21,8 +22,13 @@ ALU_CHIPS = {
     "ShiftLeft": (44, ("SLL",)),
     "ShiftRight": (67, ("SRL", "SRA", "ROR")),
     "CloClz": (17, ("CLZ", "CLO")),
+    # control flow: BranchEvent / JumpEvent records {pc, next_pc, next_next_pc, opcode, a, b, c}
+    # (crates/core/executor/src/events/instr.rs:160-217), chips crates/core/machine/src/control_flow/
+    "Branch": (62, ("BEQ", "BNE", "BLTZ", "BLEZ", "BGTZ", "BGEZ")),
+    "Jump": (66, ("Jump", "Jumpi", "JumpDirect")),
 }
-EVENT_WORDS = 7          # pc, next_pc, opcode, hi, a, b, c
+FLOW_CHIPS = ("Branch", "Jump")
+EVENT_WORDS = 7          # AluEvent: pc, next_pc, opcode, hi, a, b, c;  Branch/JumpEvent: pc, next_pc, next_next_pc, opcode, a, b, c
 EVENT_BYTES = 28
 
 
@@ -74,10 +80,44 @@ EDGE_OPERANDS = np.array([0, 1, 7, 8, 9, 31, 32, 33, 0x7F, 0x80, 0xFF, 0x100, 0x
                           0xFFFFFF, 0x1000000, 0x7FFFFFFF, 0x80000000, 0x80000001, 0xFFFFFFFE, 0xFFFFFFFF], dtype=np.uint32)
 
 
+def _flow_events(chip: str, n: int, rng, edges: bool) -> np.ndarray:
+    """Well-formed BranchEvent / JumpEvent records: next_next_pc is where the delay-slot semantics of the
+    executor lands (branch target next_pc + c when taken, else next_pc + 4; jump target in b)."""
+    ev = np.zeros((n, EVENT_WORDS), np.uint32)
+    ev[:, 0] = rng.integers(0, kb.P - 16, n) & ~np.uint32(3)
+    ev[:, 1] = ev[:, 0] + 4
+    op = rng.choice([OPCODES[o] for o in ALU_CHIPS[chip][1]], n).astype(np.uint32)
+    ev[:, 3] = op
+    a = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    c = (rng.integers(-(1 << 17), 1 << 17, n) * 4).astype(np.int64).astype(np.uint32)
+    if edges:
+        m = len(EDGE_OPERANDS)
+        k = min(n, m * m)
+        idx = np.arange(k)
+        a[:k], b[:k] = EDGE_OPERANDS[idx // m], EDGE_OPERANDS[idx % m]
+        lo, hi = k, min(n, k + 256)
+        b[lo:hi] = a[lo:hi]
+    if chip == "Branch":
+        sa, sb = a.astype(np.int32), b.astype(np.int32)
+        eq, lt, gt = a == b, sa < sb, sa > sb
+        taken = np.select([op == OPCODES["BEQ"], op == OPCODES["BNE"], op == OPCODES["BLTZ"], op == OPCODES["BLEZ"],
+                           op == OPCODES["BGTZ"], op == OPCODES["BGEZ"]], [eq, ~eq, lt, lt | eq, gt, eq | gt])
+        ev[:, 2] = np.where(taken, ev[:, 1] + c, ev[:, 1] + 4)
+    else:
+        a = (ev[:, 1] + 4).astype(np.uint32)          # link register value
+        b = (rng.integers(0, kb.P, n) & ~np.uint32(3)).astype(np.uint32)
+        ev[:, 2] = b
+    ev[:, 4], ev[:, 5], ev[:, 6] = a, b, c
+    return ev
+
+
 def synthetic_events(chip: str, n: int, seed: int = 0, edges: bool = True) -> np.ndarray:
     """n well-formed events of the chip as (n, 7) uint32 words: seeded uniform operands, the first rows
     replaced by every pair of edge operands (byte boundaries, sign bits, equal and near-equal words)."""
     rng = np.random.default_rng(0xA1E00 + seed)
+    if chip in FLOW_CHIPS:
+        return _flow_events(chip, n, rng, edges)
     ev = np.zeros((n, EVENT_WORDS), np.uint32)
     ev[:, 0] = rng.integers(0, kb.P, n) & ~np.uint32(3)
     ev[:, 1] = ev[:, 0] + 4
