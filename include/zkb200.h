@@ -140,14 +140,16 @@ int zkb200_grind(zkb200_ctx* ctx, const uint32_t challenger[34], unsigned bits, 
 /* ---- trace generation ---------------------------------------------
  * MachineAir::generate_trace of the core ALU chips AddSub, Bitwise, Lt, ShiftLeft, ShiftRight, CloClz
  * (crates/core/machine/src/alu/{add_sub,bitwise,lt,sll,sr,clo_clz}/mod.rs) and of the control-flow
- * chips Branch and Jump (crates/core/machine/src/control_flow/{branch,jump}/trace.rs); the reference's
+ * chips Branch and Jump (crates/core/machine/src/control_flow/{branch,jump}/trace.rs) and of MovCond
+ * (crates/core/machine/src/misc/mov_cond/mod.rs); the reference's
  * own C++ twins are crates/core/machine/include/*.hpp behind cpp/extern.cpp:15-90.  One event per row
  * in event order, then the chip's padding rows up to 2^log_height (next_power_of_two /
  * fixed_log2_rows, crates/core/machine/src/utils/mod.rs:101-125, is the caller's choice).
  * `events` is the record's event vector as it lies in memory, host or device: 28-byte #[repr(C)]
  * records, `AluEvent` {pc, next_pc, opcode, hi, a, b, c} for the ALU chips and `BranchEvent` /
- * `JumpEvent` {pc, next_pc, next_next_pc, opcode, a, b, c} for Branch / Jump
- * (crates/core/executor/src/events/instr.rs:11-26, :160-217).  `out` is DEVICE memory of
+ * `JumpEvent` {pc, next_pc, next_next_pc, opcode, a, b, c} for Branch / Jump, `MovCondEvent`
+ * {pc, next_pc, opcode, a, b, c, prev_a} for MovCond
+ * (crates/core/executor/src/events/instr.rs:11-26, :160-217, :287-302).  `out` is DEVICE memory of
  * 2^log_height x width words, Montgomery, row-major (col_major = 0: the RowMajorMatrix layout
  * zkb200_commit takes) or column-major (col_major = 1: the layout of the kernel-level entry points). */
 typedef struct {
@@ -162,7 +164,7 @@ typedef struct {
 } zkb200_flow_event;     /* BranchEvent / JumpEvent */
 /* NUM_*_COLS of the chip, -1 if this library has no row filler for it */
 int zkb200_alu_trace_width(const char* chip);
-/* events: zkb200_alu_event[] or, for "Branch" / "Jump", zkb200_flow_event[] */
+/* events: zkb200_alu_event[]; zkb200_flow_event[] for "Branch" / "Jump"; seven-word MovCondEvent records for "MovCond" */
 int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* events, size_t n_events,
                               unsigned log_height, uint32_t* out, int col_major);
 /* layout helpers on the context stream: row-major <-> column-major, canonical <-> Montgomery */

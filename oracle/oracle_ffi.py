@@ -60,7 +60,7 @@ def ref_core_lib():
     return l
 
 
-ALU_CHIPS = ("AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump")
+ALU_CHIPS = ("AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond")
 
 
 def alu_width(chip):

@@ -14,13 +14,14 @@
 #include "clo_clz.hpp"
 #include "branch.hpp"
 #include "jump.hpp"
+#include "mov_cond.hpp"
 
 using namespace zkm_core_machine_sys;
 
 template <class Cols> static constexpr size_t ncols() { return sizeof(Cols) / sizeof(kb31_t); }
 
 extern "C" {
-// chip: 0 AddSub, 1 Bitwise, 2 Lt, 3 ShiftLeft, 4 ShiftRight, 5 CloClz, 6 Branch, 7 Jump
+// chip: 0 AddSub, 1 Bitwise, 2 Lt, 3 ShiftLeft, 4 ShiftRight, 5 CloClz, 6 Branch, 7 Jump, 8 MovCond
 unsigned ref_alu_num_cols(int chip) {
   switch (chip) {
     case 0: return ncols<AddSubCols<kb31_t>>();
@@ -31,11 +32,13 @@ unsigned ref_alu_num_cols(int chip) {
     case 5: return ncols<CloClzCols<kb31_t>>();
     case 6: return ncols<BranchColumns<kb31_t>>();
     case 7: return ncols<JumpColumns<kb31_t>>();
+    case 8: return ncols<MovCondCols<kb31_t>>();
   }
   return 0;
 }
 // events: n records of 7 words, AluEvent {pc, next_pc, opcode, hi, a, b, c} for chips 0-5,
-// BranchEvent / JumpEvent {pc, next_pc, next_next_pc, opcode, a, b, c} for chips 6-7; rows: n x num_cols, zero-initialised here,
+// BranchEvent / JumpEvent {pc, next_pc, next_next_pc, opcode, a, b, c} for chips 6-7,
+// MovCondEvent {pc, next_pc, opcode, a, b, c, prev_a} for chip 8; rows: n x num_cols, zero-initialised here,
 // Montgomery words exactly as the reference leaves them in the trace
 int ref_alu_event_to_rows(int chip, const uint32_t* ev, size_t n, uint32_t* rows) {
   const unsigned w = ref_alu_num_cols(chip);
@@ -48,6 +51,7 @@ int ref_alu_event_to_rows(int chip, const uint32_t* ev, size_t n, uint32_t* rows
     uint32_t* r = rows + i * w;
     BranchEvent be{ev[7 * i], ev[7 * i + 1], ev[7 * i + 2], (Opcode)ev[7 * i + 3], ev[7 * i + 4], ev[7 * i + 5], ev[7 * i + 6]};
     JumpEvent je{be.pc, be.next_pc, be.next_next_pc, be.opcode, be.a, be.b, be.c};
+    MovCondEvent me{ev[7 * i], ev[7 * i + 1], (Opcode)ev[7 * i + 2], ev[7 * i + 3], ev[7 * i + 4], ev[7 * i + 5], ev[7 * i + 6]};
     switch (chip) {
       case 0: add_sub::event_to_row<kb31_t>(e, *reinterpret_cast<AddSubCols<kb31_t>*>(r)); break;
       case 1: bitwise::event_to_row<kb31_t>(e, *reinterpret_cast<BitwiseCols<kb31_t>*>(r)); break;
@@ -57,6 +61,7 @@ int ref_alu_event_to_rows(int chip, const uint32_t* ev, size_t n, uint32_t* rows
       case 5: clo_clz::event_to_row<kb31_t>(e, *reinterpret_cast<CloClzCols<kb31_t>*>(r)); break;
       case 6: branch::event_to_row<kb31_t>(be, *reinterpret_cast<BranchColumns<kb31_t>*>(r)); break;
       case 7: jump::event_to_row<kb31_t>(je, *reinterpret_cast<JumpColumns<kb31_t>*>(r)); break;
+      case 8: mov_cond::event_to_row<kb31_t>(me, *reinterpret_cast<MovCondCols<kb31_t>*>(r)); break;
     }
   }
   return 0;

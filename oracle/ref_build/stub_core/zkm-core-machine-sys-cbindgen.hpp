@@ -2,7 +2,7 @@
 // (crates/core/machine/build.rs:94-180); that build cannot run here (no Rust toolchain).  It
 // declares, with the field order of the Rust #[repr(C)] definitions cited below, the layout types
 // the reference's ALU and control-flow row fillers (crates/core/machine/include/{add_sub,bitwise,lt,
-// shift_left,shift_right,clo_clz,branch,jump}.hpp) name, plus the names utils.hpp mentions in signatures.  This file is
+// shift_left,shift_right,clo_clz,branch,jump,mov_cond}.hpp) name, plus the names utils.hpp mentions in signatures.  This file is
 // ours; the reference's headers are compiled from where they lie under /root/reference.
 #pragma once
 #include <cstddef>
@@ -40,6 +40,8 @@ struct AluEvent {
 // crates/core/executor/src/events/instr.rs:160-217 (#[repr(C)])
 struct BranchEvent { uint32_t pc, next_pc, next_next_pc; Opcode opcode; uint32_t a, b, c; };
 struct JumpEvent { uint32_t pc, next_pc, next_next_pc; Opcode opcode; uint32_t a, b, c; };
+// crates/core/executor/src/events/instr.rs:287-302 (#[repr(C)])
+struct MovCondEvent { uint32_t pc, next_pc; Opcode opcode; uint32_t a, b, c, prev_a; };
 
 template <class T> struct Word { T _0[WORD_SIZE]; };   // crates/stark/src/word.rs:21
 
@@ -137,6 +139,14 @@ template <class T> struct JumpColumns {
   Word<T> op_a_value, op_b_value, op_c_value;
   T is_jump, is_jumpi, is_jumpdirect;
   KoalaBearWordRangeChecker<T> op_a_range_checker;
+};
+
+// crates/core/machine/src/misc/mov_cond/mod.rs:36-65 (MovCondCols)
+template <class T> struct MovCondCols {
+  T pc, next_pc;
+  Word<T> op_a_value, prev_a_value, op_b_value, op_c_value;
+  IsZeroWordOperation<T> c_eq_0;
+  T is_mne, is_meq, is_wsbh;
 };
 
 }  // namespace zkm_core_machine_sys

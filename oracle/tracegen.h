@@ -10,6 +10,7 @@
 //   CloClz     crates/core/machine/src/alu/clo_clz/mod.rs:100-166
 //   Branch     crates/core/machine/src/control_flow/branch/trace.rs:45-137 (columns.rs)
 //   Jump       crates/core/machine/src/control_flow/jump/trace.rs:45-113 (columns.rs)
+//   MovCond    crates/core/machine/src/misc/mov_cond/mod.rs:91-165; operations/is_zero_word.rs, is_zero.rs
 //   range checker  crates/core/machine/src/operations/koala_bear_word.rs:35-49
 // Pinned against the reference's own C++ row fillers (crates/core/machine/include/*.hpp compiled
 // into oracle/_ref/libzkref_core.so) and the golden rows generated from them
@@ -25,11 +26,11 @@ namespace zko {
 struct AluEvent { u32 pc, next_pc, opcode, hi, a, b, c; };
 // the same seven words read as BranchEvent / JumpEvent {pc, next_pc, next_next_pc, opcode, a, b, c}
 struct FlowEvent { u32 pc, next_pc, next_next_pc, opcode, a, b, c; };
-enum { T_ADDSUB = 0, T_BITWISE, T_LT, T_SLL, T_SR, T_CLOCLZ, T_BRANCH, T_JUMP, T_NCHIPS };
-static const int ALU_WIDTHS[T_NCHIPS] = {19, 18, 32, 44, 67, 17, 62, 66};
+enum { T_ADDSUB = 0, T_BITWISE, T_LT, T_SLL, T_SR, T_CLOCLZ, T_BRANCH, T_JUMP, T_MOVCOND, T_NCHIPS };
+static const int ALU_WIDTHS[T_NCHIPS] = {19, 18, 32, 44, 67, 17, 62, 66, 32};
 enum { K_ADD = 0, K_SUB = 1, K_SLL = 9, K_SRL = 10, K_SRA = 11, K_ROR = 12, K_SLT = 13, K_SLTU = 14, K_AND = 15, K_OR = 16,
        K_XOR = 17, K_NOR = 18, K_CLZ = 19, K_CLO = 20, K_BEQ = 21, K_BGEZ = 22, K_BGTZ = 23, K_BLEZ = 24, K_BLTZ = 25, K_BNE = 26,
-       K_JUMP = 27, K_JUMPI = 28, K_JUMPDIRECT = 29 };
+       K_JUMP = 27, K_JUMPI = 28, K_JUMPDIRECT = 29, K_MEQ = 50, K_MNE = 51, K_WSBH = 52 };
 
 struct RowWriter {
   u32* r;
@@ -182,6 +183,24 @@ static inline void alu_row(int chip, const AluEvent& e, u32* row) {
   if (w.at != ALU_WIDTHS[chip]) throw std::runtime_error("oracle: ALU row width mismatch");
 }
 
+// the seven words read as MovCondEvent {pc, next_pc, opcode, a, b, c, prev_a}
+static inline void mov_cond_row(const u32* e, u32* row) {
+  RowWriter w{row};
+  const u32 opcode = e[2] & 0xff, a = e[3], b = e[4], c = e[5], prev_a = e[6];
+  w.put(e[0]); w.put(e[1]);
+  w.word(a); w.word(prev_a); w.word(b); w.word(c);
+  bool zero[4];
+  for (int i = 0; i < 4; i++) {          // IsZeroOperation per byte: inverse (0 for a zero byte), result
+    const u32 byte = (c >> (8 * i)) & 0xff;
+    zero[i] = byte == 0;
+    w.put(zero[i] ? 0 : finv(F(byte)).v);
+    w.flag(zero[i]);
+  }
+  w.flag(zero[0] && zero[1]); w.flag(zero[2] && zero[3]); w.flag(zero[0] && zero[1] && zero[2] && zero[3]);
+  w.flag(opcode == K_MNE); w.flag(opcode == K_MEQ); w.flag(opcode == K_WSBH);
+  if (w.at != ALU_WIDTHS[T_MOVCOND]) throw std::runtime_error("oracle: MovCond row width mismatch");
+}
+
 static inline void alu_padding_row(int chip, u32* row) {
   const int w = ALU_WIDTHS[chip];
   for (int i = 0; i < w; i++) row[i] = 0;
@@ -197,7 +216,10 @@ static inline void alu_trace(int chip, const AluEvent* ev, size_t n, size_t heig
   const int w = ALU_WIDTHS[chip];
   for (size_t i = 0; i < height; i++) {
     if (i >= n) alu_padding_row(chip, out + i * w);
-    else if (chip == T_BRANCH || chip == T_JUMP)
+    else if (chip == T_MOVCOND) {
+      const u32 words[7] = {ev[i].pc, ev[i].next_pc, ev[i].opcode, ev[i].hi, ev[i].a, ev[i].b, ev[i].c};
+      mov_cond_row(words, out + i * w);
+    } else if (chip == T_BRANCH || chip == T_JUMP)
       flow_row(chip, FlowEvent{ev[i].pc, ev[i].next_pc, ev[i].opcode, ev[i].hi, ev[i].a, ev[i].b, ev[i].c}, out + i * w);
     else alu_row(chip, ev[i], out + i * w);
   }

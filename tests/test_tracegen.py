@@ -82,7 +82,7 @@ def test_padded_height_rule():
 def test_synthetic_events_are_well_formed():
     for chip in CHIPS:
         ev = tg.synthetic_events(chip, 2000, seed=5)
-        opcode_word = 3 if chip in tg.FLOW_CHIPS else 2          # BranchEvent / JumpEvent vs AluEvent
+        opcode_word = 3 if chip in tg.FLOW_CHIPS else 2          # BranchEvent / JumpEvent vs AluEvent / MovCondEvent
         assert set(np.unique(ev[:, opcode_word]).tolist()) <= {tg.OPCODES[o] for o in tg.ALU_CHIPS[chip][1]}
         assert (ev[:, 0] < kb.P).all() and np.array_equal(ev[:, 1], ev[:, 0] + 4)
     ev = tg.synthetic_events("AddSub", 2000, seed=5)

@@ -12,15 +12,15 @@
 namespace zkb {
 
 enum AluChip : int { ALU_ADDSUB = 0, ALU_BITWISE = 1, ALU_LT = 2, ALU_SLL = 3, ALU_SR = 4, ALU_CLOCLZ = 5, ALU_BRANCH = 6, ALU_JUMP = 7,
-                     ALU_NCHIPS = 8 };
+                     ALU_MOVCOND = 8, ALU_NCHIPS = 9 };
 // opcodes as numbered by crates/core/executor/src/opcode.rs:25-49 (#[repr(u8)])
 enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_ROR = 12, OP_SLT = 13, OP_SLTU = 14,
              OP_AND = 15, OP_OR = 16, OP_XOR = 17, OP_NOR = 18, OP_CLZ = 19, OP_CLO = 20, OP_BEQ = 21, OP_BGEZ = 22, OP_BGTZ = 23,
-             OP_BLEZ = 24, OP_BLTZ = 25, OP_BNE = 26, OP_JUMP = 27, OP_JUMPI = 28, OP_JUMPDIRECT = 29 };
+             OP_BLEZ = 24, OP_BLTZ = 25, OP_BNE = 26, OP_JUMP = 27, OP_JUMPI = 28, OP_JUMPDIRECT = 29, OP_MEQ = 50, OP_MNE = 51, OP_WSBH = 52 };
 
 KB_HD constexpr int alu_width(int chip) {
   return chip == ALU_ADDSUB ? 19 : chip == ALU_BITWISE ? 18 : chip == ALU_LT ? 32 : chip == ALU_SLL ? 44 : chip == ALU_SR ? 67
-       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : 66;
+       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : 32;
 }
 
 // AluEvent as laid out by #[repr(C)]: seven 32-bit words, the opcode in the low byte of word 2
@@ -217,6 +217,24 @@ KB_HD void fill_jump(const FlowEv& e, u32* r) {
   tg_range_checker(r + 52, e.a);
 }
 
+// MovCondChip::event_to_row, crates/core/machine/src/misc/mov_cond/mod.rs:140-165; MovCondEvent
+// (crates/core/executor/src/events/instr.rs:287-302) is {pc, next_pc, opcode, a, b, c, prev_a}.  Columns: pc,
+// next_pc, op_a_value[4], prev_a_value[4], op_b_value[4], op_c_value[4], c_eq_0 = IsZeroWordOperation
+// {is_zero_byte[4]{inverse, result}, is_lower_half_zero, is_upper_half_zero, result}
+// (operations/is_zero_word.rs, is_zero.rs), is_mne, is_meq, is_wsbh.
+KB_HD void fill_mov_cond(const u32* w, u32* r, const u32* inv255) {
+  const u32 pc = w[0], next_pc = w[1], op = w[2] & 0xffu, a = w[3], b = w[4], c = w[5], prev_a = w[6];
+  r[0] = tg_f(pc); r[1] = tg_f(next_pc);
+  tg_word(r + 2, a); tg_word(r + 6, prev_a); tg_word(r + 10, b); tg_word(r + 14, c);
+  for (int i = 0; i < 4; i++) {
+    const u32 byte = (c >> (8 * i)) & 0xffu;
+    r[18 + 2 * i] = inv255[byte];            // entry 0 of the table is 0
+    r[19 + 2 * i] = tg_b(byte == 0);
+  }
+  r[26] = tg_b((c & 0xffffu) == 0); r[27] = tg_b((c >> 16) == 0); r[28] = tg_b(c == 0);
+  r[29] = tg_b(op == OP_MNE); r[30] = tg_b(op == OP_MEQ); r[31] = tg_b(op == OP_WSBH);
+}
+
 // Rows past the last event (generate_trace of each chip): zeros, except the dummy rows that keep the
 // shift and count-leading chips' constraints satisfied (sll/mod.rs:160-173, sr/mod.rs:184-187,
 // clo_clz/mod.rs:150-163).
@@ -238,7 +256,8 @@ KB_HD void fill_alu_row(int chip, const u32* w, u32* r, const u32* inv255) {
     case ALU_SR: fill_shift_right(alu_event_from_words(w), r); break;
     case ALU_CLOCLZ: fill_clo_clz(alu_event_from_words(w), r); break;
     case ALU_BRANCH: fill_branch(flow_event_from_words(w), r); break;
-    default: fill_jump(flow_event_from_words(w), r); break;
+    case ALU_JUMP: fill_jump(flow_event_from_words(w), r); break;
+    default: fill_mov_cond(w, r, inv255); break;
   }
 }
 

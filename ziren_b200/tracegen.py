@@ -14,7 +14,7 @@ from . import field as kb
 # MachineAir::name -> (NUM_*_COLS, opcodes the chip receives, crates/core/executor/src/opcode.rs:25-49)
 OPCODES = {"ADD": 0, "SUB": 1, "SLL": 9, "SRL": 10, "SRA": 11, "ROR": 12, "SLT": 13, "SLTU": 14, "AND": 15, "OR": 16,
            "XOR": 17, "NOR": 18, "CLZ": 19, "CLO": 20, "BEQ": 21, "BGEZ": 22, "BGTZ": 23, "BLEZ": 24, "BLTZ": 25, "BNE": 26,
-           "Jump": 27, "Jumpi": 28, "JumpDirect": 29}
+           "Jump": 27, "Jumpi": 28, "JumpDirect": 29, "MEQ": 50, "MNE": 51, "WSBH": 52}
 ALU_CHIPS = {
     "AddSub": (19, ("ADD", "SUB")),
     "Bitwise": (18, ("AND", "OR", "XOR", "NOR")),
@@ -26,9 +26,12 @@ ALU_CHIPS = {
     # (crates/core/executor/src/events/instr.rs:160-217), chips crates/core/machine/src/control_flow/
     "Branch": (62, ("BEQ", "BNE", "BLTZ", "BLEZ", "BGTZ", "BGEZ")),
     "Jump": (66, ("Jump", "Jumpi", "JumpDirect")),
+    # MovCondEvent {pc, next_pc, opcode, a, b, c, prev_a} (instr.rs:287-302), crates/core/machine/src/misc/mov_cond/
+    "MovCond": (32, ("MEQ", "MNE", "WSBH")),
 }
 FLOW_CHIPS = ("Branch", "Jump")
-EVENT_WORDS = 7          # AluEvent: pc, next_pc, opcode, hi, a, b, c;  Branch/JumpEvent: pc, next_pc, next_next_pc, opcode, a, b, c
+EVENT_WORDS = 7          # AluEvent: pc, next_pc, opcode, hi, a, b, c;  Branch/JumpEvent: pc, next_pc, next_next_pc, opcode, a, b, c;
+                         # MovCondEvent: pc, next_pc, opcode, a, b, c, prev_a
 EVENT_BYTES = 28
 
 
@@ -112,12 +115,37 @@ def _flow_events(chip: str, n: int, rng, edges: bool) -> np.ndarray:
     return ev
 
 
+def _mov_cond_events(n: int, rng, edges: bool) -> np.ndarray:
+    """MovCondEvent records {pc, next_pc, opcode, a, b, c, prev_a}: MEQ / MNE move b into a when c is / is not
+    zero (else a keeps prev_a), WSBH swaps the bytes of each half word of b."""
+    ev = np.zeros((n, EVENT_WORDS), np.uint32)
+    ev[:, 0] = rng.integers(0, kb.P - 16, n) & ~np.uint32(3)
+    ev[:, 1] = ev[:, 0] + 4
+    op = rng.choice([OPCODES[o] for o in ALU_CHIPS["MovCond"][1]], n).astype(np.uint32)
+    b = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    c = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    prev_a = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    # zero bytes in every position of c (the per-byte is-zero columns), whole-zero and half-zero words
+    masks = np.array([0xFFFFFFFF, 0, 0xFFFF0000, 0x0000FFFF, 0xFF00FF00, 0x00FF00FF, 0xFFFFFF00, 0x00FFFFFF, 0xFF000000, 0x000000FF],
+                     dtype=np.uint32)
+    c &= masks[rng.integers(0, len(masks), n)]
+    if edges and n:
+        k = min(n, len(EDGE_OPERANDS))
+        c[:k] = EDGE_OPERANDS[:k]
+    swapped = ((b & np.uint32(0x00FF00FF)) << 8) | ((b >> 8) & np.uint32(0x00FF00FF))
+    a = np.select([op == OPCODES["MEQ"], op == OPCODES["MNE"]], [np.where(c == 0, b, prev_a), np.where(c != 0, b, prev_a)], swapped)
+    ev[:, 2], ev[:, 3], ev[:, 4], ev[:, 5], ev[:, 6] = op, a.astype(np.uint32), b, c, prev_a
+    return ev
+
+
 def synthetic_events(chip: str, n: int, seed: int = 0, edges: bool = True) -> np.ndarray:
     """n well-formed events of the chip as (n, 7) uint32 words: seeded uniform operands, the first rows
     replaced by every pair of edge operands (byte boundaries, sign bits, equal and near-equal words)."""
     rng = np.random.default_rng(0xA1E00 + seed)
     if chip in FLOW_CHIPS:
         return _flow_events(chip, n, rng, edges)
+    if chip == "MovCond":
+        return _mov_cond_events(n, rng, edges)
     ev = np.zeros((n, EVENT_WORDS), np.uint32)
     ev[:, 0] = rng.integers(0, kb.P, n) & ~np.uint32(3)
     ev[:, 1] = ev[:, 0] + 4
