@@ -1,5 +1,6 @@
 #include "open.h"
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 namespace zkb {
@@ -97,6 +98,102 @@ __global__ void __launch_bounds__(EC_THREADS) eval_columns_kernel(const u32* __r
     if (c0 + c < W) partial[(((size_t)blockIdx.y * NPT + p) * W + c0 + c) * 4 + k] = v.v;
   }
 }
+// ---- column evaluation, variant 2 (opt-in: ZKB200_EVAL_V2=1; not yet measured on a B200) --------
+// One LANE per column instead of one thread per row: a warp stages a 32-column x 32-row tile of the
+// matrix in shared memory with coalesced loads (cp.async, double-buffered), then every lane walks ITS
+// column of the tile while the barycentric weights of the row are broadcast from shared memory.  The
+// accumulators of a column live in one thread for the whole row range, so there is no cross-thread
+// reduction, the weights are read once per CTA and step instead of once per four columns, and the
+// kernel needs about 50 registers (the row-parallel kernel above: 128 registers, 12 % occupancy,
+// 830 GB/s on the 2^18 x 4167 matrix; the multiply work alone allows about 2.4x that).
+constexpr int E2_WARPS = 8;      // 8 warps = 256 columns per CTA
+constexpr int E2_ROWS = 32;      // rows per step
+constexpr int E2_LD = 33;        // tile row stride: lane-along-column reads are conflict-free
+
+__device__ __forceinline__ void cp_async_4(u32* smem_dst, const u32* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int NPT>
+__global__ void __launch_bounds__(E2_WARPS * 32, 3) eval_columns_v2_kernel(const u32* __restrict__ lde, size_t H, size_t n, size_t W,
+                                                                           const u32* __restrict__ w0, const u32* __restrict__ w1,
+                                                                           u32* __restrict__ partial, size_t rows_per_split) {
+  extern __shared__ __align__(16) u32 e2_smem[];
+  // [2 buffers][E2_WARPS][32 columns][E2_LD] data words, then [2 buffers][E2_ROWS][8] weight words
+  u32* tiles = e2_smem;
+  u32* wts = e2_smem + 2 * E2_WARPS * 32 * E2_LD;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t c0 = ((size_t)blockIdx.x * E2_WARPS + warp) * 32;     // first column of this warp
+  const size_t col = c0 + lane;
+  const size_t r_begin = (size_t)blockIdx.y * rows_per_split;        // multiples of E2_ROWS (host side)
+  size_t r_end = r_begin + rows_per_split;
+  if (r_end > n) r_end = n;
+  const u32 steps = r_begin < r_end ? (u32)((r_end - r_begin) / E2_ROWS) : 0;
+
+  // stage step `st` into buffer `buf`: lane = row within the step, one 128-byte segment per column
+  auto stage = [&](u32 st, int buf) {
+    const size_t r0 = r_begin + (size_t)st * E2_ROWS;
+    u32* t = tiles + ((size_t)buf * E2_WARPS + warp) * 32 * E2_LD;
+#pragma unroll 8
+    for (int j = 0; j < 32; j++)
+      if (c0 + j < W) cp_async_4(t + j * E2_LD + lane, lde + (c0 + j) * H + r0 + lane);
+    // weights of the step: component k of row rr at wts[buf][rr][k]; threads run along rows (coalesced)
+    if (threadIdx.x < E2_ROWS * NPT * 4) {
+      const int k = threadIdx.x / E2_ROWS, rr = threadIdx.x % E2_ROWS;
+      const u32* src = (k < 4 ? w0 + (size_t)k * n : w1 + (size_t)(k - 4) * n) + r0 + rr;
+      cp_async_4(wts + ((size_t)buf * E2_ROWS + rr) * 8 + k, src);
+    }
+    cp_async_commit();
+  };
+
+  Fp tot[NPT][4];
+  u64 raw[NPT][4];
+#pragma unroll
+  for (int p = 0; p < NPT; p++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) { tot[p][k] = fp_zero(); raw[p][k] = 0; }
+
+  if (steps) stage(0, 0);
+  for (u32 st = 0; st < steps; st++) {
+    const int buf = st & 1;
+    cp_async_wait_all();
+    __syncthreads();                       // step st is in shared memory; buffer buf^1 is free (see below)
+    if (st + 1 < steps) stage(st + 1, buf ^ 1);
+    const u32* t = tiles + ((size_t)buf * E2_WARPS + warp) * 32 * E2_LD + lane * E2_LD;   // this lane's column
+    const u32* wr = wts + (size_t)buf * E2_ROWS * 8;
+#pragma unroll 2
+    for (int r4 = 0; r4 < E2_ROWS; r4 += 4) {
+      // four rows: the four products of a component are summed raw in 64 bits (4 p^2 < 2^64)
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const u32 x = t[r4 + u];
+        const uint4 a = *reinterpret_cast<const uint4*>(wr + (r4 + u) * 8);
+        raw[0][0] += (u64)a.x * x; raw[0][1] += (u64)a.y * x; raw[0][2] += (u64)a.z * x; raw[0][3] += (u64)a.w * x;
+        if (NPT > 1) {
+          const uint4 b = *reinterpret_cast<const uint4*>(wr + (r4 + u) * 8 + 4);
+          raw[NPT - 1][0] += (u64)b.x * x; raw[NPT - 1][1] += (u64)b.y * x;
+          raw[NPT - 1][2] += (u64)b.z * x; raw[NPT - 1][3] += (u64)b.w * x;
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < NPT; p++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) { tot[p][k] = tot[p][k] + fp_raw(mont_reduce_wide(raw[p][k])); raw[p][k] = 0; }
+    }
+    // the next iteration's __syncthreads (after its wait) orders these reads before buffer `buf` is
+    // staged again two steps later
+  }
+  if (col < W) {
+#pragma unroll
+    for (int p = 0; p < NPT; p++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) partial[(((size_t)blockIdx.y * NPT + p) * W + col) * 4 + k] = tot[p][k].v;
+  }
+}
+
 __global__ void sum_partials_kernel(const u32* partial, size_t count, int nsplit, u32* out) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= count) return;
@@ -107,6 +204,38 @@ __global__ void sum_partials_kernel(const u32* partial, size_t count, int nsplit
 void eval_columns(const u32* lde, size_t H, size_t n, size_t W, const u32* w0, const u32* w1, int npoints, u32* out,
                   cudaStream_t s) {
   if (!W) return;
+  static const bool use_v2 = getenv("ZKB200_EVAL_V2") && atoi(getenv("ZKB200_EVAL_V2")) != 0;
+  if (use_v2 && n >= 1024 && W >= 128) {
+    // rows are split in multiples of E2_ROWS so that every CTA runs whole steps; about three CTAs per SM
+    static std::once_flag v2_once;
+    static int v2_sms = 148;
+    const size_t smem = (size_t)(2 * E2_WARPS * 32 * E2_LD + 2 * E2_ROWS * 8) * sizeof(u32);
+    std::call_once(v2_once, [&] {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&v2_sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaFuncSetAttribute(eval_columns_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(eval_columns_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    });
+    const size_t colgroups = (W + E2_WARPS * 32 - 1) / (E2_WARPS * 32);
+    size_t nsplit = ((size_t)3 * v2_sms + colgroups - 1) / colgroups;
+    if (nsplit > n / 256) nsplit = n / 256;
+    if (nsplit < 1) nsplit = 1;
+    size_t rows_per_split = ((n + nsplit - 1) / nsplit + E2_ROWS - 1) / E2_ROWS * E2_ROWS;
+    nsplit = (n + rows_per_split - 1) / rows_per_split;
+    const size_t count = (size_t)npoints * W * 4;
+    DevBuf partial(nsplit > 1 ? nsplit * count : 0, s);
+    u32* dst = nsplit > 1 ? partial.p : out;
+    dim3 grid((unsigned)colgroups, (unsigned)nsplit);
+    if (npoints == 1) eval_columns_v2_kernel<1><<<grid, E2_WARPS * 32, smem, s>>>(lde, H, n, W, w0, w0, dst, rows_per_split);
+    else eval_columns_v2_kernel<2><<<grid, E2_WARPS * 32, smem, s>>>(lde, H, n, W, w0, w1, dst, rows_per_split);
+    ZKB_CHECK_LAUNCH();
+    if (nsplit > 1) {
+      sum_partials_kernel<<<ceil_div(count, 256), 256, 0, s>>>(partial.p, count, (int)nsplit, out);
+      ZKB_CHECK_LAUNCH();
+    }
+    return;
+  }
   const unsigned colblocks = ceil_div(W, EC_COLS);
   // Row splits: enough CTAs to fill the GPU, and for large grids the split count (<= 8) whose last
   // wave is fullest (every CTA does the same work, so a ragged last wave is lost time: the
