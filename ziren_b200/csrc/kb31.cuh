@@ -2,7 +2,8 @@
 // F[x]/(x^4 - 3), for host and device.  The in-memory representation is the one the reference's
 // RowMajorMatrix<KoalaBear> holds (constants cross-checked with
 // crates/core/machine/include/kb31_t.hpp:27-34: MOD 0x7f000001, R mod p 0x1fffffe,
-// R^2 mod p 0x17f7efe4, p^-1 mod 2^32 0x81000001).  EF4 per crates/stark/src/air/extension.rs:55-75.
+// R^2 mod p 0x17f7efe4; the reduction uses -p^-1 mod 2^32 = 0x7effffff, the negative of the
+// header's MONTY_MU 0x81000001).  EF4 per crates/stark/src/air/extension.rs:55-75.
 #pragma once
 #include <cstdint>
 #include <cstddef>
@@ -19,7 +20,6 @@ typedef uint32_t u32;
 typedef uint64_t u64;
 
 constexpr u32 KB_P = 0x7f000001u;
-constexpr u32 KB_PINV = 0x81000001u;   // p^-1 mod 2^32
 constexpr u32 KB_ONE = 0x01fffffeu;    // R mod p
 constexpr u32 KB_R2 = 0x17f7efe4u;     // R^2 mod p
 constexpr u32 KB_GEN = 3;              // multiplicative generator (canonical)
@@ -76,16 +76,6 @@ KB_HD Fp operator+(Fp a, Fp b) {
   u32 s = a.v + b.v;
   u32 t = s - KB_P;
   return fp_raw(t < s ? t : s);  // umin(s, s - p): s - p wraps high when s < p
-}
-// Modular add whose first step is written as min(a + b, big) with big = 0xffffffff read at run
-// time: a no-op mathematically, but it makes the compiler emit the fused add-min (ALU pipe) instead
-// of IMAD.IADD on the FMA-heavy pipe, which Poseidon2 saturates with its multiplies
-// (profiles/README.md, "pipe steering").
-KB_HD Fp fp_add_alu(Fp a, Fp b, u32 big) {
-  u32 s = a.v + b.v;
-  s = s < big ? s : big;
-  u32 t = s - KB_P;
-  return fp_raw(t < s ? t : s);
 }
 KB_HD Fp operator-(Fp a, Fp b) {
   u32 s = a.v - b.v;
