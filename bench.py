@@ -336,7 +336,14 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1):
                     "ms": ms, "algorithmic_bytes": alg,
                     "share_of_step": ms / max(sum(stages.values()), 1e-9)}
     if "k2_merkle" in out:
-        out["k2_merkle"]["poseidon2_Gperm_per_s"] = perms / (stages["commit_main_merkle"] / 1e3) / 1e9
+        rate = perms / (stages["commit_main_merkle"] / 1e3)
+        out["k2_merkle"]["poseidon2_Gperm_per_s"] = rate / 1e9
+        # the bound that does apply: integer issue.  profiles/r01_pipe_probe.jsonl prices a permutation at
+        # about 6200 scheduler cycles per warp (141 cubes at 20.8, the add-only internal rounds at 1.4 cycles
+        # per instruction); 148 SMs x 4 schedulers x 32 lanes at 1965 MHz
+        lanes_hz = 148 * 4 * 32 * 1.965e9
+        out["k2_merkle"]["issue_roofline"] = {"model_cycles_per_permutation": 6200, "achieved_cycles_per_permutation": lanes_hz / rate,
+                                              "frac": 6200 / (lanes_hz / rate), "source": "tools/sweep/pipe_probe.cu, profiles/README.md"}
         out["k2_merkle"]["note"] = "integer-issue bound, not HBM bound: ~4.3k instructions per permutation, IMAD.WIDE/IMAD.HI cost 4-5.5 issue cycles per warp (profiles/r01_pipe_probe.jsonl); see profiles/README.md"
     return out
 
