@@ -120,6 +120,26 @@ def test_generated_traces_satisfy_the_chips_real_constraints(oracle):
         assert not om.verify_shard(p2)[0], (chip, row, col)
 
 
+def test_lt_traces_satisfy_the_restated_lt_constraints(oracle):
+    """LtChip::eval's arithmetic constraints (sign handling, byte flags, inverse hint) over reference-identical rows."""
+    from ziren_b200 import synthetic
+    tr = {k: v[1] for k, v in _alu_traces(oracle, n_add=300, n_sll=100).items()}
+    ev = tg.synthetic_events("Lt", 2000, seed=4)
+    tr["Lt"] = oracle.alu_trace("Lt", ev, 1 << tg.padded_log_height(len(ev)))
+    case = synthetic.alu_case(tr, with_lookup_pair=False)
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    proof, _ = om.prove_shard(case.traces, case.public_values)
+    ok, err = om.verify_shard(proof)
+    assert ok, err
+    row = int(np.flatnonzero(ev[:, 5] != ev[:, 6])[-1])        # a row whose operands differ: every hint column is live
+    for col in (4, 16, 22, 27, 29, 30):
+        bad = {k: v.copy() for k, v in tr.items()}
+        bad["Lt"][row, col] = (int(bad["Lt"][row, col]) + 1) % kb.P
+        p2, _ = om.prove_shard(bad, case.public_values)
+        assert not om.verify_shard(p2)[0], col
+
+
 # ---- GPU -------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def gpu():

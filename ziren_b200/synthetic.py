@@ -414,11 +414,61 @@ def _shift_left_chip() -> Chip:
     return Chip("ShiftLeft", 0, 44, ev, local_only=True)
 
 
+def _lt_chip() -> Chip:
+    """LtChip::eval crates/core/machine/src/alu/lt/mod.rs:288-470 without its byte lookups (b_masked / c_masked
+    AND 0x7f, sltu = LTU of the comparison bytes) and its instruction receive; columns of LtCols."""
+    def ev(b):
+        is_slt, is_sltu = b.main(2), b.main(3)
+        a = [b.main(4 + i) for i in range(4)]
+        bw = [b.main(8 + i) for i in range(4)]
+        cw = [b.main(12 + i) for i in range(4)]
+        flags = [b.main(16 + i) for i in range(4)]
+        b_masked, c_masked, not_eq_inv = b.main(20), b.main(21), b.main(22)
+        msb_b, msb_c, bit_b, bit_c = b.main(23), b.main(24), b.main(25), b.main(26)
+        sltu, is_comp_eq, is_sign_eq = b.main(27), b.main(28), b.main(29)
+        cmp_b, cmp_c = b.main(30), b.main(31)
+        is_real = is_slt + is_sltu
+        b_comp = bw[:3] + [bw[3] * is_sltu + b_masked * is_slt]
+        c_comp = cw[:3] + [cw[3] * is_sltu + c_masked * is_slt]
+        b.assert_eq(bit_b, msb_b * is_slt)
+        b.assert_eq(bit_c, msb_c * is_slt)
+        inv_128 = pow(128, P - 2, P)
+        b.assert_eq(msb_b, (bw[3] - b_masked) * inv_128)
+        b.assert_eq(msb_c, (cw[3] - c_masked) * inv_128)
+        _assert_bool(b, is_sign_eq)
+        b.when(is_sign_eq).assert_eq(bit_b, bit_c)
+        b.when(is_real).when(1 - is_sign_eq).assert_eq(bit_b + bit_c, 1)
+        b.assert_eq(a[0], bit_b * (1 - bit_c) + is_sign_eq * sltu)
+        for i in (1, 2, 3):
+            b.assert_zero(a[i])
+        sum_flags = flags[0] + flags[1] + flags[2] + flags[3]
+        for f in flags:
+            _assert_bool(b, f)
+        _assert_bool(b, sum_flags)
+        b.when(is_real).assert_eq(1 - is_comp_eq, sum_flags)
+        _assert_bool(b, is_comp_eq)
+        visited = None
+        sel_b = sel_c = None
+        for i in (3, 2, 1, 0):
+            visited = flags[i] if visited is None else visited + flags[i]
+            sel_b = b_comp[i] * flags[i] if sel_b is None else sel_b + b_comp[i] * flags[i]
+            sel_c = c_comp[i] * flags[i] if sel_c is None else sel_c + c_comp[i] * flags[i]
+            b.when(1 - visited).assert_eq(b_comp[i], c_comp[i])
+            b.when(is_comp_eq).assert_zero(visited)
+        b.assert_eq(cmp_b, sel_b)
+        b.assert_eq(cmp_c, sel_c)
+        b.when(1 - is_comp_eq).assert_eq(not_eq_inv * (cmp_b - cmp_c), is_real)
+        _assert_bool(b, is_slt)
+        _assert_bool(b, is_sltu)
+        _assert_bool(b, is_real)
+    return Chip("Lt", 0, 32, ev, local_only=True)
+
+
 def alu_case(traces: dict, *, with_lookup_pair: bool = True, **kw) -> ShardCase:
-    """`traces`: {"AddSub": rows, "ShiftLeft": rows} in canonical form, as produced by trace generation.
+    """`traces`: {"AddSub": rows, "ShiftLeft": rows[, "Lt": rows]} in canonical form, as produced by trace generation.
     with_lookup_pair adds the Fibonacci/Sink pair so that the shard also has permutation traces (the two
     ALU chips alone have no lookups here)."""
-    chips = [_add_sub_chip(), _shift_left_chip()]
+    chips = [_add_sub_chip(), _shift_left_chip()] + ([_lt_chip()] if "Lt" in traces else [])
     traces = dict(traces)
     pv = np.zeros(8, dtype=np.uint32)
     if with_lookup_pair:
@@ -436,5 +486,5 @@ def alu_case(traces: dict, *, with_lookup_pair: bool = True, **kw) -> ShardCase:
         traces["Fibonacci"], traces["Sink"] = rows, sink
     machine = Machine(chips, num_pv_elts=4, num_queries=kw.get("num_queries", 8), pow_bits=kw.get("pow_bits", 4),
                       log_blowup=kw.get("log_blowup", 1))
-    cycles = sum(int(traces[k].shape[0]) for k in ("AddSub", "ShiftLeft") if k in traces)
+    cycles = sum(int(traces[k].shape[0]) for k in ("AddSub", "ShiftLeft", "Lt") if k in traces)
     return ShardCase(machine, {}, traces, pv, cycles)
