@@ -142,7 +142,7 @@ int zkb200_grind(zkb200_ctx* ctx, const uint32_t challenger[34], unsigned bits, 
  * (crates/core/machine/src/alu/{add_sub,bitwise,lt,sll,sr,clo_clz}/mod.rs) and of the control-flow
  * chips Branch and Jump (crates/core/machine/src/control_flow/{branch,jump}/trace.rs) and of MovCond
  * (crates/core/machine/src/misc/mov_cond/mod.rs); the reference's
- * own C++ twins are crates/core/machine/include/*.hpp behind cpp/extern.cpp:15-90.  One event per row
+ * own C++ twins are the chip headers under crates/core/machine/include/ behind cpp/extern.cpp:15-90.  One event per row
  * in event order, then the chip's padding rows up to 2^log_height (next_power_of_two /
  * fixed_log2_rows, crates/core/machine/src/utils/mod.rs:101-125, is the caller's choice).
  * `events` is the record's event vector as it lies in memory, host or device: 28-byte #[repr(C)]
