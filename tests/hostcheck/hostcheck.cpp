@@ -3,6 +3,9 @@
 // vectors and the oracle without a GPU.  Test infrastructure only (built by tests/test_host_logic.py).
 #include "poseidon2.cuh"
 #include "tracegen.cuh"
+#include "lane_pool.h"
+#include <atomic>
+#include <thread>
 #include <vector>
 
 namespace zkb {
@@ -71,4 +74,34 @@ int hostcheck_alu_rows(int chip, const uint32_t* ev, size_t n, size_t height, ui
   return 0;
 }
 int hostcheck_alu_width(int chip) { return alu_width(chip); }
+// stress of the lane pool (csrc/lane_pool.h): `threads` host threads take and release lanes `iters` times.
+// Returns 0 when no lane ever had two holders, never more than `active` lanes were held at once and
+// every lane below `active` was used; 1.. otherwise.
+int hostcheck_lane_pool(int threads, int iters, int active) {
+  zkb::LanePool<4> pool;
+  std::atomic<int> holders[4];
+  std::atomic<long> uses[4];
+  for (int i = 0; i < 4; i++) { holders[i] = 0; uses[i] = 0; }
+  std::atomic<int> held{0}, bad{0};
+  std::vector<std::thread> ts;
+  for (int t = 0; t < threads; t++)
+    ts.emplace_back([&, t] {
+      unsigned x = 12345u + 977u * (unsigned)t;
+      for (int i = 0; i < iters; i++) {
+        const int l = pool.acquire(active);
+        if (l < 0 || l >= active) bad |= 1;
+        if (holders[l].fetch_add(1) != 0) bad |= 2;
+        if (held.fetch_add(1) >= active) bad |= 4;
+        uses[l]++;
+        x = x * 1664525u + 1013904223u;
+        for (volatile unsigned spin = 0; spin < (x >> 24); spin++) {}
+        held.fetch_sub(1);
+        holders[l].fetch_sub(1);
+        pool.release(l);
+      }
+    });
+  for (auto& t : ts) t.join();
+  for (int i = 0; i < active && i < 4; i++) if (uses[i] == 0 && threads >= active) bad |= 8;
+  return bad.load();
+}
 }

@@ -2,6 +2,7 @@
 // reference's MachineProver implementation (crates/stark/src/prover.rs:30-184 trait,
 // :258-292 commit, :298-653 open) and of StarkMachine::setup (crates/stark/src/machine.rs:352-459).
 #pragma once
+#include "lane_pool.h"
 #include <mutex>
 #include <string>
 #include <vector>
@@ -42,6 +43,7 @@ struct Ctx {
   int active_lanes = 3;                 // ZKB200_LANES=1 serialises all compute on one stream
   cudaStream_t copy_stream = nullptr;   // host->device uploads + layout change, overlaps the compute lanes
   std::mutex copy_mu;
+  LanePool<NUM_LANES> pool;             // which lane a commit/open call runs on
   MachineInfo machine;
   NttTables tables;
   // statistics of the last open(): kernel-stage timings (ms) when profiling is enabled
@@ -88,15 +90,19 @@ DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream
 void pcs_commit(Ctx& ctx, Lane& L, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out,
                 const char* lde_stage, const char* merkle_stage);
 
-// picks a free lane (or waits for lane 0) and holds it
+// takes a free lane, waiting for any of them when all are busy, and holds it.  The lane's own mutex
+// is held as well: the kernel-level entry points (capi.cu) lock lanes[0].mu directly.
 struct LaneGuard {
+  Ctx& ctx;
+  int index;
   Lane* lane;
-  explicit LaneGuard(Ctx& ctx) : lane(nullptr) {
-    for (int i = 0; i < ctx.active_lanes && !lane; i++) if (ctx.lanes[i].mu.try_lock()) lane = &ctx.lanes[i];
-    if (!lane) { ctx.lanes[0].mu.lock(); lane = &ctx.lanes[0]; }
+  explicit LaneGuard(Ctx& c) : ctx(c), index(c.pool.acquire(c.active_lanes)), lane(&c.lanes[index]) { lane->mu.lock(); }
+  ~LaneGuard() {
+    lane->mu.unlock();
+    ctx.pool.release(index);
   }
-  ~LaneGuard() { lane->mu.unlock(); }
   LaneGuard(const LaneGuard&) = delete;
+  LaneGuard& operator=(const LaneGuard&) = delete;
 };
 
 }  // namespace zkb
