@@ -140,6 +140,28 @@ def test_lt_traces_satisfy_the_restated_lt_constraints(oracle):
         assert not om.verify_shard(p2)[0], col
 
 
+def test_all_alu_chips_traces_satisfy_their_restated_constraints(oracle):
+    """The six ALU chips in one shard: reference-identical rows (events and padding rows) under the
+    arithmetic constraints of each chip's Air::eval as restated in ziren_b200/synthetic.py."""
+    from ziren_b200 import synthetic
+    tr = {}
+    for chip, n in (("AddSub", 300), ("ShiftLeft", 200), ("Lt", 700), ("ShiftRight", 1500), ("Bitwise", 100), ("CloClz", 700)):
+        tr[chip] = oracle.alu_trace(chip, tg.synthetic_events(chip, n, seed=6), 1 << tg.padded_log_height(n))
+    case = synthetic.alu_case(tr, with_lookup_pair=False)
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    proof, _ = om.prove_shard(case.traces, case.public_values)
+    ok, err = om.verify_shard(proof)
+    assert ok, err
+    # event rows and padding rows (ShiftRight 1700, CloClz 900 are past the last event)
+    for chip, row, col in (("ShiftRight", 900, 30), ("ShiftRight", 900, 22), ("ShiftRight", 1499, 46), ("ShiftRight", 1700, 10),
+                           ("CloClz", 600, 10), ("CloClz", 900, 2), ("Bitwise", 50, 14)):
+        bad = {k: v.copy() for k, v in tr.items()}
+        bad[chip][row, col] = (int(bad[chip][row, col]) + 1) % kb.P
+        p2, _ = om.prove_shard(bad, case.public_values)
+        assert not om.verify_shard(p2)[0], (chip, row, col)
+
+
 # ---- GPU -------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def gpu():

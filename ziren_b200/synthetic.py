@@ -464,11 +464,101 @@ def _lt_chip() -> Chip:
     return Chip("Lt", 0, 32, ev, local_only=True)
 
 
+def _shift_right_chip() -> Chip:
+    """ShiftRightChip::eval crates/core/machine/src/alu/sr/mod.rs:352-512 without its byte lookups (MSB of b,
+    ShrCarry per byte, range checks) and its instruction receive; columns of ShiftRightCols."""
+    def ev(b):
+        bw = [b.main(2 + i) for i in range(4)]
+        c0 = b.main(6)
+        by_bits = [b.main(10 + i) for i in range(8)]
+        by_bytes = [b.main(18 + i) for i in range(4)]
+        byte_res = [b.main(22 + i) for i in range(8)]
+        bit_res = [b.main(30 + i) for i in range(8)]
+        carry = [b.main(38 + i) for i in range(8)]
+        shifted = [b.main(46 + i) for i in range(8)]
+        b_msb = b.main(54)
+        c_bits = [b.main(55 + i) for i in range(8)]
+        is_srl, is_ror, is_sra, is_real = b.main(63), b.main(64), b.main(65), b.main(66)
+        total = c_bits[0]
+        for i in range(1, 8):
+            total = total + c_bits[i] * (1 << i)
+        b.assert_eq(total, c0)
+        nbits = c_bits[0] + c_bits[1] * 2 + c_bits[2] * 4
+        for i in range(8):
+            b.when(by_bits[i]).assert_eq(nbits, i)
+        tot = by_bits[0]
+        for x in by_bits[1:]:
+            tot = tot + x
+        b.assert_eq(tot, 1)
+        nbytes = c_bits[3] + c_bits[4] * 2
+        for i in range(4):
+            b.when(by_bytes[i]).assert_eq(nbytes, i)
+        tot = by_bytes[0]
+        for x in by_bytes[1:]:
+            tot = tot + x
+        b.assert_eq(tot, 1)
+        ext = list(bw) + [is_sra * b_msb * 0xFF + is_ror * bw[i] for i in range(4)]
+        for k in range(4):
+            for i in range(8 - k):
+                b.when(by_bytes[k]).assert_eq(byte_res[i], ext[i + k])
+        mult = by_bits[0] * (1 << 8)
+        for i in range(1, 8):
+            mult = mult + by_bits[i] * (1 << (8 - i))
+        for i in range(7, -1, -1):
+            v = shifted[i]
+            if i + 1 < 8:
+                v = v + carry[i + 1] * mult
+            b.assert_eq(v, bit_res[i])
+        for f in (is_srl, is_sra, is_ror, is_real, b_msb):
+            _assert_bool(b, f)
+        for f in by_bytes + by_bits + c_bits:
+            _assert_bool(b, f)
+        b.assert_eq(is_srl + is_sra + is_ror, is_real)
+    return Chip("ShiftRight", 0, 67, ev, local_only=True)
+
+
+def _bitwise_chip() -> Chip:
+    """BitwiseChip::eval crates/core/machine/src/alu/bitwise/mod.rs:205-255: everything but the flag
+    constraints is a byte lookup."""
+    def ev(b):
+        flags = [b.main(14 + i) for i in range(4)]
+        for f in flags:
+            _assert_bool(b, f)
+        _assert_bool(b, flags[0] + flags[1] + flags[2] + flags[3])
+    return Chip("Bitwise", 0, 18, ev, local_only=True)
+
+
+def _clo_clz_chip() -> Chip:
+    """CloClzChip::eval crates/core/machine/src/alu/clo_clz/mod.rs:187-281 without its lookups (a[0] < 33, the SRL
+    send that pins the count) and its instruction receive; columns of CloClzCols."""
+    def ev(b):
+        a = [b.main(2 + i) for i in range(4)]
+        bw = [b.main(6 + i) for i in range(4)]
+        bb = [b.main(10 + i) for i in range(4)]
+        is_bb_zero, is_clz, is_real = b.main(14), b.main(15), b.main(16)
+        is_clo = is_real - is_clz
+        for x, y in zip(bw, bb):
+            b.when(is_clo).assert_eq(x + y, 255)
+            b.when(is_clz).assert_eq(x, y)
+        for i in (1, 2, 3):
+            b.when(is_real).assert_zero(a[i])
+        _assert_bool(b, is_bb_zero)
+        b.when(is_bb_zero).assert_zero(bb[0] + bb[1] * (1 << 8) + bb[2] * (1 << 16) + bb[3] * (1 << 24))
+        b.when(is_bb_zero).assert_zero(bb[3])
+        b.when(is_bb_zero).assert_eq(a[0], 32)
+        _assert_bool(b, is_clz)
+        _assert_bool(b, is_real)
+        b.when(is_clz).assert_eq(is_real, 1)
+    return Chip("CloClz", 0, 17, ev, local_only=True)
+
+
 def alu_case(traces: dict, *, with_lookup_pair: bool = True, **kw) -> ShardCase:
-    """`traces`: {"AddSub": rows, "ShiftLeft": rows[, "Lt": rows]} in canonical form, as produced by trace generation.
+    """`traces`: {"AddSub": rows, "ShiftLeft": rows[, "Lt" / "ShiftRight" / "Bitwise" / "CloClz": rows]} in canonical
+    form, as produced by trace generation.
     with_lookup_pair adds the Fibonacci/Sink pair so that the shard also has permutation traces (the two
     ALU chips alone have no lookups here)."""
-    chips = [_add_sub_chip(), _shift_left_chip()] + ([_lt_chip()] if "Lt" in traces else [])
+    optional = {"Lt": _lt_chip, "ShiftRight": _shift_right_chip, "Bitwise": _bitwise_chip, "CloClz": _clo_clz_chip}
+    chips = [_add_sub_chip(), _shift_left_chip()] + [make() for name, make in optional.items() if name in traces]
     traces = dict(traces)
     pv = np.zeros(8, dtype=np.uint32)
     if with_lookup_pair:
@@ -486,5 +576,5 @@ def alu_case(traces: dict, *, with_lookup_pair: bool = True, **kw) -> ShardCase:
         traces["Fibonacci"], traces["Sink"] = rows, sink
     machine = Machine(chips, num_pv_elts=4, num_queries=kw.get("num_queries", 8), pow_bits=kw.get("pow_bits", 4),
                       log_blowup=kw.get("log_blowup", 1))
-    cycles = sum(int(traces[k].shape[0]) for k in ("AddSub", "ShiftLeft", "Lt") if k in traces)
+    cycles = sum(int(traces[k].shape[0]) for k in ("AddSub", "ShiftLeft", "Lt", "ShiftRight", "Bitwise", "CloClz") if k in traces)
     return ShardCase(machine, {}, traces, pv, cycles)
