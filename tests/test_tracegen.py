@@ -91,6 +91,9 @@ def test_synthetic_events_are_well_formed():
     ev = tg.synthetic_events("Branch", 2000, seed=5)
     taken = ev[:, 2] != ev[:, 1] + 4
     assert 0.3 < taken.mean() < 0.7 and np.array_equal(ev[taken, 2], ev[taken, 1] + ev[taken, 6])
+    for chip in tg.FLOW_CHIPS:          # every program counter is a KoalaBear word
+        ev = tg.synthetic_events(chip, 2000, seed=5)
+        assert (ev[:, :3] < kb.P).all()
 
 
 def _alu_traces(oracle, n_add=1000, n_sll=300, seed=4):
@@ -156,6 +159,27 @@ def test_all_alu_chips_traces_satisfy_their_restated_constraints(oracle):
     # event rows and padding rows (ShiftRight 1700, CloClz 900 are past the last event)
     for chip, row, col in (("ShiftRight", 900, 30), ("ShiftRight", 900, 22), ("ShiftRight", 1499, 46), ("ShiftRight", 1700, 10),
                            ("CloClz", 600, 10), ("CloClz", 900, 2), ("Bitwise", 50, 14)):
+        bad = {k: v.copy() for k, v in tr.items()}
+        bad[chip][row, col] = (int(bad[chip][row, col]) + 1) % kb.P
+        p2, _ = om.prove_shard(bad, case.public_values)
+        assert not om.verify_shard(p2)[0], (chip, row, col)
+
+
+def test_branch_and_jump_traces_satisfy_their_restated_constraints(oracle):
+    """BranchChip / JumpChip arithmetic constraints (KoalaBear word range checkers, branch-taken logic, link
+    value) over reference-identical rows, including jump targets with the top byte 0x7f."""
+    from ziren_b200 import synthetic
+    tr = {}
+    for chip, n in (("AddSub", 100), ("ShiftLeft", 100), ("Branch", 1500), ("Jump", 700)):
+        tr[chip] = oracle.alu_trace(chip, tg.synthetic_events(chip, n, seed=6), 1 << tg.padded_log_height(n))
+    case = synthetic.alu_case(tr, with_lookup_pair=False)
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    proof, _ = om.prove_shard(case.traces, case.public_values)
+    ok, err = om.verify_shard(proof)
+    assert ok, err
+    for chip, row, col in (("Branch", 900, 59), ("Branch", 900, 5), ("Branch", 900, 23), ("Branch", 1400, 60), ("Jump", 2, 19),
+                           ("Jump", 600, 37), ("Jump", 650, 58), ("Jump", 900, 49)):
         bad = {k: v.copy() for k, v in tr.items()}
         bad[chip][row, col] = (int(bad[chip][row, col]) + 1) % kb.P
         p2, _ = om.prove_shard(bad, case.public_values)

@@ -552,12 +552,99 @@ def _clo_clz_chip() -> Chip:
     return Chip("CloClz", 0, 17, ev, local_only=True)
 
 
+def _word_value(w):
+    """Word::reduce: the field element sum_i byte_i 256^i."""
+    return w[0] + w[1] * (1 << 8) + w[2] * (1 << 16) + w[3] * (1 << 24)
+
+
+def _range_check_word(b, value, rc, is_real):
+    """KoalaBearWordRangeChecker::range_check crates/core/machine/src/operations/koala_bear_word.rs:51-110:
+    rc = 8 bits of the most significant byte + the running conjunctions of its low 2..7 bits."""
+    real = b.when(is_real)
+    byte = rc[0]
+    for i in range(8):
+        real.assert_zero(rc[i] * (rc[i] - 1))
+        if i:
+            byte = byte + rc[i] * (1 << i)
+    real.assert_eq(byte, value[3])
+    real.assert_zero(rc[7])
+    real.assert_eq(rc[8], rc[0] * rc[1])
+    for j in range(5):
+        real.assert_eq(rc[9 + j], rc[8 + j] * rc[2 + j])
+    b.when(is_real).when(rc[13]).assert_zero(value[0] + value[1] + value[2])
+
+
+def _branch_chip() -> Chip:
+    """BranchChip::eval crates/core/machine/src/control_flow/branch/air.rs:20-211 without its lookups (instruction
+    receive, ADD for the target, SLT for a_lt_b / a_gt_b, byte range checks); columns of BranchColumns."""
+    def ev(b):
+        next_pc = [b.main(1 + i) for i in range(4)]
+        next_rc = [b.main(5 + i) for i in range(14)]
+        target = [b.main(19 + i) for i in range(4)]
+        nn_pc = [b.main(23 + i) for i in range(4)]
+        nn_rc = [b.main(27 + i) for i in range(14)]
+        is_beq, is_bne, is_bltz, is_blez, is_bgtz, is_bgez = (b.main(53 + i) for i in range(6))
+        is_branching, a_gt_b, a_lt_b = b.main(59), b.main(60), b.main(61)
+        flags = [is_beq, is_bne, is_bltz, is_bgez, is_blez, is_bgtz]
+        for f in flags:
+            _assert_bool(b, f)
+        is_real = is_beq + is_bne + is_bltz + is_bgez + is_blez + is_bgtz
+        _assert_bool(b, is_real)
+        _range_check_word(b, next_pc, next_rc, is_real)
+        _range_check_word(b, nn_pc, nn_rc, is_real)
+        b.when(is_real).when(1 - is_branching).assert_eq(_word_value(next_pc) + 4, _word_value(nn_pc))
+        for i in range(4):
+            b.when(is_real).when(is_branching).assert_eq(target[i], nn_pc[i])
+        b.when(1 - is_real).assert_zero(is_branching)
+        b.when(is_real).assert_zero(is_branching * (is_branching - 1))
+        either = a_gt_b + a_lt_b
+        b.when(is_beq * is_branching).assert_zero(either)
+        b.when(is_beq).when(1 - is_branching).assert_eq(either, 1)
+        b.when(is_bne * is_branching).assert_eq(either, 1)
+        b.when(is_bne).when(1 - is_branching).assert_zero(either)
+        b.when(is_bltz * is_branching).assert_eq(a_lt_b, 1)
+        b.when(is_bltz).when(1 - is_branching).assert_zero(a_lt_b)
+        b.when(is_blez * is_branching).assert_zero(a_gt_b)
+        b.when(is_blez).when(1 - is_branching).assert_eq(a_gt_b, 1)
+        b.when(is_bgtz * is_branching).assert_eq(a_gt_b, 1)
+        b.when(is_bgtz).when(1 - is_branching).assert_zero(a_gt_b)
+        b.when(is_bgez * is_branching).assert_zero(a_lt_b)
+        b.when(is_bgez).when(1 - is_branching).assert_eq(a_lt_b, 1)
+    return Chip("Branch", 0, 62, ev, local_only=True)
+
+
+def _jump_chip() -> Chip:
+    """JumpChip::eval crates/core/machine/src/control_flow/jump/air.rs:20-115 without its lookups (instruction
+    receive, ADD for the pc-relative target); columns of JumpColumns."""
+    def ev(b):
+        next_pc = [b.main(1 + i) for i in range(4)]
+        next_rc = [b.main(5 + i) for i in range(14)]
+        nn_pc = [b.main(19 + i) for i in range(4)]
+        nn_rc = [b.main(23 + i) for i in range(14)]
+        op_a = [b.main(37 + i) for i in range(4)]
+        op_b = [b.main(41 + i) for i in range(4)]
+        is_jump, is_jumpi, is_jumpdirect = b.main(49), b.main(50), b.main(51)
+        a_rc = [b.main(52 + i) for i in range(14)]
+        for f in (is_jump, is_jumpi, is_jumpdirect):
+            _assert_bool(b, f)
+        is_real = is_jump + is_jumpi + is_jumpdirect
+        _assert_bool(b, is_real)
+        b.when(is_real).assert_eq(_word_value(op_a), _word_value(next_pc) + 4)
+        _range_check_word(b, op_a, a_rc, is_real)
+        _range_check_word(b, next_pc, next_rc, is_real)
+        _range_check_word(b, nn_pc, nn_rc, is_real)
+        for i in range(4):
+            b.when(is_jump + is_jumpi).assert_eq(nn_pc[i], op_b[i])
+    return Chip("Jump", 0, 66, ev, local_only=True)
+
+
 def alu_case(traces: dict, *, with_lookup_pair: bool = True, **kw) -> ShardCase:
     """`traces`: {"AddSub": rows, "ShiftLeft": rows[, "Lt" / "ShiftRight" / "Bitwise" / "CloClz": rows]} in canonical
     form, as produced by trace generation.
     with_lookup_pair adds the Fibonacci/Sink pair so that the shard also has permutation traces (the two
     ALU chips alone have no lookups here)."""
-    optional = {"Lt": _lt_chip, "ShiftRight": _shift_right_chip, "Bitwise": _bitwise_chip, "CloClz": _clo_clz_chip}
+    optional = {"Lt": _lt_chip, "ShiftRight": _shift_right_chip, "Bitwise": _bitwise_chip, "CloClz": _clo_clz_chip,
+                "Branch": _branch_chip, "Jump": _jump_chip}
     chips = [_add_sub_chip(), _shift_left_chip()] + [make() for name, make in optional.items() if name in traces]
     traces = dict(traces)
     pv = np.zeros(8, dtype=np.uint32)
@@ -576,5 +663,5 @@ def alu_case(traces: dict, *, with_lookup_pair: bool = True, **kw) -> ShardCase:
         traces["Fibonacci"], traces["Sink"] = rows, sink
     machine = Machine(chips, num_pv_elts=4, num_queries=kw.get("num_queries", 8), pow_bits=kw.get("pow_bits", 4),
                       log_blowup=kw.get("log_blowup", 1))
-    cycles = sum(int(traces[k].shape[0]) for k in ("AddSub", "ShiftLeft", "Lt", "ShiftRight", "Bitwise", "CloClz") if k in traces)
+    cycles = sum(int(traces[k].shape[0]) for k in ("AddSub", "ShiftLeft", "Lt", "ShiftRight", "Bitwise", "CloClz", "Branch", "Jump") if k in traces)
     return ShardCase(machine, {}, traces, pv, cycles)

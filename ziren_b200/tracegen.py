@@ -84,24 +84,26 @@ EDGE_OPERANDS = np.array([0, 1, 7, 8, 9, 31, 32, 33, 0x7F, 0x80, 0xFF, 0x100, 0x
 
 
 def _flow_events(chip: str, n: int, rng, edges: bool) -> np.ndarray:
-    """Well-formed BranchEvent / JumpEvent records: next_next_pc is where the delay-slot semantics of the
-    executor lands (branch target next_pc + c when taken, else next_pc + 4; jump target in b)."""
+    """Well-formed BranchEvent / JumpEvent records: every program counter is a KoalaBear word (< p, which the
+    chips range-check); next_next_pc is where the delay-slot semantics of the executor lands: the branch
+    target next_pc + c when taken, else next_pc + 4; the register value b for Jump / Jumpi, next_pc + b for
+    JumpDirect; a jump's a is the link value next_pc + 4."""
     ev = np.zeros((n, EVENT_WORDS), np.uint32)
-    ev[:, 0] = rng.integers(0, kb.P - 16, n) & ~np.uint32(3)
+    ev[:, 0] = rng.integers(1 << 22, kb.P - (1 << 22), n) & ~np.uint32(3)
     ev[:, 1] = ev[:, 0] + 4
     op = rng.choice([OPCODES[o] for o in ALU_CHIPS[chip][1]], n).astype(np.uint32)
     ev[:, 3] = op
     a = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
     b = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
     c = (rng.integers(-(1 << 17), 1 << 17, n) * 4).astype(np.int64).astype(np.uint32)
-    if edges:
-        m = len(EDGE_OPERANDS)
-        k = min(n, m * m)
-        idx = np.arange(k)
-        a[:k], b[:k] = EDGE_OPERANDS[idx // m], EDGE_OPERANDS[idx % m]
-        lo, hi = k, min(n, k + 256)
-        b[lo:hi] = a[lo:hi]
     if chip == "Branch":
+        if edges:
+            m = len(EDGE_OPERANDS)
+            k = min(n, m * m)
+            idx = np.arange(k)
+            a[:k], b[:k] = EDGE_OPERANDS[idx // m], EDGE_OPERANDS[idx % m]
+            lo, hi = k, min(n, k + 256)
+            b[lo:hi] = a[lo:hi]
         sa, sb = a.astype(np.int32), b.astype(np.int32)
         eq, lt, gt = a == b, sa < sb, sa > sb
         taken = np.select([op == OPCODES["BEQ"], op == OPCODES["BNE"], op == OPCODES["BLTZ"], op == OPCODES["BLEZ"],
@@ -109,8 +111,17 @@ def _flow_events(chip: str, n: int, rng, edges: bool) -> np.ndarray:
         ev[:, 2] = np.where(taken, ev[:, 1] + c, ev[:, 1] + 4)
     else:
         a = (ev[:, 1] + 4).astype(np.uint32)          # link register value
-        b = (rng.integers(0, kb.P, n) & ~np.uint32(3)).astype(np.uint32)
-        ev[:, 2] = b
+        direct = op == OPCODES["JumpDirect"]
+        target = (rng.integers(1 << 22, kb.P - (1 << 22), n) & ~np.uint32(3)).astype(np.uint32)
+        b = np.where(direct, c, target).astype(np.uint32)        # BAL: pc-relative offset; J / JR: absolute target
+        ev[:, 2] = np.where(direct, ev[:, 1] + c, target)
+        if edges and n:
+            # the largest KoalaBear word and its neighbours as jump targets (top byte 0x7f: the range checker's edge)
+            k = min(n, 4)
+            tops = np.array([kb.P - 1, 0x7F000000 - 4, 0x7E000000, 0x7EFFFFFC], np.uint32)[:k]
+            ev[:k, 3] = OPCODES["Jump"]
+            b[:k] = tops
+            ev[:k, 2] = tops
     ev[:, 4], ev[:, 5], ev[:, 6] = a, b, c
     return ev
 
