@@ -165,12 +165,13 @@ def test_all_alu_chips_traces_satisfy_their_restated_constraints(oracle):
         assert not om.verify_shard(p2)[0], (chip, row, col)
 
 
-def test_branch_and_jump_traces_satisfy_their_restated_constraints(oracle):
-    """BranchChip / JumpChip arithmetic constraints (KoalaBear word range checkers, branch-taken logic, link
-    value) over reference-identical rows, including jump targets with the top byte 0x7f."""
+def test_branch_jump_movcond_traces_satisfy_their_restated_constraints(oracle):
+    """BranchChip / JumpChip / MovCondChip arithmetic constraints (KoalaBear word range checkers, branch-taken
+    logic, link value, per-byte is-zero hints) over reference-identical rows, including jump targets with the
+    top byte 0x7f."""
     from ziren_b200 import synthetic
     tr = {}
-    for chip, n in (("AddSub", 100), ("ShiftLeft", 100), ("Branch", 1500), ("Jump", 700)):
+    for chip, n in (("AddSub", 100), ("ShiftLeft", 100), ("Branch", 1500), ("Jump", 700), ("MovCond", 1500)):
         tr[chip] = oracle.alu_trace(chip, tg.synthetic_events(chip, n, seed=6), 1 << tg.padded_log_height(n))
     case = synthetic.alu_case(tr, with_lookup_pair=False)
     om = oracle.OracleMachine(case.machine)
@@ -179,7 +180,8 @@ def test_branch_and_jump_traces_satisfy_their_restated_constraints(oracle):
     ok, err = om.verify_shard(proof)
     assert ok, err
     for chip, row, col in (("Branch", 900, 59), ("Branch", 900, 5), ("Branch", 900, 23), ("Branch", 1400, 60), ("Jump", 2, 19),
-                           ("Jump", 600, 37), ("Jump", 650, 58), ("Jump", 900, 49)):
+                           ("Jump", 600, 37), ("Jump", 650, 58), ("Jump", 900, 49), ("MovCond", 900, 18), ("MovCond", 901, 28),
+                           ("MovCond", 1700, 29)):
         bad = {k: v.copy() for k, v in tr.items()}
         bad[chip][row, col] = (int(bad[chip][row, col]) + 1) % kb.P
         p2, _ = om.prove_shard(bad, case.public_values)

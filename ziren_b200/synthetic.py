@@ -638,13 +638,51 @@ def _jump_chip() -> Chip:
     return Chip("Jump", 0, 66, ev, local_only=True)
 
 
+def _mov_cond_chip() -> Chip:
+    """MovCondChip::eval crates/core/machine/src/misc/mov_cond/mod.rs:170-255 with IsZeroWordOperation::eval
+    (operations/is_zero_word.rs:49-82, is_zero.rs:42-66), without the instruction receive; columns of MovCondCols."""
+    def ev(b):
+        op_a = [b.main(2 + i) for i in range(4)]
+        prev_a = [b.main(6 + i) for i in range(4)]
+        op_b = [b.main(10 + i) for i in range(4)]
+        op_c = [b.main(14 + i) for i in range(4)]
+        inv = [b.main(18 + 2 * i) for i in range(4)]
+        res = [b.main(19 + 2 * i) for i in range(4)]
+        lower, upper, result = b.main(26), b.main(27), b.main(28)
+        is_mne, is_meq, is_wsbh = b.main(29), b.main(30), b.main(31)
+        is_real = is_mne + is_meq + is_wsbh
+        real = b.when(is_real)
+        for i in range(4):
+            real.assert_eq(1 - inv[i] * op_c[i], res[i])
+            real.assert_zero(res[i] * (res[i] - 1))
+            b.when(is_real).when(res[i]).assert_zero(op_c[i])
+        _assert_bool(b, is_real)
+        for f in (lower, upper, result):
+            real.assert_zero(f * (f - 1))
+        real.assert_eq(lower, res[0] * res[1])
+        real.assert_eq(upper, res[2] * res[3])
+        real.assert_eq(result, lower * upper)
+        for i in range(4):
+            b.when(is_meq).when(result).assert_eq(op_a[i], op_b[i])
+            b.when(is_meq).when(1 - result).assert_eq(op_a[i], prev_a[i])
+            b.when(is_mne).when(1 - result).assert_eq(op_a[i], op_b[i])
+            b.when(is_mne).when(result).assert_eq(op_a[i], prev_a[i])
+        for i, j in ((0, 1), (1, 0), (2, 3), (3, 2)):
+            b.when(is_wsbh).assert_eq(op_a[i], op_b[j])
+        for i in range(4):
+            b.when(is_wsbh).assert_zero(prev_a[i])
+        for f in (is_mne, is_meq, is_wsbh):
+            _assert_bool(b, f)
+    return Chip("MovCond", 0, 32, ev, local_only=True)
+
+
 def alu_case(traces: dict, *, with_lookup_pair: bool = True, **kw) -> ShardCase:
     """`traces`: {"AddSub": rows, "ShiftLeft": rows[, "Lt" / "ShiftRight" / "Bitwise" / "CloClz": rows]} in canonical
     form, as produced by trace generation.
     with_lookup_pair adds the Fibonacci/Sink pair so that the shard also has permutation traces (the two
     ALU chips alone have no lookups here)."""
     optional = {"Lt": _lt_chip, "ShiftRight": _shift_right_chip, "Bitwise": _bitwise_chip, "CloClz": _clo_clz_chip,
-                "Branch": _branch_chip, "Jump": _jump_chip}
+                "Branch": _branch_chip, "Jump": _jump_chip, "MovCond": _mov_cond_chip}
     chips = [_add_sub_chip(), _shift_left_chip()] + [make() for name, make in optional.items() if name in traces]
     traces = dict(traces)
     pv = np.zeros(8, dtype=np.uint32)
@@ -663,5 +701,5 @@ def alu_case(traces: dict, *, with_lookup_pair: bool = True, **kw) -> ShardCase:
         traces["Fibonacci"], traces["Sink"] = rows, sink
     machine = Machine(chips, num_pv_elts=4, num_queries=kw.get("num_queries", 8), pow_bits=kw.get("pow_bits", 4),
                       log_blowup=kw.get("log_blowup", 1))
-    cycles = sum(int(traces[k].shape[0]) for k in ("AddSub", "ShiftLeft", "Lt", "ShiftRight", "Bitwise", "CloClz", "Branch", "Jump") if k in traces)
+    cycles = sum(int(traces[k].shape[0]) for k in ("AddSub", "ShiftLeft", "Lt", "ShiftRight", "Bitwise", "CloClz", "Branch", "Jump", "MovCond") if k in traces)
     return ShardCase(machine, {}, traces, pv, cycles)

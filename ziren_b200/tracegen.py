@@ -143,6 +143,7 @@ def _mov_cond_events(n: int, rng, edges: bool) -> np.ndarray:
     if edges and n:
         k = min(n, len(EDGE_OPERANDS))
         c[:k] = EDGE_OPERANDS[:k]
+    prev_a[op == OPCODES["WSBH"]] = 0          # WSBH has no previous value of a (mov_cond/mod.rs: assert_word_zero)
     swapped = ((b & np.uint32(0x00FF00FF)) << 8) | ((b >> 8) & np.uint32(0x00FF00FF))
     a = np.select([op == OPCODES["MEQ"], op == OPCODES["MNE"]], [np.where(c == 0, b, prev_a), np.where(c != 0, b, prev_a)], swapped)
     ev[:, 2], ev[:, 3], ev[:, 4], ev[:, 5], ev[:, 6] = op, a.astype(np.uint32), b, c, prev_a
