@@ -158,8 +158,8 @@ def test_commitment_gather_world_size_2_gloo():
 
 
 def test_lane_pool_hands_out_any_free_lane(host):
-    """csrc/lane_pool.h under contention: one holder per lane, never more than `active` lanes held, every
-    lane used, and the calls return (a waiter is woken by ANY release, not only lane 0's)."""
+    """csrc/lane_pool.h under contention: one holder per lane, never more than `active` lanes held, and the
+    calls return (a waiter is woken by ANY release, not only lane 0's)."""
     for threads, active in ((4, 3), (8, 3), (2, 1), (6, 4), (3, 3)):
         assert host.hostcheck_lane_pool(threads, 3000, active) == 0, (threads, active)
 
