@@ -335,6 +335,14 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1):
                     "traffic_source": "algorithmic bytes x the dram__bytes ratio of the ncu --set full capture under profiles/",
                     "ms": ms, "algorithmic_bytes": alg,
                     "share_of_step": ms / max(sum(stages.values()), 1e-9)}
+    if "k1_lde" in out:
+        # arithmetic floor of the coset LDE under the same instruction prices: per input element one inverse and two
+        # forward transforms = 1.5 log2(n) butterflies (Shoup product 8.2 + add 2.95 + sub about 1.3 cycles) and three
+        # more Shoup products (four-step twiddles, coset scale); weighted by the elements of every table
+        cyc = sum(h * w * (1.5 * max(1, int(h).bit_length() - 1) * 12.45 + 3 * 8.2) for h, w in trace_shapes.values())
+        floor_ms = cyc / (148 * 4 * 32 * 1.965e9) * 1e3
+        out["k1_lde"]["issue_roofline"] = {"model_floor_ms": floor_ms, "achieved_ms": out["k1_lde"]["ms"], "frac": floor_ms / out["k1_lde"]["ms"],
+                                           "source": "butterfly arithmetic only, prices of tools/sweep/pipe_probe.cu"}
     if "k2_merkle" in out:
         rate = perms / (stages["commit_main_merkle"] / 1e3)
         out["k2_merkle"]["poseidon2_Gperm_per_s"] = rate / 1e9
