@@ -10,6 +10,12 @@ timeout 300 python bench.py --stages --no-cpu-baseline > gpurun_out/${T}_bench_d
 ZKB200_EVAL_V2=1 timeout 300 python -m pytest tests -m gpu -q -k "proof or shard or commit or edge or reference_shapes" > gpurun_out/${T}_pytest_evalv2.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${T}_pytest_evalv2.log
 ZKB200_EVAL_V2=1 timeout 300 python bench.py --stages --no-cpu-baseline --steps 6 > gpurun_out/${T}_bench_evalv2.json 2> gpurun_out/${T}_bench_evalv2.err
+# opt-in NTT variant: parity of the transforms, then the LDE microbench both ways
+ZKB200_NTT_PRETWIDDLE=1 timeout 200 python -m pytest tests -m gpu -q -k "lde or ntt or commit or shard_proof" > gpurun_out/${T}_pytest_pretw.log 2>&1
+echo "pytest exit $?" >> gpurun_out/${T}_pytest_pretw.log
+( timeout 60 python tools/microbench.py lde --log-n 18 --width 512
+  ZKB200_NTT_PRETWIDDLE=1 timeout 60 python tools/microbench.py lde --log-n 18 --width 512 ) > gpurun_out/${T}_lde_pretw.jsonl 2>&1
+tail -3 gpurun_out/${T}_pytest_pretw.log; cut -c1-120 gpurun_out/${T}_lde_pretw.jsonl
 tail -3 gpurun_out/${T}_pytest.log gpurun_out/${T}_pytest_evalv2.log
 python - <<'PY'
 import json

@@ -220,6 +220,7 @@ struct StridedArgs {
                                      // 1: DIT (pre-twiddle) storing bit-reversed positions
   size_t out_coset_stride;           // final_dit: blockIdx.z selects the coset block of in/out
   size_t in_coset_stride;
+  int pre_twiddled;                  // final_dit: the producer already applied the four-step twiddles (ZKB200_NTT_PRETWIDDLE)
 };
 
 // LT >= 0: tile width 2^LT known at compile time (the launcher's default for this K), which folds the
@@ -246,7 +247,7 @@ __device__ __forceinline__ void strided_body(const StridedArgs& a, u32* smem) {
     const u32 row = FINAL ? bitrev32(slot, K) : slot;
     const size_t pos = ((size_t)row << logS) + t0 + q;
     const u32 v = in[pos];
-    return FINAL ? shoup_mul(v, __ldg(four + pos)) : fp_raw(v);
+    return (FINAL && !a.pre_twiddled) ? shoup_mul(v, __ldg(four + pos)) : fp_raw(v);
   };
   auto gstore = [&](u32 slot, u32 q, Fp v) {      // DIF only: post-twiddle, in-place position
     const size_t pos = ((size_t)slot << logS) + t0 + q;
@@ -311,6 +312,8 @@ struct ContigArgs {
   int bitrev_store;                  // mode 1, single level (K == logn): store bit-reversed rows
   const uint2* scale;                // per coset: n Shoup pairs, shift_c^bitrev(p) / n at position p
   size_t out_coset_stride;           // element offset between coset outputs
+  const uint2* four_dit;             // mode 1, two-level: four-step twiddles of the following strided DIT level, applied
+                                     // by this kernel's coalesced store instead of that level's scattered load (or null)
 };
 
 static constexpr int CONTIG_TILE_LOG = 12;
@@ -380,7 +383,14 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
       const u32 sub = (f0 + q) & ((1u << sub_bits) - 1);
       return shoup_mul(bufA[caddr(slot, q, ldg)], __ldg(sc + (((size_t)sub << K) + slot)));
     };
-    auto gstore = [&](u32 slot, u32 q, Fp v) { if (f0 + q < a.total_groups) outc[gaddr(slot, q, a.out_stride)] = v.v; };
+    auto gstore = [&](u32 slot, u32 q, Fp v) {
+      if (f0 + q >= a.total_groups) return;
+      if (a.four_dit) {
+        const size_t p = ((size_t)((f0 + q) & ((1u << sub_bits) - 1)) << K) + slot;     // position in the column
+        v = shoup_mul(v.v, __ldg(a.four_dit + p));
+      }
+      outc[gaddr(slot, q, a.out_stride)] = v.v;
+    };
     // ---- DIT: the same bit ranges bottom-up; the last round stores straight to global memory ----
     constexpr int RL = round_bits(K, NR - 1);
     if constexpr (NR == 1) {
@@ -424,13 +434,14 @@ static void split_levels(int logn, int& K1, int& K2) {
 
 static void launch_strided(const NttTables& tb, const u32* in, size_t in_stride, u32* out, size_t out_stride, size_t ncols,
                            int K, int logS, bool inverse, bool final_dit, int ncoset, size_t in_coset_stride,
-                           size_t out_coset_stride, cudaStream_t s) {
+                           size_t out_coset_stride, cudaStream_t s, bool pre_twiddled = false) {
   StridedArgs a;
   a.in = in; a.out = out; a.in_stride = in_stride; a.out_stride = out_stride;
   a.small_tw = (const uint2*)tb.small_tw;
   a.four = (const uint2*)tb.four_step_table(K, logS, inverse, s);
   a.logS = logS; a.inverse = inverse ? 1 : 0; a.final_dit = final_dit ? 1 : 0;
   a.in_coset_stride = in_coset_stride; a.out_coset_stride = out_coset_stride;
+  a.pre_twiddled = pre_twiddled ? 1 : 0;
   static const int tile_log = env_int("ZKB200_NTT_STRIDED_TILE_LOG", STRIDED_TILE_LOG);
   int logT = tile_log - K;                       // 8192 elements (512 threads) per tile: two CTAs per SM
   if (logT > 5) logT = 5;
@@ -556,6 +567,7 @@ void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* 
     ContigArgs b;
     b.K = K2; b.logn = (int)log_n; b.mode = 1; b.inverse = 1; b.ncoset = (int)ncoset;
     b.scale = scale;
+    b.four_dit = nullptr;
     if (!two_level) {
       b.in = in + c0 * in_stride; b.in_stride = in_stride;
       b.out = out + c0 * out_stride; b.out_stride = out_stride; b.out_coset_stride = n;
@@ -567,8 +579,13 @@ void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* 
     b.in = half.p; b.in_stride = n;
     b.out = xbuf.p; b.out_stride = n; b.out_coset_stride = chunk * n;
     b.bitrev_store = 0;
+    // opt-in (not yet measured on a B200): the fused kernel multiplies by the DIT level's four-step twiddles
+    // as it stores, so that the strided DIT launch loads data only
+    static const bool pretw = env_int("ZKB200_NTT_PRETWIDDLE", 0) != 0;
+    b.four_dit = pretw ? (const uint2*)tb.four_step_table(K1, K2, false, s) : nullptr;
     launch_contig(tb, b, nc, s);
-    launch_strided(tb, xbuf.p, n, out + c0 * out_stride, out_stride, nc, K1, K2, false, true, (int)ncoset, chunk * n, n, s);
+    launch_strided(tb, xbuf.p, n, out + c0 * out_stride, out_stride, nc, K1, K2, false, true, (int)ncoset, chunk * n, n, s,
+                   pretw);
   }
 }
 
@@ -616,6 +633,7 @@ void ntt_batch(const NttTables& tb, const u32* in, u32* out, unsigned log_n, siz
     b.in = src; b.in_stride = n; b.out = dst; b.out_stride = n; b.out_coset_stride = 0;
     b.K = K2; b.logn = (int)log_n; b.mode = 0; b.inverse = inverse ? 1 : 0; b.ncoset = 1; b.bitrev_store = 0;
     b.scale = nullptr;
+    b.four_dit = nullptr;
     launch_contig(tb, b, nc, s);
     if (!bitrev_out) bitrev_rows(tmp.p, out + c0 * n, log_n, nc, s);
   }
