@@ -30,6 +30,17 @@ def test_case_file_layout(tmp_path):
     assert w[3 + desc.size + 15] == len(case.prep)
 
 
+def test_proofs_file_round_trip(tmp_path):
+    proofs = [np.arange(10, dtype=np.uint32), np.arange(3, dtype=np.uint32) + 7]
+    words = [np.array([casefile.MAGIC_PROOFS, 1], np.uint32), np.arange(8, dtype=np.uint32) + 100, np.array([len(proofs)], np.uint32)]
+    for p in proofs:
+        words += [np.array([p.size], np.uint32), p]
+    path = str(tmp_path / "p.out")
+    np.concatenate(words).astype("<u4").tofile(path)
+    commit, got = casefile.read_proofs(path)
+    assert commit.tolist() == list(range(100, 108)) and [g.tolist() for g in got] == [p.tolist() for p in proofs]
+
+
 def test_driver_builds_and_fails_loudly_without_a_gpu(driver, tmp_path):
     try:
         import torch
