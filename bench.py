@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--sample-log-cpu", type=int, default=14, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle verifier's check of the timed proof")
     ap.add_argument("--value-threads", type=int, default=3,
                     help="host threads proving device-resident shards concurrently in the `value` arm (compute lanes)")
     ap.add_argument("--e2e-threads", type=int, default=4,
@@ -260,6 +261,21 @@ def main():
     assert np.array_equal(proof, proof2)
     d2h_bytes = int(proof.size) * 4
 
+    # the proof that was timed is checked: the oracle's verifier (restated from crates/stark/src/verifier.rs
+    # and the recursion circuit) must accept it at the bench configuration, and reject a corrupted copy
+    verified = None
+    if args.rank == 0 and not args.no_verify:
+        from oracle import oracle_ffi as o
+        om = o.OracleMachine(case.machine)
+        o.set_num_threads(os.cpu_count())
+        om.setup(case.prep)
+        ok, err = om.verify_shard(proof)
+        bad = proof.copy()
+        bad[proof.size // 2] ^= 1
+        verified = bool(ok) and not om.verify_shard(bad)[0]
+        if not ok:
+            print("oracle verifier REJECTED the timed proof:", err, file=sys.stderr)
+
     stages = None
     if args.rank == 0:
         prover.set_profile(True)
@@ -293,7 +309,7 @@ def main():
                 "e2e": {"value": total_cycles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                         "host_threads_in_flight": args.e2e_threads},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other,
+                "verified": verified, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other,
                 "cpu_baseline": cpu_base,
                 "stage_ms": stages, "cells_per_sec": cells * args.steps * args.gpus / (ms_dev / 1e3)}
         print(json.dumps(line))

@@ -62,7 +62,7 @@ int main(int argc, char** argv) {
     }
 
     zkb200::B200Prover prover(argc > 3 ? std::atoi(argv[3]) : 0, desc);     // MachineProver::new
-    zkb200::ProvingKey pk = prover.setup(prep, pc_start, gsum);             // setup + pk_to_device
+    zkb200::ProvingKey pk = prover.setup(prep, pc_start, &gsum);            // setup + pk_to_device
     auto proofs = prover.prove(pk, records);                                // commit + open per record
 
     std::ofstream o(argv[2], std::ios::binary);

@@ -80,7 +80,8 @@ const char* zkb200_last_error(zkb200_ctx* ctx);
 void* zkb200_ctx_stream(zkb200_ctx* ctx);
 
 /* MachineProver::setup + pk_to_device — prover.rs:49-63, machine.rs:352-459: commit the
- * preprocessed traces, keep traces + LDEs + tree on the device.  init_global_sum: 14 words. */
+ * preprocessed traces, keep traces + LDEs + tree on the device.  init_global_sum: 14 canonical
+ * words (x[7], y[7]); NULL = SepticDigest::zero(), the curve START point (septic_digest.rs:9-42). */
 int zkb200_setup(zkb200_ctx* ctx, const zkb200_trace* prep, int n, uint32_t pc_start,
                  const uint32_t* init_global_sum, uint32_t commit_out[8], zkb200_pk** out);
 void zkb200_pk_free(zkb200_pk* pk);

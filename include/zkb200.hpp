@@ -113,10 +113,12 @@ class B200Prover {
   ~B200Prover() { if (ctx_) zkb200_ctx_destroy(ctx_); }
 
   ProvingKey setup(const std::vector<Trace>& preprocessed, uint32_t pc_start = 0,
-                   const std::array<uint32_t, 14>& initial_global_cumulative_sum = {}) const {
+                   const std::array<uint32_t, 14>* initial_global_cumulative_sum = nullptr) const {
+    // nullptr: SepticDigest::zero(), the curve START point (crates/stark/src/septic_digest.rs:9-42)
     auto t = marshal(preprocessed);
     ProvingKey pk;
-    check(zkb200_setup(ctx_, t.data(), (int)t.size(), pc_start, initial_global_cumulative_sum.data(), pk.commit_.data(), &pk.h_));
+    check(zkb200_setup(ctx_, t.data(), (int)t.size(), pc_start,
+                       initial_global_cumulative_sum ? initial_global_cumulative_sum->data() : nullptr, pk.commit_.data(), &pk.h_));
     return pk;
   }
   ShardMainData commit(const std::vector<Trace>& traces, const std::vector<uint32_t>& public_values) const {

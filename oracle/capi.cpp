@@ -141,7 +141,7 @@ void* zko_setup(void* m_, int n, const char* const* names, const u32* const* ptr
     std::vector<std::pair<std::string, Matrix>> prep;
     for (int i = 0; i < n; i++) prep.push_back({names[i], mat_from(ptrs[i], heights[i], widths[i])});
     F gs[14];
-    for (int i = 0; i < 14; i++) gs[i] = F(init_gsum ? init_gsum[i] : 0);
+    for (int i = 0; i < 14; i++) gs[i] = F(init_gsum ? init_gsum[i] : SEPTIC_DIGEST_ZERO[i]);
     auto pk = setup(*(Machine*)m_, std::move(prep), F(pc_start), gs);
     if (commit_out) for (int i = 0; i < 8; i++) commit_out[i] = pk->commit[i].v;
     return pk.release();

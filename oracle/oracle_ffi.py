@@ -239,7 +239,7 @@ class OracleMachine:
     def setup(self, prep: dict, pc_start=0, init_gsum=None):
         mats, n, cn, ptrs, hs, ws = _named(prep)
         commit = np.zeros(8, np.uint32)
-        gs = _a(init_gsum) if init_gsum is not None else np.zeros(14, np.uint32)
+        gs = _a(init_gsum) if init_gsum is not None else np.array([637514027, 1595065213, 1998064738, 72333738, 1211544370, 822986770, 1518535784, 1604177449, 90440090, 259343427, 140470264, 1162099742, 941559812, 1064053343], np.uint32)   # SepticDigest::zero()
         self.pk = lib().zko_setup(C.c_void_p(self.h), C.c_int(n), cn, ptrs, hs, ws, C.c_uint32(pc_start), _p(gs), _p(commit))
         if not self.pk:
             raise RuntimeError("oracle: " + err())

@@ -14,6 +14,10 @@
 
 namespace zko {
 
+// SepticDigest::zero(): CURVE_CUMULATIVE_SUM_START_{X,Y}, crates/stark/src/septic_digest.rs:9-14 (canonical)
+static const u32 SEPTIC_DIGEST_ZERO[14] = {637514027u, 1595065213u, 1998064738u, 72333738u, 1211544370u, 822986770u, 1518535784u,
+                                           1604177449u, 90440090u, 259343427u, 140470264u, 1162099742u, 941559812u, 1064053343u};
+
 struct ProvingKey {
   Digest commit;
   F pc_start;
@@ -124,7 +128,9 @@ static inline std::unique_ptr<ShardProof> open(const Machine& m, const ProvingKe
     const Matrix* prep = pi >= 0 ? &pk.traces[pi] : nullptr;
     if (prep && prep->height != sd.traces[i].height) throw std::runtime_error("preprocessed and main have different heights");
     Matrix pt = generate_permutation_trace(*chips[i], prep, sd.traces[i], perm_alpha, perm_beta, local_sums[i]);
-    for (auto& x : global_sums[i]) x = F::zero();
+    // Local-scope chips carry SepticDigest::zero(), the curve START point, NOT 14 zeros
+    // (crates/stark/src/septic_digest.rs:9-42, prover.rs:352)
+    for (int k = 0; k < 14; k++) global_sums[i][k] = F(SEPTIC_DIGEST_ZERO[k]);
     if (chips[i]->global_scope) {
       const Matrix& t = sd.traces[i];
       const F* last = t.row(t.height - 1) + t.width - 14;
@@ -343,7 +349,7 @@ static inline std::string verify_shard(const Machine& m, const VerifyingKey& vk,
     ch.observe_ext(o.local_sum);
     ch.observe_slice(o.global_sum, 14);
     bool gz = true;
-    for (int k = 0; k < 14; k++) gz = gz && o.global_sum[k].is_zero();
+    for (int k = 0; k < 14; k++) gz = gz && o.global_sum[k] == F(SEPTIC_DIGEST_ZERO[k]);   // SepticDigest::is_zero, verifier.rs:102
     if (!chips[i]->global_scope && !gz) return "global cumulative sum is non-zero, but chip is Local";
     if (chips[i]->perm_width_ef() == 0 && !o.local_sum.is_zero()) return "local cumulative sum is non-zero, but no local lookups";
   }

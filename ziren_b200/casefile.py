@@ -25,7 +25,7 @@ def write_case(path: str, machine, prep: dict, records: list, pc_start: int = 0,
     parts = [np.array([MAGIC_CASE, 1], np.uint32)]
     desc = np.ascontiguousarray(machine.descriptor(), dtype=np.uint32)
     parts += [np.array([desc.size], np.uint32), desc, np.array([pc_start], np.uint32)]
-    parts.append(np.zeros(14, np.uint32) if initial_global_sum is None else np.asarray(initial_global_sum, np.uint32))
+    parts.append(kb.SEPTIC_DIGEST_ZERO.copy() if initial_global_sum is None else np.asarray(initial_global_sum, np.uint32))
     parts.append(np.array([len(prep)], np.uint32))
     for name, rows in prep.items():
         parts += _trace_words(name, rows)

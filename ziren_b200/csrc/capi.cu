@@ -25,6 +25,9 @@ static int guarded(zkb200_ctx* ctx, F&& f) {
   } catch (const std::exception& e) {
     g_err = e.what();
     cudaGetLastError();
+    // error path only: kernels of the failed call may still be queued on a lane and read buffers the
+    // caller is about to release (stream-ordered frees on another stream) - drain the device first
+    if (ctx) { cudaSetDevice(ctx->c.device); cudaDeviceSynchronize(); cudaGetLastError(); }
     return 1;
   }
 }
@@ -130,7 +133,9 @@ int zkb200_coset_lde(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, unsigne
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
     if (log_n + log_blowup > 24) throw std::runtime_error("zkb200: LDE height exceeds 2^24");
     size_t n = (size_t)1 << log_n;
-    coset_lde_batch(ctx->c.tables, in, n, out, n << log_blowup, log_n, width, log_blowup, fp_from_canonical(shift), ctx->c.lanes[0].stream);
+    Lane& L = ctx->c.lanes[0];
+    if (L.keep.size() > 32) { ZKB_CUDA(cudaStreamSynchronize(L.stream)); L.keep.clear(); }
+    coset_lde_batch(ctx->c.tables, in, n, out, n << log_blowup, log_n, width, log_blowup, fp_from_canonical(shift), L.stream, L.keep);
   });
 }
 int zkb200_ntt(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, unsigned log_n, size_t width, int inverse, int bitrev_out) {

@@ -67,6 +67,54 @@ __global__ void __launch_bounds__(128, 16) leaf_hash_kernel(const MatRef* __rest
   for (int j = 0; j < 8; j++) out[j * height + r] = st[j].v;
 }
 
+static size_t leaf_smem_for(size_t nblocks);
+
+// Piecewise leaf hashing: the sponge over a wide matrix is absorbed in column pieces as their LDEs
+// are produced (the upload of the next piece overlaps, prover_commit), the 16-word state of every
+// row parked in HBM between pieces (SoA [16][height]).  Every piece but the last is a whole number of
+// rate blocks (8 columns); the last one takes the ragged tail (PaddingFreeSponge: a short block
+// overwrites state[0..len) only) and writes the digests.
+__global__ void __launch_bounds__(128, 16) leaf_absorb_kernel(const u32* __restrict__ cols, size_t height, u32 ncols,
+                                                          u32* __restrict__ state, int first, int last,
+                                                          u32* __restrict__ digests) {
+  size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (r >= height) return;
+  Fp st[16];
+  if (first) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) st[i] = fp_zero();
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i++) st[i] = fp_raw(state[(size_t)i * height + r]);
+  }
+  const u32* __restrict__ p = cols + r;
+  u32 c = 0;
+  for (; c + 8 <= ncols; c += 8) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = fp_raw(p[(size_t)i * height]);
+    p += 8 * height;
+    p2_permute_dev(st);
+  }
+  if (c < ncols) {   // ragged tail (last piece only)
+#pragma unroll
+    for (int i = 0; i < 8; i++) if (c + i < ncols) st[i] = fp_raw(p[(size_t)i * height]);
+    p2_permute_dev(st);
+  }
+  if (last) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) digests[j * height + r] = st[j].v;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i++) state[(size_t)i * height + r] = st[i].v;
+  }
+}
+void leaf_absorb(const u32* cols, size_t height, u32 ncols, u32* state, bool first, bool last, u32* digests, cudaStream_t s) {
+  if (!last && (ncols & 7)) throw std::runtime_error("zkb200: leaf_absorb: a non-final piece must be whole rate blocks");
+  const unsigned nblocks = ceil_div(height, 128);
+  leaf_absorb_kernel<<<nblocks, 128, leaf_smem_for(nblocks), s>>>(cols, height, ncols, state, first ? 1 : 0, last ? 1 : 0, digests);
+  ZKB_CHECK_LAUNCH();
+}
+
 // next[i] = compress(prev[2i], prev[2i+1]); optionally then compress(., inject[i]) where inject holds
 // the row digests of the matrices of this height (hashed by leaf_hash_kernel, word-major)
 __global__ void __launch_bounds__(128) compress_kernel(const u32* __restrict__ prev, u32* __restrict__ next, size_t m,
@@ -153,7 +201,8 @@ static void alloc_layers(DigestLayers& out, unsigned max_log, cudaStream_t s) {
 
 // layers 1..max_log from the leaf layer; `groups` = matrices to inject, keyed by log height
 static void build_upper(DigestLayers& out, unsigned max_log, const std::map<unsigned, std::vector<MatRef>>& groups,
-                        std::map<unsigned, const MatRef*>& dev_groups, u32* root_dev, cudaStream_t s) {
+                        std::map<unsigned, const MatRef*>& dev_groups, u32* root_dev, cudaStream_t s,
+                        const std::map<unsigned, const u32*>* pre = nullptr) {
   unsigned l = 1;
   while (l <= max_log) {
     size_t m = out.count[l];
@@ -168,16 +217,18 @@ static void build_upper(DigestLayers& out, unsigned max_log, const std::map<unsi
       l = l2;
       continue;
     }
-    DevBuf inj(inject ? 8 * m : 0, s);
-    if (inject) launch_leaf_hash(dev_groups[lh], (int)groups.at(lh).size(), m, inj.p, s);
-    compress_kernel<<<ceil_div(m, 128), 128, 0, s>>>(out.layer(l - 1), out.layer(l), m, inject ? inj.p : nullptr);
+    const u32* pre_inj = (inject && pre && pre->count(lh)) ? pre->at(lh) : nullptr;
+    DevBuf inj(inject && !pre_inj ? 8 * m : 0, s);
+    if (inject && !pre_inj) launch_leaf_hash(dev_groups[lh], (int)groups.at(lh).size(), m, inj.p, s);
+    compress_kernel<<<ceil_div(m, 128), 128, 0, s>>>(out.layer(l - 1), out.layer(l), m, inject ? (pre_inj ? pre_inj : inj.p) : nullptr);
     ZKB_CHECK_LAUNCH();
     l++;
   }
   ZKB_CUDA(cudaMemcpyAsync(root_dev, out.layer(max_log), 8 * sizeof(u32), cudaMemcpyDeviceToDevice, s));
 }
 
-void merkle_build(const std::vector<MatRef>& mats, ParamArena& arena, DigestLayers& out, u32* root_dev, cudaStream_t s) {
+void merkle_build(const std::vector<MatRef>& mats, ParamArena& arena, DigestLayers& out, u32* root_dev, cudaStream_t s,
+                  const std::map<unsigned, const u32*>* pre) {
   unsigned max_log = 0;
   for (auto& m : mats) max_log = std::max(max_log, m.log_height);
   // group by height, list order preserved
@@ -187,10 +238,11 @@ void merkle_build(const std::vector<MatRef>& mats, ParamArena& arena, DigestLaye
   for (auto& g : groups) dev_groups[g.first] = arena.push(g.second.data(), g.second.size());
   alloc_layers(out, max_log, s);
   size_t h = (size_t)1 << max_log;
-  launch_leaf_hash(dev_groups[max_log], (int)groups[max_log].size(), h, out.layer(0), s);
+  if (pre && pre->count(max_log)) ZKB_CUDA(cudaMemcpyAsync(out.layer(0), pre->at(max_log), 8 * h * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+  else launch_leaf_hash(dev_groups[max_log], (int)groups[max_log].size(), h, out.layer(0), s);
   std::map<unsigned, std::vector<MatRef>> inj = groups;
   inj.erase(max_log);
-  build_upper(out, max_log, inj, dev_groups, root_dev, s);
+  build_upper(out, max_log, inj, dev_groups, root_dev, s, pre);
 }
 
 // FRI commit-phase layer: leaves are the pairs (e_{2i}, e_{2i+1}) of the folded vector flattened
@@ -293,7 +345,8 @@ void Challenger::load(const u32* w) {
   for (int i = 0; i < 8; i++) in_buf[i] = fp_from_canonical(w[17 + i]);
   n_out = w[25];
   for (int i = 0; i < 8; i++) out_buf[i] = fp_from_canonical(w[26 + i]);
-  if (n_in > 8 || n_out > 8) throw std::runtime_error("zkb200: malformed challenger state");
+  // a duplex challenger never rests with a full input buffer (observe() permutes at 8)
+  if (n_in >= 8 || n_out > 8) throw std::runtime_error("zkb200: malformed challenger state");
 }
 void Challenger::store(u32* w) const {
   for (int i = 0; i < 16; i++) w[i] = fp_to_canonical(state[i]);

@@ -4,6 +4,7 @@
 // phase (reference call sites crates/stark/src/prover.rs:277,403,497,547; structure pinned by
 // crates/recursion/circuit/src/fri.rs:363-405, hash.rs:40-80, challenger.rs:60-233).
 #pragma once
+#include <map>
 #include "common.h"
 #include "poseidon2.cuh"
 
@@ -28,7 +29,12 @@ struct DigestLayers {
 // Build the tree over column-major matrices of power-of-two heights (leaf = sponge over the
 // concatenated rows of the tallest matrices in list order; shorter ones injected on the way up).
 // `mats_dev` is the same list in device memory.  Root (Montgomery) is written to root_dev[8].
-void merkle_build(const std::vector<MatRef>& mats, ParamArena& arena, DigestLayers& out, u32* root_dev, cudaStream_t s);
+// `pre`: row digests ([8][height] word-major) already computed for whole height groups, keyed by log
+// height (leaf_absorb below); those groups are not hashed again.
+void merkle_build(const std::vector<MatRef>& mats, ParamArena& arena, DigestLayers& out, u32* root_dev, cudaStream_t s,
+                  const std::map<unsigned, const u32*>* pre = nullptr);
+// One column piece of a matrix into the per-row sponge states (state: [16][height] words); see hash.cu.
+void leaf_absorb(const u32* cols, size_t height, u32 ncols, u32* state, bool first, bool last, u32* digests, cudaStream_t s);
 
 // Tree over one FRI commit-phase layer: folded = m EF values, component-major [4][m].
 void fri_commit_layer(const u32* folded, size_t m, DigestLayers& out, u32* root_dev, cudaStream_t s);

@@ -56,6 +56,8 @@ void MachineInfo::parse(const u32* words, size_t n) {
       };
       check(l.mult);
       for (auto& v : l.values) check(v);
+      // bpow[] of the LogUp and quotient kernels holds beta^0..beta^16
+      if (l.values.size() > 16) throw std::runtime_error("zkb200: lookup tuple longer than 16 values in chip " + c.name);
       if (l.scope == 0) c.lookups.push_back(std::move(l));   // only local lookups enter the permutation
     }
     for (u32 i = 0; i < nn; i++) {
@@ -63,6 +65,7 @@ void MachineInfo::parse(const u32* words, size_t n) {
       if (nd.op > N_NEG) throw std::runtime_error("zkb200: bad node opcode in chip " + c.name);
       if (nd.op >= N_ADD && (nd.a >= i || (nd.op != N_NEG && nd.b >= i))) throw std::runtime_error("zkb200: constraint DAG is not topologically ordered");
       if (nd.op == N_MAIN && nd.a >= c.main_width) throw std::runtime_error("zkb200: main column out of range in chip " + c.name);
+      if (nd.op == N_PUB && nd.a >= num_pv_elts) throw std::runtime_error("zkb200: public value index out of range in chip " + c.name);
       if (nd.op == N_PREP && nd.a >= c.prep_width) throw std::runtime_error("zkb200: preprocessed column out of range in chip " + c.name);
       c.nodes.push_back(nd);
     }

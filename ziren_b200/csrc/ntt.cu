@@ -63,7 +63,9 @@ __global__ void small_tw_kernel(uint2* out, const u32* lo, const u32* hi) {
   if (dir) E = (0u - E) & ((1u << 24) - 1);
   out[i] = shoup_pair(tw_pow2(lo, hi, E));
 }
+void ntt_set_device_attributes();
 void NttTables::init(cudaStream_t s) {
+  ntt_set_device_attributes();
   ZKB_CUDA(cudaMalloc((void**)&tw_lo, sizeof(u32) << TW_SPLIT));
   ZKB_CUDA(cudaMalloc((void**)&tw_hi, sizeof(u32) << TW_SPLIT));
   tw_init_kernel<<<(1 << TW_SPLIT) / 256, 256, 0, s>>>(tw_lo, tw_hi);
@@ -78,8 +80,7 @@ void NttTables::destroy() {
   if (tw_hi) cudaFree(tw_hi);
   if (small_tw) cudaFree(small_tw);
   for (auto& kv : four_step) cudaFree(kv.second);
-  for (auto& kv : scale_cache) cudaFree(kv.second);
-  four_step.clear(); scale_cache.clear(); scale_cache_bytes = 0;
+  four_step.clear(); scale_cache.clear(); scale_bytes.clear(); scale_cache_bytes = 0;
   tw_lo = tw_hi = nullptr; small_tw = nullptr;
 }
 
@@ -425,6 +426,17 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
 
 // ---- launch helpers ------------------------------------------------------------------------------
 
+// Dynamic shared memory above 48 KB is a per-DEVICE function attribute: set for every instantiation
+// when a context initialises its tables on its device (NttTables::init), not behind process-wide flags.
+template <int KK>
+static void set_ntt_attrs_from() {
+  ZKB_CUDA(cudaFuncSetAttribute(ntt_strided_kernel<KK, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ZKB_CUDA(cudaFuncSetAttribute(ntt_strided_kernel<KK, strided_default_lt(KK)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  ZKB_CUDA(cudaFuncSetAttribute(ntt_contig_kernel<KK, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if constexpr (KK < KMAX) set_ntt_attrs_from<KK + 1>();
+}
+void ntt_set_device_attributes() { set_ntt_attrs_from<1>(); }
+
 static void split_levels(int logn, int& K1, int& K2) {
   if (logn <= KMAX) { K1 = 0; K2 = logn; return; }
   K2 = (logn + 1) / 2;
@@ -452,15 +464,8 @@ static void launch_strided(const NttTables& tb, const u32* in, size_t in_stride,
   unsigned threads = (unsigned)std::max<size_t>(32, tile_elems / ELEMS_PER_THREAD);
   size_t smem = ((size_t)tw_words(K) + ((size_t)1 << (K + logT))) * sizeof(u32);
   dim3 grid(1u << (logS - logT), (unsigned)ncols, (unsigned)ncoset);
-  static bool attr_done[KMAX + 1] = {false};
 #define ZKB_STRIDED_CASE(KK)                                                                                              \
   case KK:                                                                                                                \
-    if (!attr_done[KK]) {                                                                                                 \
-      ZKB_CUDA(cudaFuncSetAttribute(ntt_strided_kernel<KK, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));  \
-      ZKB_CUDA(cudaFuncSetAttribute(ntt_strided_kernel<KK, strided_default_lt(KK)>,                                       \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                            \
-      attr_done[KK] = true;                                                                                               \
-    }                                                                                                                     \
     if (logT == strided_default_lt(KK)) ntt_strided_kernel<KK, strided_default_lt(KK)><<<grid, threads, smem, s>>>(a);    \
     else ntt_strided_kernel<KK, -1><<<grid, threads, smem, s>>>(a);                                                       \
     break;
@@ -488,13 +493,8 @@ static void launch_contig(const NttTables& tb, ContigArgs a, size_t ncols, cudaS
   const size_t ldg = ((size_t)1 << K) + (((size_t)1 << K) >> 3) + 1;
   size_t smem = ((size_t)2 * tw_words(K) + ((size_t)(a.mode == 1 ? 2 : 1) << logT) * ldg) * sizeof(u32);
   unsigned grid = (unsigned)((groups + ((size_t)1 << logT) - 1) >> logT);
-  static bool attr_done[KMAX + 1] = {false};
 #define ZKB_CONTIG_CASE(KK)                                                                                               \
   case KK:                                                                                                                \
-    if (!attr_done[KK]) {                                                                                                 \
-      ZKB_CUDA(cudaFuncSetAttribute(ntt_contig_kernel<KK, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      attr_done[KK] = true;                                                                                               \
-    }                                                                                                                     \
     ntt_contig_kernel<KK, -1><<<grid, threads, smem, s>>>(a);   /* fixed tile width: no measurable gain here */          \
     break;
   switch (K) {
@@ -515,32 +515,33 @@ __global__ void scale_table_kernel(uint2* out, int logn, int log_blowup, Fp shif
   Fp sh = shift * fp_pow(wN, bitrev32(c, log_blowup));
   out[i] = shoup_pair(ninv * fp_pow(sh, bitrev32(p, logn)));
 }
-const void* NttTables::scale_table(unsigned log_n, unsigned log_blowup, Fp shift, cudaStream_t s) const {
+std::shared_ptr<void> NttTables::scale_table(unsigned log_n, unsigned log_blowup, Fp shift, cudaStream_t s) const {
   std::lock_guard<std::mutex> lock(mu);
   const u64 key = ((u64)shift.v << 16) | (log_n << 4) | log_blowup;
   auto it = scale_cache.find(key);
   if (it != scale_cache.end()) return it->second;
   const size_t count = (size_t)1 << (log_n + log_blowup);
   if (scale_cache_bytes + count * sizeof(uint2) > ((size_t)1 << 30)) {
-    // callers only hold a table for the duration of stream-ordered launches: drain before freeing
-    ZKB_CUDA(cudaDeviceSynchronize());
-    for (auto& kv : scale_cache) cudaFree(kv.second);
-    scale_cache.clear(); scale_cache_bytes = 0;
+    // drop the cache's references only: a table some lane still uses lives on in that lane's
+    // keep-alive list and is freed when the lane lets go of it
+    scale_cache.clear(); scale_bytes.clear(); scale_cache_bytes = 0;
   }
   void* p = nullptr;
   ZKB_CUDA(cudaMalloc(&p, count * sizeof(uint2)));
+  std::shared_ptr<void> sp(p, [](void* q) { cudaFree(q); });
   Fp ninv = fp_inv(fp_from_canonical((u32)(((size_t)1 << log_n) % KB_P)));
   scale_table_kernel<<<ceil_div(count, 256), 256, 0, s>>>((uint2*)p, (int)log_n, (int)log_blowup, shift, ninv,
                                                          two_adic_generator(log_n + log_blowup));
   ZKB_CHECK_LAUNCH();
-  ZKB_CUDA(cudaStreamSynchronize(s));
-  scale_cache[key] = p;
+  ZKB_CUDA(cudaStreamSynchronize(s));   // published to every lane: must be complete
+  scale_cache[key] = sp;
+  scale_bytes[key] = count * sizeof(uint2);
   scale_cache_bytes += count * sizeof(uint2);
-  return p;
+  return sp;
 }
 
 void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* out, size_t out_stride,
-                     unsigned log_n, size_t width, unsigned log_blowup, Fp shift, cudaStream_t s) {
+                     unsigned log_n, size_t width, unsigned log_blowup, Fp shift, cudaStream_t s, KeepAlive& keep) {
   if (width == 0) return;
   const size_t n = (size_t)1 << log_n;
   const unsigned ncoset = 1u << log_blowup;
@@ -551,7 +552,8 @@ void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* 
   }
   int K1, K2;
   split_levels((int)log_n, K1, K2);
-  const uint2* scale = (const uint2*)tb.scale_table(log_n, log_blowup, shift, s);
+  keep.push_back(tb.scale_table(log_n, log_blowup, shift, s));
+  const uint2* scale = (const uint2*)keep.back().get();
   // column chunks bound the scratch (n x chunk x (1 + cosets) words).  The kernels are
   // instruction-issue bound, not bandwidth bound, so large chunks (fewer, fuller launches) beat
   // L2-resident ones: measured 3.3 ms at 2^26 vs 4.3 ms at 2^22 for 2^18 x 512 (profiles/README.md)

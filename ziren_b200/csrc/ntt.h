@@ -4,7 +4,9 @@
 // crates/stark/src/machine.rs:416-417).
 #pragma once
 #include <map>
+#include <memory>
 #include <mutex>
+#include <vector>
 #include "common.h"
 
 namespace zkb {
@@ -14,20 +16,26 @@ struct NttTables {
   u32* tw_hi = nullptr;  // w^(4096 e), e in [0, 4096)
   void* small_tw = nullptr;                       // Shoup pairs of w_{2^K}^(+-e), K <= 12
   mutable std::map<int, void*> four_step;         // per (log n, direction): four-step twiddles by position
-  mutable std::map<u64, void*> scale_cache;       // per (log n, blow-up, shift): coset scale factors by position
+  // per (log n, blow-up, shift): coset scale factors by position.  Entries are reference counted: a
+  // caller parks the pointer it got in its lane's keep-alive list until that lane has drained, so
+  // evicting the cache can never free a table that queued kernels still read.
+  mutable std::map<u64, std::shared_ptr<void>> scale_cache;
+  mutable std::map<u64, size_t> scale_bytes;
   mutable size_t scale_cache_bytes = 0;
   mutable std::mutex mu;                          // tables are shared by the compute lanes
   void init(cudaStream_t s);
   void destroy();
   const void* four_step_table(int K1, int logS, bool inverse, cudaStream_t s) const;
-  const void* scale_table(unsigned log_n, unsigned log_blowup, Fp shift, cudaStream_t s) const;
+  std::shared_ptr<void> scale_table(unsigned log_n, unsigned log_blowup, Fp shift, cudaStream_t s) const;
 };
 
 // Coset LDE of every column: in = evaluations over H_n in natural order (col-major n x w,
 // column stride in_stride), out = evaluations over shift * K_{n << log_blowup} stored
 // BIT-REVERSED by row (col-major, column stride out_stride).  Montgomery residues.
+// `keep`: tables the queued kernels read; the caller drops them once the stream has drained.
+typedef std::vector<std::shared_ptr<void>> KeepAlive;
 void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* out, size_t out_stride,
-                     unsigned log_n, size_t width, unsigned log_blowup, Fp shift, cudaStream_t s);
+                     unsigned log_n, size_t width, unsigned log_blowup, Fp shift, cudaStream_t s, KeepAlive& keep);
 
 // Plain DFT of every column, natural order in; out natural (bitrev_out = false) or bit-reversed.
 void ntt_batch(const NttTables& tb, const u32* in, u32* out, unsigned log_n, size_t width, bool inverse,

@@ -194,6 +194,29 @@ __global__ void __launch_bounds__(E2_WARPS * 32, 3) eval_columns_v2_kernel(const
   }
 }
 
+// SM count, occupancy and the opt-in shared-memory size are per-device facts: cached per device
+// (a process may hold contexts on several GPUs), filled under a lock on first use.
+struct OpenDeviceInfo { bool ready = false; int sms = 148; int slots_per_sm[2] = {1, 1}; };
+static const OpenDeviceInfo& open_device_info() {
+  static std::mutex mu;
+  static OpenDeviceInfo info[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  OpenDeviceInfo& d = info[dev & 63];
+  if (!d.ready) {
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.slots_per_sm[0], eval_columns_kernel<1>, EC_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.slots_per_sm[1], eval_columns_kernel<2>, EC_THREADS, 0);
+    const size_t smem = (size_t)(2 * E2_WARPS * 32 * E2_LD + 2 * E2_ROWS * 8) * sizeof(u32);
+    cudaFuncSetAttribute(eval_columns_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(eval_columns_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (d.sms <= 0) d.sms = 148;
+    d.ready = true;
+  }
+  return d;
+}
+
 __global__ void sum_partials_kernel(const u32* partial, size_t count, int nsplit, u32* out) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= count) return;
@@ -207,16 +230,8 @@ void eval_columns(const u32* lde, size_t H, size_t n, size_t W, const u32* w0, c
   static const bool use_v2 = getenv("ZKB200_EVAL_V2") && atoi(getenv("ZKB200_EVAL_V2")) != 0;
   if (use_v2 && n >= 1024 && W >= 128) {
     // rows are split in multiples of E2_ROWS so that every CTA runs whole steps; about three CTAs per SM
-    static std::once_flag v2_once;
-    static int v2_sms = 148;
     const size_t smem = (size_t)(2 * E2_WARPS * 32 * E2_LD + 2 * E2_ROWS * 8) * sizeof(u32);
-    std::call_once(v2_once, [&] {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&v2_sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaFuncSetAttribute(eval_columns_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(eval_columns_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    });
+    const int v2_sms = open_device_info().sms;
     const size_t colgroups = (W + E2_WARPS * 32 - 1) / (E2_WARPS * 32);
     size_t nsplit = ((size_t)3 * v2_sms + colgroups - 1) / colgroups;
     if (nsplit > n / 256) nsplit = n / 256;
@@ -240,17 +255,9 @@ void eval_columns(const u32* lde, size_t H, size_t n, size_t W, const u32* w0, c
   // Row splits: enough CTAs to fill the GPU, and for large grids the split count (<= 8) whose last
   // wave is fullest (every CTA does the same work, so a ragged last wave is lost time: the
   // 1042-CTA keccak matrix runs 3.5 waves unsplit)
-  static int slots_per_sm[2] = {0, 0};
-  static int sms = 0;
-  static std::once_flag once;       // several host threads open shards concurrently
-  std::call_once(once, [] {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slots_per_sm[0], eval_columns_kernel<1>, EC_THREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slots_per_sm[1], eval_columns_kernel<2>, EC_THREADS, 0);
-    if (sms <= 0) sms = 148;
-  });
+  const OpenDeviceInfo& di = open_device_info();
+  const int sms = di.sms;
+  const int* slots_per_sm = di.slots_per_sm;
   const size_t slots = (size_t)sms * std::max(1, slots_per_sm[npoints == 1 ? 0 : 1]);
   size_t nsplit = 1;
   if (colblocks < slots) nsplit = (slots + colblocks - 1) / colblocks;

@@ -8,6 +8,7 @@
 #include <array>
 #include <cstdlib>
 #include <map>
+#include <nvtx3/nvToolsExt.h>
 #include "layout.h"
 #include "logup.h"
 #include "open.h"
@@ -16,6 +17,10 @@
 namespace zkb {
 
 std::atomic<unsigned long long> g_kernel_launches{0};
+
+// CURVE_CUMULATIVE_SUM_START_{X,Y} (canonical), crates/stark/src/septic_digest.rs:9-14
+static const u32 SEPTIC_DIGEST_ZERO[14] = {637514027u, 1595065213u, 1998064738u, 72333738u, 1211544370u, 822986770u, 1518535784u,
+                                           1604177449u, 90440090u, 259343427u, 140470264u, 1162099742u, 941559812u, 1064053343u};
 
 void Ctx::init(int dev, const u32* desc, size_t n) {
   device = dev;
@@ -47,6 +52,13 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
       ZKB_CUDA(cudaStreamSynchronize(lanes[0].stream));
     }
   }
+  {
+    int nthr = getenv("ZKB200_STAGE_THREADS") ? atoi(getenv("ZKB200_STAGE_THREADS")) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    int mb = getenv("ZKB200_STAGE_SLOT_MB") ? atoi(getenv("ZKB200_STAGE_SLOT_MB")) : 32;
+    stager.init(4, (size_t)std::max(1, mb) << 20, std::max(1, nthr));
+  }
+  if (const char* e = getenv("ZKB200_PIECE_MB")) piece_bytes = (size_t)std::max(1, atoi(e)) << 20;
+  if (const char* e = getenv("ZKB200_PIECE_KB")) piece_bytes = (size_t)std::max(1, atoi(e)) << 10;   // tests: many pieces at small sizes
   machine.upload();
   tables.init(lanes[0].stream);
   p2_upload_constants();
@@ -61,6 +73,7 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
 void Ctx::destroy() {
   cudaSetDevice(device);
   cudaDeviceSynchronize();
+  stager.destroy();
   machine.destroy();
   tables.destroy();
   for (auto& L : lanes) {
@@ -74,70 +87,175 @@ void Ctx::destroy() {
   copy_stream = nullptr;
 }
 
+// Per-stage device times (profiling mode) and NVTX ranges named after the reference's tracing spans
+// (crates/stark/src/prover.rs:340,402,427,496,546).  Times of stages with the same name accumulate:
+// the main commit interleaves layout change, LDE and leaf hashing piece by piece.
 struct StageTimer {
   Ctx& ctx; cudaStream_t stream; const char* name; cudaEvent_t a = nullptr, b = nullptr;
-  StageTimer(Ctx& c, Lane& L, const char* n) : ctx(c), stream(L.stream), name(n) {
+  StageTimer(Ctx& c, Lane& L, const char* n, const char* span = nullptr) : ctx(c), stream(L.stream), name(n) {
+    nvtxRangePushA(span ? span : n);
     if (ctx.profile) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, stream); }
   }
   ~StageTimer() {
     if (ctx.profile) {
       cudaEventRecord(b, stream); cudaEventSynchronize(b);
       float ms = 0; cudaEventElapsedTime(&ms, a, b);
-      ctx.stage_ms.push_back({name, ms});
+      {
+        std::lock_guard<std::mutex> lock(ctx.stage_mu);
+        bool found = false;
+        for (auto& kv : ctx.stage_ms) if (kv.first == name) { kv.second += ms; found = true; break; }
+        if (!found) ctx.stage_ms.push_back({name, ms});
+      }
       cudaEventDestroy(a); cudaEventDestroy(b);
     }
+    nvtxRangePop();
   }
 };
+
+static bool is_device_pointer(const void* p, bool* pinned = nullptr) {
+  cudaPointerAttributes attr;
+  if (pinned) *pinned = false;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (pinned) *pinned = attr.type == cudaMemoryTypeHost;
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
 
 // Row-major host/device matrix -> column-major device matrix, issued on stream `on`.  The result
 // is released on the compute stream, so `on` must be joined into it before first use.
 DevMat upload_colmajor(Ctx& ctx, const u32* data, size_t h, size_t w, cudaStream_t on, cudaStream_t free_on) {
-  (void)ctx;
   DevMat m(h, w, on);
   m.buf.stream = free_on;
   if (h * w == 0) return m;
-  cudaPointerAttributes attr;
-  bool on_device = false;
-  if (cudaPointerGetAttributes(&attr, data) == cudaSuccess) on_device = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
-  else cudaGetLastError();
-  if (on_device) {
+  bool pinned = false;
+  if (is_device_pointer(data, &pinned)) {
     transpose_to_colmajor(data, m.d(), h, w, on);
   } else {
     DevBuf stage(h * w, on);
-    ZKB_CUDA(cudaMemcpyAsync(stage.p, data, h * w * sizeof(u32), cudaMemcpyHostToDevice, on));
+    if (pinned) ZKB_CUDA(cudaMemcpyAsync(stage.p, data, h * w * sizeof(u32), cudaMemcpyHostToDevice, on));
+    else ctx.stager.copy_2d(stage.p, data, w, w, h, on);
     transpose_to_colmajor(stage.p, m.d(), h, w, on);
   }
   return m;
 }
 
-// TwoAdicFriPcs::commit: coset LDE (shift GENERATOR / domain_shift) of every matrix + MMCS tree.
-void pcs_commit(Ctx& ctx, Lane& L, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out,
-                const char* lde_stage, const char* merkle_stage) {
-  const unsigned lb = ctx.machine.log_blowup;
-  std::vector<MatRef> refs;
-  out.ldes.clear(); out.log_n.clear();
-  Fp gen = fp_from_canonical(KB_GEN);
-  std::unique_ptr<StageTimer> tm(lde_stage ? new StageTimer(ctx, L, lde_stage) : nullptr);
-  for (size_t i = 0; i < traces.size(); i++) {
-    const DevMat& t = traces[i];
-    unsigned ln = log2_exact(t.height);
-    if (((size_t)1 << ln) != t.height) throw std::runtime_error("zkb200: trace height is not a power of two");
-    if (ln + lb > 24) throw std::runtime_error("zkb200: LDE height exceeds the field's two-adicity (2^24)");
-    DevMat lde(t.height << lb, t.width, L.stream);
-    Fp shift = gen * fp_inv(domain_shifts[i]);
-    coset_lde_batch(ctx.tables, t.d(), t.height, lde.d(), lde.height, ln, t.width, lb, shift, L.stream);
-    refs.push_back(MatRef{lde.d(), (u32)t.width, ln + lb});
-    out.ldes.push_back(std::move(lde));
-    out.log_n.push_back(ln);
+// ---- pageable host memory --------------------------------------------------------------------
+// The reference hands over RowMajorMatrix.values, an ordinary heap Vec (prover.rs:258-262).  A DMA
+// from pageable memory is staged by the driver through one small bounce buffer on the calling
+// thread; here a few host threads gather the (strided) rows of a piece into a ring of pinned
+// slots while earlier slots are in flight, so the copy runs near the pinned rate.
+void HostStager::init(int nslots_, size_t slot_bytes_, int nthreads_) {
+  nslots = nslots_; slot_bytes = slot_bytes_; nthreads = nthreads_;
+}
+void HostStager::ensure() {
+  if (!slots.empty()) return;
+  slots.resize(nslots); free_ev.resize(nslots);
+  for (int i = 0; i < nslots; i++) {
+    ZKB_CUDA(cudaMallocHost((void**)&slots[i], slot_bytes));
+    ZKB_CUDA(cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming));
   }
-  tm.reset(merkle_stage ? new StageTimer(ctx, L, merkle_stage) : nullptr);
-  merkle_build(refs, L.arena, out.layers, L.d_small, L.stream);
+  stop = false;
+  for (int t = 0; t < nthreads; t++) workers.emplace_back([this, t] { worker(t); });
+}
+void HostStager::destroy() {
+  {
+    std::lock_guard<std::mutex> lk(m);
+    stop = true;
+  }
+  cv.notify_all();
+  for (auto& w : workers) w.join();
+  workers.clear();
+  for (auto p : slots) cudaFreeHost(p);
+  for (auto e : free_ev) cudaEventDestroy(e);
+  slots.clear(); free_ev.clear();
+}
+void HostStager::worker(int t) {
+  unsigned long long seen = 0;
+  for (;;) {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return stop || job_id != seen; });
+    if (stop) return;
+    seen = job_id;
+    const Job j = job;
+    lk.unlock();
+    // rows [r0, r1) of the job are split evenly over the threads
+    const size_t per = (j.rows + nthreads - 1) / nthreads;
+    const size_t r0 = std::min(j.rows, per * t), r1 = std::min(j.rows, r0 + per);
+    if (j.src_pitch == j.row_words) {
+      if (r1 > r0) memcpy(j.dst + r0 * j.row_words, j.src + r0 * j.src_pitch, (r1 - r0) * j.row_words * sizeof(u32));
+    } else {
+      for (size_t r = r0; r < r1; r++) memcpy(j.dst + r * j.row_words, j.src + r * j.src_pitch, j.row_words * sizeof(u32));
+    }
+    lk.lock();
+    if (++done == nthreads) cv_done.notify_all();
+  }
+}
+// dst (device, dense rows of row_words) <- src (pageable host, rows src_pitch words apart)
+void HostStager::copy_2d(u32* dst, const u32* src, size_t row_words, size_t src_pitch, size_t rows, cudaStream_t s) {
+  std::lock_guard<std::mutex> use(use_mu);     // one staged copy at a time (callers hold the copy lock anyway)
+  ensure();
+  const size_t rows_per_slot = std::max<size_t>(1, slot_bytes / (row_words * sizeof(u32)));
+  if (row_words * sizeof(u32) > slot_bytes) throw std::runtime_error("zkb200: row wider than a staging slot");
+  for (size_t r0 = 0; r0 < rows; r0 += rows_per_slot) {
+    const size_t nr = std::min(rows_per_slot, rows - r0);
+    const int slot = next_slot;
+    next_slot = (next_slot + 1) % nslots;
+    ZKB_CUDA(cudaEventSynchronize(free_ev[slot]));     // the DMA that last read this slot is done
+    {
+      std::unique_lock<std::mutex> lk(m);
+      job = Job{slots[slot], src + r0 * src_pitch, row_words, src_pitch, nr};
+      done = 0;
+      job_id++;
+      cv.notify_all();
+      cv_done.wait(lk, [&] { return done == nthreads; });
+    }
+    ZKB_CUDA(cudaMemcpyAsync(dst + r0 * row_words, slots[slot], nr * row_words * sizeof(u32), cudaMemcpyHostToDevice, s));
+    ZKB_CUDA(cudaEventRecord(free_ev[slot], s));
+  }
+}
+
+// ---- TwoAdicFriPcs::commit --------------------------------------------------------------------
+static void check_height(const MachineInfo& M, size_t height, unsigned& ln) {
+  ln = log2_exact(height);
+  if (((size_t)1 << ln) != height) throw std::runtime_error("zkb200: trace height is not a power of two");
+  if (ln + M.log_blowup > 24) throw std::runtime_error("zkb200: LDE height exceeds the field's two-adicity (2^24)");
+}
+
+// Merkle tree over LDEs that are already in `out.ldes` (`pre`: row digests of height groups hashed
+// piecewise during the upload); fetches the root.
+static void pcs_merkle(Ctx& ctx, Lane& L, Commit& out, const std::map<unsigned, const u32*>* pre, const char* merkle_stage) {
+  std::vector<MatRef> refs;
+  for (size_t i = 0; i < out.ldes.size(); i++)
+    refs.push_back(MatRef{out.ldes[i].d(), (u32)out.ldes[i].width, out.log_n[i] + ctx.machine.log_blowup});
+  std::unique_ptr<StageTimer> tm(merkle_stage ? new StageTimer(ctx, L, merkle_stage) : nullptr);
+  merkle_build(refs, L.arena, out.layers, L.d_small, L.stream, pre);
   ZKB_CUDA(cudaMemcpyAsync(L.h_small, L.d_small, 32, cudaMemcpyDeviceToHost, L.stream));
   ZKB_CUDA(cudaStreamSynchronize(L.stream));
   tm.reset();
   memcpy(out.root, L.h_small, 32);
   out.log_max_height = 0;
   for (auto& r : refs) out.log_max_height = std::max(out.log_max_height, r.log_height);
+}
+
+// coset LDE (shift GENERATOR / domain_shift) of every matrix + MMCS tree.
+void pcs_commit(Ctx& ctx, Lane& L, std::vector<DevMat>& traces, const std::vector<Fp>& domain_shifts, Commit& out,
+                const char* lde_stage, const char* merkle_stage) {
+  const unsigned lb = ctx.machine.log_blowup;
+  out.ldes.clear(); out.log_n.clear();
+  Fp gen = fp_from_canonical(KB_GEN);
+  {
+    std::unique_ptr<StageTimer> tm(lde_stage ? new StageTimer(ctx, L, lde_stage) : nullptr);
+    for (size_t i = 0; i < traces.size(); i++) {
+      const DevMat& t = traces[i];
+      unsigned ln;
+      check_height(ctx.machine, t.height, ln);
+      DevMat lde(t.height << lb, t.width, L.stream);
+      Fp shift = gen * fp_inv(domain_shifts[i]);
+      coset_lde_batch(ctx.tables, t.d(), t.height, lde.d(), lde.height, ln, t.width, lb, shift, L.stream, L.keep);
+      out.ldes.push_back(std::move(lde));
+      out.log_n.push_back(ln);
+    }
+  }
+  pcs_merkle(ctx, L, out, nullptr, merkle_stage);
 }
 
 static void sort_traces(std::vector<TraceIn>& v) {
@@ -151,7 +269,7 @@ Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, co
   ZKB_CUDA(cudaSetDevice(ctx.device));
   LaneGuard guard(ctx);
   Lane& L = *guard.lane;
-  L.arena.reset();
+  L.begin();
   std::unique_ptr<Pk> pk(new Pk());
   pk->ctx = &ctx;
   std::vector<TraceIn> prep = prep_in;
@@ -171,70 +289,131 @@ Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, co
     for (int i = 0; i < 8; i++) pk->commit_canon[i] = fp_to_canonical(fp_raw(pk->data.root[i]));
   }
   pk->pc_start = pc_start;
-  for (int i = 0; i < 14; i++) pk->init_global_sum[i] = init_gsum ? init_gsum[i] : 0;
+  for (int i = 0; i < 14; i++) pk->init_global_sum[i] = init_gsum ? init_gsum[i] : SEPTIC_DIGEST_ZERO[i];   // null: SepticDigest::zero(), as RecursionProgram (crates/recursion/core/src/runtime/program.rs:24-26)
   ZKB_CUDA(cudaStreamSynchronize(L.stream));
   return pk.release();
 }
 
+// CpuProver::commit (crates/stark/src/prover.rs:258-292), pipelined inside the shard.  Every matrix
+// is cut into column PIECES of about ZKB200_PIECE_MB; a piece travels
+//   host rows --(copy stream: 2-D DMA, or the pinned ring for pageable memory)--> row-major stage
+//   --(compute lane)--> transpose into the column-major trace -> coset LDE of its columns
+//   -> (a matrix alone in its height class) absorbed into the per-row sponge states,
+// so the layout change, the LDE and the leaf hashing of piece k run under the upload of piece k+1 and
+// one shard in flight (the reference's GPU options: shard_batch_size = 1, crates/stark/src/opts.rs:83-110)
+// already overlaps PCIe with compute.  What is left after the last piece: the Merkle levels above the leaves.
 Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32* pv, size_t npv) {
   ZKB_CUDA(cudaSetDevice(ctx.device));
+  nvtxRangePushA("commit main traces");
+  struct PopRange { ~PopRange() { nvtxRangePop(); } } pop_range;
   std::unique_ptr<Shard> sh(new Shard());
   sh->ctx = &ctx;
   std::vector<TraceIn> traces = traces_in;
   sort_traces(traces);
   if (traces.empty()) throw std::runtime_error("zkb200: commit: no traces");
-  std::vector<Fp> shifts;
-  for (auto& t : traces) {
+  const unsigned lb = ctx.machine.log_blowup;
+  std::vector<unsigned> logn(traces.size());
+  std::map<unsigned, int> group_size;
+  for (size_t i = 0; i < traces.size(); i++) {
+    const TraceIn& t = traces[i];
     const ChipInfo* c = ctx.machine.find(t.name);
     if (!c) throw std::runtime_error("zkb200: commit: unknown chip " + t.name);
     if (c->main_width != t.width) throw std::runtime_error("zkb200: commit: main width mismatch for " + t.name);
+    check_height(ctx.machine, t.height, logn[i]);
+    group_size[logn[i]]++;
+  }
+  struct Piece {
+    size_t mat, col0, ncols;
+    const u32* src = nullptr; size_t src_pitch = 0;     // row-major device source of the transpose
+    DevBuf stage;
+    cudaEvent_t ready = nullptr;
+    bool last_of_matrix = false;
+  };
+  struct Events {      // RAII: an exception between creation and the end of the call must not leak them
+    std::vector<cudaEvent_t> v;
+    ~Events() { for (auto e : v) cudaEventDestroy(e); }
+  } events;
+  std::vector<Piece> pieces;
+  const size_t piece_bytes = ctx.piece_bytes;
+  for (size_t i = 0; i < traces.size(); i++) {
+    const TraceIn& t = traces[i];
+    if (t.height * t.width == 0) continue;
+    size_t per = piece_bytes / (t.height * sizeof(u32));
+    per = per >= t.width ? t.width : std::max<size_t>(8, per & ~(size_t)7);     // whole rate blocks (hash.cu: leaf_absorb)
+    for (size_t c0 = 0; c0 < t.width; c0 += per) {
+      Piece p;
+      p.mat = i; p.col0 = c0; p.ncols = std::min(per, t.width - c0);
+      p.last_of_matrix = c0 + p.ncols == t.width;
+      pieces.push_back(std::move(p));
+    }
   }
   // Phase 1 (copy stream, its own lock): host->device DMA only, so the copy engine is never held
   // up waiting for SM slots.  Other host threads may hold the compute lanes meanwhile, the way the
   // reference keeps several shards in flight (crates/core/machine/src/utils/prove.rs:487-521).
-  struct Staged { const u32* src; DevBuf stage; };   // src: row-major device pointer to transpose from
-  std::vector<Staged> staged;
-  cudaEvent_t uploaded;
-  ZKB_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
   {
     std::lock_guard<std::mutex> lock(ctx.copy_mu);
-    for (auto& t : traces) {
-      Staged st;
-      st.src = t.data;
-      cudaPointerAttributes attr;
-      bool on_device = false;
-      if (cudaPointerGetAttributes(&attr, t.data) == cudaSuccess) on_device = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
-      else cudaGetLastError();
-      if (!on_device && t.height * t.width) {
-        st.stage = DevBuf(t.height * t.width, ctx.copy_stream);
-        ZKB_CUDA(cudaMemcpyAsync(st.stage.p, t.data, t.height * t.width * sizeof(u32), cudaMemcpyHostToDevice, ctx.copy_stream));
-        st.src = st.stage.p;
+    for (auto& p : pieces) {
+      const TraceIn& t = traces[p.mat];
+      bool pinned = false;
+      if (is_device_pointer(t.data, &pinned)) {
+        p.src = t.data + p.col0; p.src_pitch = t.width;
+        continue;
       }
-      staged.push_back(std::move(st));
+      p.stage = DevBuf(t.height * p.ncols, ctx.copy_stream);
+      if (pinned)
+        ZKB_CUDA(cudaMemcpy2DAsync(p.stage.p, p.ncols * sizeof(u32), t.data + p.col0, t.width * sizeof(u32), p.ncols * sizeof(u32),
+                                   t.height, cudaMemcpyHostToDevice, ctx.copy_stream));
+      else
+        ctx.stager.copy_2d(p.stage.p, t.data + p.col0, p.ncols, t.width, t.height, ctx.copy_stream);
+      p.src = p.stage.p; p.src_pitch = p.ncols;
+      ZKB_CUDA(cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
+      events.v.push_back(p.ready);
+      ZKB_CUDA(cudaEventRecord(p.ready, ctx.copy_stream));
     }
-    ZKB_CUDA(cudaEventRecord(uploaded, ctx.copy_stream));
   }
-  // Phase 2 (a compute lane): layout change, LDE + Merkle tree
+  // Phase 2 (a compute lane): layout change, LDE and leaf hashing piece by piece, then the tree
   LaneGuard guard(ctx);
   Lane& L = *guard.lane;
-  L.arena.reset();
-  if (ctx.profile) ctx.stage_ms.clear();
-  {
-    StageTimer tm(ctx, L, "commit_main_wait_upload_transpose");
-    ZKB_CUDA(cudaStreamWaitEvent(L.stream, uploaded, 0));
-    for (size_t i = 0; i < traces.size(); i++) {
-      const TraceIn& t = traces[i];
-      DevMat m(t.height, t.width, L.stream);
-      if (t.height * t.width) transpose_to_colmajor(staged[i].src, m.d(), t.height, t.width, L.stream);
-      staged[i].stage.stream = L.stream;     // released in lane order, after the transpose
-      staged[i].stage.release();
-      sh->names.push_back(t.name);
-      sh->traces.push_back(std::move(m));
-      shifts.push_back(fp_one());
+  L.begin();
+  if (ctx.profile) { std::lock_guard<std::mutex> lock(ctx.stage_mu); ctx.stage_ms.clear(); }
+  Commit& out = sh->main;
+  for (size_t i = 0; i < traces.size(); i++) {
+    const TraceIn& t = traces[i];
+    sh->names.push_back(t.name);
+    sh->traces.push_back(DevMat(t.height, t.width, L.stream));
+    out.ldes.push_back(DevMat(t.height << lb, t.width, L.stream));
+    out.log_n.push_back(logn[i]);
+  }
+  const Fp shift = fp_from_canonical(KB_GEN);     // trace domains are the subgroups themselves
+  std::map<unsigned, DevBuf> sponge_state, digests;
+  std::map<unsigned, const u32*> pre;
+  for (auto& p : pieces) {
+    const TraceIn& t = traces[p.mat];
+    const size_t n = t.height, H = n << lb;
+    u32* cols = sh->traces[p.mat].d() + p.col0 * n;
+    u32* lde_cols = out.ldes[p.mat].d() + p.col0 * H;
+    {
+      StageTimer tm(ctx, L, "commit_main_wait_upload_transpose");
+      if (p.ready) ZKB_CUDA(cudaStreamWaitEvent(L.stream, p.ready, 0));
+      transpose_piece_to_colmajor(p.src, p.src_pitch, cols, n, p.ncols, L.stream);
+      p.stage.stream = L.stream;     // released in lane order, after the transpose
+      p.stage.release();
+    }
+    {
+      StageTimer tm(ctx, L, "commit_main_lde");
+      coset_lde_batch(ctx.tables, cols, n, lde_cols, H, logn[p.mat], p.ncols, lb, shift, L.stream, L.keep);
+    }
+    // leaf hashing under the upload: a matrix that is alone in its height class and comes in pieces
+    const unsigned lh = logn[p.mat] + lb;
+    const bool piecewise = group_size[logn[p.mat]] == 1 && !(p.col0 == 0 && p.last_of_matrix);
+    if (piecewise) {
+      StageTimer tm(ctx, L, "commit_main_merkle");
+      if (p.col0 == 0) { sponge_state[lh] = DevBuf(16 * H, L.stream); digests[lh] = DevBuf(8 * H, L.stream); }
+      leaf_absorb(lde_cols, H, (u32)p.ncols, sponge_state[lh].p, p.col0 == 0, p.last_of_matrix, digests[lh].p, L.stream);
+      if (p.last_of_matrix) pre[lh] = digests[lh].p;
     }
   }
-  cudaEventDestroy(uploaded);
-  pcs_commit(ctx, L, sh->traces, shifts, sh->main, "commit_main_lde", "commit_main_merkle");
+  pcs_merkle(ctx, L, out, &pre, "commit_main_merkle");
   sh->public_values.assign(pv, pv + npv);
   return sh.release();
 }
@@ -272,7 +451,7 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
   ZKB_CUDA(cudaSetDevice(ctx.device));
   LaneGuard guard(ctx);
   Lane& L = *guard.lane;
-  L.arena.reset();
+  L.begin();
   cudaStream_t s = L.stream;
   const MachineInfo& M = ctx.machine;
   const unsigned lb = M.log_blowup;
@@ -325,7 +504,10 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
     for (size_t i = 0; i < nc; i++) {
       const u32* w = L.h_small + i * 18;   // canonical
       for (int c = 0; c < 4; c++) local_sums[i].c[c] = fp_from_canonical(w[c]);
-      for (int k = 0; k < 14; k++) global_sums[i][k] = fp_from_canonical(w[4 + k]).v;
+      // a Local-scope chip carries SepticDigest::zero(), which is the curve's START point and not
+      // 14 zeros (crates/stark/src/septic_digest.rs:9-42, prover.rs:352; checked by verifier.rs:102)
+      for (int k = 0; k < 14; k++)
+        global_sums[i][k] = fp_from_canonical(chips[i]->global_scope ? w[4 + k] : SEPTIC_DIGEST_ZERO[k]).v;
     }
   }
   Commit perm_commit;

@@ -3,8 +3,11 @@
 // :258-292 commit, :298-653 open) and of StarkMachine::setup (crates/stark/src/machine.rs:352-459).
 #pragma once
 #include "lane_pool.h"
+#include <condition_variable>
+#include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "common.h"
 #include "fri.h"
@@ -34,8 +37,35 @@ struct Lane {
   u32* d_small = nullptr;            // small device scratch (roots, sums)
   u32* h_small = nullptr;            // pinned mirror
   std::mutex mu;
+  KeepAlive keep;                    // shared tables the queued kernels read (ntt.h)
+  // start of a call that owns the lane: the previous call drained the stream before it returned
+  void begin() { arena.reset(); keep.clear(); }
 };
 constexpr int NUM_LANES = 4;
+
+// Pageable host memory -> device through a ring of pinned slots filled by a few host threads
+// (prover.cu).  Lazily allocated: a caller that hands over pinned or device memory never pays for it.
+struct HostStager {
+  int nslots = 4, nthreads = 8;
+  size_t slot_bytes = (size_t)32 << 20;
+  std::vector<u32*> slots;
+  std::vector<cudaEvent_t> free_ev;
+  int next_slot = 0;
+  std::mutex use_mu;
+  struct Job { u32* dst; const u32* src; size_t row_words, src_pitch, rows; };
+  std::vector<std::thread> workers;
+  std::mutex m;
+  std::condition_variable cv, cv_done;
+  Job job{};
+  unsigned long long job_id = 0;
+  int done = 0;
+  bool stop = false;
+  void init(int nslots, size_t slot_bytes, int nthreads);
+  void ensure();
+  void destroy();
+  void worker(int t);
+  void copy_2d(u32* dst, const u32* src, size_t row_words, size_t src_pitch, size_t rows, cudaStream_t s);
+};
 
 struct Ctx {
   int device = 0;
@@ -43,12 +73,15 @@ struct Ctx {
   int active_lanes = 3;                 // ZKB200_LANES=1 serialises all compute on one stream
   cudaStream_t copy_stream = nullptr;   // host->device uploads + layout change, overlaps the compute lanes
   std::mutex copy_mu;
+  HostStager stager;                    // pageable host sources
+  size_t piece_bytes = (size_t)256 << 20;   // column pieces of the main commit (prover_commit)
   LanePool<NUM_LANES> pool;             // which lane a commit/open call runs on
   MachineInfo machine;
   NttTables tables;
   // statistics of the last open(): kernel-stage timings (ms) when profiling is enabled
   bool profile = false;
   std::vector<std::pair<std::string, float>> stage_ms;
+  std::mutex stage_mu;                  // stage_ms is appended to from every lane
   unsigned long long launches = 0;
 
   void init(int device, const u32* desc, size_t n);

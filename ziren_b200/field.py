@@ -44,3 +44,8 @@ def sub(a, b) -> np.ndarray:
 
 def random_elements(rng: np.random.Generator, shape) -> np.ndarray:
     return rng.integers(0, P, size=shape, dtype=np.uint32)
+
+
+# SepticDigest::zero(): CURVE_CUMULATIVE_SUM_START_X ++ _Y (canonical), crates/stark/src/septic_digest.rs:9-14.
+# The global cumulative sum of every Local-scope chip and of a program without initial memory.
+SEPTIC_DIGEST_ZERO = np.array([637514027, 1595065213, 1998064738, 72333738, 1211544370, 822986770, 1518535784, 1604177449, 90440090, 259343427, 140470264, 1162099742, 941559812, 1064053343], dtype=np.uint32)

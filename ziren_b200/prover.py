@@ -13,6 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import _ffi
+from . import field as kb
 from .air import Machine
 
 u32p = _ffi.u32p
@@ -134,7 +135,7 @@ class B200Prover:
     def setup(self, preprocessed: dict, pc_start: int = 0, initial_global_cumulative_sum=None) -> ProvingKey:
         """`setup` + `pk_to_device` (prover.rs:49-63): commit preprocessed traces on the GPU."""
         arr, keep = self._traces(preprocessed)
-        gs = _np32(initial_global_cumulative_sum) if initial_global_cumulative_sum is not None else np.zeros(14, np.uint32)
+        gs = _np32(initial_global_cumulative_sum) if initial_global_cumulative_sum is not None else kb.SEPTIC_DIGEST_ZERO.copy()
         commit = np.zeros(8, np.uint32)
         h = C.c_void_p()
         self._check(_ffi.lib().zkb200_setup(self._h, arr, len(preprocessed), pc_start, _p(gs), _p(commit), C.byref(h)))
