@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--sample-log-cpu", type=int, default=14, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host e2e figure")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle verifier's check of the timed proof")
     ap.add_argument("--value-threads", type=int, default=3,
                     help="host threads proving device-resident shards concurrently in the `value` arm (compute lanes)")
@@ -257,8 +258,19 @@ def main():
     launches = prover.launch_count() - launches0
     timed(host_tr, max(args.warmup, args.e2e_threads), args.e2e_threads)      # warm the staging/pool paths of the e2e arm
     ms_e2e, proof2 = timed(host_tr, args.steps, args.e2e_threads)
+    # one shard in flight: what the reference's own GPU options ask for (shard_batch_size = 1,
+    # crates/stark/src/opts.rs:83-110) - upload, layout change, LDE and leaf hashing overlap INSIDE the shard
+    ms_e2e_1, proof3 = timed(host_tr, args.steps, 1)
     clocks = sampler.stop()
-    assert np.array_equal(proof, proof2)
+    assert np.array_equal(proof, proof2) and np.array_equal(proof, proof3)
+    # pageable host memory (what RowMajorMatrix.values is, prover.rs:258-262): staged through the pinned ring
+    ms_e2e_pageable = None
+    if args.world == 1 and not args.no_pageable:
+        pageable = {k: np.array(v.numpy(), copy=True) for k, v in host_tr.items()}
+        timed(pageable, 1, 1)
+        ms_e2e_pageable, proof4 = timed(pageable, max(2, args.steps // 3), 1)
+        assert np.array_equal(proof, proof4)
+        del pageable
     d2h_bytes = int(proof.size) * 4
 
     # the proof that was timed is checked: the oracle's verifier (restated from crates/stark/src/verifier.rs
@@ -308,7 +320,10 @@ def main():
                 "config": cfg,
                 "e2e": {"value": total_cycles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
-                        "host_threads_in_flight": args.e2e_threads},
+                        "host_threads_in_flight": args.e2e_threads,
+                        "one_shard_in_flight": {"value": total_cycles / (ms_e2e_1 / 1e3), "ms_per_step": ms_e2e_1 / args.steps},
+                        "pageable_host_one_shard_in_flight": None if ms_e2e_pageable is None else
+                        {"value": case.cycles * max(2, args.steps // 3) / (ms_e2e_pageable / 1e3), "ms_per_step": ms_e2e_pageable / max(2, args.steps // 3)}},
                 "verified": verified, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other,
                 "cpu_baseline": cpu_base,
                 "stage_ms": stages, "cells_per_sec": cells * args.steps * args.gpus / (ms_dev / 1e3)}

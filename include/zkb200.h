@@ -73,6 +73,19 @@ typedef struct {
 
 /* MachineProver::new(machine) — crates/stark/src/prover.rs:43.  `desc` is a ZKMD descriptor. */
 int zkb200_ctx_create(int device, const uint32_t* desc, size_t n_words, zkb200_ctx** out);
+/* One prover object over several GPUs of the node (n_devices <= 0, or device = -1 above: every visible
+ * GPU).  prove_with_context hands ONE MachineProver to all its worker threads
+ * (crates/core/machine/src/utils/prove.rs:487-521): zkb200_commit routes each shard to the device with
+ * the fewest shards in flight (or to the device that already holds device-resident traces),
+ * zkb200_open follows the shard, zkb200_setup replicates the proving key on every device. */
+int zkb200_ctx_create_multi(const int* devices, int n_devices, const uint32_t* desc, size_t n_words, zkb200_ctx** out);
+int zkb200_ctx_num_devices(const zkb200_ctx* ctx);
+/* process-wide experiment knobs used by tools/ (A/B timing inside one process): "ntt_k2" (size of the
+ * contiguous NTT level, 0 = built-in), "eval_v2" (0/1, -1 = default). */
+int zkb200_set_option(const char* key, long value);
+/* tools/h2d_probe.py: time one pass of a pinned row-major `rows x row_bytes` buffer over PCIe.  mode 0: 2-D DMA
+ * in column slices of seg_bytes over n concurrent streams; 1: the pull kernel with n CTAs; 2: contiguous DMA in n parts. */
+int zkb200_h2d_probe(zkb200_ctx* ctx, int mode, size_t row_bytes, size_t rows, size_t seg_bytes, int n, float* ms_out);
 void zkb200_ctx_destroy(zkb200_ctx* ctx);
 /* error text of the last failed call made by the calling host thread (ctx may be NULL) */
 const char* zkb200_last_error(zkb200_ctx* ctx);
@@ -92,6 +105,7 @@ int zkb200_pk_initial_challenger(const zkb200_pk* pk, uint32_t challenger[34]);
 int zkb200_commit(zkb200_ctx* ctx, const zkb200_trace* traces, int n, const uint32_t* public_values,
                   size_t n_public_values, uint32_t commit_out[8], zkb200_shard** out);
 void zkb200_shard_free(zkb200_shard* shard);
+int zkb200_shard_device(const zkb200_shard* shard);   /* CUDA device the shard was committed on */
 
 /* MachineProver::open — prover.rs:298-653.  `challenger` (in/out) is the per-shard clone of the
  * post-observe_into challenger.  The proof buffer is malloc'ed; release with zkb200_free. */

@@ -450,3 +450,39 @@ def test_piecewise_commit_matches_oracle(torch, oracle, monkeypatch):
         assert np.array_equal(got, want), name
     pk.free()
     prover.close()
+
+
+def test_multi_device_prover_routes_shards(torch, oracle):
+    """One prover object over every visible GPU (zkb200_ctx_create_multi): shards committed from
+    several host threads are spread over the devices, every proof equals the single-GPU proof.
+    On a one-GPU box the same object degenerates to one device."""
+    import threading
+    from ziren_b200.prover import B200Prover
+    cases = [synthetic.mini_case(seed=60 + i) for i in range(6)]
+    single = B200Prover(cases[0].machine, device=0)
+    pk1 = single.setup({k: kb.to_monty(v) for k, v in cases[0].prep.items()})
+    want = [single.prove_shard(pk1, {k: kb.to_monty(v) for k, v in c.traces.items()}, c.public_values)[0] for c in cases]
+    pk1.free()
+    single.close()
+    multi = B200Prover(cases[0].machine, device=-1)
+    assert multi.num_devices() == torch.cuda.device_count()
+    pk = multi.setup({k: kb.to_monty(v) for k, v in cases[0].prep.items()})
+    got, devices = [None] * len(cases), [None] * len(cases)
+    gate = threading.Barrier(len(cases))
+
+    def work(i):
+        c = cases[i]
+        data = multi.commit({k: kb.to_monty(v) for k, v in c.traces.items()}, c.public_values)
+        devices[i] = data.device()
+        gate.wait()                      # all shards are in flight before the first one is released
+        got[i], _ = multi.open(pk, data)
+        data.free()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    if multi.num_devices() > 1:
+        assert len(set(devices)) == min(multi.num_devices(), len(cases)), devices
+    pk.free()
+    multi.close()

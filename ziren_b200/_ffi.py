@@ -27,6 +27,10 @@ _lib = None
 # name -> (restype, argtypes): every symbol include/zkb200.h declares
 SIGNATURES = {
     "zkb200_ctx_create": (C.c_int, [C.c_int, u32p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "zkb200_ctx_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, u32p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "zkb200_ctx_num_devices": (C.c_int, [C.c_void_p]),
+    "zkb200_set_option": (C.c_int, [C.c_char_p, C.c_long]),
+    "zkb200_h2d_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_float)]),
     "zkb200_ctx_destroy": (None, [C.c_void_p]),
     "zkb200_last_error": (C.c_char_p, [C.c_void_p]),
     "zkb200_ctx_stream": (C.c_void_p, [C.c_void_p]),
@@ -35,6 +39,7 @@ SIGNATURES = {
     "zkb200_pk_initial_challenger": (C.c_int, [C.c_void_p, u32p]),
     "zkb200_commit": (C.c_int, [C.c_void_p, C.POINTER(Trace), C.c_int, u32p, C.c_size_t, u32p, C.POINTER(C.c_void_p)]),
     "zkb200_shard_free": (None, [C.c_void_p]),
+    "zkb200_shard_device": (C.c_int, [C.c_void_p]),
     "zkb200_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, u32p, C.POINTER(u32p), C.POINTER(C.c_size_t)]),
     "zkb200_prove_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Trace), C.c_int, u32p, C.c_size_t, u32p,
                                      C.POINTER(u32p), C.POINTER(C.c_size_t)]),

@@ -1,6 +1,7 @@
 // extern "C" surface of libzkb200.so — see include/zkb200.h for the contract.
 #include "../../include/zkb200.h"
 #include <cstdlib>
+#include <memory>
 #include "layout.h"
 #include "logup.h"
 #include "open.h"
@@ -9,10 +10,40 @@
 #include "tracegen.h"
 
 using namespace zkb;
+namespace zkb { extern std::atomic<int> g_ntt_force_k2; extern std::atomic<int> g_eval_v2; extern std::atomic<int> g_ntt_lean; }
 
-struct zkb200_ctx { Ctx c; };
-struct zkb200_pk { Pk* p; };
-struct zkb200_shard { Shard* s; };
+// One prover object over one or several GPUs.  `c` (= *devs[0]) serves the kernel-level entry points;
+// commit routes every shard to the device with the fewest shards in flight, open follows the shard,
+// the proving key is replicated per device at setup - the object prove_with_context's worker threads
+// can share (crates/core/machine/src/utils/prove.rs:487-521 calls ONE prover from all of them).
+struct zkb200_ctx {
+  std::vector<std::unique_ptr<Ctx>> devs;
+  std::unique_ptr<std::atomic<int>[]> inflight;
+  Ctx& c;
+  explicit zkb200_ctx(std::vector<std::unique_ptr<Ctx>>&& d)
+      : devs(std::move(d)), inflight(new std::atomic<int>[devs.size()]), c(*devs[0]) {
+    for (size_t i = 0; i < devs.size(); i++) inflight[i] = 0;
+  }
+  int index_of_device(int device) const {
+    for (size_t i = 0; i < devs.size(); i++) if (devs[i]->device == device) return (int)i;
+    return -1;
+  }
+  // the device that already holds the (device-resident) traces, else the least loaded one
+  int pick(const zkb200_trace* t, int n) const {
+    for (int i = 0; i < n; i++) {
+      cudaPointerAttributes attr;
+      if (t[i].data && cudaPointerGetAttributes(&attr, t[i].data) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+        int k = index_of_device(attr.device);
+        if (k >= 0) return k;
+      } else cudaGetLastError();
+    }
+    int best = 0;
+    for (size_t i = 1; i < devs.size(); i++) if (inflight[i].load() < inflight[best].load()) best = (int)i;
+    return best;
+  }
+};
+struct zkb200_pk { std::vector<Pk*> per_dev; Pk* p; };      // p = per_dev[0]
+struct zkb200_shard { Shard* s; zkb200_ctx* owner; int dev; };
 
 // MachineProver::Error text of the last failed call made by THIS host thread
 static thread_local std::string g_err;
@@ -27,7 +58,7 @@ static int guarded(zkb200_ctx* ctx, F&& f) {
     cudaGetLastError();
     // error path only: kernels of the failed call may still be queued on a lane and read buffers the
     // caller is about to release (stream-ordered frees on another stream) - drain the device first
-    if (ctx) { cudaSetDevice(ctx->c.device); cudaDeviceSynchronize(); cudaGetLastError(); }
+    if (ctx) for (auto& d : ctx->devs) { cudaSetDevice(d->device); cudaDeviceSynchronize(); cudaGetLastError(); }
     return 1;
   }
 }
@@ -41,17 +72,37 @@ static Ef ef_from_canon(const uint32_t* w) { Ef e; for (int i = 0; i < 4; i++) e
 
 extern "C" {
 
-int zkb200_ctx_create(int device, const uint32_t* desc, size_t n_words, zkb200_ctx** out) {
+int zkb200_ctx_create_multi(const int* devices, int n_devices, const uint32_t* desc, size_t n_words, zkb200_ctx** out) {
   *out = nullptr;
-  zkb200_ctx* ctx = new zkb200_ctx();
-  int rc = guarded(nullptr, [&] { ctx->c.init(device, desc, n_words); });
-  if (rc) { delete ctx; return rc; }
-  *out = ctx;
+  std::vector<std::unique_ptr<Ctx>> devs;
+  int rc = guarded(nullptr, [&] {
+    std::vector<int> ids;
+    if (n_devices <= 0) {
+      int count = 0;
+      ZKB_CUDA(cudaGetDeviceCount(&count));
+      for (int i = 0; i < count; i++) ids.push_back(i);
+    } else ids.assign(devices, devices + n_devices);
+    if (ids.empty()) throw std::runtime_error("zkb200: no CUDA device");
+    for (int id : ids) {
+      devs.emplace_back(new Ctx());
+      devs.back()->init(id, desc, n_words);
+    }
+  });
+  if (rc) {
+    for (auto& d : devs) d->destroy();
+    return rc;
+  }
+  *out = new zkb200_ctx(std::move(devs));
   return 0;
 }
+int zkb200_ctx_create(int device, const uint32_t* desc, size_t n_words, zkb200_ctx** out) {
+  if (device < 0) return zkb200_ctx_create_multi(nullptr, 0, desc, n_words, out);     // every visible GPU
+  return zkb200_ctx_create_multi(&device, 1, desc, n_words, out);
+}
+int zkb200_ctx_num_devices(const zkb200_ctx* ctx) { return (int)ctx->devs.size(); }
 void zkb200_ctx_destroy(zkb200_ctx* ctx) {
   if (!ctx) return;
-  ctx->c.destroy();
+  for (auto& d : ctx->devs) d->destroy();
   delete ctx;
 }
 const char* zkb200_last_error(zkb200_ctx* ctx) { (void)ctx; return g_err.c_str(); }
@@ -60,14 +111,23 @@ void* zkb200_ctx_stream(zkb200_ctx* ctx) { return (void*)ctx->c.lanes[0].stream;
 int zkb200_setup(zkb200_ctx* ctx, const zkb200_trace* prep, int n, uint32_t pc_start, const uint32_t* init_global_sum,
                  uint32_t commit_out[8], zkb200_pk** out) {
   return guarded(ctx, [&] {
-    Pk* pk = prover_setup(ctx->c, to_traces(prep, n), pc_start, init_global_sum);
-    if (commit_out) memcpy(commit_out, pk->commit_canon, 32);
-    *out = new zkb200_pk{pk};
+    std::unique_ptr<zkb200_pk> pk(new zkb200_pk{{}, nullptr});
+    try {
+      for (auto& d : ctx->devs) pk->per_dev.push_back(prover_setup(*d, to_traces(prep, n), pc_start, init_global_sum));
+    } catch (...) {
+      for (Pk* q : pk->per_dev) { cudaSetDevice(q->ctx->device); delete q; }
+      throw;
+    }
+    pk->p = pk->per_dev[0];
+    for (Pk* q : pk->per_dev)
+      if (memcmp(q->commit_canon, pk->p->commit_canon, 32) != 0) throw std::runtime_error("zkb200: setup: devices disagree on the preprocessed commitment");
+    if (commit_out) memcpy(commit_out, pk->p->commit_canon, 32);
+    *out = pk.release();
   });
 }
 void zkb200_pk_free(zkb200_pk* pk) {
   if (!pk) return;
-  if (pk->p) { cudaSetDevice(pk->p->ctx->device); delete pk->p; }
+  for (Pk* q : pk->per_dev) { cudaSetDevice(q->ctx->device); delete q; }
   delete pk;
 }
 int zkb200_pk_initial_challenger(const zkb200_pk* pk, uint32_t challenger[34]) {
@@ -83,21 +143,32 @@ int zkb200_pk_initial_challenger(const zkb200_pk* pk, uint32_t challenger[34]) {
 int zkb200_commit(zkb200_ctx* ctx, const zkb200_trace* traces, int n, const uint32_t* pv, size_t npv, uint32_t commit_out[8],
                   zkb200_shard** out) {
   return guarded(ctx, [&] {
-    Shard* s = prover_commit(ctx->c, to_traces(traces, n), pv, npv);
+    const int k = ctx->pick(traces, n);
+    ctx->inflight[k]++;
+    Shard* s = nullptr;
+    try {
+      s = prover_commit(*ctx->devs[k], to_traces(traces, n), pv, npv);
+    } catch (...) {
+      ctx->inflight[k]--;
+      throw;
+    }
     if (commit_out) for (int i = 0; i < 8; i++) commit_out[i] = fp_to_canonical(fp_raw(s->main.root[i]));
-    *out = new zkb200_shard{s};
+    *out = new zkb200_shard{s, ctx, k};
   });
 }
+int zkb200_shard_device(const zkb200_shard* sh) { return sh->s->ctx->device; }
 void zkb200_shard_free(zkb200_shard* sh) {
   if (!sh) return;
   if (sh->s) { cudaSetDevice(sh->s->ctx->device); delete sh->s; }
+  if (sh->owner) sh->owner->inflight[sh->dev]--;
   delete sh;
 }
 
 int zkb200_open(zkb200_ctx* ctx, const zkb200_pk* pk, zkb200_shard* shard, uint32_t challenger[34], uint32_t** proof_words,
                 size_t* n_words) {
   return guarded(ctx, [&] {
-    std::vector<u32> w = prover_open(ctx->c, *pk->p, *shard->s, challenger);
+    if (shard->owner != ctx || pk->per_dev.size() != ctx->devs.size()) throw std::runtime_error("zkb200: open: shard / proving key belong to another context");
+    std::vector<u32> w = prover_open(*ctx->devs[shard->dev], *pk->per_dev[shard->dev], *shard->s, challenger);
     *proof_words = (uint32_t*)malloc(w.size() * 4);
     memcpy(*proof_words, w.data(), w.size() * 4);
     *n_words = w.size();
@@ -114,7 +185,7 @@ int zkb200_prove_shard(zkb200_ctx* ctx, const zkb200_pk* pk, const zkb200_trace*
 }
 void zkb200_free(void* p) { free(p); }
 
-void zkb200_set_profile(zkb200_ctx* ctx, int on) { ctx->c.profile = on != 0; }
+void zkb200_set_profile(zkb200_ctx* ctx, int on) { for (auto& d : ctx->devs) d->profile = on != 0; }
 unsigned long long zkb200_launch_count(void) { return g_kernel_launches.load(); }
 int zkb200_last_stage_times(zkb200_ctx* ctx, const char** names, float* ms, int cap) {
   int n = (int)ctx->c.stage_ms.size();
@@ -272,8 +343,77 @@ int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* eve
     ZKB_CUDA(cudaStreamSynchronize(s));
   });
 }
+// tools/h2d_probe.py: how fast do column slices of a pinned row-major matrix cross PCIe?
+//   mode 0: 2-D DMA (cudaMemcpy2DAsync) of `seg_bytes`-wide slices, `nstreams` copies in flight
+//   mode 1: the pull kernel (SM-initiated reads of mapped memory), `nstreams` = CTAs
+//   mode 2: contiguous DMA of the whole buffer in `nstreams` concurrent parts
+int zkb200_h2d_probe(zkb200_ctx* ctx, int mode, size_t row_bytes, size_t rows, size_t seg_bytes, int nstreams, float* ms_out) {
+  return guarded(ctx, [&] {
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    const size_t total = row_bytes * rows;
+    static u32* host = nullptr; static size_t host_cap = 0;
+    if (host_cap < total) { if (host) cudaFreeHost(host); ZKB_CUDA(cudaMallocHost((void**)&host, total)); host_cap = total; memset(host, 1, total); }
+    u32* dev = nullptr;
+    ZKB_CUDA(cudaMalloc((void**)&dev, total));
+    std::vector<cudaStream_t> st(std::max(1, nstreams));
+    if (mode != 1) for (auto& s : st) ZKB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    ZKB_CUDA(cudaEventCreate(&e0)); ZKB_CUDA(cudaEventCreate(&e1));
+    ZKB_CUDA(cudaDeviceSynchronize());
+    cudaStream_t main_s = ctx->c.lanes[0].stream;
+    ZKB_CUDA(cudaEventRecord(e0, main_s));
+    if (mode == 1) {
+      PullPiece pp;
+      pp.base = host; pp.word_off = 0; pp.pitch = row_bytes / 4; pp.dst = dev; pp.rows = rows; pp.cols = row_bytes / 4;
+      pp.col_tiles = pull_piece_col_tiles(pp.cols); pp.tile_begin = 0;
+      u32* work = nullptr;
+      ZKB_CUDA(cudaMalloc((void**)&work, sizeof(PullPiece) + 256));
+      ZKB_CUDA(cudaMemcpy(work, &pp, sizeof(PullPiece), cudaMemcpyHostToDevice));
+      ZKB_CUDA(cudaMemset((char*)work + sizeof(PullPiece), 0, 4));
+      ZKB_CUDA(cudaEventRecord(e0, main_s));
+      pull_shard(reinterpret_cast<const PullPiece*>(work), 1, pull_piece_tiles(rows, pp.cols), (u32*)((char*)work + sizeof(PullPiece)), nstreams, main_s);
+      ZKB_CUDA(cudaEventRecord(e1, main_s)); ZKB_CUDA(cudaEventSynchronize(e1));
+      cudaFree(work);
+    } else {
+      std::vector<cudaEvent_t> done(st.size());
+      for (size_t i = 0; i < st.size(); i++) { ZKB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)); ZKB_CUDA(cudaStreamWaitEvent(st[i], e0, 0)); }
+      if (mode == 0) {
+        size_t k = 0;
+        for (size_t c0 = 0; c0 < row_bytes; c0 += seg_bytes, k++) {
+          const size_t w = std::min(seg_bytes, row_bytes - c0);
+          ZKB_CUDA(cudaMemcpy2DAsync((char*)dev + c0 * rows, w, (char*)host + c0, row_bytes, w, rows, cudaMemcpyHostToDevice, st[k % st.size()]));
+        }
+      } else {
+        const size_t part = (total / st.size() + 255) & ~(size_t)255;
+        for (size_t i = 0; i < st.size(); i++) {
+          const size_t off = i * part, len = off < total ? std::min(part, total - off) : 0;
+          if (len) ZKB_CUDA(cudaMemcpyAsync((char*)dev + off, (char*)host + off, len, cudaMemcpyHostToDevice, st[i]));
+        }
+      }
+      for (size_t i = 0; i < st.size(); i++) { ZKB_CUDA(cudaEventRecord(done[i], st[i])); ZKB_CUDA(cudaStreamWaitEvent(main_s, done[i], 0)); }
+      ZKB_CUDA(cudaEventRecord(e1, main_s));
+      ZKB_CUDA(cudaEventSynchronize(e1));
+      for (auto e : done) cudaEventDestroy(e);
+    }
+    ZKB_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
+    if (mode != 1) for (auto& s : st) cudaStreamDestroy(s);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dev);
+  });
+}
+int zkb200_set_option(const char* key, long value) {
+  const std::string k(key ? key : "");
+  if (k == "ntt_k2") { g_ntt_force_k2 = (int)value; return 0; }
+  if (k == "eval_v2") { g_eval_v2 = (int)value; return 0; }
+  if (k == "ntt_lean") { g_ntt_lean = (int)value; return 0; }
+  g_err = "zkb200: unknown option " + k;
+  return 1;
+}
 int zkb200_sync(zkb200_ctx* ctx) {
-  return guarded(ctx, [&] { ZKB_CUDA(cudaSetDevice(ctx->c.device)); ZKB_CUDA(cudaDeviceSynchronize()); });
+  return guarded(ctx, [&] {
+    for (auto& d : ctx->devs) { ZKB_CUDA(cudaSetDevice(d->device)); ZKB_CUDA(cudaDeviceSynchronize()); }
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+  });
 }
 
 }  // extern "C"

@@ -1,4 +1,5 @@
 #include "layout.h"
+#include <algorithm>
 
 namespace zkb {
 
@@ -28,6 +29,75 @@ static void transpose(const u32* in, size_t in_pitch, u32* out, size_t rows, siz
 void transpose_to_colmajor(const u32* in, u32* out, size_t h, size_t w, cudaStream_t s) { transpose(in, w, out, h, w, s); }
 void transpose_to_rowmajor(const u32* in, u32* out, size_t h, size_t w, cudaStream_t s) { transpose(in, h, out, w, h, s); }
 void transpose_piece_to_colmajor(const u32* in, size_t in_pitch, u32* out, size_t h, size_t w, cudaStream_t s) { transpose(in, in_pitch, out, h, w, s); }
+
+// ---- upload fused with the layout change ("pull") ------------------------------------------------
+// The row-major host matrices lie in PINNED, device-mapped memory: ONE persistent kernel per shard reads
+// them over PCIe itself, column piece by column piece, transposes tiles in shared memory, writes the
+// column-major device traces and bumps a per-piece counter that the compute lane waits on
+// (cuStreamWaitValue32).  No staging buffer, no second pass over HBM, and a column piece costs no more
+// than a whole matrix.  Measured on a B200 (tools/h2d_probe.py): 51 GB/s against 55.6 GB/s for a
+// contiguous DMA; a 2-D DMA of column slices is SM-driven as well and loses its SM slots to the compute
+// lanes.  The kernel takes its few CTAs once (high-priority stream) and keeps them for the whole upload:
+// 52 GB/s x ~2 us of latency is only ~100 KB in flight.
+// Rows of odd width are not 128-byte aligned: every warp loads the ALIGNED 128-byte lines that cover its
+// row segment (one extra line per 256 columns) instead of straddling two lines with every request.
+constexpr int PULL_TR = 32, PULL_TC = 256, PULL_LINES = PULL_TC / 32 + 1, PULL_THREADS = 256;
+__global__ void __launch_bounds__(PULL_THREADS) pull_shard_kernel(const PullPiece* __restrict__ pieces, int npieces,
+                                                                 unsigned long long total_tiles, u32* __restrict__ done) {
+  __shared__ u32 tile[PULL_TC][PULL_TR + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int pi = 0;
+  for (unsigned long long tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+    while (pi + 1 < npieces && tix >= pieces[pi + 1].tile_begin) pi++;
+    const PullPiece p = pieces[pi];
+    const unsigned long long local = tix - p.tile_begin;
+    const size_t c0 = (size_t)(local % p.col_tiles) * PULL_TC, r0 = (size_t)(local / p.col_tiles) * PULL_TR;
+    const size_t ncols = p.cols - c0 < (size_t)PULL_TC ? p.cols - c0 : (size_t)PULL_TC;
+    // 8 warps x 4 rows x 9 aligned lines: 36 independent loads per thread
+    u32 v[4][PULL_LINES];
+    long long first[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const size_t r = r0 + warp * 4 + k;
+      const size_t g0 = r * p.pitch + p.word_off + c0;       // word index of (r, c0) from the 128-byte aligned base
+      const size_t a0 = g0 & ~(size_t)31;
+      first[k] = (long long)a0 - (long long)g0;             // column (relative to c0) of the line's first word: -31 .. 0
+#pragma unroll
+      for (int j = 0; j < PULL_LINES; j++) {
+        const long long cc = first[k] + 32 * j + lane;
+        v[k][j] = (r < p.rows && cc >= 0 && cc < (long long)ncols) ? __ldcs(p.base + a0 + 32 * j + lane) : 0u;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int j = 0; j < PULL_LINES; j++) {
+        const long long cc = first[k] + 32 * j + lane;
+        if (cc >= 0 && cc < (long long)PULL_TC) tile[cc][warp * 4 + k] = v[k][j];
+      }
+    __syncthreads();
+    // columns leave as 128-byte runs of 32 rows
+    for (int cc = warp; cc < (int)ncols; cc += PULL_THREADS / 32) {
+      const size_t r = r0 + lane;
+      if (r < p.rows) p.dst[(c0 + cc) * p.rows + r] = tile[cc][lane];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(done + pi, 1u);
+    }
+  }
+}
+unsigned long long pull_piece_tiles(size_t rows, size_t cols) {
+  return (unsigned long long)((cols + PULL_TC - 1) / PULL_TC) * ((rows + PULL_TR - 1) / PULL_TR);
+}
+unsigned pull_piece_col_tiles(size_t cols) { return (unsigned)((cols + PULL_TC - 1) / PULL_TC); }
+void pull_shard(const PullPiece* pieces_dev, int npieces, unsigned long long total_tiles, u32* done, int ctas, cudaStream_t s) {
+  if (!npieces || !total_tiles) return;
+  const unsigned grid = (unsigned)std::min<unsigned long long>(total_tiles, (unsigned long long)std::max(1, ctas));
+  pull_shard_kernel<<<grid, PULL_THREADS, 0, s>>>(pieces_dev, npieces, total_tiles, done);
+  ZKB_CHECK_LAUNCH();
+}
 
 __global__ void to_monty_kernel(u32* d, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

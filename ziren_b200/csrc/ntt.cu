@@ -15,6 +15,7 @@
 // (2^26 elements) that keep every launch several waves deep rather than L2-sized ones.
 #include "ntt.h"
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 namespace zkb {
@@ -27,6 +28,8 @@ static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+// run-time experiment knobs (zkb200_set_option): 0 = built-in choice
+std::atomic<int> g_ntt_force_k2{0};
 
 __global__ void tw_init_kernel(u32* lo, u32* hi) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,7 +224,6 @@ struct StridedArgs {
                                      // 1: DIT (pre-twiddle) storing bit-reversed positions
   size_t out_coset_stride;           // final_dit: blockIdx.z selects the coset block of in/out
   size_t in_coset_stride;
-  int pre_twiddled;                  // final_dit: the producer already applied the four-step twiddles (ZKB200_NTT_PRETWIDDLE)
 };
 
 // LT >= 0: tile width 2^LT known at compile time (the launcher's default for this K), which folds the
@@ -248,7 +250,7 @@ __device__ __forceinline__ void strided_body(const StridedArgs& a, u32* smem) {
     const u32 row = FINAL ? bitrev32(slot, K) : slot;
     const size_t pos = ((size_t)row << logS) + t0 + q;
     const u32 v = in[pos];
-    return (FINAL && !a.pre_twiddled) ? shoup_mul(v, __ldg(four + pos)) : fp_raw(v);
+    return FINAL ? shoup_mul(v, __ldg(four + pos)) : fp_raw(v);
   };
   auto gstore = [&](u32 slot, u32 q, Fp v) {      // DIF only: post-twiddle, in-place position
     const size_t pos = ((size_t)slot << logS) + t0 + q;
@@ -299,6 +301,10 @@ __global__ void __launch_bounds__(1024, 1) ntt_strided_kernel(StridedArgs a) {
 static constexpr int STRIDED_TILE_LOG = 13;
 __host__ __device__ constexpr int strided_default_lt(int K) { return STRIDED_TILE_LOG - K > 5 ? 5 : (STRIDED_TILE_LOG - K < 0 ? 0 : STRIDED_TILE_LOG - K); }
 
+}  // namespace zkb
+#include "ntt_lean.cuh"
+namespace zkb {
+
 // ---- contiguous level (optionally fused inverse -> scale -> forward per coset) --------------------
 struct ContigArgs {
   const u32* in; u32* out;
@@ -313,8 +319,6 @@ struct ContigArgs {
   int bitrev_store;                  // mode 1, single level (K == logn): store bit-reversed rows
   const uint2* scale;                // per coset: n Shoup pairs, shift_c^bitrev(p) / n at position p
   size_t out_coset_stride;           // element offset between coset outputs
-  const uint2* four_dit;             // mode 1, two-level: four-step twiddles of the following strided DIT level, applied
-                                     // by this kernel's coalesced store instead of that level's scattered load (or null)
 };
 
 static constexpr int CONTIG_TILE_LOG = 12;
@@ -386,10 +390,6 @@ __global__ void __launch_bounds__(512, 2) ntt_contig_kernel(ContigArgs a) {
     };
     auto gstore = [&](u32 slot, u32 q, Fp v) {
       if (f0 + q >= a.total_groups) return;
-      if (a.four_dit) {
-        const size_t p = ((size_t)((f0 + q) & ((1u << sub_bits) - 1)) << K) + slot;     // position in the column
-        v = shoup_mul(v.v, __ldg(a.four_dit + p));
-      }
       outc[gaddr(slot, q, a.out_stride)] = v.v;
     };
     // ---- DIT: the same bit ranges bottom-up; the last round stores straight to global memory ----
@@ -435,25 +435,106 @@ static void set_ntt_attrs_from() {
   ZKB_CUDA(cudaFuncSetAttribute(ntt_contig_kernel<KK, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   if constexpr (KK < KMAX) set_ntt_attrs_from<KK + 1>();
 }
-void ntt_set_device_attributes() { set_ntt_attrs_from<1>(); }
+void ntt_set_lean_attributes();
+void ntt_set_device_attributes() { set_ntt_attrs_from<1>(); ntt_set_lean_attributes(); }
 
 static void split_levels(int logn, int& K1, int& K2) {
   if (logn <= KMAX) { K1 = 0; K2 = logn; return; }
-  K2 = (logn + 1) / 2;
+  // size of the contiguous level, fastest measured split per log n (tools/k2_sweep.py on a B200 with the
+  // lean strided kernels, profiles/r02_k2_sweep.jsonl): the contiguous level likes 2^10 / 2^11 (three
+  // radix rounds of a 4096-element tile), the strided level two radix-16 rounds
+  static const int best_k2[25] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 9, 10, 10, 10, 10, 10, 11, 11, 11, 11, 12, 12};
+  K2 = best_k2[logn];
+  // experiment knob: size of the contiguous level (e.g. 12: 2^18 = 2^6 x 2^12, five radix rounds instead of six)
+  static const int env_k2 = env_int("ZKB200_NTT_K2", 0);
+  const int force_k2 = g_ntt_force_k2.load() ? g_ntt_force_k2.load() : env_k2;
+  if (force_k2 > 0 && force_k2 <= KMAX && logn - force_k2 >= 1 && logn - force_k2 <= KMAX) K2 = force_k2;
   K1 = logn - K2;
   if (K2 > KMAX) throw std::runtime_error("zkb200: NTT size out of range");
 }
 
+std::atomic<int> g_ntt_lean{3};      // zkb200_set_option("ntt_lean"): bit 0 lean strided kernels, bit 1 lean contiguous kernel
+
+template <int K, int LOGS>
+static void launch_lean_pair(const LeanStridedArgs& a, bool final_dit, dim3 grid, cudaStream_t s) {
+  if (final_dit) ntt_strided_lean_kernel<K, LOGS, true><<<grid, 1 << (K + 1), lean_strided_smem<K>(true), s>>>(a);
+  else ntt_strided_lean_kernel<K, LOGS, false><<<grid, 1 << (K + 1), lean_strided_smem<K>(false), s>>>(a);
+}
+template <int K, int LOGS>
+static void set_lean_attrs_pair() {
+  ZKB_CUDA(cudaFuncSetAttribute(ntt_strided_lean_kernel<K, LOGS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_strided_smem<K>(true)));
+  ZKB_CUDA(cudaFuncSetAttribute(ntt_strided_lean_kernel<K, LOGS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_strided_smem<K>(false)));
+}
+// the (level size, stride) pairs the two-level splits of 2^13 .. 2^21 use
+#define ZKB_LEAN_PAIRS(X) \
+  X(5, 8) X(6, 8) X(7, 8) X(8, 8) X(4, 9) X(5, 9) X(6, 9) X(7, 9) X(8, 9) X(9, 9) \
+  X(4, 10) X(5, 10) X(6, 10) X(7, 10) X(8, 10) X(9, 10) X(4, 11) X(5, 11) X(6, 11) X(7, 11) X(8, 11) X(9, 11) \
+  X(6, 12) X(7, 12) X(8, 12) X(9, 12)
+static bool launch_strided_lean(const LeanStridedArgs& a, int K, int logS, bool final_dit, dim3 grid, cudaStream_t s) {
+#define X(KK, SS) if (K == KK && logS == SS) { launch_lean_pair<KK, SS>(a, final_dit, grid, s); return true; }
+  ZKB_LEAN_PAIRS(X)
+#undef X
+  return false;
+}
+template <int K>
+static void set_lean_contig_attr() {
+  ZKB_CUDA(cudaFuncSetAttribute(ntt_contig_lean_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_contig_smem<K>()));
+}
+void ntt_set_lean_attributes() {
+#define X(KK, SS) set_lean_attrs_pair<KK, SS>();
+  ZKB_LEAN_PAIRS(X)
+#undef X
+  set_lean_contig_attr<8>(); set_lean_contig_attr<9>(); set_lean_contig_attr<10>(); set_lean_contig_attr<11>(); set_lean_contig_attr<12>();
+}
+// the fused middle launch of a two-level coset LDE with the lean kernel; false: not covered (generic kernel)
+static bool launch_contig_lean(const NttTables& tb, const u32* in, size_t in_stride, u32* out, size_t out_stride, size_t out_coset_stride,
+                               const uint2* scale, int ncoset, int K, int logn, size_t ncols, cudaStream_t s) {
+  if (!(g_ntt_lean.load() & 2) || K < 8 || K > 12 || logn < 13) return false;
+  LeanContigArgs a;
+  a.in = in; a.out = out; a.in_stride = in_stride; a.out_stride = out_stride; a.out_coset_stride = out_coset_stride;
+  a.small_tw = (const uint2*)tb.small_tw; a.scale = scale; a.ncoset = ncoset;
+  dim3 grid(1u << (logn - 12), (unsigned)ncols);
+  switch (K) {
+    case 8: ntt_contig_lean_kernel<8><<<grid, 256, lean_contig_smem<8>(), s>>>(a, logn); break;
+    case 9: ntt_contig_lean_kernel<9><<<grid, 256, lean_contig_smem<9>(), s>>>(a, logn); break;
+    case 10: ntt_contig_lean_kernel<10><<<grid, 256, lean_contig_smem<10>(), s>>>(a, logn); break;
+    case 11: ntt_contig_lean_kernel<11><<<grid, 256, lean_contig_smem<11>(), s>>>(a, logn); break;
+    default: ntt_contig_lean_kernel<12><<<grid, 256, lean_contig_smem<12>(), s>>>(a, logn); break;
+  }
+  ZKB_CHECK_LAUNCH();
+  return true;
+}
+
 static void launch_strided(const NttTables& tb, const u32* in, size_t in_stride, u32* out, size_t out_stride, size_t ncols,
                            int K, int logS, bool inverse, bool final_dit, int ncoset, size_t in_coset_stride,
-                           size_t out_coset_stride, cudaStream_t s, bool pre_twiddled = false) {
+                           size_t out_coset_stride, cudaStream_t s) {
+  if (g_ntt_lean.load() & 1) {
+    LeanStridedArgs la;
+    la.in = in; la.out = out; la.in_stride = in_stride; la.out_stride = out_stride;
+    la.in_coset_stride = in_coset_stride; la.out_coset_stride = out_coset_stride;
+    la.small_tw = (const uint2*)tb.small_tw;
+    la.inverse = inverse ? 1 : 0;
+    if (logS >= 5) {
+      dim3 grid(1u << (logS - 5), (unsigned)ncols, (unsigned)ncoset);
+      // the table lookup happens only for pairs that exist: probe with a null launch config first
+      bool have = false;
+#define X(KK, SS) if (K == KK && logS == SS) have = true;
+      ZKB_LEAN_PAIRS(X)
+#undef X
+      if (have) {
+        la.four = (const uint2*)tb.four_step_table(K, logS, inverse, s);
+        launch_strided_lean(la, K, logS, final_dit, grid, s);
+        ZKB_CHECK_LAUNCH();
+        return;
+      }
+    }
+  }
   StridedArgs a;
   a.in = in; a.out = out; a.in_stride = in_stride; a.out_stride = out_stride;
   a.small_tw = (const uint2*)tb.small_tw;
   a.four = (const uint2*)tb.four_step_table(K, logS, inverse, s);
   a.logS = logS; a.inverse = inverse ? 1 : 0; a.final_dit = final_dit ? 1 : 0;
   a.in_coset_stride = in_coset_stride; a.out_coset_stride = out_coset_stride;
-  a.pre_twiddled = pre_twiddled ? 1 : 0;
   static const int tile_log = env_int("ZKB200_NTT_STRIDED_TILE_LOG", STRIDED_TILE_LOG);
   int logT = tile_log - K;                       // 8192 elements (512 threads) per tile: two CTAs per SM
   if (logT > 5) logT = 5;
@@ -569,7 +650,6 @@ void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* 
     ContigArgs b;
     b.K = K2; b.logn = (int)log_n; b.mode = 1; b.inverse = 1; b.ncoset = (int)ncoset;
     b.scale = scale;
-    b.four_dit = nullptr;
     if (!two_level) {
       b.in = in + c0 * in_stride; b.in_stride = in_stride;
       b.out = out + c0 * out_stride; b.out_stride = out_stride; b.out_coset_stride = n;
@@ -581,13 +661,8 @@ void coset_lde_batch(const NttTables& tb, const u32* in, size_t in_stride, u32* 
     b.in = half.p; b.in_stride = n;
     b.out = xbuf.p; b.out_stride = n; b.out_coset_stride = chunk * n;
     b.bitrev_store = 0;
-    // opt-in (not yet measured on a B200): the fused kernel multiplies by the DIT level's four-step twiddles
-    // as it stores, so that the strided DIT launch loads data only
-    static const bool pretw = env_int("ZKB200_NTT_PRETWIDDLE", 0) != 0;
-    b.four_dit = pretw ? (const uint2*)tb.four_step_table(K1, K2, false, s) : nullptr;
-    launch_contig(tb, b, nc, s);
-    launch_strided(tb, xbuf.p, n, out + c0 * out_stride, out_stride, nc, K1, K2, false, true, (int)ncoset, chunk * n, n, s,
-                   pretw);
+    if (!launch_contig_lean(tb, half.p, n, xbuf.p, n, chunk * n, scale, (int)ncoset, K2, (int)log_n, nc, s)) launch_contig(tb, b, nc, s);
+    launch_strided(tb, xbuf.p, n, out + c0 * out_stride, out_stride, nc, K1, K2, false, true, (int)ncoset, chunk * n, n, s);
   }
 }
 
@@ -635,7 +710,6 @@ void ntt_batch(const NttTables& tb, const u32* in, u32* out, unsigned log_n, siz
     b.in = src; b.in_stride = n; b.out = dst; b.out_stride = n; b.out_coset_stride = 0;
     b.K = K2; b.logn = (int)log_n; b.mode = 0; b.inverse = inverse ? 1 : 0; b.ncoset = 1; b.bitrev_store = 0;
     b.scale = nullptr;
-    b.four_dit = nullptr;
     launch_contig(tb, b, nc, s);
     if (!bitrev_out) bitrev_rows(tmp.p, out + c0 * n, log_n, nc, s);
   }

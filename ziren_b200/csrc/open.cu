@@ -1,9 +1,12 @@
 #include "open.h"
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
 namespace zkb {
+
+std::atomic<int> g_eval_v2{-1};    // zkb200_set_option("eval_v2"): -1 = environment / default
 
 __global__ void bary_weights_kernel(const u32* tw_lo, const u32* tw_hi, unsigned log_n, Ef zp, Ef scale, u32* out) {
   const size_t n = (size_t)1 << log_n;
@@ -227,7 +230,8 @@ __global__ void sum_partials_kernel(const u32* partial, size_t count, int nsplit
 void eval_columns(const u32* lde, size_t H, size_t n, size_t W, const u32* w0, const u32* w1, int npoints, u32* out,
                   cudaStream_t s) {
   if (!W) return;
-  static const bool use_v2 = getenv("ZKB200_EVAL_V2") && atoi(getenv("ZKB200_EVAL_V2")) != 0;
+  static const bool env_v2 = getenv("ZKB200_EVAL_V2") && atoi(getenv("ZKB200_EVAL_V2")) != 0;
+  const bool use_v2 = g_eval_v2.load() >= 0 ? g_eval_v2.load() != 0 : env_v2;
   if (use_v2 && n >= 1024 && W >= 128) {
     // rows are split in multiples of E2_ROWS so that every CTA runs whole steps; about three CTAs per SM
     const size_t smem = (size_t)(2 * E2_WARPS * 32 * E2_LD + 2 * E2_ROWS * 8) * sizeof(u32);

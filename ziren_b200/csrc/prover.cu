@@ -28,7 +28,21 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
   ZKB_CUDA(cudaSetDevice(dev));
   machine.parse(desc, n);
   for (auto& L : lanes) ZKB_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-  ZKB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  {
+    // the copy stream's "pull" kernels must get their few CTAs even while the lanes fill the SMs
+    int lo = 0, hi = 0;
+    ZKB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    ZKB_CUDA(cudaStreamCreateWithPriority(&copy_stream, cudaStreamNonBlocking, hi));
+  }
+  if (const char* e = getenv("ZKB200_UPLOAD")) upload_mode = std::string(e) == "dma" ? UPLOAD_DMA : std::string(e) == "dma2d" ? UPLOAD_DMA2D : UPLOAD_PULL;
+  // counters the pull kernel bumps and the lanes wait on: plain cudaMalloc memory (stream memory
+  // operations do not take stream-ordered pool allocations), handed out as a ring; probed once here -
+  // a driver that refuses the wait turns the pull mode off (2-D DMA instead)
+  wait_value.init();
+  ZKB_CUDA(cudaMalloc((void**)&pull_counters, PULL_COUNTER_RING * sizeof(u32)));
+  ZKB_CUDA(cudaMemset(pull_counters, 0, PULL_COUNTER_RING * sizeof(u32)));
+  if (wait_value && !wait_value.probe(lanes[0].stream, pull_counters)) wait_value.fn = nullptr;
+  if (const char* e = getenv("ZKB200_PULL_CTAS")) pull_ctas = std::max(1, atoi(e));
   // keep freed blocks in the stream-ordered pool: shard proofs reuse the same sizes
   cudaMemPool_t pool;
   ZKB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -43,7 +57,9 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
   {
     size_t free_b = 0, total_b = 0;
     ZKB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t want = std::min<size_t>((size_t)112 << 30, free_b / 10 * 7);
+    // default: a bounded reservation (32 GB or half of what is free) that covers 2^20..2^21-row shards; the
+    // pool still grows on demand for larger ones (the first such proof pays for the growth once)
+    size_t want = std::min<size_t>((size_t)32 << 30, free_b / 2);
     if (const char* e = getenv("ZKB200_POOL_GB")) want = std::min<size_t>((size_t)atol(e) << 30, free_b * 9 / 10);
     if (want) {
       void* p = nullptr;
@@ -83,6 +99,8 @@ void Ctx::destroy() {
     if (L.stream) cudaStreamDestroy(L.stream);
     L.stream = nullptr; L.d_small = nullptr; L.h_small = nullptr;
   }
+  if (pull_counters) cudaFree(pull_counters);
+  pull_counters = nullptr;
   if (copy_stream) cudaStreamDestroy(copy_stream);
   copy_stream = nullptr;
 }
@@ -111,6 +129,20 @@ struct StageTimer {
     nvtxRangePop();
   }
 };
+
+bool StreamWaitValue::probe(cudaStream_t s, const u32* zeroed_counter) const {
+  if (!fn) return false;
+  if (fn(s, (unsigned long long)(uintptr_t)zeroed_counter, 0u, 0x0) != 0) return false;     // 0 >= 0: satisfied at once
+  return cudaStreamSynchronize(s) == cudaSuccess;
+}
+void StreamWaitValue::init() {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    fn = reinterpret_cast<Fn>(p);
+  else
+    cudaGetLastError();
+}
 
 static bool is_device_pointer(const void* p, bool* pinned = nullptr) {
   cudaPointerAttributes attr;
@@ -326,7 +358,9 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     size_t mat, col0, ncols;
     const u32* src = nullptr; size_t src_pitch = 0;     // row-major device source of the transpose
     DevBuf stage;
+    std::shared_ptr<DevBuf> whole;                      // dma mode: the matrix's staging buffer, shared by its pieces
     cudaEvent_t ready = nullptr;
+    int pull_index = -1; unsigned long long pull_tiles = 0;      // pull mode: counter and its final value
     bool last_of_matrix = false;
   };
   struct Events {      // RAII: an exception between creation and the end of the call must not leak them
@@ -347,11 +381,27 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
       pieces.push_back(std::move(p));
     }
   }
-  // Phase 1 (copy stream, its own lock): host->device DMA only, so the copy engine is never held
-  // up waiting for SM slots.  Other host threads may hold the compute lanes meanwhile, the way the
-  // reference keeps several shards in flight (crates/core/machine/src/utils/prove.rs:487-521).
+  // Phase 1 (copy stream, its own lock): the traces cross PCIe.  Other host threads may hold the compute
+  // lanes meanwhile, the way the reference keeps several shards in flight
+  // (crates/core/machine/src/utils/prove.rs:487-521).  Three kinds of source:
+  //   device memory ......... nothing to copy; phase 2 transposes from it
+  //   pinned host memory .... "pull": a few persistent CTAs on the (high-priority) copy stream read the
+  //                           rows over PCIe and write the column-major trace directly (layout.cu);
+  //                           ZKB200_UPLOAD=dma: one contiguous DMA per matrix into a staging buffer
+  //   pageable host memory .. host threads gather the piece into the pinned ring, DMA, staging buffer
+  for (size_t i = 0; i < traces.size(); i++) sh->names.push_back(traces[i].name);
+  cudaEvent_t alloc_done = nullptr, pull_armed = nullptr, pull_finished = nullptr;
+  std::vector<PullPiece> pull;
+  unsigned long long pull_tiles = 0;
+  DevBuf pull_dev;
+  u32* pull_done = nullptr;
   {
     std::lock_guard<std::mutex> lock(ctx.copy_mu);
+    for (size_t i = 0; i < traces.size(); i++) sh->traces.push_back(DevMat(traces[i].height, traces[i].width, ctx.copy_stream));
+    ZKB_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
+    events.v.push_back(alloc_done);
+    ZKB_CUDA(cudaEventRecord(alloc_done, ctx.copy_stream));
+    std::vector<std::shared_ptr<DevBuf>> whole(traces.size());     // dma mode: one staging buffer per matrix
     for (auto& p : pieces) {
       const TraceIn& t = traces[p.mat];
       bool pinned = false;
@@ -359,16 +409,63 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
         p.src = t.data + p.col0; p.src_pitch = t.width;
         continue;
       }
-      p.stage = DevBuf(t.height * p.ncols, ctx.copy_stream);
-      if (pinned)
+      const u32* mapped = nullptr;
+      if (pinned && ctx.upload_mode == UPLOAD_PULL && cudaHostGetDevicePointer((void**)&mapped, (void*)t.data, 0) != cudaSuccess) { cudaGetLastError(); mapped = nullptr; }
+      if (mapped && ctx.wait_value) {
+        // one persistent kernel pulls all such pieces (launched below); the lane waits for the piece's tile count
+        PullPiece pp;
+        const uintptr_t addr = (uintptr_t)mapped;
+        pp.base = (const u32*)(addr & ~(uintptr_t)127);
+        pp.word_off = (addr & 127) / sizeof(u32) + p.col0;
+        pp.pitch = t.width;
+        pp.dst = sh->traces[p.mat].d() + p.col0 * t.height;
+        pp.rows = t.height; pp.cols = p.ncols;
+        pp.col_tiles = pull_piece_col_tiles(p.ncols);
+        pp.tile_begin = pull_tiles;
+        p.pull_index = (int)pull.size();
+        p.pull_tiles = pull_piece_tiles(t.height, p.ncols);
+        pull_tiles += p.pull_tiles;
+        pull.push_back(pp);
+        p.src = nullptr;                                   // already column-major when its counter is full
+        continue;
+      } else if (pinned && ctx.upload_mode != UPLOAD_DMA) {
+        // 2-D DMA of the column slice (ZKB200_UPLOAD=dma2d)
+        p.stage = DevBuf(t.height * p.ncols, ctx.copy_stream);
         ZKB_CUDA(cudaMemcpy2DAsync(p.stage.p, p.ncols * sizeof(u32), t.data + p.col0, t.width * sizeof(u32), p.ncols * sizeof(u32),
                                    t.height, cudaMemcpyHostToDevice, ctx.copy_stream));
-      else
+        p.src = p.stage.p; p.src_pitch = p.ncols;
+      } else if (pinned) {
+        if (!whole[p.mat]) {
+          whole[p.mat] = std::make_shared<DevBuf>(t.height * t.width, ctx.copy_stream);
+          ZKB_CUDA(cudaMemcpyAsync(whole[p.mat]->p, t.data, t.height * t.width * sizeof(u32), cudaMemcpyHostToDevice, ctx.copy_stream));
+        }
+        p.whole = whole[p.mat];
+        p.src = whole[p.mat]->p + p.col0; p.src_pitch = t.width;
+      } else {
+        p.stage = DevBuf(t.height * p.ncols, ctx.copy_stream);
         ctx.stager.copy_2d(p.stage.p, t.data + p.col0, p.ncols, t.width, t.height, ctx.copy_stream);
-      p.src = p.stage.p; p.src_pitch = p.ncols;
+        p.src = p.stage.p; p.src_pitch = p.ncols;
+      }
       ZKB_CUDA(cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
       events.v.push_back(p.ready);
       ZKB_CUDA(cudaEventRecord(p.ready, ctx.copy_stream));
+    }
+    if (!pull.empty()) {
+      pull_dev = DevBuf((pull.size() * sizeof(PullPiece) + 3) / 4, ctx.copy_stream);
+      if (pull.size() > Ctx::PULL_COUNTER_RING / 4) throw std::runtime_error("zkb200: commit: too many pieces");
+      if (ctx.pull_counter_next + pull.size() > Ctx::PULL_COUNTER_RING) ctx.pull_counter_next = 0;     // under copy_mu
+      pull_done = ctx.pull_counters + ctx.pull_counter_next;
+      ctx.pull_counter_next += pull.size();
+      ZKB_CUDA(cudaMemcpyAsync(pull_dev.p, pull.data(), pull.size() * sizeof(PullPiece), cudaMemcpyHostToDevice, ctx.copy_stream));
+      ZKB_CUDA(cudaMemsetAsync(pull_done, 0, pull.size() * sizeof(u32), ctx.copy_stream));
+      // the lane must not look at the counters before they are cleared
+      ZKB_CUDA(cudaEventCreateWithFlags(&pull_armed, cudaEventDisableTiming));
+      events.v.push_back(pull_armed);
+      ZKB_CUDA(cudaEventRecord(pull_armed, ctx.copy_stream));
+      pull_shard(reinterpret_cast<const PullPiece*>(pull_dev.p), (int)pull.size(), pull_tiles, pull_done, ctx.pull_ctas, ctx.copy_stream);
+      ZKB_CUDA(cudaEventCreateWithFlags(&pull_finished, cudaEventDisableTiming));
+      events.v.push_back(pull_finished);
+      ZKB_CUDA(cudaEventRecord(pull_finished, ctx.copy_stream));
     }
   }
   // Phase 2 (a compute lane): layout change, LDE and leaf hashing piece by piece, then the tree
@@ -377,11 +474,13 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
   L.begin();
   if (ctx.profile) { std::lock_guard<std::mutex> lock(ctx.stage_mu); ctx.stage_ms.clear(); }
   Commit& out = sh->main;
+  // the traces were allocated on the copy stream: order the lane after that, release them in lane order
+  ZKB_CUDA(cudaStreamWaitEvent(L.stream, alloc_done, 0));
+  if (pull_armed) ZKB_CUDA(cudaStreamWaitEvent(L.stream, pull_armed, 0));
+  pull_dev.stream = L.stream;
   for (size_t i = 0; i < traces.size(); i++) {
-    const TraceIn& t = traces[i];
-    sh->names.push_back(t.name);
-    sh->traces.push_back(DevMat(t.height, t.width, L.stream));
-    out.ldes.push_back(DevMat(t.height << lb, t.width, L.stream));
+    sh->traces[i].buf.stream = L.stream;
+    out.ldes.push_back(DevMat(traces[i].height << lb, traces[i].width, L.stream));
     out.log_n.push_back(logn[i]);
   }
   const Fp shift = fp_from_canonical(KB_GEN);     // trace domains are the subgroups themselves
@@ -395,9 +494,11 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     {
       StageTimer tm(ctx, L, "commit_main_wait_upload_transpose");
       if (p.ready) ZKB_CUDA(cudaStreamWaitEvent(L.stream, p.ready, 0));
-      transpose_piece_to_colmajor(p.src, p.src_pitch, cols, n, p.ncols, L.stream);
+      if (p.pull_index >= 0) ctx.wait_value(L.stream, pull_done + p.pull_index, (u32)p.pull_tiles);
+      if (p.src) transpose_piece_to_colmajor(p.src, p.src_pitch, cols, n, p.ncols, L.stream);
       p.stage.stream = L.stream;     // released in lane order, after the transpose
       p.stage.release();
+      if (p.whole) { p.whole->stream = L.stream; p.whole.reset(); }
     }
     {
       StageTimer tm(ctx, L, "commit_main_lde");
@@ -413,6 +514,7 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
       if (p.last_of_matrix) pre[lh] = digests[lh].p;
     }
   }
+  if (pull_finished) ZKB_CUDA(cudaStreamWaitEvent(L.stream, pull_finished, 0));    // the work list and counters are released in lane order
   pcs_merkle(ctx, L, out, &pre, "commit_main_merkle");
   sh->public_values.assign(pv, pv + npv);
   return sh.release();

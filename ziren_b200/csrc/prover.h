@@ -42,6 +42,21 @@ struct Lane {
   void begin() { arena.reset(); keep.clear(); }
 };
 constexpr int NUM_LANES = 4;
+enum UploadMode { UPLOAD_PULL = 0, UPLOAD_DMA = 1, UPLOAD_DMA2D = 2 };
+
+// stream-ordered wait on a 32-bit device counter (>=): the driver's cuStreamWaitValue32, fetched at run
+// time so that the library links against the runtime only.  Unavailable -> operator bool is false.
+struct StreamWaitValue {
+  typedef int (*Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+  Fn fn = nullptr;
+  void init();
+  bool probe(cudaStream_t s, const u32* zeroed_counter) const;
+  explicit operator bool() const { return fn != nullptr; }
+  void operator()(cudaStream_t s, const u32* addr, u32 value) const {
+    const int rc = fn(s, (unsigned long long)(uintptr_t)addr, value, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (rc != 0) throw std::runtime_error("zkb200: cuStreamWaitValue32 failed with CUresult " + std::to_string(rc));
+  }
+};
 
 // Pageable host memory -> device through a ring of pinned slots filled by a few host threads
 // (prover.cu).  Lazily allocated: a caller that hands over pinned or device memory never pays for it.
@@ -75,6 +90,12 @@ struct Ctx {
   std::mutex copy_mu;
   HostStager stager;                    // pageable host sources
   size_t piece_bytes = (size_t)256 << 20;   // column pieces of the main commit (prover_commit)
+  int upload_mode = UPLOAD_PULL;        // pinned host traces (ZKB200_UPLOAD=pull|dma|dma2d), see prover_commit
+  int pull_ctas = 32;                   // persistent CTAs of the pull kernel (ZKB200_PULL_CTAS)
+  StreamWaitValue wait_value;           // cuStreamWaitValue32: a lane waits for a counter of the pull kernel
+  static constexpr size_t PULL_COUNTER_RING = 1 << 16;
+  u32* pull_counters = nullptr;         // ring of counters (cudaMalloc), slices handed out under copy_mu
+  size_t pull_counter_next = 0;
   LanePool<NUM_LANES> pool;             // which lane a commit/open call runs on
   MachineInfo machine;
   NttTables tables;

@@ -75,6 +75,10 @@ class ShardMainData:
     def __init__(self, handle, main_commit, public_values):
         self._h, self.main_commit, self.public_values = handle, main_commit, public_values
 
+    def device(self) -> int:
+        """CUDA device the shard was committed on (a multi-GPU prover routes shards)."""
+        return _ffi.lib().zkb200_shard_device(self._h)
+
     def free(self):
         if self._h:
             _ffi.lib().zkb200_shard_free(self._h)
@@ -88,13 +92,19 @@ class ShardMainData:
 
 
 class B200Prover:
-    """`impl MachineProver<KoalaBearPoseidon2, A> for B200Prover` — one instance per GPU."""
+    """`impl MachineProver<KoalaBearPoseidon2, A> for B200Prover`.  `device`: one GPU index, a list of
+    indices, or -1 for every visible GPU — one prover object whose commit() routes each shard to the
+    least-loaded device (what prove_with_context's worker threads share, prove.rs:487-521)."""
 
-    def __init__(self, machine: Machine, device: int = 0):
+    def __init__(self, machine: Machine, device=0):
         self.machine_ = machine
         desc = _np32(machine.descriptor())
         h = C.c_void_p()
-        rc = _ffi.lib().zkb200_ctx_create(device, _p(desc), desc.size, C.byref(h))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*device)
+            rc = _ffi.lib().zkb200_ctx_create_multi(ids, len(device), _p(desc), desc.size, C.byref(h))
+        else:
+            rc = _ffi.lib().zkb200_ctx_create(device, _p(desc), desc.size, C.byref(h))
         if rc:
             raise ZkbError(_ffi.lib().zkb200_last_error(None).decode())
         self._h = h
@@ -119,6 +129,9 @@ class B200Prover:
 
     def machine(self) -> Machine:
         return self.machine_
+
+    def num_devices(self) -> int:
+        return _ffi.lib().zkb200_ctx_num_devices(self._h)
 
     def stream_ptr(self) -> int:
         return _ffi.lib().zkb200_ctx_stream(self._h)
