@@ -72,6 +72,8 @@ def make_case(args, sample=False):
         return synthetic.core_case(log_cpu=lc, seed=0xC0FFEE + args.rank)
     if w == "fibonacci":
         return synthetic.fibonacci_core_case(log_cpu=lc, seed=0xC0FFEE + args.rank)
+    if w == "compress":
+        return synthetic.compress_case(log_max=lc, seed=0xC0FFEE + args.rank)
     raise SystemExit(f"unknown workload {w}")
 
 
@@ -79,11 +81,14 @@ def workload_config(args, case, sample=False):
     lc = args.sample_log_cpu if sample else args.log_cpu
     names = {"keccak": "examples/keccak-precompile-like synthetic shard (Cpu 2^%d rows, KeccakSponge 2^%d x 4259 cols)" % (lc, lc - 2),
              "core": "tendermint-like maximal core shard (maximal_shapes.json[21][1] scaled to Cpu 2^%d)" % lc,
-             "fibonacci": "examples/fibonacci-like single core shard (Cpu 2^%d)" % lc}
+             "fibonacci": "examples/fibonacci-like single core shard (Cpu 2^%d)" % lc,
+             "compress": "recursion-compress-like inner proof (shrink shape, tallest table 2^%d, Poseidon2Wide 313 columns), "
+                         "setup (preprocessed commit) inside every proof as crates/prover/src/lib.rs:809-832 does" % lc}
     return {"workload": names[args.workload], "cycles_per_shard": case.cycles, "cells_per_shard": case.cells,
             "trace_bytes_per_shard": case.trace_bytes, "fri": {"log_blowup": 1, "num_queries": 84, "pow_bits": 16},
             "l2_policy": "inputs larger than L2 (trace bytes >> 126 MB); fresh shard allocations every step",
-            "parallelism": f"shard-per-gpu x{args.gpus}", "shards_in_flight_per_gpu": {"value": args.value_threads, "e2e": args.e2e_threads}}
+            "parallelism": f"shard-per-gpu x{args.gpus}", "shards_in_flight_per_gpu": {"value": args.value_threads, "e2e": args.e2e_threads},
+            **({"total_shards": args.shards, "shards_per_rank": len(range(args.rank, args.shards, args.world))} if args.shards else {})}
 
 
 class ClockSampler:
@@ -130,19 +135,26 @@ def run_reference(args):
     om.setup(case.prep)
     o.set_num_threads(os.cpu_count())     # torchrun exports OMP_NUM_THREADS=1; use every host core
     cores = o.num_threads()
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        om.prove_shard(case.traces, case.public_values)
+    # SAME configuration as the GPU arm (one full shard is about 90 s of CPU work at 2^20 cycles), so the sample is
+    # bounded by the number of shards, not by their size: one untimed-free pass, `steps` capped at one shard
+    same = args.sample_log_cpu == args.log_cpu
+    steps = 1 if same else max(1, args.steps)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
+        if args.workload == "compress":
+            om.setup(case.prep)           # setup is part of every compress proof (crates/prover/src/lib.rs:809-810)
         proof, _ = om.prove_shard(case.traces, case.public_values)
     dt = time.perf_counter() - t0
-    val = case.cycles * args.steps / dt
+    val = (case.cycles if case.cycles else 1) * steps / dt
     cfg = workload_config(args, case, sample=True)
-    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    metric, unit = (METRIC, UNIT) if case.cycles else ("compress_inner_proofs_per_sec", "proofs/s")
+    line = {"metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 (KoalaBear 31-bit prime field)", "data": "synthetic", "impl": "reference", "config": cfg,
+            "same_config_as_gpu_arm": same,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} shard(s) of the same machine scaled to Cpu 2^{args.sample_log_cpu}; "
+                             "sample": f"{steps} whole shard(s) of " + ("the bench configuration itself" if same else f"the same machine scaled to Cpu 2^{args.sample_log_cpu}") +
+                                       " (requested steps/warmup are capped: the CPU needs ~90 s per 2^20-cycle shard); "
                                        "C++ oracle (OpenMP), not Plonky3's AVX code: the Rust reference cannot be built here"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -154,9 +166,13 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="keccak", choices=["keccak", "core", "fibonacci"])
+    ap.add_argument("--workload", default="keccak", choices=["keccak", "core", "fibonacci", "compress"])
     ap.add_argument("--log-cpu", type=int, default=20)
-    ap.add_argument("--sample-log-cpu", type=int, default=14, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--sample-log-cpu", type=int, default=None,
+                    help="size of the CPU arm's shard (default: the bench configuration itself, capped at 2^20)")
+    ap.add_argument("--shards", type=int, default=0,
+                    help="strong scaling: prove this many shards in total, split round-robin over the ranks "
+                         "(BASELINE configs[2]: --workload core --log-cpu 21 --shards 18; configs[4]: --workload compress --log-cpu 18 --shards 127)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host e2e figure")
@@ -171,6 +187,8 @@ def main():
     args.rank = int(os.environ.get("RANK", "0"))
     args.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     args.world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.sample_log_cpu is None:
+        args.sample_log_cpu = min(args.log_cpu, 20)
 
     if args.impl == "reference":
         run_reference(args)
@@ -192,8 +210,14 @@ def main():
     case = make_case(args)
     prover = B200Prover(case.machine, device=args.local_rank)
     stream = torch.cuda.ExternalStream(prover.stream_ptr(), device=torch.device("cuda", args.local_rank))
-    pk = prover.setup({k: kb.to_monty(v) for k, v in case.prep.items()})
+    prep_monty = {k: kb.to_monty(v) for k, v in case.prep.items()}
+    pk = prover.setup(prep_monty)
     base_ch = pk.observe_into()
+    per_proof_setup = args.workload == "compress"      # crates/prover/src/lib.rs:809-810: setup inside every compress proof
+    units_per_shard = case.cycles if case.cycles else 1
+    metric, unit = (METRIC, UNIT) if case.cycles else ("compress_inner_proofs_per_sec", "proofs/s")
+    # strong scaling (--shards S): S shards in total, rank r proves shards r, r + world, ...
+    my_steps = len(range(args.rank, args.shards, args.world)) if args.shards else args.steps
 
     # inputs: Montgomery row-major, once in pinned host memory (e2e arm), once resident in HBM
     host_tr = {}
@@ -209,6 +233,11 @@ def main():
     torch.cuda.synchronize()
 
     def prove(traces):
+        if per_proof_setup:
+            pkk = prover.setup(prep_monty)
+            proof, _ = prover.prove_shard(pkk, traces, case.public_values, pkk.observe_into())
+            pkk.free()
+            return proof
         proof, _ = prover.prove_shard(pk, traces, case.public_values, base_ch)
         return proof
 
@@ -254,13 +283,13 @@ def main():
     sampler = ClockSampler(args.local_rank)
     sampler.start()
     launches0 = prover.launch_count()
-    ms_dev, proof = timed(dev_tr, args.steps, args.value_threads)
+    ms_dev, proof = timed(dev_tr, my_steps, args.value_threads)
     launches = prover.launch_count() - launches0
     timed(host_tr, max(args.warmup, args.e2e_threads), args.e2e_threads)      # warm the staging/pool paths of the e2e arm
-    ms_e2e, proof2 = timed(host_tr, args.steps, args.e2e_threads)
+    ms_e2e, proof2 = timed(host_tr, my_steps, args.e2e_threads)
     # one shard in flight: what the reference's own GPU options ask for (shard_batch_size = 1,
     # crates/stark/src/opts.rs:83-110) - upload, layout change, LDE and leaf hashing overlap INSIDE the shard
-    ms_e2e_1, proof3 = timed(host_tr, args.steps, 1)
+    ms_e2e_1, proof3 = timed(host_tr, my_steps, 1)
     clocks = sampler.stop()
     assert np.array_equal(proof, proof2) and np.array_equal(proof, proof3)
     # pageable host memory (what RowMajorMatrix.values is, prover.rs:258-262): staged through the pinned ring
@@ -313,20 +342,20 @@ def main():
             cpu_base = measure_cpu_baseline(args)
 
     if args.rank == 0:
-        total_cycles = case.cycles * args.steps * args.gpus
-        line = {"metric": METRIC, "value": total_cycles / (ms_dev / 1e3), "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u32 (KoalaBear 31-bit prime field)", "data": "synthetic",
+        total_cycles = units_per_shard * (args.shards if args.shards else args.steps * args.gpus)
+        line = {"metric": metric, "value": total_cycles / (ms_dev / 1e3), "unit": unit, "n_gpus": args.gpus,
+                "steps": my_steps, "warmup": args.warmup, "ms_per_step": ms_dev / max(my_steps, 1), "higher_is_better": True,
+                "scaling": "strong" if args.shards else "weak", "vs_baseline": None, "dtype": "u32 (KoalaBear 31-bit prime field)", "data": "synthetic",
                 "config": cfg,
-                "e2e": {"value": total_cycles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
+                "e2e": {"value": total_cycles / (ms_e2e / 1e3), "unit": unit, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / max(my_steps, 1),
                         "host_threads_in_flight": args.e2e_threads,
-                        "one_shard_in_flight": {"value": total_cycles / (ms_e2e_1 / 1e3), "ms_per_step": ms_e2e_1 / args.steps},
+                        "one_shard_in_flight": {"value": total_cycles / (ms_e2e_1 / 1e3), "ms_per_step": ms_e2e_1 / max(my_steps, 1)},
                         "pageable_host_one_shard_in_flight": None if ms_e2e_pageable is None else
-                        {"value": case.cycles * max(2, args.steps // 3) / (ms_e2e_pageable / 1e3), "ms_per_step": ms_e2e_pageable / max(2, args.steps // 3)}},
+                        {"value": units_per_shard * max(2, args.steps // 3) / (ms_e2e_pageable / 1e3), "ms_per_step": ms_e2e_pageable / max(2, args.steps // 3)}},
                 "verified": verified, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other,
                 "cpu_baseline": cpu_base,
-                "stage_ms": stages, "cells_per_sec": cells * args.steps * args.gpus / (ms_dev / 1e3)}
+                "stage_ms": stages, "cells_per_sec": cells * (args.shards if args.shards else args.steps * args.gpus) / (ms_dev / 1e3)}
         print(json.dumps(line))
     pk.free()
     prover.close()
@@ -389,7 +418,7 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1):
 
 def measure_cpu_baseline(args):
     out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--workload", args.workload, "--sample-log-cpu", str(args.sample_log_cpu)],
+                          "--workload", args.workload, "--log-cpu", str(args.log_cpu), "--sample-log-cpu", str(args.sample_log_cpu)],
                          capture_output=True, text=True, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
     try:
         return json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]

@@ -83,6 +83,9 @@ int zkb200_ctx_num_devices(const zkb200_ctx* ctx);
 /* process-wide experiment knobs used by tools/ (A/B timing inside one process): "ntt_k2" (size of the
  * contiguous NTT level, 0 = built-in), "eval_v2" (0/1, -1 = default). */
 int zkb200_set_option(const char* key, long value);
+/* The constraint kernels (K3) are generated per chip from the ZKMD descriptor and compiled with NVRTC at run
+ * time.  This entry point does only that (no GPU needed): chips compiled, or -1; total cubin bytes out. */
+int zkb200_codegen_compile_check(const uint32_t* desc, size_t n_words, size_t* bytes_out);
 /* tools/h2d_probe.py: time one pass of a pinned row-major `rows x row_bytes` buffer over PCIe.  mode 0: 2-D DMA
  * in column slices of seg_bytes over n concurrent streams; 1: the pull kernel with n CTAs; 2: contiguous DMA in n parts. */
 int zkb200_h2d_probe(zkb200_ctx* ctx, int mode, size_t row_bytes, size_t rows, size_t seg_bytes, int n, float* ms_out);

@@ -147,7 +147,19 @@ def test_permutation_trace_matches_oracle(torch, mini, oracle):
         assert np.array_equal(got_sum, want_sum), name
 
 
-def test_quotient_matches_oracle(torch, mini, oracle):
+@pytest.mark.parametrize("codegen", [1, 0], ids=["generated", "interpreter"])
+def test_quotient_matches_oracle(torch, mini, oracle, codegen):
+    """K3 both ways: the per-chip kernels generated and compiled at run time (NVRTC) and the bytecode
+    interpreter they replace, each bit-exact against the oracle for every chip of the machine."""
+    from ziren_b200 import _ffi
+    _ffi.lib().zkb200_set_option(b"quotient_codegen", codegen)
+    try:
+        _quotient_matches_oracle(torch, mini, oracle)
+    finally:
+        _ffi.lib().zkb200_set_option(b"quotient_codegen", 1)
+
+
+def _quotient_matches_oracle(torch, mini, oracle):
     case, prover = mini
     om = oracle.OracleMachine(case.machine)
     rng = np.random.default_rng(4)
@@ -486,3 +498,25 @@ def test_multi_device_prover_routes_shards(torch, oracle):
         assert len(set(devices)) == min(multi.num_devices(), len(cases)), devices
     pk.free()
     multi.close()
+
+
+@pytest.mark.parametrize("which", ["core", "keccak"])
+def test_interpreter_and_generated_kernels_give_the_same_proof(torch, oracle, which):
+    """whole proofs with the constraint interpreter (quotient_codegen = 0) equal the proofs made with the
+    generated kernels, which the other tests compare with the oracle"""
+    from ziren_b200 import _ffi
+    from ziren_b200.prover import B200Prover
+    case = {"core": lambda: synthetic.core_case(log_cpu=9, seed=31, num_queries=5, pow_bits=6),
+            "keccak": lambda: synthetic.keccak_case(log_cpu=8, seed=33, num_queries=5, pow_bits=6)}[which]()
+    prover = B200Prover(case.machine)
+    pk = prover.setup({k: kb.to_monty(v) for k, v in case.prep.items()})
+    tr = {k: kb.to_monty(v) for k, v in case.traces.items()}
+    a, _ = prover.prove_shard(pk, tr, case.public_values)
+    _ffi.lib().zkb200_set_option(b"quotient_codegen", 0)
+    try:
+        b, _ = prover.prove_shard(pk, tr, case.public_values)
+    finally:
+        _ffi.lib().zkb200_set_option(b"quotient_codegen", 1)
+    assert np.array_equal(a, b)
+    pk.free()
+    prover.close()

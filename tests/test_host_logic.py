@@ -163,3 +163,16 @@ def test_lane_pool_hands_out_any_free_lane(host):
     for threads, active in ((4, 3), (8, 3), (2, 1), (6, 4), (3, 3)):
         assert host.hostcheck_lane_pool(threads, 3000, active) == 0, (threads, active)
 
+
+
+def test_constraint_kernels_are_generated_and_compile_without_a_gpu():
+    """K3 code generation (csrc/quotient_codegen.cpp): every chip of a machine becomes CUDA source that NVRTC
+    compiles to an sm_100a cubin; needs no device."""
+    import ctypes as C
+    from ziren_b200 import _ffi, synthetic
+    m = synthetic.mini_case().machine
+    desc = np.ascontiguousarray(m.descriptor(), dtype=np.uint32)
+    n = C.c_size_t()
+    rc = _ffi.lib().zkb200_codegen_compile_check(desc.ctypes.data_as(_ffi.u32p), desc.size, C.byref(n))
+    assert rc == len(m.chips), _ffi.lib().zkb200_last_error(None).decode()
+    assert n.value > 10000

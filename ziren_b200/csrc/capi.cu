@@ -7,10 +7,11 @@
 #include "open.h"
 #include "prover.h"
 #include "quotient.h"
+#include "quotient_codegen.h"
 #include "tracegen.h"
 
 using namespace zkb;
-namespace zkb { extern std::atomic<int> g_ntt_force_k2; extern std::atomic<int> g_eval_v2; extern std::atomic<int> g_ntt_lean; }
+namespace zkb { extern std::atomic<int> g_ntt_force_k2; extern std::atomic<int> g_eval_v2; extern std::atomic<int> g_ntt_lean; extern std::atomic<int> g_quotient_codegen; }
 
 // One prover object over one or several GPUs.  `c` (= *devs[0]) serves the kernel-level entry points;
 // commit routes every shard to the device with the fewest shards in flight, open follows the shard,
@@ -371,7 +372,7 @@ int zkb200_h2d_probe(zkb200_ctx* ctx, int mode, size_t row_bytes, size_t rows, s
       ZKB_CUDA(cudaMemcpy(work, &pp, sizeof(PullPiece), cudaMemcpyHostToDevice));
       ZKB_CUDA(cudaMemset((char*)work + sizeof(PullPiece), 0, 4));
       ZKB_CUDA(cudaEventRecord(e0, main_s));
-      pull_shard(reinterpret_cast<const PullPiece*>(work), 1, pull_piece_tiles(rows, pp.cols), (u32*)((char*)work + sizeof(PullPiece)), nstreams, main_s);
+      pull_shard(reinterpret_cast<const PullPiece*>(work), 1, pull_piece_tiles(rows, pp.cols), (u32*)((char*)work + sizeof(PullPiece)), nstreams < 0 ? -nstreams : nstreams, nstreams < 0, main_s);
       ZKB_CUDA(cudaEventRecord(e1, main_s)); ZKB_CUDA(cudaEventSynchronize(e1));
       cudaFree(work);
     } else {
@@ -401,11 +402,44 @@ int zkb200_h2d_probe(zkb200_ctx* ctx, int mode, size_t row_bytes, size_t rows, s
     cudaFree(dev);
   });
 }
+// CPU-side check of the run-time code generator: parse a ZKMD descriptor, generate every chip's constraint
+// kernel and compile it with NVRTC for sm_100a (no GPU needed).  Returns the number of chips compiled, or -1
+// (zkb200_last_error tells why); total cubin bytes in *bytes_out.
+int zkb200_codegen_compile_check(const uint32_t* desc, size_t n_words, size_t* bytes_out) {
+  int count = -1;
+  guarded(nullptr, [&] {
+    MachineInfo m;
+    m.parse(desc, n_words);
+    // chips compile in parallel (NVRTC is thread safe); results land in the kernel cache on disk
+    std::vector<size_t> bytes(m.chips.size(), 0);
+    std::vector<std::string> errs(m.chips.size());
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+      for (size_t i = next++; i < m.chips.size(); i = next++) {
+        bytes[i] = quotient_codegen_compile_only(m.chips[i]);
+        if (!bytes[i]) errs[i] = quotient_codegen_last_error();
+      }
+    };
+    std::vector<std::thread> th;
+    const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)m.chips.size()));
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(work);
+    for (auto& t : th) t.join();
+    size_t total = 0;
+    for (size_t i = 0; i < m.chips.size(); i++) {
+      if (!bytes[i]) throw std::runtime_error("zkb200: codegen for chip " + m.chips[i].name + ": " + errs[i]);
+      total += bytes[i];
+    }
+    if (bytes_out) *bytes_out = total;
+    count = (int)m.chips.size();
+  });
+  return count;
+}
 int zkb200_set_option(const char* key, long value) {
   const std::string k(key ? key : "");
   if (k == "ntt_k2") { g_ntt_force_k2 = (int)value; return 0; }
   if (k == "eval_v2") { g_eval_v2 = (int)value; return 0; }
   if (k == "ntt_lean") { g_ntt_lean = (int)value; return 0; }
+  if (k == "quotient_codegen") { g_quotient_codegen = (int)value; return 0; }
   g_err = "zkb200: unknown option " + k;
   return 1;
 }

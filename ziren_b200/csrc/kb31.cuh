@@ -5,8 +5,15 @@
 // R^2 mod p 0x17f7efe4; the reduction uses -p^-1 mod 2^32 = 0x7effffff, the negative of the
 // header's MONTY_MU 0x81000001).  EF4 per crates/stark/src/air/extension.rs:55-75.
 #pragma once
+#if defined(__CUDACC_RTC__)
+// NVRTC (run-time compiled constraint kernels, quotient_codegen.cpp): no host headers
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+#else
 #include <cstdint>
 #include <cstddef>
+#endif
 
 #if defined(__CUDACC__)
 #define KB_HD __host__ __device__ __forceinline__

@@ -41,9 +41,14 @@ void transpose_piece_to_colmajor(const u32* in, size_t in_pitch, u32* out, size_
 // 52 GB/s x ~2 us of latency is only ~100 KB in flight.
 // Rows of odd width are not 128-byte aligned: every warp loads the ALIGNED 128-byte lines that cover its
 // row segment (one extra line per 256 columns) instead of straddling two lines with every request.
-constexpr int PULL_TR = 32, PULL_TC = 256, PULL_LINES = PULL_TC / 32 + 1, PULL_THREADS = 256;
-__global__ void __launch_bounds__(PULL_THREADS) pull_shard_kernel(const PullPiece* __restrict__ pieces, int npieces,
-                                                                 unsigned long long total_tiles, u32* __restrict__ done) {
+constexpr int PULL_TR = 32, PULL_TC = 256, PULL_LINES = PULL_TC / 32 + 1;
+// NW warps per CTA.  NW = 8: a small CTA that shares its SM with the compute kernels.  NW = 32 ("exclusive",
+// ZKB200_PULL_EXCLUSIVE=1): 1024 threads and a 200 KB dynamic shared-memory request, so that the CTA owns
+// its SM and its PCIe reads do not queue behind the compute kernels' global loads in that SM's load path.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) pull_shard_kernel(const PullPiece* __restrict__ pieces, int npieces,
+                                                             unsigned long long total_tiles, u32* __restrict__ done) {
+  constexpr int PULL_THREADS = NW * 32, RPW = PULL_TR / NW;       // rows per warp
   __shared__ u32 tile[PULL_TC][PULL_TR + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int pi = 0;
@@ -53,12 +58,12 @@ __global__ void __launch_bounds__(PULL_THREADS) pull_shard_kernel(const PullPiec
     const unsigned long long local = tix - p.tile_begin;
     const size_t c0 = (size_t)(local % p.col_tiles) * PULL_TC, r0 = (size_t)(local / p.col_tiles) * PULL_TR;
     const size_t ncols = p.cols - c0 < (size_t)PULL_TC ? p.cols - c0 : (size_t)PULL_TC;
-    // 8 warps x 4 rows x 9 aligned lines: 36 independent loads per thread
-    u32 v[4][PULL_LINES];
-    long long first[4];
+    // NW warps x RPW rows x 9 aligned lines: 9 * RPW independent loads per thread
+    u32 v[RPW][PULL_LINES];
+    long long first[RPW];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const size_t r = r0 + warp * 4 + k;
+    for (int k = 0; k < RPW; k++) {
+      const size_t r = r0 + warp * RPW + k;
       const size_t g0 = r * p.pitch + p.word_off + c0;       // word index of (r, c0) from the 128-byte aligned base
       const size_t a0 = g0 & ~(size_t)31;
       first[k] = (long long)a0 - (long long)g0;             // column (relative to c0) of the line's first word: -31 .. 0
@@ -69,11 +74,11 @@ __global__ void __launch_bounds__(PULL_THREADS) pull_shard_kernel(const PullPiec
       }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < RPW; k++)
 #pragma unroll
       for (int j = 0; j < PULL_LINES; j++) {
         const long long cc = first[k] + 32 * j + lane;
-        if (cc >= 0 && cc < (long long)PULL_TC) tile[cc][warp * 4 + k] = v[k][j];
+        if (cc >= 0 && cc < (long long)PULL_TC) tile[cc][warp * RPW + k] = v[k][j];
       }
     __syncthreads();
     // columns leave as 128-byte runs of 32 rows
@@ -92,10 +97,15 @@ unsigned long long pull_piece_tiles(size_t rows, size_t cols) {
   return (unsigned long long)((cols + PULL_TC - 1) / PULL_TC) * ((rows + PULL_TR - 1) / PULL_TR);
 }
 unsigned pull_piece_col_tiles(size_t cols) { return (unsigned)((cols + PULL_TC - 1) / PULL_TC); }
-void pull_shard(const PullPiece* pieces_dev, int npieces, unsigned long long total_tiles, u32* done, int ctas, cudaStream_t s) {
+void pull_set_device_attributes() {
+  ZKB_CUDA(cudaFuncSetAttribute(pull_shard_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+}
+void pull_shard(const PullPiece* pieces_dev, int npieces, unsigned long long total_tiles, u32* done, int ctas, bool exclusive,
+                cudaStream_t s) {
   if (!npieces || !total_tiles) return;
   const unsigned grid = (unsigned)std::min<unsigned long long>(total_tiles, (unsigned long long)std::max(1, ctas));
-  pull_shard_kernel<<<grid, PULL_THREADS, 0, s>>>(pieces_dev, npieces, total_tiles, done);
+  if (exclusive) pull_shard_kernel<32><<<grid, 1024, 190 * 1024, s>>>(pieces_dev, npieces, total_tiles, done);
+  else pull_shard_kernel<8><<<grid, 256, 0, s>>>(pieces_dev, npieces, total_tiles, done);
   ZKB_CHECK_LAUNCH();
 }
 

@@ -22,7 +22,9 @@ struct PullPiece {
 };
 unsigned long long pull_piece_tiles(size_t rows, size_t cols);
 unsigned pull_piece_col_tiles(size_t cols);
-void pull_shard(const PullPiece* pieces_dev, int npieces, unsigned long long total_tiles, u32* done, int ctas, cudaStream_t s);
+void pull_set_device_attributes();     // once per device
+void pull_shard(const PullPiece* pieces_dev, int npieces, unsigned long long total_tiles, u32* done, int ctas, bool exclusive,
+                cudaStream_t s);
 void transpose_to_rowmajor(const u32* in, u32* out, size_t h, size_t w, cudaStream_t s);
 // converts between canonical and Montgomery form in place
 void to_monty_inplace(u32* d, size_t n, cudaStream_t s);

@@ -443,7 +443,7 @@ static void split_levels(int logn, int& K1, int& K2) {
   // size of the contiguous level, fastest measured split per log n (tools/k2_sweep.py on a B200 with the
   // lean strided kernels, profiles/r02_k2_sweep.jsonl): the contiguous level likes 2^10 / 2^11 (three
   // radix rounds of a 4096-element tile), the strided level two radix-16 rounds
-  static const int best_k2[25] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 9, 10, 10, 10, 10, 10, 11, 11, 11, 11, 12, 12};
+  static const int best_k2[25] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 9, 9, 9, 9, 10, 11, 11, 11, 11, 11, 12, 12};
   K2 = best_k2[logn];
   // experiment knob: size of the contiguous level (e.g. 12: 2^18 = 2^6 x 2^12, five radix rounds instead of six)
   static const int env_k2 = env_int("ZKB200_NTT_K2", 0);

@@ -42,7 +42,10 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
   ZKB_CUDA(cudaMalloc((void**)&pull_counters, PULL_COUNTER_RING * sizeof(u32)));
   ZKB_CUDA(cudaMemset(pull_counters, 0, PULL_COUNTER_RING * sizeof(u32)));
   if (wait_value && !wait_value.probe(lanes[0].stream, pull_counters)) wait_value.fn = nullptr;
+  if (const char* e = getenv("ZKB200_PULL_EXCLUSIVE")) pull_exclusive = atoi(e) != 0;
+  if (pull_exclusive) pull_ctas = 8;
   if (const char* e = getenv("ZKB200_PULL_CTAS")) pull_ctas = std::max(1, atoi(e));
+  pull_set_device_attributes();
   // keep freed blocks in the stream-ordered pool: shard proofs reuse the same sizes
   cudaMemPool_t pool;
   ZKB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -57,9 +60,10 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
   {
     size_t free_b = 0, total_b = 0;
     ZKB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    // default: a bounded reservation (32 GB or half of what is free) that covers 2^20..2^21-row shards; the
-    // pool still grows on demand for larger ones (the first such proof pays for the growth once)
-    size_t want = std::min<size_t>((size_t)32 << 30, free_b / 2);
+    // default: 96 GB or 55 % of what is free - three or four 2^20..2^21-row shards in flight (about 25 GB each);
+    // a smaller reservation (32 GB was tried) makes the pool grow in the middle of timed proofs (value arm
+    // 169 ms instead of 109 ms per shard).  ZKB200_POOL_GB sets it for a GPU shared with other tenants.
+    size_t want = std::min<size_t>((size_t)96 << 30, free_b / 20 * 11);
     if (const char* e = getenv("ZKB200_POOL_GB")) want = std::min<size_t>((size_t)atol(e) << 30, free_b * 9 / 10);
     if (want) {
       void* p = nullptr;
@@ -462,7 +466,7 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
       ZKB_CUDA(cudaEventCreateWithFlags(&pull_armed, cudaEventDisableTiming));
       events.v.push_back(pull_armed);
       ZKB_CUDA(cudaEventRecord(pull_armed, ctx.copy_stream));
-      pull_shard(reinterpret_cast<const PullPiece*>(pull_dev.p), (int)pull.size(), pull_tiles, pull_done, ctx.pull_ctas, ctx.copy_stream);
+      pull_shard(reinterpret_cast<const PullPiece*>(pull_dev.p), (int)pull.size(), pull_tiles, pull_done, ctx.pull_ctas, ctx.pull_exclusive, ctx.copy_stream);
       ZKB_CUDA(cudaEventCreateWithFlags(&pull_finished, cudaEventDisableTiming));
       events.v.push_back(pull_finished);
       ZKB_CUDA(cudaEventRecord(pull_finished, ctx.copy_stream));

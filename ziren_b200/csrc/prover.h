@@ -41,7 +41,7 @@ struct Lane {
   // start of a call that owns the lane: the previous call drained the stream before it returned
   void begin() { arena.reset(); keep.clear(); }
 };
-constexpr int NUM_LANES = 4;
+constexpr int NUM_LANES = 8;
 enum UploadMode { UPLOAD_PULL = 0, UPLOAD_DMA = 1, UPLOAD_DMA2D = 2 };
 
 // stream-ordered wait on a 32-bit device counter (>=): the driver's cuStreamWaitValue32, fetched at run
@@ -85,13 +85,17 @@ struct HostStager {
 struct Ctx {
   int device = 0;
   Lane lanes[NUM_LANES];
-  int active_lanes = 3;                 // ZKB200_LANES=1 serialises all compute on one stream
+  // More lanes than host threads in flight: a commit holds its lane while its upload is still queued
+  // behind another shard's, and an open() must not have to wait for such an idle lane (3 lanes and 4
+  // threads starved the opens: 151 ms per shard).  ZKB200_LANES=1 serialises all compute on one stream.
+  int active_lanes = 8;
   cudaStream_t copy_stream = nullptr;   // host->device uploads + layout change, overlaps the compute lanes
   std::mutex copy_mu;
   HostStager stager;                    // pageable host sources
   size_t piece_bytes = (size_t)256 << 20;   // column pieces of the main commit (prover_commit)
   int upload_mode = UPLOAD_PULL;        // pinned host traces (ZKB200_UPLOAD=pull|dma|dma2d), see prover_commit
   int pull_ctas = 32;                   // persistent CTAs of the pull kernel (ZKB200_PULL_CTAS)
+  bool pull_exclusive = false;          // 1024-thread CTAs that own their SM (ZKB200_PULL_EXCLUSIVE=1, 8 CTAs by default)
   StreamWaitValue wait_value;           // cuStreamWaitValue32: a lane waits for a counter of the pull kernel
   static constexpr size_t PULL_COUNTER_RING = 1 << 16;
   u32* pull_counters = nullptr;         // ring of counters (cudaMalloc), slices handed out under copy_mu

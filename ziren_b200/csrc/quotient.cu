@@ -5,68 +5,22 @@
 // bytecode (machine.cpp); all threads execute the same instruction stream, so there is no
 // divergence and instruction fetches are broadcast.
 #include "quotient.h"
+#include <atomic>
+#include <cstdlib>
+#include "quotient_codegen.h"
+#include "quotient_rt.cuh"
 
 namespace zkb {
 
-struct QuotArgs {
-  const u32* prep; const u32* main_; const u32* perm;
-  size_t H;
-  u32 log_n, lqd;
-  u32 ew, batch, main_width, global_scope;
-  const Instr* code; u32 code_begin, code_end, n_air;
-  const DevTerm* terms; const DevVPC* vpcs; const DevLookup* lookups; u32 lk_begin, lk_end;
-  const u32* alpha_pow;   // [C][4] Montgomery: alpha^(C-1-k)
-  const u32* consts;      // constant pool (Montgomery)
-  const u32* pub;
-  const u32* tw_lo; const u32* tw_hi;
-  Ef perm_alpha, local_sum;
-  Ef bpow[17];
-  u32 gsum[14];
-  u32 zh[16], inv_zh[16];    // Z_H on the coset takes 2^lqd values
-  u32 gen, ginv;             // GENERATOR, g_n^-1 (Montgomery)
-  u32* out;
-};
-
-__device__ __forceinline__ Fp q_eval_vpc(const QuotArgs& a, u32 vi, size_t row) {
-  DevVPC v = a.vpcs[vi];
-  Fp acc = fp_raw(v.constant);
-  for (u32 t = v.term_begin; t < v.term_end; t++) {
-    DevTerm tm = a.terms[t];
-    const u32* base = (tm.col & 0x80000000u) ? a.main_ : a.prep;
-    acc += fp_raw(base[(size_t)(tm.col & 0x7fffffffu) * a.H + row]) * fp_raw(tm.w);
-  }
-  return acc;
-}
-__device__ __forceinline__ Ef load_ef(const u32* base, size_t H, u32 col4, size_t row) {
-  Ef e;
-#pragma unroll
-  for (int c = 0; c < 4; c++) e.c[c] = fp_raw(base[(size_t)(col4 + c) * H + row]);
-  return e;
-}
-__device__ __forceinline__ Ef load_apow(const u32* ap, u32 k) {
-  uint4 v = __ldg(reinterpret_cast<const uint4*>(ap) + k);
-  Ef e; e.c[0] = fp_raw(v.x); e.c[1] = fp_raw(v.y); e.c[2] = fp_raw(v.z); e.c[3] = fp_raw(v.w);
-  return e;
-}
+std::atomic<int> g_quotient_codegen{1};     // zkb200_set_option("quotient_codegen"); ZKB200_QUOTIENT=interp turns it off
 
 constexpr int QCHUNK = 1024;   // 16 KB of bytecode per stage
 
 template <int NREGS>
 __global__ void __launch_bounds__(128) quotient_kernel(QuotArgs a) {
-  const u32 lq = a.log_n + a.lqd;
-  const size_t Q = (size_t)1 << lq;
-  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  const bool active = t < Q;
-  if (!active) t = Q - 1;          // keep every thread in the barriers below; result discarded
-  const u32 i = bitrev32((u32)t, lq);
-  const size_t tn = bitrev32((u32)((i + (1u << a.lqd)) & (Q - 1)), lq);
-
-  // selectors at x = GENERATOR * w_Q^i   (crates/recursion/circuit/src/domain.rs:46-64)
-  Fp x = fp_raw(a.gen) * tw_pow2(a.tw_lo, a.tw_hi, i << (24 - lq));
-  Fp zh = fp_raw(a.zh[i & ((1u << a.lqd) - 1)]);
-  Fp d1 = x - fp_one(), d2 = x - fp_raw(a.ginv);
-  Fp inv12 = fp_inv(d1 * d2);
-  Fp is_first = zh * (inv12 * d2), is_last = zh * (inv12 * d1), is_trans = d2;
+  const QuotRow row = q_prologue(a);
+  const size_t t = row.t, tn = row.tn;
+  const Fp is_first = row.is_first, is_last = row.is_last, is_trans = row.is_trans;
 
   Fp regs[NREGS];
   EfAcc lazy;     // base-field constraints: alpha-power x value, reduced every fourth assert
@@ -114,57 +68,8 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotArgs a) {
   }
 
   Ef acc = lazy.value();
-  // permutation constraints (permutation.rs:205-347)
-  u32 k = a.n_air;
-  if (a.ew) {
-    u32 lk = a.lk_begin;
-    Ef sum_local = ef_zero(), sum_next = ef_zero();
-    for (u32 b = 0; b + 1 < a.ew; b++) {
-      Ef rlc[8];
-      Fp mult[8];
-      u32 cnt = 0;
-      for (; cnt < a.batch && lk < a.lk_end; cnt++, lk++) {
-        DevLookup l = a.lookups[lk];
-        Ef r = a.perm_alpha + fp_raw(l.kind);
-        u32 j = 1;
-        for (u32 vi = l.value_begin; vi < l.value_end; vi++, j++) r += a.bpow[j] * q_eval_vpc(a, vi, t);
-        Fp mu = q_eval_vpc(a, l.mult_vpc, t);
-        rlc[cnt] = r;
-        mult[cnt] = l.is_send ? mu : -mu;
-      }
-      Ef product = ef_one(), numerator = ef_zero();
-      for (u32 p = 0; p < cnt; p++) {
-        product *= rlc[p];
-        Ef abc = ef_one();
-        for (u32 q = 0; q < cnt; q++) if (q != p) abc *= rlc[q];
-        numerator += abc * mult[p];
-      }
-      Ef entry = load_ef(a.perm, a.H, 4 * b, t);
-      acc += load_apow(a.alpha_pow, k++) * (product * entry - numerator);
-      sum_local += entry;
-      sum_next += load_ef(a.perm, a.H, 4 * b, tn);
-    }
-    Ef phi_local = load_ef(a.perm, a.H, 4 * (a.ew - 1), t), phi_next = load_ef(a.perm, a.H, 4 * (a.ew - 1), tn);
-    acc += load_apow(a.alpha_pow, k++) * ((phi_local - sum_local) * is_first);
-    acc += load_apow(a.alpha_pow, k++) * ((phi_next - phi_local - sum_next) * is_trans);
-    acc += load_apow(a.alpha_pow, k++) * ((phi_local - a.local_sum) * is_last);
-  }
-  if (a.global_scope) {
-    for (int g = 0; g < 7; g++) {
-      Fp mx = fp_raw(a.main_[(size_t)(a.main_width - 14 + g) * a.H + t]);
-      Fp my = fp_raw(a.main_[(size_t)(a.main_width - 7 + g) * a.H + t]);
-      acc += load_apow(a.alpha_pow, k++) * (is_last * (mx - fp_raw(a.gsum[g])));
-      acc += load_apow(a.alpha_pow, k++) * (is_last * (my - fp_raw(a.gsum[7 + g])));
-    }
-  }
-  Ef q = acc * fp_raw(a.inv_zh[i & ((1u << a.lqd) - 1)]);
-  // chunk j = i mod 2^lqd, row k = i >> lqd (quotient_domain.split_evals, prover.rs:477-488)
-  const size_t n = (size_t)1 << a.log_n;
-  u32* o = a.out + (size_t)(i & ((1u << a.lqd) - 1)) * 4 * n + (i >> a.lqd);
-  if (active) {
-#pragma unroll
-    for (int c = 0; c < 4; c++) o[(size_t)c * n] = q.c[c].v;
-  }
+  q_lookup_constraints(a, row, acc, a.n_air);
+  q_epilogue(a, row, acc);
 }
 
 __global__ void alpha_pow_kernel(u32* out, u32 C, Ef alpha) {
@@ -214,6 +119,16 @@ void quotient_values(const MachineInfo& m, const ChipInfo& chip, const NttTables
   a.out = out;
   const size_t Q = n << a.lqd;
   const unsigned grid = ceil_div(Q, 128);
+  // generated straight-line kernel for this chip (NVRTC, quotient_codegen.cpp); the interpreter below is
+  // the fallback and, with zkb200_set_option("quotient_codegen", 0), the implementation it is tested against
+  if (g_quotient_codegen.load()) {
+    if (void* k = quotient_generated_kernel(chip)) {
+      void* params[] = {&a};
+      ZKB_CUDA(cudaLaunchKernel((const void*)k, dim3(grid), dim3(128), params, 0, s));
+      ZKB_CHECK_LAUNCH();
+      return;
+    }
+  }
   if (chip.n_regs <= 32) quotient_kernel<32><<<grid, 128, 0, s>>>(a);
   else if (chip.n_regs <= 128) quotient_kernel<128><<<grid, 128, 0, s>>>(a);
   else if (chip.n_regs <= 512) quotient_kernel<512><<<grid, 128, 0, s>>>(a);

@@ -1,0 +1,40 @@
+"""Build-time step: generate and compile (NVRTC, sm_100a, no GPU needed) the per-chip constraint kernels
+of the machines the tests and bench.py use, into the in-tree kernel cache next to libzkb200.so
+(`ziren_b200/_kernel_cache/`, which travels with the library).  A chip that is not in the cache is simply
+compiled the first time it is proved (csrc/quotient_codegen.cpp)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi, synthetic
+
+
+def machines():
+    yield "mini", synthetic.mini_case().machine
+    yield "edge", synthetic.edge_case().machine
+    yield "noprep", synthetic.noprep_case().machine
+    yield "fibonacci", synthetic.fibonacci_core_case(log_cpu=8).machine
+    yield "core", synthetic.core_case(log_cpu=9).machine
+    yield "keccak", synthetic.keccak_case(log_cpu=8).machine
+    yield "compress", synthetic.compress_case(log_max=9).machine
+
+
+def precompile(verbose: bool = False) -> int:
+    total = 0
+    for name, m in machines():
+        desc = np.ascontiguousarray(m.descriptor(), dtype=np.uint32)
+        n = C.c_size_t()
+        rc = _ffi.lib().zkb200_codegen_compile_check(desc.ctypes.data_as(_ffi.u32p), desc.size, C.byref(n))
+        if rc < 0:
+            raise RuntimeError(f"constraint-kernel generation failed for machine {name}: "
+                               + _ffi.lib().zkb200_last_error(None).decode())
+        total += rc
+        if verbose:
+            print(f"  {name}: {rc} chips, {n.value} cubin bytes")
+    return total
+
+
+if __name__ == "__main__":
+    print(precompile(verbose=True), "constraint kernels in the cache")
