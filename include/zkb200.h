@@ -85,6 +85,7 @@ int zkb200_ctx_num_devices(const zkb200_ctx* ctx);
 int zkb200_set_option(const char* key, long value);
 /* The constraint kernels (K3) are generated per chip from the ZKMD descriptor and compiled with NVRTC at run
  * time.  This entry point does only that (no GPU needed): chips compiled, or -1; total cubin bytes out. */
+void zkb200_quotient_launch_counts(unsigned long long* generated, unsigned long long* interpreted);
 int zkb200_codegen_compile_check(const uint32_t* desc, size_t n_words, size_t* bytes_out);
 /* tools/h2d_probe.py: time one pass of a pinned row-major `rows x row_bytes` buffer over PCIe.  mode 0: 2-D DMA
  * in column slices of seg_bytes over n concurrent streams; 1: the pull kernel with n CTAs; 2: contiguous DMA in n parts. */

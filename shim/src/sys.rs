@@ -1,0 +1,33 @@
+//! Raw bindings of `include/zkb200.h` (the C ABI of libzkb200.so).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct zkb200_trace {
+    pub name: *const c_char,
+    pub data: *const u32, // row-major height x width, Montgomery: RowMajorMatrix<KoalaBear>::values as is
+    pub height: usize,
+    pub width: usize,
+}
+pub enum zkb200_ctx {}
+pub enum zkb200_pk {}
+pub enum zkb200_shard {}
+
+extern "C" {
+    pub fn zkb200_ctx_create(device: c_int, desc: *const u32, n_words: usize, out: *mut *mut zkb200_ctx) -> c_int;
+    pub fn zkb200_ctx_create_multi(devices: *const c_int, n_devices: c_int, desc: *const u32, n_words: usize,
+                                   out: *mut *mut zkb200_ctx) -> c_int;
+    pub fn zkb200_ctx_num_devices(ctx: *const zkb200_ctx) -> c_int;
+    pub fn zkb200_ctx_destroy(ctx: *mut zkb200_ctx);
+    pub fn zkb200_last_error(ctx: *mut zkb200_ctx) -> *const c_char;
+    pub fn zkb200_setup(ctx: *mut zkb200_ctx, prep: *const zkb200_trace, n: c_int, pc_start: u32,
+                        init_global_sum: *const u32, commit_out: *mut u32, out: *mut *mut zkb200_pk) -> c_int;
+    pub fn zkb200_pk_free(pk: *mut zkb200_pk);
+    pub fn zkb200_pk_initial_challenger(pk: *const zkb200_pk, challenger: *mut u32) -> c_int;
+    pub fn zkb200_commit(ctx: *mut zkb200_ctx, traces: *const zkb200_trace, n: c_int, public_values: *const u32,
+                         n_public_values: usize, commit_out: *mut u32, out: *mut *mut zkb200_shard) -> c_int;
+    pub fn zkb200_shard_free(shard: *mut zkb200_shard);
+    pub fn zkb200_open(ctx: *mut zkb200_ctx, pk: *const zkb200_pk, shard: *mut zkb200_shard, challenger: *mut u32,
+                       proof_words: *mut *mut u32, n_words: *mut usize) -> c_int;
+    pub fn zkb200_free(p: *mut c_void);
+}

@@ -152,11 +152,21 @@ def test_quotient_matches_oracle(torch, mini, oracle, codegen):
     """K3 both ways: the per-chip kernels generated and compiled at run time (NVRTC) and the bytecode
     interpreter they replace, each bit-exact against the oracle for every chip of the machine."""
     from ziren_b200 import _ffi
+    import ctypes as C
     _ffi.lib().zkb200_set_option(b"quotient_codegen", codegen)
+    g0, i0 = C.c_ulonglong(), C.c_ulonglong()
+    _ffi.lib().zkb200_quotient_launch_counts(C.byref(g0), C.byref(i0))
     try:
         _quotient_matches_oracle(torch, mini, oracle)
     finally:
         _ffi.lib().zkb200_set_option(b"quotient_codegen", 1)
+    g1, i1 = C.c_ulonglong(), C.c_ulonglong()
+    _ffi.lib().zkb200_quotient_launch_counts(C.byref(g1), C.byref(i1))
+    # the path under test is the one that ran (a generated kernel that failed to build would fall back silently)
+    if codegen:
+        assert g1.value > g0.value and i1.value == i0.value
+    else:
+        assert i1.value > i0.value and g1.value == g0.value
 
 
 def _quotient_matches_oracle(torch, mini, oracle):

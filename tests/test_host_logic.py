@@ -176,3 +176,42 @@ def test_constraint_kernels_are_generated_and_compile_without_a_gpu():
     rc = _ffi.lib().zkb200_codegen_compile_check(desc.ctypes.data_as(_ffi.u32p), desc.size, C.byref(n))
     assert rc == len(m.chips), _ffi.lib().zkb200_last_error(None).decode()
     assert n.value > 10000
+
+
+def test_zkpf_decoder_follows_the_reference_proof_types(oracle):
+    """ziren_b200/proof.py (the Python twin of shim/src/proof.rs::decode_zkpf) yields the fields of the reference's
+    ShardProof / ChipOpenedValues / AirOpenedValues (crates/stark/src/types.rs:38-83) and of Plonky3's FriProof
+    (mirrored in crates/recursion/circuit/src/types.rs:35-75), in that nesting; when the reference checkout is
+    present the field names are read from it."""
+    from ziren_b200 import proof as zkproof
+    case = synthetic.mini_case()
+    om = oracle.OracleMachine(case.machine)
+    om.setup(case.prep)
+    words, _ = om.prove_shard(case.traces, case.public_values)
+    p = zkproof.parse(words)
+    want = {"ShardProof": ["commitment", "opened_values", "opening_proof", "chip_ordering", "public_values"],
+            "ShardCommitment": ["main_commit", "permutation_commit", "quotient_commit"],
+            "ChipOpenedValues": ["preprocessed", "main", "permutation", "quotient", "global_cumulative_sum",
+                                 "local_cumulative_sum", "log_degree"],
+            "AirOpenedValues": ["local", "next"]}
+    ref = "/root/reference/crates/stark/src/types.rs"
+    if os.path.exists(ref):
+        src = open(ref).read()
+        for struct, fields in want.items():
+            body = re.search(r"pub struct %s<[^{]*\{(.*?)\n\}" % struct, src, re.S).group(1)
+            assert re.findall(r"pub (\w+):", body) == fields, struct
+    assert list(p) == want["ShardProof"]
+    assert list(p["commitment"]) == want["ShardCommitment"]
+    chip = p["opened_values"]["chips"][0]
+    assert want["ChipOpenedValues"] == [k for k in chip if k != "name"]
+    assert list(chip["main"]) == want["AirOpenedValues"]
+    fri = p["opening_proof"]
+    assert set(fri) == {"commit_phase_commits", "query_proofs", "final_poly", "pow_witness"}
+    q = fri["query_proofs"][0]
+    assert list(q) == ["input_proof", "commit_phase_openings"]
+    assert list(q["input_proof"][0]) == ["opened_values", "opening_proof"]
+    assert list(q["commit_phase_openings"][0]) == ["sibling_value", "opening_proof"]
+    # the Rust decoder reads the words in the same order: its source mentions every field
+    rust = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shim", "src", "proof.rs")).read()
+    for name in sum(want.values(), []) + ["commit_phase_commits", "query_proofs", "final_poly", "pow_witness", "sibling_value"]:
+        assert name in rust, name

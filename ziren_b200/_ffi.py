@@ -30,6 +30,7 @@ SIGNATURES = {
     "zkb200_ctx_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, u32p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "zkb200_ctx_num_devices": (C.c_int, [C.c_void_p]),
     "zkb200_set_option": (C.c_int, [C.c_char_p, C.c_long]),
+    "zkb200_quotient_launch_counts": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "zkb200_codegen_compile_check": (C.c_int, [u32p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "zkb200_h2d_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_float)]),
     "zkb200_ctx_destroy": (None, [C.c_void_p]),

@@ -11,7 +11,8 @@
 #include "tracegen.h"
 
 using namespace zkb;
-namespace zkb { extern std::atomic<int> g_ntt_force_k2; extern std::atomic<int> g_eval_v2; extern std::atomic<int> g_ntt_lean; extern std::atomic<int> g_quotient_codegen; }
+namespace zkb { extern std::atomic<int> g_ntt_force_k2; extern std::atomic<int> g_eval_v2; extern std::atomic<int> g_ntt_lean; extern std::atomic<int> g_quotient_codegen;
+               extern std::atomic<unsigned long long> g_quotient_generated_launches, g_quotient_interpreter_launches; }
 
 // One prover object over one or several GPUs.  `c` (= *devs[0]) serves the kernel-level entry points;
 // commit routes every shard to the device with the fewest shards in flight, open follows the shard,
@@ -433,6 +434,11 @@ int zkb200_codegen_compile_check(const uint32_t* desc, size_t n_words, size_t* b
     count = (int)m.chips.size();
   });
   return count;
+}
+// constraint-kernel launches so far: generated (NVRTC) and interpreter
+void zkb200_quotient_launch_counts(unsigned long long* generated, unsigned long long* interpreted) {
+  if (generated) *generated = g_quotient_generated_launches.load();
+  if (interpreted) *interpreted = g_quotient_interpreter_launches.load();
 }
 int zkb200_set_option(const char* key, long value) {
   const std::string k(key ? key : "");

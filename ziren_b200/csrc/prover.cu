@@ -34,7 +34,7 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
     ZKB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     ZKB_CUDA(cudaStreamCreateWithPriority(&copy_stream, cudaStreamNonBlocking, hi));
   }
-  if (const char* e = getenv("ZKB200_UPLOAD")) upload_mode = std::string(e) == "dma" ? UPLOAD_DMA : std::string(e) == "dma2d" ? UPLOAD_DMA2D : UPLOAD_PULL;
+  if (const char* e = getenv("ZKB200_UPLOAD")) upload_mode = std::string(e) == "pull" ? UPLOAD_PULL : std::string(e) == "dma2d" ? UPLOAD_DMA2D : UPLOAD_DMA;
   // counters the pull kernel bumps and the lanes wait on: plain cudaMalloc memory (stream memory
   // operations do not take stream-ordered pool allocations), handed out as a ring; probed once here -
   // a driver that refuses the wait turns the pull mode off (2-D DMA instead)
@@ -385,6 +385,15 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
       pieces.push_back(std::move(p));
     }
   }
+  // The widest matrix crosses first: while the small ones follow, its LDE and leaf hashing already run
+  // (the commitment does not depend on the order the pieces are processed in: LDEs land in their matrix's
+  // slot and each piecewise-hashed matrix keeps its own sponge states).
+  std::stable_sort(pieces.begin(), pieces.end(), [&](const Piece& a, const Piece& b) {
+    const size_t sa = traces[a.mat].height * traces[a.mat].width, sb = traces[b.mat].height * traces[b.mat].width;
+    if (sa != sb) return sa > sb;
+    if (a.mat != b.mat) return a.mat < b.mat;
+    return a.col0 < b.col0;
+  });
   // Phase 1 (copy stream, its own lock): the traces cross PCIe.  Other host threads may hold the compute
   // lanes meanwhile, the way the reference keeps several shards in flight
   // (crates/core/machine/src/utils/prove.rs:487-521).  Three kinds of source:

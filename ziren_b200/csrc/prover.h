@@ -93,7 +93,10 @@ struct Ctx {
   std::mutex copy_mu;
   HostStager stager;                    // pageable host sources
   size_t piece_bytes = (size_t)256 << 20;   // column pieces of the main commit (prover_commit)
-  int upload_mode = UPLOAD_PULL;        // pinned host traces (ZKB200_UPLOAD=pull|dma|dma2d), see prover_commit
+  // pinned host traces (ZKB200_UPLOAD=dma|pull|dma2d), see prover_commit.  Measured on the bench shard (ms per
+  // shard, 4 threads / 1 thread in flight): dma 122.9 / 198.7, pull 144.5 / 204.3, dma2d 268.9 / 343.6 -
+  // the SM-driven gathers (pull, 2-D DMA) run at 48-51 GB/s alone but at ~31 GB/s next to the compute kernels.
+  int upload_mode = UPLOAD_DMA;
   int pull_ctas = 32;                   // persistent CTAs of the pull kernel (ZKB200_PULL_CTAS)
   bool pull_exclusive = false;          // 1024-thread CTAs that own their SM (ZKB200_PULL_EXCLUSIVE=1, 8 CTAs by default)
   StreamWaitValue wait_value;           // cuStreamWaitValue32: a lane waits for a counter of the pull kernel

@@ -12,6 +12,7 @@
 
 namespace zkb {
 
+std::atomic<unsigned long long> g_quotient_generated_launches{0}, g_quotient_interpreter_launches{0};
 std::atomic<int> g_quotient_codegen{1};     // zkb200_set_option("quotient_codegen"); ZKB200_QUOTIENT=interp turns it off
 
 constexpr int QCHUNK = 1024;   // 16 KB of bytecode per stage
@@ -126,9 +127,11 @@ void quotient_values(const MachineInfo& m, const ChipInfo& chip, const NttTables
       void* params[] = {&a};
       ZKB_CUDA(cudaLaunchKernel((const void*)k, dim3(grid), dim3(128), params, 0, s));
       ZKB_CHECK_LAUNCH();
+      g_quotient_generated_launches++;
       return;
     }
   }
+  g_quotient_interpreter_launches++;
   if (chip.n_regs <= 32) quotient_kernel<32><<<grid, 128, 0, s>>>(a);
   else if (chip.n_regs <= 128) quotient_kernel<128><<<grid, 128, 0, s>>>(a);
   else if (chip.n_regs <= 512) quotient_kernel<512><<<grid, 128, 0, s>>>(a);

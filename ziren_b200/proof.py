@@ -38,6 +38,7 @@ def parse(words) -> dict:
         c["quotient"] = r.take(16 * nq).reshape(nq, 4, 4)
         c["global_cumulative_sum"] = r.take(14)
         c["local_cumulative_sum"] = r.take(4)
+        c["log_degree"] = c.pop("log_degree")            # field order of ChipOpenedValues (types.rs:51-64)
         chips.append(c)
     p["opened_values"] = {"chips": chips}
     p["chip_ordering"] = {c["name"]: i for i, c in enumerate(chips)}
@@ -58,4 +59,5 @@ def parse(words) -> dict:
     fri["query_proofs"] = qs
     p["opening_proof"] = fri
     assert r.i == r.w.size, "trailing words in proof"
-    return p
+    # field order of ShardProof (crates/stark/src/types.rs:76-83)
+    return {k: p[k] for k in ("commitment", "opened_values", "opening_proof", "chip_ordering", "public_values")}
