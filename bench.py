@@ -64,6 +64,7 @@ def bind_to_gpu_numa_node(torch, index):
 
 
 def make_case(args, sample=False):
+    synthetic.CONSTRAINTS_PER_GROUP = args.constraint_density
     w = args.workload
     lc = args.sample_log_cpu if sample else args.log_cpu
     if w == "keccak":
@@ -86,6 +87,7 @@ def workload_config(args, case, sample=False):
                          "setup (preprocessed commit) inside every proof as crates/prover/src/lib.rs:809-832 does" % lc}
     return {"workload": names[args.workload], "cycles_per_shard": case.cycles, "cells_per_shard": case.cells,
             "trace_bytes_per_shard": case.trace_bytes, "fri": {"log_blowup": 1, "num_queries": 84, "pow_bits": 16},
+            "constraints_per_6_columns": args.constraint_density,
             "l2_policy": "inputs larger than L2 (trace bytes >> 126 MB); fresh shard allocations every step",
             "parallelism": f"shard-per-gpu x{args.gpus}", "shards_in_flight_per_gpu": {"value": args.value_threads, "e2e": args.e2e_threads},
             **({"total_shards": args.shards, "shards_per_rank": len(range(args.rank, args.shards, args.world))} if args.shards else {})}
@@ -175,6 +177,8 @@ def main():
                          "(BASELINE configs[2]: --workload core --log-cpu 21 --shards 18; configs[4]: --workload compress --log-cpu 18 --shards 127)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--constraint-density", type=int, default=2,
+                    help="constraints per 6-column group of the synthetic tables: 2 (default) ... 12 (about 2 per column)")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host e2e figure")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle verifier's check of the timed proof")
     ap.add_argument("--value-threads", type=int, default=3,
@@ -418,7 +422,8 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1):
 
 def measure_cpu_baseline(args):
     out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--workload", args.workload, "--log-cpu", str(args.log_cpu), "--sample-log-cpu", str(args.sample_log_cpu)],
+                          "--workload", args.workload, "--log-cpu", str(args.log_cpu), "--sample-log-cpu", str(args.sample_log_cpu),
+                          "--constraint-density", str(args.constraint_density)],
                          capture_output=True, text=True, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
     try:
         return json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]

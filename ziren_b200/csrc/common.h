@@ -65,8 +65,15 @@ struct DevMat {
   DevMat(size_t h, size_t w, cudaStream_t s) : buf(h * w, s), height(h), width(w) {}
 };
 
+// Small host -> device transfers issued on a COMPUTE stream must not go through the copy engine: a
+// cudaMemcpyAsync(HostToDevice) queues behind the multi-GB trace upload another shard has in flight on the
+// copy stream (one H2D engine, FIFO) and stalls the lane until that upload ends - measured: four shards in
+// flight ran as slowly as one (191 ms per shard instead of 123).  So the words are written into pinned,
+// device-mapped host memory and a tiny kernel on the lane's stream pulls them over PCIe (layout.cu).
+void pull_words(u32* dst_dev, const u32* src_pinned_mapped, size_t n_words, cudaStream_t s);
+
 // Bump arena for small tables handed to kernels (matrix lists, opening schedules...):
-// written into pinned host memory, copied in-stream, recycled when the owner knows the stream
+// written into pinned host memory, pulled in-stream by a kernel, recycled when the owner knows the stream
 // has drained.
 struct ParamArena {
   char* host = nullptr;
@@ -75,7 +82,7 @@ struct ParamArena {
   cudaStream_t stream = nullptr;
   void init(size_t bytes, cudaStream_t s) {
     cap = bytes; stream = s;
-    ZKB_CUDA(cudaMallocHost((void**)&host, bytes));
+    ZKB_CUDA(cudaHostAlloc((void**)&host, bytes, cudaHostAllocMapped));
     ZKB_CUDA(cudaMalloc((void**)&dev, bytes));
   }
   void destroy() {
@@ -89,7 +96,7 @@ struct ParamArena {
     size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
     if (used + bytes > cap) throw std::runtime_error("zkb200: parameter arena exhausted");
     memcpy(host + used, data, n * sizeof(T));
-    ZKB_CUDA(cudaMemcpyAsync(dev + used, host + used, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+    pull_words((u32*)(dev + used), (const u32*)(host + used), (n * sizeof(T) + 3) / 4, stream);
     T* r = (T*)(dev + used);
     used += bytes;
     return r;

@@ -69,12 +69,13 @@ __global__ void __launch_bounds__(128, 16) leaf_hash_kernel(const MatRef* __rest
 
 static size_t leaf_smem_for(size_t nblocks);
 
-// Piecewise leaf hashing: the sponge over a wide matrix is absorbed in column pieces as their LDEs
-// are produced (the upload of the next piece overlaps, prover_commit), the 16-word state of every
-// row parked in HBM between pieces (SoA [16][height]).  Every piece but the last is a whole number of
-// rate blocks (8 columns); the last one takes the ragged tail (PaddingFreeSponge: a short block
-// overwrites state[0..len) only) and writes the digests.
-__global__ void __launch_bounds__(128, 16) leaf_absorb_kernel(const u32* __restrict__ cols, size_t height, u32 ncols,
+// Piecewise leaf hashing: the sponge over the concatenated rows of one height class (its matrices in
+// commit order) is absorbed in column pieces as their LDEs are produced (the upload of the next piece
+// overlaps, prover_commit), the 16-word state of every row parked in HBM between pieces (SoA
+// [16][height]).  A piece is a list of column pointers, so it may straddle matrices; every piece but
+// the last is a whole number of rate blocks (8 columns), the last one takes the ragged tail
+// (PaddingFreeSponge: a short block overwrites state[0..len) only) and writes the digests.
+__global__ void __launch_bounds__(128, 16) leaf_absorb_kernel(const u32* const* __restrict__ cols, size_t height, u32 ncols,
                                                           u32* __restrict__ state, int first, int last,
                                                           u32* __restrict__ digests) {
   size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -87,17 +88,15 @@ __global__ void __launch_bounds__(128, 16) leaf_absorb_kernel(const u32* __restr
 #pragma unroll
     for (int i = 0; i < 16; i++) st[i] = fp_raw(state[(size_t)i * height + r]);
   }
-  const u32* __restrict__ p = cols + r;
   u32 c = 0;
   for (; c + 8 <= ncols; c += 8) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) st[i] = fp_raw(p[(size_t)i * height]);
-    p += 8 * height;
+    for (int i = 0; i < 8; i++) st[i] = fp_raw(cols[c + i][r]);      // the column pointers are warp-uniform
     p2_permute_dev(st);
   }
-  if (c < ncols) {   // ragged tail (last piece only)
+  if (c < ncols) {   // ragged tail (last piece of the height class only)
 #pragma unroll
-    for (int i = 0; i < 8; i++) if (c + i < ncols) st[i] = fp_raw(p[(size_t)i * height]);
+    for (int i = 0; i < 8; i++) if (c + i < ncols) st[i] = fp_raw(cols[c + i][r]);
     p2_permute_dev(st);
   }
   if (last) {
@@ -108,10 +107,11 @@ __global__ void __launch_bounds__(128, 16) leaf_absorb_kernel(const u32* __restr
     for (int i = 0; i < 16; i++) state[(size_t)i * height + r] = st[i].v;
   }
 }
-void leaf_absorb(const u32* cols, size_t height, u32 ncols, u32* state, bool first, bool last, u32* digests, cudaStream_t s) {
+void leaf_absorb(const u32* const* cols_dev, size_t height, u32 ncols, u32* state, bool first, bool last, u32* digests, cudaStream_t s) {
   if (!last && (ncols & 7)) throw std::runtime_error("zkb200: leaf_absorb: a non-final piece must be whole rate blocks");
+  if (!ncols && !last) return;
   const unsigned nblocks = ceil_div(height, 128);
-  leaf_absorb_kernel<<<nblocks, 128, leaf_smem_for(nblocks), s>>>(cols, height, ncols, state, first ? 1 : 0, last ? 1 : 0, digests);
+  leaf_absorb_kernel<<<nblocks, 128, leaf_smem_for(nblocks), s>>>(cols_dev, height, ncols, state, first ? 1 : 0, last ? 1 : 0, digests);
   ZKB_CHECK_LAUNCH();
 }
 
@@ -311,7 +311,8 @@ u32 grind_witness(const u32 st[16], unsigned n_in, unsigned bits, u32* scratch_d
   const u32 mask = (1u << bits) - 1;
   const u32 batch = 1u << 20;
   u32 init = 0xffffffffu, found = 0xffffffffu;
-  ZKB_CUDA(cudaMemcpyAsync(scratch_dev, &init, 4, cudaMemcpyHostToDevice, s));
+  (void)init;
+  ZKB_CUDA(cudaMemsetAsync(scratch_dev, 0xff, 4, s));      // no host->device copy on a compute lane (common.h: pull_words)
   for (u64 base = 0; base < KB_P; base += batch) {
     grind_kernel<<<batch / 256, 256, 0, s>>>(a, n_in, mask, (u32)base, scratch_dev);
     ZKB_CHECK_LAUNCH();

@@ -33,8 +33,9 @@ struct DigestLayers {
 // height (leaf_absorb below); those groups are not hashed again.
 void merkle_build(const std::vector<MatRef>& mats, ParamArena& arena, DigestLayers& out, u32* root_dev, cudaStream_t s,
                   const std::map<unsigned, const u32*>* pre = nullptr);
-// One column piece of a matrix into the per-row sponge states (state: [16][height] words); see hash.cu.
-void leaf_absorb(const u32* cols, size_t height, u32 ncols, u32* state, bool first, bool last, u32* digests, cudaStream_t s);
+// One piece (a device array of column pointers, all of `height` rows) of a height class into the per-row
+// sponge states (state: [16][height] words); see hash.cu.
+void leaf_absorb(const u32* const* cols_dev, size_t height, u32 ncols, u32* state, bool first, bool last, u32* digests, cudaStream_t s);
 
 // Tree over one FRI commit-phase layer: folded = m EF values, component-major [4][m].
 void fri_commit_layer(const u32* folded, size_t m, DigestLayers& out, u32* root_dev, cudaStream_t s);

@@ -109,6 +109,19 @@ void pull_shard(const PullPiece* pieces_dev, int npieces, unsigned long long tot
   ZKB_CHECK_LAUNCH();
 }
 
+// see common.h: small parameter tables cross PCIe by SM loads from mapped pinned memory, not by the copy engine
+__global__ void pull_words_kernel(u32* __restrict__ dst, const u32* __restrict__ src, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __ldcs(src + i);
+}
+void pull_words(u32* dst_dev, const u32* src_pinned_mapped, size_t n_words, cudaStream_t s) {
+  if (!n_words) return;
+  const u32* mapped = nullptr;
+  ZKB_CUDA(cudaHostGetDevicePointer((void**)&mapped, (void*)src_pinned_mapped, 0));
+  const unsigned grid = (unsigned)std::min<size_t>(64, (n_words + 255) / 256);
+  pull_words_kernel<<<grid, 256, 0, s>>>(dst_dev, mapped, n_words);
+  ZKB_CHECK_LAUNCH();
+}
+
 __global__ void to_monty_kernel(u32* d, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) d[i] = fp_from_canonical(d[i]).v;

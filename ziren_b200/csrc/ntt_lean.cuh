@@ -307,7 +307,7 @@ __host__ __device__ constexpr size_t lean_contig_smem() {
 }
 
 template <int K>
-__global__ void __launch_bounds__(256, 3) ntt_contig_lean_kernel(LeanContigArgs a, int logn) {
+__global__ void __launch_bounds__(256, 4) ntt_contig_lean_kernel(LeanContigArgs a, int logn) {
   static_assert(K >= 8 && K <= 12, "lean contiguous level: 4096-element tiles, two or three radix rounds");
   constexpr int NR = (K + 3) / 4;
   constexpr u32 TWW = (twpad(1u << (K - 1)) + 2) * 2;           // words per padded twiddle table

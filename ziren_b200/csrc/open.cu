@@ -239,7 +239,9 @@ void eval_columns(const u32* lde, size_t H, size_t n, size_t W, const u32* w0, c
     const size_t smem = (size_t)(2 * E2_WARPS * 32 * E2_LD + 2 * E2_ROWS * 8) * sizeof(u32);
     const int v2_sms = open_device_info().sms;
     const size_t colgroups = (W + E2_WARPS * 32 - 1) / (E2_WARPS * 32);
-    size_t nsplit = ((size_t)3 * v2_sms + colgroups - 1) / colgroups;
+    // ONE full wave of equal CTAs (3 per SM): rounding the split count UP put 459 CTAs on 444 slots, i.e. a
+    // second wave of 15 CTAs that doubled the kernel's time
+    size_t nsplit = ((size_t)3 * v2_sms) / colgroups;
     if (nsplit > n / 256) nsplit = n / 256;
     if (nsplit < 1) nsplit = 1;
     size_t rows_per_split = ((n + nsplit - 1) / nsplit + E2_ROWS - 1) / E2_ROWS * E2_ROWS;
@@ -349,8 +351,8 @@ __global__ void __launch_bounds__(256) reduce_ys_kernel(const u32* ys, const u32
 }
 // Two rows per thread (rows x and x + 128 of a 256-row block): the alpha powers, which every thread
 // loads per column, are used twice, and 16 column loads are in flight per thread.
-constexpr int RM_ROWS = 2;
-template <int NPT>
+std::atomic<int> g_k4b_rows{2};     // zkb200_set_option("k4b_rows"): 1, 2 or 4 rows per thread
+template <int NPT, int RM_ROWS>
 __global__ void __launch_bounds__(128) reduce_matrix_kernel(const u32* __restrict__ lde, size_t H, size_t W,
                                                             const u32* __restrict__ apow, const u32* __restrict__ rys,
                                                             Ef off0, Ef off1, const u32* __restrict__ invden0,
@@ -434,8 +436,11 @@ void reduce_matrix(const u32* lde, size_t H, size_t W, const u32* apow, const u3
   DevBuf rys(8, s);
   reduce_ys_kernel<<<npoints, 256, 0, s>>>(ys, apow, W, rys.p);
   ZKB_CHECK_LAUNCH();
-  if (npoints == 1) reduce_matrix_kernel<1><<<ceil_div(H, 128 * RM_ROWS), 128, 0, s>>>(lde, H, W, apow, rys.p, off0, off1, invden0, invden0, ro);
-  else reduce_matrix_kernel<2><<<ceil_div(H, 128 * RM_ROWS), 128, 0, s>>>(lde, H, W, apow, rys.p, off0, off1, invden0, invden1, ro);
+  const int rows = g_k4b_rows.load();
+#define ZKB_RM(NPT, R, D1) reduce_matrix_kernel<NPT, R><<<ceil_div(H, 128 * R), 128, 0, s>>>(lde, H, W, apow, rys.p, off0, off1, invden0, D1, ro)
+  if (npoints == 1) { if (rows >= 4) ZKB_RM(1, 4, invden0); else if (rows == 2) ZKB_RM(1, 2, invden0); else ZKB_RM(1, 1, invden0); }
+  else { if (rows >= 4) ZKB_RM(2, 4, invden1); else if (rows == 2) ZKB_RM(2, 2, invden1); else ZKB_RM(2, 1, invden1); }
+#undef ZKB_RM
   ZKB_CHECK_LAUNCH();
 }
 

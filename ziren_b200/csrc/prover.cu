@@ -34,7 +34,7 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
     ZKB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     ZKB_CUDA(cudaStreamCreateWithPriority(&copy_stream, cudaStreamNonBlocking, hi));
   }
-  if (const char* e = getenv("ZKB200_UPLOAD")) upload_mode = std::string(e) == "pull" ? UPLOAD_PULL : std::string(e) == "dma2d" ? UPLOAD_DMA2D : UPLOAD_DMA;
+  if (const char* e = getenv("ZKB200_UPLOAD")) upload_mode = std::string(e) == "dma" ? UPLOAD_DMA : std::string(e) == "dma2d" ? UPLOAD_DMA2D : UPLOAD_PULL;
   // counters the pull kernel bumps and the lanes wait on: plain cudaMalloc memory (stream memory
   // operations do not take stream-ordered pool allocations), handed out as a ring; probed once here -
   // a driver that refuses the wait turns the pull mode off (2-D DMA instead)
@@ -87,6 +87,7 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
     L.arena.init(8u << 20, L.stream);
     ZKB_CUDA(cudaMalloc((void**)&L.d_small, 1 << 16));
     ZKB_CUDA(cudaMallocHost((void**)&L.h_small, 1 << 16));
+    ZKB_CUDA(cudaHostAlloc((void**)&L.h_big, L.h_big_bytes, cudaHostAllocMapped));
   }
   ZKB_CUDA(cudaStreamSynchronize(lanes[0].stream));
 }
@@ -100,6 +101,8 @@ void Ctx::destroy() {
     L.arena.destroy();
     if (L.d_small) cudaFree(L.d_small);
     if (L.h_small) cudaFreeHost(L.h_small);
+    if (L.h_big) cudaFreeHost(L.h_big);
+    L.h_big = nullptr;
     if (L.stream) cudaStreamDestroy(L.stream);
     L.stream = nullptr; L.d_small = nullptr; L.h_small = nullptr;
   }
@@ -385,13 +388,16 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
       pieces.push_back(std::move(p));
     }
   }
-  // The widest matrix crosses first: while the small ones follow, its LDE and leaf hashing already run
-  // (the commitment does not depend on the order the pieces are processed in: LDEs land in their matrix's
-  // slot and each piecewise-hashed matrix keeps its own sponge states).
+  // The heaviest height class crosses first: while the light ones follow, its LDE and leaf hashing already run
+  // (the commitment does not depend on the order the CLASSES are processed in: LDEs land in their matrix's
+  // slot and every class keeps its own sponge states; inside a class the pieces keep the commit order).
+  std::map<unsigned, size_t> class_cells;
+  for (size_t i = 0; i < traces.size(); i++) class_cells[logn[i]] += traces[i].height * traces[i].width;
   std::stable_sort(pieces.begin(), pieces.end(), [&](const Piece& a, const Piece& b) {
-    const size_t sa = traces[a.mat].height * traces[a.mat].width, sb = traces[b.mat].height * traces[b.mat].width;
-    if (sa != sb) return sa > sb;
-    if (a.mat != b.mat) return a.mat < b.mat;
+    const size_t sa = class_cells[logn[a.mat]], sb = class_cells[logn[b.mat]];
+    if (sa != sb) return sa > sb;                                   // the heaviest height class first
+    if (logn[a.mat] != logn[b.mat]) return logn[a.mat] > logn[b.mat];
+    if (a.mat != b.mat) return a.mat < b.mat;                       // inside a class: commit order (the sponge's order)
     return a.col0 < b.col0;
   });
   // Phase 1 (copy stream, its own lock): the traces cross PCIe.  Other host threads may hold the compute
@@ -497,7 +503,12 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     out.log_n.push_back(logn[i]);
   }
   const Fp shift = fp_from_canonical(KB_GEN);     // trace domains are the subgroups themselves
-  std::map<unsigned, DevBuf> sponge_state, digests;
+  // Leaf hashing under the upload, per height class: the columns of its matrices (commit order = the order
+  // the pieces are processed in) are absorbed in whole rate blocks as soon as their LDE is queued; up to 7
+  // columns wait for the next piece; the last piece of the class takes the tail and writes the digests.
+  struct Group { size_t pieces_left = 0; bool started = false; std::vector<const u32*> pending; DevBuf state, digests; };
+  std::map<unsigned, Group> groups;
+  for (auto& p : pieces) groups[logn[p.mat]].pieces_left++;
   std::map<unsigned, const u32*> pre;
   for (auto& p : pieces) {
     const TraceIn& t = traces[p.mat];
@@ -517,14 +528,23 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
       StageTimer tm(ctx, L, "commit_main_lde");
       coset_lde_batch(ctx.tables, cols, n, lde_cols, H, logn[p.mat], p.ncols, lb, shift, L.stream, L.keep);
     }
-    // leaf hashing under the upload: a matrix that is alone in its height class and comes in pieces
-    const unsigned lh = logn[p.mat] + lb;
-    const bool piecewise = group_size[logn[p.mat]] == 1 && !(p.col0 == 0 && p.last_of_matrix);
-    if (piecewise) {
+    {
       StageTimer tm(ctx, L, "commit_main_merkle");
-      if (p.col0 == 0) { sponge_state[lh] = DevBuf(16 * H, L.stream); digests[lh] = DevBuf(8 * H, L.stream); }
-      leaf_absorb(lde_cols, H, (u32)p.ncols, sponge_state[lh].p, p.col0 == 0, p.last_of_matrix, digests[lh].p, L.stream);
-      if (p.last_of_matrix) pre[lh] = digests[lh].p;
+      const unsigned lh = logn[p.mat] + lb;
+      Group& g = groups[logn[p.mat]];
+      const bool last = --g.pieces_left == 0;
+      for (size_t c = 0; c < p.ncols; c++) g.pending.push_back(lde_cols + c * H);
+      const size_t take = last ? g.pending.size() : (g.pending.size() & ~(size_t)7);
+      if (take || last) {
+        const bool first = !g.started;
+        if (first && !last) g.state = DevBuf(16 * H, L.stream);
+        if (last) g.digests = DevBuf(8 * H, L.stream);
+        const u32* const* ptrs = L.arena.push(g.pending.data(), std::max<size_t>(take, 1));
+        leaf_absorb(ptrs, H, (u32)take, g.state.p, first, last, g.digests.p, L.stream);
+        g.pending.erase(g.pending.begin(), g.pending.begin() + take);
+        g.started = true;
+        if (last) { pre[lh] = g.digests.p; g.state.release(); }
+      }
     }
   }
   if (pull_finished) ZKB_CUDA(cudaStreamWaitEvent(L.stream, pull_finished, 0));    // the work list and counters are released in lane order
@@ -870,8 +890,14 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
     // gather straight into a device image of the proof, then overlay the gathered words
     DevBuf jobs_dev((jobs.size() * sizeof(GatherJob) + 3) / 4 + 1, s);
     DevBuf img(o.w.size(), s);
-    ZKB_CUDA(cudaMemcpyAsync(jobs_dev.p, jobs.data(), jobs.size() * sizeof(GatherJob), cudaMemcpyHostToDevice, s));
-    ZKB_CUDA(cudaMemcpyAsync(img.p, o.w.data(), o.w.size() * sizeof(u32), cudaMemcpyHostToDevice, s));
+    // the job list and the proof skeleton go up through the lane's pinned buffer, pulled by a kernel
+    // (not the copy engine: common.h, pull_words)
+    const size_t job_words = (jobs.size() * sizeof(GatherJob) + 3) / 4;
+    if ((job_words + o.w.size()) * sizeof(u32) > L.h_big_bytes) throw std::runtime_error("zkb200: proof skeleton exceeds the lane's staging buffer");
+    memcpy(L.h_big, jobs.data(), jobs.size() * sizeof(GatherJob));
+    memcpy(L.h_big + job_words, o.w.data(), o.w.size() * sizeof(u32));
+    pull_words(jobs_dev.p, L.h_big, job_words, s);
+    pull_words(img.p, L.h_big + job_words, o.w.size(), s);
     gather_canonical(reinterpret_cast<const GatherJob*>(jobs_dev.p), jobs.size(), img.p, s);
     ZKB_CUDA(cudaMemcpyAsync(o.w.data(), img.p, o.w.size() * sizeof(u32), cudaMemcpyDeviceToHost, s));
     ZKB_CUDA(cudaStreamSynchronize(s));

@@ -36,6 +36,8 @@ struct Lane {
   ParamArena arena;
   u32* d_small = nullptr;            // small device scratch (roots, sums)
   u32* h_small = nullptr;            // pinned mirror
+  u32* h_big = nullptr;              // pinned, device-mapped staging for host -> device tables (proof skeleton, gather jobs)
+  size_t h_big_bytes = (size_t)32 << 20;
   std::mutex mu;
   KeepAlive keep;                    // shared tables the queued kernels read (ntt.h)
   // start of a call that owns the lane: the previous call drained the stream before it returned
@@ -93,10 +95,11 @@ struct Ctx {
   std::mutex copy_mu;
   HostStager stager;                    // pageable host sources
   size_t piece_bytes = (size_t)256 << 20;   // column pieces of the main commit (prover_commit)
-  // pinned host traces (ZKB200_UPLOAD=dma|pull|dma2d), see prover_commit.  Measured on the bench shard (ms per
-  // shard, 4 threads / 1 thread in flight): dma 122.9 / 198.7, pull 144.5 / 204.3, dma2d 268.9 / 343.6 -
-  // the SM-driven gathers (pull, 2-D DMA) run at 48-51 GB/s alone but at ~31 GB/s next to the compute kernels.
-  int upload_mode = UPLOAD_DMA;
+  // pinned host traces (ZKB200_UPLOAD=pull|dma|dma2d), see prover_commit.  Measured on the bench shard (ms per
+  // shard, 4 shards / 1 shard in flight): pull 121.5 / 149.3, dma 128.1 / 193.1, dma2d 247.2 / 278.7.  The pull
+  // kernel moves 48.6 GB/s alone and about 40 GB/s next to the compute kernels, but it lets the LDE and the leaf
+  // hashing of a shard run under that shard's own upload; the contiguous DMA (55 GB/s) cannot.
+  int upload_mode = UPLOAD_PULL;
   int pull_ctas = 32;                   // persistent CTAs of the pull kernel (ZKB200_PULL_CTAS)
   bool pull_exclusive = false;          // 1024-thread CTAs that own their SM (ZKB200_PULL_EXCLUSIVE=1, 8 CTAs by default)
   StreamWaitValue wait_value;           // cuStreamWaitValue32: a lane waits for a counter of the pull kernel

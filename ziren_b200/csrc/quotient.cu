@@ -5,6 +5,7 @@
 // bytecode (machine.cpp); all threads execute the same instruction stream, so there is no
 // divergence and instruction fetches are broadcast.
 #include "quotient.h"
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include "quotient_codegen.h"
@@ -13,6 +14,7 @@
 namespace zkb {
 
 std::atomic<unsigned long long> g_quotient_generated_launches{0}, g_quotient_interpreter_launches{0};
+std::atomic<int> g_qk_block{256};            // zkb200_set_option("qk_block"): threads per CTA of the generated kernels
 std::atomic<int> g_quotient_codegen{1};     // zkb200_set_option("quotient_codegen"); ZKB200_QUOTIENT=interp turns it off
 
 constexpr int QCHUNK = 1024;   // 16 KB of bytecode per stage
@@ -125,7 +127,8 @@ void quotient_values(const MachineInfo& m, const ChipInfo& chip, const NttTables
   if (g_quotient_codegen.load()) {
     if (void* k = quotient_generated_kernel(chip)) {
       void* params[] = {&a};
-      ZKB_CUDA(cudaLaunchKernel((const void*)k, dim3(grid), dim3(128), params, 0, s));
+      const unsigned bs = (unsigned)std::max(32, std::min(256, g_qk_block.load()));
+      ZKB_CUDA(cudaLaunchKernel((const void*)k, dim3(ceil_div(Q, bs)), dim3(bs), params, 0, s));
       ZKB_CHECK_LAUNCH();
       g_quotient_generated_launches++;
       return;

@@ -42,12 +42,24 @@ class WideSpec:
         return 6 * self.groups + self.extra + (14 if self.global_scope else 0)
 
 
+# Constraints per 6-column group of the wide tables: 2 (default, "sparse": a*b = c, c*d = e) up to 12
+# ("dense", about 2 per column as SURVEY.md section 8d(i) asks for a K3 throughput figure: the real
+# KeccakSponge chip has 1 388 constraints over 4 167 columns, the ALU chips are denser still).  The extra
+# constraints are further degree <= 3 consequences of the same two identities, so the same traces satisfy them.
+CONSTRAINTS_PER_GROUP = 2
+
+
 def _wide_chip(s: WideSpec) -> Chip:
     def ev(b):
         for g in range(s.groups):
             a, bb, c, d, e, r = (b.main(6 * g + k) for k in range(6))
-            b.assert_zero(a * bb - c)
-            b.assert_zero(c * d - e)
+            x, y = a * bb - c, c * d - e
+            extra = [lambda: x * d, lambda: y * a, lambda: a * bb * d - e, lambda: x * r, lambda: y * r, lambda: x + y,
+                     lambda: x * a, lambda: y * c, lambda: x * e, lambda: y * bb]
+            b.assert_zero(x)
+            b.assert_zero(y)
+            for k in range(max(0, min(CONSTRAINTS_PER_GROUP, 12) - 2)):
+                b.assert_zero(extra[k]())
             if g < s.lookups:
                 b.send(KIND_BYTE, [r], 1)
         if s.counter:
