@@ -383,13 +383,13 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1):
     perms = sum(h * (-(-w // 8)) for h, w in shapes) + (hmax - 1) + sum(inj_heights)
     lde_bytes = sum(12.0 * h * w for h, w in trace_shapes.values())
     out = {}
-    # DRAM traffic / algorithmic bytes of the family's kernels, from the committed `ncu --set full`
-    # captures (profiles/r01_ncu_full_summary_v2.txt): leaf_hash_kernel 2^19 x 512 moves 1.0926 GB for
-    # 1.0905 GB algorithmic; the three launches of one 2^18 x 256 LDE chunk move 2.306 GB for 0.805 GB
-    # (the A->B->C intermediates go through HBM at this chunk size)
-    ncu_ratio = {"k2_merkle": 1.0019, "k1_lde": 2.864}
+    # DRAM traffic / algorithmic bytes of the family's kernels, from the committed ncu captures
+    # (profiles/r01_ncu_full_summary_v2.txt: leaf_hash_kernel 2^19 x 512 moves 1.0926 GB for 1.0905 GB algorithmic;
+    # profiles/r02_ncu_hot_kernels.txt: the three lean launches of one LDE piece move 2.28 GB for 0.805 GB, the
+    # A->B->C intermediates go through HBM)
+    ncu_ratio = {"k2_merkle": 1.0019, "k1_lde": 2.83}       # r02: 0.495 + 0.751 + 1.031 GB moved for 0.805 GB algorithmic (2^16 x 1024 piece)
     for key, stage, alg, kern in (("k2_merkle", "commit_main_merkle", merkle_bytes, "merkle_build: leaf_hash_kernel (Poseidon2 sponge over the rows of every height) + compress_kernel"),
-                                  ("k1_lde", "commit_main_lde", lde_bytes, "coset_lde_batch: ntt_strided_kernel + ntt_contig_kernel")):
+                                  ("k1_lde", "commit_main_lde", lde_bytes, "coset_lde_batch: ntt_strided_lean_kernel + ntt_contig_lean_kernel")):
         ms = stages.get(stage)
         if not ms:
             continue
@@ -410,13 +410,16 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1):
     if "k2_merkle" in out:
         rate = perms / (stages["commit_main_merkle"] / 1e3)
         out["k2_merkle"]["poseidon2_Gperm_per_s"] = rate / 1e9
-        # the bound that does apply: integer issue.  profiles/r01_pipe_probe.jsonl prices a permutation at
-        # about 6200 scheduler cycles per warp (141 cubes at 20.8, the add-only internal rounds at 1.4 cycles
-        # per instruction); 148 SMs x 4 schedulers x 32 lanes at 1965 MHz
+        # the bound that does apply: integer issue.  Hard limit = one warp instruction per scheduler cycle; the kernel
+        # executes about 4 450 warp instructions per permutation (ncu smsp__inst_executed / permutations,
+        # profiles/r02_ncu_hot_kernels.txt), so frac = instructions / scheduler cycles spent = the issue-slot utilisation
+        # (ncu: 2.45 instructions per cycle per SM of 4).  148 SMs x 4 schedulers x 32 lanes at 1965 MHz.
         lanes_hz = 148 * 4 * 32 * 1.965e9
-        out["k2_merkle"]["issue_roofline"] = {"model_cycles_per_permutation": 6200, "achieved_cycles_per_permutation": lanes_hz / rate,
-                                              "frac": 6200 / (lanes_hz / rate), "source": "tools/sweep/pipe_probe.cu, profiles/README.md"}
-        out["k2_merkle"]["note"] = "integer-issue bound, not HBM bound: ~4.3k instructions per permutation, IMAD.WIDE/IMAD.HI cost 4-5.5 issue cycles per warp (profiles/r01_pipe_probe.jsonl); see profiles/README.md"
+        cyc = lanes_hz / rate
+        out["k2_merkle"]["issue_roofline"] = {"warp_instructions_per_permutation": 4450, "scheduler_cycles_per_permutation": cyc,
+                                              "frac": 4450 / cyc, "limit": "1 warp instruction per scheduler per cycle",
+                                              "source": "profiles/r02_ncu_hot_kernels.txt (leaf_hash_kernel)"}
+        out["k2_merkle"]["note"] = "integer-issue bound, not HBM bound: fma-heavy pipe 71 %, dominant stall math_pipe_throttle; see profiles/README.md"
     return out
 
 
