@@ -44,13 +44,18 @@ def timed(fn):
 
 for log_n in range(args.min, args.max + 1):
     n = 1 << log_n
-    w = max(1, (1 << args.elems_log) >> log_n)
-    d_in = torch.randint(0, kb.P, (w, n), dtype=torch.int32, device="cuda")
-    d_out = torch.empty((w, 2 * n), dtype=torch.int32, device="cuda")
-    for kind, fn, alg in (("ntt", lambda: prover.ntt(d_in, d_out, log_n, w, False, True), 8.0 * n * w),
-                          ("coset_lde_x2", lambda: prover.coset_lde(d_in, d_out, log_n, w, 1, 3), 12.0 * n * w)):
-        ms = timed(fn)
-        gbs = alg / (ms / 1e3) / 1e9
-        print(json.dumps({"kind": kind, "log_n": log_n, "width": w, "ms": ms, "algorithmic_GB": alg / 1e9, "GB/s": gbs,
-                          "frac_of_measured_hbm": gbs / peak, "frac_of_8TBs": gbs / 8000.0}), flush=True)
-    del d_in, d_out
+    # BASELINE configs[3]: 1, 64 and 256 columns, plus the width that makes about 2^elems_log elements
+    for w in sorted({1, 64, 256, max(1, (1 << args.elems_log) >> log_n)}):
+        if n * w * 4 * 3 > (60 << 30):
+            continue
+        d_in = torch.randint(0, kb.P, (w, n), dtype=torch.int32, device="cuda")
+        d_out = torch.empty((w, 2 * n), dtype=torch.int32, device="cuda")
+        cases = [("ntt", lambda: prover.ntt(d_in, d_out, log_n, w, False, True), 8.0 * n * w)]
+        if log_n + 1 <= 24:          # the LDE domain must fit the field's two-adicity (2^24)
+            cases.append(("coset_lde_x2", lambda: prover.coset_lde(d_in, d_out, log_n, w, 1, 3), 12.0 * n * w))
+        for kind, fn, alg in cases:
+            ms = timed(fn)
+            gbs = alg / (ms / 1e3) / 1e9
+            print(json.dumps({"kind": kind, "log_n": log_n, "width": w, "ms": round(ms, 4), "algorithmic_GB": alg / 1e9, "GB/s": round(gbs, 1),
+                              "frac_of_measured_hbm": round(gbs / peak, 4), "frac_of_8TBs": round(gbs / 8000.0, 4)}), flush=True)
+        del d_in, d_out

@@ -42,6 +42,12 @@ void Ctx::init(int dev, const u32* desc, size_t n) {
   ZKB_CUDA(cudaMalloc((void**)&pull_counters, PULL_COUNTER_RING * sizeof(u32)));
   ZKB_CUDA(cudaMemset(pull_counters, 0, PULL_COUNTER_RING * sizeof(u32)));
   if (wait_value && !wait_value.probe(lanes[0].stream, pull_counters)) wait_value.fn = nullptr;
+  if (const char* e = getenv("ZKB200_PULL_SPLIT")) pull_split = atoi(e) != 0;
+  {
+    int lo = 0, hi = 0;
+    ZKB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    ZKB_CUDA(cudaStreamCreateWithPriority(&dma_stream, cudaStreamNonBlocking, hi));
+  }
   if (const char* e = getenv("ZKB200_PULL_EXCLUSIVE")) pull_exclusive = atoi(e) != 0;
   if (pull_exclusive) pull_ctas = 8;
   if (const char* e = getenv("ZKB200_PULL_CTAS")) pull_ctas = std::max(1, atoi(e));
@@ -108,6 +114,8 @@ void Ctx::destroy() {
   }
   if (pull_counters) cudaFree(pull_counters);
   pull_counters = nullptr;
+  if (dma_stream) cudaStreamDestroy(dma_stream);
+  dma_stream = nullptr;
   if (copy_stream) cudaStreamDestroy(copy_stream);
   copy_stream = nullptr;
 }
@@ -421,6 +429,11 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     events.v.push_back(alloc_done);
     ZKB_CUDA(cudaEventRecord(alloc_done, ctx.copy_stream));
     std::vector<std::shared_ptr<DevBuf>> whole(traces.size());     // dma mode: one staging buffer per matrix
+    // if every matrix is a single piece there is nothing to pull: leave them all to the pull kernel then (it
+    // needs no staging buffer) - the split only pays next to a multi-piece matrix
+    bool any_multi = false;
+    for (auto& p : pieces) if (!(p.col0 == 0 && p.last_of_matrix)) any_multi = true;
+    const bool traces_multi_piece_only = !any_multi;
     for (auto& p : pieces) {
       const TraceIn& t = traces[p.mat];
       bool pinned = false;
@@ -430,6 +443,25 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
       }
       const u32* mapped = nullptr;
       if (pinned && ctx.upload_mode == UPLOAD_PULL && cudaHostGetDevicePointer((void**)&mapped, (void*)t.data, 0) != cudaSuccess) { cudaGetLastError(); mapped = nullptr; }
+      // pull mode: a matrix that is ONE piece gains nothing from the column-wise pull; it goes by contiguous DMA
+      // on a second copy stream, so the copy engine and the pull kernel share the link (the pull kernel alone
+      // reaches ~40 GB/s next to the compute kernels, the link carries 55)
+      const bool dma_side = mapped && ctx.wait_value && ctx.pull_split && p.col0 == 0 && p.last_of_matrix && !traces_multi_piece_only;
+      if (dma_side) {
+        // the staging buffer comes from the main copy stream (stream-ordered pool); the side stream starts after that
+        p.stage = DevBuf(t.height * t.width, ctx.copy_stream);
+        cudaEvent_t staged;
+        ZKB_CUDA(cudaEventCreateWithFlags(&staged, cudaEventDisableTiming));
+        events.v.push_back(staged);
+        ZKB_CUDA(cudaEventRecord(staged, ctx.copy_stream));
+        ZKB_CUDA(cudaStreamWaitEvent(ctx.dma_stream, staged, 0));
+        ZKB_CUDA(cudaMemcpyAsync(p.stage.p, t.data, t.height * t.width * sizeof(u32), cudaMemcpyHostToDevice, ctx.dma_stream));
+        p.src = p.stage.p; p.src_pitch = t.width;
+        ZKB_CUDA(cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
+        events.v.push_back(p.ready);
+        ZKB_CUDA(cudaEventRecord(p.ready, ctx.dma_stream));
+        continue;
+      }
       if (mapped && ctx.wait_value) {
         // one persistent kernel pulls all such pieces (launched below); the lane waits for the piece's tile count
         PullPiece pp;

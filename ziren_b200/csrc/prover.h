@@ -101,6 +101,8 @@ struct Ctx {
   // hashing of a shard run under that shard's own upload; the contiguous DMA (55 GB/s) cannot.
   int upload_mode = UPLOAD_PULL;
   int pull_ctas = 32;                   // persistent CTAs of the pull kernel (ZKB200_PULL_CTAS)
+  bool pull_split = true;               // pull mode: single-piece matrices go by contiguous DMA on `dma_stream` (ZKB200_PULL_SPLIT=0: all pulled)
+  cudaStream_t dma_stream = nullptr;
   bool pull_exclusive = false;          // 1024-thread CTAs that own their SM (ZKB200_PULL_EXCLUSIVE=1, 8 CTAs by default)
   StreamWaitValue wait_value;           // cuStreamWaitValue32: a lane waits for a counter of the pull kernel
   static constexpr size_t PULL_COUNTER_RING = 1 << 16;
