@@ -66,10 +66,21 @@ typedef struct zkb200_shard zkb200_shard; /* ShardMainData<SC, DeviceMatrix, Dev
 
 typedef struct {
   const char* name;      /* chip name (MachineAir::name) */
-  const uint32_t* data;  /* row-major height x width, Montgomery; host or device pointer */
+  const uint32_t* data;  /* row-major height x width, Montgomery; host or device pointer (flags = 0) */
   size_t height;         /* power of two */
   size_t width;
+  uint32_t flags;        /* 0, or one of ZKB200_TRACE_* (zkb200_commit / zkb200_prove_shard only) */
+  size_t n_events;       /* ZKB200_TRACE_EVENTS: number of event records behind `data` */
 } zkb200_trace;
+/* `data` is a DEVICE pointer to a COLUMN-MAJOR matrix (what zkb200_generate_*_trace(col_major = 1) writes): the
+ * row-major -> column-major layout change of the commit is skipped. */
+#define ZKB200_TRACE_COL_MAJOR 1u
+/* MachineAir::generate_trace moved into the commit: `data` points to the chip's EVENT
+ * RECORDS (host or device memory; n_events of them: the 28-byte records of zkb200_generate_alu_trace, or
+ * zkb200_keccak_block records for "KeccakSponge"), height = the padded number of rows, width = the chip's width.
+ * The library's row filler writes the table column-major straight into the shard's trace storage; no trace bytes
+ * cross PCIe and no layout change runs.  Error if the library has no row filler for `name`. */
+#define ZKB200_TRACE_EVENTS 2u
 
 /* MachineProver::new(machine) — crates/stark/src/prover.rs:43.  `desc` is a ZKMD descriptor. */
 int zkb200_ctx_create(int device, const uint32_t* desc, size_t n_words, zkb200_ctx** out);
@@ -186,6 +197,37 @@ int zkb200_alu_trace_width(const char* chip);
 /* events: zkb200_alu_event[]; zkb200_flow_event[] for "Branch" / "Jump"; seven-word MovCondEvent records for "MovCond" */
 int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* events, size_t n_events,
                               unsigned log_height, uint32_t* out, int col_major);
+/* MachineAir::generate_trace of the KeccakSponge precompile chip
+ * (crates/core/machine/src/syscall/precompiles/keccak_sponge/trace.rs:58-196; the 2633 permutation columns are
+ * p3_keccak_air::generate_trace_rows of the pinned Plonky3), 3531 columns (keccak_sponge/columns.rs:14-37).
+ * The Rust KeccakSpongeEvent (crates/core/executor/src/events/precompiles/keccak_sponge.rs:15-40) holds Vecs, so
+ * the host flattens a record's events into one fixed-size record per absorbed BLOCK (= 24 rows, one per Keccak-f
+ * round), event after event, block after block:
+ *   `xored_state`      event.xored_state_list[block] as 50 words (u64 lane i = words 2i, 2i+1)
+ *   `input`            event.input[36*block .. 36*block+36]
+ *   `input_reads`      event.input_read_records[36*block ..], MemoryReadRecord {value, shard, timestamp, prev_shard,
+ *                      prev_timestamp} (crates/core/executor/src/events/memory.rs:46-60)
+ *   `input_length_read` event.input_length_record (used by block 0), `output_writes` event.output_write_records,
+ *                      MemoryWriteRecord {value, shard, timestamp, prev_value, prev_shard, prev_timestamp} (used by
+ *                      the last block)
+ * Rows past 24 * n_blocks are the chip's dummy rows up to 2^log_height.  `blocks` may be host or device memory;
+ * `out` is DEVICE memory, Montgomery, row-major (col_major = 0) or column-major (col_major = 1). */
+typedef struct {
+  uint32_t shard, clk, input_addr, output_addr;
+  uint32_t input_len;      /* event.input.len(), in words */
+  uint32_t block;          /* index of this block in its event */
+  uint32_t num_blocks;     /* event.num_blocks() */
+  uint32_t reserved;
+  uint32_t xored_state[50];
+  uint32_t input[36];
+  uint32_t input_reads[36][5];
+  uint32_t input_length_read[5];
+  uint32_t output_writes[16][6];
+  uint32_t pad[9];
+} zkb200_keccak_block;     /* 384 words */
+int zkb200_keccak_sponge_trace_width(void);    /* NUM_KECCAK_SPONGE_COLS = 3531 */
+int zkb200_generate_keccak_sponge_trace(zkb200_ctx* ctx, const zkb200_keccak_block* blocks, size_t n_blocks,
+                                        unsigned log_height, uint32_t* out, int col_major);
 /* layout helpers on the context stream: row-major <-> column-major, canonical <-> Montgomery */
 int zkb200_transpose(zkb200_ctx* ctx, const uint32_t* in, uint32_t* out, size_t height, size_t width, int to_colmajor);
 int zkb200_convert(zkb200_ctx* ctx, uint32_t* data, size_t n, int to_montgomery);

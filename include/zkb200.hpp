@@ -35,6 +35,8 @@ struct Trace {
   std::string name;
   const uint32_t* data = nullptr;
   size_t height = 0, width = 0;
+  uint32_t flags = 0;        // 0, ZKB200_TRACE_COL_MAJOR or ZKB200_TRACE_EVENTS (zkb200.h)
+  size_t n_events = 0;       // ZKB200_TRACE_EVENTS: event records behind `data`
 };
 using Commitment = std::array<uint32_t, 8>;    // canonical
 using Challenger = std::array<uint32_t, 34>;   // DuplexChallenger image, canonical (zkb200.h)
@@ -162,7 +164,7 @@ class B200Prover {
   static std::vector<zkb200_trace> marshal(const std::vector<Trace>& v) {
     std::vector<zkb200_trace> t;
     t.reserve(v.size());
-    for (auto& x : v) t.push_back(zkb200_trace{x.name.c_str(), x.data, x.height, x.width});
+    for (auto& x : v) t.push_back(zkb200_trace{x.name.c_str(), x.data, x.height, x.width, x.flags, x.n_events});
     return t;
   }
   zkb200_ctx* ctx_ = nullptr;

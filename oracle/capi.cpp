@@ -4,6 +4,7 @@
 // imports or calls this library.
 #include "prover.h"
 #include "tracegen.h"
+#include "tracegen_keccak.h"
 #include <cstdlib>
 #include <cstring>
 #ifdef _OPENMP
@@ -255,5 +256,17 @@ int zko_alu_trace(int chip, const u32* ev, size_t n, size_t height, u32* out) {
     return 1;
   }
 }
+
+// trace generation of the KeccakSponge chip (tracegen_keccak.h): n_blocks records of KS_REC_WORDS words,
+// out height x 3531 row-major canonical
+int zko_keccak_sponge_width() { return KS_WIDTH; }
+int zko_keccak_sponge_trace(const u32* recs, size_t n_blocks, size_t height, u32* out) {
+  try {
+    keccak_sponge_trace(recs, n_blocks, height, out);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+// MemoryAccessCols::populate_access alone (9 canonical words), for the comparison with the reference's memory.hpp
+void zko_mem_access(u32 value, u32 shard, u32 ts, u32 prev_shard, u32 prev_ts, u32* out9) { ks_mem_access(out9, value, shard, ts, prev_shard, prev_ts); }
 
 }  // extern "C"

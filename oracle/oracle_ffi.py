@@ -91,6 +91,34 @@ def ref_alu_rows(chip, events):
     return out
 
 
+KS_WIDTH, KS_REC_WORDS = 3531, 384
+
+
+def keccak_sponge_trace(blocks, height):
+    """blocks: (n, 384) uint32 block records (include/zkb200.h zkb200_keccak_block); (height, 3531) canonical rows."""
+    b = _a(blocks).reshape(-1, KS_REC_WORDS)
+    out = np.zeros((int(height), KS_WIDTH), np.uint32)
+    if lib().zko_keccak_sponge_trace(_p(b), C.c_size_t(b.shape[0]), C.c_size_t(int(height)), _p(out)):
+        raise RuntimeError(err())
+    return out
+
+
+def mem_access(value, shard, ts, prev_shard, prev_ts):
+    out = np.zeros(9, np.uint32)
+    lib().zko_mem_access(C.c_uint32(value), C.c_uint32(shard), C.c_uint32(ts), C.c_uint32(prev_shard), C.c_uint32(prev_ts), _p(out))
+    return out
+
+
+def ref_mem_access(value, shard, ts, prev_shard, prev_ts):
+    """MemoryAccessCols of the reference's own memory.hpp populate_read (Montgomery words), or None without oracle/_ref."""
+    l = ref_core_lib()
+    if l is None or not hasattr(l, "ref_mem_read_cols"):
+        return None
+    out = np.zeros(9, np.uint32)
+    l.ref_mem_read_cols(C.c_uint32(value), C.c_uint32(shard), C.c_uint32(ts), C.c_uint32(prev_shard), C.c_uint32(prev_ts), _p(out))
+    return out
+
+
 def _a(x):
     return np.ascontiguousarray(x, dtype=np.uint32)
 

@@ -15,6 +15,7 @@
 #include "branch.hpp"
 #include "jump.hpp"
 #include "mov_cond.hpp"
+#include "memory.hpp"
 
 using namespace zkm_core_machine_sys;
 
@@ -65,5 +66,26 @@ int ref_alu_event_to_rows(int chip, const uint32_t* ev, size_t n, uint32_t* rows
     }
   }
   return 0;
+}
+// MemoryReadCols::populate of the reference's memory.hpp:36-52 (9 Montgomery words: value[4], prev_shard, prev_clk,
+// compare_clk, diff_16bit_limb, diff_8bit_limb)
+void ref_mem_read_cols(uint32_t value, uint32_t shard, uint32_t ts, uint32_t prev_shard, uint32_t prev_ts, uint32_t* out9) {
+  MemoryReadCols<kb31_t> c;
+  std::memset(&c, 0, sizeof(c));
+  MemoryReadRecord r{value, shard, ts, prev_shard, prev_ts};
+  memory::populate_read<kb31_t>(c, r);
+  static_assert(sizeof(c) == 9 * sizeof(uint32_t), "MemoryReadCols is nine field elements");
+  std::memcpy(out9, &c, sizeof(c));
+}
+// MemoryReadWriteCols through populate_read_write_v2 with a write record (13 words: prev_value[4], access[9]) =
+// what MemoryWriteCols::populate leaves (memory/consistency/trace.rs:8-20)
+void ref_mem_write_cols(uint32_t value, uint32_t shard, uint32_t ts, uint32_t prev_value, uint32_t prev_shard, uint32_t prev_ts, uint32_t* out13) {
+  MemoryReadWriteCols<kb31_t> c;
+  std::memset(&c, 0, sizeof(c));
+  MemoryRecordEnum e;
+  e.tag = MemoryRecordEnum::Tag::Write;
+  e.write._0 = MemoryWriteRecord{value, shard, ts, prev_value, prev_shard, prev_ts};
+  memory::populate_read_write_v2<kb31_t>(c, e);
+  std::memcpy(out13, &c, sizeof(c));
 }
 }

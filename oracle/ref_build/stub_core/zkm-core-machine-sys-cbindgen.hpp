@@ -149,4 +149,25 @@ template <class T> struct MovCondCols {
   T is_mne, is_meq, is_wsbh;
 };
 
+// ---- memory records and columns named by crates/core/machine/include/memory.hpp ----
+// crates/core/executor/src/events/memory.rs:10-19, :46-60, :66-82 (#[repr(C)])
+struct MemoryRecord { uint32_t shard, timestamp, value; };
+struct MemoryReadRecord { uint32_t value, shard, timestamp, prev_shard, prev_timestamp; };
+struct MemoryWriteRecord { uint32_t value, shard, timestamp, prev_value, prev_shard, prev_timestamp; };
+// crates/core/executor/src/events/memory.rs:88-97 (MemoryRecordEnum) and its Option form as cbindgen lays tagged unions out
+struct MemoryRecordEnum {
+  enum class Tag : uint32_t { Read, Write };
+  struct Read_Body { MemoryReadRecord _0; };
+  struct Write_Body { MemoryWriteRecord _0; };
+  Tag tag;
+  union { Read_Body read; Write_Body write; };
+};
+enum class OptionMemoryRecordEnumTag : uint32_t { Read, Write, None };
+struct OptionMemoryRecordEnum { OptionMemoryRecordEnumTag tag; MemoryReadRecord read; MemoryWriteRecord write; };
+// crates/core/machine/src/memory/consistency/columns.rs:4-51
+template <class T> struct MemoryAccessCols { Word<T> value; T prev_shard, prev_clk, compare_clk, diff_16bit_limb, diff_8bit_limb; };
+template <class T> struct MemoryReadCols { MemoryAccessCols<T> access; };
+template <class T> struct MemoryWriteCols { Word<T> prev_value; MemoryAccessCols<T> access; };
+template <class T> struct MemoryReadWriteCols { Word<T> prev_value; MemoryAccessCols<T> access; };
+
 }  // namespace zkm_core_machine_sys

@@ -96,6 +96,8 @@ fn marshal(names: &[CString], mats: &[&RowMajorMatrix<F>]) -> Vec<sys::zkb200_tr
         data: m.values.as_ptr() as *const u32,
         height: m.height(),
         width: m.width(),
+        flags: 0,
+        n_events: 0,
     }).collect()
 }
 

@@ -8,7 +8,11 @@ pub struct zkb200_trace {
     pub data: *const u32, // row-major height x width, Montgomery: RowMajorMatrix<KoalaBear>::values as is
     pub height: usize,
     pub width: usize,
+    pub flags: u32,       // 0, ZKB200_TRACE_COL_MAJOR (1) or ZKB200_TRACE_EVENTS (2)
+    pub n_events: usize,  // ZKB200_TRACE_EVENTS: event records behind `data`
 }
+pub const ZKB200_TRACE_COL_MAJOR: u32 = 1;
+pub const ZKB200_TRACE_EVENTS: u32 = 2;
 pub enum zkb200_ctx {}
 pub enum zkb200_pk {}
 pub enum zkb200_shard {}

@@ -3,6 +3,7 @@
 // vectors and the oracle without a GPU.  Test infrastructure only (built by tests/test_host_logic.py).
 #include "poseidon2.cuh"
 #include "tracegen.cuh"
+#include "tracegen_keccak.cuh"
 #include "lane_pool.h"
 #include <atomic>
 #include <thread>
@@ -74,6 +75,19 @@ int hostcheck_alu_rows(int chip, const uint32_t* ev, size_t n, size_t height, ui
   return 0;
 }
 int hostcheck_alu_width(int chip) { return alu_width(chip); }
+// the product's KeccakSponge row filler (csrc/tracegen_keccak.cuh) on the host: n_blocks records of 384 words,
+// out height x 3531 row-major Montgomery, padding rows past the last block
+struct HostRowStore { uint32_t* r; void operator()(int col, u32 v) { r[col] = v; } };
+int hostcheck_keccak_rows(const uint32_t* recs, size_t n_blocks, size_t height, uint32_t* out) {
+  if (n_blocks * KS_ROUNDS > height) return 1;
+  for (size_t i = 0; i < height; i++) {
+    const size_t b = i / KS_ROUNDS;
+    HostRowStore st{out + i * KS_WIDTH};
+    ks_fill_row(b < n_blocks ? recs + b * KS_REC_WORDS : nullptr, (u32)(i % KS_ROUNDS), st);
+  }
+  return 0;
+}
+int hostcheck_keccak_width() { return KS_WIDTH; }
 // stress of the lane pool (csrc/lane_pool.h): `threads` host threads take and release lanes `iters` times.
 // Returns 0 when no lane ever had two holders and never more than `active` lanes were held at once.
 int hostcheck_lane_pool(int threads, int iters, int active) {

@@ -13,7 +13,11 @@ u32p = C.POINTER(C.c_uint32)
 
 
 class Trace(C.Structure):
-    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("height", C.c_size_t), ("width", C.c_size_t)]
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("height", C.c_size_t), ("width", C.c_size_t),
+                ("flags", C.c_uint32), ("n_events", C.c_size_t)]
+
+
+TRACE_COL_MAJOR, TRACE_EVENTS = 1, 2
 
 
 def build(verbose: bool = False) -> None:
@@ -62,6 +66,8 @@ SIGNATURES = {
     "zkb200_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "zkb200_alu_trace_width": (C.c_int, [C.c_char_p]),
     "zkb200_generate_alu_trace": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_int]),
+    "zkb200_keccak_sponge_trace_width": (C.c_int, []),
+    "zkb200_generate_keccak_sponge_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_int]),
     "zkb200_sync": (C.c_int, [C.c_void_p]),
 }
 

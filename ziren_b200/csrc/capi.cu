@@ -67,7 +67,7 @@ static int guarded(zkb200_ctx* ctx, F&& f) {
 
 static std::vector<TraceIn> to_traces(const zkb200_trace* t, int n) {
   std::vector<TraceIn> v;
-  for (int i = 0; i < n; i++) v.push_back(TraceIn{t[i].name, t[i].data, t[i].height, t[i].width});
+  for (int i = 0; i < n; i++) v.push_back(TraceIn{t[i].name, t[i].data, t[i].height, t[i].width, t[i].flags, t[i].n_events});
   return v;
 }
 static Ef ef_from_canon(const uint32_t* w) { Ef e; for (int i = 0; i < 4; i++) e.c[i] = fp_from_canonical(w[i]); return e; }
@@ -342,6 +342,39 @@ int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* eve
       ev = staged.p;
     }
     alu_trace(id, ev, n_events, height, out, col_major != 0, s);
+    ZKB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+int zkb200_keccak_sponge_trace_width(void) { return KS_WIDTH; }
+int zkb200_generate_keccak_sponge_trace(zkb200_ctx* ctx, const zkb200_keccak_block* blocks, size_t n_blocks,
+                                        unsigned log_height, uint32_t* out, int col_major) {
+  return guarded(ctx, [&] {
+    static_assert(sizeof(zkb200_keccak_block) == KS_REC_WORDS * 4, "block records are 384 32-bit words");
+    if (log_height > 30) throw std::runtime_error("zkb200: generate_keccak_sponge_trace: log_height out of range");
+    const size_t height = (size_t)1 << log_height;
+    if (n_blocks * KS_ROUNDS > height) throw std::runtime_error("zkb200: generate_keccak_sponge_trace: more rows than 2^log_height (fixed log2 rows is too small)");
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    cudaStream_t s = ctx->c.lanes[0].stream;
+    const u32* ev = reinterpret_cast<const u32*>(blocks);
+    DevBuf staged, tmp;
+    cudaPointerAttributes attr;
+    bool on_device = false;
+    if (n_blocks && cudaPointerGetAttributes(&attr, blocks) == cudaSuccess)
+      on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    else cudaGetLastError();
+    if (n_blocks && !on_device) {
+      staged = DevBuf(n_blocks * KS_REC_WORDS, s);
+      ZKB_CUDA(cudaMemcpyAsync(staged.p, blocks, n_blocks * sizeof(zkb200_keccak_block), cudaMemcpyHostToDevice, s));
+      ev = staged.p;
+    }
+    if (col_major) keccak_sponge_trace(ev, n_blocks, height, out, s);
+    else {
+      // the kernel writes columns (coalesced); the RowMajorMatrix layout is one layout change away
+      tmp = DevBuf(height * KS_WIDTH, s);
+      keccak_sponge_trace(ev, n_blocks, height, tmp.p, s);
+      transpose_to_rowmajor(tmp.p, out, height, KS_WIDTH, s);
+    }
     ZKB_CUDA(cudaStreamSynchronize(s));
   });
 }

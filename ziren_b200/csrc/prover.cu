@@ -341,6 +341,18 @@ Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, co
   return pk.release();
 }
 
+// ZKB200_TRACE_EVENTS: which row filler a chip has (csrc/tracegen.cu) and how long its event records are
+static size_t event_record_words(const std::string& chip) {
+  if (chip == "KeccakSponge") return KS_REC_WORDS;
+  if (alu_chip_by_name(chip.c_str()) >= 0) return 7;
+  throw std::runtime_error("zkb200: commit: no row filler for chip " + chip + " (ZKB200_TRACE_EVENTS)");
+}
+static void generate_trace_colmajor(const std::string& chip, const u32* events_dev, size_t n_events, size_t height, u32* out,
+                                    cudaStream_t s) {
+  if (chip == "KeccakSponge") keccak_sponge_trace(events_dev, n_events, height, out, s);
+  else alu_trace(alu_chip_by_name(chip.c_str()), events_dev, n_events, height, out, true, s);
+}
+
 // CpuProver::commit (crates/stark/src/prover.rs:258-292), pipelined inside the shard.  Every matrix
 // is cut into column PIECES of about ZKB200_PIECE_MB; a piece travels
 //   host rows --(copy stream: 2-D DMA, or the pinned ring for pageable memory)--> row-major stage
@@ -367,6 +379,14 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     if (!c) throw std::runtime_error("zkb200: commit: unknown chip " + t.name);
     if (c->main_width != t.width) throw std::runtime_error("zkb200: commit: main width mismatch for " + t.name);
     check_height(ctx.machine, t.height, logn[i]);
+    if (t.flags & TRACE_EVENTS) {
+      const size_t rows_per_event = t.name == "KeccakSponge" ? KS_ROUNDS : 1;
+      event_record_words(t.name);       // throws for a chip without a row filler
+      const size_t w = t.name == "KeccakSponge" ? (size_t)KS_WIDTH : (size_t)alu_width(alu_chip_by_name(t.name.c_str()));
+      if (w != t.width) throw std::runtime_error("zkb200: commit: the row filler of " + t.name + " writes another width");
+      if (t.n_events * rows_per_event > t.height) throw std::runtime_error("zkb200: commit: more event rows than the table holds: " + t.name);
+    } else if ((t.flags & TRACE_COL_MAJOR) && t.height * t.width && !is_device_pointer(t.data))
+      throw std::runtime_error("zkb200: commit: ZKB200_TRACE_COL_MAJOR needs a device pointer: " + t.name);
     group_size[logn[i]]++;
   }
   struct Piece {
@@ -419,6 +439,7 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
   for (size_t i = 0; i < traces.size(); i++) sh->names.push_back(traces[i].name);
   cudaEvent_t alloc_done = nullptr, pull_armed = nullptr, pull_finished = nullptr;
   std::vector<PullPiece> pull;
+  std::map<size_t, DevBuf> event_bufs;      // ZKB200_TRACE_EVENTS: device copies of host event records, by matrix
   unsigned long long pull_tiles = 0;
   DevBuf pull_dev;
   u32* pull_done = nullptr;
@@ -437,6 +458,20 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     for (auto& p : pieces) {
       const TraceIn& t = traces[p.mat];
       bool pinned = false;
+      if (t.flags & (TRACE_EVENTS | TRACE_COL_MAJOR)) {
+        // nothing crosses PCIe as a matrix: the lane generates the table from its events / copies the columns
+        p.src = nullptr;
+        if ((t.flags & TRACE_EVENTS) && p.col0 == 0 && t.n_events && !is_device_pointer(t.data, &pinned) && !pinned) {
+          // pageable event records: the copy engine brings them over (a few MB), the lane waits for the event
+          const size_t words = t.n_events * event_record_words(t.name);
+          event_bufs[p.mat] = DevBuf(words, ctx.copy_stream);
+          ZKB_CUDA(cudaMemcpyAsync(event_bufs[p.mat].p, t.data, words * sizeof(u32), cudaMemcpyHostToDevice, ctx.copy_stream));
+          ZKB_CUDA(cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
+          events.v.push_back(p.ready);
+          ZKB_CUDA(cudaEventRecord(p.ready, ctx.copy_stream));
+        }
+        continue;
+      }
       if (is_device_pointer(t.data, &pinned)) {
         p.src = t.data + p.col0; p.src_pitch = t.width;
         continue;
@@ -547,11 +582,29 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     const size_t n = t.height, H = n << lb;
     u32* cols = sh->traces[p.mat].d() + p.col0 * n;
     u32* lde_cols = out.ldes[p.mat].d() + p.col0 * H;
+    if ((t.flags & TRACE_EVENTS) && p.col0 == 0) {
+      // MachineAir::generate_trace on the device: the whole table at once, column-major, in place
+      StageTimer tm(ctx, L, "commit_main_generate_traces");
+      if (p.ready) ZKB_CUDA(cudaStreamWaitEvent(L.stream, p.ready, 0));
+      const u32* ev = t.data;
+      bool pinned = false;
+      auto eb = event_bufs.find(p.mat);
+      if (eb != event_bufs.end()) { eb->second.stream = L.stream; ev = eb->second.p; }
+      else if (t.n_events && !is_device_pointer(t.data, &pinned)) {
+        const size_t words = t.n_events * event_record_words(t.name);
+        DevBuf& b = event_bufs[p.mat] = DevBuf(words, L.stream);
+        pull_words(b.p, t.data, words, L.stream);        // pinned records: SM loads, not the copy engine (common.h)
+        ev = b.p;
+      }
+      generate_trace_colmajor(t.name, ev, t.n_events, n, sh->traces[p.mat].d(), L.stream);
+    }
     {
       StageTimer tm(ctx, L, "commit_main_wait_upload_transpose");
       if (p.ready) ZKB_CUDA(cudaStreamWaitEvent(L.stream, p.ready, 0));
       if (p.pull_index >= 0) ctx.wait_value(L.stream, pull_done + p.pull_index, (u32)p.pull_tiles);
       if (p.src) transpose_piece_to_colmajor(p.src, p.src_pitch, cols, n, p.ncols, L.stream);
+      else if (t.flags & TRACE_COL_MAJOR)
+        ZKB_CUDA(cudaMemcpyAsync(cols, t.data + p.col0 * n, p.ncols * n * sizeof(u32), cudaMemcpyDeviceToDevice, L.stream));
       p.stage.stream = L.stream;     // released in lane order, after the transpose
       p.stage.release();
       if (p.whole) { p.whole->stream = L.stream; p.whole.reset(); }

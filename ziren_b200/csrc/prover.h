@@ -121,7 +121,10 @@ struct Ctx {
   void destroy();
 };
 
-struct TraceIn { std::string name; const u32* data; size_t height, width; };   // row-major Montgomery; host or device pointer
+// row-major Montgomery, host or device pointer (flags 0); device column-major (flags 1); event records (flags 2:
+// include/zkb200.h ZKB200_TRACE_COL_MAJOR / ZKB200_TRACE_EVENTS)
+struct TraceIn { std::string name; const u32* data; size_t height, width; u32 flags = 0; size_t n_events = 0; };
+constexpr u32 TRACE_COL_MAJOR = 1u, TRACE_EVENTS = 2u;
 
 struct Pk {
   Ctx* ctx = nullptr;

@@ -66,6 +66,29 @@ void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* ou
   ZKB_CHECK_LAUNCH();
 }
 
+// K6b: KeccakSponge rows, one thread per row (block = row / 24, round = row % 24), stored column-major: the 32
+// rows of a warp are 32 consecutive words of every column.  HBM-write bound: 1536 bytes of record per 24 rows read
+// (L2 hits for 23 of them), 4 * 3531 bytes per row written.
+struct KsColStore {
+  u32* p; u32 h;      // one 32 x 32 -> 64 multiply-add per address
+  __device__ __forceinline__ void operator()(int col, u32 v) { p[(u64)((u32)col) * h] = v; }
+};
+__global__ void __launch_bounds__(TG_ROWS) keccak_sponge_rows_kernel(const u32* __restrict__ recs, size_t n_blocks, size_t height,
+                                                                     u32* __restrict__ out) {
+  const size_t row = (size_t)blockIdx.x * TG_ROWS + threadIdx.x;
+  if (row >= height) return;
+  const size_t b = row / KS_ROUNDS;
+  KsColStore st{out + row, (u32)height};
+  ks_fill_row(b < n_blocks ? recs + b * KS_REC_WORDS : nullptr, (u32)(row % KS_ROUNDS), st);
+}
+
+void keccak_sponge_trace(const u32* blocks_dev, size_t n_blocks, size_t height, u32* out_colmajor, cudaStream_t s) {
+  if (!height) return;
+  if (n_blocks * KS_ROUNDS > height) throw std::runtime_error("zkb200: keccak_sponge_trace: more rows than the table holds");
+  keccak_sponge_rows_kernel<<<ceil_div(height, TG_ROWS), TG_ROWS, 0, s>>>(blocks_dev, n_blocks, height, out_colmajor);
+  ZKB_CHECK_LAUNCH();
+}
+
 int alu_chip_by_name(const char* name) {
   static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond"};
   for (int i = 0; i < ALU_NCHIPS; i++) if (!strcmp(name, names[i])) return i;

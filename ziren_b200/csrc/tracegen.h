@@ -2,6 +2,7 @@
 #pragma once
 #include "common.h"
 #include "tracegen.cuh"
+#include "tracegen_keccak.cuh"
 
 namespace zkb {
 
@@ -11,6 +12,10 @@ void tracegen_upload_constants();   // once per device: the 1/d table of the Lt 
 // row-major (the RowMajorMatrix layout zkb200_commit takes) or column-major (the layout every kernel
 // of this library works in).  Rows >= n are the chip's padding rows.
 void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* out, bool col_major, cudaStream_t s);
+
+// blocks: n_blocks records of KS_REC_WORDS words in DEVICE memory (include/zkb200.h, zkb200_keccak_block); out: height x
+// 3531 words COLUMN-MAJOR; rows >= 24 * n_blocks are the chip's padding rows.
+void keccak_sponge_trace(const u32* blocks_dev, size_t n_blocks, size_t height, u32* out_colmajor, cudaStream_t s);
 
 int alu_chip_by_name(const char* name);   // MachineAir::name -> AluChip, -1 if not an ALU chip handled here
 

@@ -91,6 +91,25 @@ class ShardMainData:
             pass
 
 
+class EventTrace:
+    """A table handed to `commit` as the chip's EVENT RECORDS (ZKB200_TRACE_EVENTS, include/zkb200.h): the library's row
+    filler generates it on the device (MachineAir::generate_trace moved into the commit).  `events`: (n, words) uint32
+    records (numpy, pinned/pageable torch tensor or CUDA tensor): 7-word ALU / control-flow events
+    (ziren_b200/tracegen.py) or 384-word KeccakSponge block records (ziren_b200/keccak_sponge.py)."""
+
+    def __init__(self, events, log_height: int, width: int):
+        self.events, self.log_height, self.width = events, int(log_height), int(width)
+        shp = _shape(events)
+        self.n_events = int(shp[0]) if len(shp) else 0
+
+
+class ColMajorTrace:
+    """A device-resident COLUMN-MAJOR table (ZKB200_TRACE_COL_MAJOR): `data` is a CUDA tensor of width x height words."""
+
+    def __init__(self, data, height: int, width: int):
+        self.data, self.height, self.width = data, int(height), int(width)
+
+
 class B200Prover:
     """`impl MachineProver<KoalaBearPoseidon2, A> for B200Prover`.  `device`: one GPU index, a list of
     indices, or -1 for every visible GPU — one prover object whose commit() routes each shard to the
@@ -121,10 +140,16 @@ class B200Prover:
         arr = (_ffi.Trace * len(named))()
         keep = []
         for i, (name, t) in enumerate(named.items()):
-            h, w = _shape(t)
             b = name.encode()
             keep.append((b, t))
-            arr[i] = _ffi.Trace(b, _data_ptr(t), h, w)
+            if isinstance(t, EventTrace):
+                arr[i] = _ffi.Trace(b, _data_ptr(t.events) if t.n_events else None, 1 << t.log_height, t.width,
+                                    _ffi.TRACE_EVENTS, t.n_events)
+            elif isinstance(t, ColMajorTrace):
+                arr[i] = _ffi.Trace(b, _data_ptr(t.data), t.height, t.width, _ffi.TRACE_COL_MAJOR, 0)
+            else:
+                h, w = _shape(t)
+                arr[i] = _ffi.Trace(b, _data_ptr(t), h, w, 0, 0)
         return arr, keep
 
     def machine(self) -> Machine:
@@ -257,6 +282,13 @@ class B200Prover:
         self._check(_ffi.lib().zkb200_convert(self._h, _data_ptr(data), n, int(to_montgomery)))
 
     # ---- trace generation ----------------------------------------------
+    def generate_keccak_sponge_trace(self, blocks, log_height: int, out, col_major: bool = False):
+        """`MachineAir::generate_trace` of the KeccakSponge chip on the GPU.  `blocks`: (n, 384) uint32 block records
+        (ziren_b200/keccak_sponge.py; numpy or a CUDA tensor); `out`: CUDA tensor of 2^log_height x 3531 words."""
+        n = int(_shape(blocks)[0]) if len(_shape(blocks)) else 0
+        self._check(_ffi.lib().zkb200_generate_keccak_sponge_trace(self._h, _data_ptr(blocks) if n else None, n, int(log_height),
+                                                                   _data_ptr(out), int(col_major)))
+
     def generate_alu_trace(self, chip: str, events, log_height: int, out, col_major: bool = False):
         """`MachineAir::generate_trace` of an ALU chip (AddSub, Bitwise, Lt, ShiftLeft, ShiftRight,
         CloClz) on the GPU.  `events`: the record's `Vec<AluEvent>` as (n, 7) uint32 words (numpy or a
