@@ -63,10 +63,30 @@ def bind_to_gpu_numa_node(torch, index):
     return None
 
 
-def make_case(args, sample=False):
+def keccak_blocks(args, lc):
+    """Event records that fill the KeccakSponge table of the keccak-real workload: four-block sponges, 24 rows per block,
+    as many as fit 2^(lc-2) rows (2^20: 2730 events = 10920 blocks = 262080 of 262144 rows)."""
+    from ziren_b200 import keccak_sponge as ksp
+    rows = 1 << (lc - 2)
+    per = 4 if rows >= 96 else 1
+    return ksp.synthetic_blocks(max(1, rows // (24 * per)), per, seed=args.rank, shard=1)
+
+
+def make_case(args, sample=False, keccak_rows="oracle"):
     synthetic.CONSTRAINTS_PER_GROUP = args.constraint_density
     w = args.workload
     lc = args.sample_log_cpu if sample else args.log_cpu
+    if w == "keccak-real":
+        # the REAL KeccakSponge chip (3531 columns, restated Air::eval, 357 lookups).  Its rows come from a row filler:
+        # the CUDA kernel in the GPU arm (keccak_rows = None: filled in by main()), the oracle in the CPU arm
+        blocks = keccak_blocks(args, lc)
+        rows = None
+        if keccak_rows == "oracle":
+            from oracle import oracle_ffi as o
+            rows = o.keccak_sponge_trace(blocks, 1 << (lc - 2))
+        case = synthetic.keccak_real_case(blocks, rows, log_cpu=lc, seed=0xC0FFEE + args.rank)
+        case.blocks = blocks
+        return case
     if w == "keccak":
         return synthetic.keccak_case(log_cpu=lc, seed=0xC0FFEE + args.rank)
     if w == "core":
@@ -81,6 +101,9 @@ def make_case(args, sample=False):
 def workload_config(args, case, sample=False):
     lc = args.sample_log_cpu if sample else args.log_cpu
     names = {"keccak": "examples/keccak-precompile-like synthetic shard (Cpu 2^%d rows, KeccakSponge 2^%d x 4259 cols)" % (lc, lc - 2),
+             "keccak-real": "examples/keccak-precompile-like shard (Cpu 2^%d rows, synthetic core tables) with the REAL KeccakSponge chip: 2^%d rows x "
+                            "3531 main + 720 permutation columns (cost 4259 per row as mips_costs.json), restated Air::eval with 3788 "
+                            "constraints and 357 lookups, rows from the row filler on well-formed four-block sponge events" % (lc, lc - 2),
              "core": "tendermint-like maximal core shard (maximal_shapes.json[21][1] scaled to Cpu 2^%d)" % lc,
              "fibonacci": "examples/fibonacci-like single core shard (Cpu 2^%d)" % lc,
              "compress": "recursion-compress-like inner proof (shrink shape, tallest table 2^%d, Poseidon2Wide 313 columns), "
@@ -132,7 +155,9 @@ def run_reference(args):
     from oracle import oracle_ffi as o
     if args.rank != 0:
         return
+    t_gen = time.perf_counter()
     case = make_case(args, sample=True)
+    t_gen = time.perf_counter() - t_gen
     om = o.OracleMachine(case.machine)
     om.setup(case.prep)
     o.set_num_threads(os.cpu_count())     # torchrun exports OMP_NUM_THREADS=1; use every host core
@@ -154,6 +179,7 @@ def run_reference(args):
             "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 (KoalaBear 31-bit prime field)", "data": "synthetic", "impl": "reference", "config": cfg,
             "same_config_as_gpu_arm": same,
+            **({"keccak_trace_generation_s_not_in_value": t_gen} if args.workload == "keccak-real" else {}),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{steps} whole shard(s) of " + ("the bench configuration itself" if same else f"the same machine scaled to Cpu 2^{args.sample_log_cpu}") +
                                        " (requested steps/warmup are capped: the CPU needs ~90 s per 2^20-cycle shard); "
@@ -168,7 +194,7 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="keccak", choices=["keccak", "core", "fibonacci", "compress"])
+    ap.add_argument("--workload", default="keccak", choices=["keccak", "keccak-real", "core", "fibonacci", "compress"])
     ap.add_argument("--log-cpu", type=int, default=20)
     ap.add_argument("--sample-log-cpu", type=int, default=None,
                     help="size of the CPU arm's shard (default: the bench configuration itself, capped at 2^20)")
@@ -211,7 +237,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", args.local_rank))
 
-    case = make_case(args)
+    case = make_case(args, keccak_rows=None)
     prover = B200Prover(case.machine, device=args.local_rank)
     stream = torch.cuda.ExternalStream(prover.stream_ptr(), device=torch.device("cuda", args.local_rank))
     prep_monty = {k: kb.to_monty(v) for k, v in case.prep.items()}
@@ -223,6 +249,17 @@ def main():
     # strong scaling (--shards S): S shards in total, rank r proves shards r, r + world, ...
     my_steps = len(range(args.rank, args.shards, args.world)) if args.shards else args.steps
 
+    real = args.workload == "keccak-real"
+    keccak_dev = None
+    if real:
+        # MachineAir::generate_trace of the KeccakSponge chip on the device (zkb200_generate_keccak_sponge_trace): the
+        # row-major table every arm below proves; the placeholder only carries its shape into the cell / byte counts
+        from ziren_b200 import keccak_sponge as ksp
+        from ziren_b200.prover import EventTrace
+        log_hk = args.log_cpu - 2
+        keccak_dev = torch.empty((1 << log_hk, ksp.WIDTH), dtype=torch.int32, device="cuda")
+        prover.generate_keccak_sponge_trace(case.blocks, log_hk, keccak_dev, col_major=False)
+        case.traces["KeccakSponge"] = np.broadcast_to(np.zeros(1, np.uint32), (1 << log_hk, ksp.WIDTH))
     # inputs: Montgomery row-major, once in pinned host memory (e2e arm), once resident in HBM
     host_tr = {}
     cfg = workload_config(args, case)
@@ -230,10 +267,19 @@ def main():
         cfg["host_numa_binding"] = "each rank bound to its GPU's local_cpulist (rank 0: %s)" % numa_cpus
     cells, shapes = case.cells, {k: v.shape for k, v in case.traces.items()}
     for k in list(case.traces):
-        host_tr[k] = torch.from_numpy(kb.to_monty(case.traces[k]).view(np.int32)).pin_memory()
+        if real and k == "KeccakSponge":
+            host_tr[k] = keccak_dev.cpu().pin_memory()
+        else:
+            host_tr[k] = torch.from_numpy(kb.to_monty(case.traces[k]).view(np.int32)).pin_memory()
         case.traces[k] = None          # the canonical copy is not needed any more (host RAM at 8 ranks)
-    dev_tr = {k: v.cuda() for k, v in host_tr.items()}
+    dev_tr = {k: (keccak_dev if (real and k == "KeccakSponge") else v.cuda()) for k, v in host_tr.items()}
     h2d_bytes = sum(4 * v.numel() for v in host_tr.values())
+    gen_tr = None
+    if real:
+        # e2e with trace generation moved into the commit: the chip's EVENT RECORDS cross PCIe (pinned), not its rows
+        ev_pinned = torch.from_numpy(case.blocks.view(np.int32)).pin_memory()
+        gen_tr = {k: (EventTrace(ev_pinned, log_hk, ksp.WIDTH) if k == "KeccakSponge" else v) for k, v in host_tr.items()}
+        h2d_bytes_gen = h2d_bytes - 4 * host_tr["KeccakSponge"].numel() + 4 * ev_pinned.numel()
     torch.cuda.synchronize()
 
     def prove(traces):
@@ -294,6 +340,12 @@ def main():
     # one shard in flight: what the reference's own GPU options ask for (shard_batch_size = 1,
     # crates/stark/src/opts.rs:83-110) - upload, layout change, LDE and leaf hashing overlap INSIDE the shard
     ms_e2e_1, proof3 = timed(host_tr, my_steps, 1)
+    ms_gen = ms_gen_1 = None
+    if real:
+        timed(gen_tr, max(args.warmup, args.e2e_threads), args.e2e_threads)
+        ms_gen, proof5 = timed(gen_tr, my_steps, args.e2e_threads)
+        ms_gen_1, proof6 = timed(gen_tr, my_steps, 1)
+        assert np.array_equal(proof, proof5) and np.array_equal(proof, proof6)
     clocks = sampler.stop()
     assert np.array_equal(proof, proof2) and np.array_equal(proof, proof3)
     # pageable host memory (what RowMajorMatrix.values is, prover.rs:258-262): staged through the pinned ring
@@ -347,6 +399,14 @@ def main():
 
     if args.rank == 0:
         total_cycles = units_per_shard * (args.shards if args.shards else args.steps * args.gpus)
+        e2e_generated = None
+        if real:
+            e2e_generated = {"value": total_cycles / (ms_gen / 1e3), "unit": unit, "ms_per_step": ms_gen / max(my_steps, 1),
+                             "h2d_bytes_per_step": h2d_bytes_gen, "d2h_bytes_per_step": d2h_bytes, "host_threads_in_flight": args.e2e_threads,
+                             "one_shard_in_flight": {"value": total_cycles / (ms_gen_1 / 1e3), "ms_per_step": ms_gen_1 / max(my_steps, 1)},
+                             "what": "the KeccakSponge table is handed to zkb200_commit as pinned EVENT RECORDS (ZKB200_TRACE_EVENTS) and generated on "
+                                     "the device inside the commit (MachineAir::generate_trace, SURVEY.md section 8 row f3); every other table is "
+                                     "uploaded as pinned row-major rows; same proof, word for word, as the other arms"}
         line = {"metric": metric, "value": total_cycles / (ms_dev / 1e3), "unit": unit, "n_gpus": args.gpus,
                 "steps": my_steps, "warmup": args.warmup, "ms_per_step": ms_dev / max(my_steps, 1), "higher_is_better": True,
                 "scaling": "strong" if args.shards else "weak", "vs_baseline": None, "dtype": "u32 (KoalaBear 31-bit prime field)", "data": "synthetic",
@@ -357,6 +417,7 @@ def main():
                         "one_shard_in_flight": {"value": total_cycles / (ms_e2e_1 / 1e3), "ms_per_step": ms_e2e_1 / max(my_steps, 1)},
                         "pageable_host_one_shard_in_flight": None if ms_e2e_pageable is None else
                         {"value": units_per_shard * max(2, args.steps // 3) / (ms_e2e_pageable / 1e3), "ms_per_step": ms_e2e_pageable / max(2, args.steps // 3)}},
+                "e2e_trace_generation_on_device": e2e_generated,
                 "verified": verified, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other,
                 "cpu_baseline": cpu_base,
                 "stage_ms": stages, "cells_per_sec": cells * (args.shards if args.shards else args.steps * args.gpus) / (ms_dev / 1e3)}

@@ -155,6 +155,50 @@ def test_rows_have_the_structure_event_to_rows_gives_them(oracle):
     assert out_vals == [(st[i // 2] >> (32 * (i % 2))) & 0xFFFFFFFF for i in range(16)]
 
 
+def _real_case(oracle, per=(1, 2, 1, 1), log_cpu=10, seed=3):
+    from ziren_b200 import synthetic
+    b = ks.synthetic_blocks(len(per), list(per), seed=seed, shard=1)
+    t = oracle.keccak_sponge_trace(b, 1 << ks.padded_log_height(len(b)))
+    return b, synthetic.keccak_real_case(b, t, log_cpu=log_cpu, num_queries=6, pow_bits=3)
+
+
+def test_real_keccak_sponge_air_accepts_the_generated_rows(oracle):
+    """KeccakSpongeChip::eval restated (ziren_b200/keccak_air.py: the p3 KeccakAir constraints, the sponge rules, 357
+    lookups balanced by Byte / MemoryLocalPrecompile / SyscallPrecompile tables) over the row filler's rows: proved and
+    verified on the CPU, single-cell corruptions rejected.  The chip's cost equals the reference's cost table."""
+    from ziren_b200 import keccak_air
+    chip = keccak_air.keccak_sponge_chip()
+    # crates/core/executor/src/artifacts/mips_costs.json: "KeccakSponge": 102216 per 24 rows
+    assert chip.cost * 24 == 102216 and chip.main_width == 3531 and chip.perm_width_ef == 180 and chip.log_quotient_degree == 1
+    assert len(chip.builder.sends) + len(chip.builder.receives) == 357
+    b, case = _real_case(oracle)
+    om = oracle.OracleMachine(case.machine)
+    om.setup(case.prep)
+    proof, _ = om.prove_shard(case.traces, case.public_values)
+    ok, err = om.verify_shard(proof)
+    assert ok, err
+    t = case.traces["KeccakSponge"]
+    cells = [(0, C.A_PRIME + 7), (5, C.C + 64), (23, C.A_PRIME_PRIME_PRIME_0_0_LIMBS), (24, C.ORIGINAL_STATE + 3), (47, C.IS_ABSORBED),
+             (0, C.BLOCK_MEM + C.M_DIFF16), (0, C.XORED_GENERAL_RATE + 5), (71, C.OUTPUT_MEM + 4), (3, C.CLK), (100, C.STEP_FLAGS + 4),
+             (126, C.A_PRIME_PRIME + 9)]
+    for row, col in cells:
+        bad = dict(case.traces)
+        bad["KeccakSponge"] = t.copy()
+        bad["KeccakSponge"][row, col] = (int(t[row, col]) + 1) % kb.P
+        try:
+            p2, _ = om.prove_shard(bad, case.public_values)
+        except RuntimeError:
+            continue                      # the oracle prover refuses (final polynomial not constant)
+        assert not om.verify_shard(p2)[0], (row, col)
+    # a missing byte-table multiplicity unbalances the shard's local cumulative sums
+    bad = dict(case.traces)
+    bad["Byte"] = case.traces["Byte"].copy()
+    i = int(np.flatnonzero(bad["Byte"][:, 1])[0])
+    bad["Byte"][i, 1] -= 1
+    p2, _ = om.prove_shard(bad, case.public_values)
+    assert not om.verify_shard(p2)[0]
+
+
 def test_padded_height_rule():
     assert [ks.padded_log_height(n) for n in (0, 1, 2, 5, 6, 10922, 10923)] == [0, 5, 6, 7, 8, 18, 19]
     assert ks.padded_log_height(3, fixed_log2_rows=10) == 10
@@ -209,6 +253,33 @@ def test_gpu_keccak_trace_errors(gpu):
     out = torch.zeros(32 * ks.WIDTH, dtype=torch.int32, device="cuda")
     with pytest.raises(ZkbError, match="more rows than"):
         prover.generate_keccak_sponge_trace(ks.synthetic_blocks(2, 1), 5, out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["rows_host", "events_host", "events_device"])
+def test_real_keccak_shard_proves_bit_exact(gpu, oracle, mode):
+    """A shard with the REAL KeccakSponge chip: uploaded rows, or event records handed to zkb200_commit (the table is
+    generated inside the commit) - the proof is the oracle's proof over the oracle's rows, word for word."""
+    from ziren_b200.prover import B200Prover, EventTrace
+    torch, _ = gpu
+    b, case = _real_case(oracle, per=(1, 3, 2, 4, 1), log_cpu=11, seed=8)
+    om = oracle.OracleMachine(case.machine)
+    om.setup(case.prep)
+    want, _ = om.prove_shard(case.traces, case.public_values)
+    prover = B200Prover(case.machine, device=0)
+    try:
+        pk = prover.setup({k: kb.to_monty(v) for k, v in case.prep.items()})
+        inputs = {k: kb.to_monty(v) for k, v in case.traces.items()}
+        if mode != "rows_host":
+            ev = torch.from_numpy(b.view(np.int32)).cuda() if mode == "events_device" else b
+            inputs["KeccakSponge"] = EventTrace(ev, ks.padded_log_height(len(b)), ks.WIDTH)
+        got, _ = prover.prove_shard(pk, inputs, case.public_values)
+        ok, err = om.verify_shard(got)
+        assert ok, err
+        assert np.array_equal(got, want)
+        pk.free()
+    finally:
+        prover.close()
 
 
 @pytest.mark.gpu

@@ -19,7 +19,7 @@ from ziren_b200 import synthetic  # noqa: E402
 from ziren_b200.prover import B200Prover  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("what", choices=["lde", "ntt", "mmcs", "permute", "tracegen"])
+ap.add_argument("what", choices=["lde", "ntt", "mmcs", "permute", "tracegen", "keccak"])
 ap.add_argument("--chip", default="ShiftRight", help="tracegen: AddSub, Bitwise, Lt, ShiftLeft, ShiftRight or CloClz")
 ap.add_argument("--col-major", action="store_true", help="tracegen: write the column-major layout")
 ap.add_argument("--log-n", type=int, default=18)
@@ -69,12 +69,23 @@ elif args.what == "tracegen":
     d_out = torch.empty((n * w,), dtype=torch.int32, device="cuda")
     ms = timed(lambda: prover.generate_alu_trace(args.chip, d_ev, args.log_n, d_out, col_major=args.col_major))
     alg = 28.0 * (n - 77) + 4.0 * n * w          # one event read, one row written
+elif args.what == "keccak":
+    from ziren_b200 import keccak_sponge as ksp
+    w = ksp.WIDTH
+    nb = n // 24 - 3
+    blocks = ksp.synthetic_blocks(nb // 4, 4, seed=1)
+    d_ev = torch.from_numpy(blocks.view(np.int32)).cuda()
+    d_out = torch.empty((n * w,), dtype=torch.int32, device="cuda")
+    ms = timed(lambda: prover.generate_keccak_sponge_trace(d_ev, args.log_n, d_out, col_major=True))
+    alg = 1536.0 * len(blocks) + 4.0 * n * w     # one record read per block, one row written
 else:
     d_in = torch.randint(0, kb.P, (n, 16), dtype=torch.int32, device="cuda")
     ms = timed(lambda: (prover.poseidon2_permute_batch(d_in, n), prover.sync()))
     alg = 128.0 * n
 gbs = alg / (ms / 1e3) / 1e9
 out = {"what": args.what, "log_n": args.log_n, "width": w, "ms": ms, "algorithmic_GB": alg / 1e9, "GB/s": gbs, "frac_of_measured_hbm": gbs / PEAK}
+if args.what == "keccak":
+    out.update({"chip": "KeccakSponge", "layout": "column-major", "Grows/s": n / (ms / 1e3) / 1e9, "PCIe_ms_for_the_same_rows_at_55GB/s": 4.0 * n * w / 55e9 * 1e3})
 if args.what == "tracegen":
     out.update({"chip": args.chip, "width": w, "layout": "column-major" if args.col_major else "row-major", "Grows/s": n / (ms / 1e3) / 1e9})
 if args.what in ("mmcs", "permute"):

@@ -189,6 +189,15 @@ class _Filtered:
     def when(self, cond):
         return _Filtered(self._base, self._c * cond)
 
+    def when_transition(self):
+        return self.when(self._base.is_transition())
+
+    def when_first_row(self):
+        return self.when(self._base.is_first_row())
+
+    def when_last_row(self):
+        return self.when(self._base.is_last_row())
+
     def assert_zero(self, e):
         e = e if isinstance(e, Expr) else self._base.const(e)
         self._base.assert_zero(self._c * e)

@@ -8,14 +8,19 @@ namespace zkb {
 
 struct LogupArgs {
   const u32* prep; const u32* main_; size_t n;
-  const DevTerm* terms; const DevVPC* vpcs; const DevLookup* lookups;
-  u32 lk_begin, lk_end, batch, ew;
-  Ef alpha;
-  Ef bpow[17];      // beta^0 .. beta^16
+  const DevTerm* terms; const DevVPC* vpcs;
+  const DevFlatLookup* flk; const DevFlatTerm* fterms;      // the chip's own ranges
+  const u32* lkK; const u32* lkE;                           // per-proof coefficients (lookup_coefficients)
+  u32 nlk, batch, ew;
   u32* out;         // n x 4*ew column-major
   u32* rowsum;      // 4 x n
 };
 
+__device__ __forceinline__ Ef load_ef4(const u32* p, u32 i) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
+  Ef e; e.c[0] = fp_raw(v.x); e.c[1] = fp_raw(v.y); e.c[2] = fp_raw(v.z); e.c[3] = fp_raw(v.w);
+  return e;
+}
 __device__ __forceinline__ Fp eval_vpc(const LogupArgs& a, u32 vi, size_t r) {
   DevVPC v = a.vpcs[vi];
   Fp acc = fp_raw(v.constant);
@@ -28,28 +33,123 @@ __device__ __forceinline__ Fp eval_vpc(const LogupArgs& a, u32 vi, size_t r) {
   return acc;
 }
 
+// 1 / den for G denominators with ONE base-field inversion: ef_inv (kb31.cuh) takes the norm down to F and inverts
+// there (a 30-step power), so the G norms share a Montgomery batch inversion.  A zero denominator (probability
+// 2^-124 per lookup) has inverse 0 in ef_inv; here it is replaced by 1 in the product and masked afterwards, so the
+// result is the same.
+template <int G>
+__device__ __forceinline__ void ef_inv_batch(const Ef* den, Ef* out) {
+  Fp n0[G], n1[G], d[G], pref[G];
+#pragma unroll
+  for (int i = 0; i < G; i++) {
+    const Fp a0 = den[i].c[0], a1 = den[i].c[1], a2 = den[i].c[2], a3 = den[i].c[3];
+    const Fp A0 = a0 * a0 + fp_mul3(a2 * a2), A1 = fp_double(a0 * a2);
+    const Fp B0 = a1 * a1 + fp_mul3(a3 * a3), B1 = fp_double(a1 * a3);
+    n0[i] = A0 - fp_mul3(B1);
+    n1[i] = A1 - B0;
+    d[i] = n0[i] * n0[i] - fp_mul3(n1[i] * n1[i]);
+    const Fp dd = d[i].v ? d[i] : fp_one();
+    pref[i] = i ? pref[i - 1] * dd : dd;
+  }
+  Fp inv = fp_inv(pref[G - 1]);
+#pragma unroll
+  for (int i = G - 1; i >= 0; i--) {
+    const Fp dd = d[i].v ? d[i] : fp_one();
+    Fp di = i ? inv * pref[i - 1] : inv;
+    inv = inv * dd;
+    if (!d[i].v) di = fp_zero();
+    const Fp I0 = n0[i] * di, I1 = -(n1[i] * di);
+    const Fp a0 = den[i].c[0], a1 = den[i].c[1], a2 = den[i].c[2], a3 = den[i].c[3];
+    out[i].c[0] = a0 * I0 + fp_mul3(a2 * I1);
+    out[i].c[2] = a0 * I1 + a2 * I0;
+    out[i].c[1] = -(a1 * I0 + fp_mul3(a3 * I1));
+    out[i].c[3] = -(a1 * I1 + a3 * I0);
+  }
+}
+
 __global__ void __launch_bounds__(128) logup_rows_kernel(LogupArgs a) {
   size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (r >= a.n) return;
+  constexpr int G = 8;                       // lookups per shared inversion; the batch size (1, 2 or 4) divides it
   Ef total = ef_zero();
-  u32 lk = a.lk_begin;
-  for (u32 b = 0; b + 1 < a.ew; b++) {
-    Ef v = ef_zero();
-    for (u32 k = 0; k < a.batch && lk < a.lk_end; k++, lk++) {
-      DevLookup l = a.lookups[lk];
-      Ef den = a.alpha + fp_raw(l.kind);
-      u32 j = 1;
-      for (u32 vi = l.value_begin; vi < l.value_end; vi++, j++) den += a.bpow[j] * eval_vpc(a, vi, r);
-      Fp mult = eval_vpc(a, l.mult_vpc, r);
-      if (!l.is_send) mult = -mult;
-      v += ef_inv(den) * mult;
-    }
+  u32 b = 0;                                 // permutation column being filled
+  for (u32 lk0 = 0; lk0 < a.nlk; lk0 += G) {
+    Ef den[G], inv[G];
+    Fp mult[G];
 #pragma unroll
-    for (int c = 0; c < 4; c++) a.out[(size_t)(4 * b + c) * a.n + r] = v.c[c].v;
-    total += v;
+    for (int k = 0; k < G; k++) {
+      const u32 lk = lk0 + k;
+      if (lk < a.nlk) {
+        const DevFlatLookup l = a.flk[lk];
+        Ef dk = load_ef4(a.lkK, lk);
+        for (u32 t = l.fterm_begin; t < l.fterm_end; t++) {
+          const DevFlatTerm tm = a.fterms[t];
+          const u32* base = (tm.col & 0x80000000u) ? a.main_ : a.prep;
+          dk += load_ef4(a.lkE, t) * fp_raw(base[(size_t)(tm.col & 0x7fffffffu) * a.n + r]);
+        }
+        Fp m = eval_vpc(a, l.mult_vpc, r);
+        mult[k] = l.is_send ? m : -m;
+        den[k] = dk;
+      } else { den[k] = ef_one(); mult[k] = fp_zero(); }
+    }
+    ef_inv_batch<G>(den, inv);
+    Ef v = ef_zero();
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+      if (lk0 + k < a.nlk) {
+        v += inv[k] * mult[k];
+        // a batch is complete after `batch` lookups (a power of two dividing G), or at the chip's last lookup
+        if ((((u32)k + 1) & (a.batch - 1)) == 0 || lk0 + k + 1 == a.nlk) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) a.out[(size_t)(4 * b + c) * a.n + r] = v.c[c].v;
+          total += v;
+          v = ef_zero();
+          b++;
+        }
+      }
+    }
   }
 #pragma unroll
   for (int c = 0; c < 4; c++) a.rowsum[(size_t)c * a.n + r] = total.c[c].v;
+}
+
+// ---- per-proof fingerprint coefficients of the flattened lookups (machine_dev.h) ----------------------------
+struct CoefArgs {
+  const DevLookup* lookups; const DevVPC* vpcs; const DevFlatTerm* fterms;
+  u32 nlk, nterms;
+  Ef alpha;
+  Ef bpow[17];
+  u32* K; u32* E;
+};
+__global__ void lookup_coefficients_kernel(CoefArgs a) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.nlk) {
+    const DevLookup l = a.lookups[i];
+    Ef k = a.alpha + fp_raw(l.kind);
+    u32 j = 1;
+    for (u32 vi = l.value_begin; vi < l.value_end; vi++, j++) k += a.bpow[j] * fp_raw(a.vpcs[vi].constant);
+#pragma unroll
+    for (int c = 0; c < 4; c++) a.K[4 * i + c] = k.c[c].v;
+  }
+  if (i < a.nterms) {
+    const DevFlatTerm t = a.fterms[i];
+    const Ef e = a.bpow[t.j] * fp_raw(t.w);
+#pragma unroll
+    for (int c = 0; c < 4; c++) a.E[4 * i + c] = e.c[c].v;
+  }
+}
+void lookup_coefficients(const MachineInfo& m, const ChipInfo& chip, const Ef& alpha, const Ef* bpow17, u32* K_out, u32* E_out,
+                         cudaStream_t s) {
+  CoefArgs a;
+  a.lookups = m.d_lookups + chip.dev_lookup_begin; a.vpcs = m.d_vpcs; a.fterms = m.d_fterms + chip.dev_fterm_begin;
+  a.nlk = chip.dev_lookup_end - chip.dev_lookup_begin; a.nterms = chip.dev_fterm_end - chip.dev_fterm_begin;
+  a.alpha = alpha;
+  for (int i = 0; i < 17; i++) a.bpow[i] = bpow17[i];
+  a.K = K_out; a.E = E_out;
+  const u32 n = std::max(a.nlk, a.nterms);
+  if (!n) return;
+  lookup_coefficients_kernel<<<ceil_div(n, 128), 128, 0, s>>>(a);
+  ZKB_CHECK_LAUNCH();
 }
 
 // ---- modular inclusive prefix sum over 4 independent sequences of length n ----------------------
@@ -107,13 +207,19 @@ void permutation_trace(const MachineInfo& m, const ChipInfo& chip, const u32* pr
   const u32 ew = chip.perm_width_ef();
   if (ew == 0) { ZKB_CUDA(cudaMemsetAsync(local_sum_dev, 0, 16, s)); return; }
   if (chip.max_values > 16) throw std::runtime_error("zkb200: lookup tuple longer than 16 values");
+  if (chip.batch_size() > 8) throw std::runtime_error("zkb200: permutation batches of more than 8 lookups (log_quotient_degree > 3)");
   LogupArgs a;
   a.prep = prep; a.main_ = main_; a.n = n;
-  a.terms = m.d_terms; a.vpcs = m.d_vpcs; a.lookups = m.d_lookups;
-  a.lk_begin = chip.dev_lookup_begin; a.lk_end = chip.dev_lookup_end; a.batch = chip.batch_size(); a.ew = ew;
-  a.alpha = alpha;
-  a.bpow[0] = ef_one();
-  for (int i = 1; i < 17; i++) a.bpow[i] = a.bpow[i - 1] * beta;
+  a.terms = m.d_terms; a.vpcs = m.d_vpcs;
+  a.flk = m.d_flk + chip.dev_lookup_begin; a.fterms = m.d_fterms + chip.dev_fterm_begin;
+  a.nlk = chip.dev_lookup_end - chip.dev_lookup_begin; a.batch = chip.batch_size(); a.ew = ew;
+  Ef bpow[17];
+  bpow[0] = ef_one();
+  for (int i = 1; i < 17; i++) bpow[i] = bpow[i - 1] * beta;
+  const u32 nterms = chip.dev_fterm_end - chip.dev_fterm_begin;
+  DevBuf coefK(4 * (size_t)std::max<u32>(a.nlk, 1), s), coefE(4 * (size_t)std::max<u32>(nterms, 1), s);
+  lookup_coefficients(m, chip, alpha, bpow, coefK.p, coefE.p, s);
+  a.lkK = coefK.p; a.lkE = coefE.p;
   a.out = out;
   const size_t nblk = ceil_div(n, SCAN_BLOCK);
   DevBuf rowsum(4 * n, s), btot(4 * nblk, s);

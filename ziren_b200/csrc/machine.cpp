@@ -159,6 +159,8 @@ void MachineInfo::upload() {
   std::vector<DevLookup> lookups;
   std::vector<Instr> code;
   std::vector<u32> consts;
+  std::vector<DevFlatLookup> flk;
+  std::vector<DevFlatTerm> fterms;
   auto add_vpc = [&](const HostVPC& v) {
     DevVPC d;
     d.constant = fp_from_canonical(v.const_canon % KB_P).v;
@@ -170,8 +172,16 @@ void MachineInfo::upload() {
   };
   for (auto& c : chips) {
     c.dev_lookup_begin = (u32)lookups.size();
+    c.dev_fterm_begin = (u32)fterms.size();
     c.max_values = 0;
     for (auto& l : c.lookups) {
+      DevFlatLookup f;
+      f.fterm_begin = (u32)fterms.size() - c.dev_fterm_begin;
+      for (size_t j = 0; j < l.values.size(); j++)
+        for (auto& t : l.values[j].terms)
+          fterms.push_back(DevFlatTerm{t.col | (t.is_main ? 0x80000000u : 0u), (u32)j + 1, fp_from_canonical(t.w_canon % KB_P).v});
+      f.fterm_end = (u32)fterms.size() - c.dev_fterm_begin;
+      f.is_send = l.is_send ? 1 : 0;
       DevLookup d;
       d.kind = fp_from_canonical(l.kind).v;
       d.is_send = l.is_send ? 1 : 0;
@@ -181,8 +191,11 @@ void MachineInfo::upload() {
       d.value_end = (u32)vpcs.size();
       c.max_values = std::max<u32>(c.max_values, (u32)l.values.size());
       lookups.push_back(d);
+      f.mult_vpc = d.mult_vpc;
+      flk.push_back(f);
     }
     c.dev_lookup_end = (u32)lookups.size();
+    c.dev_fterm_end = (u32)fterms.size();
     lower_chip(c, code, consts);
   }
   auto up = [](auto*& dptr, const auto& v) {
@@ -194,6 +207,8 @@ void MachineInfo::upload() {
   up(d_terms, terms);
   up(d_vpcs, vpcs);
   up(d_lookups, lookups);
+  up(d_flk, flk);
+  up(d_fterms, fterms);
   up(d_code, code);
   up(d_consts, consts);
 }
@@ -202,6 +217,9 @@ void MachineInfo::destroy() {
   if (d_terms) cudaFree(d_terms);
   if (d_vpcs) cudaFree(d_vpcs);
   if (d_lookups) cudaFree(d_lookups);
+  if (d_flk) cudaFree(d_flk);
+  if (d_fterms) cudaFree(d_fterms);
+  d_flk = nullptr; d_fterms = nullptr;
   if (d_code) cudaFree(d_code);
   if (d_consts) cudaFree(d_consts);
   d_consts = nullptr;

@@ -7,6 +7,7 @@
 // (crates/stark/src/lookup/lookup.rs:10-19), the symbolic constraint DAG of
 // get_symbolic_constraints (crates/stark/src/machine.rs:377-389).
 #pragma once
+#include <atomic>
 #include "common.h"
 #include "machine_dev.h"
 #include <string>
@@ -20,6 +21,14 @@ struct HostTerm { bool is_main; u32 col; u32 w_canon; };
 struct HostVPC { u32 const_canon; std::vector<HostTerm> terms; };
 struct HostLookup { u32 kind, scope; HostVPC mult; std::vector<HostVPC> values; bool is_send; };
 struct HostNode { u32 op, a, b; };
+
+// a per-chip cache slot that copies as "empty" (ChipInfo stays copyable)
+struct KernelSlot {
+  mutable std::atomic<void*> p{nullptr};
+  KernelSlot() = default;
+  KernelSlot(const KernelSlot&) {}
+  KernelSlot& operator=(const KernelSlot&) { p.store(nullptr); return *this; }
+};
 
 struct ChipInfo {
   std::string name;
@@ -40,11 +49,14 @@ struct ChipInfo {
   }
 
   // device image (filled by MachineInfo::upload)
-  u32 dev_lookup_begin = 0, dev_lookup_end = 0;   // range in the machine-wide DevLookup table
+  u32 dev_lookup_begin = 0, dev_lookup_end = 0;   // range in the machine-wide DevLookup / DevFlatLookup tables
+  u32 dev_fterm_begin = 0, dev_fterm_end = 0;     // range in the machine-wide DevFlatTerm table
   u32 max_values = 0;                             // longest lookup tuple
   u32 code_begin = 0, code_end = 0;               // range in the machine-wide Instr table
   u32 n_regs = 0;
   u32 const_begin = 0;                            // first slot of this chip in the constant pool
+  // generated constraint kernel of this chip (quotient_codegen.cpp), looked up once: null = not yet, 1 = none (interpreter)
+  KernelSlot qk_cached;
 };
 
 struct MachineInfo {
@@ -55,6 +67,8 @@ struct MachineInfo {
   DevTerm* d_terms = nullptr;
   DevVPC* d_vpcs = nullptr;
   DevLookup* d_lookups = nullptr;
+  DevFlatLookup* d_flk = nullptr;       // per lookup, parallel to d_lookups
+  DevFlatTerm* d_fterms = nullptr;
   Instr* d_code = nullptr;
   u32* d_consts = nullptr;      // constant pool, Montgomery
 

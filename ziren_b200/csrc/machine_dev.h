@@ -10,6 +10,14 @@ struct DevTerm { u32 col; u32 w; };                 // col: bit 31 set = main tr
 struct DevVPC { u32 constant; u32 term_begin, term_end; };
 struct DevLookup { u32 kind; u32 is_send; u32 mult_vpc; u32 value_begin, value_end; };   // kind Montgomery
 
+// Flattened lookups: the fingerprint of a lookup is affine in the row,
+//   alpha + kind + sum_j beta^j v_j(row) = K + sum_t E_t * x[col_t],   K = alpha + kind + sum_j beta^j const_j,  E_t = beta^j w_t,
+// so K and the E_t are computed ONCE per proof (lookup_coefficients, logup.cu) and the row kernels (K5 permutation
+// trace, K3 LogUp constraints) run one flat loop of EF x base multiply-adds per lookup instead of walking
+// DevLookup -> DevVPC -> DevTerm for every row.  fterm_* index the chip's own term range.
+struct DevFlatLookup { u32 fterm_begin, fterm_end; u32 mult_vpc; u32 is_send; };
+struct DevFlatTerm { u32 col; u32 j; u32 w; };      // col as DevTerm; j: 1-based position of the value in the tuple; w Montgomery
+
 // Bytecode of the constraint interpreter (K3).  16-byte instructions {op|dst, a, b, c}; operands
 // are tagged references, so trace columns, public values, selectors and constants are read where
 // they are used instead of through separate load instructions:

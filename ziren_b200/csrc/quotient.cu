@@ -5,6 +5,7 @@
 // bytecode (machine.cpp); all threads execute the same instruction stream, so there is no
 // divergence and instruction fetches are broadcast.
 #include "quotient.h"
+#include "logup.h"
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
@@ -76,14 +77,13 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotArgs a) {
 }
 
 __global__ void alpha_pow_kernel(u32* out, u32 C, Ef alpha) {
-  // out[k] = alpha^(C-1-k); C is at most a few thousand: one thread, sequential, runs once per chip
-  if (blockIdx.x || threadIdx.x) return;
-  Ef p = ef_one();
-  for (u32 k = 0; k < C; k++) {
-    u32* o = out + 4 * (size_t)(C - 1 - k);
-    o[0] = p.c[0].v; o[1] = p.c[1].v; o[2] = p.c[2].v; o[3] = p.c[3].v;
-    p *= alpha;
-  }
+  // out[k] = alpha^(C-1-k), one thread per power (square and multiply): the real KeccakSponge chip has 3 970
+  // constraints, a sequential chain of that many EF products took a millisecond per proof
+  const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= C) return;
+  const Ef p = ef_pow(alpha, C - 1 - k);
+  u32* o = out + 4 * (size_t)k;
+  o[0] = p.c[0].v; o[1] = p.c[1].v; o[2] = p.c[2].v; o[3] = p.c[3].v;
 }
 
 void quotient_values(const MachineInfo& m, const ChipInfo& chip, const NttTables& tb, const QuotientInputs& in, u32* out,
@@ -97,10 +97,16 @@ void quotient_values(const MachineInfo& m, const ChipInfo& chip, const NttTables
   if (a.lqd > 4) throw std::runtime_error("zkb200: log_quotient_degree > 4 unsupported");
   a.code = m.d_code; a.code_begin = chip.code_begin; a.code_end = chip.code_end; a.n_air = (u32)chip.constraints.size();
   a.terms = m.d_terms; a.vpcs = m.d_vpcs; a.lookups = m.d_lookups; a.lk_begin = chip.dev_lookup_begin; a.lk_end = chip.dev_lookup_end;
+  a.flk = m.d_flk + chip.dev_lookup_begin; a.fterms = m.d_fterms + chip.dev_fterm_begin;
   a.pub = in.pub_dev; a.consts = m.d_consts; a.tw_lo = tb.tw_lo; a.tw_hi = tb.tw_hi;
   a.perm_alpha = in.perm_alpha; a.local_sum = in.local_sum;
   a.bpow[0] = ef_one();
   for (int i = 1; i < 17; i++) a.bpow[i] = a.bpow[i - 1] * in.perm_beta;
+  // per-proof fingerprint coefficients of the flattened lookups
+  const u32 nlk = chip.dev_lookup_end - chip.dev_lookup_begin, nft = chip.dev_fterm_end - chip.dev_fterm_begin;
+  DevBuf coefK(4 * (size_t)std::max<u32>(nlk, 1), s), coefE(4 * (size_t)std::max<u32>(nft, 1), s);
+  if (a.ew) lookup_coefficients(m, chip, in.perm_alpha, a.bpow, coefK.p, coefE.p, s);
+  a.lkK = coefK.p; a.lkE = coefE.p;
   memcpy(a.gsum, in.global_sum, sizeof(a.gsum));
   // Z_H(x) = x^n - 1 on x = g * w_Q^i:  g^n * (w_Q^n)^i, w_Q^n of order 2^lqd
   const size_t n = (size_t)1 << in.log_n;
@@ -116,7 +122,7 @@ void quotient_values(const MachineInfo& m, const ChipInfo& chip, const NttTables
   a.ginv = fp_inv(two_adic_generator(in.log_n)).v;
   const u32 C = chip.num_constraints();
   DevBuf apow((size_t)4 * (C ? C : 1), s);
-  alpha_pow_kernel<<<1, 32, 0, s>>>(apow.p, C, in.alpha);
+  alpha_pow_kernel<<<ceil_div(std::max<u32>(C, 1), 128), 128, 0, s>>>(apow.p, C, in.alpha);
   ZKB_CHECK_LAUNCH();
   a.alpha_pow = apow.p;
   a.out = out;

@@ -19,6 +19,8 @@ struct QuotArgs {
   u32 ew, batch, main_width, global_scope;
   const Instr* code; u32 code_begin, code_end, n_air;
   const DevTerm* terms; const DevVPC* vpcs; const DevLookup* lookups; u32 lk_begin, lk_end;
+  const DevFlatLookup* flk; const DevFlatTerm* fterms;      // the chip's own flattened lookups (machine_dev.h)
+  const u32* lkK; const u32* lkE;                           // their per-proof coefficients (lookup_coefficients, logup.cu)
   const u32* alpha_pow;   // [C][4] Montgomery: alpha^(C-1-k)
   const u32* consts;      // constant pool (Montgomery)
   const u32* pub;
@@ -82,32 +84,53 @@ __device__ __forceinline__ QuotRow q_prologue(const QuotArgs& a) {
   return r;
 }
 
+// fingerprint and signed multiplicity of the chip's lookup `lk` on row t: K + sum_t E_t * x[col_t] (machine_dev.h)
+__device__ __forceinline__ void q_lookup(const QuotArgs& a, u32 lk, size_t t, Ef& rr, Fp& mult) {
+  const DevFlatLookup l = a.flk[lk];
+  rr = load_apow(a.lkK, lk);
+  for (u32 ti = l.fterm_begin; ti < l.fterm_end; ti++) {
+    const DevFlatTerm tm = a.fterms[ti];
+    const u32* base = (tm.col & 0x80000000u) ? a.main_ : a.prep;
+    rr += load_apow(a.lkE, ti) * fp_raw(__ldg(base + (size_t)(tm.col & 0x7fffffffu) * a.H + t));
+  }
+  const Fp mu = q_eval_vpc(a, l.mult_vpc, t);
+  mult = l.is_send ? mu : -mu;
+}
+
 // permutation constraints (permutation.rs:205-347), then the global cumulative sum rows; k: index of the
 // next constraint's alpha power
 __device__ __forceinline__ void q_lookup_constraints(const QuotArgs& a, const QuotRow& r, Ef& acc, u32 k) {
   const size_t t = r.t, tn = r.tn;
   if (a.ew) {
-    u32 lk = a.lk_begin;
+    const u32 nlk = a.lk_end - a.lk_begin;
+    u32 lk = 0;
     Ef sum_local = ef_zero(), sum_next = ef_zero();
     for (u32 b = 0; b + 1 < a.ew; b++) {
-      Ef rlc[8];
-      Fp mult[8];
-      u32 cnt = 0;
-      for (; cnt < a.batch && lk < a.lk_end; cnt++, lk++) {
-        DevLookup l = a.lookups[lk];
-        Ef rr = a.perm_alpha + fp_raw(l.kind);
-        u32 j = 1;
-        for (u32 vi = l.value_begin; vi < l.value_end; vi++, j++) rr += a.bpow[j] * q_eval_vpc(a, vi, t);
-        Fp mu = q_eval_vpc(a, l.mult_vpc, t);
-        rlc[cnt] = rr;
-        mult[cnt] = l.is_send ? mu : -mu;
-      }
-      Ef product = ef_one(), numerator = ef_zero();
-      for (u32 p = 0; p < cnt; p++) {
-        product *= rlc[p];
-        Ef abc = ef_one();
-        for (u32 q = 0; q < cnt; q++) if (q != p) abc *= rlc[q];
-        numerator += abc * mult[p];
+      // product = prod_p rlc_p, numerator = sum_p mult_p prod_{q != p} rlc_q over the batch's lookups
+      Ef product, numerator;
+      if (a.batch == 1) {
+        Fp m0;
+        q_lookup(a, lk++, t, product, m0);
+        numerator = ef_from_fp(m0);
+      } else if (a.batch == 2) {
+        Ef r0, r1 = ef_one();
+        Fp m0, m1 = fp_zero();
+        q_lookup(a, lk++, t, r0, m0);
+        if (lk < nlk) q_lookup(a, lk++, t, r1, m1);
+        product = r0 * r1;
+        numerator = r1 * m0 + r0 * m1;
+      } else {
+        Ef rlc[8];
+        Fp mult[8];
+        u32 cnt = 0;
+        for (; cnt < a.batch && lk < nlk; cnt++, lk++) q_lookup(a, lk, t, rlc[cnt], mult[cnt]);
+        product = ef_one(); numerator = ef_zero();
+        for (u32 p = 0; p < cnt; p++) {
+          product *= rlc[p];
+          Ef abc = ef_one();
+          for (u32 q = 0; q < cnt; q++) if (q != p) abc *= rlc[q];
+          numerator += abc * mult[p];
+        }
       }
       Ef entry = load_ef(a.perm, a.H, 4 * b, t);
       acc += load_apow(a.alpha_pow, k++) * (product * entry - numerator);

@@ -162,9 +162,11 @@ def _plain_trace(rng, log_height: int) -> np.ndarray:
 
 def build_case(wides: list[WideSpec], *, with_fib: int | None = None, seed: int = 0xC0FFEE,
                num_queries: int = 84, pow_bits: int = 16, cycles: int | None = None, log_blowup: int = 1,
-               plain: list[tuple[str, int]] = ()) -> ShardCase:
+               plain: list[tuple[str, int]] = (), real: dict | None = None) -> ShardCase:
     """Assemble a machine from wide tables (+ optional Fibonacci/Sink pair of log height
-    `with_fib`) and generate one balanced shard."""
+    `with_fib`) and generate one balanced shard.  `real`: restated real chips next to the synthetic ones
+    (keccak_real_case): {"chips": [...], "traces": {...}, "byte_mults": (65536, 3)}; the Byte table is then the one of
+    ziren_b200/keccak_air.py, which also receives their XOR / range lookups."""
     rng = np.random.Generator(np.random.PCG64(seed))
     pv = np.zeros(8, dtype=np.uint32)
     chips, traces, prep = [], {}, {}
@@ -179,9 +181,18 @@ def build_case(wides: list[WideSpec], *, with_fib: int | None = None, seed: int 
         traces[w.name] = t
         for g in range(w.lookups):
             byte_counts += np.bincount(t[:, 6 * g + 5], minlength=1 << RANGE_BITS).astype(np.uint64)
-    chips.append(_byte_chip())
-    prep["Byte"] = np.arange(1 << RANGE_BITS, dtype=np.uint32).reshape(-1, 1)
-    traces["Byte"] = (byte_counts % np.uint64(P)).astype(np.uint32).reshape(-1, 1)
+    if real is None:
+        chips.append(_byte_chip())
+        prep["Byte"] = np.arange(1 << RANGE_BITS, dtype=np.uint32).reshape(-1, 1)
+        traces["Byte"] = (byte_counts % np.uint64(P)).astype(np.uint32).reshape(-1, 1)
+    else:
+        from . import keccak_air
+        chips.append(keccak_air.byte_chip())
+        prep["Byte"] = keccak_air.byte_prep()
+        mults = np.concatenate([byte_counts.reshape(-1, 1), np.asarray(real["byte_mults"], dtype=np.uint64)], axis=1)
+        traces["Byte"] = (mults % np.uint64(P)).astype(np.uint32)
+        chips.extend(real["chips"])
+        traces.update(real["traces"])
     if counter_specs:
         n = 1 << counter_specs[0].log_height
         chips.append(_program_chip())
@@ -314,6 +325,31 @@ def keccak_case(log_cpu: int = 20, log_keccak: int | None = None, seed: int = 0x
              tune_wide("SyscallInstrs", h - 8, 97, 6), tune_wide("SyscallCore", h - 8, 39, 3),
              tune_wide("KeccakSponge", lk, 4259, 40)]
     return build_case(wides, seed=seed, **kw)
+
+
+def keccak_real_case(blocks: np.ndarray, keccak_trace: np.ndarray | None, log_cpu: int = 20, seed: int = 0xC0FFEE, **kw) -> ShardCase:
+    """S2 'keccak-2^20' with the REAL KeccakSponge chip: the reference's 3531-column layout and its restated
+    `Air::eval` (ziren_b200/keccak_air.py: 358 lookups, degree 3) instead of the synthetic 4167-column stand-in of
+    keccak_case, next to the same synthetic core tables.  `blocks`: (n, 384) block records
+    (ziren_b200/keccak_sponge.py); `keccak_trace`: the chip's rows in canonical form as a row filler wrote them
+    (oracle in the tests, the CUDA kernel in bench.py), or None to leave the table out of `traces` (it is then handed to
+    the prover as event records).  The Byte multiplicities, one MemoryLocalPrecompile row per memory access and one
+    SyscallPrecompile row per event balance the chip's local lookups."""
+    from . import keccak_air
+    from . import keccak_sponge as ksp
+    h = log_cpu
+    wides = [tune_wide("Cpu", h, 119, 10, counter=True), tune_wide("AddSub", h - 1, 47, 4),
+             tune_wide("MemoryInstrs", h - 2, 115, 8), tune_wide("Bitwise", h - 2, 42, 4),
+             tune_wide("Global", h - 3, 115, 6, global_scope=True), tune_wide("MemoryLocal", h - 5, 100, 6),
+             tune_wide("SyscallInstrs", h - 8, 97, 6), tune_wide("SyscallCore", h - 8, 39, 3)]
+    mults, mem, sysc = keccak_air.receiver_tables(blocks)
+    real_traces = {"MemoryLocalPrecompile": keccak_air.pad_rows(mem), "SyscallPrecompile": keccak_air.pad_rows(sysc)}
+    if keccak_trace is not None:
+        assert keccak_trace.shape[1] == ksp.WIDTH and keccak_trace.shape[0] >= len(blocks) * ksp.NUM_ROUNDS
+        real_traces["KeccakSponge"] = keccak_trace
+    real = {"chips": [keccak_air.keccak_sponge_chip(), keccak_air.memory_local_chip(), keccak_air.syscall_precompile_chip()],
+            "traces": real_traces, "byte_mults": mults}
+    return build_case(wides, seed=seed, real=real, **kw)
 
 
 # recursion "compress" machine (BASELINE.json configs[4]); heights = shrink_shape of
