@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="keccak", choices=["keccak", "keccak-real", "core", "fibonacci", "compress"])
+    ap.add_argument("--workload", default="keccak-real", choices=["keccak", "keccak-real", "core", "fibonacci", "compress"])
     ap.add_argument("--log-cpu", type=int, default=20)
     ap.add_argument("--sample-log-cpu", type=int, default=None,
                     help="size of the CPU arm's shard (default: the bench configuration itself, capped at 2^20)")
@@ -335,23 +335,30 @@ def main():
     launches0 = prover.launch_count()
     ms_dev, proof = timed(dev_tr, my_steps, args.value_threads)
     launches = prover.launch_count() - launches0
-    timed(host_tr, max(args.warmup, args.e2e_threads), args.e2e_threads)      # warm the staging/pool paths of the e2e arm
-    ms_e2e, proof2 = timed(host_tr, my_steps, args.e2e_threads)
+    # e2e inputs.  keccak-real: what a caller of this library hands over - pinned EVENT RECORDS for the chip that has a row
+    # filler on the device (KeccakSponge: ZKB200_TRACE_EVENTS, its table is generated inside the commit) and pinned rows for
+    # every other table; the arm that uploads the chip's rows instead is timed as well and reported next to it.
+    e2e_in = gen_tr if real else host_tr
+    timed(e2e_in, max(args.warmup, args.e2e_threads), args.e2e_threads)      # warm the staging/pool paths of the e2e arm
+    ms_e2e, proof2 = timed(e2e_in, my_steps, args.e2e_threads)
     # one shard in flight: what the reference's own GPU options ask for (shard_batch_size = 1,
     # crates/stark/src/opts.rs:83-110) - upload, layout change, LDE and leaf hashing overlap INSIDE the shard
-    ms_e2e_1, proof3 = timed(host_tr, my_steps, 1)
-    ms_gen = ms_gen_1 = None
+    ms_e2e_1, proof3 = timed(e2e_in, my_steps, 1)
+    ms_up = ms_up_1 = None
     if real:
-        timed(gen_tr, max(args.warmup, args.e2e_threads), args.e2e_threads)
-        ms_gen, proof5 = timed(gen_tr, my_steps, args.e2e_threads)
-        ms_gen_1, proof6 = timed(gen_tr, my_steps, 1)
+        timed(host_tr, max(args.warmup, args.e2e_threads), args.e2e_threads)
+        ms_up, proof5 = timed(host_tr, my_steps, args.e2e_threads)
+        ms_up_1, proof6 = timed(host_tr, my_steps, 1)
         assert np.array_equal(proof, proof5) and np.array_equal(proof, proof6)
     clocks = sampler.stop()
     assert np.array_equal(proof, proof2) and np.array_equal(proof, proof3)
-    # pageable host memory (what RowMajorMatrix.values is, prover.rs:258-262): staged through the pinned ring
+    # pageable host memory (what RowMajorMatrix.values and the record's event vectors are, prover.rs:258-262): rows staged
+    # through the pinned ring, event records by one DMA
     ms_e2e_pageable = None
     if args.world == 1 and not args.no_pageable:
         pageable = {k: np.array(v.numpy(), copy=True) for k, v in host_tr.items()}
+        if real:
+            pageable["KeccakSponge"] = EventTrace(np.array(case.blocks, copy=True), log_hk, ksp.WIDTH)
         timed(pageable, 1, 1)
         ms_e2e_pageable, proof4 = timed(pageable, max(2, args.steps // 3), 1)
         assert np.array_equal(proof, proof4)
@@ -390,7 +397,9 @@ def main():
 
     roofline = roofline_other = cpu_base = None
     if args.rank == 0:
-        rl = stage_rooflines(shapes, stages or {})
+        k3_bytes = sum(8.0 * shapes[c.name][0] * (c.prep_width + c.main_width + 4 * c.perm_width_ef) + 32.0 * shapes[c.name][0]
+                       for c in case.machine.chips if c.name in shapes)
+        rl = stage_rooflines(shapes, stages or {}, k3_bytes=k3_bytes)
         ranked = sorted(rl.values(), key=lambda r: -r["ms"])
         if ranked:
             roofline, roofline_other = ranked[0], ranked[1:]
@@ -399,25 +408,27 @@ def main():
 
     if args.rank == 0:
         total_cycles = units_per_shard * (args.shards if args.shards else args.steps * args.gpus)
-        e2e_generated = None
+        e2e_uploaded = None
         if real:
-            e2e_generated = {"value": total_cycles / (ms_gen / 1e3), "unit": unit, "ms_per_step": ms_gen / max(my_steps, 1),
-                             "h2d_bytes_per_step": h2d_bytes_gen, "d2h_bytes_per_step": d2h_bytes, "host_threads_in_flight": args.e2e_threads,
-                             "one_shard_in_flight": {"value": total_cycles / (ms_gen_1 / 1e3), "ms_per_step": ms_gen_1 / max(my_steps, 1)},
-                             "what": "the KeccakSponge table is handed to zkb200_commit as pinned EVENT RECORDS (ZKB200_TRACE_EVENTS) and generated on "
-                                     "the device inside the commit (MachineAir::generate_trace, SURVEY.md section 8 row f3); every other table is "
-                                     "uploaded as pinned row-major rows; same proof, word for word, as the other arms"}
+            e2e_uploaded = {"value": total_cycles / (ms_up / 1e3), "unit": unit, "ms_per_step": ms_up / max(my_steps, 1),
+                            "h2d_bytes_per_step": h2d_bytes, "host_threads_in_flight": args.e2e_threads,
+                            "one_shard_in_flight": {"value": total_cycles / (ms_up_1 / 1e3), "ms_per_step": ms_up_1 / max(my_steps, 1)},
+                            "what": "the same proof with the KeccakSponge ROWS uploaded from pinned host memory (trace generation left on "
+                                    "the host, as the synthetic workload of earlier rounds had to)"}
         line = {"metric": metric, "value": total_cycles / (ms_dev / 1e3), "unit": unit, "n_gpus": args.gpus,
                 "steps": my_steps, "warmup": args.warmup, "ms_per_step": ms_dev / max(my_steps, 1), "higher_is_better": True,
                 "scaling": "strong" if args.shards else "weak", "vs_baseline": None, "dtype": "u32 (KoalaBear 31-bit prime field)", "data": "synthetic",
                 "config": cfg,
-                "e2e": {"value": total_cycles / (ms_e2e / 1e3), "unit": unit, "h2d_bytes_per_step": h2d_bytes,
+                "e2e": {"value": total_cycles / (ms_e2e / 1e3), "unit": unit, "h2d_bytes_per_step": h2d_bytes_gen if real else h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / max(my_steps, 1),
                         "host_threads_in_flight": args.e2e_threads,
+                        **({"inputs": "pinned host memory: EVENT RECORDS of the KeccakSponge chip (zkb200_keccak_block, ZKB200_TRACE_EVENTS: "
+                                      "MachineAir::generate_trace runs on the device inside zkb200_commit, SURVEY.md section 8 row f3) and "
+                                      "row-major rows of every other table; the proof is word for word the one of the other arms",
+                            "uploaded_keccak_rows": e2e_uploaded} if real else {}),
                         "one_shard_in_flight": {"value": total_cycles / (ms_e2e_1 / 1e3), "ms_per_step": ms_e2e_1 / max(my_steps, 1)},
                         "pageable_host_one_shard_in_flight": None if ms_e2e_pageable is None else
                         {"value": units_per_shard * max(2, args.steps // 3) / (ms_e2e_pageable / 1e3), "ms_per_step": ms_e2e_pageable / max(2, args.steps // 3)}},
-                "e2e_trace_generation_on_device": e2e_generated,
                 "verified": verified, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other": roofline_other,
                 "cpu_baseline": cpu_base,
                 "stage_ms": stages, "cells_per_sec": cells * (args.shards if args.shards else args.steps * args.gpus) / (ms_dev / 1e3)}
@@ -429,7 +440,7 @@ def main():
         dist.destroy_process_group()
 
 
-def stage_rooflines(trace_shapes, stages, log_blowup=1):
+def stage_rooflines(trace_shapes, stages, log_blowup=1, k3_bytes=None):
     """HBM rooflines of the two dominant kernel families from the per-stage CUDA-event times of a
     live profiled step (zkb200_set_profile): K2 = Merkle build of the main commit, K1 = coset LDE of
     the main commit.  Algorithmic bytes per SURVEY.md section 8d."""
@@ -460,6 +471,15 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1):
                     "traffic_source": "algorithmic bytes x the dram__bytes ratio of the ncu --set full capture under profiles/",
                     "ms": ms, "algorithmic_bytes": alg,
                     "share_of_step": ms / max(sum(stages.values()), 1e-9)}
+    if k3_bytes and stages.get("quotient"):
+        ms = stages["quotient"]
+        ach = k3_bytes / (ms / 1e3) / 1e9
+        out["k3_quotient"] = {"bound": "hbm", "kernel": "quotient_values: generated per-chip constraint kernels qk (NVRTC) + LogUp constraints",
+                              "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                              "ms": ms, "algorithmic_bytes": k3_bytes, "share_of_step": ms / max(sum(stages.values()), 1e-9),
+                              "note": "4*2n*(P+M+4E) + 16*2n bytes per chip (SURVEY.md section 8d); on the real KeccakSponge chip the kernel "
+                                      "executes 515 k warp instructions per row-warp (3 788 constraints = 66 k node evaluations, 357 lookups) and "
+                                      "is load-latency bound: issue slots 35 % busy, long_scoreboard 13 (profiles/r02_qk_keccak_ncu.txt)"}
     if "k1_lde" in out:
         # arithmetic floor of the coset LDE under the same instruction prices: per input element one inverse and two
         # forward transforms = 1.5 log2(n) butterflies (Shoup product 8.2 + add 2.95 + sub about 1.3 cycles) and three
