@@ -3,11 +3,16 @@
 namespace zkb {
 
 __global__ void __launch_bounds__(128) fri_fold_kernel(const u32* tw_lo, const u32* tw_hi, const u32* __restrict__ in, size_t m,
-                                                       unsigned log_m, Ef beta, Ef beta2, Fp neg_half, Fp half,
+                                                       unsigned log_m, Ef beta, Ef beta2, const u32* __restrict__ beta_dev, Fp neg_half, Fp half,
                                                        const u32* __restrict__ ro_next, u32* __restrict__ out) {
   const size_t hm = m >> 1;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= hm) return;
+  if (beta_dev) {            // beta sampled by the device-resident challenger (hash.cu)
+#pragma unroll
+    for (int c = 0; c < 4; c++) beta.c[c] = fp_raw(__ldg(beta_dev + c));
+    beta2 = beta * beta;
+  }
   Ef e0, e1;
 #pragma unroll
   for (int c = 0; c < 4; c++) {
@@ -34,7 +39,14 @@ __global__ void __launch_bounds__(128) fri_fold_kernel(const u32* tw_lo, const u
 void fri_fold(const NttTables& tb, const u32* in, size_t m, const Ef& beta, const u32* ro_next, u32* out, cudaStream_t s) {
   const size_t hm = m >> 1;
   Fp half = fp_halve(fp_one());
-  fri_fold_kernel<<<ceil_div(hm, 128), 128, 0, s>>>(tb.tw_lo, tb.tw_hi, in, m, log2_exact(m), beta, beta * beta, -half, half,
+  fri_fold_kernel<<<ceil_div(hm, 128), 128, 0, s>>>(tb.tw_lo, tb.tw_hi, in, m, log2_exact(m), beta, beta * beta, nullptr, -half, half,
+                                                    ro_next, out);
+  ZKB_CHECK_LAUNCH();
+}
+void fri_fold_dev_beta(const NttTables& tb, const u32* in, size_t m, const u32* beta_dev, const u32* ro_next, u32* out, cudaStream_t s) {
+  const size_t hm = m >> 1;
+  Fp half = fp_halve(fp_one());
+  fri_fold_kernel<<<ceil_div(hm, 128), 128, 0, s>>>(tb.tw_lo, tb.tw_hi, in, m, log2_exact(m), ef_zero(), ef_zero(), beta_dev, -half, half,
                                                     ro_next, out);
   ZKB_CHECK_LAUNCH();
 }

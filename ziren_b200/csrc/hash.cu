@@ -323,6 +323,54 @@ u32 grind_witness(const u32 st[16], unsigned n_in, unsigned bits, u32* scratch_d
   throw std::runtime_error("zkb200: proof-of-work witness not found");
 }
 
+// ---- device-resident challenger (FRI commit phase) ----------------------------------------------------
+__device__ void dch_duplexing(DevChallenger& c) {
+  Fp st[16];
+  for (int i = 0; i < 16; i++) st[i] = fp_raw(i < (int)c.n_in ? c.in_buf[i & 7] : c.state[i]);
+  c.n_in = 0;
+  p2_permute_dev(st);
+  for (int i = 0; i < 16; i++) c.state[i] = st[i].v;
+  for (int i = 0; i < 8; i++) c.out_buf[i] = st[i].v;
+  c.n_out = 8;
+}
+__device__ void dch_observe(DevChallenger& c, u32 v) {
+  c.n_out = 0;
+  c.in_buf[c.n_in++] = v;
+  if (c.n_in == 8) dch_duplexing(c);
+}
+__device__ u32 dch_sample(DevChallenger& c) {
+  if (c.n_in != 0 || c.n_out == 0) dch_duplexing(c);
+  return c.out_buf[--c.n_out];
+}
+__global__ void challenger_set_kernel(DevChallenger* dst, DevChallenger v) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *dst = v;
+}
+__global__ void challenger_observe_sample_kernel(DevChallenger* ch, const u32* __restrict__ root, u32* __restrict__ beta) {
+  if (blockIdx.x || threadIdx.x) return;
+  DevChallenger c = *ch;
+  for (int i = 0; i < 8; i++) dch_observe(c, root[i]);
+  for (int i = 0; i < 4; i++) beta[i] = dch_sample(c);
+  *ch = c;
+}
+void challenger_to_device(const Challenger& ch, DevChallenger* dst, cudaStream_t s) {
+  DevChallenger v;
+  for (int i = 0; i < 16; i++) v.state[i] = ch.state[i].v;
+  for (int i = 0; i < 8; i++) { v.in_buf[i] = i < (int)ch.n_in ? ch.in_buf[i].v : 0; v.out_buf[i] = i < (int)ch.n_out ? ch.out_buf[i].v : 0; }
+  v.n_in = ch.n_in; v.n_out = ch.n_out;
+  challenger_set_kernel<<<1, 32, 0, s>>>(dst, v);
+  ZKB_CHECK_LAUNCH();
+}
+void challenger_observe_digest_sample_ext(DevChallenger* ch, const u32* root_dev, u32* beta_dev, cudaStream_t s) {
+  challenger_observe_sample_kernel<<<1, 32, 0, s>>>(ch, root_dev, beta_dev);
+  ZKB_CHECK_LAUNCH();
+}
+void Challenger::load_device_image(const DevChallenger& d) {
+  if (d.n_in >= 8 || d.n_out > 8) throw std::runtime_error("zkb200: malformed device challenger state");
+  for (int i = 0; i < 16; i++) state[i] = fp_raw(d.state[i]);
+  n_in = d.n_in; n_out = d.n_out;
+  for (int i = 0; i < 8; i++) { in_buf[i] = fp_raw(d.in_buf[i]); out_buf[i] = fp_raw(d.out_buf[i]); }
+}
+
 // ---- host challenger ------------------------------------------------------------------------------
 void Challenger::duplexing() {
   for (unsigned i = 0; i < n_in; i++) state[i] = in_buf[i];

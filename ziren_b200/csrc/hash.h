@@ -46,6 +46,16 @@ void permute_batch(u32* states, size_t n, cudaStream_t s);   // n x 16 row-major
 // st: sponge state (Montgomery) with the pending inputs already written to st[0..n_in).
 u32 grind_witness(const u32 st[16], unsigned n_in, unsigned bits, u32* scratch_dev, cudaStream_t s);
 
+// The same duplex challenger RESIDENT ON THE DEVICE for the FRI commit phase ([P3-upstream] fri::prover::commit_phase:
+// observe the layer's commitment, sample beta, fold; structure pinned by crates/recursion/circuit/src/fri.rs:247-361):
+// the transcript of the ~20 layers advances in one-thread kernels between the tree and fold kernels, so the host
+// enqueues the whole phase without a round trip per layer and reads roots, final polynomial and challenger back once.
+struct DevChallenger { u32 state[16]; u32 in_buf[8]; u32 out_buf[8]; u32 n_in, n_out; };     // Montgomery
+// dst <- the host challenger's image (passed by value: no host-to-device copy on a compute lane)
+void challenger_to_device(const struct Challenger& ch, DevChallenger* dst, cudaStream_t s);
+// observe the 8-word digest at root_dev (Montgomery), then sample an extension element into beta_dev[4]
+void challenger_observe_digest_sample_ext(DevChallenger* ch, const u32* root_dev, u32* beta_dev, cudaStream_t s);
+
 // DuplexChallenger<KoalaBear, Poseidon2, 16, 8> on the host (Montgomery residues internally).
 struct Challenger {
   Fp state[16];
@@ -64,6 +74,7 @@ struct Challenger {
   // 34-word canonical image: state[16], n_in, in[8], n_out, out[8]
   void load(const u32* w);
   void store(u32* w) const;
+  void load_device_image(const DevChallenger& d);     // after the FRI commit phase ran on the device
 };
 
 }  // namespace zkb

@@ -849,30 +849,45 @@ std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& sh, u32* challenger3
     DevBuf cur = std::move(ro[log_gmax]);
     size_t m = (size_t)1 << log_gmax;
     const size_t blowup = (size_t)1 << lb;
+    // The transcript of the commit phase runs ON THE DEVICE (hash.h, DevChallenger): per layer a one-thread kernel
+    // observes the layer's root and samples beta where the fold kernel reads it, so the ~20 layers are enqueued
+    // back to back and the host reads the roots, the final polynomial and the challenger once (it used to wait
+    // for a 32-byte copy per layer).  tr: [0, 64) challenger image, then 8 words of root and 4 of beta per layer,
+    // then the final evaluations.
+    const size_t nlayers = log_gmax > lb ? log_gmax - lb : 0;
+    const size_t tr_roots = 64, tr_final = tr_roots + 12 * nlayers, tr_words = tr_final + 4 * blowup;
+    if (tr_words * sizeof(u32) > (1 << 16)) throw std::runtime_error("zkb200: FRI transcript exceeds the lane's scratch");
+    DevBuf tr(tr_words, s);
+    DevChallenger* dch = reinterpret_cast<DevChallenger*>(tr.p);
+    static_assert(sizeof(DevChallenger) <= 64 * sizeof(u32), "challenger image fits its slot");
+    challenger_to_device(ch, dch, s);
+    size_t li = 0;
     while (m > blowup) {
       FriLayer FL;
       FL.m = m;
-      fri_commit_layer(cur.p, m, FL.tree, L.d_small, s);
-      ZKB_CUDA(cudaMemcpyAsync(L.h_small, L.d_small, 32, cudaMemcpyDeviceToHost, s));
-      ZKB_CUDA(cudaStreamSynchronize(s));
-      memcpy(FL.root, L.h_small, 32);
-      ch.observe_digest(FL.root);
-      const Ef beta = ch.sample_ext();
+      u32* root_dev = tr.p + tr_roots + 12 * li;
+      fri_commit_layer(cur.p, m, FL.tree, root_dev, s);
+      challenger_observe_digest_sample_ext(dch, root_dev, root_dev + 8, s);
       const unsigned lnext = log2_exact(m) - 1;
       DevBuf next(4 * (m >> 1), s);
-      fri_fold(ctx.tables, cur.p, m, beta, ro[lnext].p, next.p, s);
+      fri_fold_dev_beta(ctx.tables, cur.p, m, root_dev + 8, ro[lnext].p, next.p, s);
       FL.folded = std::move(cur);
       cur = std::move(next);
       fri_layers.push_back(std::move(FL));
       m >>= 1;
+      li++;
     }
     // `cur` holds blowup evaluations of a constant polynomial
-    ZKB_CUDA(cudaMemcpyAsync(L.h_small, cur.p, 4 * m * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    ZKB_CUDA(cudaMemcpyAsync(tr.p + tr_final, cur.p, 4 * m * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+    ZKB_CUDA(cudaMemcpyAsync(L.h_small, tr.p, tr_words * sizeof(u32), cudaMemcpyDeviceToHost, s));
     ZKB_CUDA(cudaStreamSynchronize(s));
-    for (int c = 0; c < 4; c++) final_poly.c[c] = fp_raw(L.h_small[c * m]);
+    ch.load_device_image(*reinterpret_cast<const DevChallenger*>(L.h_small));
+    for (size_t l = 0; l < fri_layers.size(); l++) memcpy(fri_layers[l].root, L.h_small + tr_roots + 12 * l, 32);
+    const u32* fin = L.h_small + tr_final;
+    for (int c = 0; c < 4; c++) final_poly.c[c] = fp_raw(fin[c * m]);
     for (size_t i = 1; i < m; i++)
       for (int c = 0; c < 4; c++)
-        if (L.h_small[c * m + i] != final_poly.c[c].v) throw std::runtime_error("zkb200: FRI final polynomial is not constant (unsatisfied constraints?)");
+        if (fin[c * m + i] != final_poly.c[c].v) throw std::runtime_error("zkb200: FRI final polynomial is not constant (unsatisfied constraints?)");
   }
   ch.observe_ext(final_poly);
 
