@@ -17,6 +17,7 @@
 pub mod export;
 pub mod proof;
 pub mod sys;
+pub mod tracegen;
 
 use std::ffi::{CStr, CString};
 use std::ptr::null_mut;
@@ -117,6 +118,29 @@ fn challenger_from_words(c: &mut <SC as StarkGenericConfig>::Challenger, w: &[u3
     c.output_buffer = (0..w[25] as usize).map(|i| F::from_canonical_u32(w[26 + i])).collect();
 }
 
+/// What the device-side trace generation needs from a record; `ExecutionRecord` (the core machine) provides it, the
+/// recursion records do not (their tables are uploaded as rows).
+pub trait DeviceTraceEvents {
+    fn keccak_sponge_blocks(&self) -> Option<Vec<tracegen::KeccakBlock>> { None }
+    fn fixed_log2_rows_of(&self, _chip: &str) -> Option<usize> { None }
+}
+impl DeviceTraceEvents for zkm_core_executor::ExecutionRecord {
+    fn keccak_sponge_blocks(&self) -> Option<Vec<tracegen::KeccakBlock>> {
+        let b = tracegen::flatten_keccak_sponge_events(self);
+        if b.is_empty() { None } else { Some(b) }
+    }
+    fn fixed_log2_rows_of(&self, chip: &str) -> Option<usize> {
+        self.shape.as_ref().and_then(|s| s.inner.get(chip).copied())
+    }
+}
+impl<A: MachineAir<F>> B200Prover<A>
+where
+    A::Record: DeviceTraceEvents,
+{
+    fn keccak_blocks_of(&self, record: &A::Record) -> Option<Vec<tracegen::KeccakBlock>> { record.keccak_sponge_blocks() }
+    fn fixed_log2_rows(&self, record: &A::Record, chip: &str) -> Option<usize> { record.fixed_log2_rows_of(chip) }
+}
+
 impl<A> MachineProver<SC, A> for B200Prover<A>
 where
     A: MachineAir<F> + Air<SymbolicAirBuilder<F>> + Send + Sync + 'static,
@@ -171,7 +195,21 @@ where
         let _span = tracing::debug_span!("commit to main traces (b200)").entered();
         let names: Vec<CString> = traces.iter().map(|(n, _)| CString::new(n.as_str()).unwrap()).collect();
         let mats: Vec<&RowMajorMatrix<F>> = traces.iter().map(|(_, m)| m).collect();
-        let t = marshal(&names, &mats);
+        let mut t = marshal(&names, &mats);
+        // Trace generation on the device (tracegen.rs): a core-machine caller whose `generate_traces` left the
+        // KeccakSponge table out as an EMPTY matrix of the right width hands its event records over here, and
+        // libzkb200's row filler writes the table inside the commit (ZKB200_TRACE_EVENTS).
+        let keccak_blocks = self.keccak_blocks_of(record);
+        if let Some(blocks) = keccak_blocks.as_ref() {
+            if let Some(i) = traces.iter().position(|(n, m)| n == "KeccakSponge" && m.values.is_empty()) {
+                let log_h = tracegen::keccak_sponge_log_height(blocks.len(), self.fixed_log2_rows(record, "KeccakSponge"));
+                t[i].data = blocks.as_ptr() as *const u32;
+                t[i].height = 1 << log_h;
+                t[i].width = tracegen::NUM_KECCAK_SPONGE_COLS;
+                t[i].flags = sys::ZKB200_TRACE_EVENTS;
+                t[i].n_events = blocks.len();
+            }
+        }
         let public_values = record.public_values::<F>();
         let pv: Vec<u32> = public_values.iter().map(|v| v.as_canonical_u32()).collect();
         let (mut commit, mut shard) = ([0u32; 8], null_mut());
