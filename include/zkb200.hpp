@@ -8,7 +8,8 @@
 //   trait item (prover.rs)                          here
 //   MachineProver::new(machine)            :43      B200Prover(device, descriptor)
 //   setup(&Program) / pk_to_device         :49-63   setup(preprocessed traces, pc_start, initial_global_cumulative_sum)
-//   generate_traces(record)                :70-108  generate_trace(chip, events, log_height)   (ALU / control-flow chips)
+//   generate_traces(record)                :70-108  generate_trace(chip, events, log_height)   (ALU / control-flow chips),
+//                                                   generate_keccak_sponge_trace(blocks, ...), events_trace(...) into commit()
 //   commit(record, traces)                 :258     commit(traces, public_values) -> ShardMainData
 //   open(pk, data, &mut challenger)        :298     open(pk, data, challenger) -> proof words (ZKPF)
 //   prove(pk, records, challenger, opts)   :660-693 prove(pk, records)
@@ -155,7 +156,21 @@ class B200Prover {
                       bool col_major = false) const {
     check(zkb200_generate_alu_trace(ctx_, chip.c_str(), events, n_events, log_height, out_dev, col_major ? 1 : 0));
   }
-  static int trace_width(const std::string& chip) { return zkb200_alu_trace_width(chip.c_str()); }
+  // generate_trace of the KeccakSponge chip from flattened block records (zkb200_keccak_block, 24 rows each)
+  void generate_keccak_sponge_trace(const zkb200_keccak_block* blocks, size_t n_blocks, unsigned log_height, uint32_t* out_dev,
+                                    bool col_major = false) const {
+    check(zkb200_generate_keccak_sponge_trace(ctx_, blocks, n_blocks, log_height, out_dev, col_major ? 1 : 0));
+  }
+  // a table handed to commit() as the chip's event records: the row filler runs inside the commit (ZKB200_TRACE_EVENTS)
+  static Trace events_trace(const std::string& chip, const void* events, size_t n_events, unsigned log_height, size_t width) {
+    Trace t;
+    t.name = chip; t.data = static_cast<const uint32_t*>(events); t.height = (size_t)1 << log_height; t.width = width;
+    t.flags = ZKB200_TRACE_EVENTS; t.n_events = n_events;
+    return t;
+  }
+  static int trace_width(const std::string& chip) {
+    return chip == "KeccakSponge" ? zkb200_keccak_sponge_trace_width() : zkb200_alu_trace_width(chip.c_str());
+  }
   void sync() const { check(zkb200_sync(ctx_)); }
   zkb200_ctx* handle() const { return ctx_; }
 

@@ -34,4 +34,8 @@ extern "C" {
     pub fn zkb200_open(ctx: *mut zkb200_ctx, pk: *const zkb200_pk, shard: *mut zkb200_shard, challenger: *mut u32,
                        proof_words: *mut *mut u32, n_words: *mut usize) -> c_int;
     pub fn zkb200_free(p: *mut c_void);
+    /// MachineAir::generate_trace of the KeccakSponge chip on the device (tracegen.rs: KeccakBlock = zkb200_keccak_block)
+    pub fn zkb200_keccak_sponge_trace_width() -> c_int;
+    pub fn zkb200_generate_keccak_sponge_trace(ctx: *mut zkb200_ctx, blocks: *const crate::tracegen::KeccakBlock, n_blocks: usize,
+                                               log_height: std::os::raw::c_uint, out: *mut u32, col_major: c_int) -> c_int;
 }
