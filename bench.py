@@ -72,6 +72,17 @@ def keccak_blocks(args, lc):
     return ksp.synthetic_blocks(max(1, rows // (24 * per)), per, seed=args.rank, shard=1)
 
 
+def host_mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
 def make_case(args, sample=False, keccak_rows="oracle"):
     synthetic.CONSTRAINTS_PER_GROUP = args.constraint_density
     w = args.workload
@@ -220,9 +231,11 @@ def main():
     if args.sample_log_cpu is None:
         # the CPU arm proves ONE shard of the same machine: the bench configuration itself for the synthetic workloads
         # (about 75 s per 2^20-cycle shard on 16 cores); the real KeccakSponge chip costs the scalar oracle about four
-        # times as much per cycle (3 788 constraints, 357 lookups per row) and tens of GB of host memory at 2^20 cycles,
-        # so its sample is the same machine at a quarter of the height (about 30 s)
-        args.sample_log_cpu = min(args.log_cpu, 18 if args.workload == "keccak-real" else 20)
+        # times as much per cycle (3 788 constraints, 357 lookups per row: about 80 s per 2^20-cycle shard on 16 cores) and
+        # about 35 GB of host memory: the bench configuration itself on a host with >= 96 GB available, else the same
+        # machine at a quarter of the height (about 20 s)
+        roomy = host_mem_available_gb() >= 96.0
+        args.sample_log_cpu = min(args.log_cpu, 20 if (args.workload != "keccak-real" or roomy) else 18)
 
     if args.impl == "reference":
         run_reference(args)

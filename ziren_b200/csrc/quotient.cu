@@ -22,7 +22,7 @@ constexpr int QCHUNK = 1024;   // 16 KB of bytecode per stage
 
 template <int NREGS>
 __global__ void __launch_bounds__(128) quotient_kernel(QuotArgs a) {
-  const QuotRow row = q_prologue(a);
+  const QuotRow row = q_prologue(a, blockIdx.x);
   const size_t t = row.t, tn = row.tn;
   const Fp is_first = row.is_first, is_last = row.is_last, is_trans = row.is_trans;
 
@@ -86,6 +86,29 @@ __global__ void alpha_pow_kernel(u32* out, u32 C, Ef alpha) {
   o[0] = p.c[0].v; o[1] = p.c[1].v; o[2] = p.c[2].v; o[3] = p.c[3].v;
 }
 
+// Rows whose constraints were evaluated by `groups` CTAs each (generated kernels of large chips): sum the partial
+// sums, divide by Z_H, split into chunks (q_epilogue).
+__global__ void __launch_bounds__(256) quotient_combine_kernel(QuotArgs a) {
+  const u32 lq = a.log_n + a.lqd;
+  const size_t Q = (size_t)1 << lq;
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= Q) return;
+  Ef acc = ef_zero();
+  for (u32 g = 0; g < a.groups; g++) {
+    Ef p;
+#pragma unroll
+    for (int c = 0; c < 4; c++) p.c[c] = fp_raw(a.partial[((size_t)g * 4 + c) * Q + t]);
+    acc += p;
+  }
+  QuotRow r;
+  r.t = t; r.tn = t; r.active = true;
+  r.i = bitrev32((u32)t, lq);
+  r.is_first = r.is_last = r.is_trans = fp_zero();
+  QuotArgs b = a;
+  b.groups = 1;
+  q_epilogue(b, r, acc);
+}
+
 void quotient_values(const MachineInfo& m, const ChipInfo& chip, const NttTables& tb, const QuotientInputs& in, u32* out,
                      cudaStream_t s) {
   QuotArgs a;
@@ -126,6 +149,7 @@ void quotient_values(const MachineInfo& m, const ChipInfo& chip, const NttTables
   ZKB_CHECK_LAUNCH();
   a.alpha_pow = apow.p;
   a.out = out;
+  a.groups = 1; a.partial = nullptr;
   const size_t Q = n << a.lqd;
   const unsigned grid = ceil_div(Q, 128);
   // generated straight-line kernel for this chip (NVRTC, quotient_codegen.cpp); the interpreter below is
@@ -134,8 +158,18 @@ void quotient_values(const MachineInfo& m, const ChipInfo& chip, const NttTables
     if (void* k = quotient_generated_kernel(chip)) {
       void* params[] = {&a};
       const unsigned bs = (unsigned)std::max(32, std::min(256, g_qk_block.load()));
-      ZKB_CUDA(cudaLaunchKernel((const void*)k, dim3(ceil_div(Q, bs)), dim3(bs), params, 0, s));
+      // large chips: `groups` CTAs per row tile, each a slice of the constraints (quotient_codegen.cpp); the tile's
+      // CTAs are neighbours in launch order, so the columns one slice loaded are in L2 when the next slice wants them
+      const unsigned groups = quotient_codegen_groups(chip);
+      DevBuf partial(groups > 1 ? (size_t)groups * 4 * Q : 0, s);
+      a.groups = groups; a.partial = partial.p;
+      const dim3 grid = groups > 1 ? dim3(groups, ceil_div(Q, bs)) : dim3(ceil_div(Q, bs));
+      ZKB_CUDA(cudaLaunchKernel((const void*)k, grid, dim3(bs), params, 0, s));
       ZKB_CHECK_LAUNCH();
+      if (groups > 1) {
+        quotient_combine_kernel<<<ceil_div(Q, 256), 256, 0, s>>>(a);
+        ZKB_CHECK_LAUNCH();
+      }
       g_quotient_generated_launches++;
       return;
     }

@@ -18,6 +18,9 @@ std::string quotient_kernel_source(const ChipInfo& chip);
 // memoised per source text for the life of the process.
 void* quotient_generated_kernel(const ChipInfo& chip);
 const char* quotient_codegen_last_error();
+// How many CTAs share a row tile in the chip's generated kernel (1: the whole constraint set in one CTA).  Pure
+// function of the chip, the same number the generator wrote the kernel for.
+unsigned quotient_codegen_groups(const ChipInfo& chip);
 // NVRTC only (no device needed): size of the chip's sm_100a cubin, 0 on failure.  Used by the CPU tests.
 size_t quotient_codegen_compile_only(const ChipInfo& chip);
 

@@ -31,6 +31,11 @@ struct QuotArgs {
   u32 zh[16], inv_zh[16];    // Z_H on the coset takes 2^lqd values
   u32 gen, ginv;             // GENERATOR, g_n^-1 (Montgomery)
   u32* out;
+  // generated kernels of large chips run as `groups` CTAs per row tile (blockIdx.x = group, blockIdx.y = tile), each
+  // evaluating a slice of the constraints; their partial sums ([group][4][Q] words) are combined by
+  // quotient_combine_kernel.  groups <= 1: one CTA per tile (blockIdx.x), results written directly.
+  u32 groups;
+  u32* partial;
 };
 
 struct QuotRow {
@@ -66,11 +71,11 @@ __device__ __forceinline__ Ef load_apow(const u32* ap, u32 k) {
 }
 
 // row indices and selectors at x = GENERATOR * w_Q^i   (crates/recursion/circuit/src/domain.rs:46-64)
-__device__ __forceinline__ QuotRow q_prologue(const QuotArgs& a) {
+__device__ __forceinline__ QuotRow q_prologue(const QuotArgs& a, size_t tile) {
   QuotRow r;
   const u32 lq = a.log_n + a.lqd;
   const size_t Q = (size_t)1 << lq;
-  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t t = tile * (size_t)blockDim.x + threadIdx.x;
   r.active = t < Q;
   if (!r.active) t = Q - 1;          // keep every thread in the barriers of the interpreter; result discarded
   r.t = t;
@@ -97,15 +102,21 @@ __device__ __forceinline__ void q_lookup(const QuotArgs& a, u32 lk, size_t t, Ef
   mult = l.is_send ? mu : -mu;
 }
 
-// permutation constraints (permutation.rs:205-347), then the global cumulative sum rows; k: index of the
-// next constraint's alpha power
-__device__ __forceinline__ void q_lookup_constraints(const QuotArgs& a, const QuotRow& r, Ef& acc, u32 k) {
+// permutation constraints (permutation.rs:205-347), then the global cumulative sum rows; k: index of the first
+// LogUp constraint's alpha power.  The batches [b0, b1) are evaluated here: a kernel split into groups hands every
+// group a range; the three running-sum constraints are linear in the batch entries, so every group adds its own
+// entries' share and the group that owns the last batch (`tail`) adds the phi terms and the global-sum rows.
+__device__ __forceinline__ void q_lookup_constraints(const QuotArgs& a, const QuotRow& r, Ef& acc, u32 k, u32 b0 = 0,
+                                                     u32 b1 = 0xffffffffu, bool tail = true) {
   const size_t t = r.t, tn = r.tn;
   if (a.ew) {
     const u32 nlk = a.lk_end - a.lk_begin;
-    u32 lk = 0;
+    const u32 k_sums = k + (a.ew - 1);
+    if (b1 > a.ew - 1) b1 = a.ew - 1;
+    u32 lk = b0 * a.batch;
+    k += b0;
     Ef sum_local = ef_zero(), sum_next = ef_zero();
-    for (u32 b = 0; b + 1 < a.ew; b++) {
+    for (u32 b = b0; b < b1; b++) {
       // product = prod_p rlc_p, numerator = sum_p mult_p prod_{q != p} rlc_q over the batch's lookups
       Ef product, numerator;
       if (a.batch == 1) {
@@ -137,12 +148,15 @@ __device__ __forceinline__ void q_lookup_constraints(const QuotArgs& a, const Qu
       sum_local += entry;
       sum_next += load_ef(a.perm, a.H, 4 * b, tn);
     }
-    Ef phi_local = load_ef(a.perm, a.H, 4 * (a.ew - 1), t), phi_next = load_ef(a.perm, a.H, 4 * (a.ew - 1), tn);
+    Ef phi_local = ef_zero(), phi_next = ef_zero();
+    if (tail) { phi_local = load_ef(a.perm, a.H, 4 * (a.ew - 1), t); phi_next = load_ef(a.perm, a.H, 4 * (a.ew - 1), tn); }
+    k = k_sums;
     acc += load_apow(a.alpha_pow, k++) * ((phi_local - sum_local) * r.is_first);
     acc += load_apow(a.alpha_pow, k++) * ((phi_next - phi_local - sum_next) * r.is_trans);
-    acc += load_apow(a.alpha_pow, k++) * ((phi_local - a.local_sum) * r.is_last);
+    if (tail) acc += load_apow(a.alpha_pow, k) * ((phi_local - a.local_sum) * r.is_last);
+    k++;
   }
-  if (a.global_scope) {
+  if (a.global_scope && tail) {
     for (int g = 0; g < 7; g++) {
       Fp mx = fp_raw(a.main_[(size_t)(a.main_width - 14 + g) * a.H + t]);
       Fp my = fp_raw(a.main_[(size_t)(a.main_width - 7 + g) * a.H + t]);
@@ -155,6 +169,14 @@ __device__ __forceinline__ void q_lookup_constraints(const QuotArgs& a, const Qu
 // quotient value and the split into 2^lqd chunks: chunk j = i mod 2^lqd, row k = i >> lqd
 // (quotient_domain.split_evals, prover.rs:477-488)
 __device__ __forceinline__ void q_epilogue(const QuotArgs& a, const QuotRow& r, const Ef& acc) {
+  if (a.groups > 1) {          // this group's share of the row's sum; quotient_combine_kernel finishes the row
+    const size_t Q = (size_t)1 << (a.log_n + a.lqd);
+    if (r.active) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) a.partial[((size_t)blockIdx.x * 4 + c) * Q + r.t] = acc.c[c].v;
+    }
+    return;
+  }
   Ef q = acc * fp_raw(a.inv_zh[r.i & ((1u << a.lqd) - 1)]);
   const size_t n = (size_t)1 << a.log_n;
   u32* o = a.out + (size_t)(r.i & ((1u << a.lqd) - 1)) * 4 * n + (r.i >> a.lqd);
