@@ -215,3 +215,20 @@ def test_zkpf_decoder_follows_the_reference_proof_types(oracle):
     rust = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shim", "src", "proof.rs")).read()
     for name in sum(want.values(), []) + ["commit_phase_commits", "query_proofs", "final_poly", "pow_witness", "sibling_value"]:
         assert name in rust, name
+
+
+def test_constraint_generator_groups_the_keccak_chip_by_shape(tmp_path, monkeypatch):
+    """K3 generator (csrc/quotient_codegen.cpp): the real KeccakSponge chip's 3 788 constraints become a few loops over
+    parameter tables (one per expression shape) instead of straight-line code per constraint; the kernel compiles with
+    NVRTC for sm_100a without a GPU."""
+    import ctypes as C
+    from ziren_b200 import _ffi, keccak_sponge, synthetic
+    monkeypatch.setenv("ZKB200_CODEGEN_DUMP", str(tmp_path))
+    m = synthetic.keccak_real_case(keccak_sponge.synthetic_blocks(1, 1), None, log_cpu=10).machine
+    desc = np.ascontiguousarray(m.descriptor(), dtype=np.uint32)
+    n = C.c_size_t()
+    assert _ffi.lib().zkb200_codegen_compile_check(desc.ctypes.data_as(_ffi.u32p), desc.size, C.byref(n)) == len(m.chips)
+    src = (tmp_path / "qk_KeccakSponge.cu").read_text()
+    n_shapes = src.count("static __device__ __noinline__ Ef shape")
+    assert 10 <= n_shapes <= 40 and src.count("static __device__ __noinline__ Ef seg") <= 3
+    assert "QK_TAB[" in src and src.count("\n") < 12000          # the per-constraint version was ~70 k lines

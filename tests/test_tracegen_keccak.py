@@ -256,6 +256,29 @@ def test_gpu_keccak_trace_errors(gpu):
 
 
 @pytest.mark.gpu
+def test_commit_from_events_errors(gpu, oracle):
+    """ZKB200_TRACE_EVENTS for a chip without a row filler, too many events, a wrong width: MachineProver::Error, no crash."""
+    from ziren_b200 import synthetic
+    from ziren_b200.prover import B200Prover, EventTrace, ZkbError
+    case = synthetic.mini_case()
+    prover = B200Prover(case.machine, device=0)
+    try:
+        inputs = {k: kb.to_monty(v) for k, v in case.traces.items()}
+        bad = dict(inputs)
+        bad["Cpu"] = EventTrace(np.zeros((4, 7), np.uint32), 6, case.traces["Cpu"].shape[1])
+        with pytest.raises(ZkbError, match="no row filler"):
+            prover.commit(bad, case.public_values)
+        bad = dict(inputs)
+        bad["AddSub"] = EventTrace(tg.synthetic_events("AddSub", 40), 5, case.traces["AddSub"].shape[1])
+        with pytest.raises(ZkbError, match="another width|more event rows"):
+            prover.commit(bad, case.public_values)
+        data = prover.commit(inputs, case.public_values)      # the context is still usable
+        data.free()
+    finally:
+        prover.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["rows_host", "events_host", "events_device"])
 def test_real_keccak_shard_proves_bit_exact(gpu, oracle, mode):
     """A shard with the REAL KeccakSponge chip: uploaded rows, or event records handed to zkb200_commit (the table is
