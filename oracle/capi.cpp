@@ -257,6 +257,13 @@ int zko_alu_trace(int chip, const u32* ev, size_t n, size_t height, u32* out) {
   }
 }
 
+// MulChip rows (tracegen.h): events n x 16 words (CompAluEvent), out height x 58 row-major canonical
+int zko_mul_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  try {
+    mul_trace(ev, n, height, out);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
 // trace generation of the KeccakSponge chip (tracegen_keccak.h): n_blocks records of KS_REC_WORDS words,
 // out height x 3531 row-major canonical
 int zko_keccak_sponge_width() { return KS_WIDTH; }

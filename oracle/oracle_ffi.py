@@ -91,6 +91,30 @@ def ref_alu_rows(chip, events):
     return out
 
 
+MUL_WIDTH, COMP_EVENT_WORDS = 58, 16
+
+
+def mul_trace(events, height):
+    """events: (n, 16) uint32 CompAluEvent records; (height, 58) canonical rows of the Mul chip."""
+    ev = _a(events).reshape(-1, COMP_EVENT_WORDS)
+    out = np.zeros((int(height), MUL_WIDTH), np.uint32)
+    if lib().zko_mul_trace(_p(ev), C.c_size_t(ev.shape[0]), C.c_size_t(int(height)), _p(out)):
+        raise RuntimeError(err())
+    return out
+
+
+def ref_mul_rows(events):
+    """Rows of the reference's own mul.hpp event_to_row (Montgomery words), or None without oracle/_ref."""
+    l = ref_core_lib()
+    if l is None or not hasattr(l, "ref_mul_event_to_rows"):
+        return None
+    ev = _a(events).reshape(-1, COMP_EVENT_WORDS)
+    out = np.zeros((ev.shape[0], MUL_WIDTH), np.uint32)
+    if l.ref_mul_event_to_rows(_p(ev), C.c_size_t(ev.shape[0]), _p(out)):
+        raise RuntimeError("reference row filler failed")
+    return out
+
+
 KS_WIDTH, KS_REC_WORDS = 3531, 384
 
 

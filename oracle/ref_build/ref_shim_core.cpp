@@ -16,6 +16,7 @@
 #include "jump.hpp"
 #include "mov_cond.hpp"
 #include "memory.hpp"
+#include "mul.hpp"
 
 using namespace zkm_core_machine_sys;
 
@@ -87,5 +88,19 @@ void ref_mem_write_cols(uint32_t value, uint32_t shard, uint32_t ts, uint32_t pr
   e.write._0 = MemoryWriteRecord{value, shard, ts, prev_value, prev_shard, prev_ts};
   memory::populate_read_write_v2<kb31_t>(c, e);
   std::memcpy(out13, &c, sizeof(c));
+}
+// MulChip rows of the reference's mul.hpp: events n x 16 words {shard, clk, pc, next_pc, opcode, hi, a, b, c,
+// hi_record{value, shard, timestamp, prev_value, prev_shard, prev_timestamp}, hi_record_is_real}; rows n x 58 Montgomery words
+unsigned ref_mul_num_cols() { return ncols<MulCols<kb31_t>>(); }
+int ref_mul_event_to_rows(const uint32_t* ev, size_t n, uint32_t* rows) {
+  const unsigned w = ref_mul_num_cols();
+  std::memset(rows, 0, n * w * sizeof(uint32_t));
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t* e = ev + 16 * i;
+    CompAluEvent c{e[0], e[1], e[2], e[3], (Opcode)e[4], e[5], e[6], e[7], e[8],
+                   MemoryWriteRecord{e[9], e[10], e[11], e[12], e[13], e[14]}, e[15] != 0};
+    mul::event_to_row<kb31_t>(c, *reinterpret_cast<MulCols<kb31_t>*>(rows + i * w));
+  }
+  return 0;
 }
 }

@@ -170,4 +170,26 @@ template <class T> struct MemoryReadCols { MemoryAccessCols<T> access; };
 template <class T> struct MemoryWriteCols { Word<T> prev_value; MemoryAccessCols<T> access; };
 template <class T> struct MemoryReadWriteCols { Word<T> prev_value; MemoryAccessCols<T> access; };
 
+// ---- Mul (crates/core/machine/include/mul.hpp) ----
+// crates/core/executor/src/events/instr.rs:47-73 (#[repr(C)])
+struct CompAluEvent {
+  uint32_t shard, clk, pc, next_pc;
+  Opcode opcode;
+  uint32_t hi, a, b, c;
+  MemoryWriteRecord hi_record;
+  bool hi_record_is_real;
+};
+// crates/core/machine/src/alu/mul/mod.rs:76-139 (MulCols)
+template <class T> struct MulCols {
+  T pc, next_pc;
+  Word<T> hi, a, b, c;
+  T carry[PRODUCT_SIZE];
+  T product[PRODUCT_SIZE];
+  T b_msb, c_msb, b_sign_extend, c_sign_extend;
+  T is_mul, is_mult, is_multu, is_real;
+  MemoryReadWriteCols<T> op_hi_access;
+  T hi_record_is_real;
+  T shard, clk;
+};
+
 }  // namespace zkm_core_machine_sys

@@ -225,4 +225,60 @@ static inline void alu_trace(int chip, const AluEvent* ev, size_t n, size_t heig
   }
 }
 
+// ---- Mul (crates/core/machine/src/alu/mul/mod.rs:235-336; C++ twin include/mul.hpp) ---------------------------------
+// CompAluEvent (crates/core/executor/src/events/instr.rs:47-73) as 16 words: shard, clk, pc, next_pc, opcode, hi, a, b, c,
+// hi_record {value, shard, timestamp, prev_value, prev_shard, prev_timestamp}, hi_record_is_real.
+// MulCols (58): pc, next_pc, hi[4], a[4], b[4], c[4], carry[8], product[8], b_msb, c_msb, b_sign_extend, c_sign_extend, is_mul,
+// is_mult, is_multu, is_real, op_hi_access {prev_value[4], value[4], prev_shard, prev_clk, compare_clk, diff_16bit_limb,
+// diff_8bit_limb}, hi_record_is_real, shard, clk.  Padding rows are zero (mod.rs:165-193).
+enum { K_MUL = 2, K_MULT = 3, K_MULTU = 4, MUL_WIDTH = 58, COMP_EVENT_WORDS = 16 };
+static inline void mul_row(const u32* e, u32* row) {
+  RowWriter w{row};
+  const u32 shard = e[0], clk = e[1], pc = e[2], next_pc = e[3], opcode = e[4] & 0xff, hi = e[5], a = e[6], b = e[7], c = e[8];
+  const bool hi_real = e[15] != 0;
+  w.put(pc); w.put(next_pc);
+  w.word(hi); w.word(a); w.word(b); w.word(c);
+  // byte vectors, sign-extended to eight bytes for MULT with a negative operand
+  std::vector<u32> bv, cv;
+  for (int i = 0; i < 4; i++) { bv.push_back((b >> (8 * i)) & 0xff); cv.push_back((c >> (8 * i)) & 0xff); }
+  const u32 b_msb = b >> 31, c_msb = c >> 31;
+  const bool b_ext = opcode == K_MULT && b_msb, c_ext = opcode == K_MULT && c_msb;
+  if (b_ext) bv.resize(8, 0xff);
+  if (c_ext) cv.resize(8, 0xff);
+  u32 product[8] = {0}, carry[8] = {0};
+  for (size_t i = 0; i < bv.size(); i++)
+    for (size_t j = 0; j < cv.size(); j++)
+      if (i + j < 8) product[i + j] += bv[i] * cv[j];
+  for (int i = 0; i < 8; i++) {
+    carry[i] = product[i] / 256;
+    product[i] %= 256;
+    if (i + 1 < 8) product[i + 1] += carry[i];
+  }
+  for (int i = 0; i < 8; i++) w.put(carry[i]);
+  for (int i = 0; i < 8; i++) w.put(product[i]);
+  w.put(b_msb); w.put(c_msb); w.flag(b_ext); w.flag(c_ext);
+  w.flag(opcode == K_MUL); w.flag(opcode == K_MULT); w.flag(opcode == K_MULTU); w.flag(true);
+  if (hi_real) {
+    // MemoryReadWriteCols::populate_write (memory/consistency/trace.rs:44-53): prev_value word, then the access columns
+    const u32 value = e[9], rshard = e[10], ts = e[11], prev_value = e[12], prev_shard = e[13], prev_ts = e[14];
+    w.word(prev_value);
+    w.word(value);
+    w.put(prev_shard); w.put(prev_ts);
+    const bool same = prev_shard == rshard;
+    w.flag(same);
+    const u32 d = (same ? ts - prev_ts : rshard - prev_shard) - 1u;
+    w.put(d & 0xffff); w.put((d >> 16) & 0xff);
+  } else for (int i = 0; i < 13; i++) w.put(0);
+  w.flag(hi_real);
+  w.put(hi_real ? shard : 0); w.put(hi_real ? clk : 0);
+  if (w.at != MUL_WIDTH) throw std::runtime_error("oracle: Mul row width mismatch");
+}
+static inline void mul_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  if (n > height) throw std::runtime_error("oracle: more events than rows");
+  for (size_t i = 0; i < height; i++) {
+    if (i < n) mul_row(ev + COMP_EVENT_WORDS * i, out + i * MUL_WIDTH);
+    else for (int k = 0; k < MUL_WIDTH; k++) out[i * MUL_WIDTH + k] = 0;
+  }
+}
+
 }  // namespace zko

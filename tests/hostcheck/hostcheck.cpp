@@ -69,7 +69,7 @@ int hostcheck_alu_rows(int chip, const uint32_t* ev, size_t n, size_t height, ui
   if (!init) { alu_build_inv255(inv255); init = true; }
   const int w = alu_width(chip);
   for (size_t i = 0; i < height; i++) {
-    if (i < n) fill_alu_row(chip, ev + 7 * i, out + i * w, inv255);
+    if (i < n) fill_alu_row(chip, ev + (size_t)alu_event_words(chip) * i, out + i * w, inv255);
     else fill_alu_padding(chip, out + i * w);
   }
   return 0;

@@ -337,8 +337,9 @@ int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* eve
       on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
     else cudaGetLastError();
     if (n_events && !on_device) {
-      staged = DevBuf(n_events * 7, s);
-      ZKB_CUDA(cudaMemcpyAsync(staged.p, events, n_events * 28, cudaMemcpyHostToDevice, s));
+      const size_t ew = (size_t)alu_event_words(id);
+      staged = DevBuf(n_events * ew, s);
+      ZKB_CUDA(cudaMemcpyAsync(staged.p, events, n_events * ew * sizeof(u32), cudaMemcpyHostToDevice, s));
       ev = staged.p;
     }
     alu_trace(id, ev, n_events, height, out, col_major != 0, s);

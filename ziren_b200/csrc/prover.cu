@@ -344,7 +344,7 @@ Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, co
 // ZKB200_TRACE_EVENTS: which row filler a chip has (csrc/tracegen.cu) and how long its event records are
 static size_t event_record_words(const std::string& chip) {
   if (chip == "KeccakSponge") return KS_REC_WORDS;
-  if (alu_chip_by_name(chip.c_str()) >= 0) return 7;
+  if (alu_chip_by_name(chip.c_str()) >= 0) return (size_t)alu_event_words(alu_chip_by_name(chip.c_str()));
   throw std::runtime_error("zkb200: commit: no row filler for chip " + chip + " (ZKB200_TRACE_EVENTS)");
 }
 static void generate_trace_colmajor(const std::string& chip, const u32* events_dev, size_t n_events, size_t height, u32* out,

@@ -23,15 +23,16 @@ __global__ void __launch_bounds__(TG_ROWS) alu_rows_kernel(const u32* __restrict
                                                            u32* __restrict__ out, int col_major) {
   constexpr int W = alu_width(CHIP);
   constexpr int WP = W | 1;
-  __shared__ u32 ev_s[TG_ROWS * 7];
+  constexpr int EW = alu_event_words(CHIP);
+  __shared__ u32 ev_s[TG_ROWS * EW];
   __shared__ u32 tile[TG_ROWS * WP];
   const size_t row0 = (size_t)blockIdx.x * TG_ROWS;
-  // the CTA's events are 7 * 128 consecutive words: coalesced load, then one record per thread
-  const size_t ev_words = row0 < n ? (n - row0 < TG_ROWS ? (n - row0) * 7 : (size_t)TG_ROWS * 7) : 0;
-  for (u32 i = threadIdx.x; i < ev_words; i += TG_ROWS) ev_s[i] = events[row0 * 7 + i];
+  // the CTA's events are EW * 128 consecutive words: coalesced load, then one record per thread
+  const size_t ev_words = row0 < n ? (n - row0 < TG_ROWS ? (n - row0) * EW : (size_t)TG_ROWS * EW) : 0;
+  for (u32 i = threadIdx.x; i < ev_words; i += TG_ROWS) ev_s[i] = events[row0 * EW + i];
   __syncthreads();
   u32* r = tile + threadIdx.x * WP;
-  if (row0 + threadIdx.x < n) fill_alu_row(CHIP, ev_s + 7 * threadIdx.x, r, d_inv255);
+  if (row0 + threadIdx.x < n) fill_alu_row(CHIP, ev_s + EW * threadIdx.x, r, d_inv255);
   else fill_alu_padding(CHIP, r);
   __syncthreads();
   const size_t rows = height - row0 < TG_ROWS ? height - row0 : TG_ROWS;
@@ -61,6 +62,7 @@ void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* ou
     case ALU_BRANCH: alu_rows_kernel<ALU_BRANCH><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     case ALU_JUMP: alu_rows_kernel<ALU_JUMP><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     case ALU_MOVCOND: alu_rows_kernel<ALU_MOVCOND><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_MUL: alu_rows_kernel<ALU_MUL><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     default: throw std::runtime_error("zkb200: alu_trace: unknown chip");
   }
   ZKB_CHECK_LAUNCH();
@@ -90,7 +92,7 @@ void keccak_sponge_trace(const u32* blocks_dev, size_t n_blocks, size_t height, 
 }
 
 int alu_chip_by_name(const char* name) {
-  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond"};
+  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond", "Mul"};
   for (int i = 0; i < ALU_NCHIPS; i++) if (!strcmp(name, names[i])) return i;
   return -1;
 }

@@ -12,7 +12,7 @@
 namespace zkb {
 
 enum AluChip : int { ALU_ADDSUB = 0, ALU_BITWISE = 1, ALU_LT = 2, ALU_SLL = 3, ALU_SR = 4, ALU_CLOCLZ = 5, ALU_BRANCH = 6, ALU_JUMP = 7,
-                     ALU_MOVCOND = 8, ALU_NCHIPS = 9 };
+                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_NCHIPS = 10 };
 // opcodes as numbered by crates/core/executor/src/opcode.rs:25-49 (#[repr(u8)])
 enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_ROR = 12, OP_SLT = 13, OP_SLTU = 14,
              OP_AND = 15, OP_OR = 16, OP_XOR = 17, OP_NOR = 18, OP_CLZ = 19, OP_CLO = 20, OP_BEQ = 21, OP_BGEZ = 22, OP_BGTZ = 23,
@@ -20,8 +20,10 @@ enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_RO
 
 KB_HD constexpr int alu_width(int chip) {
   return chip == ALU_ADDSUB ? 19 : chip == ALU_BITWISE ? 18 : chip == ALU_LT ? 32 : chip == ALU_SLL ? 44 : chip == ALU_SR ? 67
-       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : 32;
+       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : 32;
 }
+// 32-bit words per event record: seven for AluEvent / BranchEvent / JumpEvent / MovCondEvent, sixteen for CompAluEvent (Mul)
+KB_HD constexpr int alu_event_words(int chip) { return chip == ALU_MUL ? 16 : 7; }
 
 // AluEvent as laid out by #[repr(C)]: seven 32-bit words, the opcode in the low byte of word 2
 struct AluEv { u32 pc, next_pc, opcode, hi, a, b, c; };
@@ -235,6 +237,50 @@ KB_HD void fill_mov_cond(const u32* w, u32* r, const u32* inv255) {
   r[29] = tg_b(op == OP_MNE); r[30] = tg_b(op == OP_MEQ); r[31] = tg_b(op == OP_WSBH);
 }
 
+// MulChip::event_to_row, crates/core/machine/src/alu/mul/mod.rs:235-336 (C++ twin include/mul.hpp).  Event: CompAluEvent
+// (crates/core/executor/src/events/instr.rs:47-73) as 16 words {shard, clk, pc, next_pc, opcode, hi, a, b, c, hi_record{value,
+// shard, timestamp, prev_value, prev_shard, prev_timestamp}, hi_record_is_real}.  Columns (58): pc, next_pc, hi[4], a[4], b[4],
+// c[4], carry[8], product[8], b_msb, c_msb, b_sign_extend, c_sign_extend, is_mul, is_mult, is_multu, is_real, op_hi_access
+// {prev_value[4], value[4], prev_shard, prev_clk, compare_clk, diff_16bit_limb, diff_8bit_limb}, hi_record_is_real, shard, clk.
+// The operands are widened to 64 bits (sign-extended for MULT); byte k of the schoolbook product and the carry out of it
+// come from the column sums of the 8 x 8 byte products.
+constexpr int MUL_WIDTH = 58, COMP_EVENT_WORDS = 16;
+enum : u32 { OP_MUL = 2, OP_MULT = 3, OP_MULTU = 4 };
+KB_HD void fill_mul(const u32* e, u32* r) {
+  const u32 shard = e[0], clk = e[1], pc = e[2], next_pc = e[3], op = e[4] & 0xffu, hi = e[5], a = e[6], b = e[7], c = e[8];
+  const bool hi_real = e[15] != 0;
+  r[0] = tg_f(pc); r[1] = tg_f(next_pc);
+  tg_word(r + 2, hi); tg_word(r + 6, a); tg_word(r + 10, b); tg_word(r + 14, c);
+  const bool b_ext = op == OP_MULT && (b >> 31), c_ext = op == OP_MULT && (c >> 31);
+  const u64 bw = b_ext ? (u64)(int64_t)(int32_t)b : (u64)b, cw = c_ext ? (u64)(int64_t)(int32_t)c : (u64)c;
+  u32 carry = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    u32 sum = carry;
+#pragma unroll
+    for (int i = 0; i <= k; i++) sum += (u32)((bw >> (8 * i)) & 0xffu) * (u32)((cw >> (8 * (k - i))) & 0xffu);
+    carry = sum >> 8;
+    r[18 + k] = tg_f(carry);
+    r[26 + k] = tg_f(sum & 0xffu);
+  }
+  r[34] = tg_b(b >> 31); r[35] = tg_b(c >> 31); r[36] = tg_b(b_ext); r[37] = tg_b(c_ext);
+  r[38] = tg_b(op == OP_MUL); r[39] = tg_b(op == OP_MULT); r[40] = tg_b(op == OP_MULTU); r[41] = KB_ONE;
+  if (hi_real) {
+    const u32 value = e[9], rshard = e[10], ts = e[11], prev_value = e[12], prev_shard = e[13], prev_ts = e[14];
+    tg_word(r + 42, prev_value);
+    tg_word(r + 46, value);
+    r[50] = tg_f(prev_shard); r[51] = tg_f(prev_ts);
+    const bool same = prev_shard == rshard;
+    r[52] = tg_b(same);
+    const u32 d = (same ? ts - prev_ts : rshard - prev_shard) - 1u;
+    r[53] = tg_f(d & 0xffffu); r[54] = tg_f((d >> 16) & 0xffu);
+  } else {
+    for (int i = 42; i < 55; i++) r[i] = 0;
+  }
+  r[55] = tg_b(hi_real);
+  r[56] = hi_real ? tg_f(shard) : 0u; r[57] = hi_real ? tg_f(clk) : 0u;
+}
+
 // Rows past the last event (generate_trace of each chip): zeros, except the dummy rows that keep the
 // shift and count-leading chips' constraints satisfied (sll/mod.rs:160-173, sr/mod.rs:184-187,
 // clo_clz/mod.rs:150-163).
@@ -257,6 +303,7 @@ KB_HD void fill_alu_row(int chip, const u32* w, u32* r, const u32* inv255) {
     case ALU_CLOCLZ: fill_clo_clz(alu_event_from_words(w), r); break;
     case ALU_BRANCH: fill_branch(flow_event_from_words(w), r); break;
     case ALU_JUMP: fill_jump(flow_event_from_words(w), r); break;
+    case ALU_MUL: fill_mul(w, r); break;
     default: fill_mov_cond(w, r, inv255); break;
   }
 }

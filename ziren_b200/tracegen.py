@@ -29,6 +29,11 @@ ALU_CHIPS = {
     # MovCondEvent {pc, next_pc, opcode, a, b, c, prev_a} (instr.rs:287-302), crates/core/machine/src/misc/mov_cond/
     "MovCond": (32, ("MEQ", "MNE", "WSBH")),
 }
+# chips whose events are CompAluEvent records of sixteen words {shard, clk, pc, next_pc, opcode, hi, a, b, c, hi_record{value,
+# shard, timestamp, prev_value, prev_shard, prev_timestamp}, hi_record_is_real} (crates/core/executor/src/events/instr.rs:47-73)
+COMP_CHIPS = {"Mul": (58, ("MUL", "MULT", "MULTU"))}
+COMP_EVENT_WORDS = 16
+OPCODES.update({"MUL": 2, "MULT": 3, "MULTU": 4})
 FLOW_CHIPS = ("Branch", "Jump")
 EVENT_WORDS = 7          # AluEvent: pc, next_pc, opcode, hi, a, b, c;  Branch/JumpEvent: pc, next_pc, next_next_pc, opcode, a, b, c;
                          # MovCondEvent: pc, next_pc, opcode, a, b, c, prev_a
@@ -36,7 +41,11 @@ EVENT_BYTES = 28
 
 
 def width(chip: str) -> int:
-    return ALU_CHIPS[chip][0]
+    return (ALU_CHIPS.get(chip) or COMP_CHIPS[chip])[0]
+
+
+def event_words(chip: str) -> int:
+    return COMP_EVENT_WORDS if chip in COMP_CHIPS else EVENT_WORDS
 
 
 def padded_log_height(n_events: int, fixed_log2_rows: int | None = None) -> int:
@@ -176,4 +185,44 @@ def synthetic_events(chip: str, n: int, seed: int = 0, edges: bool = True) -> np
         lo2, hi2 = hi, min(n, hi + 256)
         ev[lo2:hi2, 6] = ev[lo2:hi2, 5] ^ (np.uint32(1) << rng.integers(0, 32, hi2 - lo2).astype(np.uint32))   # one bit apart
     ev[:, 4] = _alu_result(ev[:, 2], ev[:, 5], ev[:, 6])
+    return ev
+
+
+def synthetic_mul_events(n: int, seed: int = 0, edges: bool = True) -> np.ndarray:
+    """n well-formed CompAluEvent records of the Mul chip as (n, 16) uint32 words: MUL keeps the low word of b * c, MULT /
+    MULTU write the high word to HI (hi_record: a memory write at clk + 4 of this shard, previous access earlier in this
+    shard or in an earlier one)."""
+    rng = np.random.default_rng(0x3A1 + seed)
+    ev = np.zeros((n, COMP_EVENT_WORDS), np.uint32)
+    shard = 3
+    ev[:, 0] = shard
+    ev[:, 1] = (5 + 8 * np.arange(1, n + 1)).astype(np.uint32)
+    ev[:, 2] = rng.integers(0, kb.P - 16, n) & ~np.uint32(3)
+    ev[:, 3] = ev[:, 2] + 4
+    op = rng.choice([OPCODES[o] for o in COMP_CHIPS["Mul"][1]], n).astype(np.uint32)
+    b = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    c = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    if edges:
+        m = len(EDGE_OPERANDS)
+        k = min(n, m * m)
+        idx = np.arange(k)
+        b[:k], c[:k] = EDGE_OPERANDS[idx // m], EDGE_OPERANDS[idx % m]
+    signed = op == OPCODES["MULT"]
+    prod_u = b.astype(np.uint64) * c.astype(np.uint64)
+    prod_s = (b.astype(np.int32).astype(np.int64) * c.astype(np.int32).astype(np.int64)).astype(np.uint64)
+    prod = np.where(signed, prod_s, prod_u)
+    has_hi = op != OPCODES["MUL"]
+    ev[:, 4] = op
+    ev[:, 5] = np.where(has_hi, (prod >> np.uint64(32)).astype(np.uint32), 0)
+    ev[:, 6] = (prod & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    ev[:, 7], ev[:, 8] = b, c
+    earlier = rng.integers(0, 6, n) == 0
+    ev[:, 9] = ev[:, 5]
+    ev[:, 10] = shard
+    ev[:, 11] = ev[:, 1] + 4
+    ev[:, 12] = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    ev[:, 13] = np.where(earlier, rng.integers(1, shard, n), shard)
+    ev[:, 14] = np.where(earlier, rng.integers(0, 1 << 22, n), ev[:, 11] - rng.integers(1, 9, n)).astype(np.uint32)
+    ev[:, 15] = has_hi
+    ev[~has_hi, 9:15] = 0
     return ev
