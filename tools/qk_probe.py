@@ -18,6 +18,9 @@ from ziren_b200.prover import B200Prover  # noqa: E402
 
 log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+if len(sys.argv) > 3:       # threads per CTA of the generated kernel
+    from ziren_b200 import _ffi
+    _ffi.lib().zkb200_set_option(b"qk_block", int(sys.argv[3]))
 case = synthetic.keccak_real_case(ks.synthetic_blocks(1, 1), None, log_cpu=10)
 chip = case.machine.chip("KeccakSponge")
 prover = B200Prover(case.machine)
