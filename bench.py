@@ -495,8 +495,9 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1, k3_bytes=None):
                               "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                               "ms": ms, "algorithmic_bytes": k3_bytes, "share_of_step": ms / max(sum(stages.values()), 1e-9),
                               "note": "4*2n*(P+M+4E) + 16*2n bytes per chip (SURVEY.md section 8d); on the real KeccakSponge chip the kernel "
-                                      "executes 515 k warp instructions per row-warp (3 788 constraints = 66 k node evaluations, 357 lookups) and "
-                                      "is load-latency bound: issue slots 35 % busy, long_scoreboard 13 (profiles/r02_qk_keccak_ncu.txt)"}
+                                      "executes 471 k warp instructions per row-warp (3 788 constraints = 66 k node evaluations, 357 lookups): "
+                                      "issue slots 42 % busy, fma-heavy pipe 50 %, DRAM 3.5 x the algorithmic bytes because every constraint "
+                                      "family re-loads its columns (profiles/r02_qk_keccak_ncu.txt)"}
     if "k1_lde" in out:
         # arithmetic floor of the coset LDE under the same instruction prices: per input element one inverse and two
         # forward transforms = 1.5 log2(n) butterflies (Shoup product 8.2 + add 2.95 + sub about 1.3 cycles) and three
