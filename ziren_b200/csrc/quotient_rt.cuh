@@ -166,6 +166,31 @@ __device__ __forceinline__ void q_lookup_constraints(const QuotArgs& a, const Qu
   }
 }
 
+// What is left of the LogUp constraints once the batch constraints have been evaluated by GENERATED code
+// (quotient_codegen.cpp, lookup shapes): the three running-sum constraints and the global cumulative sum rows.
+// sum_local / sum_next: the sums of the batch entries on the local and the next row; k: alpha index of the first LogUp
+// constraint.
+struct QLookupSums { Ef acc, sum_local, sum_next; };
+__device__ __forceinline__ void q_lookup_tail(const QuotArgs& a, const QuotRow& r, Ef& acc, u32 k, const Ef& sum_local,
+                                              const Ef& sum_next) {
+  const size_t t = r.t, tn = r.tn;
+  if (a.ew) {
+    k += a.ew - 1;
+    const Ef phi_local = load_ef(a.perm, a.H, 4 * (a.ew - 1), t), phi_next = load_ef(a.perm, a.H, 4 * (a.ew - 1), tn);
+    acc += load_apow(a.alpha_pow, k++) * ((phi_local - sum_local) * r.is_first);
+    acc += load_apow(a.alpha_pow, k++) * ((phi_next - phi_local - sum_next) * r.is_trans);
+    acc += load_apow(a.alpha_pow, k++) * ((phi_local - a.local_sum) * r.is_last);
+  }
+  if (a.global_scope) {
+    for (int g = 0; g < 7; g++) {
+      Fp mx = fp_raw(a.main_[(size_t)(a.main_width - 14 + g) * a.H + t]);
+      Fp my = fp_raw(a.main_[(size_t)(a.main_width - 7 + g) * a.H + t]);
+      acc += load_apow(a.alpha_pow, k++) * (r.is_last * (mx - fp_raw(a.gsum[g])));
+      acc += load_apow(a.alpha_pow, k++) * (r.is_last * (my - fp_raw(a.gsum[7 + g])));
+    }
+  }
+}
+
 // quotient value and the split into 2^lqd chunks: chunk j = i mod 2^lqd, row k = i >> lqd
 // (quotient_domain.split_evals, prover.rs:477-488)
 __device__ __forceinline__ void q_epilogue(const QuotArgs& a, const QuotRow& r, const Ef& acc) {
