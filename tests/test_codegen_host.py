@@ -1,0 +1,156 @@
+"""The K3 constraint kernels the generator writes (ziren_b200/csrc/quotient_codegen.cpp: constraint shapes, parameter tables,
+LogUp batch shapes, on top of the run-time header quotient_rt.cuh), compiled FOR THE HOST behind a few shims
+(tests/hostcheck/qk_host.cpp) and run row by row against the oracle's quotient (oracle/air.h quotient_values) - the same
+comparison tests/test_gpu_parity.py::test_quotient_matches_oracle makes on a GPU, here for the generated SOURCE without one.
+Chips: the real KeccakSponge chip (3 788 constraints, 357 lookups, 19 + 8 shapes) and the chips of a small machine with
+preprocessed columns, public values, the global-scope rows and lookup batches of one and two."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ziren_b200 import _ffi
+from ziren_b200 import field as kb
+from ziren_b200.air import SCOPE_LOCAL
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+P = kb.P
+W4 = 3          # EF = F[x] / (x^4 - 3)
+
+
+def ef_mul(a, b):
+    r = [0, 0, 0, 0, 0, 0, 0]
+    for i in range(4):
+        for j in range(4):
+            r[i + j] += a[i] * b[j]
+    return [(r[k] + W4 * (r[k + 4] if k + 4 < 7 else 0)) % P for k in range(4)]
+
+
+def ef_add(a, b):
+    return [(x + y) % P for x, y in zip(a, b)]
+
+
+def ef_scale(a, s):
+    return [(x * s) % P for x in a]
+
+
+def two_adic_generator(bits):
+    g = pow(3, 127, P)
+    for _ in range(bits, 24):
+        g = g * g % P
+    return g
+
+
+def monty(x):
+    return kb.to_monty(np.asarray(x, dtype=np.uint32).reshape(-1)).reshape(np.asarray(x).shape)
+
+
+@pytest.fixture(scope="module")
+def tw_tables():
+    w = two_adic_generator(24)
+    lo = np.empty(4096, np.uint32)
+    hi = np.empty(4096, np.uint32)
+    x, w4096 = 1, pow(w, 4096, P)
+    y = 1
+    for e in range(4096):
+        lo[e], hi[e] = x, y
+        x, y = x * w % P, y * w4096 % P
+    return monty(lo), monty(hi)
+
+
+def _build_host_kernel(machine, chip_name, tmp):
+    desc = np.ascontiguousarray(machine.descriptor(), dtype=np.uint32)
+    n = C.c_size_t()
+    os.environ["ZKB200_CODEGEN_DUMP"] = str(tmp)
+    try:
+        assert _ffi.lib().zkb200_codegen_compile_check(desc.ctypes.data_as(_ffi.u32p), desc.size, C.byref(n)) == len(machine.chips)
+    finally:
+        del os.environ["ZKB200_CODEGEN_DUMP"]
+    src = os.path.join(str(tmp), f"qk_{chip_name}.cu")
+    so = os.path.join(str(tmp), f"qk_{chip_name}.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-I" + os.path.join(ROOT, "ziren_b200", "csrc"),
+                           f'-DQK_SOURCE="{src}"', os.path.join(HERE, "hostcheck", "qk_host.cpp"), "-o", so])
+    return C.CDLL(so)
+
+
+def _check_chip(oracle, om, machine, name, prep, trace, public_values, tw_tables, tmp, seed=4):
+    chip = machine.chip(name)
+    lib = _build_host_kernel(machine, name, tmp)
+    rng = np.random.default_rng(seed)
+    pa, pb, al = ([int(v) for v in kb.random_elements(rng, 4)] for _ in range(3))
+    n = trace.shape[0]
+    log_n, lqd = int(np.log2(n)), chip.log_quotient_degree
+    perm, lsum = om.permutation_trace(name, prep, trace, pa, pb)
+    gsum = trace[-1, -14:] if chip.global_scope else kb.SEPTIC_DIGEST_ZERO
+    main_lde = oracle.coset_lde(trace)
+    perm_lde = oracle.coset_lde(perm) if perm.shape[1] else np.zeros((2 * n, 0), np.uint32)
+    prep_lde = oracle.coset_lde(prep) if prep is not None else None
+    want = om.quotient_values(name, log_n, prep_lde, main_lde, perm_lde, pa, pb, lsum, gsum, al, public_values)
+    # what quotient.cu / lookup_coefficients prepare on the device, here in Python
+    lookups = [l for l in chip.builder.sends + chip.builder.receives if l["scope"] == SCOPE_LOCAL]
+    bpow = [[1, 0, 0, 0]]
+    for _ in range(16):
+        bpow.append(ef_mul(bpow[-1], pb))
+    K, E = [], []
+    for l in lookups:
+        k = ef_add(pa, [l["kind"], 0, 0, 0])
+        for j, (const, terms) in enumerate(l["values"], start=1):
+            k = ef_add(k, ef_scale(bpow[j], const))
+            for _is_main, _col, w in terms:
+                E.append(ef_scale(bpow[j], w))
+        K.append(k)
+    ncons = chip.num_constraints
+    apow = [[1, 0, 0, 0]]
+    for _ in range(ncons - 1):
+        apow.append(ef_mul(apow[-1], al))
+    apow = apow[::-1]                                    # alpha_pow[k] = alpha^(C-1-k)
+    gn = pow(3, n, P)
+    wq = two_adic_generator(lqd)
+    zh = [(gn * pow(wq, v, P) - 1) % P for v in range(1 << lqd)]
+    inv_zh = [pow(z, P - 2, P) for z in zh]
+    arr = lambda x, shape=None: np.ascontiguousarray(monty(np.array(x, dtype=np.uint32).reshape(shape or -1)))
+    colmajor = lambda a: np.ascontiguousarray(a.T)
+    m_prep = monty(colmajor(prep_lde)) if prep_lde is not None else np.zeros(1, np.uint32)
+    m_main, m_perm = monty(colmajor(main_lde)), (monty(colmajor(perm_lde)) if perm_lde.size else np.zeros(1, np.uint32))
+    a_apow, a_K, a_E = arr(apow, (-1, 4)), arr(K or [[0] * 4], (-1, 4)), arr(E or [[0] * 4], (-1, 4))
+    a_pub = arr(np.asarray(public_values, dtype=np.uint64) % P)
+    a_lsum, a_gsum, a_zh, a_izh = arr(lsum), arr(gsum), arr(zh), arr(inv_zh)
+    tw_lo, tw_hi = tw_tables
+    nch = 1 << lqd
+    out = np.zeros((nch, 4, n), np.uint32)
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    rc = lib.qk_host_run(C.c_uint(log_n), C.c_uint(lqd), C.c_size_t(2 * n), p(m_prep), p(m_main), p(m_perm),
+                         C.c_uint(chip.perm_width_ef), C.c_uint(1 << lqd), C.c_uint(chip.main_width), C.c_uint(int(chip.global_scope)),
+                         C.c_uint(len(chip.builder.constraints)), C.c_uint(len(lookups)), p(a_apow), p(a_K), p(a_E), p(a_pub),
+                         p(tw_lo), p(tw_hi), p(a_lsum), p(a_gsum), p(a_zh), p(a_izh),
+                         C.c_uint32(int(monty(np.array([3], np.uint32))[0])),
+                         C.c_uint32(int(monty(np.array([pow(two_adic_generator(log_n), P - 2, P)], np.uint32))[0])), p(out))
+    assert rc == 0
+    got = kb.from_monty(out.reshape(-1)).reshape(out.shape)
+    want_chunks = want.reshape(n, nch, 4).transpose(1, 2, 0)
+    assert np.array_equal(got, want_chunks), name
+
+
+def test_generated_keccak_kernel_matches_the_oracle_on_the_host(oracle, tw_tables, tmp_path):
+    from ziren_b200 import keccak_sponge as ks
+    from ziren_b200 import synthetic
+    b = ks.synthetic_blocks(2, [1, 2], seed=3)
+    t = oracle.keccak_sponge_trace(b, 1 << ks.padded_log_height(len(b)))
+    case = synthetic.keccak_real_case(b, t, log_cpu=10, num_queries=6, pow_bits=3)
+    om = oracle.OracleMachine(case.machine)
+    om.setup(case.prep)
+    _check_chip(oracle, om, case.machine, "KeccakSponge", None, case.traces["KeccakSponge"], case.public_values, tw_tables, tmp_path)
+    # the extended Byte table: preprocessed columns, four receives in batches of two
+    _check_chip(oracle, om, case.machine, "Byte", case.prep["Byte"], case.traces["Byte"], case.public_values, tw_tables, tmp_path)
+
+
+@pytest.mark.parametrize("name", ["Cpu", "Global", "Fibonacci", "Sink"])
+def test_generated_kernels_of_the_mini_machine_match_the_oracle_on_the_host(oracle, tw_tables, tmp_path, name):
+    from ziren_b200 import synthetic
+    case = synthetic.mini_case(seed=11)
+    om = oracle.OracleMachine(case.machine)
+    om.setup(case.prep)
+    _check_chip(oracle, om, case.machine, name, case.prep.get(name), case.traces[name], case.public_values, tw_tables, tmp_path)
