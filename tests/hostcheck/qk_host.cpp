@@ -49,4 +49,19 @@ int qk_host_run(unsigned log_n, unsigned lqd, size_t H, const uint32_t* prep, co
     }
   return 0;
 }
+#ifdef QK_HAS_LK
+// the generated K5 kernel `lk` of the same module: traces column-major with n rows; out: n x 4E column-major, rowsum [4][n]
+int lk_host_run(size_t n, const uint32_t* prep, const uint32_t* main_, const uint32_t* lkK, const uint32_t* lkE, uint32_t* out,
+                uint32_t* rowsum) {
+  PermArgs a;
+  a.prep = prep; a.main_ = main_; a.n = n; a.lkK = lkK; a.lkE = lkE; a.out = out; a.rowsum = rowsum;
+  blockDim.x = 128;
+  for (size_t b = 0; b < (n + 127) / 128; b++)
+    for (unsigned t = 0; t < 128; t++) {
+      blockIdx.x = (unsigned)b; threadIdx.x = t;
+      lk(a);
+    }
+  return 0;
+}
+#endif
 }

@@ -71,8 +71,9 @@ def _build_host_kernel(machine, chip_name, tmp):
         del os.environ["ZKB200_CODEGEN_DUMP"]
     src = os.path.join(str(tmp), f"qk_{chip_name}.cu")
     so = os.path.join(str(tmp), f"qk_{chip_name}.so")
+    has_lk = ["-DQK_HAS_LK"] if " lk(const PermArgs a)" in open(src).read() else []
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-I" + os.path.join(ROOT, "ziren_b200", "csrc"),
-                           f'-DQK_SOURCE="{src}"', os.path.join(HERE, "hostcheck", "qk_host.cpp"), "-o", so])
+                           f'-DQK_SOURCE="{src}"', *has_lk, os.path.join(HERE, "hostcheck", "qk_host.cpp"), "-o", so])
     return C.CDLL(so)
 
 
@@ -132,6 +133,19 @@ def _check_chip(oracle, om, machine, name, prep, trace, public_values, tw_tables
     got = kb.from_monty(out.reshape(-1)).reshape(out.shape)
     want_chunks = want.reshape(n, nch, 4).transpose(1, 2, 0)
     assert np.array_equal(got, want_chunks), name
+    # K5 from the same module: the permutation trace's batch columns and the row sums (the running-sum column is the
+    # scan kernels' job), against the oracle's permutation trace
+    if hasattr(lib, "lk_host_run") and chip.perm_width_ef:
+        ew = chip.perm_width_ef
+        t_prep = monty(colmajor(prep)) if prep is not None else np.zeros(1, np.uint32)
+        t_main = monty(colmajor(trace))
+        pout = np.zeros((4 * ew, n), np.uint32)
+        rowsum = np.zeros((4, n), np.uint32)
+        assert lib.lk_host_run(C.c_size_t(n), p(t_prep), p(t_main), p(a_K), p(a_E), p(pout), p(rowsum)) == 0
+        got_perm = kb.from_monty(pout.reshape(-1)).reshape(pout.shape).T            # n x 4E
+        assert np.array_equal(got_perm[:, :4 * (ew - 1)], perm[:, :4 * (ew - 1)]), name
+        batches = perm[:, :4 * (ew - 1)].reshape(n, ew - 1, 4).astype(np.uint64).sum(axis=1) % P
+        assert np.array_equal(kb.from_monty(rowsum.reshape(-1)).reshape(4, n).T.astype(np.uint64), batches), name
 
 
 def test_generated_keccak_kernel_matches_the_oracle_on_the_host(oracle, tw_tables, tmp_path):

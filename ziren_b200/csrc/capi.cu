@@ -11,7 +11,7 @@
 #include "tracegen.h"
 
 using namespace zkb;
-namespace zkb { extern std::atomic<int> g_ntt_force_k2; extern std::atomic<int> g_eval_v2; extern std::atomic<int> g_ntt_lean; extern std::atomic<int> g_quotient_codegen; extern std::atomic<int> g_k4b_rows; extern std::atomic<int> g_qk_block;
+namespace zkb { extern std::atomic<int> g_ntt_force_k2; extern std::atomic<int> g_eval_v2; extern std::atomic<int> g_ntt_lean; extern std::atomic<int> g_quotient_codegen; extern std::atomic<int> g_k4b_rows; extern std::atomic<int> g_qk_block; extern std::atomic<int> g_logup_codegen;
                extern std::atomic<unsigned long long> g_quotient_generated_launches, g_quotient_interpreter_launches; }
 
 // One prover object over one or several GPUs.  `c` (= *devs[0]) serves the kernel-level entry points;
@@ -482,6 +482,7 @@ int zkb200_set_option(const char* key, long value) {
   if (k == "quotient_codegen") { g_quotient_codegen = (int)value; return 0; }
   if (k == "k4b_rows") { g_k4b_rows = (int)value; return 0; }
   if (k == "qk_block") { g_qk_block = (int)value; return 0; }
+  if (k == "logup_codegen") { g_logup_codegen = (int)value; return 0; }
   g_err = "zkb200: unknown option " + k;
   return 1;
 }

@@ -175,6 +175,38 @@ KB_HD Ef ef_inv(const Ef& a) {
   return r;
 }
 
+// 1 / den for G denominators with ONE base-field inversion: ef_inv (kb31.cuh) takes the norm down to F and inverts
+// there (a 30-step power), so the G norms share a Montgomery batch inversion.  A zero denominator (probability
+// 2^-124 per lookup) has inverse 0 in ef_inv; here it is replaced by 1 in the product and masked afterwards, so the
+// result is the same.
+template <int G>
+KB_HD void ef_inv_batch(const Ef* den, Ef* out) {
+  Fp n0[G], n1[G], d[G], pref[G];
+  for (int i = 0; i < G; i++) {
+    const Fp a0 = den[i].c[0], a1 = den[i].c[1], a2 = den[i].c[2], a3 = den[i].c[3];
+    const Fp A0 = a0 * a0 + fp_mul3(a2 * a2), A1 = fp_double(a0 * a2);
+    const Fp B0 = a1 * a1 + fp_mul3(a3 * a3), B1 = fp_double(a1 * a3);
+    n0[i] = A0 - fp_mul3(B1);
+    n1[i] = A1 - B0;
+    d[i] = n0[i] * n0[i] - fp_mul3(n1[i] * n1[i]);
+    const Fp dd = d[i].v ? d[i] : fp_one();
+    pref[i] = i ? pref[i - 1] * dd : dd;
+  }
+  Fp inv = fp_inv(pref[G - 1]);
+  for (int i = G - 1; i >= 0; i--) {
+    const Fp dd = d[i].v ? d[i] : fp_one();
+    Fp di = i ? inv * pref[i - 1] : inv;
+    inv = inv * dd;
+    if (!d[i].v) di = fp_zero();
+    const Fp I0 = n0[i] * di, I1 = -(n1[i] * di);
+    const Fp a0 = den[i].c[0], a1 = den[i].c[1], a2 = den[i].c[2], a3 = den[i].c[3];
+    out[i].c[0] = a0 * I0 + fp_mul3(a2 * I1);
+    out[i].c[2] = a0 * I1 + a2 * I0;
+    out[i].c[1] = -(a1 * I0 + fp_mul3(a3 * I1));
+    out[i].c[3] = -(a1 * I1 + a3 * I0);
+  }
+}
+
 KB_HD unsigned log2_exact(size_t n) { unsigned l = 0; while (((size_t)1 << l) < n) l++; return l; }
 KB_HD u32 bitrev32(u32 x, unsigned bits) {
 #if defined(__CUDA_ARCH__)

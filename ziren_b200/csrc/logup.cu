@@ -4,7 +4,11 @@
 // running-sum column.  Column-major traces keep every load of a warp contiguous.
 #include "logup.h"
 
+#include <atomic>
+#include "quotient_codegen.h"
+#include "quotient_rt.cuh"
 namespace zkb {
+std::atomic<int> g_logup_codegen{1};         // zkb200_set_option("logup_codegen"): K5 from the generated module (1) or the run-time loop (0)
 
 struct LogupArgs {
   const u32* prep; const u32* main_; size_t n;
@@ -31,40 +35,6 @@ __device__ __forceinline__ Fp eval_vpc(const LogupArgs& a, u32 vi, size_t r) {
     acc += x * fp_raw(tm.w);
   }
   return acc;
-}
-
-// 1 / den for G denominators with ONE base-field inversion: ef_inv (kb31.cuh) takes the norm down to F and inverts
-// there (a 30-step power), so the G norms share a Montgomery batch inversion.  A zero denominator (probability
-// 2^-124 per lookup) has inverse 0 in ef_inv; here it is replaced by 1 in the product and masked afterwards, so the
-// result is the same.
-template <int G>
-__device__ __forceinline__ void ef_inv_batch(const Ef* den, Ef* out) {
-  Fp n0[G], n1[G], d[G], pref[G];
-#pragma unroll
-  for (int i = 0; i < G; i++) {
-    const Fp a0 = den[i].c[0], a1 = den[i].c[1], a2 = den[i].c[2], a3 = den[i].c[3];
-    const Fp A0 = a0 * a0 + fp_mul3(a2 * a2), A1 = fp_double(a0 * a2);
-    const Fp B0 = a1 * a1 + fp_mul3(a3 * a3), B1 = fp_double(a1 * a3);
-    n0[i] = A0 - fp_mul3(B1);
-    n1[i] = A1 - B0;
-    d[i] = n0[i] * n0[i] - fp_mul3(n1[i] * n1[i]);
-    const Fp dd = d[i].v ? d[i] : fp_one();
-    pref[i] = i ? pref[i - 1] * dd : dd;
-  }
-  Fp inv = fp_inv(pref[G - 1]);
-#pragma unroll
-  for (int i = G - 1; i >= 0; i--) {
-    const Fp dd = d[i].v ? d[i] : fp_one();
-    Fp di = i ? inv * pref[i - 1] : inv;
-    inv = inv * dd;
-    if (!d[i].v) di = fp_zero();
-    const Fp I0 = n0[i] * di, I1 = -(n1[i] * di);
-    const Fp a0 = den[i].c[0], a1 = den[i].c[1], a2 = den[i].c[2], a3 = den[i].c[3];
-    out[i].c[0] = a0 * I0 + fp_mul3(a2 * I1);
-    out[i].c[2] = a0 * I1 + a2 * I0;
-    out[i].c[1] = -(a1 * I0 + fp_mul3(a3 * I1));
-    out[i].c[3] = -(a1 * I1 + a3 * I0);
-  }
 }
 
 __global__ void __launch_bounds__(128) logup_rows_kernel(LogupArgs a) {
@@ -224,7 +194,16 @@ void permutation_trace(const MachineInfo& m, const ChipInfo& chip, const u32* pr
   const size_t nblk = ceil_div(n, SCAN_BLOCK);
   DevBuf rowsum(4 * n, s), btot(4 * nblk, s);
   a.rowsum = rowsum.p;
-  logup_rows_kernel<<<ceil_div(n, 128), 128, 0, s>>>(a);
+  // the chip's generated K5 kernel (quotient_codegen.cpp: one loop per batch shape, loads first), else the data-driven loop
+  void* gen = g_logup_codegen.load() ? permutation_generated_kernel(chip) : nullptr;
+  if (gen) {
+    PermArgs pa;
+    pa.prep = prep; pa.main_ = main_; pa.n = n; pa.lkK = coefK.p; pa.lkE = coefE.p; pa.out = out; pa.rowsum = rowsum.p;
+    void* params[] = {&pa};
+    ZKB_CUDA(cudaLaunchKernel((const void*)gen, dim3(ceil_div(n, 128)), dim3(128), params, 0, s));
+  } else {
+    logup_rows_kernel<<<ceil_div(n, 128), 128, 0, s>>>(a);
+  }
   ZKB_CHECK_LAUNCH();
   u32* last = out + (size_t)4 * (ew - 1) * n;   // the 4 running-sum columns are contiguous
   scan_phase1<<<dim3((unsigned)nblk, 4), SCAN_BLOCK, 0, s>>>(rowsum.p, last, btot.p, n, nblk);

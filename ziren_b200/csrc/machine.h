@@ -25,10 +25,11 @@ struct HostNode { u32 op, a, b; };
 // a per-chip cache slot that copies as "empty" (ChipInfo stays copyable)
 struct KernelSlot {
   mutable std::atomic<void*> p{nullptr};
+  mutable std::atomic<void*> lk{nullptr};       // the module's K5 kernel, same encoding as p
   mutable std::atomic<unsigned> groups{0};      // CTAs per row tile of the generated kernel, 0 = not computed yet
   KernelSlot() = default;
   KernelSlot(const KernelSlot&) {}
-  KernelSlot& operator=(const KernelSlot&) { p.store(nullptr); groups.store(0); return *this; }
+  KernelSlot& operator=(const KernelSlot&) { p.store(nullptr); lk.store(nullptr); groups.store(0); return *this; }
 };
 
 struct ChipInfo {

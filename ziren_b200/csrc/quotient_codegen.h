@@ -17,6 +17,8 @@ std::string quotient_kernel_source(const ChipInfo& chip);
 // unavailable / failed (the reason is kept in quotient_codegen_last_error()).  Thread safe; results are
 // memoised per source text for the life of the process.
 void* quotient_generated_kernel(const ChipInfo& chip);
+// `lk` of the same module: the chip's LogUp permutation-trace rows (K5), or nullptr (no lookups / compilation unavailable)
+void* permutation_generated_kernel(const ChipInfo& chip);
 const char* quotient_codegen_last_error();
 // How many CTAs share a row tile in the chip's generated kernel (1: the whole constraint set in one CTA).  Pure
 // function of the chip, the same number the generator wrote the kernel for.

@@ -38,6 +38,16 @@ struct QuotArgs {
   u32* partial;
 };
 
+// K5 as generated code (quotient_codegen.cpp, kernel `lk`): the LogUp permutation trace rows of one chip.  prep / main_: column-major
+// TRACES of n rows; out: n x 4E column-major (the batch columns; the running-sum column is filled by the scan kernels of
+// logup.cu); rowsum: [4][n], the row's sum over its batches.
+struct PermArgs {
+  const u32* prep; const u32* main_;
+  size_t n;
+  const u32* lkK; const u32* lkE;
+  u32* out; u32* rowsum;
+};
+
 struct QuotRow {
   size_t t, tn;            // storage rows of the local and the next row
   u32 i;                   // natural index on the quotient domain
