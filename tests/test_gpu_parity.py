@@ -129,7 +129,19 @@ def test_commit_matches_oracle(torch, mini, oracle):
     pk.free()
 
 
-def test_permutation_trace_matches_oracle(torch, mini, oracle):
+@pytest.mark.parametrize("codegen", [1, 0], ids=["generated", "data-driven"])
+def test_permutation_trace_matches_oracle(torch, mini, oracle, codegen):
+    """K5 both ways: the rows from the chip's generated module (kernel `lk`) and from the data-driven kernel over the
+    flattened lookups, each bit-exact against the oracle for every chip of the machine."""
+    from ziren_b200 import _ffi
+    _ffi.lib().zkb200_set_option(b"logup_codegen", codegen)
+    try:
+        _permutation_trace_matches_oracle(torch, mini, oracle)
+    finally:
+        _ffi.lib().zkb200_set_option(b"logup_codegen", 1)
+
+
+def _permutation_trace_matches_oracle(torch, mini, oracle):
     case, prover = mini
     om = oracle.OracleMachine(case.machine)
     rng = np.random.default_rng(3)
