@@ -379,6 +379,8 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     if (!c) throw std::runtime_error("zkb200: commit: unknown chip " + t.name);
     if (c->main_width != t.width) throw std::runtime_error("zkb200: commit: main width mismatch for " + t.name);
     check_height(ctx.machine, t.height, logn[i]);
+    if ((t.flags & ~(TRACE_EVENTS | TRACE_COL_MAJOR)) || (t.flags & (TRACE_EVENTS | TRACE_COL_MAJOR)) == (TRACE_EVENTS | TRACE_COL_MAJOR))
+      throw std::runtime_error("zkb200: commit: bad zkb200_trace.flags for " + t.name);
     if (t.flags & TRACE_EVENTS) {
       const size_t rows_per_event = t.name == "KeccakSponge" ? KS_ROUNDS : 1;
       event_record_words(t.name);       // throws for a chip without a row filler
