@@ -3,14 +3,17 @@
 
 A "step" proves ONE shard of the named workload through the reference-facing C ABI
 (`zkb200_commit` + `zkb200_open`, i.e. MachineProver::{commit, open}).  Default workload at N=1 is
-BASELINE.json configs[1] ("examples/keccak-precompile, 2^20-row shards"): a synthetic core shard
-with a 2^20-row Cpu table whose area is dominated by a KeccakSponge precompile table (no guest ELF
-can be built here, see ziren_b200/synthetic.py).  cycles per shard = rows of the Cpu table.
+BASELINE.json configs[1] ("examples/keccak-precompile, 2^20-row shards"): a core shard with a 2^20-row Cpu table
+(synthetic core tables: no guest ELF can be built here, see ziren_b200/synthetic.py) whose area is dominated by the
+reference's REAL KeccakSponge precompile chip - its 3531-column layout, its restated Air::eval (3 788 constraints,
+357 lookups; ziren_b200/keccak_air.py), 2^18 rows from the row filler on well-formed sponge events.
+cycles per shard = rows of the Cpu table.
 
   value : device-resident inputs (row-major traces already in HBM), timed with CUDA events on the
           prover's stream, max over ranks.
-  e2e   : the same call with traces in PINNED HOST memory; H2D of the traces and D2H of the proof
-          are inside the timed region.
+  e2e   : the same calls with HOST inputs, H2D and the proof's D2H inside the timed region: pinned event records for
+          the chip whose table the library generates on the device (ZKB200_TRACE_EVENTS), pinned rows for every other
+          table; `e2e.uploaded_keccak_rows` is the same proof with that chip's rows uploaded instead.
   roofline / cpu_baseline : see DESIGN.md §Measurement.
 
 Multi-GPU (torchrun, one rank per GPU): shards are independent, every rank proves
