@@ -168,3 +168,15 @@ def test_generated_kernels_of_the_mini_machine_match_the_oracle_on_the_host(orac
     om = oracle.OracleMachine(case.machine)
     om.setup(case.prep)
     _check_chip(oracle, om, case.machine, name, case.prep.get(name), case.traces[name], case.public_values, tw_tables, tmp_path)
+
+
+@pytest.mark.parametrize("which,name", [("edge", "PlainA"), ("edge", "Alu"), ("edge", "Program"), ("compress", "Poseidon2Wide"),
+                                        ("compress", "PublicValues"), ("core", "MemoryInstrs"), ("core", "Byte")])
+def test_generated_kernels_of_other_machines_match_the_oracle_on_the_host(oracle, tw_tables, tmp_path, which, name):
+    """Chips without lookups (no LogUp code at all), preprocessed-only tables, the wide recursion-like and core-like tables."""
+    from ziren_b200 import synthetic
+    case = {"edge": lambda: synthetic.edge_case(), "compress": lambda: synthetic.compress_case(log_max=7),
+            "core": lambda: synthetic.core_case(log_cpu=8)}[which]()
+    om = oracle.OracleMachine(case.machine)
+    om.setup(case.prep)
+    _check_chip(oracle, om, case.machine, name, case.prep.get(name), case.traces[name], case.public_values, tw_tables, tmp_path)
