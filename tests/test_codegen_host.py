@@ -86,9 +86,10 @@ def _check_chip(oracle, om, machine, name, prep, trace, public_values, tw_tables
     log_n, lqd = int(np.log2(n)), chip.log_quotient_degree
     perm, lsum = om.permutation_trace(name, prep, trace, pa, pb)
     gsum = trace[-1, -14:] if chip.global_scope else kb.SEPTIC_DIGEST_ZERO
-    main_lde = oracle.coset_lde(trace)
-    perm_lde = oracle.coset_lde(perm) if perm.shape[1] else np.zeros((2 * n, 0), np.uint32)
-    prep_lde = oracle.coset_lde(prep) if prep is not None else None
+    lb = machine.log_blowup
+    main_lde = oracle.coset_lde(trace, added_bits=lb)
+    perm_lde = oracle.coset_lde(perm, added_bits=lb) if perm.shape[1] else np.zeros((n << lb, 0), np.uint32)
+    prep_lde = oracle.coset_lde(prep, added_bits=lb) if prep is not None else None
     want = om.quotient_values(name, log_n, prep_lde, main_lde, perm_lde, pa, pb, lsum, gsum, al, public_values)
     # what quotient.cu / lookup_coefficients prepare on the device, here in Python
     lookups = [l for l in chip.builder.sends + chip.builder.receives if l["scope"] == SCOPE_LOCAL]
@@ -123,7 +124,7 @@ def _check_chip(oracle, om, machine, name, prep, trace, public_values, tw_tables
     nch = 1 << lqd
     out = np.zeros((nch, 4, n), np.uint32)
     p = lambda x: x.ctypes.data_as(C.c_void_p)
-    rc = lib.qk_host_run(C.c_uint(log_n), C.c_uint(lqd), C.c_size_t(2 * n), p(m_prep), p(m_main), p(m_perm),
+    rc = lib.qk_host_run(C.c_uint(log_n), C.c_uint(lqd), C.c_size_t(n << lb), p(m_prep), p(m_main), p(m_perm),
                          C.c_uint(chip.perm_width_ef), C.c_uint(1 << lqd), C.c_uint(chip.main_width), C.c_uint(int(chip.global_scope)),
                          C.c_uint(len(chip.builder.constraints)), C.c_uint(len(lookups)), p(a_apow), p(a_K), p(a_E), p(a_pub),
                          p(tw_lo), p(tw_hi), p(a_lsum), p(a_gsum), p(a_zh), p(a_izh),
@@ -180,3 +181,84 @@ def test_generated_kernels_of_other_machines_match_the_oracle_on_the_host(oracle
     om = oracle.OracleMachine(case.machine)
     om.setup(case.prep)
     _check_chip(oracle, om, case.machine, name, case.prep.get(name), case.traces[name], case.public_values, tw_tables, tmp_path)
+
+
+def _random_chip(rng, name, degree_cap, lookups=True):
+    """A chip with random constraints and lookups: templates of random expressions (degree <= degree_cap) stamped over
+    several column offsets (so that the generator finds repeated shapes), a few one-off constraints, and an odd or even number
+    of sends / receives whose values are constants, columns, and affine combinations."""
+    from ziren_b200.air import KIND_BYTE, KIND_MEMORY, Chip
+    prep_w, main_w = int(rng.integers(0, 4)), int(rng.integers(8, 14))
+    n_templates, reps = int(rng.integers(2, 5)), int(rng.integers(3, 7))
+    n_lookups = int(rng.integers(1, 10)) if lookups else 0
+    seeds = rng.integers(0, 1 << 30, 64)
+
+    def ev(b):
+        def leaf(r, off):
+            k = int(r.integers(0, 10))
+            if k <= 4:
+                return b.main(int(r.integers(0, main_w - 7)) + off, next=bool(r.integers(0, 4) == 0))
+            if k == 5 and prep_w:
+                return b.prep(int(r.integers(0, prep_w)), next=bool(r.integers(0, 2)))
+            if k == 6:
+                return b.const(int(r.integers(0, 1 << 31)))
+            if k == 7:
+                return b.pub(int(r.integers(0, 4)))
+            if k == 8:
+                return [b.is_first_row(), b.is_last_row(), b.is_transition()][int(r.integers(0, 3))]
+            return b.main(int(r.integers(0, main_w - 7)) + off)
+
+        def expr(r, off, depth):
+            if depth == 0:
+                return leaf(r, off)
+            op = int(r.integers(0, 4))
+            x = expr(r, off, depth - 1)
+            if op == 3:
+                return -x
+            y = expr(r, off, depth - 1)
+            if op == 2:
+                if x.deg + y.deg > degree_cap:
+                    return x + y
+                return x * y
+            return x + y if op == 0 else x - y
+        for t in range(n_templates):
+            for off in range(reps):                      # the same expression over shifted columns: one shape, `reps` members
+                b.assert_zero(expr(np.random.default_rng(int(seeds[t])), off, 3))
+        for t in range(3):                               # one-off constraints
+            b.assert_zero(expr(np.random.default_rng(int(seeds[10 + t])), 0, 2))
+        if degree_cap >= 4:                              # a product of degree_cap columns: more than two quotient chunks
+            prod = b.main(0)
+            for k in range(1, degree_cap):
+                prod = prod * b.main(k % main_w, next=bool(k == 2))
+            b.assert_zero(prod - b.main(main_w - 1))
+        r = np.random.default_rng(int(seeds[20]))
+        for i in range(n_lookups):
+            vals = []
+            for _ in range(int(r.integers(1, 5))):
+                k = int(r.integers(0, 4))
+                c0 = b.main(int(r.integers(0, main_w)))
+                vals.append(int(r.integers(0, 300)) if k == 0 else c0 if k == 1 else c0 + int(r.integers(1, 99)) if k == 2
+                            else c0 * int(r.integers(2, 9)) + b.main(int(r.integers(0, main_w))))
+            mult = [1, b.main(int(r.integers(0, main_w))), b.main(int(r.integers(0, main_w))) * 3 + 2][int(r.integers(0, 3))]
+            (b.send if i % 3 else b.receive)(KIND_MEMORY if i % 2 else KIND_BYTE, vals, mult)
+    return Chip(name, prep_w, main_w, ev)
+
+
+@pytest.mark.parametrize("seed,log_blowup,degree_cap,lookups", [(1, 1, 3, True), (2, 1, 3, True), (3, 2, 5, True), (4, 3, 5, True),
+                                                                (5, 1, 2, False), (6, 2, 4, True), (7, 3, 9, True)])
+def test_generated_kernels_of_random_chips_match_the_oracle_on_the_host(oracle, tw_tables, tmp_path, seed, log_blowup, degree_cap,
+                                                                        lookups):
+    """Generator fuzz: random constraint DAGs (repeated shapes and one-off constraints, every leaf kind, degrees up to 5 with
+    quotient chunk counts 1, 2 and 4) and random lookups (batches of 1, 2 and 4; constants, columns and affine values; odd
+    counts), evaluated on random traces: the generated K3 and K5 source must reproduce the oracle exactly."""
+    from ziren_b200.air import Machine
+    rng = np.random.default_rng(1000 + seed)
+    chip = _random_chip(rng, "Fuzz", degree_cap, lookups)
+    assert chip.log_quotient_degree == {2: 0 if not lookups else 1, 3: 1, 4: 2, 5: 2, 9: 3}[degree_cap]
+    machine = Machine([chip], num_pv_elts=4, log_blowup=log_blowup, num_queries=4, pow_bits=2)
+    n = 1 << int(rng.integers(3, 7))
+    trace = kb.random_elements(rng, (n, chip.main_width))
+    prep = kb.random_elements(rng, (n, chip.prep_width)) if chip.prep_width else None
+    pv = kb.random_elements(rng, 8)
+    om = oracle.OracleMachine(machine)
+    _check_chip(oracle, om, machine, "Fuzz", prep, trace, pv, tw_tables, tmp_path, seed=seed)
