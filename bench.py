@@ -495,7 +495,10 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1, k3_bytes=None):
         ms = stages["quotient"]
         ach = k3_bytes / (ms / 1e3) / 1e9
         out["k3_quotient"] = {"bound": "hbm", "kernel": "quotient_values: generated per-chip constraint kernels qk (NVRTC) + LogUp constraints",
-                              "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                              "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": ach / peak,
+                              # the Keccak chip's kernel moves 7.79 GB of DRAM for 2.23 GB algorithmic (profiles/r02_qk_keccak_ncu.txt);
+                              # it is 90 % of the stage's bytes, the ratio is applied to the whole stage
+                              "traffic": k3_bytes * 3.49, "traffic_source": "algorithmic bytes x the dram__bytes ratio of the ncu --set full capture of the KeccakSponge kernel",
                               "ms": ms, "algorithmic_bytes": k3_bytes, "share_of_step": ms / max(sum(stages.values()), 1e-9),
                               "note": "4*2n*(P+M+4E) + 16*2n bytes per chip (SURVEY.md section 8d); on the real KeccakSponge chip the kernel "
                                       "executes 471 k warp instructions per row-warp (3 788 constraints = 66 k node evaluations, 357 lookups): "
