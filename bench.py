@@ -419,7 +419,7 @@ def main():
     if args.rank == 0:
         k3_bytes = sum(8.0 * shapes[c.name][0] * (c.prep_width + c.main_width + 4 * c.perm_width_ef) + 32.0 * shapes[c.name][0]
                        for c in case.machine.chips if c.name in shapes)
-        rl = stage_rooflines(shapes, stages or {}, k3_bytes=k3_bytes)
+        rl = stage_rooflines(shapes, stages or {}, k3_bytes=k3_bytes, k3_dram_ratio=3.49 if real else None)
         ranked = sorted(rl.values(), key=lambda r: -r["ms"])
         if ranked:
             roofline, roofline_other = ranked[0], ranked[1:]
@@ -460,7 +460,7 @@ def main():
         dist.destroy_process_group()
 
 
-def stage_rooflines(trace_shapes, stages, log_blowup=1, k3_bytes=None):
+def stage_rooflines(trace_shapes, stages, log_blowup=1, k3_bytes=None, k3_dram_ratio=None):
     """HBM rooflines of the two dominant kernel families from the per-stage CUDA-event times of a
     live profiled step (zkb200_set_profile): K2 = Merkle build of the main commit, K1 = coset LDE of
     the main commit.  Algorithmic bytes per SURVEY.md section 8d."""
@@ -498,7 +498,8 @@ def stage_rooflines(trace_shapes, stages, log_blowup=1, k3_bytes=None):
                               "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": ach / peak,
                               # the Keccak chip's kernel moves 7.79 GB of DRAM for 2.23 GB algorithmic (profiles/r02_qk_keccak_ncu.txt);
                               # it is 90 % of the stage's bytes, the ratio is applied to the whole stage
-                              "traffic": k3_bytes * 3.49, "traffic_source": "algorithmic bytes x the dram__bytes ratio of the ncu --set full capture of the KeccakSponge kernel",
+                              "traffic": k3_bytes * k3_dram_ratio if k3_dram_ratio else None,
+                              "traffic_source": "algorithmic bytes x the dram__bytes ratio of the ncu --set full capture of the KeccakSponge kernel" if k3_dram_ratio else None,
                               "ms": ms, "algorithmic_bytes": k3_bytes, "share_of_step": ms / max(sum(stages.values()), 1e-9),
                               "note": "4*2n*(P+M+4E) + 16*2n bytes per chip (SURVEY.md section 8d); on the real KeccakSponge chip the kernel "
                                       "executes 471 k warp instructions per row-warp (3 788 constraints = 66 k node evaluations, 357 lookups): "
