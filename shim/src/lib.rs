@@ -144,6 +144,7 @@ where
 impl<A> MachineProver<SC, A> for B200Prover<A>
 where
     A: MachineAir<F> + Air<SymbolicAirBuilder<F>> + Send + Sync + 'static,
+    A::Record: DeviceTraceEvents,           // implement it (all defaults) for a record type without device row fillers
     CpuProver<SC, A>: MachineProver<SC, A, DeviceProvingKey = StarkProvingKey<SC>>,
 {
     type DeviceMatrix = B200Matrix;
@@ -216,10 +217,11 @@ where
         let rc = unsafe { sys::zkb200_commit(self.ctx, t.as_ptr(), t.len() as i32, pv.as_ptr(), pv.len(), commit.as_mut_ptr(), &mut shard) };
         check(self.ctx, rc).expect("zkb200_commit");          // the trait's commit is infallible (prover.rs:110-114)
         // chip ordering as CpuProver::commit sorts it: (Reverse(height), name), prover.rs:264
-        let mut order: Vec<(usize, &str)> = traces.iter().map(|(n, m)| (m.height(), n.as_str())).collect();
-        order.sort_by(|a, b| b.0.cmp(&a.0).then(a.1.cmp(b.1)));
-        let chip_ordering: HashMap<String, usize> = order.iter().enumerate().map(|(i, (_, n))| (n.to_string(), i)).collect();
-        let shapes = order.iter().map(|(h, n)| B200Matrix { height: *h, width: traces.iter().find(|(m, _)| m == n).unwrap().1.width() }).collect();
+        // heights and widths as handed to the library (a table passed as event records has its padded height there)
+        let mut order: Vec<(usize, usize, &str)> = traces.iter().zip(&t).map(|((n, _), d)| (d.height, d.width, n.as_str())).collect();
+        order.sort_by(|a, b| b.0.cmp(&a.0).then(a.2.cmp(b.2)));
+        let chip_ordering: HashMap<String, usize> = order.iter().enumerate().map(|(i, (_, _, n))| (n.to_string(), i)).collect();
+        let shapes = order.iter().map(|(h, w, _)| B200Matrix { height: *h, width: *w }).collect();
         let main_commit: [F; 8] = core::array::from_fn(|i| F::from_canonical_u32(commit[i]));
         ShardMainData::new(shapes, main_commit.into(), B200ProverData(shard), chip_ordering, public_values)
     }
