@@ -181,7 +181,10 @@ int zkb200_grind(zkb200_ctx* ctx, const uint32_t challenger[34], unsigned bits, 
  * {pc, next_pc, opcode, a, b, c, prev_a} for MovCond
  * (crates/core/executor/src/events/instr.rs:11-26, :160-217, :287-302).  "Mul" (crates/core/machine/src/alu/mul/mod.rs, C++
  * twin include/mul.hpp) takes 64-byte `CompAluEvent` records {shard, clk, pc, next_pc, opcode, hi, a, b, c, hi_record
- * {value, shard, timestamp, prev_value, prev_shard, prev_timestamp}, hi_record_is_real} (instr.rs:47-73).  `out` is DEVICE memory of
+ * {value, shard, timestamp, prev_value, prev_shard, prev_timestamp}, hi_record_is_real} (instr.rs:47-73).  "MemoryInstrs"
+ * (crates/core/machine/src/memory/instructions/trace.rs:103-263, C++ twin include/memory_instrs.hpp; 79 columns) takes 64-byte
+ * `MemInstrEvent` records {shard, clk, pc, next_pc, opcode, a, b, c, mem_access {tag: 0 Read / 1 Write, record: six words},
+ * prev_a_val} (instr.rs:114-136, events/memory.rs:46-97).  `out` is DEVICE memory of
  * 2^log_height x width words, Montgomery, row-major (col_major = 0: the RowMajorMatrix layout
  * zkb200_commit takes) or column-major (col_major = 1: the layout of the kernel-level entry points). */
 typedef struct {

@@ -264,6 +264,13 @@ int zko_mul_trace(const u32* ev, size_t n, size_t height, u32* out) {
     return 0;
   } catch (const std::exception& e) { return fail(e); }
 }
+// MemoryInstrs rows (tracegen.h): events n x 16 words (MemInstrEvent), out height x 79 row-major canonical
+int zko_mem_instr_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  try {
+    mem_instr_trace(ev, n, height, out);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
 // trace generation of the KeccakSponge chip (tracegen_keccak.h): n_blocks records of KS_REC_WORDS words,
 // out height x 3531 row-major canonical
 int zko_keccak_sponge_width() { return KS_WIDTH; }

@@ -115,6 +115,30 @@ def ref_mul_rows(events):
     return out
 
 
+MEMINSTR_WIDTH = 79
+
+
+def mem_instr_trace(events, height):
+    """events: (n, 16) uint32 MemInstrEvent records; (height, 79) canonical rows of the MemoryInstrs chip."""
+    ev = _a(events).reshape(-1, COMP_EVENT_WORDS)
+    out = np.zeros((int(height), MEMINSTR_WIDTH), np.uint32)
+    if lib().zko_mem_instr_trace(_p(ev), C.c_size_t(ev.shape[0]), C.c_size_t(int(height)), _p(out)):
+        raise RuntimeError(err())
+    return out
+
+
+def ref_mem_instr_rows(events):
+    """Rows of the reference's own memory_instrs.hpp event_to_row (Montgomery words), or None without oracle/_ref."""
+    l = ref_core_lib()
+    if l is None or not hasattr(l, "ref_mem_instr_event_to_rows"):
+        return None
+    ev = _a(events).reshape(-1, COMP_EVENT_WORDS)
+    out = np.zeros((ev.shape[0], MEMINSTR_WIDTH), np.uint32)
+    if l.ref_mem_instr_event_to_rows(_p(ev), C.c_size_t(ev.shape[0]), _p(out)):
+        raise RuntimeError("reference row filler failed")
+    return out
+
+
 KS_WIDTH, KS_REC_WORDS = 3531, 384
 
 

@@ -17,6 +17,7 @@
 #include "mov_cond.hpp"
 #include "memory.hpp"
 #include "mul.hpp"
+#include "memory_instrs.hpp"
 
 using namespace zkm_core_machine_sys;
 
@@ -100,6 +101,30 @@ int ref_mul_event_to_rows(const uint32_t* ev, size_t n, uint32_t* rows) {
     CompAluEvent c{e[0], e[1], e[2], e[3], (Opcode)e[4], e[5], e[6], e[7], e[8],
                    MemoryWriteRecord{e[9], e[10], e[11], e[12], e[13], e[14]}, e[15] != 0};
     mul::event_to_row<kb31_t>(c, *reinterpret_cast<MulCols<kb31_t>*>(rows + i * w));
+  }
+  return 0;
+}
+// MemoryInstrs rows of the reference's memory_instrs.hpp: events n x 16 words, the #[repr(C)] image of MemInstrEvent {shard,
+// clk, pc, next_pc, opcode, a, b, c, mem_access{tag, six record words}, prev_a_val}; rows n x 79 Montgomery words
+unsigned ref_mem_instr_num_cols() { return ncols<MemoryInstructionsColumns<kb31_t>>(); }
+int ref_mem_instr_event_to_rows(const uint32_t* ev, size_t n, uint32_t* rows) {
+  static_assert(sizeof(MemInstrEvent) == 16 * sizeof(uint32_t), "MemInstrEvent is sixteen words");
+  const unsigned w = ref_mem_instr_num_cols();
+  std::memset(rows, 0, n * w * sizeof(uint32_t));
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t* e = ev + 16 * i;
+    MemInstrEvent m;
+    std::memset(&m, 0, sizeof(m));
+    m.shard = e[0]; m.clk = e[1]; m.pc = e[2]; m.next_pc = e[3]; m.opcode = (Opcode)e[4]; m.a = e[5]; m.b = e[6]; m.c = e[7];
+    if (e[8] == 0) {
+      m.mem_access.tag = MemoryRecordEnum::Tag::Read;
+      m.mem_access.read._0 = MemoryReadRecord{e[9], e[10], e[11], e[12], e[13]};
+    } else {
+      m.mem_access.tag = MemoryRecordEnum::Tag::Write;
+      m.mem_access.write._0 = MemoryWriteRecord{e[9], e[10], e[11], e[12], e[13], e[14]};
+    }
+    m.prev_a_val = e[15];
+    memory_instrs::event_to_row<kb31_t>(m, *reinterpret_cast<MemoryInstructionsColumns<kb31_t>*>(rows + i * w));
   }
   return 0;
 }

@@ -192,4 +192,28 @@ template <class T> struct MulCols {
   T shard, clk;
 };
 
+// ---- MemoryInstrs (crates/core/machine/include/memory_instrs.hpp) ----
+// crates/core/executor/src/events/instr.rs:114-136 (#[repr(C)])
+struct MemInstrEvent {
+  uint32_t shard, clk, pc, next_pc;
+  Opcode opcode;
+  uint32_t a, b, c;
+  MemoryRecordEnum mem_access;
+  uint32_t prev_a_val;
+};
+// crates/core/machine/src/memory/instructions/columns.rs:15-117 (MemoryInstructionsColumns)
+template <class T> struct MemoryInstructionsColumns {
+  T pc, next_pc, shard, clk;
+  Word<T> op_a_value, op_b_value, op_c_value;
+  T is_lb, is_lbu, is_lh, is_lhu, is_lw, is_lwl, is_lwr, is_ll, is_sb, is_sh, is_sw, is_swl, is_swr, is_sc;
+  Word<T> addr_word;
+  T addr_aligned, addr_ls_two_bits, ls_bits_is_one, ls_bits_is_two, ls_bits_is_three;
+  KoalaBearWordRangeChecker<T> addr_word_range_checker;
+  MemoryReadWriteCols<T> memory_access;
+  Word<T> prev_a_val;
+  Word<T> unsigned_mem_val;
+  T most_sig_bit, most_sig_byte, mem_value_is_neg;
+  IsZeroOperation<T> most_sig_bytes_zero;
+};
+
 }  // namespace zkm_core_machine_sys

@@ -235,7 +235,7 @@ enum { K_MUL = 2, K_MULT = 3, K_MULTU = 4, MUL_WIDTH = 58, COMP_EVENT_WORDS = 16
 static inline void mul_row(const u32* e, u32* row) {
   RowWriter w{row};
   const u32 shard = e[0], clk = e[1], pc = e[2], next_pc = e[3], opcode = e[4] & 0xff, hi = e[5], a = e[6], b = e[7], c = e[8];
-  const bool hi_real = e[15] != 0;
+  const bool hi_real = (e[15] & 0xff) != 0;      // a Rust bool: one byte
   w.put(pc); w.put(next_pc);
   w.word(hi); w.word(a); w.word(b); w.word(c);
   // byte vectors, sign-extended to eight bytes for MULT with a negative operand
@@ -278,6 +278,86 @@ static inline void mul_trace(const u32* ev, size_t n, size_t height, u32* out) {
   for (size_t i = 0; i < height; i++) {
     if (i < n) mul_row(ev + COMP_EVENT_WORDS * i, out + i * MUL_WIDTH);
     else for (int k = 0; k < MUL_WIDTH; k++) out[i * MUL_WIDTH + k] = 0;
+  }
+}
+
+// ---- MemoryInstrs (crates/core/machine/src/memory/instructions/trace.rs:103-263, columns.rs:15-117; C++ twin
+// include/memory_instrs.hpp) ------------------------------------------------------------------------------------------
+// MemInstrEvent (crates/core/executor/src/events/instr.rs:114-136) as its 16 #[repr(C)] words: shard, clk, pc, next_pc, opcode,
+// a, b, c, mem_access tag (0 Read, 1 Write), the record (MemoryReadRecord {value, shard, timestamp, prev_shard,
+// prev_timestamp} or MemoryWriteRecord {value, shard, timestamp, prev_value, prev_shard, prev_timestamp}, six words),
+// prev_a_val.  Padding rows are zero (trace.rs:57-80).
+enum { K_LB = 31, K_LBU, K_LH, K_LHU, K_LW, K_LWL, K_LWR, K_LL, K_SB, K_SH, K_SW, K_SWL, K_SWR, K_SC, MEMINSTR_WIDTH = 79 };
+static inline void mem_instr_row(const u32* e, u32* row) {
+  RowWriter w{row};
+  const u32 shard = e[0], clk = e[1], pc = e[2], next_pc = e[3], opcode = e[4] & 0xff, a = e[5], b = e[6], c = e[7], tag = e[8];
+  const u32* rec = e + 9;
+  const u32 prev_a_val = e[15];
+  w.put(pc); w.put(next_pc); w.put(shard); w.put(clk);
+  w.word(a); w.word(b); w.word(c);
+  for (u32 k = K_LB; k <= K_SC; k++) w.flag(opcode == k);
+  const u32 memory_addr = b + c;                                   // wrapping_add
+  const u32 aligned_addr = memory_addr - memory_addr % 4;
+  const u32 ls = memory_addr % 4;
+  w.word(memory_addr);
+  w.put(aligned_addr); w.put(ls);
+  w.flag(ls == 1); w.flag(ls == 2); w.flag(ls == 3);
+  w.range_checker(memory_addr);
+  // MemoryReadWriteCols::populate (memory/consistency/trace.rs:31-42): current and previous record of either kind
+  u32 cur_value, cur_shard, cur_ts, prev_value, prev_shard, prev_ts;
+  if (tag == 0) { cur_value = rec[0]; cur_shard = rec[1]; cur_ts = rec[2]; prev_value = rec[0]; prev_shard = rec[3]; prev_ts = rec[4]; }
+  else if (tag == 1) { cur_value = rec[0]; cur_shard = rec[1]; cur_ts = rec[2]; prev_value = rec[3]; prev_shard = rec[4]; prev_ts = rec[5]; }
+  else throw std::runtime_error("oracle: MemInstrEvent with a bad memory record tag");
+  w.word(prev_value);
+  w.word(cur_value);
+  w.put(prev_shard); w.put(prev_ts);
+  const bool use_clk = prev_shard == cur_shard;
+  w.flag(use_clk);
+  const u32 prev_time = use_clk ? prev_ts : prev_shard, cur_time = use_clk ? cur_ts : cur_shard;
+  const u32 diff_minus_one = cur_time - prev_time - 1;
+  w.put(diff_minus_one & 0xffff); w.put((diff_minus_one >> 16) & 0xff);
+  w.word(prev_a_val);
+  // the loaded value before sign extension
+  const u32 mem_value = cur_value;
+  unsigned char mb[4];
+  for (int i = 0; i < 4; i++) mb[i] = (unsigned char)(mem_value >> (8 * i));
+  u32 unsigned_mem_val = 0, most_sig_byte = 0, most_sig_bit = 0;
+  bool is_neg = false;
+  if (opcode >= K_LB && opcode <= K_LL) {
+    switch (opcode) {
+      case K_LB: case K_LBU: unsigned_mem_val = mb[ls]; break;
+      case K_LH: case K_LHU: unsigned_mem_val = ((ls >> 1) % 2 == 0) ? (mem_value & 0x0000FFFF) : ((mem_value & 0xFFFF0000) >> 16); break;
+      case K_LW: case K_LL: unsigned_mem_val = mem_value; break;
+      case K_LWL: {
+        const u32 val = mem_value << (24 - ls * 8), mask = 0xFFFFFFFFu << (24 - ls * 8);
+        unsigned_mem_val = (prev_a_val & ~mask) | val;
+        break;
+      }
+      case K_LWR: {
+        const u32 val = mem_value >> (ls * 8), mask = 0xFFFFFFFFu >> (ls * 8);
+        unsigned_mem_val = (prev_a_val & ~mask) | val;
+        break;
+      }
+    }
+    if (opcode == K_LB || opcode == K_LH) {
+      most_sig_byte = opcode == K_LB ? (unsigned_mem_val & 0xff) : ((unsigned_mem_val >> 8) & 0xff);
+      most_sig_bit = most_sig_byte >> 7;
+      is_neg = most_sig_bit == 1;
+    }
+  }
+  w.word(unsigned_mem_val);
+  w.put(most_sig_bit); w.put(most_sig_byte); w.flag(is_neg);
+  // IsZeroOperation::populate_from_field_element on addr_word[1] + addr_word[2] + addr_word[3] (operations/is_zero.rs)
+  const u32 upper = ((memory_addr >> 8) & 0xff) + ((memory_addr >> 16) & 0xff) + ((memory_addr >> 24) & 0xff);
+  w.put(upper ? finv(F(upper)).v : 0);
+  w.flag(upper == 0);
+  if (w.at != MEMINSTR_WIDTH) throw std::runtime_error("oracle: MemoryInstrs row width mismatch");
+}
+static inline void mem_instr_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  if (n > height) throw std::runtime_error("oracle: more events than rows");
+  for (size_t i = 0; i < height; i++) {
+    if (i < n) mem_instr_row(ev + COMP_EVENT_WORDS * i, out + i * MEMINSTR_WIDTH);
+    else for (int k = 0; k < MEMINSTR_WIDTH; k++) out[i * MEMINSTR_WIDTH + k] = 0;
   }
 }
 

@@ -122,6 +122,9 @@ fn challenger_from_words(c: &mut <SC as StarkGenericConfig>::Challenger, w: &[u3
 /// recursion records do not (their tables are uploaded as rows).
 pub trait DeviceTraceEvents {
     fn keccak_sponge_blocks(&self) -> Option<Vec<tracegen::KeccakBlock>> { None }
+    /// The chip's `#[repr(C)]` event vector as it lies in the record (tracegen.rs `EventVector`), for the chips whose
+    /// rows are one event each.
+    fn event_vector(&self, _chip: &str) -> Option<tracegen::EventVector> { None }
     fn fixed_log2_rows_of(&self, _chip: &str) -> Option<usize> { None }
 }
 impl DeviceTraceEvents for zkm_core_executor::ExecutionRecord {
@@ -129,6 +132,7 @@ impl DeviceTraceEvents for zkm_core_executor::ExecutionRecord {
         let b = tracegen::flatten_keccak_sponge_events(self);
         if b.is_empty() { None } else { Some(b) }
     }
+    fn event_vector(&self, chip: &str) -> Option<tracegen::EventVector> { tracegen::event_vector(self, chip) }
     fn fixed_log2_rows_of(&self, chip: &str) -> Option<usize> {
         self.shape.as_ref().and_then(|s| s.inner.get(chip).copied())
     }
@@ -209,6 +213,18 @@ where
                 t[i].width = tracegen::NUM_KECCAK_SPONGE_COLS;
                 t[i].flags = sys::ZKB200_TRACE_EVENTS;
                 t[i].n_events = blocks.len();
+            }
+        }
+        // The one-event-per-row chips: the record's event vector crosses as it lies (28 or 64 bytes per row instead of
+        // 4 x width), same convention - the caller left the table out as an empty matrix of the chip's width.
+        for (i, (name, m)) in traces.iter().enumerate() {
+            if !m.values.is_empty() || name == "KeccakSponge" { continue; }
+            if let Some(ev) = record.event_vector(name) {
+                assert_eq!(m.width(), ev.width, "row filler of {name} writes another width");
+                t[i].data = ev.words;
+                t[i].height = tracegen::padded_height(ev.n_events, self.fixed_log2_rows(record, name));
+                t[i].flags = sys::ZKB200_TRACE_EVENTS;
+                t[i].n_events = ev.n_events;
             }
         }
         let public_values = record.public_values::<F>();

@@ -3,8 +3,10 @@
 //! include/zkb200.h).  The table is written column-major straight into the shard's trace storage on the GPU: none of its
 //! bytes cross PCIe and no layout change runs (KeccakSponge: 1.5 KB of record per 24 rows x 3531 columns = 339 KB of rows).
 //!
-//! * ALU / control-flow chips: `AluEvent`, `BranchEvent`, `JumpEvent`, `MovCondEvent` are `#[repr(C)]` seven-word records
-//!   (crates/core/executor/src/events/instr.rs) and cross as they lie in `record.add_events` etc.
+//! * ALU / control-flow chips: `AluEvent`, `BranchEvent`, `JumpEvent`, `MovCondEvent` are `#[repr(C)]` seven-word records,
+//!   `CompAluEvent` (Mul) and `MemInstrEvent` (MemoryInstrs) sixteen-word ones (crates/core/executor/src/events/instr.rs);
+//!   they cross as they lie in `record.add_sub_events` etc. (`event_vector`).  The byte-lookup multiplicities these
+//!   chips' `event_to_row` also emits come from `generate_dependencies`, which the caller still runs on the host.
 //! * KeccakSponge: `KeccakSpongeEvent` (crates/core/executor/src/events/precompiles/keccak_sponge.rs:15-40) holds Vecs, so
 //!   it is flattened into one `zkb200_keccak_block` per absorbed block (24 rows), mirroring the block loop of
 //!   `KeccakSpongeChip::event_to_rows` (crates/core/machine/src/syscall/precompiles/keccak_sponge/trace.rs:101-196).
@@ -97,5 +99,53 @@ pub fn keccak_sponge_log_height(n_blocks: usize, fixed_log2_rows: Option<usize>)
     match fixed_log2_rows {
         Some(l) => { assert!(rows <= 1 << l, "fixed log2 rows is too small"); l }
         None => rows.next_power_of_two().trailing_zeros() as usize,
+    }
+}
+
+/// A chip's event vector as it lies in the record: `n_events` records of `words_per_event` 32-bit words.
+pub struct EventVector {
+    pub words: *const u32,
+    pub n_events: usize,
+    pub words_per_event: usize,
+    pub width: usize,
+}
+
+fn vector_of<T>(v: &[T], width: usize) -> Option<EventVector> {
+    debug_assert!(core::mem::size_of::<T>() % 4 == 0 && core::mem::align_of::<T>() == 4);
+    Some(EventVector { words: v.as_ptr() as *const u32, n_events: v.len(), words_per_event: core::mem::size_of::<T>() / 4, width })
+}
+
+// the record sizes libzkb200's row fillers read (csrc/tracegen.cuh alu_event_words)
+const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::AluEvent>() == 28);
+const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::BranchEvent>() == 28);
+const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::JumpEvent>() == 28);
+const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MovCondEvent>() == 28);
+const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::CompAluEvent>() == 64);
+const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MemInstrEvent>() == 64);
+
+/// Chip name (`MachineAir::name`) -> the record field its `generate_trace` walks, with the chip's column count
+/// (csrc/tracegen.cuh `alu_width`).
+pub fn event_vector(record: &ExecutionRecord, chip: &str) -> Option<EventVector> {
+    match chip {
+        "AddSub" => vector_of(&record.add_sub_events, 19),
+        "Bitwise" => vector_of(&record.bitwise_events, 18),
+        "Lt" => vector_of(&record.lt_events, 32),
+        "ShiftLeft" => vector_of(&record.shift_left_events, 44),
+        "ShiftRight" => vector_of(&record.shift_right_events, 67),
+        "CloClz" => vector_of(&record.cloclz_events, 17),
+        "Branch" => vector_of(&record.branch_events, 62),
+        "Jump" => vector_of(&record.jump_events, 66),
+        "MovCond" => vector_of(&record.movcond_events, 32),
+        "Mul" => vector_of(&record.mul_events, 58),
+        "MemoryInstrs" => vector_of(&record.memory_instr_events, 79),
+        _ => None,
+    }
+}
+
+/// `next_power_of_two(n, fixed_log2_rows)` of crates/core/machine/src/utils/mod.rs:101-125 (at least 16 rows).
+pub fn padded_height(n_events: usize, fixed_log2_rows: Option<usize>) -> usize {
+    match fixed_log2_rows {
+        Some(l) => { assert!(n_events <= 1 << l, "fixed log2 rows is too small"); 1 << l }
+        None => n_events.next_power_of_two().max(16),
     }
 }

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(TG_ROWS) alu_rows_kernel(const u32* __restrict
   constexpr int W = alu_width(CHIP);
   constexpr int WP = W | 1;
   constexpr int EW = alu_event_words(CHIP);
+  static_assert((size_t)TG_ROWS * (EW + WP) * sizeof(u32) <= 48 * 1024, "events and row tile must fit the static shared-memory limit");
   __shared__ u32 ev_s[TG_ROWS * EW];
   __shared__ u32 tile[TG_ROWS * WP];
   const size_t row0 = (size_t)blockIdx.x * TG_ROWS;
@@ -63,6 +64,7 @@ void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* ou
     case ALU_JUMP: alu_rows_kernel<ALU_JUMP><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     case ALU_MOVCOND: alu_rows_kernel<ALU_MOVCOND><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     case ALU_MUL: alu_rows_kernel<ALU_MUL><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_MEMINSTR: alu_rows_kernel<ALU_MEMINSTR><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     default: throw std::runtime_error("zkb200: alu_trace: unknown chip");
   }
   ZKB_CHECK_LAUNCH();
@@ -92,7 +94,7 @@ void keccak_sponge_trace(const u32* blocks_dev, size_t n_blocks, size_t height, 
 }
 
 int alu_chip_by_name(const char* name) {
-  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond", "Mul"};
+  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond", "Mul", "MemoryInstrs"};
   for (int i = 0; i < ALU_NCHIPS; i++) if (!strcmp(name, names[i])) return i;
   return -1;
 }

@@ -12,7 +12,7 @@
 namespace zkb {
 
 enum AluChip : int { ALU_ADDSUB = 0, ALU_BITWISE = 1, ALU_LT = 2, ALU_SLL = 3, ALU_SR = 4, ALU_CLOCLZ = 5, ALU_BRANCH = 6, ALU_JUMP = 7,
-                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_NCHIPS = 10 };
+                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_MEMINSTR = 10, ALU_NCHIPS = 11 };
 // opcodes as numbered by crates/core/executor/src/opcode.rs:25-49 (#[repr(u8)])
 enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_ROR = 12, OP_SLT = 13, OP_SLTU = 14,
              OP_AND = 15, OP_OR = 16, OP_XOR = 17, OP_NOR = 18, OP_CLZ = 19, OP_CLO = 20, OP_BEQ = 21, OP_BGEZ = 22, OP_BGTZ = 23,
@@ -20,10 +20,11 @@ enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_RO
 
 KB_HD constexpr int alu_width(int chip) {
   return chip == ALU_ADDSUB ? 19 : chip == ALU_BITWISE ? 18 : chip == ALU_LT ? 32 : chip == ALU_SLL ? 44 : chip == ALU_SR ? 67
-       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : 32;
+       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : chip == ALU_MEMINSTR ? 79 : 32;
 }
 // 32-bit words per event record: seven for AluEvent / BranchEvent / JumpEvent / MovCondEvent, sixteen for CompAluEvent (Mul)
-KB_HD constexpr int alu_event_words(int chip) { return chip == ALU_MUL ? 16 : 7; }
+// and MemInstrEvent (MemoryInstrs)
+KB_HD constexpr int alu_event_words(int chip) { return chip == ALU_MUL || chip == ALU_MEMINSTR ? 16 : 7; }
 
 // AluEvent as laid out by #[repr(C)]: seven 32-bit words, the opcode in the low byte of word 2
 struct AluEv { u32 pc, next_pc, opcode, hi, a, b, c; };
@@ -248,7 +249,7 @@ constexpr int MUL_WIDTH = 58, COMP_EVENT_WORDS = 16;
 enum : u32 { OP_MUL = 2, OP_MULT = 3, OP_MULTU = 4 };
 KB_HD void fill_mul(const u32* e, u32* r) {
   const u32 shard = e[0], clk = e[1], pc = e[2], next_pc = e[3], op = e[4] & 0xffu, hi = e[5], a = e[6], b = e[7], c = e[8];
-  const bool hi_real = e[15] != 0;
+  const bool hi_real = (e[15] & 0xffu) != 0;          // a Rust bool: one byte, the other three are padding
   r[0] = tg_f(pc); r[1] = tg_f(next_pc);
   tg_word(r + 2, hi); tg_word(r + 6, a); tg_word(r + 10, b); tg_word(r + 14, c);
   const bool b_ext = op == OP_MULT && (b >> 31), c_ext = op == OP_MULT && (c >> 31);
@@ -281,6 +282,52 @@ KB_HD void fill_mul(const u32* e, u32* r) {
   r[56] = hi_real ? tg_f(shard) : 0u; r[57] = hi_real ? tg_f(clk) : 0u;
 }
 
+// MemoryInstructionsChip::event_to_row, crates/core/machine/src/memory/instructions/trace.rs:103-263 (C++ twin
+// include/memory_instrs.hpp).  Event: MemInstrEvent (crates/core/executor/src/events/instr.rs:114-136) as its 16 #[repr(C)]
+// words {shard, clk, pc, next_pc, opcode, a, b, c, mem_access{tag, record}, prev_a_val}; the record is a MemoryReadRecord
+// {value, shard, timestamp, prev_shard, prev_timestamp, -} for tag 0 and a MemoryWriteRecord {value, shard, timestamp,
+// prev_value, prev_shard, prev_timestamp} for tag 1 (events/memory.rs:46-97).  Columns (79, columns.rs:15-117): pc, next_pc,
+// shard, clk, op_a[4], op_b[4], op_c[4], is_lb .. is_sc (14), addr_word[4], addr_aligned, addr_ls_two_bits, ls_bits_is_one /
+// two / three, addr_word_range_checker[14], memory_access {prev_value[4], value[4], prev_shard, prev_clk, compare_clk,
+// diff_16bit_limb, diff_8bit_limb}, prev_a_val[4], unsigned_mem_val[4], most_sig_bit, most_sig_byte, mem_value_is_neg,
+// most_sig_bytes_zero {inverse, result}.  The loaded value is one shift-and-mask per opcode family instead of byte arrays.
+constexpr int MEMINSTR_WIDTH = 79;
+enum : u32 { OP_LB = 31, OP_LBU = 32, OP_LH = 33, OP_LHU = 34, OP_LW = 35, OP_LWL = 36, OP_LWR = 37, OP_LL = 38, OP_SB = 39 };
+KB_HD void fill_mem_instr(const u32* e, u32* r) {
+  const u32 shard = e[0], clk = e[1], pc = e[2], next_pc = e[3], op = e[4] & 0xffu, a = e[5], b = e[6], c = e[7];
+  const bool is_write = e[8] != 0;
+  const u32 value = e[9], rshard = e[10], ts = e[11];
+  const u32 prev_value = is_write ? e[12] : value, prev_shard = is_write ? e[13] : e[12], prev_ts = is_write ? e[14] : e[13];
+  const u32 prev_a = e[15];
+  r[0] = tg_f(pc); r[1] = tg_f(next_pc); r[2] = tg_f(shard); r[3] = tg_f(clk);
+  tg_word(r + 4, a); tg_word(r + 8, b); tg_word(r + 12, c);
+  tg_onehot(r + 16, 14, op - OP_LB);
+  const u32 addr = b + c, ls = addr & 3u, sh = 8u * ls;
+  tg_word(r + 30, addr);
+  r[34] = tg_f(addr - ls); r[35] = tg_f(ls);
+  r[36] = tg_b(ls == 1); r[37] = tg_b(ls == 2); r[38] = tg_b(ls == 3);
+  tg_range_checker(r + 39, addr);
+  tg_word(r + 53, prev_value); tg_word(r + 57, value);
+  r[61] = tg_f(prev_shard); r[62] = tg_f(prev_ts);
+  const bool same = prev_shard == rshard;
+  r[63] = tg_b(same);
+  const u32 d = (same ? ts - prev_ts : rshard - prev_shard) - 1u;
+  r[64] = tg_f(d & 0xffffu); r[65] = tg_f((d >> 16) & 0xffu);
+  tg_word(r + 66, prev_a);
+  u32 um = 0;
+  if (op == OP_LB || op == OP_LBU) um = (value >> sh) & 0xffu;
+  else if (op == OP_LH || op == OP_LHU) um = (value >> (8u * (ls & 2u))) & 0xffffu;
+  else if (op == OP_LW || op == OP_LL) um = value;
+  else if (op == OP_LWL) um = (prev_a & ~(0xffffffffu << (24u - sh))) | (value << (24u - sh));
+  else if (op == OP_LWR) um = (prev_a & ~(0xffffffffu >> sh)) | (value >> sh);
+  tg_word(r + 70, um);
+  const u32 msbyte = op == OP_LB ? um & 0xffu : op == OP_LH ? (um >> 8) & 0xffu : 0u;
+  r[74] = tg_b(msbyte >> 7); r[75] = tg_f(msbyte); r[76] = tg_b(msbyte >> 7);
+  const u32 upper = ((addr >> 8) & 0xffu) + ((addr >> 16) & 0xffu) + (addr >> 24);
+  r[77] = upper ? fp_inv(fp_from_canonical(upper)).v : 0u;
+  r[78] = tg_b(upper == 0);
+}
+
 // Rows past the last event (generate_trace of each chip): zeros, except the dummy rows that keep the
 // shift and count-leading chips' constraints satisfied (sll/mod.rs:160-173, sr/mod.rs:184-187,
 // clo_clz/mod.rs:150-163).
@@ -304,6 +351,7 @@ KB_HD void fill_alu_row(int chip, const u32* w, u32* r, const u32* inv255) {
     case ALU_BRANCH: fill_branch(flow_event_from_words(w), r); break;
     case ALU_JUMP: fill_jump(flow_event_from_words(w), r); break;
     case ALU_MUL: fill_mul(w, r); break;
+    case ALU_MEMINSTR: fill_mem_instr(w, r); break;
     default: fill_mov_cond(w, r, inv255); break;
   }
 }

@@ -31,9 +31,11 @@ ALU_CHIPS = {
 }
 # chips whose events are CompAluEvent records of sixteen words {shard, clk, pc, next_pc, opcode, hi, a, b, c, hi_record{value,
 # shard, timestamp, prev_value, prev_shard, prev_timestamp}, hi_record_is_real} (crates/core/executor/src/events/instr.rs:47-73)
-COMP_CHIPS = {"Mul": (58, ("MUL", "MULT", "MULTU"))}
+MEM_OPCODES = ("LB", "LBU", "LH", "LHU", "LW", "LWL", "LWR", "LL", "SB", "SH", "SW", "SWL", "SWR", "SC")
+COMP_CHIPS = {"Mul": (58, ("MUL", "MULT", "MULTU")), "MemoryInstrs": (79, MEM_OPCODES)}
 COMP_EVENT_WORDS = 16
 OPCODES.update({"MUL": 2, "MULT": 3, "MULTU": 4})
+OPCODES.update({name: 31 + i for i, name in enumerate(MEM_OPCODES)})
 FLOW_CHIPS = ("Branch", "Jump")
 EVENT_WORDS = 7          # AluEvent: pc, next_pc, opcode, hi, a, b, c;  Branch/JumpEvent: pc, next_pc, next_next_pc, opcode, a, b, c;
                          # MovCondEvent: pc, next_pc, opcode, a, b, c, prev_a
@@ -225,4 +227,81 @@ def synthetic_mul_events(n: int, seed: int = 0, edges: bool = True) -> np.ndarra
     ev[:, 14] = np.where(earlier, rng.integers(0, 1 << 22, n), ev[:, 11] - rng.integers(1, 9, n)).astype(np.uint32)
     ev[:, 15] = has_hi
     ev[~has_hi, 9:15] = 0
+    return ev
+
+
+def _sext(v: np.ndarray, bits: int) -> np.ndarray:
+    v = v.astype(np.uint32)
+    sign = (v >> np.uint32(bits - 1)) & np.uint32(1)
+    return np.where(sign == 1, v | np.uint32((0xFFFFFFFF << bits) & 0xFFFFFFFF), v).astype(np.uint32)
+
+
+def synthetic_mem_instr_events(n: int, seed: int = 0, edges: bool = True) -> np.ndarray:
+    """n well-formed MemInstrEvent records of the MemoryInstrs chip as (n, 16) uint32 words, the #[repr(C)] image of
+    crates/core/executor/src/events/instr.rs:114-136: {shard, clk, pc, next_pc, opcode, a, b, c, tag, record[6], prev_a_val}.
+    Loads carry a MemoryReadRecord (tag 0: value, shard, timestamp, prev_shard, prev_timestamp, unused), stores a
+    MemoryWriteRecord (tag 1: value, shard, timestamp, prev_value, prev_shard, prev_timestamp); `a` and the stored word follow
+    execute_load / execute_store (crates/core/executor/src/executor.rs:1925-2090): halfword accesses are two-aligned, word
+    accesses (LW, LL, SW, SC) four-aligned, the address stays below the field modulus."""
+    rng = np.random.default_rng(0x4D31 + seed)
+    ev = np.zeros((n, COMP_EVENT_WORDS), np.uint32)
+    if n == 0:
+        return ev
+    shard = 3
+    O = OPCODES
+    op = rng.choice([O[o] for o in MEM_OPCODES], n).astype(np.uint32)
+    if edges:
+        op[: min(n, 4 * len(MEM_OPCODES))] = np.repeat([O[o] for o in MEM_OPCODES], 4)[: min(n, 4 * len(MEM_OPCODES))]
+    addr = rng.integers(0, 0x7F000000, n).astype(np.uint32)
+    small = rng.integers(0, 8, n) == 0                        # registers' address range: the upper three bytes are zero
+    addr = np.where(small, addr & np.uint32(0xFF), addr)
+    if edges:
+        k = min(n, 4 * len(MEM_OPCODES))
+        addr[:k] = (addr[:k] & ~np.uint32(3)) | (np.arange(k) % 4).astype(np.uint32)      # every opcode at every byte offset
+    half = np.isin(op, [O["LH"], O["LHU"], O["SH"]])
+    word = np.isin(op, [O["LW"], O["LL"], O["SW"], O["SC"]])
+    addr = np.where(half, addr & ~np.uint32(1), np.where(word, addr & ~np.uint32(3), addr)).astype(np.uint32)
+    c = _sext(rng.integers(0, 1 << 16, n).astype(np.uint32), 16)          # the sign-extended 16-bit offset
+    b = (addr - c).astype(np.uint32)
+    ls = addr & np.uint32(3)
+    sh = (np.uint32(8) * ls).astype(np.uint32)
+    mem = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)  # the aligned word before the instruction
+    rt = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)   # register a before the instruction
+    if edges:
+        k = min(n, 4 * len(MEM_OPCODES))
+        mem[:k:2] |= np.uint32(0x80808080)                                # negative bytes and halfwords
+    full = np.uint32(0xFFFFFFFF)
+    is_load = op <= O["LL"]
+    byte = (mem >> sh) & np.uint32(0xFF)
+    hw = (mem >> (np.uint32(8) * (ls & np.uint32(2)))) & np.uint32(0xFFFF)
+    s24 = (np.uint32(24) - sh).astype(np.uint32)
+    load_val = np.select(
+        [op == O["LB"], op == O["LBU"], op == O["LH"], op == O["LHU"], op == O["LW"], op == O["LL"], op == O["LWL"], op == O["LWR"]],
+        [_sext(byte, 8), byte, _sext(hw, 16), hw, mem, mem,
+         (rt & ~(full << s24)) | (mem << s24), (rt & ~(full >> sh)) | (mem >> sh)], default=0).astype(np.uint32)
+    hsh = (np.uint32(8) * (ls & np.uint32(2))).astype(np.uint32)
+    store_val = np.select(
+        [op == O["SB"], op == O["SH"], op == O["SW"], op == O["SC"], op == O["SWL"], op == O["SWR"]],
+        [(mem & (full ^ (np.uint32(0xFF) << sh))) | ((rt & np.uint32(0xFF)) << sh),
+         (mem & (full ^ (np.uint32(0xFFFF) << hsh))) | ((rt & np.uint32(0xFFFF)) << hsh),
+         rt, rt, (mem & ~(full >> s24)) | (rt >> s24), (mem & ~(full << sh)) | (rt << sh)], default=0).astype(np.uint32)
+    ev[:, 0] = shard
+    ev[:, 1] = (5 + 8 * np.arange(1, n + 1)).astype(np.uint32)
+    ev[:, 2] = rng.integers(0, kb.P - 16, n) & ~np.uint32(3)
+    ev[:, 3] = ev[:, 2] + 4
+    ev[:, 4] = op
+    ev[:, 5] = np.where(is_load, load_val, np.where(op == O["SC"], 1, rt))
+    ev[:, 6], ev[:, 7] = b, c
+    ev[:, 8] = ~is_load
+    earlier = rng.integers(0, 6, n) == 0
+    prev_shard = np.where(earlier, rng.integers(1, shard, n), shard).astype(np.uint32)
+    ts = ev[:, 1] + 1                                                     # MemoryAccessPosition::Memory
+    prev_ts = np.where(earlier, rng.integers(0, 1 << 22, n), ts - rng.integers(1, 5, n)).astype(np.uint32)
+    ev[:, 9] = np.where(is_load, mem, store_val)
+    ev[:, 10] = shard
+    ev[:, 11] = ts
+    ev[:, 12] = np.where(is_load, prev_shard, mem)
+    ev[:, 13] = np.where(is_load, prev_ts, prev_shard)
+    ev[:, 14] = np.where(is_load, 0, prev_ts)
+    ev[:, 15] = rt
     return ev
