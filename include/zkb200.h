@@ -184,7 +184,10 @@ int zkb200_grind(zkb200_ctx* ctx, const uint32_t challenger[34], unsigned bits, 
  * {value, shard, timestamp, prev_value, prev_shard, prev_timestamp}, hi_record_is_real} (instr.rs:47-73).  "MemoryInstrs"
  * (crates/core/machine/src/memory/instructions/trace.rs:103-263, C++ twin include/memory_instrs.hpp; 79 columns) takes 64-byte
  * `MemInstrEvent` records {shard, clk, pc, next_pc, opcode, a, b, c, mem_access {tag: 0 Read / 1 Write, record: six words},
- * prev_a_val} (instr.rs:114-136, events/memory.rs:46-97).  `out` is DEVICE memory of
+ * prev_a_val} (instr.rs:114-136, events/memory.rs:46-97).  "MemoryLocal" (crates/core/machine/src/memory/local.rs:146-190, C++
+ * twin include/memory_local.hpp; 56 columns) takes 28-byte `MemoryLocalEvent` records {addr, initial_mem_access {shard,
+ * timestamp, value}, final_mem_access {shard, timestamp, value}} (events/memory.rs:228-237) and packs FOUR events into a row:
+ * n_events may be up to 4 * 2^log_height.  `out` is DEVICE memory of
  * 2^log_height x width words, Montgomery, row-major (col_major = 0: the RowMajorMatrix layout
  * zkb200_commit takes) or column-major (col_major = 1: the layout of the kernel-level entry points). */
 typedef struct {

@@ -271,6 +271,13 @@ int zko_mem_instr_trace(const u32* ev, size_t n, size_t height, u32* out) {
     return 0;
   } catch (const std::exception& e) { return fail(e); }
 }
+// MemoryLocal rows (tracegen.h): events n x 7 words (MemoryLocalEvent), four per row, out height x 56 row-major canonical
+int zko_memory_local_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  try {
+    memory_local_trace(ev, n, height, out);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
 // trace generation of the KeccakSponge chip (tracegen_keccak.h): n_blocks records of KS_REC_WORDS words,
 // out height x 3531 row-major canonical
 int zko_keccak_sponge_width() { return KS_WIDTH; }

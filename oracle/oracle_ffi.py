@@ -139,6 +139,31 @@ def ref_mem_instr_rows(events):
     return out
 
 
+MEMLOCAL_WIDTH, MEMLOCAL_ENTRY_WIDTH = 56, 14
+
+
+def memory_local_trace(events, height):
+    """events: (n, 7) uint32 MemoryLocalEvent records, four per row; (height, 56) canonical rows of the MemoryLocal chip."""
+    ev = _a(events).reshape(-1, 7)
+    out = np.zeros((int(height), MEMLOCAL_WIDTH), np.uint32)
+    if lib().zko_memory_local_trace(_p(ev), C.c_size_t(ev.shape[0]), C.c_size_t(int(height)), _p(out)):
+        raise RuntimeError(err())
+    return out
+
+
+def ref_memory_local_entries(events):
+    """One SingleMemoryLocal (14 Montgomery words) per event from the reference's own memory_local.hpp, or None without
+    oracle/_ref."""
+    l = ref_core_lib()
+    if l is None or not hasattr(l, "ref_memory_local_entries"):
+        return None
+    ev = _a(events).reshape(-1, 7)
+    out = np.zeros((ev.shape[0], MEMLOCAL_ENTRY_WIDTH), np.uint32)
+    if l.ref_memory_local_entries(_p(ev), C.c_size_t(ev.shape[0]), _p(out)):
+        raise RuntimeError("reference row filler failed")
+    return out
+
+
 KS_WIDTH, KS_REC_WORDS = 3531, 384
 
 

@@ -18,6 +18,7 @@
 #include "memory.hpp"
 #include "mul.hpp"
 #include "memory_instrs.hpp"
+#include "memory_local.hpp"
 
 using namespace zkm_core_machine_sys;
 
@@ -125,6 +126,19 @@ int ref_mem_instr_event_to_rows(const uint32_t* ev, size_t n, uint32_t* rows) {
     }
     m.prev_a_val = e[15];
     memory_instrs::event_to_row<kb31_t>(m, *reinterpret_cast<MemoryInstructionsColumns<kb31_t>*>(rows + i * w));
+  }
+  return 0;
+}
+// One SingleMemoryLocal entry (14 Montgomery words) per MemoryLocalEvent (seven words: addr, initial {shard, timestamp,
+// value}, final {shard, timestamp, value}) through the reference's memory_local.hpp
+int ref_memory_local_entries(const uint32_t* ev, size_t n, uint32_t* out) {
+  static_assert(sizeof(MemoryLocalEvent) == 7 * sizeof(uint32_t), "MemoryLocalEvent is seven words");
+  static_assert(sizeof(SingleMemoryLocal<kb31_t>) == 14 * sizeof(uint32_t), "SingleMemoryLocal is fourteen field elements");
+  std::memset(out, 0, n * 14 * sizeof(uint32_t));
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t* e = ev + 7 * i;
+    MemoryLocalEvent m{e[0], MemoryRecord{e[1], e[2], e[3]}, MemoryRecord{e[4], e[5], e[6]}};
+    memory_local::event_to_row<kb31_t, kb31_septic_extension_t>(&m, reinterpret_cast<SingleMemoryLocal<kb31_t>*>(out + 14 * i));
   }
   return 0;
 }

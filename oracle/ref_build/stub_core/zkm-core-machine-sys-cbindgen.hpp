@@ -216,4 +216,14 @@ template <class T> struct MemoryInstructionsColumns {
   IsZeroOperation<T> most_sig_bytes_zero;
 };
 
+// ---- MemoryLocal (crates/core/machine/include/memory_local.hpp) ----
+// crates/core/executor/src/events/memory.rs:228-237 (#[repr(C)])
+struct MemoryLocalEvent { uint32_t addr; MemoryRecord initial_mem_access; MemoryRecord final_mem_access; };
+// crates/core/machine/src/memory/local.rs:29-55 (SingleMemoryLocal)
+template <class T> struct SingleMemoryLocal {
+  T addr, initial_shard, final_shard, initial_clk, final_clk;
+  Word<T> initial_value, final_value;
+  T is_real;
+};
+
 }  // namespace zkm_core_machine_sys

@@ -361,4 +361,31 @@ static inline void mem_instr_trace(const u32* ev, size_t n, size_t height, u32* 
   }
 }
 
+// ---- MemoryLocal (crates/core/machine/src/memory/local.rs:146-190; C++ twin of one entry include/memory_local.hpp) -----
+// MemoryLocalEvent (crates/core/executor/src/events/memory.rs:228-237) as seven words: addr, initial_mem_access {shard,
+// timestamp, value}, final_mem_access {shard, timestamp, value}.  Four events per row (NUM_LOCAL_MEMORY_ENTRIES_PER_ROW);
+// SingleMemoryLocal (local.rs:29-55): addr, initial_shard, final_shard, initial_clk, final_clk, initial_value[4],
+// final_value[4], is_real.  Entries and rows past the last event are zero.
+enum { MEMLOCAL_ENTRIES = 4, MEMLOCAL_ENTRY_WIDTH = 14, MEMLOCAL_WIDTH = 56, MEMLOCAL_EVENT_WORDS = 7 };
+static inline void memory_local_entry(const u32* e, u32* cols) {
+  RowWriter w{cols};
+  const u32 addr = e[0], i_shard = e[1], i_ts = e[2], i_value = e[3], f_shard = e[4], f_ts = e[5], f_value = e[6];
+  w.put(addr);
+  w.put(i_shard); w.put(f_shard);
+  w.put(i_ts); w.put(f_ts);
+  w.word(i_value); w.word(f_value);
+  w.flag(true);
+  if (w.at != MEMLOCAL_ENTRY_WIDTH) throw std::runtime_error("oracle: MemoryLocal entry width mismatch");
+}
+static inline void memory_local_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  const size_t nb_rows = (n + MEMLOCAL_ENTRIES - 1) / MEMLOCAL_ENTRIES;
+  if (nb_rows > height) throw std::runtime_error("oracle: more events than rows");
+  for (size_t i = 0; i < height * MEMLOCAL_WIDTH; i++) out[i] = 0;
+  for (size_t row = 0; row < nb_rows; row++)
+    for (size_t k = 0; k < MEMLOCAL_ENTRIES; k++) {
+      const size_t idx = row * MEMLOCAL_ENTRIES + k;
+      if (idx < n) memory_local_entry(ev + MEMLOCAL_EVENT_WORDS * idx, out + row * MEMLOCAL_WIDTH + k * MEMLOCAL_ENTRY_WIDTH);
+    }
+}
+
 }  // namespace zko

@@ -125,6 +125,9 @@ pub trait DeviceTraceEvents {
     /// The chip's `#[repr(C)]` event vector as it lies in the record (tracegen.rs `EventVector`), for the chips whose
     /// rows are one event each.
     fn event_vector(&self, _chip: &str) -> Option<tracegen::EventVector> { None }
+    /// MemoryLocal: the shard's local memory events gathered into one vector (the record keeps them in several places,
+    /// `ExecutionRecord::get_local_mem_events`), four to a row.
+    fn memory_local_events(&self) -> Option<Vec<zkm_core_executor::events::MemoryLocalEvent>> { None }
     fn fixed_log2_rows_of(&self, _chip: &str) -> Option<usize> { None }
 }
 impl DeviceTraceEvents for zkm_core_executor::ExecutionRecord {
@@ -133,6 +136,9 @@ impl DeviceTraceEvents for zkm_core_executor::ExecutionRecord {
         if b.is_empty() { None } else { Some(b) }
     }
     fn event_vector(&self, chip: &str) -> Option<tracegen::EventVector> { tracegen::event_vector(self, chip) }
+    fn memory_local_events(&self) -> Option<Vec<zkm_core_executor::events::MemoryLocalEvent>> {
+        Some(self.get_local_mem_events().copied().collect())
+    }
     fn fixed_log2_rows_of(&self, chip: &str) -> Option<usize> {
         self.shape.as_ref().and_then(|s| s.inner.get(chip).copied())
     }
@@ -226,6 +232,16 @@ where
                 t[i].flags = sys::ZKB200_TRACE_EVENTS;
                 t[i].n_events = ev.n_events;
             }
+        }
+        // MemoryLocal: four seven-word events per row, gathered from the record's local-memory iterators
+        let local_events = traces.iter().position(|(n, m)| n == "MemoryLocal" && m.values.is_empty())
+            .and_then(|i| record.memory_local_events().map(|v| (i, v)));
+        if let Some((i, ev)) = local_events.as_ref() {
+            const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MemoryLocalEvent>() == 28);
+            t[*i].data = ev.as_ptr() as *const u32;
+            t[*i].height = tracegen::padded_height(ev.len().div_ceil(tracegen::MEMORY_LOCAL_ENTRIES_PER_ROW), self.fixed_log2_rows(record, "MemoryLocal"));
+            t[*i].flags = sys::ZKB200_TRACE_EVENTS;
+            t[*i].n_events = ev.len();
         }
         let public_values = record.public_values::<F>();
         let pv: Vec<u32> = public_values.iter().map(|v| v.as_canonical_u32()).collect();

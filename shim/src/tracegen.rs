@@ -7,6 +7,9 @@
 //!   `CompAluEvent` (Mul) and `MemInstrEvent` (MemoryInstrs) sixteen-word ones (crates/core/executor/src/events/instr.rs);
 //!   they cross as they lie in `record.add_sub_events` etc. (`event_vector`).  The byte-lookup multiplicities these
 //!   chips' `event_to_row` also emits come from `generate_dependencies`, which the caller still runs on the host.
+//! * MemoryLocal: seven-word `MemoryLocalEvent` records (crates/core/executor/src/events/memory.rs:228-237), four to a row;
+//!   the record keeps them in several vectors (`get_local_mem_events`), so they are gathered into one (28 bytes per event
+//!   against 224 bytes per row of four).
 //! * KeccakSponge: `KeccakSpongeEvent` (crates/core/executor/src/events/precompiles/keccak_sponge.rs:15-40) holds Vecs, so
 //!   it is flattened into one `zkb200_keccak_block` per absorbed block (24 rows), mirroring the block loop of
 //!   `KeccakSpongeChip::event_to_rows` (crates/core/machine/src/syscall/precompiles/keccak_sponge/trace.rs:101-196).
@@ -141,6 +144,9 @@ pub fn event_vector(record: &ExecutionRecord, chip: &str) -> Option<EventVector>
         _ => None,
     }
 }
+
+/// NUM_LOCAL_MEMORY_ENTRIES_PER_ROW (crates/core/machine/src/memory/local.rs:26)
+pub const MEMORY_LOCAL_ENTRIES_PER_ROW: usize = 4;
 
 /// `next_power_of_two(n, fixed_log2_rows)` of crates/core/machine/src/utils/mod.rs:101-125 (at least 16 rows).
 pub fn padded_height(n_events: usize, fixed_log2_rows: Option<usize>) -> usize {

@@ -63,13 +63,15 @@ void hostcheck_efacc(const uint32_t* w, const uint32_t* x, size_t n, uint32_t* o
 // the product's ALU row fillers (csrc/tracegen.cuh) on the host: events n x 7 words, out height x width
 // row-major Montgomery, padding rows past the last event
 int hostcheck_alu_rows(int chip, const uint32_t* ev, size_t n, size_t height, uint32_t* out) {
-  if (chip < 0 || chip >= ALU_NCHIPS || n > height) return 1;
+  if (chip < 0 || chip >= ALU_NCHIPS) return 1;
+  const size_t epr = (size_t)alu_events_per_row(chip);
+  if ((n + epr - 1) / epr > height) return 1;
   static u32 inv255[256];
   static bool init = false;
   if (!init) { alu_build_inv255(inv255); init = true; }
   const int w = alu_width(chip);
   for (size_t i = 0; i < height; i++) {
-    if (i < n) fill_alu_row(chip, ev + (size_t)alu_event_words(chip) * i, out + i * w, inv255);
+    if (i * epr < n) fill_alu_row(chip, ev + (size_t)alu_event_words(chip) * epr * i, out + i * w, inv255, (int)(n - i * epr < epr ? n - i * epr : epr));
     else fill_alu_padding(chip, out + i * w);
   }
   return 0;

@@ -325,7 +325,8 @@ int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* eve
     if (id < 0) throw std::runtime_error(std::string("zkb200: generate_alu_trace: no row filler for chip ") + chip);
     if (log_height > 30) throw std::runtime_error("zkb200: generate_alu_trace: log_height out of range");
     const size_t height = (size_t)1 << log_height;
-    if (n_events > height) throw std::runtime_error("zkb200: generate_alu_trace: more events than rows (fixed log2 rows is too small)");
+    if (ceil_div(n_events, (size_t)alu_events_per_row(id)) > height)
+      throw std::runtime_error("zkb200: generate_alu_trace: more events than rows (fixed log2 rows is too small)");
     std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
     cudaStream_t s = ctx->c.lanes[0].stream;

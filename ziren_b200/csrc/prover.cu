@@ -382,11 +382,12 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     if ((t.flags & ~(TRACE_EVENTS | TRACE_COL_MAJOR)) || (t.flags & (TRACE_EVENTS | TRACE_COL_MAJOR)) == (TRACE_EVENTS | TRACE_COL_MAJOR))
       throw std::runtime_error("zkb200: commit: bad zkb200_trace.flags for " + t.name);
     if (t.flags & TRACE_EVENTS) {
-      const size_t rows_per_event = t.name == "KeccakSponge" ? KS_ROUNDS : 1;
+      const size_t rows_needed = t.name == "KeccakSponge" ? t.n_events * KS_ROUNDS
+                                                          : ceil_div(t.n_events, (size_t)alu_events_per_row(alu_chip_by_name(t.name.c_str())));
       event_record_words(t.name);       // throws for a chip without a row filler
       const size_t w = t.name == "KeccakSponge" ? (size_t)KS_WIDTH : (size_t)alu_width(alu_chip_by_name(t.name.c_str()));
       if (w != t.width) throw std::runtime_error("zkb200: commit: the row filler of " + t.name + " writes another width");
-      if (t.n_events * rows_per_event > t.height) throw std::runtime_error("zkb200: commit: more event rows than the table holds: " + t.name);
+      if (rows_needed > t.height) throw std::runtime_error("zkb200: commit: more event rows than the table holds: " + t.name);
     } else if ((t.flags & TRACE_COL_MAJOR) && t.height * t.width && !is_device_pointer(t.data))
       throw std::runtime_error("zkb200: commit: ZKB200_TRACE_COL_MAJOR needs a device pointer: " + t.name);
     group_size[logn[i]]++;

@@ -24,16 +24,20 @@ __global__ void __launch_bounds__(TG_ROWS) alu_rows_kernel(const u32* __restrict
   constexpr int W = alu_width(CHIP);
   constexpr int WP = W | 1;
   constexpr int EW = alu_event_words(CHIP);
-  static_assert((size_t)TG_ROWS * (EW + WP) * sizeof(u32) <= 48 * 1024, "events and row tile must fit the static shared-memory limit");
-  __shared__ u32 ev_s[TG_ROWS * EW];
+  constexpr int EPR = alu_events_per_row(CHIP);
+  constexpr int RW = EW * EPR;                    // event words per row
+  static_assert((size_t)TG_ROWS * (RW + WP) * sizeof(u32) <= 48 * 1024, "events and row tile must fit the static shared-memory limit");
+  __shared__ u32 ev_s[TG_ROWS * RW];
   __shared__ u32 tile[TG_ROWS * WP];
   const size_t row0 = (size_t)blockIdx.x * TG_ROWS;
-  // the CTA's events are EW * 128 consecutive words: coalesced load, then one record per thread
-  const size_t ev_words = row0 < n ? (n - row0 < TG_ROWS ? (n - row0) * EW : (size_t)TG_ROWS * EW) : 0;
-  for (u32 i = threadIdx.x; i < ev_words; i += TG_ROWS) ev_s[i] = events[row0 * EW + i];
+  // the CTA's events are at most RW * 128 consecutive words: coalesced load, then one row's records per thread
+  const size_t e0 = row0 * EPR;
+  const size_t ev_words = e0 < n ? (n - e0 < (size_t)TG_ROWS * EPR ? (n - e0) * EW : (size_t)TG_ROWS * RW) : 0;
+  for (u32 i = threadIdx.x; i < ev_words; i += TG_ROWS) ev_s[i] = events[e0 * EW + i];
   __syncthreads();
   u32* r = tile + threadIdx.x * WP;
-  if (row0 + threadIdx.x < n) fill_alu_row(CHIP, ev_s + EW * threadIdx.x, r, d_inv255);
+  const size_t first = (row0 + threadIdx.x) * EPR;          // the row's first event
+  if (first < n) fill_alu_row(CHIP, ev_s + RW * threadIdx.x, r, d_inv255, n - first < (size_t)EPR ? (int)(n - first) : EPR);
   else fill_alu_padding(CHIP, r);
   __syncthreads();
   const size_t rows = height - row0 < TG_ROWS ? height - row0 : TG_ROWS;
@@ -50,7 +54,7 @@ __global__ void __launch_bounds__(TG_ROWS) alu_rows_kernel(const u32* __restrict
 
 void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* out, bool col_major, cudaStream_t s) {
   if (!height) return;
-  if (n > height) throw std::runtime_error("zkb200: alu_trace: more events than rows");
+  if (ceil_div(n, (size_t)alu_events_per_row(chip)) > height) throw std::runtime_error("zkb200: alu_trace: more events than rows");
   const unsigned grid = ceil_div(height, TG_ROWS);
   const int cm = col_major ? 1 : 0;
   switch (chip) {
@@ -65,6 +69,7 @@ void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* ou
     case ALU_MOVCOND: alu_rows_kernel<ALU_MOVCOND><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     case ALU_MUL: alu_rows_kernel<ALU_MUL><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     case ALU_MEMINSTR: alu_rows_kernel<ALU_MEMINSTR><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_MEMLOCAL: alu_rows_kernel<ALU_MEMLOCAL><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     default: throw std::runtime_error("zkb200: alu_trace: unknown chip");
   }
   ZKB_CHECK_LAUNCH();
@@ -94,7 +99,7 @@ void keccak_sponge_trace(const u32* blocks_dev, size_t n_blocks, size_t height, 
 }
 
 int alu_chip_by_name(const char* name) {
-  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond", "Mul", "MemoryInstrs"};
+  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond", "Mul", "MemoryInstrs", "MemoryLocal"};
   for (int i = 0; i < ALU_NCHIPS; i++) if (!strcmp(name, names[i])) return i;
   return -1;
 }

@@ -12,7 +12,7 @@
 namespace zkb {
 
 enum AluChip : int { ALU_ADDSUB = 0, ALU_BITWISE = 1, ALU_LT = 2, ALU_SLL = 3, ALU_SR = 4, ALU_CLOCLZ = 5, ALU_BRANCH = 6, ALU_JUMP = 7,
-                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_MEMINSTR = 10, ALU_NCHIPS = 11 };
+                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_MEMINSTR = 10, ALU_MEMLOCAL = 11, ALU_NCHIPS = 12 };
 // opcodes as numbered by crates/core/executor/src/opcode.rs:25-49 (#[repr(u8)])
 enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_ROR = 12, OP_SLT = 13, OP_SLTU = 14,
              OP_AND = 15, OP_OR = 16, OP_XOR = 17, OP_NOR = 18, OP_CLZ = 19, OP_CLO = 20, OP_BEQ = 21, OP_BGEZ = 22, OP_BGTZ = 23,
@@ -20,11 +20,13 @@ enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_RO
 
 KB_HD constexpr int alu_width(int chip) {
   return chip == ALU_ADDSUB ? 19 : chip == ALU_BITWISE ? 18 : chip == ALU_LT ? 32 : chip == ALU_SLL ? 44 : chip == ALU_SR ? 67
-       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : chip == ALU_MEMINSTR ? 79 : 32;
+       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : chip == ALU_MEMINSTR ? 79 : chip == ALU_MEMLOCAL ? 56 : 32;
 }
 // 32-bit words per event record: seven for AluEvent / BranchEvent / JumpEvent / MovCondEvent, sixteen for CompAluEvent (Mul)
 // and MemInstrEvent (MemoryInstrs)
 KB_HD constexpr int alu_event_words(int chip) { return chip == ALU_MUL || chip == ALU_MEMINSTR ? 16 : 7; }
+// events per row: MemoryLocal packs four seven-word MemoryLocalEvents into a row, every other chip has one event per row
+KB_HD constexpr int alu_events_per_row(int chip) { return chip == ALU_MEMLOCAL ? 4 : 1; }
 
 // AluEvent as laid out by #[repr(C)]: seven 32-bit words, the opcode in the low byte of word 2
 struct AluEv { u32 pc, next_pc, opcode, hi, a, b, c; };
@@ -328,6 +330,28 @@ KB_HD void fill_mem_instr(const u32* e, u32* r) {
   r[78] = tg_b(upper == 0);
 }
 
+// MemoryLocalChip::generate_trace, crates/core/machine/src/memory/local.rs:146-190 (C++ twin include/memory_local.hpp, one
+// entry).  Event: MemoryLocalEvent (crates/core/executor/src/events/memory.rs:228-237) as its seven #[repr(C)] words {addr,
+// initial_mem_access{shard, timestamp, value}, final_mem_access{shard, timestamp, value}}; FOUR events per row
+// (NUM_LOCAL_MEMORY_ENTRIES_PER_ROW), event 4 i + k in entry k of row i.  Entry columns (14, local.rs:29-55): addr,
+// initial_shard, final_shard, initial_clk, final_clk, initial_value[4], final_value[4], is_real; entries past the last event
+// are zero.
+constexpr int MEMLOCAL_ENTRIES = 4, MEMLOCAL_ENTRY_WIDTH = 14;
+KB_HD void fill_memory_local(const u32* e, int n_valid, u32* r) {
+#pragma unroll
+  for (int k = 0; k < MEMLOCAL_ENTRIES; k++, e += 7, r += MEMLOCAL_ENTRY_WIDTH) {
+    if (k < n_valid) {
+      r[0] = tg_f(e[0]);
+      r[1] = tg_f(e[1]); r[2] = tg_f(e[4]);
+      r[3] = tg_f(e[2]); r[4] = tg_f(e[5]);
+      tg_word(r + 5, e[3]); tg_word(r + 9, e[6]);
+      r[13] = KB_ONE;
+    } else {
+      for (int i = 0; i < MEMLOCAL_ENTRY_WIDTH; i++) r[i] = 0;
+    }
+  }
+}
+
 // Rows past the last event (generate_trace of each chip): zeros, except the dummy rows that keep the
 // shift and count-leading chips' constraints satisfied (sll/mod.rs:160-173, sr/mod.rs:184-187,
 // clo_clz/mod.rs:150-163).
@@ -339,8 +363,9 @@ KB_HD void fill_alu_padding(int chip, u32* r) {
   if (chip == ALU_CLOCLZ) { tg_word(r + 2, 32); r[14] = KB_ONE; }
 }
 
-// w: the event's seven words as they lie in the record's event vector
-KB_HD void fill_alu_row(int chip, const u32* w, u32* r, const u32* inv255) {
+// w: the row's event words as they lie in the record's event vector (alu_events_per_row x alu_event_words of them, the first
+// n_valid events present)
+KB_HD void fill_alu_row(int chip, const u32* w, u32* r, const u32* inv255, int n_valid = 1) {
   switch (chip) {
     case ALU_ADDSUB: fill_add_sub(alu_event_from_words(w), r); break;
     case ALU_BITWISE: fill_bitwise(alu_event_from_words(w), r); break;
@@ -352,6 +377,7 @@ KB_HD void fill_alu_row(int chip, const u32* w, u32* r, const u32* inv255) {
     case ALU_JUMP: fill_jump(flow_event_from_words(w), r); break;
     case ALU_MUL: fill_mul(w, r); break;
     case ALU_MEMINSTR: fill_mem_instr(w, r); break;
+    case ALU_MEMLOCAL: fill_memory_local(w, n_valid, r); break;
     default: fill_mov_cond(w, r, inv255); break;
   }
 }

@@ -42,16 +42,28 @@ EVENT_WORDS = 7          # AluEvent: pc, next_pc, opcode, hi, a, b, c;  Branch/J
 EVENT_BYTES = 28
 
 
+PACKED_CHIPS = {"MemoryLocal": (56, 4)}       # width, events per row (seven-word MemoryLocalEvent records)
+
+
 def width(chip: str) -> int:
+    if chip in PACKED_CHIPS:
+        return PACKED_CHIPS[chip][0]
     return (ALU_CHIPS.get(chip) or COMP_CHIPS[chip])[0]
+
+
+def events_per_row(chip: str) -> int:
+    return PACKED_CHIPS[chip][1] if chip in PACKED_CHIPS else 1
 
 
 def event_words(chip: str) -> int:
     return COMP_EVENT_WORDS if chip in COMP_CHIPS else EVENT_WORDS
 
 
-def padded_log_height(n_events: int, fixed_log2_rows: int | None = None) -> int:
-    """`next_power_of_two(n, fixed_log2_rows)`: at least 16 rows, or the shape's fixed height."""
+def padded_log_height(n_events: int, fixed_log2_rows: int | None = None, chip: str | None = None) -> int:
+    """`next_power_of_two(n, fixed_log2_rows)`: at least 16 rows, or the shape's fixed height.  `chip`: a chip that packs
+    several events into a row (MemoryLocal) needs ceil(n / events_per_row) rows."""
+    if chip is not None:
+        n_events = -(-n_events // events_per_row(chip))
     if fixed_log2_rows is not None:
         if n_events > (1 << fixed_log2_rows):
             raise ValueError(f"fixed log2 rows is too small: got {n_events}, expected {1 << fixed_log2_rows}")
@@ -304,4 +316,25 @@ def synthetic_mem_instr_events(n: int, seed: int = 0, edges: bool = True) -> np.
     ev[:, 13] = np.where(is_load, prev_ts, prev_shard)
     ev[:, 14] = np.where(is_load, 0, prev_ts)
     ev[:, 15] = rt
+    return ev
+
+
+def synthetic_memory_local_events(n: int, seed: int = 0, shard: int = 3) -> np.ndarray:
+    """n MemoryLocalEvent records as (n, 7) uint32 words {addr, initial {shard, timestamp, value}, final {shard, timestamp,
+    value}} (crates/core/executor/src/events/memory.rs:228-237): distinct word-aligned addresses (registers included), the
+    initial access in an earlier shard (or shard 0, clk 0 for untouched memory), the final one in this shard."""
+    rng = np.random.default_rng(0x10CA1 + seed)
+    ev = np.zeros((n, EVENT_WORDS), np.uint32)
+    if n == 0:
+        return ev
+    addr = rng.choice(1 << 22, n, replace=False).astype(np.uint32) * np.uint32(4)
+    addr[: min(n, 36)] = np.arange(min(n, 36), dtype=np.uint32)           # the register file
+    untouched = rng.integers(0, 3, n) == 0
+    ev[:, 0] = addr
+    ev[:, 1] = np.where(untouched, 0, rng.integers(1, shard + 1, n))
+    ev[:, 2] = np.where(untouched, 0, rng.integers(1, 1 << 22, n))
+    ev[:, 3] = np.where(untouched, 0, rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32))
+    ev[:, 4] = shard
+    ev[:, 5] = rng.integers(1 << 22, 1 << 23, n)
+    ev[:, 6] = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
     return ev
