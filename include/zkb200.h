@@ -200,9 +200,28 @@ typedef struct {
   uint8_t opcode;
   uint32_t a, b, c;
 } zkb200_flow_event;     /* BranchEvent / JumpEvent */
+/* "Cpu" (crates/core/machine/src/cpu/trace.rs:45-246, C++ twin include/cpu.hpp behind cpu_event_to_row_koalabear(CpuEventFfi,
+ * shard, InstructionFfi), cpp/extern.cpp:6-14; 67 columns, cpu/columns/mod.rs:18-84).  CpuEvent
+ * (crates/core/executor/src/events/cpu.rs:15-44) holds Options and the instruction is fetched from the program, so the host
+ * writes one flat 112-byte record per event holding what the row needs of the event, of `program.fetch(event.pc)` and the
+ * shard number:
+ *   flags     bit 0: hi is Some; bits 1-2: a_record 0 None / 1 Read / 2 Write; bit 3: b_record is Some(Read); bit 4: c_record
+ *             is Some(Read); bit 5: instruction.imm_b; bit 6: instruction.imm_c
+ *   op_word   instruction.opcode | instruction.op_a << 8 | public_values.execution_shard << 16
+ *   a_record  the MemoryRecordEnum payload as it lies: Read {value, shard, timestamp, prev_shard, prev_timestamp, -},
+ *             Write {value, shard, timestamp, prev_value, prev_shard, prev_timestamp} (events/memory.rs:46-82)
+ *   b_record, c_record   MemoryReadRecord {value, shard, timestamp, prev_shard, prev_timestamp}
+ * Rows past the last event are the chip's padding rows (imm_b = imm_c = is_rw_a = 1, trace.rs:60-63). */
+typedef struct {
+  uint32_t clk, pc, next_pc, next_next_pc, a, b, c, hi;
+  uint32_t flags, op_word, op_b, op_c;
+  uint32_t a_record[6], b_record[5], c_record[5];
+} zkb200_cpu_event;
 /* NUM_*_COLS of the chip, -1 if this library has no row filler for it */
 int zkb200_alu_trace_width(const char* chip);
-/* events: zkb200_alu_event[]; zkb200_flow_event[] for "Branch" / "Jump"; seven-word MovCondEvent records for "MovCond" */
+/* events: zkb200_alu_event[]; zkb200_flow_event[] for "Branch" / "Jump"; seven-word MovCondEvent records for "MovCond";
+ * CompAluEvent / MemInstrEvent / MemoryLocalEvent records as they lie for "Mul" / "MemoryInstrs" / "MemoryLocal";
+ * zkb200_cpu_event[] for "Cpu" */
 int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* events, size_t n_events,
                               unsigned log_height, uint32_t* out, int col_major);
 /* MachineAir::generate_trace of the KeccakSponge precompile chip

@@ -278,6 +278,13 @@ int zko_memory_local_trace(const u32* ev, size_t n, size_t height, u32* out) {
     return 0;
   } catch (const std::exception& e) { return fail(e); }
 }
+// Cpu rows (tracegen.h): events n x 28 words (zkb200_cpu_event), out height x 67 row-major canonical
+int zko_cpu_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  try {
+    cpu_trace(ev, n, height, out);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
 // trace generation of the KeccakSponge chip (tracegen_keccak.h): n_blocks records of KS_REC_WORDS words,
 // out height x 3531 row-major canonical
 int zko_keccak_sponge_width() { return KS_WIDTH; }

@@ -164,6 +164,30 @@ def ref_memory_local_entries(events):
     return out
 
 
+CPU_WIDTH, CPU_EVENT_WORDS = 67, 28
+
+
+def cpu_trace(events, height):
+    """events: (n, 28) uint32 zkb200_cpu_event records; (height, 67) canonical rows of the Cpu chip."""
+    ev = _a(events).reshape(-1, CPU_EVENT_WORDS)
+    out = np.zeros((int(height), CPU_WIDTH), np.uint32)
+    if lib().zko_cpu_trace(_p(ev), C.c_size_t(ev.shape[0]), C.c_size_t(int(height)), _p(out)):
+        raise RuntimeError(err())
+    return out
+
+
+def ref_cpu_rows(events):
+    """Rows of the reference's own cpu.hpp event_to_row (Montgomery words), or None without oracle/_ref."""
+    l = ref_core_lib()
+    if l is None or not hasattr(l, "ref_cpu_event_to_rows"):
+        return None
+    ev = _a(events).reshape(-1, CPU_EVENT_WORDS)
+    out = np.zeros((ev.shape[0], CPU_WIDTH), np.uint32)
+    if l.ref_cpu_event_to_rows(_p(ev), C.c_size_t(ev.shape[0]), _p(out)):
+        raise RuntimeError("reference row filler failed")
+    return out
+
+
 KS_WIDTH, KS_REC_WORDS = 3531, 384
 
 

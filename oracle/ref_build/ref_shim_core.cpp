@@ -19,6 +19,7 @@
 #include "mul.hpp"
 #include "memory_instrs.hpp"
 #include "memory_local.hpp"
+#include "cpu.hpp"
 
 using namespace zkm_core_machine_sys;
 
@@ -139,6 +140,39 @@ int ref_memory_local_entries(const uint32_t* ev, size_t n, uint32_t* out) {
     const uint32_t* e = ev + 7 * i;
     MemoryLocalEvent m{e[0], MemoryRecord{e[1], e[2], e[3]}, MemoryRecord{e[4], e[5], e[6]}};
     memory_local::event_to_row<kb31_t, kb31_septic_extension_t>(&m, reinterpret_cast<SingleMemoryLocal<kb31_t>*>(out + 14 * i));
+  }
+  return 0;
+}
+// Cpu rows of the reference's cpu.hpp: events n x 28 words (include/zkb200.h zkb200_cpu_event: clk, pc, next_pc, next_next_pc,
+// a, b, c, hi, flags, opcode | op_a << 8 | shard << 16, op_b, op_c, a_record[6], b_record[5], c_record[5]) unpacked into the
+// CpuEventFfi / InstructionFfi / shard arguments of cpu_event_to_row_koalabear (cpp/extern.cpp:6-14); rows n x 67 Montgomery words
+static OptionMemoryRecordEnum option_record(unsigned kind, const uint32_t* r) {
+  OptionMemoryRecordEnum o;
+  std::memset(&o, 0, sizeof(o));
+  o.tag = kind == 1 ? OptionMemoryRecordEnumTag::Read : kind == 2 ? OptionMemoryRecordEnumTag::Write : OptionMemoryRecordEnumTag::None;
+  if (kind == 1) o.read = MemoryReadRecord{r[0], r[1], r[2], r[3], r[4]};
+  if (kind == 2) o.write = MemoryWriteRecord{r[0], r[1], r[2], r[3], r[4], r[5]};
+  return o;
+}
+unsigned ref_cpu_num_cols() { return ncols<CpuCols<kb31_t>>(); }
+int ref_cpu_event_to_rows(const uint32_t* ev, size_t n, uint32_t* rows) {
+  const unsigned w = ref_cpu_num_cols();
+  std::memset(rows, 0, n * w * sizeof(uint32_t));
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t* e = ev + 28 * i;
+    const uint32_t fl = e[8];
+    CpuEventFfi c;
+    std::memset(&c, 0, sizeof(c));
+    c.clk = e[0]; c.pc = e[1]; c.next_pc = e[2]; c.next_next_pc = e[3]; c.a = e[4]; c.b = e[5]; c.c = e[6];
+    c.hi = OptionU32{(fl & 1) ? OptionValTag::Some : OptionValTag::None, e[7]};
+    c.a_record = option_record((fl >> 1) & 3, e + 12);
+    c.b_record = option_record((fl >> 3) & 1, e + 18);
+    c.c_record = option_record((fl >> 4) & 1, e + 23);
+    c.hi_record = option_record(0, nullptr);
+    c.memory_record = option_record(0, nullptr);
+    InstructionFfi ins{(Opcode)(e[9] & 0xff), (uint8_t)((e[9] >> 8) & 0xff), e[10], e[11], ((fl >> 5) & 1) != 0, ((fl >> 6) & 1) != 0,
+                       OptionU32{OptionValTag::None, 0}};
+    cpu::event_to_row<kb31_t>(c, e[9] >> 16, ins, *reinterpret_cast<CpuCols<kb31_t>*>(rows + i * w));
   }
   return 0;
 }

@@ -24,7 +24,8 @@ enum class Opcode : uint8_t {
   SWR = 43, SC = 44, INS = 45, MADDU = 46, MSUBU = 47, MADD = 48, MSUB = 49, MEQ = 50, MNE = 51, WSBH = 52, EXT = 53,
   TEQ = 54, SEXT = 55, UNIMPL = 0xff,
 };
-enum class SyscallCode : uint32_t { HALT = 0 };   // only named by utils.hpp:to_syscall_id
+// crates/core/executor/src/syscalls/code.rs:33, :154 (the two codes cpu.hpp names; utils.hpp:to_syscall_id takes the type)
+enum class SyscallCode : uint32_t { HALT = 0, SYS_EXT_GROUP = 4246 };
 
 // crates/core/executor/src/events/instr.rs:11-26 (#[repr(C)])
 struct AluEvent {
@@ -224,6 +225,34 @@ template <class T> struct SingleMemoryLocal {
   T addr, initial_shard, final_shard, initial_clk, final_clk;
   Word<T> initial_value, final_value;
   T is_real;
+};
+
+// ---- Cpu (crates/core/machine/include/cpu.hpp, instruction.hpp) ----
+// crates/core/executor/src/lib.rs:40-52 (#[repr(u8)] tag, #[repr(C)] struct)
+enum class OptionValTag : uint8_t { Some = 0, None };
+struct OptionU32 { OptionValTag tag; uint32_t value; };
+// crates/core/executor/src/events/cpu.rs:46-77 (#[repr(C)])
+struct CpuEventFfi {
+  uint32_t clk, pc, next_pc, next_next_pc;
+  uint32_t a; OptionMemoryRecordEnum a_record;
+  uint32_t b; OptionMemoryRecordEnum b_record;
+  uint32_t c; OptionMemoryRecordEnum c_record;
+  OptionU32 hi;
+  OptionMemoryRecordEnum hi_record, memory_record;
+  uint32_t exit_code;
+};
+// crates/core/executor/src/instruction.rs:29-46 (#[repr(C)])
+struct InstructionFfi { Opcode opcode; uint8_t op_a; uint32_t op_b, op_c; bool imm_b, imm_c; OptionU32 raw; };
+// crates/core/machine/src/cpu/columns/instruction.rs:12-28, cpu/columns/mod.rs:18-84
+template <class T> struct InstructionCols { T opcode, op_a; Word<T> op_b, op_c; T op_a_0, imm_b, imm_c; };
+template <class T> struct CpuCols {
+  T shard, clk_16bit_limb, clk_8bit_limb, shard_to_send, clk_to_send, pc, next_pc, next_next_pc;
+  InstructionCols<T> instruction;
+  T num_extra_cycles, is_rw_a, is_check_memory, is_halt, is_sequential;
+  Word<T> op_a_value, hi_or_prev_a;
+  MemoryReadWriteCols<T> op_a_access;
+  MemoryReadCols<T> op_b_access, op_c_access;
+  T is_real, op_a_immutable;
 };
 
 }  // namespace zkm_core_machine_sys

@@ -388,4 +388,85 @@ static inline void memory_local_trace(const u32* ev, size_t n, size_t height, u3
     }
 }
 
+// ---- Cpu (crates/core/machine/src/cpu/trace.rs:45-246, cpu/columns/mod.rs:18-84, columns/instruction.rs:12-44; C++ twin
+// include/cpu.hpp) -------------------------------------------------------------------------------------------------------
+// One 28-word record per CpuEvent + its Instruction (include/zkb200.h zkb200_cpu_event): clk, pc, next_pc, next_next_pc, a, b,
+// c, hi, flags, opcode | op_a << 8 | shard << 16, op_b, op_c, a_record[6], b_record[5], c_record[5].  Padding rows:
+// imm_b = imm_c = is_rw_a = 1 (trace.rs:60-63).
+enum { CPU_WIDTH = 67, CPU_EVENT_WORDS = 28, K_SYSCALL = 30, K_INS = 45, K_MADDU = 46, K_MSUBU = 47, K_MADD = 48, K_MSUB = 49,
+       K_TEQ = 54, K_DIV = 5, K_DIVU = 6 };
+struct CpuInstr {
+  u32 opcode;
+  bool is_memory_load() const { return opcode >= K_LB && opcode <= K_LL; }
+  bool is_memory_store() const { return opcode >= K_SB && opcode <= K_SC; }
+  bool is_memory_store_except_sc() const { return is_memory_store() && opcode != K_SC; }
+  bool is_maddsub() const { return opcode == K_MADDU || opcode == K_MSUBU || opcode == K_MADD || opcode == K_MSUB; }
+  bool is_syscall() const { return opcode == K_SYSCALL; }
+  bool is_check_memory() const { return is_syscall() || is_maddsub() || is_memory_load() || is_memory_store(); }
+  bool is_rw_a() const { return is_check_memory() || opcode == K_INS || opcode == K_MEQ || opcode == K_MNE; }
+  bool is_branch() const { return opcode >= K_BEQ && opcode <= K_BNE; }
+  bool is_jump() const { return opcode == K_JUMP || opcode == K_JUMPI || opcode == K_JUMPDIRECT; }
+  bool is_mult_div() const { return opcode == K_MULT || opcode == K_MULTU || opcode == K_DIV || opcode == K_DIVU; }
+};
+// MemoryAccessCols::populate_access without the value word (memory/consistency/trace.rs:56-98)
+static inline void cpu_access_tail(RowWriter& w, u32 shard, u32 ts, u32 prev_shard, u32 prev_ts) {
+  w.put(prev_shard); w.put(prev_ts);
+  const bool use_clk = shard == prev_shard;
+  w.flag(use_clk);
+  const u32 diff_minus_one = (use_clk ? ts - prev_ts : shard - prev_shard) - 1;
+  w.put(diff_minus_one & 0xffff); w.put((diff_minus_one >> 16) & 0xff);
+}
+static inline void cpu_row(const u32* e, u32* row) {
+  RowWriter w{row};
+  const u32 clk = e[0], pc = e[1], next_pc = e[2], next_next_pc = e[3], a = e[4], b = e[5], c = e[6], hi = e[7], flags = e[8];
+  const bool hi_some = flags & 1, b_read = (flags >> 3) & 1, c_read = (flags >> 4) & 1, imm_b = (flags >> 5) & 1, imm_c = (flags >> 6) & 1;
+  const u32 a_kind = (flags >> 1) & 3;                             // 0 None, 1 Read, 2 Write
+  if (a_kind == 3) throw std::runtime_error("oracle: cpu event with a bad a_record kind");
+  const CpuInstr ins{e[9] & 0xff};
+  const u32 op_a = (e[9] >> 8) & 0xff, shard = e[9] >> 16, op_b = e[10], op_c = e[11];
+  const u32 *ra = e + 12, *rb = e + 18, *rc = e + 23;
+  const bool send = ins.is_check_memory() || ins.is_mult_div();
+  w.put(shard); w.put(clk & 0xffff); w.put((clk >> 16) & 0xff);
+  w.put(send ? shard : 0); w.put(send ? clk : 0);
+  w.put(pc); w.put(next_pc); w.put(next_next_pc);
+  w.put(ins.opcode); w.put(op_a); w.word(op_b); w.word(op_c);
+  w.flag(op_a == 0); w.flag(imm_b); w.flag(imm_c);
+  // the syscall columns need register a's previous value, known once the a record is read
+  u32 prev_a = 0, a_value = a, a_tail[5] = {0, 0, 0, 0, 0};
+  if (a_kind) {
+    RowWriter t{a_tail};
+    a_value = ra[0];
+    if (a_kind == 1) { prev_a = ra[0]; cpu_access_tail(t, ra[1], ra[2], ra[3], ra[4]); }
+    else { prev_a = ra[3]; cpu_access_tail(t, ra[1], ra[2], ra[4], ra[5]); }
+  }
+  bool is_halt = false;
+  u32 num_extra_cycles = 0;
+  if (ins.is_syscall()) {
+    const u32 id0 = prev_a & 0xff, id1 = (prev_a >> 8) & 0xff, sys_exit_group = 4246 & 0x0FFFF;
+    is_halt = (id0 == 0 && id1 == 0) || (id0 == (sys_exit_group & 0xff) && id1 == (sys_exit_group >> 8));
+    num_extra_cycles = prev_a >> 24;
+  }
+  w.put(num_extra_cycles);
+  w.flag(ins.is_rw_a()); w.flag(send); w.flag(is_halt);
+  w.flag(!is_halt && !ins.is_branch() && !ins.is_jump());
+  w.word(a);
+  w.word(hi_some ? hi : 0);
+  w.word(prev_a); w.word(a_value);
+  for (int i = 0; i < 5; i++) w.put(a_tail[i]);
+  if (b_read) { w.word(rb[0]); cpu_access_tail(w, rb[1], rb[2], rb[3], rb[4]); } else { w.word(b); for (int i = 0; i < 5; i++) w.put(0); }
+  if (c_read) { w.word(rc[0]); cpu_access_tail(w, rc[1], rc[2], rc[3], rc[4]); } else { w.word(c); for (int i = 0; i < 5; i++) w.put(0); }
+  w.flag(true);
+  w.flag(ins.is_memory_store_except_sc() || ins.is_branch() || ins.opcode == K_TEQ);
+  if (w.at != CPU_WIDTH) throw std::runtime_error("oracle: Cpu row width mismatch");
+}
+static inline void cpu_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  if (n > height) throw std::runtime_error("oracle: more events than rows");
+  for (size_t i = 0; i < height; i++) {
+    u32* r = out + i * CPU_WIDTH;
+    if (i < n) { cpu_row(ev + CPU_EVENT_WORDS * i, r); continue; }
+    for (int k = 0; k < CPU_WIDTH; k++) r[k] = 0;
+    r[19] = 1; r[20] = 1; r[22] = 1;
+  }
+}
+
 }  // namespace zko

@@ -128,6 +128,8 @@ pub trait DeviceTraceEvents {
     /// MemoryLocal: the shard's local memory events gathered into one vector (the record keeps them in several places,
     /// `ExecutionRecord::get_local_mem_events`), four to a row.
     fn memory_local_events(&self) -> Option<Vec<zkm_core_executor::events::MemoryLocalEvent>> { None }
+    /// Cpu: one `zkb200_cpu_event` per `CpuEvent` with its fetched instruction and the shard number (tracegen.rs).
+    fn cpu_events(&self) -> Option<Vec<tracegen::CpuEventFlat>> { None }
     fn fixed_log2_rows_of(&self, _chip: &str) -> Option<usize> { None }
 }
 impl DeviceTraceEvents for zkm_core_executor::ExecutionRecord {
@@ -139,6 +141,7 @@ impl DeviceTraceEvents for zkm_core_executor::ExecutionRecord {
     fn memory_local_events(&self) -> Option<Vec<zkm_core_executor::events::MemoryLocalEvent>> {
         Some(self.get_local_mem_events().copied().collect())
     }
+    fn cpu_events(&self) -> Option<Vec<tracegen::CpuEventFlat>> { Some(tracegen::flatten_cpu_events(self)) }
     fn fixed_log2_rows_of(&self, chip: &str) -> Option<usize> {
         self.shape.as_ref().and_then(|s| s.inner.get(chip).copied())
     }
@@ -240,6 +243,16 @@ where
             const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MemoryLocalEvent>() == 28);
             t[*i].data = ev.as_ptr() as *const u32;
             t[*i].height = tracegen::padded_height(ev.len().div_ceil(tracegen::MEMORY_LOCAL_ENTRIES_PER_ROW), self.fixed_log2_rows(record, "MemoryLocal"));
+            t[*i].flags = sys::ZKB200_TRACE_EVENTS;
+            t[*i].n_events = ev.len();
+        }
+        // Cpu: 112-byte flat records (event + fetched instruction + shard) instead of 268-byte rows
+        let cpu_events = traces.iter().position(|(n, m)| n == "Cpu" && m.values.is_empty())
+            .and_then(|i| record.cpu_events().map(|v| (i, v)));
+        if let Some((i, ev)) = cpu_events.as_ref() {
+            t[*i].data = ev.as_ptr() as *const u32;
+            // CpuChip::num_rows (cpu/trace.rs:32-43): the shape's height, else at least 16 rows
+            t[*i].height = tracegen::padded_height(ev.len(), self.fixed_log2_rows(record, "Cpu"));
             t[*i].flags = sys::ZKB200_TRACE_EVENTS;
             t[*i].n_events = ev.len();
         }

@@ -10,6 +10,9 @@
 //! * MemoryLocal: seven-word `MemoryLocalEvent` records (crates/core/executor/src/events/memory.rs:228-237), four to a row;
 //!   the record keeps them in several vectors (`get_local_mem_events`), so they are gathered into one (28 bytes per event
 //!   against 224 bytes per row of four).
+//! * Cpu: `CpuEvent` (crates/core/executor/src/events/cpu.rs:15-44) holds Options and its instruction lives in the program,
+//!   so each event is flattened into a 28-word `zkb200_cpu_event` (`flatten_cpu_events`), the same information the
+//!   reference's own FFI passes as (CpuEventFfi, shard, InstructionFfi) (crates/core/machine/src/sys.rs:24-29).
 //! * KeccakSponge: `KeccakSpongeEvent` (crates/core/executor/src/events/precompiles/keccak_sponge.rs:15-40) holds Vecs, so
 //!   it is flattened into one `zkb200_keccak_block` per absorbed block (24 rows), mirroring the block loop of
 //!   `KeccakSpongeChip::event_to_rows` (crates/core/machine/src/syscall/precompiles/keccak_sponge/trace.rs:101-196).
@@ -154,4 +157,53 @@ pub fn padded_height(n_events: usize, fixed_log2_rows: Option<usize>) -> usize {
         Some(l) => { assert!(n_events <= 1 << l, "fixed log2 rows is too small"); 1 << l }
         None => n_events.next_power_of_two().max(16),
     }
+}
+
+/// `zkb200_cpu_event` (include/zkb200.h): 28 words.
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct CpuEventFlat {
+    pub clk: u32,
+    pub pc: u32,
+    pub next_pc: u32,
+    pub next_next_pc: u32,
+    pub a: u32,
+    pub b: u32,
+    pub c: u32,
+    pub hi: u32,
+    pub flags: u32,
+    pub op_word: u32,
+    pub op_b: u32,
+    pub op_c: u32,
+    pub a_record: [u32; 6],
+    pub b_record: [u32; 5],
+    pub c_record: [u32; 5],
+}
+const _: () = assert!(core::mem::size_of::<CpuEventFlat>() == 28 * 4);
+
+/// What `CpuChip::generate_trace` reads per row (cpu/trace.rs:45-75): the event, `input.program.fetch(event.pc)` and
+/// `input.public_values.execution_shard`.
+pub fn flatten_cpu_events(record: &ExecutionRecord) -> Vec<CpuEventFlat> {
+    use zkm_core_executor::events::MemoryRecordEnum;
+    let shard = record.public_values.execution_shard;
+    debug_assert!(shard < 1 << 16, "the Cpu chip range-checks the shard number to 16 bits");
+    record.cpu_events.iter().map(|e| {
+        let ins = record.program.fetch(e.pc);
+        let mut f = CpuEventFlat {
+            clk: e.clk, pc: e.pc, next_pc: e.next_pc, next_next_pc: e.next_next_pc, a: e.a, b: e.b, c: e.c,
+            hi: e.hi.unwrap_or(0),
+            op_word: ins.opcode as u32 | (ins.op_a as u32) << 8 | shard << 16,
+            op_b: ins.op_b, op_c: ins.op_c,
+            ..Default::default()
+        };
+        f.flags = e.hi.is_some() as u32 | (ins.imm_b as u32) << 5 | (ins.imm_c as u32) << 6;
+        match e.a_record {
+            Some(MemoryRecordEnum::Read(r)) => { f.flags |= 1 << 1; f.a_record[..5].copy_from_slice(&read_words(&r)); }
+            Some(MemoryRecordEnum::Write(w)) => { f.flags |= 2 << 1; f.a_record = write_words(&w); }
+            None => {}
+        }
+        if let Some(MemoryRecordEnum::Read(r)) = e.b_record { f.flags |= 1 << 3; f.b_record = read_words(&r); }
+        if let Some(MemoryRecordEnum::Read(r)) = e.c_record { f.flags |= 1 << 4; f.c_record = read_words(&r); }
+        f
+    }).collect()
 }

@@ -321,6 +321,7 @@ int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* eve
                               unsigned log_height, uint32_t* out, int col_major) {
   return guarded(ctx, [&] {
     static_assert(sizeof(zkb200_alu_event) == 28 && sizeof(zkb200_flow_event) == 28, "event records are seven 32-bit words");
+    static_assert(sizeof(zkb200_cpu_event) == CPU_EVENT_WORDS * 4, "cpu event records are 28 32-bit words");
     const int id = alu_chip_by_name(chip);
     if (id < 0) throw std::runtime_error(std::string("zkb200: generate_alu_trace: no row filler for chip ") + chip);
     if (log_height > 30) throw std::runtime_error("zkb200: generate_alu_trace: log_height out of range");

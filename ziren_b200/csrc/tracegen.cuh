@@ -12,7 +12,7 @@
 namespace zkb {
 
 enum AluChip : int { ALU_ADDSUB = 0, ALU_BITWISE = 1, ALU_LT = 2, ALU_SLL = 3, ALU_SR = 4, ALU_CLOCLZ = 5, ALU_BRANCH = 6, ALU_JUMP = 7,
-                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_MEMINSTR = 10, ALU_MEMLOCAL = 11, ALU_NCHIPS = 12 };
+                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_MEMINSTR = 10, ALU_MEMLOCAL = 11, ALU_CPU = 12, ALU_NCHIPS = 13 };
 // opcodes as numbered by crates/core/executor/src/opcode.rs:25-49 (#[repr(u8)])
 enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_ROR = 12, OP_SLT = 13, OP_SLTU = 14,
              OP_AND = 15, OP_OR = 16, OP_XOR = 17, OP_NOR = 18, OP_CLZ = 19, OP_CLO = 20, OP_BEQ = 21, OP_BGEZ = 22, OP_BGTZ = 23,
@@ -20,11 +20,11 @@ enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_RO
 
 KB_HD constexpr int alu_width(int chip) {
   return chip == ALU_ADDSUB ? 19 : chip == ALU_BITWISE ? 18 : chip == ALU_LT ? 32 : chip == ALU_SLL ? 44 : chip == ALU_SR ? 67
-       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : chip == ALU_MEMINSTR ? 79 : chip == ALU_MEMLOCAL ? 56 : 32;
+       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : chip == ALU_MEMINSTR ? 79 : chip == ALU_MEMLOCAL ? 56 : chip == ALU_CPU ? 67 : 32;
 }
 // 32-bit words per event record: seven for AluEvent / BranchEvent / JumpEvent / MovCondEvent, sixteen for CompAluEvent (Mul)
-// and MemInstrEvent (MemoryInstrs)
-KB_HD constexpr int alu_event_words(int chip) { return chip == ALU_MUL || chip == ALU_MEMINSTR ? 16 : 7; }
+// and MemInstrEvent (MemoryInstrs), twenty-eight for the flattened CpuEvent + Instruction (zkb200_cpu_event)
+KB_HD constexpr int alu_event_words(int chip) { return chip == ALU_CPU ? 28 : chip == ALU_MUL || chip == ALU_MEMINSTR ? 16 : 7; }
 // events per row: MemoryLocal packs four seven-word MemoryLocalEvents into a row, every other chip has one event per row
 KB_HD constexpr int alu_events_per_row(int chip) { return chip == ALU_MEMLOCAL ? 4 : 1; }
 
@@ -352,6 +352,91 @@ KB_HD void fill_memory_local(const u32* e, int n_valid, u32* r) {
   }
 }
 
+// CpuChip::event_to_row, crates/core/machine/src/cpu/trace.rs:119-246 (C++ twin include/cpu.hpp).  CpuEvent holds Options
+// and the instruction is fetched from the program, so the host flattens both into a 28-word `zkb200_cpu_event`
+// (include/zkb200.h): clk, pc, next_pc, next_next_pc, a, b, c, hi, flags (bit 0 hi is Some; bits 1-2 a_record: 0 None, 1 Read,
+// 2 Write; bit 3 b_record is Read; bit 4 c_record is Read; bit 5 imm_b; bit 6 imm_c), opcode | op_a << 8 | shard << 16, op_b,
+// op_c, a_record (six words laid out as the MemoryRecordEnum payload: read {value, shard, timestamp, prev_shard,
+// prev_timestamp, -}, write {value, shard, timestamp, prev_value, prev_shard, prev_timestamp}), b_record and c_record
+// (MemoryReadRecord, five words each).  Columns (67, cpu/columns/mod.rs:18-84): shard, clk_16bit_limb, clk_8bit_limb,
+// shard_to_send, clk_to_send, pc, next_pc, next_next_pc, instruction {opcode, op_a, op_b[4], op_c[4], op_a_0, imm_b, imm_c},
+// num_extra_cycles, is_rw_a, is_check_memory, is_halt, is_sequential, op_a_value[4], hi_or_prev_a[4], op_a_access
+// {prev_value[4], value[4], prev_shard, prev_clk, compare_clk, diff_16bit_limb, diff_8bit_limb}, op_b_access[9],
+// op_c_access[9], is_real, op_a_immutable.  The instruction classes (crates/core/executor/src/instruction.rs:147-310) are bit
+// masks over the opcode number.
+constexpr int CPU_WIDTH = 67, CPU_EVENT_WORDS = 28;
+KB_HD constexpr u64 tg_opmask(int lo, int hi) { return ((~0ull) >> (63 - (hi - lo))) << lo; }     // opcodes lo..hi
+constexpr u64 CPU_M_LOADS = tg_opmask(31, 38), CPU_M_STORES_NO_SC = tg_opmask(39, 43), CPU_M_SC = 1ull << 44,
+              CPU_M_BRANCH = tg_opmask(21, 26), CPU_M_JUMP = tg_opmask(27, 29), CPU_M_SYSCALL = 1ull << 30,
+              CPU_M_MADDSUB = tg_opmask(46, 49), CPU_M_INS = 1ull << 45, CPU_M_MOVCOND = tg_opmask(50, 51), CPU_M_TEQ = 1ull << 54,
+              CPU_M_MULT_DIV = tg_opmask(3, 6);
+constexpr u64 CPU_M_CHECK_MEMORY = CPU_M_SYSCALL | CPU_M_MADDSUB | CPU_M_LOADS | CPU_M_STORES_NO_SC | CPU_M_SC;
+constexpr u64 CPU_M_RW_A = CPU_M_CHECK_MEMORY | CPU_M_INS | CPU_M_MOVCOND;
+// MemoryAccessCols::populate_access (memory/consistency/trace.rs:56-98): prev_shard, prev_clk, compare_clk and the two limbs
+// of (current - previous - 1) in the compared time
+KB_HD void tg_mem_access_tail(u32* r, u32 shard, u32 ts, u32 prev_shard, u32 prev_ts) {
+  r[0] = tg_f(prev_shard); r[1] = tg_f(prev_ts);
+  const bool same = prev_shard == shard;
+  r[2] = tg_b(same);
+  const u32 d = (same ? ts - prev_ts : shard - prev_shard) - 1u;
+  r[3] = tg_f(d & 0xffffu); r[4] = tg_f((d >> 16) & 0xffu);
+}
+KB_HD void fill_cpu(const u32* e, u32* r) {
+  const u32 clk = e[0], pc = e[1], next_pc = e[2], next_next_pc = e[3], a = e[4], b = e[5], c = e[6], hi = e[7], fl = e[8];
+  const u32 op = e[9] & 0xffu, op_a = (e[9] >> 8) & 0xffu, shard = e[9] >> 16, op_b = e[10], op_c = e[11];
+  const u64 bit = op < 64 ? 1ull << op : 0ull;
+  const bool check_or_multdiv = (bit & (CPU_M_CHECK_MEMORY | CPU_M_MULT_DIV)) != 0;
+  r[0] = tg_f(shard); r[1] = tg_f(clk & 0xffffu); r[2] = tg_f((clk >> 16) & 0xffu);
+  r[3] = check_or_multdiv ? tg_f(shard) : 0u; r[4] = check_or_multdiv ? tg_f(clk) : 0u;
+  r[5] = tg_f(pc); r[6] = tg_f(next_pc); r[7] = tg_f(next_next_pc);
+  r[8] = tg_f(op); r[9] = tg_f(op_a);
+  tg_word(r + 10, op_b); tg_word(r + 14, op_c);
+  r[18] = tg_b(op_a == 0); r[19] = tg_b((fl >> 5) & 1u); r[20] = tg_b((fl >> 6) & 1u);
+  r[22] = tg_b((bit & CPU_M_RW_A) != 0);
+  r[23] = tg_b(check_or_multdiv);
+  tg_word(r + 26, a);
+  tg_word(r + 30, (fl & 1u) ? hi : 0u);
+  // op_a_access: the value word is `a` unless a record overwrites it
+  const u32 a_kind = (fl >> 1) & 3u;
+  const u32* ra = e + 12;
+  u32 a_prev_value = 0;
+  if (a_kind == 0) {
+    for (int i = 34; i < 38; i++) r[i] = 0;
+    tg_word(r + 38, a);
+    for (int i = 42; i < 47; i++) r[i] = 0;
+  } else {
+    const bool wr = a_kind == 2;
+    a_prev_value = wr ? ra[3] : ra[0];
+    tg_word(r + 34, a_prev_value);
+    tg_word(r + 38, ra[0]);
+    tg_mem_access_tail(r + 42, ra[1], ra[2], wr ? ra[4] : ra[3], wr ? ra[5] : ra[4]);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; k++) {                       // op_b_access, op_c_access
+    u32* rc = r + 47 + 9 * k;
+    const u32* rec = e + 18 + 5 * k;
+    if ((fl >> (3 + k)) & 1u) {
+      tg_word(rc, rec[0]);
+      tg_mem_access_tail(rc + 4, rec[1], rec[2], rec[3], rec[4]);
+    } else {
+      tg_word(rc, k ? c : b);
+      for (int i = 4; i < 9; i++) rc[i] = 0;
+    }
+  }
+  // SYSCALL: HALT (id 0) and SYS_EXT_GROUP (4246) end the program; the syscall code is register a's previous value
+  bool is_halt = false;
+  u32 extra = 0;
+  if (bit & CPU_M_SYSCALL) {
+    const u32 id = a_prev_value & 0xffffu;
+    is_halt = id == 0u || id == (4246u & 0xffffu);
+    extra = tg_f(a_prev_value >> 24);
+  }
+  r[21] = extra; r[24] = tg_b(is_halt);
+  r[25] = tg_b(!is_halt && !(bit & (CPU_M_BRANCH | CPU_M_JUMP)));
+  r[65] = KB_ONE;
+  r[66] = tg_b((bit & (CPU_M_STORES_NO_SC | CPU_M_BRANCH | CPU_M_TEQ)) != 0);
+}
+
 // Rows past the last event (generate_trace of each chip): zeros, except the dummy rows that keep the
 // shift and count-leading chips' constraints satisfied (sll/mod.rs:160-173, sr/mod.rs:184-187,
 // clo_clz/mod.rs:150-163).
@@ -361,6 +446,7 @@ KB_HD void fill_alu_padding(int chip, u32* r) {
   if (chip == ALU_SLL) { r[22] = KB_ONE; r[30] = KB_ONE; r[39] = KB_ONE; }
   if (chip == ALU_SR) { r[10] = KB_ONE; r[18] = KB_ONE; }
   if (chip == ALU_CLOCLZ) { tg_word(r + 2, 32); r[14] = KB_ONE; }
+  if (chip == ALU_CPU) { r[19] = KB_ONE; r[20] = KB_ONE; r[22] = KB_ONE; }      // imm_b, imm_c, is_rw_a (cpu/trace.rs:60-63)
 }
 
 // w: the row's event words as they lie in the record's event vector (alu_events_per_row x alu_event_words of them, the first
@@ -378,6 +464,7 @@ KB_HD void fill_alu_row(int chip, const u32* w, u32* r, const u32* inv255, int n
     case ALU_MUL: fill_mul(w, r); break;
     case ALU_MEMINSTR: fill_mem_instr(w, r); break;
     case ALU_MEMLOCAL: fill_memory_local(w, n_valid, r); break;
+    case ALU_CPU: fill_cpu(w, r); break;
     default: fill_mov_cond(w, r, inv255); break;
   }
 }

@@ -42,12 +42,15 @@ EVENT_WORDS = 7          # AluEvent: pc, next_pc, opcode, hi, a, b, c;  Branch/J
 EVENT_BYTES = 28
 
 
+CPU_WIDTH, CPU_EVENT_WORDS = 67, 28            # zkb200_cpu_event: the flattened CpuEvent + Instruction
 PACKED_CHIPS = {"MemoryLocal": (56, 4)}       # width, events per row (seven-word MemoryLocalEvent records)
 
 
 def width(chip: str) -> int:
     if chip in PACKED_CHIPS:
         return PACKED_CHIPS[chip][0]
+    if chip == "Cpu":
+        return CPU_WIDTH
     return (ALU_CHIPS.get(chip) or COMP_CHIPS[chip])[0]
 
 
@@ -56,6 +59,8 @@ def events_per_row(chip: str) -> int:
 
 
 def event_words(chip: str) -> int:
+    if chip == "Cpu":
+        return CPU_EVENT_WORDS
     return COMP_EVENT_WORDS if chip in COMP_CHIPS else EVENT_WORDS
 
 
@@ -337,4 +342,77 @@ def synthetic_memory_local_events(n: int, seed: int = 0, shard: int = 3) -> np.n
     ev[:, 4] = shard
     ev[:, 5] = rng.integers(1 << 22, 1 << 23, n)
     ev[:, 6] = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    return ev
+
+
+ALL_OPCODES = {"ADD": 0, "SUB": 1, "MUL": 2, "MULT": 3, "MULTU": 4, "DIV": 5, "DIVU": 6, "MOD": 7, "MODU": 8, "SLL": 9, "SRL": 10,
+               "SRA": 11, "ROR": 12, "SLT": 13, "SLTU": 14, "AND": 15, "OR": 16, "XOR": 17, "NOR": 18, "CLZ": 19, "CLO": 20,
+               "BEQ": 21, "BGEZ": 22, "BGTZ": 23, "BLEZ": 24, "BLTZ": 25, "BNE": 26, "Jump": 27, "Jumpi": 28, "JumpDirect": 29,
+               "SYSCALL": 30, "LB": 31, "LBU": 32, "LH": 33, "LHU": 34, "LW": 35, "LWL": 36, "LWR": 37, "LL": 38, "SB": 39,
+               "SH": 40, "SW": 41, "SWL": 42, "SWR": 43, "SC": 44, "INS": 45, "MADDU": 46, "MSUBU": 47, "MADD": 48, "MSUB": 49,
+               "MEQ": 50, "MNE": 51, "WSBH": 52, "EXT": 53, "TEQ": 54, "SEXT": 55}      # crates/core/executor/src/opcode.rs:25-89
+# syscall codes the Cpu row looks at (crates/core/executor/src/syscalls/code.rs): HALT, SYS_EXT_GROUP, and others whose
+# byte 3 is the number of extra cycles
+_SYSCALL_CODES = np.array([0x00000000, 4246, 0x00000002, 0x00010005, 0x01010109, 0x00300130, 4003, 0x000000F0], np.uint32)
+
+
+def synthetic_cpu_events(n: int, seed: int = 0, shard: int = 3) -> np.ndarray:
+    """n `zkb200_cpu_event` records (include/zkb200.h) as (n, 28) uint32 words - what the shim writes per CpuEvent
+    (crates/core/executor/src/events/cpu.rs:15-44) and its fetched Instruction: clk, pc, next_pc, next_next_pc, a, b, c, hi,
+    flags, opcode | op_a << 8 | shard << 16, op_b, op_c, a_record[6], b_record[5], c_record[5].  Every opcode occurs; register
+    a is written (most instructions), read (stores, branches) or untouched; b and c are register reads unless immediate;
+    SYSCALL rows carry the syscall code as register a's previous value."""
+    rng = np.random.default_rng(0xC9D + seed)
+    ev = np.zeros((n, CPU_EVENT_WORDS), np.uint32)
+    if n == 0:
+        return ev
+    O = ALL_OPCODES
+    ops = np.array(list(O.values()), np.uint32)
+    op = rng.choice(ops, n).astype(np.uint32)
+    op[: min(n, len(ops))] = ops[: min(n, len(ops))]
+    u32 = lambda: rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    clk = (5 + 5 * np.arange(1, n + 1) + (1 << 16) * (np.arange(n) % 3)).astype(np.uint32)       # exercises the 8-bit limb
+    pc = (rng.integers(0, 1 << 22, n) * 4).astype(np.uint32)
+    is_branch = (op >= O["BEQ"]) & (op <= O["BNE"])
+    is_jump = (op >= O["Jump"]) & (op <= O["JumpDirect"])
+    is_store = (op >= O["SB"]) & (op <= O["SWR"])
+    is_sys = op == O["SYSCALL"]
+    has_hi = np.isin(op, [O["MULT"], O["MULTU"], O["DIV"], O["DIVU"], O["MADDU"], O["MSUBU"], O["MADD"], O["MSUB"]])
+    a, b, c = u32(), u32(), u32()
+    imm_b = rng.integers(0, 4, n) == 0
+    imm_c = (rng.integers(0, 2, n) == 0) | imm_b
+    op_a = rng.integers(0, 34, n).astype(np.uint32)
+    op_a[rng.integers(0, 8, n) == 0] = 0
+    # register a: read for stores / branches, untouched for some jumps, written otherwise
+    a_kind = np.where(is_store | is_branch, 1, np.where(is_jump & (rng.integers(0, 2, n) == 0), 0, 2)).astype(np.uint32)
+    flags = (has_hi.astype(np.uint32) | (a_kind << 1) | ((~imm_b).astype(np.uint32) << 3) | ((~imm_c).astype(np.uint32) << 4)
+             | (imm_b.astype(np.uint32) << 5) | (imm_c.astype(np.uint32) << 6))
+    ev[:, 0], ev[:, 1], ev[:, 2] = clk, pc, pc + 4
+    ev[:, 3] = np.where(is_branch | is_jump, (rng.integers(0, 1 << 22, n) * 4).astype(np.uint32), pc + 8)
+    ev[:, 4], ev[:, 5], ev[:, 6] = a, b, c
+    ev[:, 7] = np.where(has_hi, u32(), 0)
+    ev[:, 8] = flags
+    ev[:, 9] = op | (op_a << 8) | (np.uint32(shard) << 16)
+    ev[:, 10] = np.where(imm_b, b, rng.integers(0, 34, n))
+    ev[:, 11] = np.where(imm_c, c, rng.integers(0, 34, n))
+
+    def prev(cur_ts):
+        earlier = (rng.integers(0, 6, n) == 0) & (shard > 1)
+        pshard = np.where(earlier, rng.integers(1, max(shard, 2), n), shard).astype(np.uint32)
+        pts = np.where(earlier, rng.integers(0, 1 << 22, n), cur_ts.astype(np.int64) - rng.integers(1, 5, n)).astype(np.uint32)
+        return pshard, pts
+
+    # a_record at clk + 0 (MemoryAccessPosition::A... the position offsets only need to be distinct and increasing here)
+    ps, pt = prev(clk + 3)
+    prev_a = np.where(is_sys, rng.choice(_SYSCALL_CODES, n), u32()).astype(np.uint32)
+    wr = a_kind == 2
+    ev[:, 12], ev[:, 13], ev[:, 14] = a, shard, clk + 3
+    ev[:, 15] = np.where(wr, prev_a, ps)
+    ev[:, 16] = np.where(wr, ps, pt)
+    ev[:, 17] = np.where(wr, pt, 0)
+    ev[a_kind == 0, 12:18] = 0
+    for col0, val, imm, off in ((18, b, imm_b, 1), (23, c, imm_c, 2)):
+        ps, pt = prev(clk + off)
+        ev[:, col0], ev[:, col0 + 1], ev[:, col0 + 2], ev[:, col0 + 3], ev[:, col0 + 4] = val, shard, clk + off, ps, pt
+        ev[imm, col0:col0 + 5] = 0
     return ev
