@@ -187,7 +187,9 @@ int zkb200_grind(zkb200_ctx* ctx, const uint32_t challenger[34], unsigned bits, 
  * prev_a_val} (instr.rs:114-136, events/memory.rs:46-97).  "MemoryLocal" (crates/core/machine/src/memory/local.rs:146-190, C++
  * twin include/memory_local.hpp; 56 columns) takes 28-byte `MemoryLocalEvent` records {addr, initial_mem_access {shard,
  * timestamp, value}, final_mem_access {shard, timestamp, value}} (events/memory.rs:228-237) and packs FOUR events into a row:
- * n_events may be up to 4 * 2^log_height.  `out` is DEVICE memory of
+ * n_events may be up to 4 * 2^log_height.  "MiscInstrs" (crates/core/machine/src/misc/others/trace.rs:91-275, C++ twin
+ * include/misc_instrs.hpp; 72 columns, 44 of them a union per opcode family) takes 60-byte `MiscEvent` records {shard, clk, pc,
+ * next_pc, opcode, a, b, c, prev_a, hi_record[6]} (instr.rs:241-261).  `out` is DEVICE memory of
  * 2^log_height x width words, Montgomery, row-major (col_major = 0: the RowMajorMatrix layout
  * zkb200_commit takes) or column-major (col_major = 1: the layout of the kernel-level entry points). */
 typedef struct {
@@ -220,7 +222,8 @@ typedef struct {
 /* NUM_*_COLS of the chip, -1 if this library has no row filler for it */
 int zkb200_alu_trace_width(const char* chip);
 /* events: zkb200_alu_event[]; zkb200_flow_event[] for "Branch" / "Jump"; seven-word MovCondEvent records for "MovCond";
- * CompAluEvent / MemInstrEvent / MemoryLocalEvent records as they lie for "Mul" / "MemoryInstrs" / "MemoryLocal";
+ * CompAluEvent / MemInstrEvent / MemoryLocalEvent / MiscEvent records as they lie for "Mul" / "MemoryInstrs" / "MemoryLocal" /
+ * "MiscInstrs";
  * zkb200_cpu_event[] for "Cpu" */
 int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* events, size_t n_events,
                               unsigned log_height, uint32_t* out, int col_major);

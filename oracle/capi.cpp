@@ -285,6 +285,13 @@ int zko_cpu_trace(const u32* ev, size_t n, size_t height, u32* out) {
     return 0;
   } catch (const std::exception& e) { return fail(e); }
 }
+// MiscInstrs rows (tracegen.h): events n x 15 words (MiscEvent), out height x 72 row-major canonical
+int zko_misc_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  try {
+    misc_trace(ev, n, height, out);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
 // trace generation of the KeccakSponge chip (tracegen_keccak.h): n_blocks records of KS_REC_WORDS words,
 // out height x 3531 row-major canonical
 int zko_keccak_sponge_width() { return KS_WIDTH; }

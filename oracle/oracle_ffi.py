@@ -188,6 +188,30 @@ def ref_cpu_rows(events):
     return out
 
 
+MISC_WIDTH, MISC_EVENT_WORDS = 72, 15
+
+
+def misc_trace(events, height):
+    """events: (n, 15) uint32 MiscEvent records; (height, 72) canonical rows of the MiscInstrs chip."""
+    ev = _a(events).reshape(-1, MISC_EVENT_WORDS)
+    out = np.zeros((int(height), MISC_WIDTH), np.uint32)
+    if lib().zko_misc_trace(_p(ev), C.c_size_t(ev.shape[0]), C.c_size_t(int(height)), _p(out)):
+        raise RuntimeError(err())
+    return out
+
+
+def ref_misc_rows(events):
+    """Rows of the reference's own misc_instrs.hpp event_to_row (Montgomery words), or None without oracle/_ref."""
+    l = ref_core_lib()
+    if l is None or not hasattr(l, "ref_misc_event_to_rows"):
+        return None
+    ev = _a(events).reshape(-1, MISC_EVENT_WORDS)
+    out = np.zeros((ev.shape[0], MISC_WIDTH), np.uint32)
+    if l.ref_misc_event_to_rows(_p(ev), C.c_size_t(ev.shape[0]), _p(out)):
+        raise RuntimeError("reference row filler failed")
+    return out
+
+
 KS_WIDTH, KS_REC_WORDS = 3531, 384
 
 

@@ -20,6 +20,7 @@
 #include "memory_instrs.hpp"
 #include "memory_local.hpp"
 #include "cpu.hpp"
+#include "misc_instrs.hpp"
 
 using namespace zkm_core_machine_sys;
 
@@ -173,6 +174,20 @@ int ref_cpu_event_to_rows(const uint32_t* ev, size_t n, uint32_t* rows) {
     InstructionFfi ins{(Opcode)(e[9] & 0xff), (uint8_t)((e[9] >> 8) & 0xff), e[10], e[11], ((fl >> 5) & 1) != 0, ((fl >> 6) & 1) != 0,
                        OptionU32{OptionValTag::None, 0}};
     cpu::event_to_row<kb31_t>(c, e[9] >> 16, ins, *reinterpret_cast<CpuCols<kb31_t>*>(rows + i * w));
+  }
+  return 0;
+}
+// MiscInstrs rows of the reference's misc_instrs.hpp: events n x 15 words, the #[repr(C)] image of MiscEvent {shard, clk, pc,
+// next_pc, opcode, a, b, c, prev_a, hi_record[6]}; rows n x 72 Montgomery words
+unsigned ref_misc_num_cols() { return ncols<MiscInstrColumns<kb31_t>>(); }
+int ref_misc_event_to_rows(const uint32_t* ev, size_t n, uint32_t* rows) {
+  static_assert(sizeof(MiscEvent) == 15 * sizeof(uint32_t), "MiscEvent is fifteen words");
+  const unsigned w = ref_misc_num_cols();
+  std::memset(rows, 0, n * w * sizeof(uint32_t));
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t* e = ev + 15 * i;
+    MiscEvent m{e[0], e[1], e[2], e[3], (Opcode)(e[4] & 0xff), e[5], e[6], e[7], e[8], MemoryWriteRecord{e[9], e[10], e[11], e[12], e[13], e[14]}};
+    misc_instrs::event_to_row<kb31_t>(m, *reinterpret_cast<MiscInstrColumns<kb31_t>*>(rows + i * w));
   }
   return 0;
 }

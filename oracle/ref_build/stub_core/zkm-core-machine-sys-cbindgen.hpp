@@ -255,4 +255,30 @@ template <class T> struct CpuCols {
   T is_real, op_a_immutable;
 };
 
+// ---- MiscInstrs (crates/core/machine/include/misc_instrs.hpp) ----
+// crates/core/executor/src/events/instr.rs:241-261 (#[repr(C)])
+struct MiscEvent {
+  uint32_t shard, clk, pc, next_pc;
+  Opcode opcode;
+  uint32_t a, b, c, prev_a;
+  MemoryWriteRecord hi_record;
+};
+// crates/core/machine/src/misc/others/columns/{maddsub,sext,ext,ins,misc_specific,mod}.rs
+template <class T> struct MaddsubCols {
+  Word<T> mul_lo, mul_hi;
+  AddDoubleOperation<T> add_operation;
+  Word<T> src2_hi, src2_lo;
+  MemoryReadWriteCols<T> op_hi_access;
+};
+template <class T> struct SextCols { T most_sig_bit, sig_byte; IsEqualWordOperation<T> a_eq_b; T is_seb, is_seh; };
+template <class T> struct ExtCols { T lsb, msbd; Word<T> sll_val; };
+template <class T> struct InsCols { T lsb, msb; Word<T> ror_val, srl1_val, srl_val, sll_val, add_val; };
+template <class T> union MiscSpecificCols { MaddsubCols<T> maddsub; SextCols<T> sext; ExtCols<T> ext; InsCols<T> ins; };
+template <class T> struct MiscInstrColumns {
+  T shard, clk, pc, next_pc;
+  Word<T> op_a_value, prev_a_value, op_b_value, op_c_value;
+  MiscSpecificCols<T> misc_specific_columns;
+  T is_sext, is_ins, is_ext, is_maddu, is_msubu, is_madd, is_msub, is_teq;
+};
+
 }  // namespace zkm_core_machine_sys

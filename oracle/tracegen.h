@@ -469,4 +469,79 @@ static inline void cpu_trace(const u32* ev, size_t n, size_t height, u32* out) {
   }
 }
 
+// ---- MiscInstrs (crates/core/machine/src/misc/others/trace.rs:91-275, columns/{mod,maddsub,sext,ext,ins}.rs; C++ twin
+// include/misc_instrs.hpp) ---------------------------------------------------------------------------------------------
+// MiscEvent (crates/core/executor/src/events/instr.rs:241-261) as 15 words: shard, clk, pc, next_pc, opcode, a, b, c, prev_a,
+// hi_record {value, shard, timestamp, prev_value, prev_shard, prev_timestamp}.  72 columns; the 44 columns after op_c_value
+// are a union read as MaddsubCols / SextCols / ExtCols / InsCols by opcode.  Padding rows are zero.
+enum { MISC_WIDTH = 72, MISC_EVENT_WORDS = 15, MISC_UNION = 44, K_EXT = 53, K_SEXT = 55 };
+static inline void misc_row(const u32* e, u32* row) {
+  const u32 shard = e[0], clk = e[1], pc = e[2], next_pc = e[3], opcode = e[4] & 0xff, a = e[5], b = e[6], c = e[7], prev_a = e[8];
+  const u32 hi_value = e[9], hi_shard = e[10], hi_ts = e[11], hi_prev_value = e[12], hi_prev_shard = e[13], hi_prev_ts = e[14];
+  RowWriter w{row};
+  w.put(shard); w.put(clk); w.put(pc); w.put(next_pc);
+  w.word(a); w.word(prev_a); w.word(b); w.word(c);
+  u32 un[MISC_UNION] = {0};
+  RowWriter u{un};
+  if (opcode == K_SEXT || opcode == K_TEQ) {
+    // populate_sext: SextCols {most_sig_bit, sig_byte, a_eq_b, is_seb, is_seh}
+    const bool seh = c > 0;
+    const u32 sig_bit = seh ? ((b & 0xffff) >> 15) : ((b & 0xff) >> 7), sig_byte = seh ? ((b >> 8) & 0xff) : (b & 0xff);
+    u.put(sig_bit); u.put(sig_byte);
+    // IsEqualWordOperation -> IsZeroWordOperation over the byte differences as field elements (operations/is_equal_word.rs,
+    // is_zero_word.rs, is_zero.rs)
+    bool zero[4];
+    for (int i = 0; i < 4; i++) {
+      const F diff = F((a >> (8 * i)) & 0xff) - F((b >> (8 * i)) & 0xff);
+      zero[i] = diff.is_zero();
+      u.put(zero[i] ? 0 : finv(diff).v);
+      u.flag(zero[i]);
+    }
+    u.flag(zero[0] && zero[1]); u.flag(zero[2] && zero[3]); u.flag(zero[0] && zero[1] && zero[2] && zero[3]);
+    u.flag(!seh); u.flag(seh);
+  } else if (opcode == K_MADDU || opcode == K_MSUBU || opcode == K_MADD || opcode == K_MSUB) {
+    // populate_maddsub: MaddsubCols {mul_lo, mul_hi, add_operation, src2_hi, src2_lo, op_hi_access}
+    const bool is_sign = opcode == K_MADD || opcode == K_MSUB, is_add = opcode == K_MADDU || opcode == K_MADD;
+    const u64 multiply = is_sign ? (u64)((long long)(int)b * (long long)(int)c) : (u64)b * (u64)c;
+    u.word((u32)multiply); u.word((u32)(multiply >> 32));
+    const u32 src2_lo = is_add ? prev_a : a, src2_hi = is_add ? hi_prev_value : hi_value;
+    const u64 src2 = ((u64)src2_hi << 32) + src2_lo, expected = multiply + src2;
+    u.word((u32)expected); u.word((u32)(expected >> 32));
+    u32 carry = 0;
+    for (int i = 0; i < 7; i++) {                 // AddDoubleOperation::populate (operations/adddouble.rs:24-64)
+      carry = (((multiply >> (8 * i)) & 0xff) + ((src2 >> (8 * i)) & 0xff) + carry) > 255 ? 1 : 0;
+      u.put(carry);
+    }
+    u.word(src2_hi); u.word(src2_lo);
+    u.word(hi_prev_value); u.word(hi_value);
+    u.put(hi_prev_shard); u.put(hi_prev_ts);
+    const bool use_clk = hi_shard == hi_prev_shard;
+    u.flag(use_clk);
+    const u32 diff_minus_one = (use_clk ? hi_ts - hi_prev_ts : hi_shard - hi_prev_shard) - 1;
+    u.put(diff_minus_one & 0xffff); u.put((diff_minus_one >> 16) & 0xff);
+  } else if (opcode == K_EXT) {
+    const u32 lsb = c & 0x1f, msbd = c >> 5;
+    if (lsb + msbd > 31) throw std::runtime_error("oracle: EXT event with lsb + msbd > 31");
+    u.put(lsb); u.put(msbd); u.word(b << (31 - lsb - msbd));
+  } else if (opcode == K_INS) {
+    const u32 lsb = c & 0x1f, msb = c >> 5;
+    if (msb < lsb || msb > 31) throw std::runtime_error("oracle: INS event with msb < lsb");
+    const u32 ror_val = lsb ? ((prev_a >> lsb) | (prev_a << (32 - lsb))) : prev_a;
+    const u32 srl1_val = ror_val >> 1, srl_val = srl1_val >> (msb - lsb), sll_val = b << (31 - msb + lsb);
+    u.put(lsb); u.put(msb);
+    u.word(ror_val); u.word(srl1_val); u.word(srl_val); u.word(sll_val); u.word(srl_val + sll_val);
+  }
+  for (int i = 0; i < MISC_UNION; i++) w.put(un[i]);
+  w.flag(opcode == K_SEXT); w.flag(opcode == K_INS); w.flag(opcode == K_EXT); w.flag(opcode == K_MADDU);
+  w.flag(opcode == K_MSUBU); w.flag(opcode == K_MADD); w.flag(opcode == K_MSUB); w.flag(opcode == K_TEQ);
+  if (w.at != MISC_WIDTH) throw std::runtime_error("oracle: MiscInstrs row width mismatch");
+}
+static inline void misc_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  if (n > height) throw std::runtime_error("oracle: more events than rows");
+  for (size_t i = 0; i < height; i++) {
+    if (i < n) misc_row(ev + MISC_EVENT_WORDS * i, out + i * MISC_WIDTH);
+    else for (int k = 0; k < MISC_WIDTH; k++) out[i * MISC_WIDTH + k] = 0;
+  }
+}
+
 }  // namespace zko

@@ -4,7 +4,8 @@
 //! bytes cross PCIe and no layout change runs (KeccakSponge: 1.5 KB of record per 24 rows x 3531 columns = 339 KB of rows).
 //!
 //! * ALU / control-flow chips: `AluEvent`, `BranchEvent`, `JumpEvent`, `MovCondEvent` are `#[repr(C)]` seven-word records,
-//!   `CompAluEvent` (Mul) and `MemInstrEvent` (MemoryInstrs) sixteen-word ones (crates/core/executor/src/events/instr.rs);
+//!   `CompAluEvent` (Mul) and `MemInstrEvent` (MemoryInstrs) sixteen-word ones, `MiscEvent` (MiscInstrs) fifteen words
+//!   (crates/core/executor/src/events/instr.rs);
 //!   they cross as they lie in `record.add_sub_events` etc. (`event_vector`).  The byte-lookup multiplicities these
 //!   chips' `event_to_row` also emits come from `generate_dependencies`, which the caller still runs on the host.
 //! * MemoryLocal: seven-word `MemoryLocalEvent` records (crates/core/executor/src/events/memory.rs:228-237), four to a row;
@@ -128,6 +129,7 @@ const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::JumpEvent>
 const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MovCondEvent>() == 28);
 const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::CompAluEvent>() == 64);
 const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MemInstrEvent>() == 64);
+const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MiscEvent>() == 60);
 
 /// Chip name (`MachineAir::name`) -> the record field its `generate_trace` walks, with the chip's column count
 /// (csrc/tracegen.cuh `alu_width`).
@@ -144,6 +146,7 @@ pub fn event_vector(record: &ExecutionRecord, chip: &str) -> Option<EventVector>
         "MovCond" => vector_of(&record.movcond_events, 32),
         "Mul" => vector_of(&record.mul_events, 58),
         "MemoryInstrs" => vector_of(&record.memory_instr_events, 79),
+        "MiscInstrs" => vector_of(&record.misc_events, 72),
         _ => None,
     }
 }

@@ -49,7 +49,8 @@ CHIPS["Mul"] = (lambda n, s: tg.synthetic_mul_events(n, seed=s), orc.mul_trace)
 CHIPS["MemoryInstrs"] = (lambda n, s: tg.synthetic_mem_instr_events(n, seed=s), orc.mem_instr_trace)
 CHIPS["MemoryLocal"] = (lambda n, s: tg.synthetic_memory_local_events(n, seed=s), orc.memory_local_trace)
 CHIPS["Cpu"] = (lambda n, s: tg.synthetic_cpu_events(n, seed=s), orc.cpu_trace)
-GOLDEN = {"Mul": "mul_rows.json", "MemoryInstrs": "mem_instr_rows.json", "Cpu": "cpu_rows.json"}
+CHIPS["MiscInstrs"] = (lambda n, s: tg.synthetic_misc_events(n, seed=s), orc.misc_trace)
+GOLDEN = {"Mul": "mul_rows.json", "MemoryInstrs": "mem_instr_rows.json", "Cpu": "cpu_rows.json", "MiscInstrs": "misc_rows.json"}
 
 prover = B200Prover(synthetic.mini_case().machine, device=0)
 bad = 0

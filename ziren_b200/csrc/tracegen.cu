@@ -71,6 +71,7 @@ void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* ou
     case ALU_MEMINSTR: alu_rows_kernel<ALU_MEMINSTR><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     case ALU_MEMLOCAL: alu_rows_kernel<ALU_MEMLOCAL><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     case ALU_CPU: alu_rows_kernel<ALU_CPU><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    case ALU_MISC: alu_rows_kernel<ALU_MISC><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
     default: throw std::runtime_error("zkb200: alu_trace: unknown chip");
   }
   ZKB_CHECK_LAUNCH();
@@ -100,7 +101,7 @@ void keccak_sponge_trace(const u32* blocks_dev, size_t n_blocks, size_t height, 
 }
 
 int alu_chip_by_name(const char* name) {
-  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond", "Mul", "MemoryInstrs", "MemoryLocal", "Cpu"};
+  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond", "Mul", "MemoryInstrs", "MemoryLocal", "Cpu", "MiscInstrs"};
   for (int i = 0; i < ALU_NCHIPS; i++) if (!strcmp(name, names[i])) return i;
   return -1;
 }

@@ -12,7 +12,7 @@
 namespace zkb {
 
 enum AluChip : int { ALU_ADDSUB = 0, ALU_BITWISE = 1, ALU_LT = 2, ALU_SLL = 3, ALU_SR = 4, ALU_CLOCLZ = 5, ALU_BRANCH = 6, ALU_JUMP = 7,
-                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_MEMINSTR = 10, ALU_MEMLOCAL = 11, ALU_CPU = 12, ALU_NCHIPS = 13 };
+                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_MEMINSTR = 10, ALU_MEMLOCAL = 11, ALU_CPU = 12, ALU_MISC = 13, ALU_NCHIPS = 14 };
 // opcodes as numbered by crates/core/executor/src/opcode.rs:25-49 (#[repr(u8)])
 enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_ROR = 12, OP_SLT = 13, OP_SLTU = 14,
              OP_AND = 15, OP_OR = 16, OP_XOR = 17, OP_NOR = 18, OP_CLZ = 19, OP_CLO = 20, OP_BEQ = 21, OP_BGEZ = 22, OP_BGTZ = 23,
@@ -20,11 +20,14 @@ enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_RO
 
 KB_HD constexpr int alu_width(int chip) {
   return chip == ALU_ADDSUB ? 19 : chip == ALU_BITWISE ? 18 : chip == ALU_LT ? 32 : chip == ALU_SLL ? 44 : chip == ALU_SR ? 67
-       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : chip == ALU_MEMINSTR ? 79 : chip == ALU_MEMLOCAL ? 56 : chip == ALU_CPU ? 67 : 32;
+       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : chip == ALU_MEMINSTR ? 79 : chip == ALU_MEMLOCAL ? 56 : chip == ALU_CPU ? 67 : chip == ALU_MISC ? 72 : 32;
 }
 // 32-bit words per event record: seven for AluEvent / BranchEvent / JumpEvent / MovCondEvent, sixteen for CompAluEvent (Mul)
 // and MemInstrEvent (MemoryInstrs), twenty-eight for the flattened CpuEvent + Instruction (zkb200_cpu_event)
-KB_HD constexpr int alu_event_words(int chip) { return chip == ALU_CPU ? 28 : chip == ALU_MUL || chip == ALU_MEMINSTR ? 16 : 7; }
+// fifteen for MiscEvent (MiscInstrs)
+KB_HD constexpr int alu_event_words(int chip) {
+  return chip == ALU_CPU ? 28 : chip == ALU_MUL || chip == ALU_MEMINSTR ? 16 : chip == ALU_MISC ? 15 : 7;
+}
 // events per row: MemoryLocal packs four seven-word MemoryLocalEvents into a row, every other chip has one event per row
 KB_HD constexpr int alu_events_per_row(int chip) { return chip == ALU_MEMLOCAL ? 4 : 1; }
 
@@ -437,6 +440,72 @@ KB_HD void fill_cpu(const u32* e, u32* r) {
   r[66] = tg_b((bit & (CPU_M_STORES_NO_SC | CPU_M_BRANCH | CPU_M_TEQ)) != 0);
 }
 
+// MiscInstrsChip::event_to_row, crates/core/machine/src/misc/others/trace.rs:91-275 (C++ twin include/misc_instrs.hpp).  Event:
+// MiscEvent (crates/core/executor/src/events/instr.rs:241-261) as its 15 #[repr(C)] words {shard, clk, pc, next_pc, opcode, a,
+// b, c, prev_a, hi_record{value, shard, timestamp, prev_value, prev_shard, prev_timestamp}}.  Columns (72,
+// misc/others/columns/mod.rs): shard, clk, pc, next_pc, op_a[4], prev_a[4], op_b[4], op_c[4], a 44-column UNION viewed per
+// opcode family, is_sext, is_ins, is_ext, is_maddu, is_msubu, is_madd, is_msub, is_teq.  Union views (columns/*.rs):
+//   maddsub  mul_lo[4], mul_hi[4], add_operation{value[4], value_hi[4], carry[7]}, src2_hi[4], src2_lo[4], op_hi_access[13]
+//   sext     most_sig_bit, sig_byte, a_eq_b{is_zero_byte[4]{inverse, result}, lower_half_zero, upper_half_zero, result}, is_seb, is_seh
+//   ext      lsb, msbd, sll_val[4]            ins   lsb, msb, ror_val[4], srl1_val[4], srl_val[4], sll_val[4], add_val[4]
+constexpr int MISC_WIDTH = 72, MISC_EVENT_WORDS = 15;
+enum : u32 { OP_INS = 45, OP_MADDU = 46, OP_MSUBU = 47, OP_MADD = 48, OP_MSUB = 49, OP_EXT = 53, OP_TEQ = 54, OP_SEXT = 55 };
+KB_HD void fill_misc(const u32* e, u32* r, const u32* inv255) {
+  const u32 shard = e[0], clk = e[1], pc = e[2], next_pc = e[3], op = e[4] & 0xffu, a = e[5], b = e[6], c = e[7], prev_a = e[8];
+  r[0] = tg_f(shard); r[1] = tg_f(clk); r[2] = tg_f(pc); r[3] = tg_f(next_pc);
+  tg_word(r + 4, a); tg_word(r + 8, prev_a); tg_word(r + 12, b); tg_word(r + 16, c);
+  u32* u = r + 20;
+  for (int i = 0; i < 44; i++) u[i] = 0;
+  r[64] = tg_b(op == OP_SEXT); r[65] = tg_b(op == OP_INS); r[66] = tg_b(op == OP_EXT); r[67] = tg_b(op == OP_MADDU);
+  r[68] = tg_b(op == OP_MSUBU); r[69] = tg_b(op == OP_MADD); r[70] = tg_b(op == OP_MSUB); r[71] = tg_b(op == OP_TEQ);
+  if (op == OP_SEXT || op == OP_TEQ) {
+    const bool seh = c > 0;
+    const u32 sig_byte = seh ? (b >> 8) & 0xffu : b & 0xffu;
+    u[0] = tg_b(sig_byte >> 7); u[1] = tg_f(sig_byte);
+    u32 zero_mask = 0;
+    for (int i = 0; i < 4; i++) {
+      const u32 x = (a >> (8 * i)) & 0xffu, y = (b >> (8 * i)) & 0xffu;
+      // 1 / (x - y): the table holds 1/d for d = 1..255, a negative difference negates it
+      u[2 + 2 * i] = x > y ? inv255[x - y] : x < y ? KB_P - inv255[y - x] : 0u;
+      u[3 + 2 * i] = tg_b(x == y);
+      zero_mask |= (u32)(x == y) << i;
+    }
+    u[10] = tg_b((zero_mask & 3u) == 3u); u[11] = tg_b((zero_mask & 12u) == 12u); u[12] = tg_b(zero_mask == 15u);
+    u[13] = tg_b(!seh); u[14] = tg_b(seh);
+  } else if (op >= OP_MADDU && op <= OP_MSUB) {
+    const bool is_sign = op == OP_MADD || op == OP_MSUB, is_add = op == OP_MADDU || op == OP_MADD;
+    const u64 multiply = is_sign ? (u64)((int64_t)(int32_t)b * (int64_t)(int32_t)c) : (u64)b * (u64)c;
+    const u32 hv = e[9], hshard = e[10], hts = e[11], hprev_value = e[12], hprev_shard = e[13], hprev_ts = e[14];
+    tg_word(u + 0, (u32)multiply); tg_word(u + 4, (u32)(multiply >> 32));
+    const u32 src2_lo = is_add ? prev_a : a, src2_hi = is_add ? hprev_value : hv;
+    const u64 src2 = ((u64)src2_hi << 32) + src2_lo, sum = multiply + src2;
+    tg_long(u + 8, sum);
+#pragma unroll
+    for (int k = 0; k < 7; k++) {                   // carry out of the low k + 1 bytes
+      const u64 mask = (1ull << (8 * (k + 1))) - 1ull;
+      u[16 + k] = tg_b((((multiply & mask) + (src2 & mask)) >> (8 * (k + 1))) != 0);
+    }
+    tg_word(u + 23, src2_hi); tg_word(u + 27, src2_lo);
+    tg_word(u + 31, hprev_value); tg_word(u + 35, hv);
+    u[39] = tg_f(hprev_shard); u[40] = tg_f(hprev_ts);
+    const bool same = hprev_shard == hshard;
+    u[41] = tg_b(same);
+    const u32 d = (same ? hts - hprev_ts : hshard - hprev_shard) - 1u;
+    u[42] = tg_f(d & 0xffffu); u[43] = tg_f((d >> 16) & 0xffu);
+  } else if (op == OP_EXT) {
+    const u32 lsb = c & 0x1fu, msbd = c >> 5;
+    u[0] = tg_f(lsb); u[1] = tg_f(msbd);
+    tg_word(u + 2, b << ((31u - lsb - msbd) & 31u));
+  } else if (op == OP_INS) {
+    const u32 lsb = c & 0x1fu, msb = c >> 5;
+    const u32 ror_val = lsb ? (prev_a >> lsb) | (prev_a << (32u - lsb)) : prev_a;
+    const u32 srl1_val = ror_val >> 1, srl_val = srl1_val >> ((msb - lsb) & 31u), sll_val = b << ((31u - msb + lsb) & 31u);
+    u[0] = tg_f(lsb); u[1] = tg_f(msb);
+    tg_word(u + 2, ror_val); tg_word(u + 6, srl1_val); tg_word(u + 10, srl_val); tg_word(u + 14, sll_val);
+    tg_word(u + 18, srl_val + sll_val);
+  }
+}
+
 // Rows past the last event (generate_trace of each chip): zeros, except the dummy rows that keep the
 // shift and count-leading chips' constraints satisfied (sll/mod.rs:160-173, sr/mod.rs:184-187,
 // clo_clz/mod.rs:150-163).
@@ -465,6 +534,7 @@ KB_HD void fill_alu_row(int chip, const u32* w, u32* r, const u32* inv255, int n
     case ALU_MEMINSTR: fill_mem_instr(w, r); break;
     case ALU_MEMLOCAL: fill_memory_local(w, n_valid, r); break;
     case ALU_CPU: fill_cpu(w, r); break;
+    case ALU_MISC: fill_misc(w, r, inv255); break;
     default: fill_mov_cond(w, r, inv255); break;
   }
 }

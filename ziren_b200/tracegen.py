@@ -43,6 +43,7 @@ EVENT_BYTES = 28
 
 
 CPU_WIDTH, CPU_EVENT_WORDS = 67, 28            # zkb200_cpu_event: the flattened CpuEvent + Instruction
+MISC_WIDTH, MISC_EVENT_WORDS = 72, 15          # MiscEvent
 PACKED_CHIPS = {"MemoryLocal": (56, 4)}       # width, events per row (seven-word MemoryLocalEvent records)
 
 
@@ -51,6 +52,8 @@ def width(chip: str) -> int:
         return PACKED_CHIPS[chip][0]
     if chip == "Cpu":
         return CPU_WIDTH
+    if chip == "MiscInstrs":
+        return MISC_WIDTH
     return (ALU_CHIPS.get(chip) or COMP_CHIPS[chip])[0]
 
 
@@ -61,6 +64,8 @@ def events_per_row(chip: str) -> int:
 def event_words(chip: str) -> int:
     if chip == "Cpu":
         return CPU_EVENT_WORDS
+    if chip == "MiscInstrs":
+        return MISC_EVENT_WORDS
     return COMP_EVENT_WORDS if chip in COMP_CHIPS else EVENT_WORDS
 
 
@@ -415,4 +420,82 @@ def synthetic_cpu_events(n: int, seed: int = 0, shard: int = 3) -> np.ndarray:
         ps, pt = prev(clk + off)
         ev[:, col0], ev[:, col0 + 1], ev[:, col0 + 2], ev[:, col0 + 3], ev[:, col0 + 4] = val, shard, clk + off, ps, pt
         ev[imm, col0:col0 + 5] = 0
+    return ev
+
+
+MISC_OPCODES = ("SEXT", "EXT", "INS", "MADDU", "MSUBU", "MADD", "MSUB", "TEQ")
+
+
+def synthetic_misc_events(n: int, seed: int = 0, shard: int = 3) -> np.ndarray:
+    """n well-formed MiscEvent records of the MiscInstrs chip as (n, 15) uint32 words {shard, clk, pc, next_pc, opcode, a, b,
+    c, prev_a, hi_record{value, shard, timestamp, prev_value, prev_shard, prev_timestamp}}
+    (crates/core/executor/src/events/instr.rs:241-261), `a` and the HI write following execute_sext / ext / ins / maddu /
+    msubu / madd / msub / teq (crates/core/executor/src/executor.rs:1686-1828): SEXT with c = 0 (byte) and c > 0 (halfword),
+    EXT with lsb + msbd <= 31, INS with lsb <= msb, TEQ with a != b except for shared low bytes."""
+    rng = np.random.default_rng(0x315C + seed)
+    ev = np.zeros((n, MISC_EVENT_WORDS), np.uint32)
+    if n == 0:
+        return ev
+    O = ALL_OPCODES
+    u32 = lambda: rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    op = rng.choice([O[o] for o in MISC_OPCODES], n).astype(np.uint32)
+    op[: min(n, 8)] = [O[o] for o in MISC_OPCODES][: min(n, 8)]
+    b, c, prev_a = u32(), u32(), u32()
+    b[rng.integers(0, 4, n) == 0] |= np.uint32(0x8080)                     # negative bytes / halfwords
+    a = np.zeros(n, np.uint32)
+    hi_prev, hi_new = u32(), np.zeros(n, np.uint32)
+    full = np.uint64(0xFFFFFFFFFFFFFFFF)
+    # SEXT
+    m = op == O["SEXT"]
+    c[m] = rng.integers(0, 2, int(m.sum()))
+    a[m] = np.where(c[m] > 0, _sext(b[m] & np.uint32(0xFFFF), 16), _sext(b[m] & np.uint32(0xFF), 8))
+    # TEQ: a = src1, b = src2, differing, some bytes equal
+    m = op == O["TEQ"]
+    c[m] = 0
+    flip = (np.uint32(0xFF) << (np.uint32(8) * rng.integers(0, 4, int(m.sum())).astype(np.uint32))).astype(np.uint32)
+    a[m] = b[m] ^ np.where(rng.integers(0, 2, int(m.sum())) == 0, flip, rng.integers(1, 1 << 32, int(m.sum()), dtype=np.uint64).astype(np.uint32))
+    # EXT: a = (b & mask(msbd + lsb + 1)) >> lsb
+    m = op == O["EXT"]
+    k = int(m.sum())
+    lsb = rng.integers(0, 32, k)
+    msbd = np.array([rng.integers(0, 32 - l) for l in lsb], np.int64) if k else np.zeros(0, np.int64)
+    c[m] = (lsb | (msbd << 5)).astype(np.uint32)
+    top = (msbd + lsb + 1).astype(np.uint64)
+    mask = np.where(top == 32, np.uint64(0xFFFFFFFF), (np.uint64(1) << top) - np.uint64(1)).astype(np.uint32)
+    a[m] = (b[m] & mask) >> lsb.astype(np.uint32)
+    # INS: a = (prev_a & ~field) | ((b << lsb) & field)
+    m = op == O["INS"]
+    k = int(m.sum())
+    lsb = rng.integers(0, 32, k)
+    msb = np.array([rng.integers(l, 32) for l in lsb], np.int64) if k else np.zeros(0, np.int64)
+    c[m] = (lsb | (msb << 5)).astype(np.uint32)
+    wid = (msb - lsb + 1).astype(np.uint64)
+    mask = np.where(wid == 32, np.uint64(0xFFFFFFFF), (np.uint64(1) << wid) - np.uint64(1)).astype(np.uint32)
+    field = (mask.astype(np.uint64) << lsb.astype(np.uint64)).astype(np.uint32)
+    a[m] = (prev_a[m] & ~field) | ((b[m].astype(np.uint64) << lsb.astype(np.uint64)).astype(np.uint32) & field)
+    # MADDU / MSUBU / MADD / MSUB: (hi, lo) +- b * c
+    for name, signed, add in (("MADDU", False, True), ("MSUBU", False, False), ("MADD", True, True), ("MSUB", True, False)):
+        m = op == O[name]
+        if not m.any():
+            continue
+        if signed:
+            prod = (b[m].astype(np.int32).astype(np.int64) * c[m].astype(np.int32).astype(np.int64)).astype(np.uint64)
+        else:
+            prod = b[m].astype(np.uint64) * c[m].astype(np.uint64)
+        addend = (hi_prev[m].astype(np.uint64) << np.uint64(32)) + prev_a[m].astype(np.uint64)
+        out = (addend + prod) & full if add else (addend - prod) & full
+        a[m] = (out & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        hi_new[m] = (out >> np.uint64(32)).astype(np.uint32)
+    is_mac = (op >= O["MADDU"]) & (op <= O["MSUB"])
+    ev[:, 0] = shard
+    ev[:, 1] = (5 + 5 * np.arange(1, n + 1)).astype(np.uint32)
+    ev[:, 2] = rng.integers(0, kb.P - 16, n) & ~np.uint32(3)
+    ev[:, 3] = ev[:, 2] + 4
+    ev[:, 4], ev[:, 5], ev[:, 6], ev[:, 7], ev[:, 8] = op, a, b, c, prev_a
+    earlier = rng.integers(0, 6, n) == 0
+    ts = ev[:, 1] + 4
+    ev[:, 9], ev[:, 10], ev[:, 11], ev[:, 12] = hi_new, shard, ts, hi_prev
+    ev[:, 13] = np.where(earlier, rng.integers(1, shard, n), shard)
+    ev[:, 14] = np.where(earlier, rng.integers(0, 1 << 22, n), ts - rng.integers(1, 9, n)).astype(np.uint32)
+    ev[~is_mac, 9:15] = 0
     return ev
