@@ -219,11 +219,33 @@ typedef struct {
   uint32_t flags, op_word, op_b, op_c;
   uint32_t a_record[6], b_record[5], c_record[5];
 } zkb200_cpu_event;
+/* "DivRem" (crates/core/machine/src/alu/divrem/mod.rs:229-364, C++ twin include/div_rem.hpp; 106 columns) takes 64-byte
+ * `CompAluEvent` records as they lie in record.divrem_events, like "Mul".  "SyscallInstrs"
+ * (crates/core/machine/src/syscall/instructions/trace.rs:89-177, C++ twin include/syscall_instrs.hpp; 77 columns) takes the
+ * 56-byte `SyscallEvent` records {pc, next_pc, shard, clk, a_record[6], a_record_is_real, syscall_id, arg1, arg2}
+ * (crates/core/executor/src/events/syscall.rs:8-29) of record.syscall_events.  "SyscallCore" and "SyscallPrecompile"
+ * (crates/core/machine/src/syscall/chip.rs:184-268, C++ twin include/syscall.hpp; 11 columns) take `SyscallEvent` records too:
+ * SyscallCore the events generate_trace keeps (a_record.prev_value byte 2 == 1 or byte 1 != 0, chip.rs:233-240 - the caller
+ * filters, the rows are dense), SyscallPrecompile one event per precompile event whose a_record carries what row_fn reads from
+ * the PrecompileEvent, in the convention of syscall.hpp precompile_event_to_row: prev_value = 1 and value = v0 for
+ * PrecompileEvent::Linux, prev_value = 0 otherwise.
+ * "MemoryGlobalInit" / "MemoryGlobalFinalize" (crates/core/machine/src/memory/global.rs:115-192, C++ twin
+ * include/memory_global.hpp for the per-event columns; 111 columns): the `MemoryInitializeFinalizeEvent`s
+ * (crates/core/executor/src/events/memory.rs:138-149) SORTED BY ADDRESS as generate_trace sorts them, each followed by the
+ * address its row is compared with and by its position - the two things the reference's sequential loop (global.rs:150-180)
+ * takes from the neighbouring row, so that every row depends on its own record only. */
+typedef struct {
+  uint32_t addr, value, shard, timestamp;   /* MemoryInitializeFinalizeEvent */
+  uint32_t prev_addr;                       /* the previous event's addr; first event: the public values' previous_init_addr /
+                                               previous_finalize_addr (their *_addr_bits recombined), 0 in the first shard */
+  uint32_t position;                        /* bit 0: first event of the table, bit 1: last event */
+} zkb200_memory_global_event;
 /* NUM_*_COLS of the chip, -1 if this library has no row filler for it */
 int zkb200_alu_trace_width(const char* chip);
 /* events: zkb200_alu_event[]; zkb200_flow_event[] for "Branch" / "Jump"; seven-word MovCondEvent records for "MovCond";
  * CompAluEvent / MemInstrEvent / MemoryLocalEvent / MiscEvent records as they lie for "Mul" / "MemoryInstrs" / "MemoryLocal" /
- * "MiscInstrs";
+ * "MiscInstrs"; CompAluEvent records for "DivRem"; SyscallEvent records for "SyscallCore" / "SyscallPrecompile" /
+ * "SyscallInstrs"; zkb200_memory_global_event[] for "MemoryGlobalInit" / "MemoryGlobalFinalize";
  * zkb200_cpu_event[] for "Cpu" */
 int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* events, size_t n_events,
                               unsigned log_height, uint32_t* out, int col_major);

@@ -292,6 +292,24 @@ int zko_misc_trace(const u32* ev, size_t n, size_t height, u32* out) {
     return 0;
   } catch (const std::exception& e) { return fail(e); }
 }
+// DivRem / SyscallCore / SyscallPrecompile / SyscallInstrs rows (tracegen.h chip_trace): events n x chip_event_words, out
+// height x chip_trace_width row-major canonical
+int zko_chip_trace_width(const char* chip) { return chip_trace_width(chip); }
+int zko_chip_event_words(const char* chip) { return chip_event_words(chip); }
+int zko_chip_trace(const char* chip, const u32* ev, size_t n, size_t height, u32* out) {
+  try {
+    chip_trace(chip, ev, n, height, out);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+// MemoryGlobalInit / MemoryGlobalFinalize rows (tracegen.h memory_global_trace): address-sorted events n x 4 words and the
+// public values' previous address, out height x 111 row-major canonical
+int zko_memory_global_trace(const u32* ev, size_t n, u32 previous_addr, size_t height, u32* out) {
+  try {
+    memory_global_trace(ev, n, previous_addr, height, out);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
 // trace generation of the KeccakSponge chip (tracegen_keccak.h): n_blocks records of KS_REC_WORDS words,
 // out height x 3531 row-major canonical
 int zko_keccak_sponge_width() { return KS_WIDTH; }

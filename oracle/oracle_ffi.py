@@ -212,6 +212,56 @@ def ref_misc_rows(events):
     return out
 
 
+ROW_CHIPS = ("DivRem", "SyscallCore", "SyscallPrecompile", "SyscallInstrs")
+MEMGLOBAL_WIDTH = 111
+
+
+def chip_trace_width(chip):
+    return lib().zko_chip_trace_width(chip.encode())
+
+
+def chip_event_words(chip):
+    return lib().zko_chip_event_words(chip.encode())
+
+
+def chip_trace(chip, events, height):
+    """DivRem (CompAluEvent, 16 words) / SyscallCore, SyscallPrecompile, SyscallInstrs (SyscallEvent, 14 words): (height, width)
+    canonical rows, zero padding rows."""
+    w, ew = chip_trace_width(chip), chip_event_words(chip)
+    if w < 0:
+        raise ValueError(f"oracle: no row filler for chip {chip}")
+    ev = _a(events).reshape(-1, ew)
+    out = np.zeros((int(height), w), np.uint32)
+    if lib().zko_chip_trace(chip.encode(), _p(ev), C.c_size_t(ev.shape[0]), C.c_size_t(int(height)), _p(out)):
+        raise RuntimeError(err())
+    return out
+
+
+def memory_global_trace(events, previous_addr, height):
+    """events: (n, 4) uint32 address-sorted MemoryInitializeFinalizeEvent records {addr, value, shard, timestamp};
+    previous_addr: the public values' previous_init / previous_finalize address; (height, 111) canonical rows."""
+    ev = _a(events).reshape(-1, 4)
+    out = np.zeros((int(height), MEMGLOBAL_WIDTH), np.uint32)
+    if lib().zko_memory_global_trace(_p(ev), C.c_size_t(ev.shape[0]), C.c_uint32(int(previous_addr)), C.c_size_t(int(height)), _p(out)):
+        raise RuntimeError(err())
+    return out
+
+
+def ref_chip_rows(chip, events, event_words):
+    """Rows of the reference's own div_rem.hpp / syscall.hpp / syscall_instrs.hpp / memory_global.hpp event_to_row (Montgomery
+    words), or None without oracle/_ref."""
+    l = ref_core_lib()
+    if l is None or not hasattr(l, "ref_chip_event_to_rows"):
+        return None
+    l.ref_chip_num_cols.restype = C.c_uint
+    w = l.ref_chip_num_cols(chip.encode())
+    ev = _a(events).reshape(-1, event_words)
+    out = np.zeros((ev.shape[0], w), np.uint32)
+    if l.ref_chip_event_to_rows(chip.encode(), _p(ev), C.c_size_t(ev.shape[0]), _p(out)):
+        raise RuntimeError("reference row filler failed")
+    return out
+
+
 KS_WIDTH, KS_REC_WORDS = 3531, 384
 
 

@@ -4,6 +4,7 @@
 #include <cassert>
 #include <algorithm>
 #include <cstring>
+#include <string>
 #include "zkm-core-machine-sys-cbindgen.hpp"
 #include "kb31_t.hpp"
 #include "add_sub.hpp"
@@ -21,6 +22,10 @@
 #include "memory_local.hpp"
 #include "cpu.hpp"
 #include "misc_instrs.hpp"
+#include "div_rem.hpp"
+#include "syscall.hpp"
+#include "syscall_instrs.hpp"
+#include "memory_global.hpp"
 
 using namespace zkm_core_machine_sys;
 
@@ -188,6 +193,48 @@ int ref_misc_event_to_rows(const uint32_t* ev, size_t n, uint32_t* rows) {
     const uint32_t* e = ev + 15 * i;
     MiscEvent m{e[0], e[1], e[2], e[3], (Opcode)(e[4] & 0xff), e[5], e[6], e[7], e[8], MemoryWriteRecord{e[9], e[10], e[11], e[12], e[13], e[14]}};
     misc_instrs::event_to_row<kb31_t>(m, *reinterpret_cast<MiscInstrColumns<kb31_t>*>(rows + i * w));
+  }
+  return 0;
+}
+// rows of the reference's div_rem.hpp / syscall.hpp / syscall_instrs.hpp / memory_global.hpp event_to_row by chip name
+// (MachineAir::name); events as the #[repr(C)] words of CompAluEvent (16), SyscallEvent (14), MemoryInitializeFinalizeEvent (4);
+// rows n x num_cols Montgomery words.  memory_global.hpp fills only the columns that depend on the event alone.
+static SyscallEvent syscall_event_from_words(const uint32_t* e) {
+  return SyscallEvent{e[0], e[1], e[2], e[3], MemoryWriteRecord{e[4], e[5], e[6], e[7], e[8], e[9]}, (e[10] & 0xff) != 0, e[11], e[12], e[13]};
+}
+unsigned ref_chip_num_cols(const char* chip) {
+  const std::string c(chip);
+  if (c == "DivRem") return ncols<DivRemCols<kb31_t>>();
+  if (c == "SyscallCore" || c == "SyscallPrecompile") return ncols<SyscallCols<kb31_t>>();
+  if (c == "SyscallInstrs") return ncols<SyscallInstrColumns<kb31_t>>();
+  if (c == "MemoryGlobalInit" || c == "MemoryGlobalFinalize") return ncols<MemoryInitCols<kb31_t>>();
+  return 0;
+}
+int ref_chip_event_to_rows(const char* chip, const uint32_t* ev, size_t n, uint32_t* rows) {
+  static_assert(sizeof(SyscallEvent) == 14 * sizeof(uint32_t), "SyscallEvent is fourteen words");
+  static_assert(sizeof(CompAluEvent) == 16 * sizeof(uint32_t), "CompAluEvent is sixteen words");
+  const std::string c(chip);
+  const unsigned w = ref_chip_num_cols(chip);
+  if (!w) return 1;
+  std::memset(rows, 0, n * w * sizeof(uint32_t));
+  for (size_t i = 0; i < n; i++) {
+    uint32_t* r = rows + i * w;
+    if (c == "DivRem") {
+      const uint32_t* e = ev + 16 * i;
+      CompAluEvent m{e[0], e[1], e[2], e[3], (Opcode)(e[4] & 0xff), e[5], e[6], e[7], e[8],
+                     MemoryWriteRecord{e[9], e[10], e[11], e[12], e[13], e[14]}, (e[15] & 0xff) != 0};
+      div_rem::event_to_row<kb31_t>(m, *reinterpret_cast<DivRemCols<kb31_t>*>(r));
+    } else if (c == "SyscallCore") {
+      syscall::core_event_to_row<kb31_t>(syscall_event_from_words(ev + 14 * i), *reinterpret_cast<SyscallCols<kb31_t>*>(r));
+    } else if (c == "SyscallPrecompile") {
+      syscall::precompile_event_to_row<kb31_t>(syscall_event_from_words(ev + 14 * i), *reinterpret_cast<SyscallCols<kb31_t>*>(r));
+    } else if (c == "SyscallInstrs") {
+      syscall_instrs::event_to_row<kb31_t>(syscall_event_from_words(ev + 14 * i), *reinterpret_cast<SyscallInstrColumns<kb31_t>*>(r));
+    } else {
+      const uint32_t* e = ev + 4 * i;
+      MemoryInitializeFinalizeEvent m{e[0], e[1], e[2], e[3]};
+      memory_global::event_to_row<kb31_t, kb31_septic_extension_t>(&m, c == "MemoryGlobalFinalize", reinterpret_cast<MemoryInitCols<kb31_t>*>(r));
+    }
   }
   return 0;
 }

@@ -24,8 +24,12 @@ enum class Opcode : uint8_t {
   SWR = 43, SC = 44, INS = 45, MADDU = 46, MSUBU = 47, MADD = 48, MSUB = 49, MEQ = 50, MNE = 51, WSBH = 52, EXT = 53,
   TEQ = 54, SEXT = 55, UNIMPL = 0xff,
 };
-// crates/core/executor/src/syscalls/code.rs:33, :154 (the two codes cpu.hpp names; utils.hpp:to_syscall_id takes the type)
-enum class SyscallCode : uint32_t { HALT = 0, SYS_EXT_GROUP = 4246 };
+// crates/core/executor/src/syscalls/code.rs:28-154 (the codes cpu.hpp and syscall_instrs.hpp name; utils.hpp:to_syscall_id
+// takes the type)
+enum class SyscallCode : uint32_t {
+  HALT = 0x00, ENTER_UNCONSTRAINED = 0x03, COMMIT = 0x10, COMMIT_DEFERRED_PROOFS = 0x1A, SYSHINTLEN = 0xF0, SYS_EXT_GROUP = 4246,
+};
+constexpr size_t PV_DIGEST_NUM_WORDS = 8;   // crates/stark/src/air/public_values.rs
 
 // crates/core/executor/src/events/instr.rs:11-26 (#[repr(C)])
 struct AluEvent {
@@ -279,6 +283,64 @@ template <class T> struct MiscInstrColumns {
   Word<T> op_a_value, prev_a_value, op_b_value, op_c_value;
   MiscSpecificCols<T> misc_specific_columns;
   T is_sext, is_ins, is_ext, is_maddu, is_msubu, is_madd, is_msub, is_teq;
+};
+
+// ---- DivRem (crates/core/machine/include/div_rem.hpp) ----
+// crates/core/machine/src/alu/divrem/mod.rs:109-204
+template <class T> struct DivRemCols {
+  T pc, next_pc;
+  Word<T> b, c, quotient, remainder, abs_remainder, abs_c, max_abs_c_or_1;
+  T c_times_quotient[LONG_WORD_SIZE];
+  T carry[LONG_WORD_SIZE];
+  IsZeroWordOperation<T> is_c_0;
+  T is_div, is_divu, is_mod, is_modu, is_overflow;
+  IsEqualWordOperation<T> is_overflow_b, is_overflow_c;
+  T b_msb, rem_msb, c_msb, b_neg, rem_neg, c_neg, remainder_check_multiplicity;
+  MemoryReadWriteCols<T> op_hi_access;
+  T shard, clk;
+};
+
+// ---- SyscallCore / SyscallPrecompile / SyscallInstrs (crates/core/machine/include/syscall.hpp, syscall_instrs.hpp) ----
+// crates/core/executor/src/events/syscall.rs:8-29 (#[repr(C)])
+struct SyscallEvent {
+  uint32_t pc, next_pc, shard, clk;
+  MemoryWriteRecord a_record;
+  bool a_record_is_real;
+  uint32_t syscall_id, arg1, arg2;
+};
+// crates/core/machine/src/syscall/chip.rs:71-107
+template <class T> struct SyscallCols { T shard, clk, syscall_id, arg1_lo, arg1_hi, arg2_lo, arg2_hi, result_lo, result_hi, is_linux, is_real; };
+// crates/core/machine/src/syscall/instructions/columns.rs:11-59
+template <class T> struct SyscallInstrColumns {
+  T pc, next_pc, shard, clk, num_extra_cycles, is_halt, is_sys_linux;
+  IsZeroOperation<T> is_prev_a1_zero;
+  T syscall_id;
+  Word<T> op_a_value, op_b_value, op_c_value, prev_a_value;
+  IsZeroOperation<T> is_enter_unconstrained, is_hint_len, is_halt_check, is_exit_group_check, is_commit, is_commit_deferred_proofs;
+  T index_bitmap[PV_DIGEST_NUM_WORDS];
+  KoalaBearWordRangeChecker<T> op_b_range_check, op_c_range_check;
+  T op_b_check, op_c_check, is_real;
+};
+
+// ---- MemoryGlobalInit / MemoryGlobalFinalize (crates/core/machine/include/memory_global.hpp) ----
+// crates/core/executor/src/events/memory.rs:138-149 (#[repr(C)])
+struct MemoryInitializeFinalizeEvent { uint32_t addr, value, shard, timestamp; };
+// crates/core/machine/src/operations/cmp.rs:295-298, koala_bear_range.rs:10-31
+template <class T, size_t N> struct AssertLtColsBits { T bit_flags[N]; };
+template <class T> struct KoalaBearBitDecomposition {
+  T bits[32];
+  T and_most_sig_byte_decomp_0_to_2, and_most_sig_byte_decomp_0_to_3, and_most_sig_byte_decomp_0_to_4,
+      and_most_sig_byte_decomp_0_to_5, and_most_sig_byte_decomp_0_to_6, and_most_sig_byte_decomp_0_to_7;
+};
+// crates/core/machine/src/memory/global.rs:210-245
+template <class T> struct MemoryInitCols {
+  T shard, timestamp, addr;
+  AssertLtColsBits<T, 32> lt_cols;
+  KoalaBearBitDecomposition<T> addr_bits;
+  T value[32];
+  T is_real, is_next_comp;
+  IsZeroOperation<T> is_prev_addr_zero;
+  T is_first_comp, is_last_addr;
 };
 
 }  // namespace zkm_core_machine_sys

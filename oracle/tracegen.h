@@ -18,6 +18,7 @@
 #pragma once
 #include <cstring>
 #include <stdexcept>
+#include <string>
 #include <vector>
 #include "kb.h"
 
@@ -541,6 +542,219 @@ static inline void misc_trace(const u32* ev, size_t n, size_t height, u32* out) 
   for (size_t i = 0; i < height; i++) {
     if (i < n) misc_row(ev + MISC_EVENT_WORDS * i, out + i * MISC_WIDTH);
     else for (int k = 0; k < MISC_WIDTH; k++) out[i * MISC_WIDTH + k] = 0;
+  }
+}
+
+// ---- shared column groups of the chips below ------------------------------------------------------------------------------
+// IsZeroOperation::populate_from_field_element (operations/is_zero.rs:29-40): inverse, result
+static inline void put_is_zero(RowWriter& w, F a) {
+  w.put(a.is_zero() ? 0 : finv(a).v);
+  w.flag(a.is_zero());
+}
+// IsZeroWordOperation::populate_from_field_element (operations/is_zero_word.rs): four IsZeroOperations over the bytes,
+// is_lower_half_zero, is_upper_half_zero, result
+static inline void put_is_zero_word(RowWriter& w, const F bytes[4]) {
+  bool z[4];
+  for (int i = 0; i < 4; i++) { z[i] = bytes[i].is_zero(); put_is_zero(w, bytes[i]); }
+  w.flag(z[0] && z[1]); w.flag(z[2] && z[3]); w.flag(z[0] && z[1] && z[2] && z[3]);
+}
+// IsEqualWordOperation::populate (operations/is_equal_word.rs): the zero test of the byte-wise differences a - b
+static inline void put_is_equal_word(RowWriter& w, u32 a, u32 b) {
+  F d[4];
+  for (int i = 0; i < 4; i++) d[i] = F((a >> (8 * i)) & 0xff) - F((b >> (8 * i)) & 0xff);
+  put_is_zero_word(w, d);
+}
+// MemoryReadWriteCols::populate of a write record {value, shard, timestamp, prev_value, prev_shard, prev_timestamp}
+// (memory/consistency/trace.rs:44-53, :70-100)
+static inline void put_write_access(RowWriter& w, const u32* rec) {
+  w.word(rec[3]); w.word(rec[0]);
+  w.put(rec[4]); w.put(rec[5]);
+  const bool use_clk = rec[4] == rec[1];
+  w.flag(use_clk);
+  const u32 diff_minus_one = (use_clk ? rec[2] - rec[5] : rec[1] - rec[4]) - 1;
+  w.put(diff_minus_one & 0xffff); w.put((diff_minus_one >> 16) & 0xff);
+}
+
+// ---- DivRem (crates/core/machine/src/alu/divrem/mod.rs:109-204 columns, :229-364 generate_trace; C++ twin include/div_rem.hpp,
+// which returns INT32_MAX instead of u32::MAX for c = 0, writes max(1, |c|) into abs_c and divides INT_MIN by -1 natively: the
+// Rust is the authority, the twin pins the rows where both agree) -----------------------------------------------------------
+// CompAluEvent as for Mul (16 words).  106 columns; padding rows are zero.
+enum { DIVREM_WIDTH = 106, K_MOD = 7, K_MODU = 8 };
+static inline void div_rem_row(const u32* e, u32* row) {
+  const u32 shard = e[0], clk = e[1], pc = e[2], next_pc = e[3], opcode = e[4] & 0xff, b = e[7], c = e[8];
+  if (opcode != K_DIV && opcode != K_DIVU && opcode != K_MOD && opcode != K_MODU) throw std::runtime_error("oracle: DivRem event with another opcode");
+  const bool is_signed = opcode == K_DIV || opcode == K_MOD;
+  // get_quotient_and_remainder (crates/core/executor/src/utils.rs:33-43): wrapping_div / wrapping_rem
+  u32 quotient, remainder;
+  if (c == 0) { quotient = 0xffffffffu; remainder = b; }
+  else if (is_signed) {
+    const long long sb = (int)b, sc = (int)c;           // 64-bit so that INT_MIN / -1 wraps instead of trapping
+    quotient = (u32)(sb / sc); remainder = (u32)(sb % sc);
+  } else { quotient = b / c; remainder = b % c; }
+  RowWriter w{row};
+  w.put(pc); w.put(next_pc);
+  w.word(b); w.word(c); w.word(quotient); w.word(remainder);
+  const auto unsigned_abs = [](u32 v) { return (v >> 31) ? (u32)(0 - v) : v; };
+  if (is_signed) {
+    const u32 abs_c = unsigned_abs(c);
+    w.word(unsigned_abs(remainder)); w.word(abs_c); w.word(abs_c > 1 ? abs_c : 1);
+  } else {
+    w.word(remainder); w.word(c); w.word(c > 1 ? c : 1);
+  }
+  unsigned char ctq[8], rb[8];
+  const u64 prod = is_signed ? (u64)((long long)(int)quotient * (long long)(int)c) : (u64)quotient * (u64)c;
+  const u64 rem64 = is_signed ? (u64)(long long)(int)remainder : (u64)remainder;
+  for (int i = 0; i < 8; i++) { ctq[i] = (unsigned char)(prod >> (8 * i)); rb[i] = (unsigned char)(rem64 >> (8 * i)); }
+  w.bytes(ctq, 8);
+  u32 carry[8];
+  for (int i = 0; i < 8; i++) {
+    u32 x = (u32)ctq[i] + (u32)rb[i];
+    if (i > 0) x += carry[i - 1];
+    carry[i] = x / 256;
+    w.put(carry[i]);
+  }
+  F cb[4];
+  for (int i = 0; i < 4; i++) cb[i] = F((c >> (8 * i)) & 0xff);
+  put_is_zero_word(w, cb);                                                   // is_c_0
+  w.flag(opcode == K_DIV); w.flag(opcode == K_DIVU); w.flag(opcode == K_MOD); w.flag(opcode == K_MODU);
+  w.flag(is_signed && b == 0x80000000u && c == 0xffffffffu);                 // is_overflow
+  put_is_equal_word(w, b, 0x80000000u); put_is_equal_word(w, c, 0xffffffffu);
+  const u32 b_msb = b >> 31, rem_msb = remainder >> 31, c_msb = c >> 31;
+  w.put(b_msb); w.put(rem_msb); w.put(c_msb);
+  w.put(is_signed ? b_msb : 0); w.put(is_signed ? rem_msb : 0); w.put(is_signed ? c_msb : 0);
+  w.flag(c != 0);                                                            // remainder_check_multiplicity = 1 - is_c_0.result
+  if (opcode == K_DIV || opcode == K_DIVU) { put_write_access(w, e + 9); w.put(shard); w.put(clk); }
+  else for (int i = 0; i < 15; i++) w.put(0);
+  if (w.at != DIVREM_WIDTH) throw std::runtime_error("oracle: DivRem row width mismatch");
+}
+
+// ---- SyscallCore / SyscallPrecompile (crates/core/machine/src/syscall/chip.rs:71-107 columns, :184-268 generate_trace; C++ twin
+// include/syscall.hpp) ---------------------------------------------------------------------------------------------------------
+// SyscallEvent (crates/core/executor/src/events/syscall.rs:8-29) as 14 words: pc, next_pc, shard, clk, a_record {value, shard,
+// timestamp, prev_value, prev_shard, prev_timestamp}, a_record_is_real, syscall_id, arg1, arg2.  Core: the events whose
+// prev_value has byte 2 = 1 or byte 1 != 0 (the caller filters, chip.rs:233-240), is_linux = byte 1 != 0.  Precompile: the
+// record carries what row_fn takes from the PrecompileEvent, in the convention of syscall.hpp precompile_event_to_row:
+// prev_value = 1 and value = v0 for PrecompileEvent::Linux, prev_value = 0 otherwise.  11 columns; padding rows are zero.
+enum { SYSCALL_WIDTH = 11, SYSCALL_EVENT_WORDS = 14 };
+static inline void syscall_row(const u32* e, bool precompile, u32* row) {
+  const u32 shard = e[2], clk = e[3], value = e[4], prev_value = e[7], syscall_id = e[11], arg1 = e[12], arg2 = e[13];
+  unsigned char a1[4], a2[4], rb[4];
+  for (int i = 0; i < 4; i++) { a1[i] = (unsigned char)(arg1 >> (8 * i)); a2[i] = (unsigned char)(arg2 >> (8 * i)); rb[i] = (unsigned char)(value >> (8 * i)); }
+  const bool is_linux = precompile ? prev_value == 1 : ((prev_value >> 8) & 0xff) != 0;
+  RowWriter w{row};
+  w.put(shard); w.put(clk); w.put(syscall_id);
+  w.put(a1[0] + a1[1] * 256u); w.put(a1[2] + a1[3] * 256u);
+  w.put(a2[0] + a2[1] * 256u); w.put(a2[2] + a2[3] * 256u);
+  w.put(is_linux ? rb[0] + rb[1] * 256u : 0); w.put(is_linux ? rb[2] + rb[3] * 256u : 0);
+  w.flag(is_linux); w.flag(true);
+  if (w.at != SYSCALL_WIDTH) throw std::runtime_error("oracle: Syscall row width mismatch");
+}
+
+// ---- SyscallInstrs (crates/core/machine/src/syscall/instructions/trace.rs:89-177, columns.rs:11-59; C++ twin
+// include/syscall_instrs.hpp) -----------------------------------------------------------------------------------------------
+// SyscallEvent records; 77 columns; padding rows are zero.  SyscallCode::syscall_id() = the low 16 bits of the code
+// (crates/core/executor/src/syscalls/code.rs:269-271).
+enum { SYSINSTR_WIDTH = 77, S_HALT = 0x00, S_ENTER_UNCONSTRAINED = 0x03, S_COMMIT = 0x10, S_COMMIT_DEFERRED_PROOFS = 0x1a,
+       S_SYSHINTLEN = 0xf0, S_SYS_EXT_GROUP = 4246 };
+static inline void syscall_instr_row(const u32* e, u32* row) {
+  const u32 pc = e[0], next_pc = e[1], shard = e[2], clk = e[3], value = e[4], prev_value = e[7], syscall_code = e[11], arg1 = e[12], arg2 = e[13];
+  const u32 id = prev_value & 0xffff;
+  unsigned char pa[4];
+  for (int i = 0; i < 4; i++) pa[i] = (unsigned char)(prev_value >> (8 * i));
+  const bool is_halt = id == S_HALT || id == S_SYS_EXT_GROUP, send_to_table = pa[1] != 0 || pa[2] == 1;
+  RowWriter w{row};
+  w.put(pc); w.put(next_pc); w.put(shard); w.put(clk);
+  w.put(pa[3]);                                     // num_extra_cycles = prev_a_value[3]
+  w.flag(is_halt); w.flag((prev_value & 0x0ff00) != 0);
+  put_is_zero(w, F(pa[1]));                         // is_prev_a1_zero
+  w.put(syscall_code);
+  w.word(value); w.word(arg1); w.word(arg2); w.word(prev_value);
+  const u32 tested[6] = {S_ENTER_UNCONSTRAINED, S_SYSHINTLEN, S_HALT, S_SYS_EXT_GROUP, S_COMMIT, S_COMMIT_DEFERRED_PROOFS};
+  for (int i = 0; i < 6; i++) put_is_zero(w, F(id) - F(tested[i]));
+  const bool commits = id == S_COMMIT || id == S_COMMIT_DEFERRED_PROOFS;
+  if (commits && arg1 >= 8) throw std::runtime_error("oracle: COMMIT with a digest index past PV_DIGEST_NUM_WORDS");
+  for (u32 i = 0; i < 8; i++) w.flag(commits && arg1 == i);
+  const bool b_check = send_to_table || is_halt, c_check = send_to_table || id == S_COMMIT_DEFERRED_PROOFS;
+  if (b_check) w.range_checker(arg1); else for (int i = 0; i < 14; i++) w.put(0);
+  if (c_check) w.range_checker(arg2); else for (int i = 0; i < 14; i++) w.put(0);
+  w.flag(b_check); w.flag(c_check); w.flag(true);
+  if (w.at != SYSINSTR_WIDTH) throw std::runtime_error("oracle: SyscallInstrs row width mismatch");
+}
+
+// ---- MemoryGlobalInit / MemoryGlobalFinalize (crates/core/machine/src/memory/global.rs:115-192 generate_trace, :210-245 columns;
+// C++ twin include/memory_global.hpp for the columns of the first, per-event loop) ------------------------------------------
+// The trace takes the address-SORTED MemoryInitializeFinalizeEvent vector {addr, value, shard, timestamp}
+// (events/memory.rs:138-149) and the previous address of the public values (previous_init_addr_bits /
+// previous_finalize_addr_bits recombined); row i compares with event i - 1, row 0 with the public previous address when that
+// is not zero.  111 columns; padding rows are zero.
+enum { MEMGLOBAL_WIDTH = 111, MEMGLOBAL_EVENT_WORDS = 4 };
+static inline void memory_global_trace(const u32* ev, size_t n, u32 previous_addr, size_t height, u32* out) {
+  if (n > height) throw std::runtime_error("oracle: more events than rows");
+  for (size_t i = 0; i < height; i++) {
+    u32* row = out + i * MEMGLOBAL_WIDTH;
+    if (i >= n) { for (int k = 0; k < MEMGLOBAL_WIDTH; k++) row[k] = 0; continue; }
+    const u32 addr = ev[4 * i], value = ev[4 * i + 1], shard = ev[4 * i + 2], timestamp = ev[4 * i + 3];
+    if (i > 0 && ev[4 * (i - 1)] >= addr) throw std::runtime_error("oracle: memory events are not sorted by address");
+    u32 lt[32] = {0};
+    // AssertLtColsBits::populate (operations/cmp.rs:300-319): from the top bit down, flag the first bit where a < b
+    const auto populate_lt = [&](u32 a, u32 b) {
+      for (int k = 31; k >= 0; k--) {
+        const u32 ak = (a >> k) & 1, bk = (b >> k) & 1;
+        if (ak > bk) throw std::runtime_error("oracle: previous address is not below the address");
+        if (ak < bk) { lt[k] = 1; break; }
+      }
+    };
+    bool is_next_comp = false, is_first_comp = false;
+    u32 prev_inverse = 0; bool prev_zero = false;
+    if (i == 0) {
+      prev_zero = previous_addr == 0;
+      prev_inverse = prev_zero ? 0 : finv(F(previous_addr)).v;
+      is_first_comp = !prev_zero;
+      if (!prev_zero) populate_lt(previous_addr, addr);
+    } else {
+      is_next_comp = true;
+      populate_lt(ev[4 * (i - 1)], addr);
+    }
+    RowWriter w{row};
+    w.put(shard); w.put(timestamp); w.put(addr);
+    for (int k = 0; k < 32; k++) w.put(lt[k]);
+    // KoalaBearBitDecomposition::populate (operations/koala_bear_range.rs:34-48)
+    u32 bit[32];
+    for (int k = 0; k < 32; k++) { bit[k] = (addr >> k) & 1; w.put(bit[k]); }
+    u32 acc = bit[24] * bit[25];
+    w.put(acc);
+    for (int k = 26; k <= 30; k++) { acc *= bit[k]; w.put(acc); }
+    for (int k = 0; k < 32; k++) w.put((value >> k) & 1);
+    w.flag(true); w.flag(is_next_comp);
+    w.put(prev_inverse); w.flag(i == 0 && prev_zero);
+    w.flag(is_first_comp); w.flag(i == n - 1);
+    if (w.at != MEMGLOBAL_WIDTH) throw std::runtime_error("oracle: MemoryGlobal row width mismatch");
+  }
+}
+
+// one-event-per-row chips by name: rows of `height` x width canonical words, zero padding rows
+static inline int chip_trace_width(const std::string& chip) {
+  if (chip == "DivRem") return DIVREM_WIDTH;
+  if (chip == "SyscallCore" || chip == "SyscallPrecompile") return SYSCALL_WIDTH;
+  if (chip == "SyscallInstrs") return SYSINSTR_WIDTH;
+  return -1;
+}
+static inline int chip_event_words(const std::string& chip) {
+  if (chip == "DivRem") return COMP_EVENT_WORDS;
+  if (chip == "SyscallCore" || chip == "SyscallPrecompile" || chip == "SyscallInstrs") return SYSCALL_EVENT_WORDS;
+  return -1;
+}
+static inline void chip_trace(const std::string& chip, const u32* ev, size_t n, size_t height, u32* out) {
+  const int w = chip_trace_width(chip), ew = chip_event_words(chip);
+  if (w < 0) throw std::runtime_error("oracle: no row filler for chip " + chip);
+  if (n > height) throw std::runtime_error("oracle: more events than rows");
+  for (size_t i = 0; i < height; i++) {
+    u32* row = out + i * w;
+    if (i >= n) { for (int k = 0; k < w; k++) row[k] = 0; continue; }
+    const u32* e = ev + (size_t)ew * i;
+    if (chip == "DivRem") div_rem_row(e, row);
+    else if (chip == "SyscallInstrs") syscall_instr_row(e, row);
+    else syscall_row(e, chip == "SyscallPrecompile", row);
   }
 }
 

@@ -130,6 +130,9 @@ pub trait DeviceTraceEvents {
     fn memory_local_events(&self) -> Option<Vec<zkm_core_executor::events::MemoryLocalEvent>> { None }
     /// Cpu: one `zkb200_cpu_event` per `CpuEvent` with its fetched instruction and the shard number (tracegen.rs).
     fn cpu_events(&self) -> Option<Vec<tracegen::CpuEventFlat>> { None }
+    /// SyscallCore, SyscallPrecompile, MemoryGlobalInit, MemoryGlobalFinalize: records built from the record's events
+    /// (tracegen.rs `owned_events`).
+    fn owned_events(&self, _chip: &str) -> Option<tracegen::OwnedEvents> { None }
     fn fixed_log2_rows_of(&self, _chip: &str) -> Option<usize> { None }
 }
 impl DeviceTraceEvents for zkm_core_executor::ExecutionRecord {
@@ -142,6 +145,7 @@ impl DeviceTraceEvents for zkm_core_executor::ExecutionRecord {
         Some(self.get_local_mem_events().copied().collect())
     }
     fn cpu_events(&self) -> Option<Vec<tracegen::CpuEventFlat>> { Some(tracegen::flatten_cpu_events(self)) }
+    fn owned_events(&self, chip: &str) -> Option<tracegen::OwnedEvents> { tracegen::owned_events(self, chip) }
     fn fixed_log2_rows_of(&self, chip: &str) -> Option<usize> {
         self.shape.as_ref().and_then(|s| s.inner.get(chip).copied())
     }
@@ -235,6 +239,18 @@ where
                 t[i].flags = sys::ZKB200_TRACE_EVENTS;
                 t[i].n_events = ev.n_events;
             }
+        }
+        // SyscallCore / SyscallPrecompile / MemoryGlobalInit / MemoryGlobalFinalize: records built here, kept alive until the
+        // commit returns
+        let owned: Vec<(usize, tracegen::OwnedEvents)> = traces.iter().enumerate()
+            .filter(|(_, (_, m))| m.values.is_empty())
+            .filter_map(|(i, (n, _))| record.owned_events(n).map(|ev| (i, ev))).collect();
+        for (i, ev) in owned.iter() {
+            assert_eq!(traces[*i].1.width(), ev.width, "row filler of {} writes another width", traces[*i].0);
+            t[*i].data = ev.words.as_ptr();
+            t[*i].height = tracegen::padded_height(ev.n_events, self.fixed_log2_rows(record, &traces[*i].0));
+            t[*i].flags = sys::ZKB200_TRACE_EVENTS;
+            t[*i].n_events = ev.n_events;
         }
         // MemoryLocal: four seven-word events per row, gathered from the record's local-memory iterators
         let local_events = traces.iter().position(|(n, m)| n == "MemoryLocal" && m.values.is_empty())

@@ -8,6 +8,9 @@
 //!   (crates/core/executor/src/events/instr.rs);
 //!   they cross as they lie in `record.add_sub_events` etc. (`event_vector`).  The byte-lookup multiplicities these
 //!   chips' `event_to_row` also emits come from `generate_dependencies`, which the caller still runs on the host.
+//! * DivRem (`CompAluEvent`) and SyscallInstrs (`SyscallEvent`, fourteen words) cross as they lie too; SyscallCore,
+//!   SyscallPrecompile and MemoryGlobalInit / MemoryGlobalFinalize take records built here (`owned_events`): the filtered /
+//!   normalised syscall events, and the address-sorted memory events with the neighbour's address folded into each record.
 //! * MemoryLocal: seven-word `MemoryLocalEvent` records (crates/core/executor/src/events/memory.rs:228-237), four to a row;
 //!   the record keeps them in several vectors (`get_local_mem_events`), so they are gathered into one (28 bytes per event
 //!   against 224 bytes per row of four).
@@ -130,6 +133,8 @@ const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MovCondEve
 const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::CompAluEvent>() == 64);
 const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MemInstrEvent>() == 64);
 const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MiscEvent>() == 60);
+const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::SyscallEvent>() == 56);
+const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MemoryInitializeFinalizeEvent>() == 16);
 
 /// Chip name (`MachineAir::name`) -> the record field its `generate_trace` walks, with the chip's column count
 /// (csrc/tracegen.cuh `alu_width`).
@@ -147,6 +152,68 @@ pub fn event_vector(record: &ExecutionRecord, chip: &str) -> Option<EventVector>
         "Mul" => vector_of(&record.mul_events, 58),
         "MemoryInstrs" => vector_of(&record.memory_instr_events, 79),
         "MiscInstrs" => vector_of(&record.misc_events, 72),
+        "DivRem" => vector_of(&record.divrem_events, 106),
+        "SyscallInstrs" => vector_of(&record.syscall_events, 77),
+        _ => None,
+    }
+}
+
+/// Event records the shim has to build (the record does not hold them in the form the row filler reads): `words` holds
+/// `n_events` records of `words.len() / n_events` 32-bit words.
+pub struct OwnedEvents {
+    pub words: Vec<u32>,
+    pub n_events: usize,
+    pub width: usize,
+}
+
+fn syscall_words(e: &zkm_core_executor::events::SyscallEvent) -> [u32; 14] {
+    let r = &e.a_record;
+    [e.pc, e.next_pc, e.shard, e.clk, r.value, r.shard, r.timestamp, r.prev_value, r.prev_shard, r.prev_timestamp,
+     e.a_record_is_real as u32, e.syscall_id, e.arg1, e.arg2]
+}
+
+/// * "SyscallCore": the events `SyscallChip::generate_trace` keeps (crates/core/machine/src/syscall/chip.rs:233-240).
+/// * "SyscallPrecompile": one `SyscallEvent` per precompile event, its `a_record` carrying what `row_fn` takes from the
+///   `PrecompileEvent` (chip.rs:207-222) in the convention of include/syscall.hpp `precompile_event_to_row`.
+/// * "MemoryGlobalInit" / "MemoryGlobalFinalize": `zkb200_memory_global_event` records - the events sorted by address
+///   (crates/core/machine/src/memory/global.rs:130), each with the address its row is compared with (the previous event's,
+///   for the first one the public values' previous address) and its position, so that the sequential loop of
+///   global.rs:150-180 becomes one independent record per row.
+pub fn owned_events(record: &ExecutionRecord, chip: &str) -> Option<OwnedEvents> {
+    use zkm_core_executor::events::PrecompileEvent;
+    match chip {
+        "SyscallCore" => {
+            let kept: Vec<[u32; 14]> = record.syscall_events.iter()
+                .filter(|e| { let b = e.a_record.prev_value.to_le_bytes(); b[2] == 1 || b[1] != 0 })
+                .map(syscall_words).collect();
+            Some(OwnedEvents { n_events: kept.len(), words: kept.concat(), width: 11 })
+        }
+        "SyscallPrecompile" => {
+            let all: Vec<[u32; 14]> = record.precompile_events.all_events().map(|(e, p)| {
+                let mut w = syscall_words(e);
+                match p {
+                    PrecompileEvent::Linux(l) => { w[4] = l.v0; w[7] = 1; }
+                    _ => { w[4] = 0; w[7] = 0; }
+                }
+                w
+            }).collect();
+            Some(OwnedEvents { n_events: all.len(), words: all.concat(), width: 11 })
+        }
+        "MemoryGlobalInit" | "MemoryGlobalFinalize" => {
+            let init = chip == "MemoryGlobalInit";
+            let mut ev = if init { record.global_memory_initialize_events.clone() } else { record.global_memory_finalize_events.clone() };
+            let bits = if init { record.public_values.previous_init_addr_bits } else { record.public_values.previous_finalize_addr_bits };
+            let mut prev: u32 = bits.iter().enumerate().map(|(j, b)| b << j).sum();
+            ev.sort_by_key(|e| e.addr);
+            let n = ev.len();
+            let mut words = Vec::with_capacity(6 * n);
+            for (i, e) in ev.iter().enumerate() {
+                let position = (i == 0) as u32 | ((i + 1 == n) as u32) << 1;
+                words.extend_from_slice(&[e.addr, e.value, e.shard, e.timestamp, prev, position]);
+                prev = e.addr;
+            }
+            Some(OwnedEvents { n_events: n, words, width: 111 })
+        }
         _ => None,
     }
 }

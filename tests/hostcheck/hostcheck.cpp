@@ -5,6 +5,7 @@
 #include "tracegen.cuh"
 #include "tracegen_keccak.cuh"
 #include "lane_pool.h"
+#include <algorithm>
 #include <atomic>
 #include <thread>
 #include <vector>
@@ -17,6 +18,29 @@ const P2Consts& p2_host_consts() {
 }  // namespace zkb
 using namespace zkb;
 
+// the CTA of the row kernel (csrc/tracegen.cuh AluCta, the three phases csrc/tracegen.cu alu_rows_kernel runs between its
+// barriers) walked thread by thread on the host: the same load / fill / store index arithmetic as on the GPU, shared memory
+// as two arrays per CTA.  Poisoned shared memory and output catch reads of words the load phase did not bring in and rows
+// the store phase does not write.
+template <int CHIP>
+static void walk_ctas(const uint32_t* ev, size_t n, size_t height, uint32_t* out, int col_major, const u32* inv255) {
+  using C = AluCta<CHIP>;
+  std::vector<u32> ev_s((size_t)C::R * C::RW), tile((size_t)C::R * C::WP);
+  const size_t ctas = (height + C::R - 1) / C::R;
+  for (size_t cta = 0; cta < ctas; cta++) {
+    std::fill(ev_s.begin(), ev_s.end(), 0xDEADBEEFu);
+    std::fill(tile.begin(), tile.end(), 0xDEADBEEFu);
+    for (u32 t = 0; t < (u32)C::R; t++) C::load(t, cta, ev, n, ev_s.data());
+    for (u32 t = 0; t < (u32)C::R; t++) C::fill(t, cta, n, ev_s.data(), tile.data(), inv255);
+    for (u32 t = 0; t < (u32)C::R; t++) C::store(t, cta, height, tile.data(), out, col_major);
+  }
+}
+template <int CHIP>
+static int walk_dispatch(int chip, const uint32_t* ev, size_t n, size_t height, uint32_t* out, int col_major, const u32* inv255) {
+  if (chip == CHIP) { walk_ctas<CHIP>(ev, n, height, out, col_major, inv255); return 0; }
+  if constexpr (CHIP + 1 < ALU_NCHIPS) return walk_dispatch<CHIP + 1>(chip, ev, n, height, out, col_major, inv255);
+  return 1;
+}
 extern "C" {
 // canonical in / out, n states of 16 words
 void hostcheck_permute(uint32_t* st, size_t n) {
@@ -77,6 +101,18 @@ int hostcheck_alu_rows(int chip, const uint32_t* ev, size_t n, size_t height, ui
   return 0;
 }
 int hostcheck_alu_width(int chip) { return alu_width(chip); }
+int hostcheck_alu_rows_cta(int chip, const uint32_t* ev, size_t n, size_t height, uint32_t* out, int col_major) {
+  if (chip < 0 || chip >= ALU_NCHIPS) return 1;
+  const size_t epr = (size_t)alu_events_per_row(chip);
+  if ((n + epr - 1) / epr > height) return 1;
+  static u32 inv255[256];
+  static bool init = false;
+  if (!init) { alu_build_inv255(inv255); init = true; }
+  return walk_dispatch<0>(chip, ev, n, height, out, col_major, inv255);
+}
+int hostcheck_alu_cta_rows(int chip) { return alu_cta_rows(chip); }
+int hostcheck_alu_event_words(int chip) { return alu_event_words(chip); }
+int hostcheck_alu_nchips() { return ALU_NCHIPS; }
 // the product's KeccakSponge row filler (csrc/tracegen_keccak.cuh) on the host: n_blocks records of 384 words,
 // out height x 3531 row-major Montgomery, padding rows past the last block
 struct HostRowStore { uint32_t* r; void operator()(int col, u32 v) { r[col] = v; } };

@@ -50,6 +50,18 @@ CHIPS["MemoryInstrs"] = (lambda n, s: tg.synthetic_mem_instr_events(n, seed=s), 
 CHIPS["MemoryLocal"] = (lambda n, s: tg.synthetic_memory_local_events(n, seed=s), orc.memory_local_trace)
 CHIPS["Cpu"] = (lambda n, s: tg.synthetic_cpu_events(n, seed=s), orc.cpu_trace)
 CHIPS["MiscInstrs"] = (lambda n, s: tg.synthetic_misc_events(n, seed=s), orc.misc_trace)
+CHIPS["DivRem"] = (lambda n, s: tg.synthetic_div_rem_events(n, seed=s), lambda ev, h: orc.chip_trace("DivRem", ev, h))
+for _chip, _kind in (("SyscallCore", "core"), ("SyscallPrecompile", "precompile"), ("SyscallInstrs", "instrs")):
+    CHIPS[_chip] = (lambda n, s, k=_kind: tg.synthetic_syscall_events(n, seed=s, kind=k), lambda ev, h, c=_chip: orc.chip_trace(c, ev, h))
+
+
+def _memory_global_trace(records, h):
+    """The oracle takes the sorted events and the previous address; both are in the flattened records."""
+    return orc.memory_global_trace(records[:, :4], int(records[0, 4]) if len(records) else 0, h)
+
+
+for _chip in ("MemoryGlobalInit", "MemoryGlobalFinalize"):
+    CHIPS[_chip] = (lambda n, s: tg.memory_global_records(tg.synthetic_memory_global_events(n, seed=s), 0 if s % 2 else 5), _memory_global_trace)
 GOLDEN = {"Mul": "mul_rows.json", "MemoryInstrs": "mem_instr_rows.json", "Cpu": "cpu_rows.json", "MiscInstrs": "misc_rows.json"}
 
 prover = B200Prover(synthetic.mini_case().machine, device=0)

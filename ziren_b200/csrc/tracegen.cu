@@ -16,64 +16,38 @@ void tracegen_upload_constants() {
   ZKB_CUDA(cudaMemcpyToSymbol(d_inv255, h, sizeof(h)));
 }
 
-constexpr int TG_ROWS = 128;   // rows per CTA = threads per CTA
+constexpr int TG_ROWS = 128;   // threads per CTA of the KeccakSponge kernel
 
+// the three phases are AluCta<CHIP> in tracegen.cuh (also walked on the host by tests/hostcheck)
 template <int CHIP>
-__global__ void __launch_bounds__(TG_ROWS) alu_rows_kernel(const u32* __restrict__ events, size_t n, size_t height,
-                                                           u32* __restrict__ out, int col_major) {
-  constexpr int W = alu_width(CHIP);
-  constexpr int WP = W | 1;
-  constexpr int EW = alu_event_words(CHIP);
-  constexpr int EPR = alu_events_per_row(CHIP);
-  constexpr int RW = EW * EPR;                    // event words per row
-  static_assert((size_t)TG_ROWS * (RW + WP) * sizeof(u32) <= 48 * 1024, "events and row tile must fit the static shared-memory limit");
-  __shared__ u32 ev_s[TG_ROWS * RW];
-  __shared__ u32 tile[TG_ROWS * WP];
-  const size_t row0 = (size_t)blockIdx.x * TG_ROWS;
-  // the CTA's events are at most RW * 128 consecutive words: coalesced load, then one row's records per thread
-  const size_t e0 = row0 * EPR;
-  const size_t ev_words = e0 < n ? (n - e0 < (size_t)TG_ROWS * EPR ? (n - e0) * EW : (size_t)TG_ROWS * RW) : 0;
-  for (u32 i = threadIdx.x; i < ev_words; i += TG_ROWS) ev_s[i] = events[e0 * EW + i];
+__global__ void __launch_bounds__(AluCta<CHIP>::R) alu_rows_kernel(const u32* __restrict__ events, size_t n, size_t height,
+                                                                   u32* __restrict__ out, int col_major) {
+  using C = AluCta<CHIP>;
+  __shared__ u32 ev_s[C::R * C::RW];
+  __shared__ u32 tile[C::R * C::WP];
+  C::load(threadIdx.x, blockIdx.x, events, n, ev_s);
   __syncthreads();
-  u32* r = tile + threadIdx.x * WP;
-  const size_t first = (row0 + threadIdx.x) * EPR;          // the row's first event
-  if (first < n) fill_alu_row(CHIP, ev_s + RW * threadIdx.x, r, d_inv255, n - first < (size_t)EPR ? (int)(n - first) : EPR);
-  else fill_alu_padding(CHIP, r);
+  C::fill(threadIdx.x, blockIdx.x, n, ev_s, tile, d_inv255);
   __syncthreads();
-  const size_t rows = height - row0 < TG_ROWS ? height - row0 : TG_ROWS;
-  if (col_major) {
-    if (threadIdx.x < rows) {
-#pragma unroll 4
-      for (int c = 0; c < W; c++) out[(size_t)c * height + row0 + threadIdx.x] = tile[threadIdx.x * WP + c];
-    }
-  } else {
-    u32* dst = out + row0 * W;
-    for (u32 i = threadIdx.x; i < rows * W; i += TG_ROWS) dst[i] = tile[(i / W) * WP + (i % W)];
-  }
+  C::store(threadIdx.x, blockIdx.x, height, tile, out, col_major);
 }
 
 void alu_trace(int chip, const u32* events_dev, size_t n, size_t height, u32* out, bool col_major, cudaStream_t s) {
   if (!height) return;
+  if (chip < 0 || chip >= ALU_NCHIPS) throw std::runtime_error("zkb200: alu_trace: unknown chip");
   if (ceil_div(n, (size_t)alu_events_per_row(chip)) > height) throw std::runtime_error("zkb200: alu_trace: more events than rows");
-  const unsigned grid = ceil_div(height, TG_ROWS);
   const int cm = col_major ? 1 : 0;
+#define ZKB_ALU_CASE(C) \
+  case C: alu_rows_kernel<C><<<(unsigned)ceil_div(height, (size_t)AluCta<C>::R), AluCta<C>::R, 0, s>>>(events_dev, n, height, out, cm); break;
   switch (chip) {
-    case ALU_ADDSUB: alu_rows_kernel<ALU_ADDSUB><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_BITWISE: alu_rows_kernel<ALU_BITWISE><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_LT: alu_rows_kernel<ALU_LT><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_SLL: alu_rows_kernel<ALU_SLL><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_SR: alu_rows_kernel<ALU_SR><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_CLOCLZ: alu_rows_kernel<ALU_CLOCLZ><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_BRANCH: alu_rows_kernel<ALU_BRANCH><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_JUMP: alu_rows_kernel<ALU_JUMP><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_MOVCOND: alu_rows_kernel<ALU_MOVCOND><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_MUL: alu_rows_kernel<ALU_MUL><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_MEMINSTR: alu_rows_kernel<ALU_MEMINSTR><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_MEMLOCAL: alu_rows_kernel<ALU_MEMLOCAL><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_CPU: alu_rows_kernel<ALU_CPU><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
-    case ALU_MISC: alu_rows_kernel<ALU_MISC><<<grid, TG_ROWS, 0, s>>>(events_dev, n, height, out, cm); break;
+    ZKB_ALU_CASE(ALU_ADDSUB) ZKB_ALU_CASE(ALU_BITWISE) ZKB_ALU_CASE(ALU_LT) ZKB_ALU_CASE(ALU_SLL) ZKB_ALU_CASE(ALU_SR)
+    ZKB_ALU_CASE(ALU_CLOCLZ) ZKB_ALU_CASE(ALU_BRANCH) ZKB_ALU_CASE(ALU_JUMP) ZKB_ALU_CASE(ALU_MOVCOND) ZKB_ALU_CASE(ALU_MUL)
+    ZKB_ALU_CASE(ALU_MEMINSTR) ZKB_ALU_CASE(ALU_MEMLOCAL) ZKB_ALU_CASE(ALU_CPU) ZKB_ALU_CASE(ALU_MISC) ZKB_ALU_CASE(ALU_DIVREM)
+    ZKB_ALU_CASE(ALU_SYSCALL_CORE) ZKB_ALU_CASE(ALU_SYSCALL_PRECOMPILE) ZKB_ALU_CASE(ALU_SYSCALL_INSTRS)
+    ZKB_ALU_CASE(ALU_MEMGLOBAL_INIT) ZKB_ALU_CASE(ALU_MEMGLOBAL_FINALIZE)
     default: throw std::runtime_error("zkb200: alu_trace: unknown chip");
   }
+#undef ZKB_ALU_CASE
   ZKB_CHECK_LAUNCH();
 }
 
@@ -101,7 +75,8 @@ void keccak_sponge_trace(const u32* blocks_dev, size_t n_blocks, size_t height, 
 }
 
 int alu_chip_by_name(const char* name) {
-  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond", "Mul", "MemoryInstrs", "MemoryLocal", "Cpu", "MiscInstrs"};
+  static const char* names[ALU_NCHIPS] = {"AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond", "Mul", "MemoryInstrs", "MemoryLocal", "Cpu", "MiscInstrs", "DivRem",
+                                          "SyscallCore", "SyscallPrecompile", "SyscallInstrs", "MemoryGlobalInit", "MemoryGlobalFinalize"};
   for (int i = 0; i < ALU_NCHIPS; i++) if (!strcmp(name, names[i])) return i;
   return -1;
 }

@@ -12,7 +12,8 @@
 namespace zkb {
 
 enum AluChip : int { ALU_ADDSUB = 0, ALU_BITWISE = 1, ALU_LT = 2, ALU_SLL = 3, ALU_SR = 4, ALU_CLOCLZ = 5, ALU_BRANCH = 6, ALU_JUMP = 7,
-                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_MEMINSTR = 10, ALU_MEMLOCAL = 11, ALU_CPU = 12, ALU_MISC = 13, ALU_NCHIPS = 14 };
+                     ALU_MOVCOND = 8, ALU_MUL = 9, ALU_MEMINSTR = 10, ALU_MEMLOCAL = 11, ALU_CPU = 12, ALU_MISC = 13, ALU_DIVREM = 14, ALU_SYSCALL_CORE = 15,
+                     ALU_SYSCALL_PRECOMPILE = 16, ALU_SYSCALL_INSTRS = 17, ALU_MEMGLOBAL_INIT = 18, ALU_MEMGLOBAL_FINALIZE = 19, ALU_NCHIPS = 20 };
 // opcodes as numbered by crates/core/executor/src/opcode.rs:25-49 (#[repr(u8)])
 enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_ROR = 12, OP_SLT = 13, OP_SLTU = 14,
              OP_AND = 15, OP_OR = 16, OP_XOR = 17, OP_NOR = 18, OP_CLZ = 19, OP_CLO = 20, OP_BEQ = 21, OP_BGEZ = 22, OP_BGTZ = 23,
@@ -20,13 +21,18 @@ enum : u32 { OP_ADD = 0, OP_SUB = 1, OP_SLL = 9, OP_SRL = 10, OP_SRA = 11, OP_RO
 
 KB_HD constexpr int alu_width(int chip) {
   return chip == ALU_ADDSUB ? 19 : chip == ALU_BITWISE ? 18 : chip == ALU_LT ? 32 : chip == ALU_SLL ? 44 : chip == ALU_SR ? 67
-       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : chip == ALU_MEMINSTR ? 79 : chip == ALU_MEMLOCAL ? 56 : chip == ALU_CPU ? 67 : chip == ALU_MISC ? 72 : 32;
+       : chip == ALU_CLOCLZ ? 17 : chip == ALU_BRANCH ? 62 : chip == ALU_JUMP ? 66 : chip == ALU_MUL ? 58 : chip == ALU_MEMINSTR ? 79 : chip == ALU_MEMLOCAL ? 56 : chip == ALU_CPU ? 67 : chip == ALU_MISC ? 72
+       : chip == ALU_DIVREM ? 106 : chip == ALU_SYSCALL_CORE || chip == ALU_SYSCALL_PRECOMPILE ? 11 : chip == ALU_SYSCALL_INSTRS ? 77
+       : chip == ALU_MEMGLOBAL_INIT || chip == ALU_MEMGLOBAL_FINALIZE ? 111 : 32;
 }
 // 32-bit words per event record: seven for AluEvent / BranchEvent / JumpEvent / MovCondEvent, sixteen for CompAluEvent (Mul)
 // and MemInstrEvent (MemoryInstrs), twenty-eight for the flattened CpuEvent + Instruction (zkb200_cpu_event)
-// fifteen for MiscEvent (MiscInstrs)
+// fifteen for MiscEvent (MiscInstrs), sixteen for CompAluEvent (DivRem), fourteen for SyscallEvent (SyscallCore, SyscallPrecompile,
+// SyscallInstrs), six for the flattened MemoryInitializeFinalizeEvent (zkb200_memory_global_event)
 KB_HD constexpr int alu_event_words(int chip) {
-  return chip == ALU_CPU ? 28 : chip == ALU_MUL || chip == ALU_MEMINSTR ? 16 : chip == ALU_MISC ? 15 : 7;
+  return chip == ALU_CPU ? 28 : chip == ALU_MUL || chip == ALU_MEMINSTR || chip == ALU_DIVREM ? 16 : chip == ALU_MISC ? 15
+       : chip == ALU_SYSCALL_CORE || chip == ALU_SYSCALL_PRECOMPILE || chip == ALU_SYSCALL_INSTRS ? 14
+       : chip == ALU_MEMGLOBAL_INIT || chip == ALU_MEMGLOBAL_FINALIZE ? 6 : 7;
 }
 // events per row: MemoryLocal packs four seven-word MemoryLocalEvents into a row, every other chip has one event per row
 KB_HD constexpr int alu_events_per_row(int chip) { return chip == ALU_MEMLOCAL ? 4 : 1; }
@@ -506,6 +512,155 @@ KB_HD void fill_misc(const u32* e, u32* r, const u32* inv255) {
   }
 }
 
+// IsEqualWordOperation::populate (operations/is_equal_word.rs) = IsZeroWordOperation over the byte differences x[i] - y[i] as
+// field elements (is_zero_word.rs: is_zero_byte[4]{inverse, result}, is_lower_half_zero, is_upper_half_zero, result); y = 0
+// gives IsZeroWordOperation::populate(x).  Eleven columns.
+KB_HD void tg_is_equal_word(u32* r, u32 x, u32 y, const u32* inv255) {
+  u32 zero_mask = 0;
+  for (int i = 0; i < 4; i++) {
+    const u32 p = (x >> (8 * i)) & 0xffu, q = (y >> (8 * i)) & 0xffu;
+    r[2 * i] = p > q ? inv255[p - q] : p < q ? KB_P - inv255[q - p] : 0u;
+    r[2 * i + 1] = tg_b(p == q);
+    zero_mask |= (u32)(p == q) << i;
+  }
+  r[8] = tg_b((zero_mask & 3u) == 3u); r[9] = tg_b((zero_mask & 12u) == 12u); r[10] = tg_b(zero_mask == 15u);
+}
+// MemoryReadWriteCols::populate of a MemoryWriteRecord {value, shard, timestamp, prev_value, prev_shard, prev_timestamp}
+// (crates/core/machine/src/memory/trace.rs): prev_value[4], value[4], prev_shard, prev_clk, compare_clk, diff_16bit_limb,
+// diff_8bit_limb.  Thirteen columns.
+KB_HD void tg_write_access(u32* r, const u32* rec) {
+  tg_word(r, rec[3]); tg_word(r + 4, rec[0]);
+  r[8] = tg_f(rec[4]); r[9] = tg_f(rec[5]);
+  const bool same = rec[4] == rec[1];
+  r[10] = tg_b(same);
+  const u32 d = (same ? rec[2] - rec[5] : rec[1] - rec[4]) - 1u;
+  r[11] = tg_f(d & 0xffffu); r[12] = tg_f((d >> 16) & 0xffu);
+}
+// IsZeroOperation::populate_from_field_element (operations/is_zero.rs:29-40) of the difference x - k of two small integers
+KB_HD void tg_is_zero_diff(u32* r, u32 x, u32 k) {
+  r[0] = x == k ? 0u : fp_inv(fp_from_canonical(x) - fp_from_canonical(k)).v;
+  r[1] = tg_b(x == k);
+}
+
+// DivRemChip::generate_trace, crates/core/machine/src/alu/divrem/mod.rs:229-364 (C++ twin include/div_rem.hpp, which differs
+// from it for c = 0 and for INT_MIN / -1; the Rust is followed).  Event: CompAluEvent as for Mul.  Columns (106,
+// divrem/mod.rs:109-204): pc, next_pc, b[4], c[4], quotient[4], remainder[4], abs_remainder[4], abs_c[4], max_abs_c_or_1[4],
+// c_times_quotient[8], carry[8], is_c_0[11], is_div, is_divu, is_mod, is_modu, is_overflow, is_overflow_b[11],
+// is_overflow_c[11], b_msb, rem_msb, c_msb, b_neg, rem_neg, c_neg, remainder_check_multiplicity, op_hi_access[13], shard, clk.
+constexpr int DIVREM_WIDTH = 106;
+enum : u32 { OP_DIV = 5, OP_DIVU = 6, OP_MOD = 7, OP_MODU = 8 };
+KB_HD void fill_div_rem(const u32* e, u32* r, const u32* inv255) {
+  const u32 shard = e[0], clk = e[1], pc = e[2], next_pc = e[3], op = e[4] & 0xffu, b = e[7], c = e[8];
+  const bool sgn = op == OP_DIV || op == OP_MOD, overflow = b == 0x80000000u && c == 0xffffffffu;
+  // get_quotient_and_remainder, crates/core/executor/src/utils.rs:33-43 (wrapping division)
+  u32 quot, rem;
+  if (c == 0) { quot = 0xffffffffu; rem = b; }
+  else if (!sgn) { quot = b / c; rem = b % c; }
+  else if (overflow) { quot = 0x80000000u; rem = 0; }
+  else { quot = (u32)((int32_t)b / (int32_t)c); rem = (u32)((int32_t)b % (int32_t)c); }
+  r[0] = tg_f(pc); r[1] = tg_f(next_pc);
+  tg_word(r + 2, b); tg_word(r + 6, c); tg_word(r + 10, quot); tg_word(r + 14, rem);
+  const u32 abs_rem = sgn && (rem >> 31) ? 0u - rem : rem, abs_c = sgn && (c >> 31) ? 0u - c : c;
+  tg_word(r + 18, abs_rem); tg_word(r + 22, abs_c); tg_word(r + 26, abs_c ? abs_c : 1u);
+  const u64 ctq = sgn ? (u64)((int64_t)(int32_t)quot * (int64_t)(int32_t)c) : (u64)quot * (u64)c;
+  const u64 remw = sgn ? (u64)(int64_t)(int32_t)rem : (u64)rem;
+  u32 carry = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r[30 + i] = tg_f((u32)(ctq >> (8 * i)) & 0xffu);
+    carry = ((u32)((ctq >> (8 * i)) & 0xffu) + (u32)((remw >> (8 * i)) & 0xffu) + carry) >> 8;
+    r[38 + i] = tg_b(carry);
+  }
+  tg_is_equal_word(r + 46, c, 0u, inv255);
+  r[57] = tg_b(op == OP_DIV); r[58] = tg_b(op == OP_DIVU); r[59] = tg_b(op == OP_MOD); r[60] = tg_b(op == OP_MODU);
+  r[61] = tg_b(sgn && overflow);
+  tg_is_equal_word(r + 62, b, 0x80000000u, inv255);
+  tg_is_equal_word(r + 73, c, 0xffffffffu, inv255);
+  r[84] = tg_b(b >> 31); r[85] = tg_b(rem >> 31); r[86] = tg_b(c >> 31);
+  r[87] = tg_b(sgn && (b >> 31)); r[88] = tg_b(sgn && (rem >> 31)); r[89] = tg_b(sgn && (c >> 31));
+  r[90] = tg_b(c != 0);
+  if (op == OP_DIV || op == OP_DIVU) {          // the HI write of DIV / DIVU (mod.rs:259-267)
+    tg_write_access(r + 91, e + 9);
+    r[104] = tg_f(shard); r[105] = tg_f(clk);
+  } else {
+    for (int i = 91; i < 106; i++) r[i] = 0;
+  }
+}
+
+// SyscallChip::generate_trace row_fn, crates/core/machine/src/syscall/chip.rs:189-230 (C++ twin include/syscall.hpp).  Event:
+// SyscallEvent (crates/core/executor/src/events/syscall.rs:8-29) as its 14 #[repr(C)] words {pc, next_pc, shard, clk,
+// a_record{value, shard, timestamp, prev_value, prev_shard, prev_timestamp}, a_record_is_real, syscall_id, arg1, arg2}.
+// SyscallCore takes the events that are sent to the table (prev_value byte 2 = 1 or byte 1 != 0, chip.rs:233-240: the caller
+// filters); SyscallPrecompile takes one event per precompile event with a_record.prev_value = 1 / a_record.value = v0 for
+// PrecompileEvent::Linux and prev_value = 0 otherwise (the convention of syscall.hpp precompile_event_to_row).
+// Columns (11): shard, clk, syscall_id, arg1_lo, arg1_hi, arg2_lo, arg2_hi, result_lo, result_hi, is_linux, is_real.
+constexpr int SYSCALL_WIDTH = 11, SYSCALL_EVENT_WORDS = 14;
+KB_HD void fill_syscall(const u32* e, u32* r, bool precompile) {
+  const u32 value = e[4], prev_value = e[7], arg1 = e[12], arg2 = e[13];
+  const bool is_linux = precompile ? prev_value == 1u : ((prev_value >> 8) & 0xffu) != 0;
+  r[0] = tg_f(e[2]); r[1] = tg_f(e[3]); r[2] = tg_f(e[11]);
+  r[3] = tg_f(arg1 & 0xffffu); r[4] = tg_f(arg1 >> 16); r[5] = tg_f(arg2 & 0xffffu); r[6] = tg_f(arg2 >> 16);
+  r[7] = is_linux ? tg_f(value & 0xffffu) : 0u; r[8] = is_linux ? tg_f(value >> 16) : 0u;
+  r[9] = tg_b(is_linux); r[10] = KB_ONE;
+}
+
+// SyscallInstrsChip::event_to_row, crates/core/machine/src/syscall/instructions/trace.rs:89-177 (C++ twin
+// include/syscall_instrs.hpp).  Event: SyscallEvent.  Columns (77, instructions/columns.rs:11-59): pc, next_pc, shard, clk,
+// num_extra_cycles, is_halt, is_sys_linux, is_prev_a1_zero{inverse, result}, syscall_id, op_a[4], op_b[4], op_c[4], prev_a[4],
+// is_enter_unconstrained, is_hint_len, is_halt_check, is_exit_group_check, is_commit, is_commit_deferred_proofs (each
+// {inverse, result}), index_bitmap[8], op_b_range_check[14], op_c_range_check[14], op_b_check, op_c_check, is_real.
+constexpr int SYSINSTR_WIDTH = 77;
+enum : u32 { SYS_HALT = 0x00, SYS_ENTER_UNCONSTRAINED = 0x03, SYS_COMMIT = 0x10, SYS_COMMIT_DEFERRED_PROOFS = 0x1a, SYS_HINT_LEN = 0xf0,
+             SYS_EXT_GROUP = 4246 };           // SyscallCode::syscall_id(), crates/core/executor/src/syscalls/code.rs
+KB_HD void fill_syscall_instr(const u32* e, u32* r, const u32* inv255) {
+  const u32 value = e[4], prev_value = e[7], arg1 = e[12], arg2 = e[13];
+  const u32 sid = prev_value & 0xffffu, b1 = (prev_value >> 8) & 0xffu, b2 = (prev_value >> 16) & 0xffu;
+  const bool is_halt = sid == SYS_HALT || sid == SYS_EXT_GROUP, send_to_table = b1 != 0 || b2 == 1;
+  r[0] = tg_f(e[0]); r[1] = tg_f(e[1]); r[2] = tg_f(e[2]); r[3] = tg_f(e[3]);
+  r[4] = tg_f(prev_value >> 24);
+  r[5] = tg_b(is_halt); r[6] = tg_b(b1 != 0);
+  r[7] = b1 ? inv255[b1] : 0u; r[8] = tg_b(b1 == 0);
+  r[9] = tg_f(e[11]);
+  tg_word(r + 10, value); tg_word(r + 14, arg1); tg_word(r + 18, arg2); tg_word(r + 22, prev_value);
+  tg_is_zero_diff(r + 26, sid, SYS_ENTER_UNCONSTRAINED); tg_is_zero_diff(r + 28, sid, SYS_HINT_LEN);
+  tg_is_zero_diff(r + 30, sid, SYS_HALT); tg_is_zero_diff(r + 32, sid, SYS_EXT_GROUP);
+  tg_is_zero_diff(r + 34, sid, SYS_COMMIT); tg_is_zero_diff(r + 36, sid, SYS_COMMIT_DEFERRED_PROOFS);
+  const bool commits = sid == SYS_COMMIT || sid == SYS_COMMIT_DEFERRED_PROOFS;
+  for (u32 i = 0; i < 8; i++) r[38 + i] = tg_b(commits && arg1 == i);
+  const bool b_check = send_to_table || is_halt, c_check = send_to_table || sid == SYS_COMMIT_DEFERRED_PROOFS;
+  if (b_check) tg_range_checker(r + 46, arg1); else for (int i = 46; i < 60; i++) r[i] = 0;
+  if (c_check) tg_range_checker(r + 60, arg2); else for (int i = 60; i < 74; i++) r[i] = 0;
+  r[74] = tg_b(b_check); r[75] = tg_b(c_check); r[76] = KB_ONE;
+}
+
+// MemoryGlobalChip::generate_trace, crates/core/machine/src/memory/global.rs:115-192 (C++ twin include/memory_global.hpp for
+// the columns that depend on the event alone).  Event: zkb200_memory_global_event, the MemoryInitializeFinalizeEvent {addr,
+// value, shard, timestamp} (events/memory.rs:138-149) of the address-sorted vector followed by prev_addr - the previous event's
+// address, for the first event the public values' previous_init / previous_finalize address - and position (bit 0: first
+// event, bit 1: last event), the two things the reference's sequential second loop reads from the neighbouring row.
+// Columns (111, global.rs:210-245): shard, timestamp, addr, lt_cols.bit_flags[32], addr_bits{bits[32],
+// and_most_sig_byte_decomp_0_to_2 .. 0_to_7}, value[32], is_real, is_next_comp, is_prev_addr_zero{inverse, result},
+// is_first_comp, is_last_addr.
+constexpr int MEMGLOBAL_WIDTH = 111, MEMGLOBAL_EVENT_WORDS = 6;
+KB_HD void fill_memory_global(const u32* e, u32* r) {
+  const u32 addr = e[0], value = e[1], prev_addr = e[4];
+  const bool first = e[5] & 1u, last = (e[5] >> 1) & 1u;
+  r[0] = tg_f(e[2]); r[1] = tg_f(e[3]); r[2] = tg_f(addr);
+  // AssertLtColsBits::populate (operations/cmp.rs:300-319): the most significant bit where prev_addr < addr differ
+  const bool compare = (!first || prev_addr != 0) && prev_addr != addr;
+  tg_onehot(r + 3, 32, compare ? tg_top_bit(prev_addr ^ addr) : 32u);
+  tg_bits(r + 35, 32, addr);
+  u32 acc = (addr >> 24) & (addr >> 25) & 1u;
+  r[67] = tg_b(acc);
+  for (int i = 2; i <= 6; i++) { acc &= addr >> (24 + i); r[66 + i] = tg_b(acc & 1u); }
+  tg_bits(r + 73, 32, value);
+  r[105] = KB_ONE; r[106] = tg_b(!first);
+  r[107] = first && prev_addr ? fp_inv(fp_from_canonical(prev_addr)).v : 0u;
+  r[108] = tg_b(first && prev_addr == 0);
+  r[109] = tg_b(first && prev_addr != 0);
+  r[110] = tg_b(last);
+}
+
 // Rows past the last event (generate_trace of each chip): zeros, except the dummy rows that keep the
 // shift and count-leading chips' constraints satisfied (sll/mod.rs:160-173, sr/mod.rs:184-187,
 // clo_clz/mod.rs:150-163).
@@ -535,9 +690,56 @@ KB_HD void fill_alu_row(int chip, const u32* w, u32* r, const u32* inv255, int n
     case ALU_MEMLOCAL: fill_memory_local(w, n_valid, r); break;
     case ALU_CPU: fill_cpu(w, r); break;
     case ALU_MISC: fill_misc(w, r, inv255); break;
+    case ALU_DIVREM: fill_div_rem(w, r, inv255); break;
+    case ALU_SYSCALL_CORE: fill_syscall(w, r, false); break;
+    case ALU_SYSCALL_PRECOMPILE: fill_syscall(w, r, true); break;
+    case ALU_SYSCALL_INSTRS: fill_syscall_instr(w, r, inv255); break;
+    case ALU_MEMGLOBAL_INIT: case ALU_MEMGLOBAL_FINALIZE: fill_memory_global(w, r); break;
     default: fill_mov_cond(w, r, inv255); break;
   }
 }
+
+// One CTA of the row kernel (csrc/tracegen.cu alu_rows_kernel), as three phases separated by CTA barriers: one thread per row,
+// R rows per CTA.  Written host/device so that tests/hostcheck can walk the same index arithmetic thread by thread.
+//   load   the CTA's events are at most R * RW consecutive words: coalesced copy into shared memory
+//   fill   one row per thread into a tile whose row stride WP is odd (conflict-free column-wise read-back)
+//   store  the tile with coalesced writes: R rows are one contiguous block of the row-major matrix, and R consecutive
+//          elements of every column of the column-major one
+// R = 128, or 64 for the chips whose events and tile would not fit the 48 KB of static shared memory (DivRem, MemoryGlobal*).
+KB_HD constexpr int alu_cta_rows(int chip) {
+  return (size_t)128 * (size_t)(alu_event_words(chip) * alu_events_per_row(chip) + (alu_width(chip) | 1)) * sizeof(u32) <= 48 * 1024 ? 128 : 64;
+}
+template <int CHIP>
+struct AluCta {
+  static constexpr int W = alu_width(CHIP), WP = W | 1, EW = alu_event_words(CHIP), EPR = alu_events_per_row(CHIP);
+  static constexpr int RW = EW * EPR;                  // event words per row
+  static constexpr int R = alu_cta_rows(CHIP);         // rows per CTA = threads per CTA
+  static_assert((size_t)R * (RW + WP) * sizeof(u32) <= 48 * 1024, "events and row tile must fit the static shared-memory limit");
+  static KB_HD void load(u32 tid, size_t cta, const u32* events, size_t n, u32* ev_s) {
+    const size_t e0 = cta * R * EPR;
+    const size_t ev_words = e0 < n ? (n - e0 < (size_t)R * EPR ? (n - e0) * EW : (size_t)R * RW) : 0;
+    for (u32 i = tid; i < ev_words; i += R) ev_s[i] = events[e0 * EW + i];
+  }
+  static KB_HD void fill(u32 tid, size_t cta, size_t n, const u32* ev_s, u32* tile, const u32* inv255) {
+    u32* r = tile + tid * WP;
+    const size_t first = (cta * R + tid) * EPR;        // the row's first event
+    if (first < n) fill_alu_row(CHIP, ev_s + RW * tid, r, inv255, n - first < (size_t)EPR ? (int)(n - first) : EPR);
+    else fill_alu_padding(CHIP, r);
+  }
+  static KB_HD void store(u32 tid, size_t cta, size_t height, const u32* tile, u32* out, int col_major) {
+    const size_t row0 = cta * R;
+    const size_t rows = height - row0 < (size_t)R ? height - row0 : (size_t)R;
+    if (col_major) {
+      if (tid < rows) {
+#pragma unroll 4
+        for (int c = 0; c < W; c++) out[(size_t)c * height + row0 + tid] = tile[tid * WP + c];
+      }
+    } else {
+      u32* dst = out + row0 * W;
+      for (u32 i = tid; i < rows * W; i += R) dst[i] = tile[(i / W) * WP + (i % W)];
+    }
+  }
+};
 
 // 1/d for d = 0..255 in Montgomery form (entry 0 unused)
 inline void alu_build_inv255(u32* out) {

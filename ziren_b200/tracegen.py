@@ -45,6 +45,11 @@ EVENT_BYTES = 28
 CPU_WIDTH, CPU_EVENT_WORDS = 67, 28            # zkb200_cpu_event: the flattened CpuEvent + Instruction
 MISC_WIDTH, MISC_EVENT_WORDS = 72, 15          # MiscEvent
 PACKED_CHIPS = {"MemoryLocal": (56, 4)}       # width, events per row (seven-word MemoryLocalEvent records)
+SYSCALL_EVENT_WORDS = 14                       # SyscallEvent
+MEMGLOBAL_EVENT_WORDS = 6                      # zkb200_memory_global_event: MemoryInitializeFinalizeEvent + prev_addr + position
+# chip -> (width, event words): DivRem takes CompAluEvent records like Mul, the three syscall tables SyscallEvent records
+ROW_CHIPS = {"DivRem": (106, 16), "SyscallCore": (11, 14), "SyscallPrecompile": (11, 14), "SyscallInstrs": (77, 14),
+             "MemoryGlobalInit": (111, 6), "MemoryGlobalFinalize": (111, 6)}
 
 
 def width(chip: str) -> int:
@@ -54,6 +59,8 @@ def width(chip: str) -> int:
         return CPU_WIDTH
     if chip == "MiscInstrs":
         return MISC_WIDTH
+    if chip in ROW_CHIPS:
+        return ROW_CHIPS[chip][0]
     return (ALU_CHIPS.get(chip) or COMP_CHIPS[chip])[0]
 
 
@@ -66,6 +73,8 @@ def event_words(chip: str) -> int:
         return CPU_EVENT_WORDS
     if chip == "MiscInstrs":
         return MISC_EVENT_WORDS
+    if chip in ROW_CHIPS:
+        return ROW_CHIPS[chip][1]
     return COMP_EVENT_WORDS if chip in COMP_CHIPS else EVENT_WORDS
 
 
@@ -498,4 +507,169 @@ def synthetic_misc_events(n: int, seed: int = 0, shard: int = 3) -> np.ndarray:
     ev[:, 13] = np.where(earlier, rng.integers(1, shard, n), shard)
     ev[:, 14] = np.where(earlier, rng.integers(0, 1 << 22, n), ts - rng.integers(1, 9, n)).astype(np.uint32)
     ev[~is_mac, 9:15] = 0
+    return ev
+
+
+def _write_record(rng, n: int, shard: int, ts: np.ndarray, value: np.ndarray, prev_value: np.ndarray) -> np.ndarray:
+    """(n, 6) MemoryWriteRecord words {value, shard, timestamp, prev_value, prev_shard, prev_timestamp}, the previous access in
+    the same shard at an earlier clock or in an earlier shard."""
+    rec = np.zeros((n, 6), np.uint32)
+    earlier = rng.integers(0, 6, n) == 0
+    rec[:, 0], rec[:, 1], rec[:, 2], rec[:, 3] = value, shard, ts, prev_value
+    rec[:, 4] = np.where(earlier, rng.integers(1, max(2, shard), n), shard)
+    rec[:, 5] = np.where(earlier, rng.integers(0, 1 << 22, n), ts - rng.integers(1, 9, n)).astype(np.uint32)
+    return rec
+
+
+def synthetic_div_rem_events(n: int, seed: int = 0, shard: int = 3, edges: bool = True) -> np.ndarray:
+    """n well-formed CompAluEvent records of the DivRem chip as (n, 16) uint32 words {shard, clk, pc, next_pc, opcode, hi, a, b,
+    c, hi_record[6], hi_record_is_real} (crates/core/executor/src/events/instr.rs:47-73) for DIV / DIVU / MOD / MODU, lo / hi as
+    get_quotient_and_remainder leaves them (crates/core/executor/src/utils.rs:33-43).  `edges`: also c = 0, INT_MIN / -1,
+    c = +-1 and equal operands - the rows where the reference's C++ twin differs from its Rust are among them."""
+    rng = np.random.default_rng(0xD17 + seed)
+    ev = np.zeros((n, 16), np.uint32)
+    if n == 0:
+        return ev
+    O = ALL_OPCODES
+    ops = [O["DIV"], O["DIVU"], O["MOD"], O["MODU"]]
+    op = rng.choice(ops, n).astype(np.uint32)
+    op[: min(n, 4)] = ops[: min(n, 4)]
+    b = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    c = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    small = rng.integers(0, 3, n) == 0
+    c[small] = (c[small] >> rng.integers(8, 31, int(small.sum())).astype(np.uint32)) | np.uint32(1)
+    neg = rng.integers(0, 4, n) == 0
+    c[neg] = (~c[neg]) + np.uint32(1)
+    if edges and n >= 16:
+        k = np.arange(n)
+        c[k % 23 == 5] = 0
+        c[k % 29 == 7] = 0xFFFFFFFF
+        b[k % 58 == 7] = 0x80000000                       # with c = -1: the overflow row
+        c[k % 31 == 9] = 1
+        m = k % 37 == 11
+        c[m] = b[m]
+        b[k % 41 == 13] = 0x80000000
+    sgn = (op == O["DIV"]) | (op == O["MOD"])
+    sb, sc = b.astype(np.int32).astype(np.int64), c.astype(np.int32).astype(np.int64)
+    nz = c != 0
+    q = np.full(n, 0xFFFFFFFF, np.uint64)
+    r = b.astype(np.uint64)
+    scs = np.where(nz, sc, 1)
+    qs = np.abs(sb) // np.abs(scs) * np.sign(sb) * np.sign(scs)            # truncation toward zero
+    rs = sb - qs * scs
+    cu = np.where(nz, c, 1).astype(np.uint64)
+    q = np.where(nz, np.where(sgn, qs.astype(np.uint64) & np.uint64(0xFFFFFFFF), b.astype(np.uint64) // cu), q)
+    r = np.where(nz, np.where(sgn, rs.astype(np.uint64) & np.uint64(0xFFFFFFFF), b.astype(np.uint64) % cu), r)
+    ev[:, 0] = shard
+    ev[:, 1] = (5 + 5 * np.arange(1, n + 1)).astype(np.uint32)
+    ev[:, 2] = rng.integers(0, kb.P - 16, n) & ~np.uint32(3)
+    ev[:, 3] = ev[:, 2] + 4
+    ev[:, 4], ev[:, 5], ev[:, 6], ev[:, 7], ev[:, 8] = op, r.astype(np.uint32), q.astype(np.uint32), b, c
+    is_div = (op == O["DIV"]) | (op == O["DIVU"])
+    rec = _write_record(rng, n, shard, ev[:, 1] + 4, r.astype(np.uint32), rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32))
+    ev[:, 9:15] = np.where(is_div[:, None], rec, 0)
+    ev[:, 15] = is_div
+    return ev
+
+
+# SyscallCode values (crates/core/executor/src/syscalls/code.rs): byte 0-1 the id, byte 1 != 0 for the linux calls, byte 2 = 1
+# "send to table" (precompiles), byte 3 the extra cycles
+_SYSCALL_TABLE = np.array([0x00000000, 0x00000002, 0x00000003, 0x00000004, 0x00000010, 0x0000001A, 0x000000F0, 0x000000F1, 4246,
+                           4003, 4004, 4045, 4090, 0x00010005, 0x01010109, 0x00300130, 0x0101010A, 0x0001011C, 0x0001011E], np.uint32)
+
+
+def synthetic_syscall_events(n: int, seed: int = 0, shard: int = 3, kind: str = "instrs") -> np.ndarray:
+    """n SyscallEvent records as (n, 14) uint32 words {pc, next_pc, shard, clk, a_record[6], a_record_is_real, syscall_id, arg1,
+    arg2} (crates/core/executor/src/events/syscall.rs:8-29); a_record.prev_value holds the syscall code the instruction read from
+    $v0, a_record.value the result.  kind "instrs": every syscall of the shard (SyscallInstrs), COMMIT / COMMIT_DEFERRED_PROOFS
+    with a digest index below 8, arguments on both sides of the KoalaBear modulus' top byte; "core": only the events
+    SyscallCore keeps (prev_value byte 2 = 1 or byte 1 != 0, chip.rs:233-240); "precompile": one event per precompile event
+    with prev_value = 1 / value = v0 for the Linux ones and prev_value = 0 otherwise (include/syscall.hpp
+    precompile_event_to_row)."""
+    rng = np.random.default_rng(0x5C11 + seed)
+    ev = np.zeros((n, SYSCALL_EVENT_WORDS), np.uint32)
+    if n == 0:
+        return ev
+    u32 = lambda: rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    code = rng.choice(_SYSCALL_TABLE, n).astype(np.uint32)
+    code[: min(n, len(_SYSCALL_TABLE))] = _SYSCALL_TABLE[: min(n, len(_SYSCALL_TABLE))]
+    if kind == "core":
+        keep = _SYSCALL_TABLE[(((_SYSCALL_TABLE >> 16) & 0xFF) == 1) | (((_SYSCALL_TABLE >> 8) & 0xFF) != 0)]
+        code = rng.choice(keep, n).astype(np.uint32)
+        code[: min(n, len(keep))] = keep[: min(n, len(keep))]
+    arg1, arg2 = u32(), u32()
+    top = rng.integers(0, 4, n)
+    arg1 = np.where(top == 0, (arg1 & np.uint32(0x00FFFFFF)) | (rng.choice([0x7E, 0x7F, 0x3F, 0x1F, 0x0F], n).astype(np.uint32) << np.uint32(24)), arg1 & np.uint32(0x7EFFFFFF))
+    arg2 = np.where(top == 1, (arg2 & np.uint32(0x00FFFFFF)) | np.uint32(0x7F000000), arg2 & np.uint32(0x7EFFFFFF))
+    sid = code & np.uint32(0xFFFF)
+    commits = (sid == 0x10) | (sid == 0x1A)
+    arg1 = np.where(commits, rng.integers(0, 8, n), arg1).astype(np.uint32)
+    value = u32()
+    prev_value = code.copy()
+    if kind == "precompile":
+        linux = rng.integers(0, 3, n) == 0
+        prev_value = linux.astype(np.uint32)
+        value = np.where(linux, value, 0).astype(np.uint32)
+    ev[:, 0] = rng.integers(0, kb.P - 16, n) & ~np.uint32(3)
+    ev[:, 1] = ev[:, 0] + 4
+    ev[:, 2] = shard
+    ev[:, 3] = (5 + 5 * np.arange(1, n + 1)).astype(np.uint32)
+    ev[:, 4:10] = _write_record(rng, n, shard, ev[:, 3], value, prev_value)
+    if kind == "precompile":
+        ev[:, 5:7] = 0
+        ev[:, 8:10] = 0                                   # a default MemoryWriteRecord apart from the two fields above
+    ev[:, 10] = 0 if kind == "precompile" else 1
+    ev[:, 11] = sid if kind != "precompile" else rng.choice(_SYSCALL_TABLE & 0xFFFF, n)
+    ev[:, 12], ev[:, 13] = arg1, arg2
+    return ev
+
+
+def memory_global_records(events: np.ndarray, previous_addr: int) -> np.ndarray:
+    """The flattened records `zkb200_generate_alu_trace("MemoryGlobalInit" | "MemoryGlobalFinalize")` takes: the (n, 4)
+    MemoryInitializeFinalizeEvent records {addr, value, shard, timestamp} sorted by address as generate_trace does
+    (crates/core/machine/src/memory/global.rs:130), each followed by the address it is compared with (the previous event's; for
+    the first event the public values' previous_init_addr / previous_finalize_addr) and its position (bit 0 first, bit 1 last):
+    what the reference's second, sequential loop (global.rs:150-180) reads from the neighbouring row."""
+    ev = np.ascontiguousarray(events, dtype=np.uint32).reshape(-1, 4)
+    ev = ev[np.argsort(ev[:, 0], kind="stable")]
+    n = len(ev)
+    out = np.zeros((n, MEMGLOBAL_EVENT_WORDS), np.uint32)
+    if n == 0:
+        return out
+    out[:, :4] = ev
+    out[0, 4] = previous_addr
+    out[1:, 4] = ev[:-1, 0]
+    out[0, 5] |= 1
+    out[n - 1, 5] |= 2
+    return out
+
+
+def synthetic_memory_global_events(n: int, seed: int = 0, shard: int = 3) -> np.ndarray:
+    """n MemoryInitializeFinalizeEvent records (n, 4) {addr, value, shard, timestamp} with distinct addresses below the
+    KoalaBear modulus, UNSORTED as they sit in record.global_memory_initialize_events: neighbouring addresses that differ in
+    their lowest and in their highest bits, addresses with the top byte 0x7E / 0x7F prefix bits set."""
+    rng = np.random.default_rng(0x3E3 + seed)
+    ev = np.zeros((n, 4), np.uint32)
+    if n == 0:
+        return ev
+    addr = set()
+    base = int(rng.integers(1, 1 << 20))
+    while len(addr) < n:
+        r = int(rng.integers(0, 4))
+        if r == 0:
+            base += int(rng.integers(1, 3))
+        elif r == 1:
+            base += int(rng.integers(1, 1 << 12))
+        elif r == 2:
+            base = int(rng.integers(1, kb.P))
+        else:
+            base = int(rng.choice([0x7E000000, 0x7F000000, 0x3F000000, 0x7C000000])) - int(rng.integers(1, 1 << 16))
+        if 0 < base < kb.P:
+            addr.add(base)
+    a = np.array(sorted(addr), np.uint32)
+    rng.shuffle(a)
+    ev[:, 0] = a
+    ev[:, 1] = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    ev[:, 2] = rng.integers(0, shard + 1, n)
+    ev[:, 3] = rng.integers(0, 1 << 24, n)
     return ev
