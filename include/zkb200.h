@@ -234,6 +234,15 @@ typedef struct {
  * (crates/core/executor/src/events/memory.rs:138-149) SORTED BY ADDRESS as generate_trace sorts them, each followed by the
  * address its row is compared with and by its position - the two things the reference's sequential loop (global.rs:150-180)
  * takes from the neighbouring row, so that every row depends on its own record only. */
+/* "Global" (crates/core/machine/src/global/mod.rs:115-194; 99 columns) takes the 32-byte `GlobalLookupEvent` records {message[7],
+ * is_receive: bool, kind: u8} (crates/core/executor/src/events/global.rs:6-15) as they lie in record.global_lookup_events.  It is
+ * the one table that is not row-local and whose rows are compute-heavy: every message is lifted to a point of the septic curve
+ * (SepticCurve::lift_x, crates/stark/src/septic_curve.rs:130-154: a square test and a square root in F_p^7 per trial), the points
+ * are summed along the table (a scan under the curve addition) and each row holds two neighbouring sums. */
+typedef struct {
+  uint32_t message[7];
+  uint32_t is_receive_kind;                 /* byte 0: is_receive, byte 1: kind (LookupKind), bytes 2-3 padding */
+} zkb200_global_lookup_event;
 typedef struct {
   uint32_t addr, value, shard, timestamp;   /* MemoryInitializeFinalizeEvent */
   uint32_t prev_addr;                       /* the previous event's addr; first event: the public values' previous_init_addr /
@@ -245,7 +254,7 @@ int zkb200_alu_trace_width(const char* chip);
 /* events: zkb200_alu_event[]; zkb200_flow_event[] for "Branch" / "Jump"; seven-word MovCondEvent records for "MovCond";
  * CompAluEvent / MemInstrEvent / MemoryLocalEvent / MiscEvent records as they lie for "Mul" / "MemoryInstrs" / "MemoryLocal" /
  * "MiscInstrs"; CompAluEvent records for "DivRem"; SyscallEvent records for "SyscallCore" / "SyscallPrecompile" /
- * "SyscallInstrs"; zkb200_memory_global_event[] for "MemoryGlobalInit" / "MemoryGlobalFinalize";
+ * "SyscallInstrs"; zkb200_memory_global_event[] for "MemoryGlobalInit" / "MemoryGlobalFinalize"; zkb200_global_lookup_event[] for "Global";
  * zkb200_cpu_event[] for "Cpu" */
 int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* events, size_t n_events,
                               unsigned log_height, uint32_t* out, int col_major);

@@ -4,6 +4,7 @@
 // imports or calls this library.
 #include "prover.h"
 #include "tracegen.h"
+#include "tracegen_global.h"
 #include "tracegen_keccak.h"
 #include <cstdlib>
 #include <cstring>
@@ -309,6 +310,40 @@ int zko_memory_global_trace(const u32* ev, size_t n, u32 previous_addr, size_t h
     memory_global_trace(ev, n, previous_addr, height, out);
     return 0;
   } catch (const std::exception& e) { return fail(e); }
+}
+// Global rows (tracegen_global.h): events n x 8 words (GlobalLookupEvent), out height x 99 row-major canonical
+int zko_global_trace(const u32* ev, size_t n, size_t height, u32* out) {
+  try {
+    global_trace(ev, n, height, out);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+// septic extension / curve primitives of tracegen_global.h, canonical words: op 0 a * b, 1 1 / a, 2 sqrt(a) (returns 1 when a is
+// not a square), 3 frobenius(a), 4 double_frobenius(a), 5 curve_formula(a) (7 words each); 6 complete addition of two points
+// (a, b, out: 14 words each, the point at infinity as zeros)
+int zko_septic_op(int op, const u32* a, const u32* b, u32* out) {
+  try {
+    Septic x, y, r;
+    for (int i = 0; i < 7; i++) { x.c[i] = F(a[i]); if (b) y.c[i] = F(b[i]); }
+    if (op == 6) {
+      CurvePoint p = curve_point_from_words(a), q = curve_point_from_words(b);
+      p.infinity = p.x.is_zero() && p.y.is_zero(); q.infinity = q.x.is_zero() && q.y.is_zero();
+      const CurvePoint s = curve_add_complete(p, q);
+      for (int i = 0; i < 7; i++) { out[i] = s.infinity ? 0 : s.x.c[i].v; out[7 + i] = s.infinity ? 0 : s.y.c[i].v; }
+      return 0;
+    }
+    switch (op) {
+      case 0: r = x * y; break;
+      case 1: r = septic_inv(x); break;
+      case 2: if (!septic_sqrt(x, r)) return 1; break;
+      case 3: r = septic_frobenius(x); break;
+      case 4: r = septic_double_frobenius(x); break;
+      case 5: r = curve_formula(x); break;
+      default: throw std::runtime_error("oracle: unknown septic op");
+    }
+    for (int i = 0; i < 7; i++) out[i] = r.c[i].v;
+    return 0;
+  } catch (const std::exception& e) { fail(e); return -1; }
 }
 // trace generation of the KeccakSponge chip (tracegen_keccak.h): n_blocks records of KS_REC_WORDS words,
 // out height x 3531 row-major canonical

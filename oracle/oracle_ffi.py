@@ -262,6 +262,45 @@ def ref_chip_rows(chip, events, event_words):
     return out
 
 
+GLOBAL_WIDTH, GLOBAL_EVENT_WORDS = 99, 8
+
+
+def global_trace(events, height):
+    """events: (n, 8) uint32 GlobalLookupEvent records {message[7], is_receive | kind << 8}; (height, 99) canonical rows of the
+    Global chip."""
+    ev = _a(events).reshape(-1, GLOBAL_EVENT_WORDS)
+    out = np.zeros((int(height), GLOBAL_WIDTH), np.uint32)
+    if lib().zko_global_trace(_p(ev), C.c_size_t(ev.shape[0]), C.c_size_t(int(height)), _p(out)):
+        raise RuntimeError(err())
+    return out
+
+
+SEPTIC_OPS = {"mul": 0, "inv": 1, "sqrt": 2, "frobenius": 3, "double_frobenius": 4, "curve_formula": 5, "curve_add": 6}
+
+
+def _septic_call(fn, op, a, b):
+    a = _a(a)
+    b = _a(b) if b is not None else None
+    out = np.zeros(14 if op == "curve_add" else 7, np.uint32)
+    rc = fn(SEPTIC_OPS[op], _p(a), _p(b) if b is not None else None, _p(out))
+    if rc < 0:
+        raise RuntimeError("septic op failed")
+    return None if rc else out
+
+
+def septic_op(op, a, b=None):
+    """F_p^7 / septic-curve primitives of oracle/tracegen_global.h on canonical words; None for the root of a non-square."""
+    return _septic_call(lib().zko_septic_op, op, a, b)
+
+
+def ref_septic_op(op, a, b=None):
+    """The same through the reference's kb31_septic_extension_t.hpp; raises LookupError without oracle/_ref."""
+    l = ref_core_lib()
+    if l is None or not hasattr(l, "ref_septic_op"):
+        raise LookupError("oracle/_ref not built")
+    return _septic_call(l.ref_septic_op, op, a, b)
+
+
 KS_WIDTH, KS_REC_WORDS = 3531, 384
 
 

@@ -238,4 +238,37 @@ int ref_chip_event_to_rows(const char* chip, const uint32_t* ev, size_t n, uint3
   }
   return 0;
 }
+// the reference's septic extension and curve (crates/core/machine/include/kb31_septic_extension_t.hpp), canonical words in and
+// out: op 0 a * b, 1 reciprocal, 2 sqrt (returns 1 when a is not a square), 3 frobenius, 4 double_frobenius, 5 curve_formula
+// (7 words each); 6 point addition (14 words each, infinity as zeros; its doubling branch differs from the Rust and is not used)
+int ref_septic_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  kb31_t av[14], bv[14];
+  for (int i = 0; i < 14; i++) {
+    av[i] = kb31_t::from_canonical_u32(op == 6 || i < 7 ? a[i] : 0);
+    bv[i] = kb31_t::from_canonical_u32(b && (op == 6 || i < 7) ? b[i] : 0);
+  }
+  if (op == 6) {
+    kb31_septic_curve_t p(av), q(bv);
+    p += q;
+    for (int i = 0; i < 7; i++) { out[i] = p.x.value[i].as_canonical_u32(); out[7 + i] = p.y.value[i].as_canonical_u32(); }
+    return 0;
+  }
+  kb31_septic_extension_t x(av), y(bv), r;
+  switch (op) {
+    case 0: r = x * y; break;
+    case 1: r = x.reciprocal(); break;
+    case 2: {
+      const kb31_t pow_r = x.pow_r();
+      if ((pow_r ^ 1065353216) != kb31_t::one()) return 1;
+      r = x.sqrt(pow_r);
+      break;
+    }
+    case 3: r = x.frobenius(); break;
+    case 4: r = x.double_frobenius(); break;
+    case 5: r = x.curve_formula(); break;
+    default: return -1;
+  }
+  for (int i = 0; i < 7; i++) out[i] = r.value[i].as_canonical_u32();
+  return 0;
+}
 }

@@ -8,6 +8,8 @@
 //!   (crates/core/executor/src/events/instr.rs);
 //!   they cross as they lie in `record.add_sub_events` etc. (`event_vector`).  The byte-lookup multiplicities these
 //!   chips' `event_to_row` also emits come from `generate_dependencies`, which the caller still runs on the host.
+//! * Global: the 32-byte `GlobalLookupEvent` records as they lie; the curve lift (a square root in F_p^7 per trial) and the
+//!   running curve sum - the expensive part of `GlobalChip::generate_trace` - run on the device.
 //! * DivRem (`CompAluEvent`) and SyscallInstrs (`SyscallEvent`, fourteen words) cross as they lie too; SyscallCore,
 //!   SyscallPrecompile and MemoryGlobalInit / MemoryGlobalFinalize take records built here (`owned_events`): the filtered /
 //!   normalised syscall events, and the address-sorted memory events with the neighbour's address folded into each record.
@@ -134,6 +136,7 @@ const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::CompAluEve
 const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MemInstrEvent>() == 64);
 const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MiscEvent>() == 60);
 const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::SyscallEvent>() == 56);
+const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::GlobalLookupEvent>() == 32);
 const _: () = assert!(core::mem::size_of::<zkm_core_executor::events::MemoryInitializeFinalizeEvent>() == 16);
 
 /// Chip name (`MachineAir::name`) -> the record field its `generate_trace` walks, with the chip's column count
@@ -154,6 +157,8 @@ pub fn event_vector(record: &ExecutionRecord, chip: &str) -> Option<EventVector>
         "MiscInstrs" => vector_of(&record.misc_events, 72),
         "DivRem" => vector_of(&record.divrem_events, 106),
         "SyscallInstrs" => vector_of(&record.syscall_events, 77),
+        // the one table that is not row-local: the library lifts every message to its curve point and scans the points
+        "Global" => vector_of(&record.global_lookup_events, 99),
         _ => None,
     }
 }

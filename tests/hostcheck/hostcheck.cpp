@@ -4,6 +4,7 @@
 #include "poseidon2.cuh"
 #include "tracegen.cuh"
 #include "tracegen_keccak.cuh"
+#include "tracegen_global.cuh"
 #include "lane_pool.h"
 #include <algorithm>
 #include <atomic>
@@ -113,6 +114,60 @@ int hostcheck_alu_rows_cta(int chip, const uint32_t* ev, size_t n, size_t height
 int hostcheck_alu_cta_rows(int chip) { return alu_cta_rows(chip); }
 int hostcheck_alu_event_words(int chip) { return alu_event_words(chip); }
 int hostcheck_alu_nchips() { return ALU_NCHIPS; }
+// the Global chip's three steps (csrc/tracegen_global.cuh; csrc/tracegen.cu global_trace) walked on the host in the kernels'
+// order: lift per event, the chunked scan level by level (totals, recursion, rescan: one call per GPU thread), finish per row
+static const GlobalConsts& host_global_consts() {
+  static const GlobalConsts k = [] { GlobalConsts c; global_build_consts(c); return c; }();
+  return k;
+}
+static void host_global_scan(u32* pts, size_t n, const GlobalConsts& k) {
+  if (n <= 1) return;
+  const size_t chunks = (n + GLOBAL_SCAN_CHUNK - 1) / GLOBAL_SCAN_CHUNK;
+  if (chunks == 1) { global_chunk_rescan(pts, n, 0, k, nullptr); return; }
+  std::vector<u32> totals(chunks * GLOBAL_POINT_WORDS, 0xDEADBEEFu);
+  for (size_t t = 0; t < chunks; t++) global_chunk_total(pts, n, t, k, totals.data());
+  host_global_scan(totals.data(), chunks, k);
+  for (size_t t = 0; t < chunks; t++) global_chunk_rescan(pts, n, t, k, totals.data());
+}
+int hostcheck_global_rows(const uint32_t* ev, size_t n, size_t height, uint32_t* out, int col_major) {
+  if (n > height) return 1;
+  const GlobalConsts& k = host_global_consts();
+  const GlobalOut o{out, col_major ? (size_t)1 : (size_t)GLOBAL_WIDTH, col_major ? height : (size_t)1};
+  std::vector<u32> points((n + 1) * GLOBAL_POINT_WORDS, 0xDEADBEEFu);
+  curve_store(points.data(), k.start);
+  for (size_t row = 0; row < n; row++) global_lift_row(ev + GLOBAL_EVENT_WORDS * row, row, k, o, points.data());
+  host_global_scan(points.data(), n + 1, k);
+  for (size_t row = 0; row < height; row++) global_finish_row(row, n, points.data(), k, o);
+  return 0;
+}
+int hostcheck_global_width() { return GLOBAL_WIDTH; }
+// septic primitives, canonical words in and out; ops as oracle/capi.cpp zko_septic_op
+int hostcheck_septic_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  const GlobalConsts& k = host_global_consts();
+  Sep x, y = sep_zero(), r;
+  for (int i = 0; i < 7; i++) { x.c[i] = fp_from_canonical(a[i]); if (b) y.c[i] = fp_from_canonical(b[i]); }
+  if (op == 6) {
+    CurvePt p, q;
+    for (int i = 0; i < 7; i++) {
+      p.x.c[i] = fp_from_canonical(a[i]); p.y.c[i] = fp_from_canonical(a[7 + i]);
+      q.x.c[i] = fp_from_canonical(b[i]); q.y.c[i] = fp_from_canonical(b[7 + i]);
+    }
+    const CurvePt s = curve_add(p, q, k);
+    for (int i = 0; i < 7; i++) { out[i] = fp_to_canonical(s.x.c[i]); out[7 + i] = fp_to_canonical(s.y.c[i]); }
+    return 0;
+  }
+  switch (op) {
+    case 0: r = x * y; break;
+    case 1: r = sep_inv(x, k); break;
+    case 2: if (!sep_sqrt(x, k, r)) return 1; break;
+    case 3: r = sep_frobenius(x, k); break;
+    case 4: r = sep_double_frobenius(x, k); break;
+    case 5: r = curve_formula(x); break;
+    default: return -1;
+  }
+  for (int i = 0; i < 7; i++) out[i] = fp_to_canonical(r.c[i]);
+  return 0;
+}
 // the product's KeccakSponge row filler (csrc/tracegen_keccak.cuh) on the host: n_blocks records of 384 words,
 // out height x 3531 row-major Montgomery, padding rows past the last block
 struct HostRowStore { uint32_t* r; void operator()(int col, u32 v) { r[col] = v; } };

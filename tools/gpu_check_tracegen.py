@@ -62,6 +62,7 @@ def _memory_global_trace(records, h):
 
 for _chip in ("MemoryGlobalInit", "MemoryGlobalFinalize"):
     CHIPS[_chip] = (lambda n, s: tg.memory_global_records(tg.synthetic_memory_global_events(n, seed=s), 0 if s % 2 else 5), _memory_global_trace)
+CHIPS["Global"] = (lambda n, s: tg.synthetic_global_events(n, seed=s), orc.global_trace)
 GOLDEN = {"Mul": "mul_rows.json", "MemoryInstrs": "mem_instr_rows.json", "Cpu": "cpu_rows.json", "MiscInstrs": "misc_rows.json"}
 
 prover = B200Prover(synthetic.mini_case().machine, device=0)

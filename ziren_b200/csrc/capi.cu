@@ -1,4 +1,5 @@
 // extern "C" surface of libzkb200.so — see include/zkb200.h for the contract.
+#include <cstring>
 #include "../../include/zkb200.h"
 #include <cstdlib>
 #include <memory>
@@ -314,6 +315,7 @@ int zkb200_convert(zkb200_ctx* ctx, uint32_t* data, size_t n, int to_montgomery)
   });
 }
 int zkb200_alu_trace_width(const char* chip) {
+  if (!strcmp(chip, "Global")) return GLOBAL_WIDTH;
   const int id = alu_chip_by_name(chip);
   return id < 0 ? -1 : alu_width(id);
 }
@@ -322,11 +324,12 @@ int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* eve
   return guarded(ctx, [&] {
     static_assert(sizeof(zkb200_alu_event) == 28 && sizeof(zkb200_flow_event) == 28, "event records are seven 32-bit words");
     static_assert(sizeof(zkb200_cpu_event) == CPU_EVENT_WORDS * 4, "cpu event records are 28 32-bit words");
-    const int id = alu_chip_by_name(chip);
-    if (id < 0) throw std::runtime_error(std::string("zkb200: generate_alu_trace: no row filler for chip ") + chip);
+    const bool is_global = !strcmp(chip, "Global");          // the one table that is not row-local: lift, curve-point scan, finish
+    const int id = is_global ? -1 : alu_chip_by_name(chip);
+    if (id < 0 && !is_global) throw std::runtime_error(std::string("zkb200: generate_alu_trace: no row filler for chip ") + chip);
     if (log_height > 30) throw std::runtime_error("zkb200: generate_alu_trace: log_height out of range");
     const size_t height = (size_t)1 << log_height;
-    if (ceil_div(n_events, (size_t)alu_events_per_row(id)) > height)
+    if ((is_global ? n_events : ceil_div(n_events, (size_t)alu_events_per_row(id))) > height)
       throw std::runtime_error("zkb200: generate_alu_trace: more events than rows (fixed log2 rows is too small)");
     std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
     ZKB_CUDA(cudaSetDevice(ctx->c.device));
@@ -339,12 +342,13 @@ int zkb200_generate_alu_trace(zkb200_ctx* ctx, const char* chip, const void* eve
       on_device = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
     else cudaGetLastError();
     if (n_events && !on_device) {
-      const size_t ew = (size_t)alu_event_words(id);
+      const size_t ew = is_global ? (size_t)GLOBAL_EVENT_WORDS : (size_t)alu_event_words(id);
       staged = DevBuf(n_events * ew, s);
       ZKB_CUDA(cudaMemcpyAsync(staged.p, events, n_events * ew * sizeof(u32), cudaMemcpyHostToDevice, s));
       ev = staged.p;
     }
-    alu_trace(id, ev, n_events, height, out, col_major != 0, s);
+    if (is_global) global_trace(ev, n_events, height, out, col_major != 0, s);
+    else alu_trace(id, ev, n_events, height, out, col_major != 0, s);
     ZKB_CUDA(cudaStreamSynchronize(s));
   });
 }

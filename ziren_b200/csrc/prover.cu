@@ -344,12 +344,14 @@ Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep_in, u32 pc_start, co
 // ZKB200_TRACE_EVENTS: which row filler a chip has (csrc/tracegen.cu) and how long its event records are
 static size_t event_record_words(const std::string& chip) {
   if (chip == "KeccakSponge") return KS_REC_WORDS;
+  if (chip == "Global") return GLOBAL_EVENT_WORDS;
   if (alu_chip_by_name(chip.c_str()) >= 0) return (size_t)alu_event_words(alu_chip_by_name(chip.c_str()));
   throw std::runtime_error("zkb200: commit: no row filler for chip " + chip + " (ZKB200_TRACE_EVENTS)");
 }
 static void generate_trace_colmajor(const std::string& chip, const u32* events_dev, size_t n_events, size_t height, u32* out,
                                     cudaStream_t s) {
   if (chip == "KeccakSponge") keccak_sponge_trace(events_dev, n_events, height, out, s);
+  else if (chip == "Global") global_trace(events_dev, n_events, height, out, true, s);
   else alu_trace(alu_chip_by_name(chip.c_str()), events_dev, n_events, height, out, true, s);
 }
 
@@ -382,10 +384,11 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
     if ((t.flags & ~(TRACE_EVENTS | TRACE_COL_MAJOR)) || (t.flags & (TRACE_EVENTS | TRACE_COL_MAJOR)) == (TRACE_EVENTS | TRACE_COL_MAJOR))
       throw std::runtime_error("zkb200: commit: bad zkb200_trace.flags for " + t.name);
     if (t.flags & TRACE_EVENTS) {
-      const size_t rows_needed = t.name == "KeccakSponge" ? t.n_events * KS_ROUNDS
-                                                          : ceil_div(t.n_events, (size_t)alu_events_per_row(alu_chip_by_name(t.name.c_str())));
       event_record_words(t.name);       // throws for a chip without a row filler
-      const size_t w = t.name == "KeccakSponge" ? (size_t)KS_WIDTH : (size_t)alu_width(alu_chip_by_name(t.name.c_str()));
+      const size_t rows_needed = t.name == "KeccakSponge" ? t.n_events * KS_ROUNDS : t.name == "Global" ? t.n_events
+                                 : ceil_div(t.n_events, (size_t)alu_events_per_row(alu_chip_by_name(t.name.c_str())));
+      const size_t w = t.name == "KeccakSponge" ? (size_t)KS_WIDTH : t.name == "Global" ? (size_t)GLOBAL_WIDTH
+                       : (size_t)alu_width(alu_chip_by_name(t.name.c_str()));
       if (w != t.width) throw std::runtime_error("zkb200: commit: the row filler of " + t.name + " writes another width");
       if (rows_needed > t.height) throw std::runtime_error("zkb200: commit: more event rows than the table holds: " + t.name);
     } else if ((t.flags & TRACE_COL_MAJOR) && t.height * t.width && !is_device_pointer(t.data))

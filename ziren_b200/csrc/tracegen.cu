@@ -10,10 +10,14 @@ namespace zkb {
 
 __constant__ u32 d_inv255[256];
 
+__constant__ GlobalConsts d_global_consts;
+
 void tracegen_upload_constants() {
   u32 h[256];
   alu_build_inv255(h);
   ZKB_CUDA(cudaMemcpyToSymbol(d_inv255, h, sizeof(h)));
+  static const GlobalConsts g = [] { GlobalConsts k; global_build_consts(k); return k; }();
+  ZKB_CUDA(cudaMemcpyToSymbol(d_global_consts, &g, sizeof(g)));
 }
 
 constexpr int TG_ROWS = 128;   // threads per CTA of the KeccakSponge kernel
@@ -71,6 +75,60 @@ void keccak_sponge_trace(const u32* blocks_dev, size_t n_blocks, size_t height, 
   if (!height) return;
   if (n_blocks * KS_ROUNDS > height) throw std::runtime_error("zkb200: keccak_sponge_trace: more rows than the table holds");
   keccak_sponge_rows_kernel<<<ceil_div(height, TG_ROWS), TG_ROWS, 0, s>>>(blocks_dev, n_blocks, height, out_colmajor);
+  ZKB_CHECK_LAUNCH();
+}
+
+// K6c: the Global chip (tracegen_global.cuh): lift every event to its curve point, scan the points under the curve addition,
+// write the accumulation columns.  One thread per event / chunk / row; compute-bound (a few thousand field products per event
+// in the lift, about a thousand per curve addition), the rows are 99 words.
+constexpr int TG_GLOBAL_THREADS = 128;
+__global__ void __launch_bounds__(TG_GLOBAL_THREADS) global_lift_kernel(const u32* __restrict__ events, size_t n, GlobalOut out,
+                                                                        u32* __restrict__ points) {
+  const size_t row = (size_t)blockIdx.x * TG_GLOBAL_THREADS + threadIdx.x;
+  if (row == 0) curve_store(points, d_global_consts.start);
+  if (row < n) global_lift_row(events + GLOBAL_EVENT_WORDS * row, row, d_global_consts, out, points);
+}
+__global__ void __launch_bounds__(TG_GLOBAL_THREADS) global_total_kernel(const u32* __restrict__ pts, size_t n, size_t chunks,
+                                                                         u32* __restrict__ totals) {
+  const size_t t = (size_t)blockIdx.x * TG_GLOBAL_THREADS + threadIdx.x;
+  if (t < chunks) global_chunk_total(pts, n, t, d_global_consts, totals);
+}
+__global__ void __launch_bounds__(TG_GLOBAL_THREADS) global_rescan_kernel(u32* __restrict__ pts, size_t n, size_t chunks,
+                                                                          const u32* __restrict__ scanned_totals) {
+  const size_t t = (size_t)blockIdx.x * TG_GLOBAL_THREADS + threadIdx.x;
+  if (t < chunks) global_chunk_rescan(pts, n, t, d_global_consts, scanned_totals);
+}
+__global__ void __launch_bounds__(TG_GLOBAL_THREADS) global_finish_kernel(size_t n, size_t height, const u32* __restrict__ sums,
+                                                                          GlobalOut out) {
+  const size_t row = (size_t)blockIdx.x * TG_GLOBAL_THREADS + threadIdx.x;
+  if (row < height) global_finish_row(row, n, sums, d_global_consts, out);
+}
+// inclusive scan of n points in place: chunk totals, the same scan over the totals, every chunk again from its prefix
+static void global_scan(u32* pts, size_t n, cudaStream_t s) {
+  if (n <= 1) return;
+  const size_t chunks = ceil_div(n, (size_t)GLOBAL_SCAN_CHUNK);
+  const unsigned grid = (unsigned)ceil_div(chunks, (size_t)TG_GLOBAL_THREADS);
+  if (chunks == 1) {
+    global_rescan_kernel<<<1, TG_GLOBAL_THREADS, 0, s>>>(pts, n, 1, nullptr);
+    ZKB_CHECK_LAUNCH();
+    return;
+  }
+  DevBuf totals(chunks * GLOBAL_POINT_WORDS, s);
+  global_total_kernel<<<grid, TG_GLOBAL_THREADS, 0, s>>>(pts, n, chunks, totals.p);
+  ZKB_CHECK_LAUNCH();
+  global_scan(totals.p, chunks, s);
+  global_rescan_kernel<<<grid, TG_GLOBAL_THREADS, 0, s>>>(pts, n, chunks, totals.p);
+  ZKB_CHECK_LAUNCH();
+}
+void global_trace(const u32* events_dev, size_t n, size_t height, u32* out, bool col_major, cudaStream_t s) {
+  if (!height) return;
+  if (n > height) throw std::runtime_error("zkb200: global_trace: more events than rows");
+  const GlobalOut o{out, col_major ? (size_t)1 : (size_t)GLOBAL_WIDTH, col_major ? height : (size_t)1};
+  DevBuf points((n + 1) * GLOBAL_POINT_WORDS, s);
+  global_lift_kernel<<<(unsigned)ceil_div(n ? n : (size_t)1, (size_t)TG_GLOBAL_THREADS), TG_GLOBAL_THREADS, 0, s>>>(events_dev, n, o, points.p);
+  ZKB_CHECK_LAUNCH();
+  global_scan(points.p, n + 1, s);
+  global_finish_kernel<<<(unsigned)ceil_div(height, (size_t)TG_GLOBAL_THREADS), TG_GLOBAL_THREADS, 0, s>>>(n, height, points.p, o);
   ZKB_CHECK_LAUNCH();
 }
 

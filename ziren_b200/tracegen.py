@@ -45,6 +45,7 @@ EVENT_BYTES = 28
 CPU_WIDTH, CPU_EVENT_WORDS = 67, 28            # zkb200_cpu_event: the flattened CpuEvent + Instruction
 MISC_WIDTH, MISC_EVENT_WORDS = 72, 15          # MiscEvent
 PACKED_CHIPS = {"MemoryLocal": (56, 4)}       # width, events per row (seven-word MemoryLocalEvent records)
+GLOBAL_WIDTH, GLOBAL_EVENT_WORDS = 99, 8        # GlobalLookupEvent: message[7], is_receive | kind << 8
 SYSCALL_EVENT_WORDS = 14                       # SyscallEvent
 MEMGLOBAL_EVENT_WORDS = 6                      # zkb200_memory_global_event: MemoryInitializeFinalizeEvent + prev_addr + position
 # chip -> (width, event words): DivRem takes CompAluEvent records like Mul, the three syscall tables SyscallEvent records
@@ -61,6 +62,8 @@ def width(chip: str) -> int:
         return MISC_WIDTH
     if chip in ROW_CHIPS:
         return ROW_CHIPS[chip][0]
+    if chip == "Global":
+        return GLOBAL_WIDTH
     return (ALU_CHIPS.get(chip) or COMP_CHIPS[chip])[0]
 
 
@@ -75,6 +78,8 @@ def event_words(chip: str) -> int:
         return MISC_EVENT_WORDS
     if chip in ROW_CHIPS:
         return ROW_CHIPS[chip][1]
+    if chip == "Global":
+        return GLOBAL_EVENT_WORDS
     return COMP_EVENT_WORDS if chip in COMP_CHIPS else EVENT_WORDS
 
 
@@ -672,4 +677,25 @@ def synthetic_memory_global_events(n: int, seed: int = 0, shard: int = 3) -> np.
     ev[:, 1] = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
     ev[:, 2] = rng.integers(0, shard + 1, n)
     ev[:, 3] = rng.integers(0, 1 << 24, n)
+    return ev
+
+
+def synthetic_global_events(n: int, seed: int = 0, shard: int = 3) -> np.ndarray:
+    """n GlobalLookupEvent records as (n, 8) uint32 words {message[7], is_receive | kind << 8}
+    (crates/core/executor/src/events/global.rs:6-15): memory messages {shard, timestamp, addr, four value bytes} of kind
+    LookupKind::Memory = 1 (crates/core/machine/src/memory/local.rs generate_dependencies), sent and received, and syscall
+    messages {shard, clk, syscall_id, four half-words} of kinds Syscall = 6 / SyscallResult = 8 (crates/stark/src/lookup/lookup.rs:25-47,
+    syscall/chip.rs:152-167);
+    message[0] below 2^16 as the chip range-checks it."""
+    rng = np.random.default_rng(0x610B + seed)
+    ev = np.zeros((n, GLOBAL_EVENT_WORDS), np.uint32)
+    if n == 0:
+        return ev
+    mem = rng.integers(0, 4, n) != 0
+    ev[:, 0] = rng.integers(0, shard + 1, n)
+    ev[:, 1] = rng.integers(0, 1 << 24, n)
+    ev[:, 2] = np.where(mem, rng.integers(0, kb.P, n), rng.choice(_SYSCALL_TABLE & 0xFFFF, n))
+    ev[:, 3:7] = np.where(mem[:, None], rng.integers(0, 256, (n, 4)), rng.integers(0, 1 << 16, (n, 4)))
+    kind = np.where(mem, 1, rng.choice([6, 8], n)).astype(np.uint32)
+    ev[:, 7] = rng.integers(0, 2, n).astype(np.uint32) | (kind << np.uint32(8))
     return ev
