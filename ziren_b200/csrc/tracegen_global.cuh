@@ -135,12 +135,15 @@ KB_HD Fp fp_sqrt_ts(Fp a, Fp root) {
   }
   return x;
 }
-// SepticExtension::sqrt (septic_extension.rs:632-680): false if n is not a square (zero counts as none: lift_x skips y = 0).
-// n^((r + 1) / 2) with r = 1 + p + ... + p^6 squares to norm(n) * n, so it is divided by a root of the norm.
-KB_HD bool sep_sqrt(const Sep& n, const GlobalConsts& k, Sep& out) {
-  const Sep q = sep_pow_r_1(n, k);
-  const Fp norm = sep_norm_with(n, q);
-  if (fp_pow(norm, (KB_P - 1) / 2) != fp_one()) return false;
+// SepticExtension::is_square (septic_extension.rs:621-628): n is a square iff its norm n^(1 + p + ... + p^6) is one in F_p.
+// Zero counts as a non-square here: lift_x skips y = 0 anyway.
+KB_HD bool sep_is_square(const Sep& n, const GlobalConsts& k, Fp& norm) {
+  norm = sep_norm_with(n, sep_pow_r_1(n, k));
+  return fp_pow(norm, (KB_P - 1) / 2) == fp_one();
+}
+// SepticExtension::sqrt (septic_extension.rs:632-680) of a square with the given norm: n^((r + 1) / 2), r = 1 + p + ... + p^6,
+// squares to norm(n) * n, so it is divided by a root of the norm.
+KB_HD Sep sep_sqrt_of_square(const Sep& n, Fp norm, const GlobalConsts& k) {
   Sep it = n, pw = n;                              // n^((p + 1) / 2) = n^(1 + 2^23 + ... + 2^29)
   for (int i = 1; i < 30; i++) {
     it = sep_sqr(it);
@@ -151,7 +154,12 @@ KB_HD bool sep_sqrt(const Sep& n, const GlobalConsts& k, Sep& out) {
   f = sep_double_frobenius(f, k); den = den * f;
   f = sep_double_frobenius(f, k); den = den * f;
   den = den * n;
-  out = den * fp_sqrt_ts(fp_inv(norm), k.ts_root);
+  return den * fp_sqrt_ts(fp_inv(norm), k.ts_root);
+}
+KB_HD bool sep_sqrt(const Sep& n, const GlobalConsts& k, Sep& out) {
+  Fp norm;
+  if (!sep_is_square(n, k, norm)) return false;
+  out = sep_sqrt_of_square(n, norm, k);
   return true;
 }
 // x^3 + 3z x - 3 (septic_curve.rs:97-121)
@@ -212,12 +220,22 @@ KB_HD void global_lift_row(const u32* e, size_t row, const GlobalConsts& k, cons
   const Fp m6 = x.c[6] * fp_from_canonical(256);
   CurvePt pt = curve_infinity();
   u32 offset = 0;
+  // The search for the first offset whose curve value is a square (a norm and a Legendre symbol per trial, two trials on
+  // average, a different number in every lane of a warp) is kept apart from the root (six times the work of a trial), so
+  // that the lanes of a warp take their roots together instead of one trial position after the other.
   for (u32 o = 0; o < 256; o++) {
-    x.c[6] = m6 + fp_from_canonical(o);
-    Sep y;
-    if (!sep_sqrt(curve_formula(x), k, y)) continue;
+    Sep n;
+    Fp norm;
+    bool found = false;
+    for (; o < 256; o++) {
+      x.c[6] = m6 + fp_from_canonical(o);
+      n = curve_formula(x);
+      if (sep_is_square(n, k, norm)) { found = true; break; }
+    }
+    if (!found) break;
+    const Sep y = sep_sqrt_of_square(n, norm, k);
     const u32 y6 = fp_to_canonical(y.c[6]);
-    if (y6 == 0) continue;                                        // is_exception
+    if (y6 == 0) continue;                                        // is_exception: on to the next offset
     // lift_x returns the root with 1 <= y6 <= (p - 1) / 2; a send takes the negated point (global_lookup.rs:31-43)
     const bool low = y6 <= (KB_P - 1) / 2;
     pt.x = x; pt.y = low == is_receive ? y : -y;
