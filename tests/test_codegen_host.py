@@ -171,6 +171,18 @@ def test_generated_kernels_of_the_mini_machine_match_the_oracle_on_the_host(orac
     _check_chip(oracle, om, case.machine, name, case.prep.get(name), case.traces[name], case.public_values, tw_tables, tmp_path)
 
 
+def test_generated_kernel_of_the_real_global_chip_matches_the_oracle_on_the_host(oracle, tw_tables, tmp_path):
+    """GlobalChip::eval restated (ziren_b200/synthetic.py _global_chip: 120 constraints of degree three over septic-extension
+    products, first-row and transition selectors, the global-scope cumulative sum) over rows from trace generation."""
+    from ziren_b200 import synthetic
+    from ziren_b200 import tracegen as tg
+    ev = tg.synthetic_global_events(50, seed=4)
+    case = synthetic.global_case(oracle.global_trace(ev, 64), num_queries=6, pow_bits=3)
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    _check_chip(oracle, om, case.machine, "Global", None, case.traces["Global"], case.public_values, tw_tables, tmp_path)
+
+
 @pytest.mark.parametrize("which,name", [("edge", "PlainA"), ("edge", "Alu"), ("edge", "Program"), ("compress", "Poseidon2Wide"),
                                         ("compress", "PublicValues"), ("core", "MemoryInstrs"), ("core", "Byte")])
 def test_generated_kernels_of_other_machines_match_the_oracle_on_the_host(oracle, tw_tables, tmp_path, which, name):

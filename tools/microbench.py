@@ -20,7 +20,7 @@ from ziren_b200.prover import B200Prover  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("what", choices=["lde", "ntt", "mmcs", "permute", "tracegen", "keccak"])
-ap.add_argument("--chip", default="ShiftRight", help="tracegen: AddSub, Bitwise, Lt, ShiftLeft, ShiftRight or CloClz")
+ap.add_argument("--chip", default="ShiftRight", help="tracegen: any chip with a row filler (csrc/tracegen.cu alu_chip_by_name, or Global)")
 ap.add_argument("--col-major", action="store_true", help="tracegen: write the column-major layout")
 ap.add_argument("--log-n", type=int, default=18)
 ap.add_argument("--width", type=int, default=512)
@@ -64,11 +64,18 @@ elif args.what == "mmcs":
 elif args.what == "tracegen":
     from ziren_b200 import tracegen as tg
     w = tg.width(args.chip)
-    ev = tg.synthetic_events(args.chip, n - 77, seed=1)
+    gens = {"Mul": tg.synthetic_mul_events, "MemoryInstrs": tg.synthetic_mem_instr_events, "MemoryLocal": tg.synthetic_memory_local_events,
+            "Cpu": tg.synthetic_cpu_events, "MiscInstrs": tg.synthetic_misc_events, "DivRem": tg.synthetic_div_rem_events,
+            "Global": tg.synthetic_global_events,
+            "SyscallInstrs": lambda k, seed: tg.synthetic_syscall_events(k, seed=seed, kind="instrs"),
+            "SyscallCore": lambda k, seed: tg.synthetic_syscall_events(k, seed=seed, kind="core"),
+            "MemoryGlobalInit": lambda k, seed: tg.memory_global_records(tg.synthetic_memory_global_events(k, seed=seed), 0)}
+    n_ev = (n - 77) * tg.events_per_row(args.chip)
+    ev = gens[args.chip](n_ev, seed=1) if args.chip in gens else tg.synthetic_events(args.chip, n_ev, seed=1)
     d_ev = torch.from_numpy(ev.view(np.int32)).cuda()
     d_out = torch.empty((n * w,), dtype=torch.int32, device="cuda")
     ms = timed(lambda: prover.generate_alu_trace(args.chip, d_ev, args.log_n, d_out, col_major=args.col_major))
-    alg = 28.0 * (n - 77) + 4.0 * n * w          # one event read, one row written
+    alg = 4.0 * ev.size + 4.0 * n * w            # the event records read, the rows written (Global is compute-bound: see Grows/s)
 elif args.what == "keccak":
     from ziren_b200 import keccak_sponge as ksp
     w = ksp.WIDTH

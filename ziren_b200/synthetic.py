@@ -751,3 +751,123 @@ def alu_case(traces: dict, *, with_lookup_pair: bool = True, **kw) -> ShardCase:
                       log_blowup=kw.get("log_blowup", 1))
     cycles = sum(int(traces[k].shape[0]) for k in ("AddSub", "ShiftLeft", "Lt", "ShiftRight", "Bitwise", "CloClz", "Branch", "Jump", "MovCond") if k in traces)
     return ShardCase(machine, {}, traces, pv, cycles)
+
+
+# ---- the Global chip (crates/core/machine/src/global/mod.rs) -------------------------------------------------------------------
+# CURVE_CUMULATIVE_SUM_START_{X,Y}, crates/stark/src/septic_digest.rs:9-14
+GLOBAL_START_POINT = (637514027, 1595065213, 1998064738, 72333738, 1211544370, 822986770, 1518535784,
+                      1604177449, 90440090, 259343427, 140470264, 1162099742, 941559812, 1064053343)
+
+
+def _sep_mul(a, b):
+    """Product in F_p[z] / (z^7 + 2z - 8) of two coefficient lists of expressions (SepticExtension::mul,
+    crates/stark/src/septic_extension.rs:306-323)."""
+    r = [None] * 13
+    for i in range(7):
+        for j in range(7):
+            t = a[i] * b[j]
+            r[i + j] = t if r[i + j] is None else r[i + j] + t
+    out = r[:7]
+    for i in range(7, 13):
+        out[i - 7] = out[i - 7] + r[i] * 8
+        out[i - 6] = out[i - 6] - r[i] * 2
+    return out
+
+
+def _sep_add(a, b):
+    return [x + y for x, y in zip(a, b)]
+
+
+def _sep_sub(a, b):
+    return [x - y for x, y in zip(a, b)]
+
+
+def _global_chip() -> Chip:
+    """GlobalChip::eval crates/core/machine/src/global/mod.rs:216-276 with GlobalLookupOperation::eval_single_digest
+    (operations/global_lookup.rs:93-175) and GlobalAccumulationOperation::eval_accumulation
+    (operations/global_accumulation.rs:129-224), N = 1; columns of GlobalCols (global/mod.rs:53-63).  Left out: the receive of the
+    message from the chips that emit it and the U16Range byte lookup of message[0] (lookups; their senders are other tables).
+    The chip commits in the global scope: its last fourteen columns are the shard's cumulative sum."""
+    def ev(b):
+        m = [b.main(i) for i in range(7)]
+        kind = b.main(7)
+        offset_bits = [b.main(8 + i) for i in range(8)]
+        x = [b.main(16 + i) for i in range(7)]
+        y = [b.main(23 + i) for i in range(7)]
+        y6_bits = [b.main(30 + i) for i in range(30)]
+        witness, is_receive, is_send, is_real = b.main(60), b.main(61), b.main(62), b.main(63)
+        init_x, init_y = [b.main(64 + i) for i in range(7)], [b.main(71 + i) for i in range(7)]
+        checker = [b.main(78 + i) for i in range(7)]
+        cum_x, cum_y = [b.main(85 + i) for i in range(7)], [b.main(92 + i) for i in range(7)]
+        next_real = b.main(63, next=True)
+        next_init_x, next_init_y = [b.main(64 + i, next=True) for i in range(7)], [b.main(71 + i, next=True) for i in range(7)]
+        real = b.when(is_real)
+        # eval_single_digest
+        _assert_bool(b, is_real)
+        offset = offset_bits[0]
+        for i in range(8):
+            _assert_bool(b, offset_bits[i])
+            if i:
+                offset = offset + offset_bits[i] * (1 << i)
+        real.assert_eq(x[0], m[0] + kind * 65536)
+        for i in range(1, 6):
+            real.assert_eq(x[i], m[i])
+        real.assert_eq(x[6], m[6] * 256 + offset)
+        y2 = _sep_mul(y, y)
+        x3 = _sep_mul(_sep_mul(x, x), x)
+        rhs = list(x3)
+        # + 3z * x - 3: z * (x0 .. x6) = (8 x6, x0 - 2 x6, x1, .. x5)
+        zx = [x[6] * 8, x[0] - x[6] * 2] + [x[i] for i in range(1, 6)]
+        rhs = [rhs[i] + zx[i] * 3 for i in range(7)]
+        rhs[0] = rhs[0] - 3
+        for i in range(7):
+            b.assert_eq(y2[i], rhs[i])
+        y6_value, top = y6_bits[0], None
+        for i in range(30):
+            _assert_bool(b, y6_bits[i])
+            if i:
+                y6_value = y6_value + y6_bits[i] * (1 << i)
+            if i >= 23:
+                top = y6_bits[i] if top is None else top + y6_bits[i]
+        real.assert_eq(witness * (top - 7), 1)
+        b.when(is_receive).assert_eq(y[6], y6_value + 1)
+        b.when(is_send).assert_eq(y[6], y6_value + ((1 << 30) - (1 << 23) + 1))
+        # eval_accumulation
+        b.when_transition().when(1 - is_real).assert_zero(next_real)
+        first = b.when_first_row()
+        for i in range(7):
+            first.assert_eq(init_x[i], GLOBAL_START_POINT[i])
+            first.assert_eq(init_y[i], GLOBAL_START_POINT[7 + i])
+        dx, dy = _sep_sub(x, init_x), _sep_sub(y, init_y)
+        chk_x = _sep_sub(_sep_mul(_sep_add(_sep_add(init_x, x), cum_x), _sep_mul(dx, dx)), _sep_mul(dy, dy))
+        chk_y = _sep_sub(_sep_mul(_sep_add(init_y, cum_y), dx), _sep_mul(dy, _sep_sub(init_x, cum_x)))
+        not_real = b.when(1 - is_real)
+        trans = b.when_transition()
+        for i in range(7):
+            b.assert_eq(chk_x[i], checker[i])
+            real.assert_zero(checker[i])
+            real.assert_zero(chk_y[i])
+            not_real.assert_eq(init_x[i], cum_x[i])
+            not_real.assert_eq(init_y[i], cum_y[i])
+            trans.assert_eq(cum_x[i], next_init_x[i])
+            trans.assert_eq(cum_y[i], next_init_y[i])
+    return Chip("Global", 0, 99, ev, global_scope=True)
+
+
+def global_case(global_rows: np.ndarray, **kw) -> ShardCase:
+    """A shard with the Global table (canonical rows as trace generation produces them) under the chip's restated constraints,
+    next to the Fibonacci / Sink pair so that the shard also has permutation traces."""
+    n = 1 << 5
+    a, b_ = 0, 1
+    rows = np.empty((n, 2), dtype=np.uint32)
+    for i in range(n):
+        rows[i] = (a, b_)
+        a, b_ = b_, (a + b_) % P
+    pv = np.zeros(8, dtype=np.uint32)
+    pv[1], pv[2], pv[3] = 0, 1, rows[-1, 1]
+    sink = np.zeros((n, 3), dtype=np.uint32)
+    sink[:, :2] = rows[::-1]
+    sink[:, 2] = 1
+    machine = Machine([_global_chip(), _fib_chip(), _sink_chip()], num_pv_elts=4, num_queries=kw.get("num_queries", 8),
+                      pow_bits=kw.get("pow_bits", 4), log_blowup=kw.get("log_blowup", 1))
+    return ShardCase(machine, {}, {"Global": global_rows, "Fibonacci": rows, "Sink": sink}, pv, int(global_rows.shape[0]))
