@@ -183,6 +183,25 @@ def test_generated_kernel_of_the_real_global_chip_matches_the_oracle_on_the_host
     _check_chip(oracle, om, case.machine, "Global", None, case.traces["Global"], case.public_values, tw_tables, tmp_path)
 
 
+def test_generated_kernels_of_the_memory_global_tables_match_the_oracle_on_the_host(oracle, tw_tables, tmp_path):
+    """MemoryGlobalChip::eval restated (320 constraints, public values, next-row columns, one send per row) and the Global chip
+    with its receive: constraint kernel and permutation-trace kernel of each."""
+    from ziren_b200 import synthetic
+    from ziren_b200 import tracegen as tg
+    init = tg.synthetic_memory_global_events(20, seed=1)
+    init[:, 2], init[:, 3] = 0, 1
+    fin = tg.synthetic_memory_global_events(30, seed=2)
+    pi, pf = int(init[:, 0].min()) - 1, int(fin[:, 0].min()) - 1
+    gev = np.concatenate([tg.memory_global_lookup_events(init, False), tg.memory_global_lookup_events(fin, True)])
+    si, sf = init[np.argsort(init[:, 0])], fin[np.argsort(fin[:, 0])]
+    case = synthetic.memory_global_case(oracle.memory_global_trace(si, pi, 32), oracle.memory_global_trace(sf, pf, 32),
+                                        oracle.global_trace(gev, 64), pi, pf, num_queries=6, pow_bits=3)
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    for name in ("MemoryGlobalInit", "MemoryGlobalFinalize", "Global"):
+        _check_chip(oracle, om, case.machine, name, None, case.traces[name], case.public_values, tw_tables, tmp_path)
+
+
 @pytest.mark.parametrize("which,name", [("edge", "PlainA"), ("edge", "Alu"), ("edge", "Program"), ("compress", "Poseidon2Wide"),
                                         ("compress", "PublicValues"), ("core", "MemoryInstrs"), ("core", "Byte")])
 def test_generated_kernels_of_other_machines_match_the_oracle_on_the_host(oracle, tw_tables, tmp_path, which, name):

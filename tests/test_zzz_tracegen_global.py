@@ -229,6 +229,52 @@ def test_generated_rows_satisfy_the_restated_air(oracle):
         assert not om.verify_shard(p2)[0], (row, col)
 
 
+def _memory_shard(oracle, first_shard, n_init=40, n_fin=70, log_init=6, log_fin=7, seed=1):
+    """Memory initialisation / finalisation events of one shard, the global lookups they emit
+    (MemoryGlobalChip::generate_dependencies) and the three tables from trace generation."""
+    from ziren_b200 import synthetic
+    init = tg.synthetic_memory_global_events(n_init, seed=seed)
+    init[:, 2], init[:, 3] = 0, 1                        # MemoryGlobalInit constrains timestamp = 1
+    fin = tg.synthetic_memory_global_events(n_fin, seed=seed + 1)
+    if first_shard:                                      # previous address 0: the table starts with register 0 = 0
+        init[0, :2] = 0
+        fin[0, :2] = 0
+        prev_init = prev_fin = 0
+    else:
+        prev_init, prev_fin = int(init[:, 0].min()) - 1, int(fin[:, 0].min()) - 3
+    rec_init, rec_fin = tg.memory_global_records(init, prev_init), tg.memory_global_records(fin, prev_fin)
+    gev = np.concatenate([tg.memory_global_lookup_events(init, False), tg.memory_global_lookup_events(fin, True)])
+    log_g = tg.padded_log_height(len(gev))
+    rows = {"MemoryGlobalInit": oracle.memory_global_trace(rec_init[:, :4], prev_init, 1 << log_init),
+            "MemoryGlobalFinalize": oracle.memory_global_trace(rec_fin[:, :4], prev_fin, 1 << log_fin),
+            "Global": oracle.global_trace(gev, 1 << log_g)}
+    case = synthetic.memory_global_case(rows["MemoryGlobalInit"], rows["MemoryGlobalFinalize"], rows["Global"], prev_init, prev_fin)
+    events = {"MemoryGlobalInit": (rec_init, log_init), "MemoryGlobalFinalize": (rec_fin, log_fin), "Global": (gev, log_g)}
+    return case, rows, events
+
+
+@pytest.mark.parametrize("first_shard", [False, True])
+def test_memory_tables_and_global_table_satisfy_their_airs_and_the_lookup_between_them(oracle, first_shard):
+    """MemoryGlobalInit, MemoryGlobalFinalize and Global from trace generation under MemoryGlobalChip::eval / GlobalChip::eval
+    restated as data, tied by the real lookup: every real memory row sends (shard, timestamp, addr, value bytes, is_send,
+    is_receive, Memory), Global receives its messages - so the Global table's events must be exactly the memory tables'
+    rows.  The restated prover and verifier accept the shard and reject single-cell corruptions (a flipped value bit breaks
+    the lookup balance, the others a constraint)."""
+    case, rows, _ = _memory_shard(oracle, first_shard)
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    proof, _ = om.prove_shard(case.traces, case.public_values)
+    ok, err = om.verify_shard(proof)
+    assert ok, err
+    # addr, address bit, lt flag, value bit, is_next_comp, is_first_comp, is_last_addr; a Global message word
+    for name, row, col in (("MemoryGlobalInit", 3, 2), ("MemoryGlobalInit", 7, 40), ("MemoryGlobalFinalize", 9, 10), ("MemoryGlobalFinalize", 5, 80),
+                           ("MemoryGlobalFinalize", 4, 106), ("MemoryGlobalFinalize", 0, 109), ("MemoryGlobalFinalize", 69, 110), ("Global", 4, 3)):
+        bad = rows[name].copy()
+        bad[row, col] = (int(bad[row, col]) + 1) % P
+        p2, _ = om.prove_shard({**case.traces, name: bad}, case.public_values)
+        assert not om.verify_shard(p2)[0], (name, row, col)
+
+
 @pytest.fixture(scope="module")
 def gpu():
     import torch
@@ -277,6 +323,30 @@ def test_global_shard_proves_bit_exact(gpu, oracle, mode):
         if mode != "rows_host":
             d = torch.from_numpy(ev.view(np.int32)).cuda() if mode == "events_device" else ev
             inputs["Global"] = EventTrace(d, log_h, tg.GLOBAL_WIDTH)
+        got, _ = prover.prove_shard(pk, inputs, case.public_values)
+        ok, err = om.verify_shard(got)
+        assert ok, err
+        assert np.array_equal(got, want)
+        pk.free()
+    finally:
+        prover.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("first_shard", [False, True])
+def test_memory_and_global_tables_prove_from_event_records(gpu, oracle, first_shard):
+    """The three tables that carry memory across shards handed to zkb200_commit as EVENT RECORDS (the memory events with their
+    neighbour's address folded in, the global lookups they emit): rows, permutation traces of the lookup between them,
+    quotients of the restated AIRs - the proof is the oracle's, word for word."""
+    from ziren_b200.prover import B200Prover, EventTrace
+    case, _, events = _memory_shard(oracle, first_shard, n_init=900, n_fin=2000, log_init=10, log_fin=11, seed=5)
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    want, _ = om.prove_shard(case.traces, case.public_values)
+    prover = B200Prover(case.machine, device=0)
+    try:
+        pk = prover.setup({})
+        inputs = {name: EventTrace(ev, log_h, tg.width(name)) for name, (ev, log_h) in events.items()}
         got, _ = prover.prove_shard(pk, inputs, case.public_values)
         ok, err = om.verify_shard(got)
         assert ok, err

@@ -782,11 +782,12 @@ def _sep_sub(a, b):
     return [x - y for x, y in zip(a, b)]
 
 
-def _global_chip() -> Chip:
+def _global_chip(with_receive: bool = False) -> Chip:
     """GlobalChip::eval crates/core/machine/src/global/mod.rs:216-276 with GlobalLookupOperation::eval_single_digest
     (operations/global_lookup.rs:93-175) and GlobalAccumulationOperation::eval_accumulation
-    (operations/global_accumulation.rs:129-224), N = 1; columns of GlobalCols (global/mod.rs:53-63).  Left out: the receive of the
-    message from the chips that emit it and the U16Range byte lookup of message[0] (lookups; their senders are other tables).
+    (operations/global_accumulation.rs:129-224), N = 1; columns of GlobalCols (global/mod.rs:53-63).  with_receive: the receive
+    of (message, is_send, is_receive, kind) from the tables that emit global lookups (global/mod.rs:232-250); left out: the
+    U16Range byte lookup of message[0].
     The chip commits in the global scope: its last fourteen columns are the shard's cumulative sum."""
     def ev(b):
         m = [b.main(i) for i in range(7)]
@@ -802,6 +803,8 @@ def _global_chip() -> Chip:
         next_real = b.main(63, next=True)
         next_init_x, next_init_y = [b.main(64 + i, next=True) for i in range(7)], [b.main(71 + i, next=True) for i in range(7)]
         real = b.when(is_real)
+        if with_receive:
+            b.receive(KIND_GLOBAL, m + [is_send, is_receive, kind], is_real)
         # eval_single_digest
         _assert_bool(b, is_real)
         offset = offset_bits[0]
@@ -871,3 +874,99 @@ def global_case(global_rows: np.ndarray, **kw) -> ShardCase:
     machine = Machine([_global_chip(), _fib_chip(), _sink_chip()], num_pv_elts=4, num_queries=kw.get("num_queries", 8),
                       pow_bits=kw.get("pow_bits", 4), log_blowup=kw.get("log_blowup", 1))
     return ShardCase(machine, {}, {"Global": global_rows, "Fibonacci": rows, "Sink": sink}, pv, int(global_rows.shape[0]))
+
+
+def _memory_global_chip(finalize: bool, pv_prev: int, pv_last: int) -> Chip:
+    """MemoryGlobalChip::eval crates/core/machine/src/memory/global.rs:248-445 with KoalaBearBitDecomposition::range_check
+    (operations/koala_bear_range.rs:50-117), AssertLtColsBits::eval (operations/cmp.rs:322-391) and IsZeroOperation::eval
+    (operations/is_zero.rs:42-71); columns of MemoryInitCols (global.rs:210-245).  pv_prev / pv_last: where the 32 bits of
+    previous_{init,finalize}_addr_bits and last_{init,finalize}_addr_bits start in the public values."""
+    def ev(b):
+        shard, timestamp, addr = b.main(0), b.main(1), b.main(2)
+        lt = [b.main(3 + i) for i in range(32)]
+        bits = [b.main(35 + i) for i in range(32)]
+        ands = [b.main(67 + i) for i in range(6)]
+        value = [b.main(73 + i) for i in range(32)]
+        is_real, is_next_comp, inverse, prev_zero, is_first_comp, is_last_addr = (b.main(105 + i) for i in range(6))
+        n_lt = [b.main(3 + i, next=True) for i in range(32)]
+        n_bits = [b.main(35 + i, next=True) for i in range(32)]
+        n_real, n_next_comp = b.main(105, next=True), b.main(106, next=True)
+        prev_bits = [b.pub(pv_prev + i) for i in range(32)]
+        last_bits = [b.pub(pv_last + i) for i in range(32)]
+        _assert_bool(b, is_real)
+        for v in value:
+            _assert_bool(b, v)
+        byte = [sum((value[8 * k + i] * (1 << i) for i in range(1, 8)), value[8 * k]) for k in range(4)]
+        if finalize:
+            b.send(KIND_GLOBAL, [shard, timestamp, addr] + byte + [is_real * 0, is_real * 1, KIND_MEMORY], is_real)
+        else:
+            b.send(KIND_GLOBAL, [0, 0, addr] + byte + [is_real * 1, is_real * 0, KIND_MEMORY], is_real)
+        # KoalaBearBitDecomposition::range_check(addr, addr_bits, is_real)
+        real = b.when(is_real)
+        for x in bits:
+            real.assert_zero(x * (x - 1))
+        real.assert_eq(sum((bits[i] * ((1 << i) % P) for i in range(1, 32)), bits[0]), addr)
+        top = bits[24:32]
+        real.assert_zero(top[7])
+        real.assert_eq(ands[0], top[0] * top[1])
+        for i in range(1, 6):
+            real.assert_eq(ands[i], ands[i - 1] * top[i + 1])
+        real.when(ands[5]).assert_zero(sum(bits[1:24], bits[0]))
+
+        def assert_lt(flags, a_bits, b_bits, cond):             # AssertLtColsBits::eval
+            for f in flags:
+                _assert_bool(b, f)
+            on = b.when(cond)
+            on.assert_eq(sum(flags[1:], flags[0]), 1)
+            visited, a_cmp, b_cmp = None, None, None
+            for i in reversed(range(32)):
+                visited = flags[i] if visited is None else visited + flags[i]
+                a_cmp = a_bits[i] * flags[i] if a_cmp is None else a_cmp + a_bits[i] * flags[i]
+                b_cmp = b_bits[i] * flags[i] if b_cmp is None else b_cmp + b_bits[i] * flags[i]
+                on.when(1 - visited).assert_eq(a_bits[i], b_bits[i])
+            on.assert_zero(a_cmp)
+            on.assert_eq(b_cmp, 1)
+
+        b.when_transition().assert_eq(n_next_comp, n_real)
+        assert_lt(n_lt, bits, n_bits, n_next_comp)
+        b.when_transition().when(1 - is_real).assert_zero(n_real)
+        prev_addr = sum((prev_bits[i] * ((1 << i) % P) for i in range(1, 32)), prev_bits[0])
+        first = b.when_first_row()
+        first.assert_eq(1 - inverse * prev_addr, prev_zero)      # IsZeroOperation::eval(prev_addr, is_prev_addr_zero, is_first_row)
+        first.assert_zero(prev_zero * (prev_zero - 1))
+        first.when(prev_zero).assert_zero(prev_addr)
+        _assert_bool(b, is_first_comp)
+        first.assert_eq(is_first_comp, 1 - prev_zero)
+        first.assert_eq(is_real, 1)
+        assert_lt(lt, prev_bits, bits, is_first_comp)
+        first.when(prev_zero).assert_zero(addr)
+        first.when(prev_zero).assert_eq(n_real, 1)
+        first.when(prev_zero).assert_eq(n_next_comp, 1)
+        if not finalize:
+            real.assert_eq(timestamp, 1)
+        for v in value:
+            first.when(1 - is_first_comp).assert_zero(v)
+        b.when_transition().assert_eq(is_last_addr, is_real * (1 - n_real))
+        for x, pub in zip(bits, last_bits):
+            b.when_last_row().when(is_real).assert_eq(x, pub)
+            b.when_transition().when(is_last_addr).assert_eq(x, pub)
+    return Chip("MemoryGlobalFinalize" if finalize else "MemoryGlobalInit", 0, 111, ev)
+
+
+def memory_global_case(init_rows: np.ndarray, finalize_rows: np.ndarray, global_rows: np.ndarray, previous_init_addr: int,
+                       previous_finalize_addr: int, **kw) -> ShardCase:
+    """A shard of the three tables that carry memory across shards, under their restated constraints AND the lookup that ties
+    them: MemoryGlobalInit / MemoryGlobalFinalize send (shard, timestamp, addr, value bytes, is_send, is_receive, Memory) for
+    every real row, Global receives its messages.  Public values: the bits of previous_init_addr, last_init_addr,
+    previous_finalize_addr, last_finalize_addr (the last addresses read off the tables)."""
+    def last_addr(rows):
+        real = rows[rows[:, 105] == 1]
+        return int(real[-1, 2]) if len(real) else 0
+    pv = np.zeros(128, dtype=np.uint32)
+    for k, a in enumerate((previous_init_addr, last_addr(init_rows), previous_finalize_addr, last_addr(finalize_rows))):
+        pv[32 * k: 32 * k + 32] = [(a >> i) & 1 for i in range(32)]
+    machine = Machine([_memory_global_chip(False, 0, 32), _memory_global_chip(True, 64, 96), _global_chip(with_receive=True)],
+                      num_pv_elts=128, num_queries=kw.get("num_queries", 8), pow_bits=kw.get("pow_bits", 4),
+                      log_blowup=kw.get("log_blowup", 1))
+    traces = {"MemoryGlobalInit": init_rows, "MemoryGlobalFinalize": finalize_rows, "Global": global_rows}
+    return ShardCase(machine, {}, traces, pv, int(global_rows.shape[0]))

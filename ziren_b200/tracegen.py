@@ -699,3 +699,19 @@ def synthetic_global_events(n: int, seed: int = 0, shard: int = 3) -> np.ndarray
     kind = np.where(mem, 1, rng.choice([6, 8], n)).astype(np.uint32)
     ev[:, 7] = rng.integers(0, 2, n).astype(np.uint32) | (kind << np.uint32(8))
     return ev
+
+
+def memory_global_lookup_events(events: np.ndarray, finalize: bool) -> np.ndarray:
+    """MemoryGlobalChip::generate_dependencies (crates/core/machine/src/memory/global.rs:62-97): one GlobalLookupEvent (n, 8)
+    per address-sorted memory event - an initialisation sends {0, 0, addr, value bytes}, a finalisation receives {shard,
+    timestamp, addr, value bytes} - of kind LookupKind::Memory."""
+    ev = np.ascontiguousarray(events, dtype=np.uint32).reshape(-1, 4)
+    ev = ev[np.argsort(ev[:, 0], kind="stable")]
+    out = np.zeros((len(ev), GLOBAL_EVENT_WORDS), np.uint32)
+    if finalize:
+        out[:, 0], out[:, 1] = ev[:, 2], ev[:, 3]
+    out[:, 2] = ev[:, 0]
+    for k in range(4):
+        out[:, 3 + k] = (ev[:, 1] >> np.uint32(8 * k)) & np.uint32(0xFF)
+    out[:, 7] = np.uint32(int(finalize)) | np.uint32(1 << 8)
+    return out
