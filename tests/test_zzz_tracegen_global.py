@@ -229,7 +229,7 @@ def test_generated_rows_satisfy_the_restated_air(oracle):
         assert not om.verify_shard(p2)[0], (row, col)
 
 
-def _memory_shard(oracle, first_shard, n_init=40, n_fin=70, log_init=6, log_fin=7, seed=1):
+def _memory_shard(oracle, first_shard, n_init=40, n_fin=70, log_init=6, log_fin=7, seed=1, n_syscalls=0):
     """Memory initialisation / finalisation events of one shard, the global lookups they emit
     (MemoryGlobalChip::generate_dependencies) and the three tables from trace generation."""
     from ziren_b200 import synthetic
@@ -244,23 +244,32 @@ def _memory_shard(oracle, first_shard, n_init=40, n_fin=70, log_init=6, log_fin=
         prev_init, prev_fin = int(init[:, 0].min()) - 1, int(fin[:, 0].min()) - 3
     rec_init, rec_fin = tg.memory_global_records(init, prev_init), tg.memory_global_records(fin, prev_fin)
     gev = np.concatenate([tg.memory_global_lookup_events(init, False), tg.memory_global_lookup_events(fin, True)])
+    sys_ev = tg.synthetic_syscall_events(n_syscalls, seed=seed, kind="core")
+    if n_syscalls:                                       # a core shard's syscall table: two more global lookups per row
+        gev = np.concatenate([gev, tg.syscall_global_lookup_events(sys_ev)])
     log_g = tg.padded_log_height(len(gev))
     rows = {"MemoryGlobalInit": oracle.memory_global_trace(rec_init[:, :4], prev_init, 1 << log_init),
             "MemoryGlobalFinalize": oracle.memory_global_trace(rec_fin[:, :4], prev_fin, 1 << log_fin),
             "Global": oracle.global_trace(gev, 1 << log_g)}
-    case = synthetic.memory_global_case(rows["MemoryGlobalInit"], rows["MemoryGlobalFinalize"], rows["Global"], prev_init, prev_fin)
     events = {"MemoryGlobalInit": (rec_init, log_init), "MemoryGlobalFinalize": (rec_fin, log_fin), "Global": (gev, log_g)}
+    if n_syscalls:
+        log_s = tg.padded_log_height(n_syscalls)
+        rows["SyscallCore"] = oracle.chip_trace("SyscallCore", sys_ev, 1 << log_s)
+        events["SyscallCore"] = (sys_ev, log_s)
+    case = synthetic.memory_global_case(rows["MemoryGlobalInit"], rows["MemoryGlobalFinalize"], rows["Global"], prev_init, prev_fin,
+                                        syscall_rows=rows.get("SyscallCore"))
     return case, rows, events
 
 
 @pytest.mark.parametrize("first_shard", [False, True])
 def test_memory_tables_and_global_table_satisfy_their_airs_and_the_lookup_between_them(oracle, first_shard):
-    """MemoryGlobalInit, MemoryGlobalFinalize and Global from trace generation under MemoryGlobalChip::eval / GlobalChip::eval
+    """MemoryGlobalInit, MemoryGlobalFinalize, Global (and, in the later shard, SyscallCore with its two global lookups per row:
+    SyscallChip::eval restated) from trace generation under MemoryGlobalChip::eval / GlobalChip::eval
     restated as data, tied by the real lookup: every real memory row sends (shard, timestamp, addr, value bytes, is_send,
     is_receive, Memory), Global receives its messages - so the Global table's events must be exactly the memory tables'
     rows.  The restated prover and verifier accept the shard and reject single-cell corruptions (a flipped value bit breaks
     the lookup balance, the others a constraint)."""
-    case, rows, _ = _memory_shard(oracle, first_shard)
+    case, rows, _ = _memory_shard(oracle, first_shard, n_syscalls=0 if first_shard else 25)
     om = oracle.OracleMachine(case.machine)
     om.setup({})
     proof, _ = om.prove_shard(case.traces, case.public_values)
@@ -268,7 +277,10 @@ def test_memory_tables_and_global_table_satisfy_their_airs_and_the_lookup_betwee
     assert ok, err
     # addr, address bit, lt flag, value bit, is_next_comp, is_first_comp, is_last_addr; a Global message word
     for name, row, col in (("MemoryGlobalInit", 3, 2), ("MemoryGlobalInit", 7, 40), ("MemoryGlobalFinalize", 9, 10), ("MemoryGlobalFinalize", 5, 80),
-                           ("MemoryGlobalFinalize", 4, 106), ("MemoryGlobalFinalize", 0, 109), ("MemoryGlobalFinalize", 69, 110), ("Global", 4, 3)):
+                           ("MemoryGlobalFinalize", 4, 106), ("MemoryGlobalFinalize", 0, 109), ("MemoryGlobalFinalize", 69, 110), ("Global", 4, 3),
+                           ("SyscallCore", 3, 4), ("SyscallCore", 6, 7), ("SyscallCore", 30, 9)):       # an argument half-word, a result half-word, is_linux of a padding row
+        if name not in rows:
+            continue
         bad = rows[name].copy()
         bad[row, col] = (int(bad[row, col]) + 1) % P
         p2, _ = om.prove_shard({**case.traces, name: bad}, case.public_values)
@@ -339,7 +351,8 @@ def test_memory_and_global_tables_prove_from_event_records(gpu, oracle, first_sh
     neighbour's address folded in, the global lookups they emit): rows, permutation traces of the lookup between them,
     quotients of the restated AIRs - the proof is the oracle's, word for word."""
     from ziren_b200.prover import B200Prover, EventTrace
-    case, _, events = _memory_shard(oracle, first_shard, n_init=900, n_fin=2000, log_init=10, log_fin=11, seed=5)
+    case, _, events = _memory_shard(oracle, first_shard, n_init=900, n_fin=2000, log_init=10, log_fin=11, seed=5,
+                                    n_syscalls=0 if first_shard else 300)
     om = oracle.OracleMachine(case.machine)
     om.setup({})
     want, _ = om.prove_shard(case.traces, case.public_values)

@@ -22,7 +22,8 @@ def machines():
     # the real Global chip (synthetic.py _global_chip: septic-extension constraints of degree three)
     yield "global", synthetic.global_case(np.zeros((16, 99), np.uint32)).machine
     yield "memory-global", synthetic.memory_global_case(np.zeros((16, 111), np.uint32), np.zeros((16, 111), np.uint32),
-                                                        np.zeros((16, 99), np.uint32), 0, 0).machine
+                                                        np.zeros((16, 99), np.uint32), 0, 0,
+                                                        syscall_rows=np.zeros((16, 11), np.uint32)).machine
     # the real KeccakSponge chip (ziren_b200/keccak_air.py: 3788 constraints, 357 lookups): minutes of NVRTC time once
     from . import keccak_sponge
     yield "keccak-real", synthetic.keccak_real_case(keccak_sponge.synthetic_blocks(1, 1), None, log_cpu=10).machine

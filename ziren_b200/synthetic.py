@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import field as kb
-from .air import (KIND_BYTE, KIND_GLOBAL, KIND_MEMORY, KIND_PROGRAM, SCOPE_GLOBAL, Chip, Machine)
+from .air import (KIND_BYTE, KIND_GLOBAL, KIND_MEMORY, KIND_PROGRAM, KIND_SYSCALL, KIND_SYSCALL_RESULT, SCOPE_GLOBAL, Chip, Machine)
 
 P = kb.P
 RANGE_BITS = 16  # the reference's Byte table has 2^16 rows
@@ -953,8 +953,27 @@ def _memory_global_chip(finalize: bool, pv_prev: int, pv_last: int) -> Chip:
     return Chip("MemoryGlobalFinalize" if finalize else "MemoryGlobalInit", 0, 111, ev)
 
 
+def _syscall_chip(precompile: bool) -> Chip:
+    """SyscallChip::eval crates/core/machine/src/syscall/chip.rs:304-497; columns of SyscallCols (chip.rs:71-107).  The two
+    cross-shard lookups every real row sends to the Global table - (shard, clk, syscall_id, arg half-words) of kind Syscall and
+    (shard, clk, syscall_id, result half-words, 0, 0) of kind SyscallResult, as a send in a core shard and as a receive in a
+    precompile shard - are stated; left out: the four U16Range byte lookups and the syscall / syscall-result lookups with the
+    SyscallInstrs table or the precompile tables (their other ends are tables this machine does not have)."""
+    def ev(b):
+        shard, clk, syscall_id, a1_lo, a1_hi, a2_lo, a2_hi, r_lo, r_hi, is_linux, is_real = (b.main(i) for i in range(11))
+        _assert_bool(b, is_real)
+        _assert_bool(b, is_linux)
+        b.when(1 - is_real).assert_zero(is_linux)
+        b.when(1 - is_linux).assert_zero(r_lo)
+        b.when(1 - is_linux).assert_zero(r_hi)
+        is_send, is_receive = (is_real * 0, is_real * 1) if precompile else (is_real * 1, is_real * 0)
+        b.send(KIND_GLOBAL, [shard, clk, syscall_id, a1_lo, a1_hi, a2_lo, a2_hi, is_send, is_receive, KIND_SYSCALL], is_real)
+        b.send(KIND_GLOBAL, [shard, clk, syscall_id, r_lo, r_hi, 0, 0, is_send, is_receive, KIND_SYSCALL_RESULT], is_real)
+    return Chip("SyscallPrecompile" if precompile else "SyscallCore", 0, 11, ev)
+
+
 def memory_global_case(init_rows: np.ndarray, finalize_rows: np.ndarray, global_rows: np.ndarray, previous_init_addr: int,
-                       previous_finalize_addr: int, **kw) -> ShardCase:
+                       previous_finalize_addr: int, syscall_rows: np.ndarray | None = None, **kw) -> ShardCase:
     """A shard of the three tables that carry memory across shards, under their restated constraints AND the lookup that ties
     them: MemoryGlobalInit / MemoryGlobalFinalize send (shard, timestamp, addr, value bytes, is_send, is_receive, Memory) for
     every real row, Global receives its messages.  Public values: the bits of previous_init_addr, last_init_addr,
@@ -965,8 +984,12 @@ def memory_global_case(init_rows: np.ndarray, finalize_rows: np.ndarray, global_
     pv = np.zeros(128, dtype=np.uint32)
     for k, a in enumerate((previous_init_addr, last_addr(init_rows), previous_finalize_addr, last_addr(finalize_rows))):
         pv[32 * k: 32 * k + 32] = [(a >> i) & 1 for i in range(32)]
-    machine = Machine([_memory_global_chip(False, 0, 32), _memory_global_chip(True, 64, 96), _global_chip(with_receive=True)],
-                      num_pv_elts=128, num_queries=kw.get("num_queries", 8), pow_bits=kw.get("pow_bits", 4),
+    chips = [_memory_global_chip(False, 0, 32), _memory_global_chip(True, 64, 96), _global_chip(with_receive=True)]
+    if syscall_rows is not None:            # a core shard's syscall table: two more global lookups per row
+        chips.append(_syscall_chip(False))
+    machine = Machine(chips, num_pv_elts=128, num_queries=kw.get("num_queries", 8), pow_bits=kw.get("pow_bits", 4),
                       log_blowup=kw.get("log_blowup", 1))
     traces = {"MemoryGlobalInit": init_rows, "MemoryGlobalFinalize": finalize_rows, "Global": global_rows}
+    if syscall_rows is not None:
+        traces["SyscallCore"] = syscall_rows
     return ShardCase(machine, {}, traces, pv, int(global_rows.shape[0]))

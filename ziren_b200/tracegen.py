@@ -715,3 +715,24 @@ def memory_global_lookup_events(events: np.ndarray, finalize: bool) -> np.ndarra
         out[:, 3 + k] = (ev[:, 1] >> np.uint32(8 * k)) & np.uint32(0xFF)
     out[:, 7] = np.uint32(int(finalize)) | np.uint32(1 << 8)
     return out
+
+
+def syscall_global_lookup_events(events: np.ndarray, precompile: bool = False) -> np.ndarray:
+    """SyscallChip::generate_dependencies (crates/core/machine/src/syscall/chip.rs:119-172): two GlobalLookupEvents (2n, 8) per
+    SyscallEvent record of the table - {shard, clk, syscall_id, arg1 half-words, arg2 half-words} of kind Syscall = 6 and {shard,
+    clk, syscall_id, result half-words, 0, 0} of kind SyscallResult = 8, the result only for the linux calls - sent by a core
+    shard, received by a precompile shard."""
+    ev = np.ascontiguousarray(events, dtype=np.uint32).reshape(-1, SYSCALL_EVENT_WORDS)
+    n = len(ev)
+    out = np.zeros((2 * n, GLOBAL_EVENT_WORDS), np.uint32)
+    prev_value, value = ev[:, 7], ev[:, 4]
+    linux = (prev_value == 1) if precompile else (((prev_value >> 8) & 0xFF) != 0)
+    result = np.where(linux, value, 0).astype(np.uint32)
+    for k in (0, 1):
+        out[k::2, 0], out[k::2, 1], out[k::2, 2] = ev[:, 2], ev[:, 3], ev[:, 11]
+    out[0::2, 3], out[0::2, 4] = ev[:, 12] & 0xFFFF, ev[:, 12] >> 16
+    out[0::2, 5], out[0::2, 6] = ev[:, 13] & 0xFFFF, ev[:, 13] >> 16
+    out[1::2, 3], out[1::2, 4] = result & 0xFFFF, result >> 16
+    out[0::2, 7] = np.uint32(int(precompile)) | np.uint32(6 << 8)
+    out[1::2, 7] = np.uint32(int(precompile)) | np.uint32(8 << 8)
+    return out
