@@ -142,6 +142,41 @@ def test_div_rem_rows_hold_the_executor_semantics(oracle):
     assert (t[:n, 91:106][~is_div] == 0).all() and np.array_equal(word(95)[is_div], hi[is_div])
 
 
+def test_div_rem_rows_satisfy_the_restated_air_where_the_cpp_twin_does_not(oracle):
+    """DivRemChip::eval restated as data (ziren_b200/synthetic.py _div_rem_chip): rows from trace generation - divisions by zero
+    and INT_MIN / -1 among them, the rows the reference's C++ twin cannot pin - are accepted by the restated prover and verifier;
+    single-cell corruptions are rejected, and so is what div_rem.hpp writes for c = 0 (quotient INT32_MAX, abs_c = 1): the Rust
+    generate_trace is the one the constraints accept."""
+    from ziren_b200 import synthetic
+    ev = tg.synthetic_div_rem_events(500, seed=3)
+    rows = oracle.chip_trace("DivRem", ev, 512)
+    b, c = ev[:, 7], ev[:, 8]
+    assert (c == 0).sum() >= 10 and ((b == 0x80000000) & (c == 0xFFFFFFFF)).sum() >= 3
+    case = synthetic.chips_case({"DivRem": rows})
+    chip = case.machine.chip("DivRem")
+    assert chip.log_quotient_degree == 1 and chip.num_constraints == 120
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    proof, _ = om.prove_shard(case.traces, case.public_values)
+    ok, err = om.verify_shard(proof)
+    assert ok, err
+    zero = int(np.argmax(c == 0))
+    ovf = int(np.argmax((b == 0x80000000) & (c == 0xFFFFFFFF) & ((ev[:, 4] == 5) | (ev[:, 4] == 7))))
+    for row, col in ((zero, 10), (zero, 26), (4, 14), (7, 38), (ovf, 61), (20, 90), (500, 57)):
+        bad = rows.copy()
+        bad[row, col] = (int(bad[row, col]) + 1) % kb.P
+        p2, _ = om.prove_shard({**case.traces, "DivRem": bad}, case.public_values)
+        assert not om.verify_shard(p2)[0], (row, col)
+    twin = rows.copy()
+    twin[zero, 10:14] = [0xFF, 0xFF, 0xFF, 0x7F]          # INT32_MAX as the quotient of a division by zero
+    p2, _ = om.prove_shard({**case.traces, "DivRem": twin}, case.public_values)
+    assert not om.verify_shard(p2)[0]
+    twin = rows.copy()
+    twin[zero, 22] = 1                                     # abs_c = max(1, |c|)
+    p2, _ = om.prove_shard({**case.traces, "DivRem": twin}, case.public_values)
+    assert not om.verify_shard(p2)[0]
+
+
 def test_syscall_rows_hold_the_chip_semantics(oracle):
     n = 4000
     ev = tg.synthetic_syscall_events(n, seed=6, kind="instrs")
@@ -279,3 +314,32 @@ def test_gpu_trace_matches_oracle(gpu, oracle, chip, n, log_h, col_major, on_dev
         out2 = torch.zeros((128 * w,), dtype=torch.int32, device="cuda")
         prover.generate_alu_trace(chip, gev, 7, out2)
         assert np.array_equal(out2.cpu().numpy().view(np.uint32).reshape(128, w)[: len(gev)], grows)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["events_host", "events_device"])
+def test_div_rem_shard_proves_from_event_records(gpu, oracle, mode):
+    """The DivRem table under its restated constraints, handed to zkb200_commit as CompAluEvent records: the proof is the
+    oracle's proof over the oracle's rows, word for word."""
+    from ziren_b200 import synthetic
+    from ziren_b200.prover import B200Prover, EventTrace
+    torch, _ = gpu
+    ev = tg.synthetic_div_rem_events(3000, seed=33)
+    log_h = tg.padded_log_height(len(ev))
+    case = synthetic.chips_case({"DivRem": oracle.chip_trace("DivRem", ev, 1 << log_h)})
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    want, _ = om.prove_shard(case.traces, case.public_values)
+    prover = B200Prover(case.machine, device=0)
+    try:
+        pk = prover.setup({})
+        inputs = {k: kb.to_monty(v) for k, v in case.traces.items() if k != "DivRem"}
+        d = torch.from_numpy(ev.view(np.int32)).cuda() if mode == "events_device" else ev
+        inputs["DivRem"] = EventTrace(d, log_h, tg.width("DivRem"))
+        got, _ = prover.prove_shard(pk, inputs, case.public_values)
+        ok, err = om.verify_shard(got)
+        assert ok, err
+        assert np.array_equal(got, want)
+        pk.free()
+    finally:
+        prover.close()

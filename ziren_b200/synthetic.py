@@ -993,3 +993,98 @@ def memory_global_case(init_rows: np.ndarray, finalize_rows: np.ndarray, global_
     if syscall_rows is not None:
         traces["SyscallCore"] = syscall_rows
     return ShardCase(machine, {}, traces, pv, int(global_rows.shape[0]))
+
+
+def _eval_is_zero_word(b, a, cols, is_real):
+    """IsZeroWordOperation::eval (crates/core/machine/src/operations/is_zero_word.rs:49-82) over four expressions `a`; cols = the
+    operation's eleven columns {is_zero_byte[4]{inverse, result}, is_lower_half_zero, is_upper_half_zero, result}."""
+    on = b.when(is_real)
+    for i in range(4):
+        inverse, result = cols[2 * i], cols[2 * i + 1]
+        on.assert_eq(1 - inverse * a[i], result)               # IsZeroOperation::eval, is_zero.rs:42-71
+        on.assert_zero(result * (result - 1))
+        on.when(result).assert_zero(a[i])
+    _assert_bool(b, is_real)
+    lower, upper, result = cols[8], cols[9], cols[10]
+    for x in (lower, upper, result):
+        on.assert_zero(x * (x - 1))
+    on.assert_eq(lower, cols[1] * cols[3])
+    on.assert_eq(upper, cols[5] * cols[7])
+    on.assert_eq(result, lower * upper)
+
+
+def _div_rem_chip() -> Chip:
+    """DivRemChip::eval crates/core/machine/src/alu/divrem/mod.rs:390-795; columns of DivRemCols (mod.rs:109-204).  Left out (lookups
+    whose other ends are other tables): the MULT / MULTU send for c * quotient, the ADD sends for the absolute values, the SLTU
+    send for |remainder| < max(|c|, 1), the MSB and range byte lookups, the instruction receives and the HI register's memory
+    access."""
+    def ev(b):
+        word = lambda c0: [b.main(c0 + i) for i in range(4)]
+        bb, c, quotient, remainder, abs_remainder, abs_c, max_abs_c_or_1 = (word(2 + 4 * k) for k in range(7))
+        ctq = [b.main(30 + i) for i in range(8)]
+        carry = [b.main(38 + i) for i in range(8)]
+        is_c_0 = [b.main(46 + i) for i in range(11)]
+        is_div, is_divu, is_mod, is_modu, is_overflow = (b.main(57 + i) for i in range(5))
+        ovf_b = [b.main(62 + i) for i in range(11)]
+        ovf_c = [b.main(73 + i) for i in range(11)]
+        b_msb, rem_msb, c_msb, b_neg, rem_neg, c_neg, multiplicity = (b.main(84 + i) for i in range(7))
+        hi_value = word(95)                                     # op_hi_access.value(): prev_value[4], then the access columns' value
+        is_real = is_div + is_divu + is_mod + is_modu
+        signed = is_div + is_mod
+        for msb, neg in ((b_msb, b_neg), (rem_msb, rem_neg), (c_msb, c_neg)):
+            b.assert_eq(msb * signed, neg)
+        int_min, minus_one = [0, 0, 0, 0x80], [0xFF] * 4
+        _eval_is_zero_word(b, [bb[i] - int_min[i] for i in range(4)], ovf_b, is_real)
+        _eval_is_zero_word(b, [c[i] - minus_one[i] for i in range(4)], ovf_c, is_real)
+        b.assert_eq(is_overflow, ovf_b[10] * ovf_c[10] * signed)
+        # c * quotient + remainder = b, byte by byte with carries, the remainder sign-extended
+        total = []
+        for i in range(8):
+            t = ctq[i] + (remainder[i] if i < 4 else rem_neg * 255) - carry[i] * 256
+            total.append(t + carry[i - 1] if i else t)
+        for i in range(4):
+            b.assert_eq(bb[i], total[i])
+        for i in range(4, 8):
+            b.when(1 - is_overflow).when(b_neg).assert_eq(total[i], 255)
+            b.when(1 - is_overflow).when(1 - b_neg).assert_zero(total[i])
+            b.when(is_overflow).assert_zero(total[i])
+        rem_sum = remainder[0] + remainder[1] + remainder[2] + remainder[3]
+        b.when(rem_neg).assert_eq(b_neg, 1)
+        b.when(rem_sum).when(1 - rem_neg).assert_zero(b_neg)
+        _eval_is_zero_word(b, c, is_c_0, is_real)
+        for i in range(4):
+            b.when(is_c_0[10]).assert_eq(quotient[i], 255)
+            b.when(1 - c_neg).assert_eq(c[i], abs_c[i])
+            b.when(1 - rem_neg).assert_eq(remainder[i], abs_remainder[i])
+        b.when(is_real).assert_eq(max_abs_c_or_1[0], is_c_0[10] + (1 - is_c_0[10]) * abs_c[0])
+        for i in range(1, 4):
+            b.when(is_real).assert_eq(max_abs_c_or_1[i], (1 - is_c_0[10]) * abs_c[i])
+        b.assert_eq((1 - is_c_0[10]) * is_real, multiplicity)
+        for x in carry:
+            _assert_bool(b, x)
+        for x in (is_div, is_divu, is_mod, is_modu, is_overflow, b_msb, rem_msb, c_msb, b_neg, rem_neg, c_neg):
+            _assert_bool(b, x)
+        b.when(is_real).assert_eq(is_divu + is_div + is_mod + is_modu, 1)
+        for i in range(4):
+            b.when(is_div + is_divu).assert_eq(remainder[i], hi_value[i])
+    return Chip("DivRem", 0, 106, ev, local_only=True)
+
+
+def chips_case(traces: dict, **kw) -> ShardCase:
+    """Tables of the chips whose Air::eval is restated here one by one ({"DivRem": rows, ...}, canonical rows from trace
+    generation) next to the Fibonacci / Sink pair, so that the shard also has permutation traces."""
+    makers = {"DivRem": _div_rem_chip}
+    n = 1 << 5
+    a, b_ = 0, 1
+    rows = np.empty((n, 2), dtype=np.uint32)
+    for i in range(n):
+        rows[i] = (a, b_)
+        a, b_ = b_, (a + b_) % P
+    pv = np.zeros(8, dtype=np.uint32)
+    pv[1], pv[2], pv[3] = 0, 1, rows[-1, 1]
+    sink = np.zeros((n, 3), dtype=np.uint32)
+    sink[:, :2] = rows[::-1]
+    sink[:, 2] = 1
+    machine = Machine([makers[k]() for k in traces] + [_fib_chip(), _sink_chip()], num_pv_elts=4, num_queries=kw.get("num_queries", 8),
+                      pow_bits=kw.get("pow_bits", 4), log_blowup=kw.get("log_blowup", 1))
+    return ShardCase(machine, {}, {**traces, "Fibonacci": rows, "Sink": sink}, pv, sum(int(v.shape[0]) for v in traces.values()))
