@@ -287,6 +287,33 @@ def test_memory_tables_and_global_table_satisfy_their_airs_and_the_lookup_betwee
         assert not om.verify_shard(p2)[0], (name, row, col)
 
 
+def _precompile_shard(oracle, n, seed=3):
+    from ziren_b200 import synthetic
+    ev = tg.synthetic_syscall_events(n, seed=seed, kind="precompile")
+    gev = tg.syscall_global_lookup_events(ev, precompile=True)
+    log_s, log_g = tg.padded_log_height(n), tg.padded_log_height(len(gev))
+    rows = {"SyscallPrecompile": oracle.chip_trace("SyscallPrecompile", ev, 1 << log_s), "Global": oracle.global_trace(gev, 1 << log_g)}
+    case = synthetic.syscall_precompile_case(rows["SyscallPrecompile"], rows["Global"])
+    return case, rows, {"SyscallPrecompile": (ev, log_s), "Global": (gev, log_g)}
+
+
+def test_precompile_shard_tables_satisfy_their_airs_and_the_lookup_between_them(oracle):
+    """SyscallPrecompile (one SyscallEvent per precompile event, linux results carried in a_record) and the Global table of the
+    lookups it emits - received here, sent by the core shard - under the restated constraints and the real lookup."""
+    case, rows, _ = _precompile_shard(oracle, 40)
+    assert (rows["SyscallPrecompile"][:40, 9] == 1).any() and (rows["Global"][:80, 61] == 1).all()
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    proof, _ = om.prove_shard(case.traces, case.public_values)
+    ok, err = om.verify_shard(proof)
+    assert ok, err
+    for name, row, col in (("SyscallPrecompile", 3, 5), ("SyscallPrecompile", 2, 2), ("Global", 7, 61), ("Global", 9, 7)):
+        bad = rows[name].copy()
+        bad[row, col] = (int(bad[row, col]) + 1) % P
+        p2, _ = om.prove_shard({**case.traces, name: bad}, case.public_values)
+        assert not om.verify_shard(p2)[0], (name, row, col)
+
+
 @pytest.fixture(scope="module")
 def gpu():
     import torch
@@ -353,6 +380,26 @@ def test_memory_and_global_tables_prove_from_event_records(gpu, oracle, first_sh
     from ziren_b200.prover import B200Prover, EventTrace
     case, _, events = _memory_shard(oracle, first_shard, n_init=900, n_fin=2000, log_init=10, log_fin=11, seed=5,
                                     n_syscalls=0 if first_shard else 300)
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    want, _ = om.prove_shard(case.traces, case.public_values)
+    prover = B200Prover(case.machine, device=0)
+    try:
+        pk = prover.setup({})
+        inputs = {name: EventTrace(ev, log_h, tg.width(name)) for name, (ev, log_h) in events.items()}
+        got, _ = prover.prove_shard(pk, inputs, case.public_values)
+        ok, err = om.verify_shard(got)
+        assert ok, err
+        assert np.array_equal(got, want)
+        pk.free()
+    finally:
+        prover.close()
+
+
+@pytest.mark.gpu
+def test_precompile_shard_tables_prove_from_event_records(gpu, oracle):
+    from ziren_b200.prover import B200Prover, EventTrace
+    case, _, events = _precompile_shard(oracle, 700, seed=8)
     om = oracle.OracleMachine(case.machine)
     om.setup({})
     want, _ = om.prove_shard(case.traces, case.public_values)

@@ -22,6 +22,7 @@ def machines():
     # the real Global chip (synthetic.py _global_chip: septic-extension constraints of degree three)
     yield "global", synthetic.global_case(np.zeros((16, 99), np.uint32)).machine
     yield "div-rem", synthetic.chips_case({"DivRem": np.zeros((16, 106), np.uint32)}).machine
+    yield "syscall-precompile", synthetic.syscall_precompile_case(np.zeros((16, 11), np.uint32), np.zeros((16, 99), np.uint32)).machine
     yield "memory-global", synthetic.memory_global_case(np.zeros((16, 111), np.uint32), np.zeros((16, 111), np.uint32),
                                                         np.zeros((16, 99), np.uint32), 0, 0,
                                                         syscall_rows=np.zeros((16, 11), np.uint32)).machine

@@ -1088,3 +1088,12 @@ def chips_case(traces: dict, **kw) -> ShardCase:
     machine = Machine([makers[k]() for k in traces] + [_fib_chip(), _sink_chip()], num_pv_elts=4, num_queries=kw.get("num_queries", 8),
                       pow_bits=kw.get("pow_bits", 4), log_blowup=kw.get("log_blowup", 1))
     return ShardCase(machine, {}, {**traces, "Fibonacci": rows, "Sink": sink}, pv, sum(int(v.shape[0]) for v in traces.values()))
+
+
+def syscall_precompile_case(syscall_rows: np.ndarray, global_rows: np.ndarray, **kw) -> ShardCase:
+    """A precompile shard's cross-shard tables: SyscallPrecompile (SyscallChip::eval with shard_kind Precompile: its two global
+    lookups per row are RECEIVES) and Global, tied by the real lookup."""
+    machine = Machine([_syscall_chip(True), _global_chip(with_receive=True)], num_pv_elts=4, num_queries=kw.get("num_queries", 8),
+                      pow_bits=kw.get("pow_bits", 4), log_blowup=kw.get("log_blowup", 1))
+    return ShardCase(machine, {}, {"SyscallPrecompile": syscall_rows, "Global": global_rows}, np.zeros(8, dtype=np.uint32),
+                     int(global_rows.shape[0]))
