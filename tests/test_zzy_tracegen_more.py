@@ -177,6 +177,38 @@ def test_div_rem_rows_satisfy_the_restated_air_where_the_cpp_twin_does_not(oracl
     assert not om.verify_shard(p2)[0]
 
 
+def test_syscall_instrs_rows_satisfy_the_restated_air(oracle):
+    """SyscallInstrsChip::eval restated as data (ziren_b200/synthetic.py _syscall_instrs_chip: 109 constraints - the six id tests,
+    the linux / send-to-table flags, both KoalaBear range checks, the COMMIT digest words and the HALT exit code against the
+    public values): rows from well-formed events are accepted, single-cell corruptions and a wrong exit code rejected."""
+    from ziren_b200 import synthetic
+    ev = tg.synthetic_syscall_events(400, seed=4, kind="instrs")
+    rows = oracle.chip_trace("SyscallInstrs", ev, 512)
+    digest, deferred, exit_code = tg.syscall_public_values(4)
+    case = synthetic.syscall_instrs_case(rows, digest, deferred, exit_code)
+    assert case.machine.chip("SyscallInstrs").num_constraints == 109
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    proof, _ = om.prove_shard(case.traces, case.public_values)
+    ok, err = om.verify_shard(proof)
+    assert ok, err
+    sid = ev[:, 7] & 0xFFFF
+    halt, commit, deferred_row, enter = (int(np.argmax(sid == v)) for v in (0, 0x10, 0x1A, 0x03))
+    send = int(np.argmax(((ev[:, 7] >> 16) & 0xFF) == 1))
+    # is_halt, next_pc of a halt, the digest word of a COMMIT, the bitmap, the deferred digest, syscall_id of ENTER_UNCONSTRAINED,
+    # a range-check bit of a row sent to the table, num_extra_cycles, is_real of a padding row
+    for row, col in ((halt, 5), (halt, 1), (commit, 19), (commit, 40), (deferred_row, 18), (enter, 9), (send, 47), (send, 4), (450, 76)):
+        bad = rows.copy()
+        bad[row, col] = (int(bad[row, col]) + 1) % kb.P
+        p2, _ = om.prove_shard({"SyscallInstrs": bad}, case.public_values)
+        assert not om.verify_shard(p2)[0], (row, col)
+    wrong = synthetic.syscall_instrs_case(rows, digest, deferred, exit_code + 1)
+    om2 = oracle.OracleMachine(wrong.machine)
+    om2.setup({})
+    p2, _ = om2.prove_shard(wrong.traces, wrong.public_values)
+    assert not om2.verify_shard(p2)[0]
+
+
 def test_syscall_rows_hold_the_chip_semantics(oracle):
     n = 4000
     ev = tg.synthetic_syscall_events(n, seed=6, kind="instrs")
@@ -337,6 +369,30 @@ def test_div_rem_shard_proves_from_event_records(gpu, oracle, mode):
         d = torch.from_numpy(ev.view(np.int32)).cuda() if mode == "events_device" else ev
         inputs["DivRem"] = EventTrace(d, log_h, tg.width("DivRem"))
         got, _ = prover.prove_shard(pk, inputs, case.public_values)
+        ok, err = om.verify_shard(got)
+        assert ok, err
+        assert np.array_equal(got, want)
+        pk.free()
+    finally:
+        prover.close()
+
+
+@pytest.mark.gpu
+def test_syscall_instrs_shard_proves_from_event_records(gpu, oracle):
+    """The SyscallInstrs table under its restated constraints (public values: digests and exit code), handed to zkb200_commit as
+    the record's SyscallEvent vector."""
+    from ziren_b200 import synthetic
+    from ziren_b200.prover import B200Prover, EventTrace
+    ev = tg.synthetic_syscall_events(1800, seed=6, kind="instrs")
+    log_h = tg.padded_log_height(len(ev))
+    case = synthetic.syscall_instrs_case(oracle.chip_trace("SyscallInstrs", ev, 1 << log_h), *tg.syscall_public_values(6))
+    om = oracle.OracleMachine(case.machine)
+    om.setup({})
+    want, _ = om.prove_shard(case.traces, case.public_values)
+    prover = B200Prover(case.machine, device=0)
+    try:
+        pk = prover.setup({})
+        got, _ = prover.prove_shard(pk, {"SyscallInstrs": EventTrace(ev, log_h, tg.width("SyscallInstrs"))}, case.public_values)
         ok, err = om.verify_shard(got)
         assert ok, err
         assert np.array_equal(got, want)

@@ -23,6 +23,7 @@ def machines():
     yield "global", synthetic.global_case(np.zeros((16, 99), np.uint32)).machine
     yield "div-rem", synthetic.chips_case({"DivRem": np.zeros((16, 106), np.uint32)}).machine
     yield "syscall-precompile", synthetic.syscall_precompile_case(np.zeros((16, 11), np.uint32), np.zeros((16, 99), np.uint32)).machine
+    yield "syscall-instrs", synthetic.syscall_instrs_case(np.zeros((16, 77), np.uint32), np.zeros(8, np.uint32), np.zeros(8, np.uint32), 0).machine
     yield "memory-global", synthetic.memory_global_case(np.zeros((16, 111), np.uint32), np.zeros((16, 111), np.uint32),
                                                         np.zeros((16, 99), np.uint32), 0, 0,
                                                         syscall_rows=np.zeros((16, 11), np.uint32)).machine

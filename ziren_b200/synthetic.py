@@ -1097,3 +1097,95 @@ def syscall_precompile_case(syscall_rows: np.ndarray, global_rows: np.ndarray, *
                       pow_bits=kw.get("pow_bits", 4), log_blowup=kw.get("log_blowup", 1))
     return ShardCase(machine, {}, {"SyscallPrecompile": syscall_rows, "Global": global_rows}, np.zeros(8, dtype=np.uint32),
                      int(global_rows.shape[0]))
+
+
+def _syscall_instrs_chip() -> Chip:
+    """SyscallInstrsChip::eval crates/core/machine/src/syscall/instructions/air.rs:28-446; columns of SyscallInstrColumns
+    (columns.rs:11-59).  Public values as this machine lays them out: [0, 32) committed_value_digest (eight words as bytes),
+    [32, 40) deferred_proofs_digest, 40 exit_code.  Left out (lookups whose other ends are other tables): the instruction receive
+    from the Cpu table, the syscall / syscall-result sends to SyscallCore and SysLinux."""
+    def ev(b):
+        pc, next_pc, shard, clk, num_extra_cycles, is_halt, is_sys_linux = (b.main(i) for i in range(7))
+        a1_zero = (b.main(7), b.main(8))
+        syscall_id_col = b.main(9)
+        word = lambda c0: [b.main(c0 + i) for i in range(4)]
+        op_a, op_b, op_c, prev_a = word(10), word(14), word(18), word(22)
+        iz = lambda c0: (b.main(c0), b.main(c0 + 1))
+        is_enter, is_hint, halt_chk, exit_chk, is_commit, is_deferred = (iz(26 + 2 * k) for k in range(6))
+        bitmap = [b.main(38 + i) for i in range(8)]
+        b_rc, c_rc = [b.main(46 + i) for i in range(14)], [b.main(60 + i) for i in range(14)]
+        b_check, c_check, is_real = b.main(74), b.main(75), b.main(76)
+        digest = [[b.pub(4 * w + k) for k in range(4)] for w in range(8)]
+        deferred = [b.pub(32 + i) for i in range(8)]
+        exit_code = b.pub(40)
+        real = b.when(is_real)
+        reduce = lambda w: w[0] + w[1] * 256 + w[2] * 65536 + w[3] * (1 << 24)
+
+        def is_zero(a, cols):                                   # IsZeroOperation::eval(a, cols, is_real), is_zero.rs:42-71
+            inverse, result = cols
+            real.assert_eq(1 - inverse * a, result)
+            real.assert_zero(result * (result - 1))
+            real.when(result).assert_zero(a)
+            return result
+
+        _assert_bool(b, is_real)
+        sid = prev_a[0] + prev_a[1] * 256
+        # eval_is_halt_syscall
+        halt, exit_group = is_zero(sid - 0x00, halt_chk), is_zero(sid - 4246, exit_chk)
+        b.assert_eq(is_halt, (halt + exit_group) * is_real)
+        b.assert_eq(num_extra_cycles, prev_a[3] * is_real)
+        # eval_syscall
+        send_to_table = is_sys_linux + prev_a[2]
+        _assert_bool(b, prev_a[2])
+        _assert_bool(b, is_sys_linux)
+        _assert_bool(b, send_to_table)
+        real.assert_eq(is_sys_linux, 1 - is_zero(prev_a[1], a1_zero))
+        b.when(1 - is_real).assert_zero(send_to_table)
+        _assert_bool(b, b_check)
+        _assert_bool(b, c_check)
+        b.when(send_to_table).assert_eq(b_check, 1)
+        b.when(is_halt).assert_eq(b_check, 1)
+        b.when(send_to_table).assert_eq(c_check, 1)
+        b.when(is_deferred[1]).assert_eq(c_check, 1)
+        b.when(1 - is_real).assert_zero(b_check)
+        b.when(1 - is_real).assert_zero(c_check)
+        _range_check_word(b, op_b, b_rc, b_check)
+        _range_check_word(b, op_c, c_rc, c_check)
+        enter = is_zero(sid - 0x03, is_enter)
+        real.when(1 - enter).assert_eq(syscall_id_col, sid)
+        real.when(enter).assert_eq(syscall_id_col, 0x04)          # EXIT_UNCONSTRAINED
+        hint = is_zero(sid - 0xF0, is_hint)
+        for i in range(4):
+            real.when(enter).assert_zero(op_a[i])
+            real.when(1 - (enter + hint + is_sys_linux)).assert_eq(op_a[i], prev_a[i])
+        # eval_commit
+        commit, commit_deferred = is_zero(sid - 0x10, is_commit), is_zero(sid - 0x1A, is_deferred)
+        for bit in bitmap:
+            real.assert_zero(bit * (bit - 1))
+        bitmap_sum = sum(bitmap[1:], bitmap[0])
+        real.when(commit + commit_deferred).assert_eq(bitmap_sum, 1)
+        real.when(1 - (commit + commit_deferred)).assert_zero(bitmap_sum)
+        for i, bit in enumerate(bitmap):
+            real.when(bit).assert_eq(op_b[0], i)
+        for i in range(1, 4):
+            real.when(commit + commit_deferred).assert_zero(op_b[i])
+        for k in range(4):
+            real.when(commit).assert_eq(sum((bitmap[w] * digest[w][k] for w in range(1, 8)), bitmap[0] * digest[0][k]), op_c[k])
+        real.when(commit_deferred).assert_eq(sum((bitmap[w] * deferred[w] for w in range(1, 8)), bitmap[0] * deferred[0]), reduce(op_c))
+        # eval_halt_unimpl
+        b.when(is_halt).assert_zero(next_pc)
+        b.when(is_halt).assert_eq(reduce(op_b), exit_code)
+    return Chip("SyscallInstrs", 0, 77, ev, local_only=True)
+
+
+def syscall_instrs_case(rows: np.ndarray, digest: np.ndarray, deferred: np.ndarray, exit_code: int, **kw) -> ShardCase:
+    """The SyscallInstrs table under its restated constraints, with the public values its COMMIT / COMMIT_DEFERRED_PROOFS / HALT
+    rows are checked against."""
+    pv = np.zeros(48, dtype=np.uint32)
+    for w in range(8):
+        pv[4 * w: 4 * w + 4] = [(int(digest[w]) >> (8 * k)) & 0xFF for k in range(4)]
+    pv[32:40] = deferred
+    pv[40] = exit_code
+    machine = Machine([_syscall_instrs_chip()], num_pv_elts=41, num_queries=kw.get("num_queries", 8), pow_bits=kw.get("pow_bits", 4),
+                      log_blowup=kw.get("log_blowup", 1))
+    return ShardCase(machine, {}, {"SyscallInstrs": rows}, pv, int(rows.shape[0]))

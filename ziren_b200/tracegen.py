@@ -577,46 +577,67 @@ def synthetic_div_rem_events(n: int, seed: int = 0, shard: int = 3, edges: bool 
     return ev
 
 
-# SyscallCode values (crates/core/executor/src/syscalls/code.rs): byte 0-1 the id, byte 1 != 0 for the linux calls, byte 2 = 1
-# "send to table" (precompiles), byte 3 the extra cycles
-_SYSCALL_TABLE = np.array([0x00000000, 0x00000002, 0x00000003, 0x00000004, 0x00000010, 0x0000001A, 0x000000F0, 0x000000F1, 4246,
-                           4003, 4004, 4045, 4090, 0x00010005, 0x01010109, 0x00300130, 0x0101010A, 0x0001011C, 0x0001011E], np.uint32)
+# SyscallCode values (crates/core/executor/src/syscalls/code.rs:28-160): bytes 0-1 the id (byte 1 != 0 for the linux calls), byte 2
+# "send to table" (1 for the precompiles), byte 3 the extra cycles: HALT, WRITE, ENTER_UNCONSTRAINED, EXIT_UNCONSTRAINED,
+# COMMIT, COMMIT_DEFERRED_PROOFS, VERIFY_ZKM_PROOF, SYSHINTLEN, SYSHINTREAD, SYS_EXT_GROUP, SYS_READ, SYS_WRITE, SYS_BRK,
+# SYS_MMAP2, SHA_EXTEND, SHA_COMPRESS, ED_DECOMPRESS, KECCAK_SPONGE, BLS12381_DECOMPRESS, UINT256_MUL
+_SYSCALL_TABLE = np.array([0x00000000, 0x00000002, 0x00000003, 0x00000004, 0x00000010, 0x0000001A, 0x0000001B, 0x000000F0, 0x000000F1, 4246,
+                           4003, 4004, 4045, 4090, 0x30010005, 0x01010006, 0x00010008, 0x01010009, 0x0001001C, 0x0101001D], np.uint32)
+
+
+def syscall_public_values(seed: int = 0):
+    """The public values SyscallInstrs' COMMIT / COMMIT_DEFERRED_PROOFS / HALT rows are checked against
+    (crates/core/machine/src/syscall/instructions/air.rs:274-358): committed_value_digest (8 words), deferred_proofs_digest (8 field
+    elements), exit_code."""
+    rng = np.random.default_rng(0x9B + seed)
+    return (rng.integers(0, 1 << 32, 8, dtype=np.uint64).astype(np.uint32), rng.integers(0, kb.P, 8).astype(np.uint32), 7)
 
 
 def synthetic_syscall_events(n: int, seed: int = 0, shard: int = 3, kind: str = "instrs") -> np.ndarray:
-    """n SyscallEvent records as (n, 14) uint32 words {pc, next_pc, shard, clk, a_record[6], a_record_is_real, syscall_id, arg1,
-    arg2} (crates/core/executor/src/events/syscall.rs:8-29); a_record.prev_value holds the syscall code the instruction read from
-    $v0, a_record.value the result.  kind "instrs": every syscall of the shard (SyscallInstrs), COMMIT / COMMIT_DEFERRED_PROOFS
-    with a digest index below 8, arguments on both sides of the KoalaBear modulus' top byte; "core": only the events
-    SyscallCore keeps (prev_value byte 2 = 1 or byte 1 != 0, chip.rs:233-240); "precompile": one event per precompile event
-    with prev_value = 1 / value = v0 for the Linux ones and prev_value = 0 otherwise (include/syscall.hpp
+    """n well-formed SyscallEvent records as (n, 14) uint32 words {pc, next_pc, shard, clk, a_record[6], a_record_is_real,
+    syscall_id, arg1, arg2} (crates/core/executor/src/events/syscall.rs:8-29); a_record.prev_value holds the syscall code the
+    instruction read from $v0, a_record.value what it left there.  kind "instrs": every syscall of the shard (SyscallInstrs), as
+    the executor emits them (crates/core/executor/src/executor.rs execute_syscall) - $v0 unchanged except for
+    ENTER_UNCONSTRAINED (0), SYSHINTLEN and the linux calls (a result), syscall_id EXIT_UNCONSTRAINED for ENTER_UNCONSTRAINED,
+    next_pc = 0 and arg1 = the exit code for HALT / SYS_EXT_GROUP, COMMIT / COMMIT_DEFERRED_PROOFS with a digest index below 8
+    and the digest word of syscall_public_values(seed), arguments below the KoalaBear modulus on both sides of its top byte;
+    "core": only the events SyscallCore keeps (prev_value byte 2 = 1 or byte 1 != 0, chip.rs:233-240); "precompile": one event
+    per precompile event with prev_value = 1 / value = v0 for the Linux ones and prev_value = 0 otherwise (include/syscall.hpp
     precompile_event_to_row)."""
     rng = np.random.default_rng(0x5C11 + seed)
     ev = np.zeros((n, SYSCALL_EVENT_WORDS), np.uint32)
     if n == 0:
         return ev
     u32 = lambda: rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
-    code = rng.choice(_SYSCALL_TABLE, n).astype(np.uint32)
-    code[: min(n, len(_SYSCALL_TABLE))] = _SYSCALL_TABLE[: min(n, len(_SYSCALL_TABLE))]
+    table = _SYSCALL_TABLE
     if kind == "core":
-        keep = _SYSCALL_TABLE[(((_SYSCALL_TABLE >> 16) & 0xFF) == 1) | (((_SYSCALL_TABLE >> 8) & 0xFF) != 0)]
-        code = rng.choice(keep, n).astype(np.uint32)
-        code[: min(n, len(keep))] = keep[: min(n, len(keep))]
-    arg1, arg2 = u32(), u32()
-    top = rng.integers(0, 4, n)
-    arg1 = np.where(top == 0, (arg1 & np.uint32(0x00FFFFFF)) | (rng.choice([0x7E, 0x7F, 0x3F, 0x1F, 0x0F], n).astype(np.uint32) << np.uint32(24)), arg1 & np.uint32(0x7EFFFFFF))
-    arg2 = np.where(top == 1, (arg2 & np.uint32(0x00FFFFFF)) | np.uint32(0x7F000000), arg2 & np.uint32(0x7EFFFFFF))
+        table = table[(((table >> 16) & 0xFF) == 1) | (((table >> 8) & 0xFF) != 0)]
+    code = rng.choice(table, n).astype(np.uint32)
+    code[: min(n, len(table))] = table[: min(n, len(table))]
+
+    def below_p():
+        v = u32() & np.uint32(0x7EFFFFFF)
+        pick = rng.integers(0, 6, n)
+        v = np.where(pick == 0, np.uint32(0x7F000000), v)                       # the largest top byte: the low bytes must be zero
+        return np.where(pick == 1, (v & np.uint32(0x00FFFFFF)) | np.uint32(0x7E000000), v).astype(np.uint32)
+    arg1, arg2 = below_p(), below_p()
     sid = code & np.uint32(0xFFFF)
-    commits = (sid == 0x10) | (sid == 0x1A)
-    arg1 = np.where(commits, rng.integers(0, 8, n), arg1).astype(np.uint32)
-    value = u32()
+    digest, deferred, exit_code = syscall_public_values(seed)
+    idx = rng.integers(0, 8, n)
+    is_commit, is_deferred = sid == 0x10, sid == 0x1A
+    arg1 = np.where(is_commit | is_deferred, idx, arg1).astype(np.uint32)
+    arg2 = np.where(is_commit, digest[idx], np.where(is_deferred, deferred[idx], arg2)).astype(np.uint32)
+    is_halt = (sid == 0) | (sid == 4246)
+    arg1 = np.where(is_halt, exit_code, arg1).astype(np.uint32)
+    linux = ((code >> 8) & 0xFF) != 0
+    value = np.where(sid == 0x03, 0, np.where((sid == 0xF0) | linux, u32(), code)).astype(np.uint32)
     prev_value = code.copy()
     if kind == "precompile":
-        linux = rng.integers(0, 3, n) == 0
-        prev_value = linux.astype(np.uint32)
-        value = np.where(linux, value, 0).astype(np.uint32)
+        is_linux = rng.integers(0, 3, n) == 0
+        prev_value = is_linux.astype(np.uint32)
+        value = np.where(is_linux, u32(), 0).astype(np.uint32)
     ev[:, 0] = rng.integers(0, kb.P - 16, n) & ~np.uint32(3)
-    ev[:, 1] = ev[:, 0] + 4
+    ev[:, 1] = np.where(is_halt & (kind != "precompile"), 0, ev[:, 0] + 4)
     ev[:, 2] = shard
     ev[:, 3] = (5 + 5 * np.arange(1, n + 1)).astype(np.uint32)
     ev[:, 4:10] = _write_record(rng, n, shard, ev[:, 3], value, prev_value)
@@ -624,7 +645,7 @@ def synthetic_syscall_events(n: int, seed: int = 0, shard: int = 3, kind: str = 
         ev[:, 5:7] = 0
         ev[:, 8:10] = 0                                   # a default MemoryWriteRecord apart from the two fields above
     ev[:, 10] = 0 if kind == "precompile" else 1
-    ev[:, 11] = sid if kind != "precompile" else rng.choice(_SYSCALL_TABLE & 0xFFFF, n)
+    ev[:, 11] = np.where(sid == 0x03, 0x04, sid)
     ev[:, 12], ev[:, 13] = arg1, arg2
     return ev
 
