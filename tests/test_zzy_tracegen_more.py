@@ -63,6 +63,11 @@ def test_shapes(oracle, host):
         assert oracle.chip_trace_width(chip) == tg.width(chip) == GOLD[chip]["width"]
         assert oracle.chip_event_words(chip) == tg.event_words(chip)
     assert GOLD["MemoryGlobalInit"]["width"] == oracle.MEMGLOBAL_WIDTH == 111
+    # the C ABI knows every chip by its MachineAir::name (no GPU needed for this call)
+    from ziren_b200 import _ffi
+    for chip in list(tg.ROW_CHIPS) + ["Global", "Cpu", "MiscInstrs", "MemoryLocal", "Mul", "AddSub"]:
+        assert _ffi.lib().zkb200_alu_trace_width(chip.encode()) == tg.width(chip), chip
+    assert _ffi.lib().zkb200_alu_trace_width(b"Byte") == -1
     # the wide chips run 64 rows per CTA so that events + row tile fit 48 KB of static shared memory, the others 128
     assert host.hostcheck_alu_cta_rows(CHIP_ID["DivRem"]) == host.hostcheck_alu_cta_rows(CHIP_ID["MemoryGlobalInit"]) == 64
     assert host.hostcheck_alu_cta_rows(CHIP_ID["SyscallInstrs"]) == host.hostcheck_alu_cta_rows(12) == 128
