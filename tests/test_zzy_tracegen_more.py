@@ -102,6 +102,36 @@ def test_product_matches_oracle_through_the_cta_phases(oracle, host, chip, n, he
     assert np.array_equal(_host_rows(host, chip, ev, height, cta=True, col_major=True), want)
 
 
+def test_cta_phases_agree_with_the_plain_row_loop_for_every_chip(host):
+    """All twenty chips of alu_rows_kernel: the CTA walk (load / fill / store as the kernel indexes them, 128 or 64 rows per
+    CTA, both layouts, a ragged last CTA and a table shorter than one CTA) against the row-by-row loop over the same fillers."""
+    names = ["AddSub", "Bitwise", "Lt", "ShiftLeft", "ShiftRight", "CloClz", "Branch", "Jump", "MovCond", "Mul", "MemoryInstrs", "MemoryLocal",
+             "Cpu", "MiscInstrs", "DivRem", "SyscallCore", "SyscallPrecompile", "SyscallInstrs", "MemoryGlobalInit", "MemoryGlobalFinalize"]
+    gens = {"Mul": tg.synthetic_mul_events, "MemoryInstrs": tg.synthetic_mem_instr_events, "MemoryLocal": tg.synthetic_memory_local_events,
+            "Cpu": tg.synthetic_cpu_events, "MiscInstrs": tg.synthetic_misc_events, "DivRem": tg.synthetic_div_rem_events,
+            "SyscallCore": lambda n, seed: tg.synthetic_syscall_events(n, seed=seed, kind="core"),
+            "SyscallPrecompile": lambda n, seed: tg.synthetic_syscall_events(n, seed=seed, kind="precompile"),
+            "SyscallInstrs": lambda n, seed: tg.synthetic_syscall_events(n, seed=seed, kind="instrs"),
+            "MemoryGlobalInit": lambda n, seed: tg.memory_global_records(tg.synthetic_memory_global_events(n, seed=seed), 0),
+            "MemoryGlobalFinalize": lambda n, seed: tg.memory_global_records(tg.synthetic_memory_global_events(n, seed=seed), 0)}
+    assert host.hostcheck_alu_nchips() == len(names)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for cid, chip in enumerate(names):
+        w, epr = tg.width(chip), tg.events_per_row(chip)
+        assert host.hostcheck_alu_width(cid) == w and host.hostcheck_alu_event_words(cid) == tg.event_words(chip), chip
+        for rows, height in ((300, 384), (40, 48)):
+            n = rows * epr - (1 if epr > 1 else 0)
+            ev = gens[chip](n, seed=7) if chip in gens else tg.synthetic_events(chip, n, seed=7)
+            ev = np.ascontiguousarray(ev, dtype=np.uint32)
+            plain = np.full(height * w, 0xFFFFFFFF, np.uint32)
+            assert host.hostcheck_alu_rows(cid, p(ev), ctypes.c_size_t(n), ctypes.c_size_t(height), p(plain)) == 0
+            for col_major in (0, 1):
+                out = np.full(height * w, 0xFFFFFFFF, np.uint32)
+                assert host.hostcheck_alu_rows_cta(cid, p(ev), ctypes.c_size_t(n), ctypes.c_size_t(height), p(out), col_major) == 0
+                got = out.reshape(w, height).T if col_major else out.reshape(height, w)
+                assert np.array_equal(got, plain.reshape(height, w)), (chip, height, col_major)
+
+
 def test_cta_phases_of_the_earlier_chips(oracle, host):
     """The same walk for chips of the earlier rounds: one with four events per row, the two widest records."""
     for chip, cid, ev, orc in (("MemoryLocal", 11, tg.synthetic_memory_local_events(1021, seed=2), oracle.memory_local_trace),
