@@ -152,6 +152,26 @@ int zkb200_mmcs_root(zkb200_ctx* ctx, const uint32_t* const* mats, const unsigne
                      int n, uint32_t root_out[8]);
 /* K2: n Poseidon2 permutations in place, states row-major n x 16 */
 int zkb200_poseidon2_permute_batch(zkb200_ctx* ctx, uint32_t* states, size_t n);
+/* K7: the multiplicity columns of a table that only RECEIVES lookups (Byte, Program, range tables), derived from the rows of
+ * the tables that send to it.  In the reference these are histograms the host accumulates while it generates every other
+ * table: each chip's generate_dependencies -> record.byte_lookups -> ByteChip::generate_trace
+ * (crates/core/machine/src/bytes/trace.rs:46-67), the Cpu events' pcs -> ProgramChip::generate_trace
+ * (crates/core/machine/src/program/mod.rs:115-158).  Here the machine description already says which tuple every row of every
+ * chip sends (the sends of its Air::eval, as in `Chip::sends`, crates/stark/src/chip.rs), so ONE pass over the resident rows -
+ * uploaded or generated on the device - gives the same multiplicities without the per-chip byte-lookup bookkeeping.
+ * `receiver`: a chip with receives whose values are made of preprocessed columns only and whose multiplicity is a main column;
+ * `receiver_prep`: its preprocessed trace; `senders`: the shard's other tables (chips without a matching send are skipped);
+ * every pointer is DEVICE memory, column-major, Montgomery.  `out`: receiver_height x main_width of the receiver, column-major
+ * Montgomery (columns that are not multiplicities are zero).  Among equal tuples of the receiver the lowest (receive, row)
+ * takes the multiplicity.  Fails (MachineProver::Error) when a sent tuple is in no row of the receiver. */
+typedef struct {
+  const char* chip;
+  const uint32_t* prep;         /* NULL for a chip without preprocessed columns */
+  const uint32_t* main_trace;
+  size_t height;
+} zkb200_table;
+int zkb200_derive_multiplicities(zkb200_ctx* ctx, const char* receiver, const uint32_t* receiver_prep, size_t receiver_height,
+                                 const zkb200_table* senders, int n_senders, uint32_t* out, uint64_t* n_lookups_out);
 /* K5: LogUp permutation trace of one chip; out n x 4E column-major, local_sum canonical[4] */
 int zkb200_permutation_trace(zkb200_ctx* ctx, const char* chip, const uint32_t* prep, const uint32_t* main_trace,
                              size_t height, const uint32_t alpha[4], const uint32_t beta[4], uint32_t* out,

@@ -6,6 +6,8 @@
 #include "tracegen.h"
 #include "tracegen_global.h"
 #include "tracegen_keccak.h"
+#include <map>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #ifdef _OPENMP
@@ -215,6 +217,59 @@ int zko_permutation_trace(void* m_, const char* chip, const u32* prep, const u32
     Matrix r = generate_permutation_trace(*c, prep ? &pm : nullptr, mm, e_from(alpha), e_from(beta), ls);
     for (size_t i = 0; i < r.v.size(); i++) out[i] = r.v[i].v;
     e_to(ls, local_sum);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+// The multiplicity columns of a receive-only table from the rows of its senders (the checker of csrc/derive.cuh): what the
+// reference accumulates on the host as record.byte_lookups -> ByteChip::generate_trace (crates/core/machine/src/bytes/trace.rs:
+// 46-67) and as instruction counts -> ProgramChip::generate_trace (program/mod.rs:115-158), stated through the lookups of the
+// machine description - a std::map from (kind, tuple) to the first (receive, row) of the receiver that holds it.
+// Tables row-major canonical; senders: n_senders x {chip name, prep or null, main, height}; out height x main_width canonical.
+int zko_derive_multiplicities(void* m_, const char* receiver, const u32* receiver_prep, size_t receiver_height, int n_senders,
+                              const char* const* sender_names, const u32* const* sender_prep, const u32* const* sender_main,
+                              const size_t* sender_heights, u32* out, unsigned long long* n_lookups) {
+  try {
+    const Machine& m = *(Machine*)m_;
+    const Chip* r = m.find(receiver);
+    if (!r) throw std::runtime_error("unknown chip");
+    std::map<std::vector<u32>, std::pair<size_t, u32>> where;      // (kind, values...) -> (row, multiplicity column)
+    std::vector<u32> kinds;
+    for (auto& l : r->receives) {
+      if (l.scope != 0) continue;
+      bool prep_only = true;
+      for (auto& v : l.values) for (auto& t : v.terms) prep_only = prep_only && !t.is_main;
+      if (!prep_only || !l.mult.constant.is_zero() || l.mult.terms.size() != 1 || !l.mult.terms[0].is_main || l.mult.terms[0].w != F::one()) continue;
+      kinds.push_back(l.kind);
+      for (size_t row = 0; row < receiver_height; row++) {
+        std::vector<u32> key{l.kind};
+        for (auto& v : l.values) key.push_back(v.apply<F, F>((const F*)receiver_prep + row * r->prep_width, (const F*)nullptr).v);
+        where.emplace(key, std::make_pair(row, l.mult.terms[0].col));      // the first (receive, row) keeps a repeated tuple
+      }
+    }
+    if (kinds.empty()) throw std::runtime_error("no receive of preprocessed columns with a main column as its multiplicity");
+    std::vector<u64> counts(receiver_height * r->main_width, 0);
+    unsigned long long n = 0;
+    for (int i = 0; i < n_senders; i++) {
+      const Chip* c = m.find(sender_names[i]);
+      if (!c) throw std::runtime_error("unknown chip");
+      for (auto& l : c->sends) {
+        if (l.scope != 0 || std::find(kinds.begin(), kinds.end(), l.kind) == kinds.end()) continue;
+        for (size_t row = 0; row < sender_heights[i]; row++) {
+          const F* pr = sender_prep[i] ? (const F*)sender_prep[i] + row * c->prep_width : nullptr;
+          const F* mr = (const F*)sender_main[i] + row * c->main_width;
+          const F mult = l.mult.apply<F, F>(pr, mr);
+          if (mult.is_zero()) continue;
+          std::vector<u32> key{l.kind};
+          for (auto& v : l.values) key.push_back(v.apply<F, F>(pr, mr).v);
+          auto it = where.find(key);
+          if (it == where.end()) throw std::runtime_error("a lookup of " + c->name + " is in no row of " + r->name);
+          counts[it->second.first * r->main_width + it->second.second] += mult.v;
+          n++;
+        }
+      }
+    }
+    for (size_t i = 0; i < counts.size(); i++) out[i] = (u32)(counts[i] % P);
+    if (n_lookups) *n_lookups = n;
     return 0;
   } catch (const std::exception& e) { return fail(e); }
 }

@@ -527,6 +527,26 @@ class OracleMachine:
             raise RuntimeError("oracle: " + err())
         return out, ls
 
+    def derive_multiplicities(self, receiver, receiver_prep, senders, main_width):
+        """The multiplicity columns of a receive-only table from the rows of its senders (zko_derive_multiplicities).
+        receiver_prep: (height, prep_width) canonical; senders: [(chip, prep or None, main)] canonical rows.  Returns
+        ((height, main_width) canonical, number of lookups)."""
+        rp = _a(receiver_prep)
+        out = np.zeros((rp.shape[0], int(main_width)), np.uint32)
+        k = len(senders)
+        names = (C.c_char_p * max(1, k))(*[s[0].encode() for s in senders])
+        preps = [(_a(s[1]) if s[1] is not None else None) for s in senders]
+        mains = [_a(s[2]) for s in senders]
+        pp = (C.c_void_p * max(1, k))(*[(p.ctypes.data if p is not None else None) for p in preps])
+        mp = (C.c_void_p * max(1, k))(*[m.ctypes.data for m in mains])
+        hs = (C.c_size_t * max(1, k))(*[m.shape[0] for m in mains])
+        n = C.c_ulonglong(0)
+        rc = lib().zko_derive_multiplicities(C.c_void_p(self.h), receiver.encode(), _p(rp), C.c_size_t(rp.shape[0]), C.c_int(k), names, pp, mp,
+                                             hs, _p(out), C.byref(n))
+        if rc:
+            raise RuntimeError("oracle: " + err())
+        return out, int(n.value)
+
     def quotient_values(self, chip, log_n, prep_lde, main_lde, perm_lde, perm_alpha, perm_beta, local_sum, global_sum,
                         alpha, pub):
         info = self.chip_info(chip)

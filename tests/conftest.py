@@ -31,7 +31,7 @@ def host():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libhostcheck.so")
     csrc = os.path.join(ROOT, "ziren_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("kb31.cuh", "poseidon2.cuh", "tracegen.cuh", "tracegen_keccak.cuh", "tracegen_global.cuh", "lane_pool.h", "p2_rc.inc")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("kb31.cuh", "poseidon2.cuh", "tracegen.cuh", "tracegen_keccak.cuh", "tracegen_global.cuh", "derive.cuh", "machine_dev.h", "lane_pool.h", "p2_rc.inc")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I" + csrc, "-x", "c++", src, "-o", so])
     return ctypes.CDLL(so)

@@ -5,6 +5,7 @@
 #include "tracegen.cuh"
 #include "tracegen_keccak.cuh"
 #include "tracegen_global.cuh"
+#include "derive.cuh"
 #include "lane_pool.h"
 #include <algorithm>
 #include <atomic>
@@ -166,6 +167,36 @@ int hostcheck_septic_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* 
     default: return -1;
   }
   for (int i = 0; i < 7; i++) out[i] = fp_to_canonical(r.c[i]);
+  return 0;
+}
+// K7 (csrc/derive.cuh; csrc/derive.cu derive_multiplicities) walked on the host in the kernels' order: fill, one insert per
+// (receive, row), one probe per (send, row), finish.  The machine tables arrive as the flat arrays MachineInfo::upload builds
+// (DevLookup 5 words, DevVPC 3, DevTerm 2, Montgomery weights); tables column-major Montgomery.  stats: lookups counted, misses.
+int hostcheck_derive(const uint32_t* lookups, const uint32_t* vpcs, const uint32_t* terms, const uint32_t* recv, uint32_t n_recv,
+                     const uint32_t* receiver_prep, size_t receiver_height, uint32_t main_width, int n_sends, const uint32_t* send_lookup,
+                     const uint32_t* send_table, const uint32_t* const* table_prep, const uint32_t* const* table_main,
+                     const size_t* table_height, uint32_t* out, unsigned long long* stats) {
+  static_assert(sizeof(DevLookup) == 20 && sizeof(DevVPC) == 12 && sizeof(DevTerm) == 8 && sizeof(DeriveReceive) == 8, "flat table layout");
+  const DevLookup* L = reinterpret_cast<const DevLookup*>(lookups);
+  const DevVPC* V = reinterpret_cast<const DevVPC*>(vpcs);
+  const DevTerm* T = reinterpret_cast<const DevTerm*>(terms);
+  const DeriveReceive* R = reinterpret_cast<const DeriveReceive*>(recv);
+  const size_t entries = (size_t)n_recv * receiver_height;
+  size_t cap = 1;
+  while (cap < 2 * entries) cap <<= 1;
+  std::vector<u32> slots(cap, DERIVE_EMPTY);
+  std::vector<u64> counts((size_t)main_width * receiver_height, 0);
+  const DeriveTable r{receiver_prep, nullptr, receiver_height};
+  for (size_t i = 0; i < entries; i++) derive_insert((u32)(i / receiver_height), i % receiver_height, R, L, V, T, r, slots.data(), (u32)(cap - 1));
+  stats[0] = stats[1] = 0;
+  for (int k = 0; k < n_sends; k++) {
+    const DeriveTable st{table_prep[send_table[k]], table_main[send_table[k]], table_height[send_table[k]]};
+    for (size_t row = 0; row < st.height; row++) {
+      const int rc = derive_probe(L[send_lookup[k]], row, st, R, L, V, T, r, slots.data(), (u32)(cap - 1), counts.data());
+      if (rc) stats[rc - 1]++;
+    }
+  }
+  for (size_t i = 0; i < counts.size(); i++) out[i] = derive_finish(counts[i]);
   return 0;
 }
 // the product's KeccakSponge row filler (csrc/tracegen_keccak.cuh) on the host: n_blocks records of 384 words,

@@ -20,6 +20,11 @@ class Trace(C.Structure):
 TRACE_COL_MAJOR, TRACE_EVENTS = 1, 2
 
 
+class Table(C.Structure):
+    """zkb200_table (include/zkb200.h): a resident table, device pointers, column-major Montgomery."""
+    _fields_ = [("chip", C.c_char_p), ("prep", C.c_void_p), ("main_trace", C.c_void_p), ("height", C.c_size_t)]
+
+
 def build(verbose: bool = False) -> None:
     """Compile every CUDA source for sm_100a into ziren_b200/libzkb200.so (in-tree)."""
     subprocess.run(["make", "-C", os.path.join(_DIR, "csrc"), "-j8"], check=True,
@@ -57,6 +62,7 @@ SIGNATURES = {
     "zkb200_ntt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t, C.c_int, C.c_int]),
     "zkb200_mmcs_root": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint), C.POINTER(C.c_size_t), C.c_int, u32p]),
     "zkb200_poseidon2_permute_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "zkb200_derive_multiplicities": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong)]),
     "zkb200_permutation_trace": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, u32p, u32p, C.c_void_p, u32p]),
     "zkb200_quotient": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, u32p, u32p, u32p, u32p,
                                   u32p, u32p, C.c_size_t, C.c_void_p]),

@@ -3,6 +3,7 @@
 #include "../../include/zkb200.h"
 #include <cstdlib>
 #include <memory>
+#include "derive.h"
 #include "layout.h"
 #include "logup.h"
 #include "open.h"
@@ -254,6 +255,27 @@ int zkb200_permutation_trace(zkb200_ctx* ctx, const char* chip, const uint32_t* 
     ZKB_CUDA(cudaMemcpyAsync(ctx->c.lanes[0].h_small, ctx->c.lanes[0].d_small, 16, cudaMemcpyDeviceToHost, ctx->c.lanes[0].stream));
     ZKB_CUDA(cudaStreamSynchronize(ctx->c.lanes[0].stream));
     for (int i = 0; i < 4; i++) local_sum_out[i] = fp_to_canonical(fp_raw(ctx->c.lanes[0].h_small[i]));
+  });
+}
+int zkb200_derive_multiplicities(zkb200_ctx* ctx, const char* receiver, const uint32_t* receiver_prep, size_t receiver_height,
+                                 const zkb200_table* senders, int n_senders, uint32_t* out, uint64_t* n_lookups_out) {
+  return guarded(ctx, [&] {
+    std::lock_guard<std::mutex> lock(ctx->c.lanes[0].mu);
+    ZKB_CUDA(cudaSetDevice(ctx->c.device));
+    const ChipInfo* r = ctx->c.machine.find(receiver);
+    if (!r) throw std::runtime_error(std::string("zkb200: unknown chip ") + receiver);
+    if (!receiver_prep || !out) throw std::runtime_error("zkb200: derive_multiplicities: null receiver table");
+    if (n_senders > 0 && !senders) throw std::runtime_error("zkb200: derive_multiplicities: null sender list");
+    std::vector<DeriveSender> snd;
+    for (int i = 0; i < n_senders; i++) {
+      const ChipInfo* c = ctx->c.machine.find(senders[i].chip);
+      if (!c) throw std::runtime_error(std::string("zkb200: unknown chip ") + senders[i].chip);
+      if (senders[i].height && !senders[i].main_trace) throw std::runtime_error(std::string("zkb200: derive_multiplicities: no main trace for ") + senders[i].chip);
+      if (c->prep_width && !senders[i].prep && senders[i].height) throw std::runtime_error(std::string("zkb200: derive_multiplicities: no preprocessed trace for ") + senders[i].chip);
+      snd.push_back({c, DeriveTable{senders[i].prep, senders[i].main_trace, senders[i].height}});
+    }
+    const u64 n = derive_multiplicities(ctx->c.machine, *r, receiver_prep, receiver_height, snd, out, ctx->c.lanes[0].stream);
+    if (n_lookups_out) *n_lookups_out = n;
   });
 }
 int zkb200_quotient(zkb200_ctx* ctx, const char* chip, unsigned log_n, const uint32_t* prep_lde, const uint32_t* main_lde,

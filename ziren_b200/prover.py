@@ -258,6 +258,18 @@ class B200Prover:
                                                         _data_ptr(main), height, _p(a), _p(b), _data_ptr(out), _p(ls)))
         return ls
 
+    def derive_multiplicities(self, receiver: str, receiver_prep, receiver_height: int, senders, out) -> int:
+        """K7: the multiplicity columns of a receive-only table (Byte, Program, range tables) from the rows of the tables that
+        send to it.  senders: [(chip, prep or None, main, height)], CUDA tensors column-major Montgomery; out: CUDA tensor of
+        receiver_height x main_width words, column-major.  Returns the number of lookups counted."""
+        arr = (_ffi.Table * max(1, len(senders)))()
+        for i, (chip, prep, main, height) in enumerate(senders):
+            arr[i] = _ffi.Table(chip.encode(), _data_ptr(prep) if prep is not None else None, _data_ptr(main) if height else None, int(height))
+        n = C.c_ulonglong(0)
+        self._check(_ffi.lib().zkb200_derive_multiplicities(self._h, receiver.encode(), _data_ptr(receiver_prep), int(receiver_height),
+                                                            C.cast(arr, C.c_void_p), len(senders), _data_ptr(out), C.byref(n)))
+        return int(n.value)
+
     def quotient(self, chip, log_n, prep_lde, main_lde, perm_lde, perm_alpha, perm_beta, local_sum, global_sum, alpha, pub, out):
         args = [_np32(x) for x in (perm_alpha, perm_beta, local_sum, global_sum, alpha, pub)]
         self._check(_ffi.lib().zkb200_quotient(self._h, chip.encode(), log_n, _data_ptr(prep_lde) if prep_lde is not None else None,
