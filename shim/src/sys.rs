@@ -13,6 +13,14 @@ pub struct zkb200_trace {
 }
 pub const ZKB200_TRACE_COL_MAJOR: u32 = 1;
 pub const ZKB200_TRACE_EVENTS: u32 = 2;
+/// A table resident on the device, column-major Montgomery (`zkb200_table`): a sender of `zkb200_derive_multiplicities`.
+#[repr(C)]
+pub struct zkb200_table {
+    pub chip: *const c_char,
+    pub prep: *const u32,       // null for a chip without preprocessed columns
+    pub main_trace: *const u32,
+    pub height: usize,
+}
 pub enum zkb200_ctx {}
 pub enum zkb200_pk {}
 pub enum zkb200_shard {}
@@ -38,4 +46,10 @@ extern "C" {
     pub fn zkb200_keccak_sponge_trace_width() -> c_int;
     pub fn zkb200_generate_keccak_sponge_trace(ctx: *mut zkb200_ctx, blocks: *const crate::tracegen::KeccakBlock, n_blocks: usize,
                                                log_height: std::os::raw::c_uint, out: *mut u32, col_major: c_int) -> c_int;
+    /// K7: the multiplicity columns of a receive-only table (Byte, Program) from the device-resident rows of its senders -
+    /// what generate_dependencies -> record.byte_lookups -> ByteChip::generate_trace (bytes/trace.rs:46-67) and
+    /// ProgramChip::generate_trace (program/mod.rs:115-158) count on the host.  Every pointer is device memory.
+    pub fn zkb200_derive_multiplicities(ctx: *mut zkb200_ctx, receiver: *const c_char, receiver_prep: *const u32,
+                                        receiver_height: usize, senders: *const zkb200_table, n_senders: c_int,
+                                        out: *mut u32, n_lookups_out: *mut u64) -> c_int;
 }
