@@ -19,6 +19,10 @@ def machines():
     yield "core", synthetic.core_case(log_cpu=9).machine
     yield "keccak", synthetic.keccak_case(log_cpu=8).machine
     yield "compress", synthetic.compress_case(log_max=9).machine
+    # the nine narrow core chips with their restated Air::eval (tests/test_tracegen.py: shards proved from event records)
+    from . import tracegen as tg
+    narrow = {n: np.zeros((16, tg.width(n)), np.uint32) for n in ("AddSub", "ShiftLeft", "Lt", "ShiftRight", "Bitwise", "CloClz", "Branch", "Jump", "MovCond")}
+    yield "alu", synthetic.alu_case(narrow, with_lookup_pair=True).machine
     # the real Global chip (synthetic.py _global_chip: septic-extension constraints of degree three)
     yield "global", synthetic.global_case(np.zeros((16, 99), np.uint32)).machine
     yield "div-rem", synthetic.chips_case({"DivRem": np.zeros((16, 106), np.uint32)}).machine
