@@ -35,3 +35,20 @@ def host():
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I" + csrc, "-x", "c++", src, "-o", so])
     return ctypes.CDLL(so)
+
+
+# GPU run order (`pytest -m gpu -x`): the prover's own parity tests first, then the row fillers that have run bit-exact on a
+# B200, then what was written after the round's GPU budget was spent and has only been checked on the host (DESIGN.md
+# "f3 chip by chip", column "B200 run") - a first-run failure there must not cut the established tests short.
+_GPU_ORDER = [("test_gpu_parity", "test_zz_cpp_host", "test_tracegen_keccak"),
+              ("test_tracegen", "test_tracegen_mul", "test_zz_tracegen_mem_instr", "test_zz_tracegen_memory_local")]
+
+
+def pytest_collection_modifyitems(config, items):
+    def rank(item):
+        mod = os.path.splitext(os.path.basename(str(item.fspath)))[0]
+        for r, mods in enumerate(_GPU_ORDER):
+            if mod in mods:
+                return r
+        return len(_GPU_ORDER)
+    items.sort(key=rank)       # stable: file and definition order inside a rank
