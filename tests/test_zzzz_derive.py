@@ -99,7 +99,7 @@ def _flatten(machine):
 
 def _derivable(l):
     c, ts = l["mult"]
-    return (all(not is_main for _, vt in l["values"] for is_main, _, _ in vt) and c == 0 and len(ts) == 1 and ts[0][0] == 1
+    return (l["scope"] == 0 and all(not is_main for _, vt in l["values"] for is_main, _, _ in vt) and c == 0 and len(ts) == 1 and ts[0][0] == 1
             and ts[0][2] == 1)
 
 
@@ -122,7 +122,7 @@ def _host_derive(host, case, receiver):
     send_lookup, send_table = [], []
     for ti, n in enumerate(names):
         for i, l in enumerate(machine.chip(n).builder.sends):
-            if l["kind"] in kinds:
+            if l["kind"] in kinds and l["scope"] == 0:
                 send_lookup.append(begin[n] + i)
                 send_table.append(ti)
     rprep = cm(case.prep[receiver])

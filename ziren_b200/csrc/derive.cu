@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(DV_THREADS) derive_finish_kernel(const u64* co
 // which receives of a chip can be derived: every value made of preprocessed columns (and constants), the multiplicity one
 // main column with weight one
 static bool derivable(const HostLookup& l, u32& mult_col) {
-  if (l.is_send || l.values.size() > DERIVE_MAX_VALUES) return false;
+  if (l.is_send || l.scope != 0 || l.values.size() > DERIVE_MAX_VALUES) return false;      // local-scope receives only
   for (auto& v : l.values)
     for (auto& t : v.terms) if (t.is_main) return false;
   if (l.mult.const_canon != 0 || l.mult.terms.size() != 1 || !l.mult.terms[0].is_main || l.mult.terms[0].w_canon != 1) return false;
@@ -76,7 +76,7 @@ u64 derive_multiplicities(const MachineInfo& m, const ChipInfo& receiver, const 
     if (!snd.table.height) continue;
     for (size_t i = 0; i < snd.chip->lookups.size(); i++) {
       const HostLookup& l = snd.chip->lookups[i];
-      bool wanted = l.is_send && l.values.size() <= DERIVE_MAX_VALUES;
+      bool wanted = l.is_send && l.scope == 0 && l.values.size() <= DERIVE_MAX_VALUES;
       if (wanted) { wanted = false; for (u32 k : kinds) wanted = wanted || k == l.kind; }
       if (!wanted) continue;
       derive_probe_kernel<<<(unsigned)ceil_div(snd.table.height, (size_t)DV_THREADS), DV_THREADS, 0, s>>>(
