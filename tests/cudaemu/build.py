@@ -57,6 +57,13 @@ def rewrite_launches(text: str) -> tuple[str, int]:
         n += 1
 
 
+def poison_shared(text: str) -> tuple[str, int]:
+    """`__shared__ T name[n];` -> the same static array, filled with 0xDEADBEEF once per block before its first use: shared
+    memory is not zero on a GPU and keeps what the previous block left, so a kernel that reads a word it has not written must
+    not pass here by reading a stale zero."""
+    return re.subn(r"__shared__\s+(\w+)\s+(\w+)\[([^\]]*)\];", r"static \1 \2[\3]; emu_poison(\2, sizeof(\2));", text)
+
+
 def build() -> str:
     out_dir = os.path.join(HERE, "_build")
     os.makedirs(out_dir, exist_ok=True)
@@ -70,6 +77,8 @@ def build() -> str:
     for name in SOURCES:
         text, n = rewrite_launches(open(os.path.join(CSRC, name)).read())
         sites += n
+        text, n_shared = poison_shared(text)
+        assert n_shared == (2 if name == "tracegen.cu" else 0), (name, n_shared)
         dst = os.path.join(out_dir, os.path.splitext(name)[0] + "_emu.cpp")
         with open(dst, "w") as f:
             f.write(f'#line 1 "{os.path.join(CSRC, name)}"\n' + text)

@@ -47,6 +47,7 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 
 struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
 struct EmuBlock {
+  std::vector<void*> poisoned;      // shared arrays already filled with the poison pattern for this block
   std::barrier<> barrier;
   explicit EmuBlock(unsigned n) : barrier((std::ptrdiff_t)n) {}
 };
@@ -58,6 +59,14 @@ inline void __syncthreads() {
   emu_baton.unlock();
   emu_block->barrier.arrive_and_wait();
   emu_baton.lock();
+}
+
+// tests/cudaemu/build.py puts this after every `__shared__` array declaration (runs under the baton)
+inline void emu_poison(void* p, size_t bytes) {
+  for (void* q : emu_block->poisoned) if (q == p) return;
+  emu_block->poisoned.push_back(p);
+  unsigned* w = static_cast<unsigned*>(p);
+  for (size_t i = 0; i < bytes / 4; i++) w[i] = 0xDEADBEEFu;
 }
 
 template <class K, class... A>
