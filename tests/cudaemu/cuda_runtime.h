@@ -25,7 +25,8 @@ constexpr unsigned cudaHostAllocMapped = 2;
 
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+// device memory is not zero either: fresh allocations carry a pattern
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); if (*p) memset(*p, 0xA5, n); return *p ? 0 : 2; }
 inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFree(void* p) { free(p); return 0; }
 inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return 0; }
