@@ -27,19 +27,38 @@ def _split_top_level(s: str) -> list[str]:
     return out
 
 
+def _kernel_name_start(text: str, at: int) -> tuple[int, int]:
+    """the kernel expression that ends right before `<<<`: identifier, optionally with template arguments"""
+    i = at
+    while text[i - 1].isspace():
+        i -= 1
+    end = i
+    if text[i - 1] == ">":
+        depth = 0
+        while True:
+            i -= 1
+            if text[i] == ">":
+                depth += 1
+            elif text[i] == "<":
+                depth -= 1
+                if depth == 0:
+                    break
+    while text[i - 1].isalnum() or text[i - 1] in "_:":
+        i -= 1
+    return i, end
+
+
 def rewrite_launches(text: str) -> tuple[str, int]:
-    """kernel<<<g, b, shm, stream>>>(args) -> emu_launch(kernel, g, b, args); returns (text, number of launch sites)"""
+    """kernel<<<g, b, shm, stream>>>(args) -> emu_launch_dyn((kernel), g, b, shm, args); returns (text, number of launch sites)"""
     n = 0
     while True:
         at = text.find("<<<")
         if at < 0:
             return text, n
-        m = re.search(r"([A-Za-z_][\w:]*(?:<[^<>;(){}]*>)?)\s*$", text[:at])
-        assert m, "no kernel name before <<<"
+        ks, ke = _kernel_name_start(text, at)
         end = text.index(">>>", at)
         cfg = _split_top_level(text[at + 3:end])
         assert len(cfg) in (2, 3, 4), cfg
-        assert len(cfg) < 3 or cfg[2] == "0", "dynamic shared memory is not emulated"
         k = end + 3
         while text[k].isspace():
             k += 1
@@ -52,16 +71,21 @@ def rewrite_launches(text: str) -> tuple[str, int]:
                 break
             j += 1
         args = text[k + 1:j].strip()
-        call = f"emu_launch({m.group(1)}, {cfg[0]}, {cfg[1]}" + (", " + args if args else "") + ")"
-        text = text[:m.start(1)] + call + text[j + 1:]
+        shm = cfg[2] if len(cfg) > 2 else "0"
+        call = f"emu_launch_dyn(({text[ks:ke]}), {cfg[0]}, {cfg[1]}, {shm}" + (", " + args if args else "") + ")"
+        text = text[:ks] + call + text[j + 1:]
         n += 1
 
 
 def poison_shared(text: str) -> tuple[str, int]:
-    """`__shared__ T name[n];` -> the same static array, filled with 0xDEADBEEF once per block before its first use: shared
+    """`__shared__ T name[n]...;` -> the same static array, filled with 0xDEADBEEF once per block before its first use: shared
     memory is not zero on a GPU and keeps what the previous block left, so a kernel that reads a word it has not written must
-    not pass here by reading a stale zero."""
-    return re.subn(r"__shared__\s+(\w+)\s+(\w+)\[([^\]]*)\];", r"static \1 \2[\3]; emu_poison(\2, sizeof(\2));", text)
+    not pass here by reading a stale zero.  `extern __shared__ T name[];` -> a pointer to the launch's dynamic shared memory."""
+    text, n_dyn = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = static_cast<\1*>(emu_dyn_shared());", text)
+    text, n = re.subn(r"__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)((?:\[[^\]]*\])+);",
+                      r"alignas(16) static \1 \2\3; emu_poison(\2, sizeof(\2));", text)
+    assert "__shared__" not in re.sub(r"//[^\n]*", "", text), "a __shared__ declaration the rewrite does not know"
+    return text, n + n_dyn
 
 
 def build() -> str:
@@ -78,7 +102,6 @@ def build() -> str:
         text, n = rewrite_launches(open(os.path.join(CSRC, name)).read())
         sites += n
         text, n_shared = poison_shared(text)
-        assert n_shared == (2 if name == "tracegen.cu" else 0), (name, n_shared)
         dst = os.path.join(out_dir, os.path.splitext(name)[0] + "_emu.cpp")
         with open(dst, "w") as f:
             f.write(f'#line 1 "{os.path.join(CSRC, name)}"\n' + text)
