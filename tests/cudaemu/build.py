@@ -82,8 +82,8 @@ def poison_shared(text: str) -> tuple[str, int]:
     memory is not zero on a GPU and keeps what the previous block left, so a kernel that reads a word it has not written must
     not pass here by reading a stale zero.  `extern __shared__ T name[];` -> a pointer to the launch's dynamic shared memory."""
     text, n_dyn = re.subn(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];", r"\1* \2 = static_cast<\1*>(emu_dyn_shared());", text)
-    text, n = re.subn(r"__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)((?:\[[^\]]*\])+);",
-                      r"alignas(16) static \1 \2\3; emu_poison(\2, sizeof(\2));", text)
+    text, n = re.subn(r"__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)((?:\[[^\]]*\])*);",
+                      r"alignas(16) static \1 \2\3; emu_poison(&\2, sizeof(\2));", text)
     assert "__shared__" not in re.sub(r"//[^\n]*", "", text), "a __shared__ declaration the rewrite does not know"
     return text, n + n_dyn
 
@@ -112,5 +112,55 @@ def build() -> str:
     return so
 
 
+ALL_SOURCES = ("tracegen.cu", "derive.cu", "ntt.cu", "hash.cu", "layout.cu", "logup.cu", "quotient.cu", "open.cu", "fri.cu", "prover.cu",
+               "capi.cu", "machine.cpp", "quotient_codegen.cpp")
+
+
+def replace_ptx(text: str) -> str:
+    """the three cp.async statements of csrc/open.cu: a 4-byte copy, and nothing to wait for"""
+    text = text.replace('asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");',
+                        "*reinterpret_cast<unsigned*>(d) = *reinterpret_cast<const unsigned*>(gmem_src);")
+    text = text.replace('asm volatile("cp.async.commit_group;" ::: "memory");', ";")
+    text = text.replace('asm volatile("cp.async.wait_group 0;" ::: "memory");', ";")
+    assert "asm volatile" not in text
+    return text
+
+
+def build_full() -> str:
+    """tests/cudaemu/_build/libzkb200emu.so: EVERY source of libzkb200.so for the host, exporting the same C ABI"""
+    out_dir = os.path.join(HERE, "_build", "full")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(HERE, "_build", "libzkb200emu.so")
+    deps = [os.path.join(HERE, f) for f in ("cuda_runtime.h", "build.py")]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp", ".inc"))]
+    if os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
+        return so
+    objs = []
+    procs = []
+    for name in os.listdir(CSRC):          # headers hold device code too (ntt_lean.cuh: dynamic shared memory)
+        if name.endswith((".cuh", ".h", ".inc")):
+            text, _ = poison_shared(open(os.path.join(CSRC, name)).read())
+            with open(os.path.join(out_dir, name), "w") as f:
+                f.write(text)
+    for name in ALL_SOURCES:
+        text, _ = rewrite_launches(open(os.path.join(CSRC, name)).read())
+        text, _ = poison_shared(text)
+        text = replace_ptx(text).replace('"../../include/zkb200.h"', '"' + os.path.join(ROOT, "include", "zkb200.h") + '"')
+        dst = os.path.join(out_dir, os.path.splitext(name)[0] + "_emu.cpp")
+        with open(dst, "w") as f:
+            f.write(f'#line 1 "{os.path.join(CSRC, name)}"\n' + text)
+        obj = dst[:-4] + ".o"
+        objs.append(obj)
+        procs.append(subprocess.Popen(["g++", "-O1", "-std=c++20", "-fPIC", "-pthread", "-fpermissive", "-w", "-D__CUDACC__", "-I" + HERE, "-I" + out_dir,
+                                       "-c", dst, "-o", obj]))
+    assert all(p.wait() == 0 for p in procs), "emulated build failed"
+    subprocess.check_call(["g++", "-shared", "-pthread", *objs, "-ldl", "-o", so])
+    return so
+
+
 if __name__ == "__main__":
+    import sys
+    if "full" in sys.argv:
+        print(build_full())
+        sys.exit(0)
     print(build())

@@ -5,12 +5,15 @@
 // into emu_launch(k, g, b, args)).  Test infrastructure only; the product never sees this header (it is found before the
 // real <cuda_runtime.h> only through -I tests/cudaemu).
 //
-// Execution model: the blocks of a grid run one after the other; the threads of a block are real threads that pass a baton,
-// so exactly one runs at a time and the others wait - at the start, or inside __syncthreads(), where a thread hands the baton
-// on and waits at the block's barrier.  `__shared__` is `static` (one block at a time), `__constant__` a plain global.
+// Execution model: the blocks of a grid run one after the other; the threads of a block are fibers of the launching thread:
+// one runs at a time, until it ends or reaches a barrier (__syncthreads, a warp shuffle), and a barrier opens when every live
+// thread of the block / warp has arrived.  `__shared__` is `static` (one block at a time), `__constant__` a plain global.
 #pragma once
+#include <ucontext.h>
 #include <algorithm>
-#include <barrier>
+#include <array>
+#include <cstdio>
+#include <functional>
 #include <cstdint>
 #include <map>
 #include <type_traits>
@@ -152,88 +155,125 @@ inline void __threadfence() {}
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 template <class A, class B> inline typename std::common_type<A, B>::type min(A a, B b) { using C = typename std::common_type<A, B>::type; return (C)a < (C)b ? (C)a : (C)b; }
 template <class A, class B> inline typename std::common_type<A, B>::type max(A a, B b) { using C = typename std::common_type<A, B>::type; return (C)a < (C)b ? (C)b : (C)a; }
-// one thread runs at a time (the baton), so plain read-modify-writes are atomic here
+// one thread runs at a time, so plain read-modify-writes are atomic here
 template <class T, class V> inline T atomicAdd(T* p, V v) { T o = *p; *p = (T)(o + (T)v); return o; }
 template <class T, class V> inline T atomicMin(T* p, V v) { T o = *p; if ((T)v < o) *p = (T)v; return o; }
 template <class T> inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 
 struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
-struct EmuWarp {
-  unsigned vals[32];
-  std::barrier<> barrier;
-  explicit EmuWarp(unsigned lanes) : barrier((std::ptrdiff_t)lanes) {}
+// One CUDA thread = one fiber (ucontext) of the OS thread that launches the grid.  A fiber runs until it ends or reaches a
+// barrier (__syncthreads: the block's; a warp shuffle: its warp's), the scheduler then runs the next one; a barrier opens when
+// every fiber that is still alive in its block / warp has arrived.
+struct EmuFiber {
+  ucontext_t ctx;
+  int wait = 0;          // 0 runnable, 1 at the block barrier, 2 at the warp barrier
+  bool done = false;
 };
 struct EmuBlock {
   std::vector<void*> poisoned;      // shared arrays already filled with the poison pattern for this block
-  bool dyn_poisoned = false;
-  std::barrier<> barrier;
-  std::vector<std::unique_ptr<EmuWarp>> warps;
-  explicit EmuBlock(unsigned n) : barrier((std::ptrdiff_t)n) {
-    for (unsigned w = 0; w * 32 < n; w++) warps.emplace_back(new EmuWarp(std::min(32u, n - 32 * w)));
-  }
+  std::vector<EmuFiber> fibers;
+  std::vector<std::array<unsigned, 32>> warp_vals;
+  ucontext_t scheduler;
+  unsigned current = 0;
 };
 inline thread_local EmuIdx threadIdx, blockIdx, blockDim, gridDim;
 inline thread_local EmuBlock* emu_block = nullptr;
-inline thread_local unsigned emu_linear_tid = 0;
 inline thread_local void* emu_dyn_smem = nullptr;
-inline std::mutex emu_baton;
+inline thread_local std::function<void()>* emu_body = nullptr;
 inline std::mutex emu_launch_mu;       // one grid at a time: `__shared__` arrays are statics
 
-inline void __syncthreads() {
-  emu_baton.unlock();
-  emu_block->barrier.arrive_and_wait();
-  emu_baton.lock();
+inline void emu_yield(int wait) {
+  EmuFiber& f = emu_block->fibers[emu_block->current];
+  f.wait = wait;
+  swapcontext(&f.ctx, &emu_block->scheduler);
 }
+inline void __syncthreads() { emu_yield(1); }
 inline void* emu_dyn_shared() { return emu_dyn_smem; }
-// every lane of the warp takes part (all masks in this library are full)
+// every live lane of the warp takes part (all masks in this library are full)
 inline unsigned __shfl_xor_sync(unsigned, unsigned v, int d) {
-  EmuWarp& w = *emu_block->warps[emu_linear_tid / 32];
-  const unsigned lane = emu_linear_tid % 32;
-  w.vals[lane] = v;
-  emu_baton.unlock(); w.barrier.arrive_and_wait(); emu_baton.lock();
-  const unsigned r = w.vals[lane ^ (unsigned)d];
-  emu_baton.unlock(); w.barrier.arrive_and_wait(); emu_baton.lock();
+  const unsigned t = emu_block->current;
+  std::array<unsigned, 32>& vals = emu_block->warp_vals[t / 32];
+  vals[t % 32] = v;
+  emu_yield(2);
+  const unsigned r = vals[(t % 32) ^ (unsigned)d];
+  emu_yield(2);
   return r;
 }
-// tests/cudaemu/build.py puts this after every `__shared__` array declaration (runs under the baton)
+// tests/cudaemu/build.py puts this after every `__shared__` array declaration
 inline void emu_poison(void* p, size_t bytes) {
   for (void* q : emu_block->poisoned) if (q == p) return;
   emu_block->poisoned.push_back(p);
   unsigned* w = static_cast<unsigned*>(p);
   for (size_t i = 0; i < bytes / 4; i++) w[i] = 0xDEADBEEFu;
 }
+inline void emu_trampoline() {
+  (*emu_body)();
+  EmuFiber& f = emu_block->fibers[emu_block->current];
+  f.done = true;
+  swapcontext(&f.ctx, &emu_block->scheduler);
+}
 
-// `block` threads per launch, reused for every block of the grid; a block starts when the one before it has ended
 template <class K, class... A>
 void emu_launch_dyn(K kernel, dim3 grid, dim3 block, size_t dyn_bytes, A... args) {
   std::lock_guard<std::mutex> one_grid(emu_launch_mu);
   const unsigned nthreads = block.x * block.y * block.z, nblocks = grid.x * grid.y * grid.z;
-  std::vector<std::unique_ptr<EmuBlock>> blocks;
-  for (unsigned b = 0; b < nblocks; b++) blocks.emplace_back(new EmuBlock(nthreads));
+  constexpr size_t STACK = 512 << 10;
+  std::vector<std::unique_ptr<char[]>> stacks;
+  for (unsigned t = 0; t < nthreads; t++) stacks.emplace_back(new char[STACK]);
   std::vector<unsigned> dyn((dyn_bytes + 3) / 4 + 4);
-  std::barrier<> block_end((std::ptrdiff_t)nthreads);
-  std::vector<std::thread> ts;
-  ts.reserve(nthreads);
-  for (unsigned t = 0; t < nthreads; t++)
-    ts.emplace_back([&, t] {
-      for (unsigned b = 0; b < nblocks; b++) {
+  std::function<void()> body = [&] { kernel(args...); };
+  emu_body = &body;
+  emu_dyn_smem = (void*)(((uintptr_t)dyn.data() + 15) & ~(uintptr_t)15);
+  blockDim.x = block.x; blockDim.y = block.y; blockDim.z = block.z;
+  gridDim.x = grid.x; gridDim.y = grid.y; gridDim.z = grid.z;
+  EmuBlock blk;
+  blk.fibers.resize(nthreads);
+  blk.warp_vals.resize((nthreads + 31) / 32);
+  emu_block = &blk;
+  for (unsigned b = 0; b < nblocks; b++) {
+    blockIdx.x = b % grid.x; blockIdx.y = b / grid.x % grid.y; blockIdx.z = b / (grid.x * grid.y);
+    blk.poisoned.clear();
+    std::fill(dyn.begin(), dyn.end(), 0xDEADBEEFu);
+    for (unsigned t = 0; t < nthreads; t++) {
+      EmuFiber& f = blk.fibers[t];
+      f.wait = 0; f.done = false;
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = stacks[t].get();
+      f.ctx.uc_stack.ss_size = STACK;
+      f.ctx.uc_link = nullptr;
+      makecontext(&f.ctx, emu_trampoline, 0);
+    }
+    unsigned alive = nthreads;
+    while (alive) {
+      bool progress = false;
+      for (unsigned t = 0; t < nthreads; t++) {
+        EmuFiber& f = blk.fibers[t];
+        if (f.done || f.wait) continue;
         threadIdx.x = t % block.x; threadIdx.y = t / block.x % block.y; threadIdx.z = t / (block.x * block.y);
-        blockIdx.x = b % grid.x; blockIdx.y = b / grid.x % grid.y; blockIdx.z = b / (grid.x * grid.y);
-        blockDim.x = block.x; blockDim.y = block.y; blockDim.z = block.z;
-        gridDim.x = grid.x; gridDim.y = grid.y; gridDim.z = grid.z;
-        emu_linear_tid = t;
-        emu_block = blocks[b].get();
-        emu_dyn_smem = (void*)(((uintptr_t)dyn.data() + 15) & ~(uintptr_t)15);
-        emu_baton.lock();
-        if (!emu_block->dyn_poisoned) { std::fill(dyn.begin(), dyn.end(), 0xDEADBEEFu); emu_block->dyn_poisoned = true; }   // the block's first thread to run
-        kernel(args...);
-        emu_baton.unlock();
-        emu_block->warps[t / 32]->barrier.arrive_and_drop();
-        emu_block->barrier.arrive_and_drop();
-        block_end.arrive_and_wait();
+        blk.current = t;
+        swapcontext(&blk.scheduler, &f.ctx);
+        progress = true;
+        if (f.done) alive--;
       }
-    });
-  for (auto& th : ts) th.join();
+      // barriers open when every live fiber of the block / warp has arrived
+      bool all_block = alive > 0;
+      for (auto& f : blk.fibers) if (!f.done && f.wait != 1) { all_block = false; break; }
+      if (all_block) { for (auto& f : blk.fibers) f.wait = 0; progress = true; }
+      for (unsigned w = 0; w * 32 < nthreads; w++) {
+        bool all = false, any = false;
+        for (unsigned t = 32 * w; t < nthreads && t < 32 * w + 32; t++) {
+          const EmuFiber& f = blk.fibers[t];
+          if (f.done) continue;
+          if (f.wait == 2) any = true; else { any = false; all = false; goto next_warp; }
+          all = true;
+        }
+        if (all && any) { for (unsigned t = 32 * w; t < nthreads && t < 32 * w + 32; t++) if (!blk.fibers[t].done) blk.fibers[t].wait = 0; progress = true; }
+      next_warp:;
+      }
+      if (alive && !progress) { fprintf(stderr, "cudaemu: deadlock (a barrier some thread of the block never reaches)\n"); abort(); }
+    }
+  }
+  emu_block = nullptr;
 }
 template <class K, class... A>
 void emu_launch(K kernel, dim3 grid, dim3 block, A... args) { emu_launch_dyn(kernel, grid, block, 0, args...); }
