@@ -245,7 +245,7 @@ def test_gpu_trace_errors(gpu):
     torch, prover = gpu
     out = torch.zeros(16 * 67, dtype=torch.int32, device="cuda")
     with pytest.raises(ZkbError, match="no row filler"):
-        prover.generate_alu_trace("Cpu", np.zeros((1, 7), np.uint32), 4, out)
+        prover.generate_alu_trace("Byte", np.zeros((1, 7), np.uint32), 4, out)      # multiplicities, not rows of events (K7)
     with pytest.raises(ZkbError, match="more events than rows"):
         prover.generate_alu_trace("AddSub", tg.synthetic_events("AddSub", 17), 4, out)
 

@@ -265,7 +265,7 @@ def test_commit_from_events_errors(gpu, oracle):
     try:
         inputs = {k: kb.to_monty(v) for k, v in case.traces.items()}
         bad = dict(inputs)
-        bad["Cpu"] = EventTrace(np.zeros((4, 7), np.uint32), 6, case.traces["Cpu"].shape[1])
+        bad["Byte"] = EventTrace(np.zeros((4, 7), np.uint32), 16, case.traces["Byte"].shape[1])     # a table without a row filler
         with pytest.raises(ZkbError, match="no row filler"):
             prover.commit(bad, case.public_values)
         bad = dict(inputs)
