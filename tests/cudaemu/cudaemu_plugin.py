@@ -39,6 +39,15 @@ def _wrap_factory(fn):
     return f
 
 
+def _pinned(t):
+    t = t.clone().contiguous()
+    if t.numel():
+        _lib.emu_register(t.data_ptr(), t.numel() * t.element_size(), 1)      # cudaMemoryTypeHost
+        _keep.append(t)
+    return t
+
+
+torch.Tensor.pin_memory = lambda self, *a, **kw: _pinned(self)
 torch.cuda.is_available = lambda: True
 torch.cuda.device_count = lambda: 1
 torch.Tensor.cuda = lambda self, *a, **kw: _as_device(self.clone())
