@@ -81,6 +81,12 @@ typedef struct {
  * The library's row filler writes the table column-major straight into the shard's trace storage; no trace bytes
  * cross PCIe and no layout change runs.  Error if the library has no row filler for `name`. */
 #define ZKB200_TRACE_EVENTS 2u
+/* A table that only RECEIVES lookups (Byte, Program): nothing is handed over (`data` is ignored, height = the height of its
+ * preprocessed trace); its multiplicity columns are counted on the device from the shard's other tables (K7,
+ * zkb200_derive_multiplicities below) - what the host accumulates in the reference while it generates those tables
+ * (crates/core/machine/src/bytes/trace.rs:46-67, program/mod.rs:115-158).  zkb200_prove_shard only: the proving key holds the
+ * preprocessed tables the count needs; zkb200_commit refuses the flag.  Excludes the other flags. */
+#define ZKB200_TRACE_DERIVED 4u
 
 /* MachineProver::new(machine) — crates/stark/src/prover.rs:43.  `desc` is a ZKMD descriptor. */
 int zkb200_ctx_create(int device, const uint32_t* desc, size_t n_words, zkb200_ctx** out);

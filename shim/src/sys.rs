@@ -13,6 +13,7 @@ pub struct zkb200_trace {
 }
 pub const ZKB200_TRACE_COL_MAJOR: u32 = 1;
 pub const ZKB200_TRACE_EVENTS: u32 = 2;
+pub const ZKB200_TRACE_DERIVED: u32 = 4; // zkb200_prove_shard only: Byte / Program multiplicities counted on the device (K7)
 /// A table resident on the device, column-major Montgomery (`zkb200_table`): a sender of `zkb200_derive_multiplicities`.
 #[repr(C)]
 pub struct zkb200_table {

@@ -43,9 +43,10 @@ def test_kernel_level_entry_points_under_emulation():
 
 
 def test_derive_multiplicities_gpu_cases_under_emulation():
-    """K7 through the C ABI (zkb200_derive_multiplicities), the test cases the B200 run will execute"""
+    """K7 through the C ABI (zkb200_derive_multiplicities) and shards proved with ZKB200_TRACE_DERIVED tables (Byte and Program
+    never handed over): the test cases the B200 run will execute"""
     out = _run_emulated("tests/test_zzzz_derive.py")
-    assert "4 passed" in out, out
+    assert "6 passed" in out, out
 
 
 @pytest.mark.parametrize("selection", [

@@ -242,3 +242,32 @@ def test_derive_multiplicities_reports_a_missing_tuple(oracle):
             prover.derive_multiplicities("Byte", dev(case.prep["Byte"]), h, snd, d_out)
     finally:
         prover.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["mini", "edge"])
+def test_shard_proves_with_derived_tables(oracle, which):
+    """ZKB200_TRACE_DERIVED: Byte and Program are not handed over at all - zkb200_prove_shard counts their multiplicity columns
+    from the shard's other tables (made resident first) and the proof is the oracle's proof over the full set of tables, word
+    for word; zkb200_commit, which has no proving key, refuses the flag."""
+    from ziren_b200.prover import B200Prover, DerivedTrace, ZkbError
+    case = dict(_cases())[which]
+    om = oracle.OracleMachine(case.machine)
+    om.setup(case.prep)
+    want, _ = om.prove_shard(case.traces, case.public_values)
+    prover = B200Prover(case.machine, device=0)
+    try:
+        pk = prover.setup({k: kb.to_monty(v) for k, v in case.prep.items()})
+        inputs = {k: kb.to_monty(v) for k, v in case.traces.items()}
+        for r in ("Byte", "Program"):
+            if r in inputs:
+                inputs[r] = DerivedTrace(*case.traces[r].shape)
+        got, _ = prover.prove_shard(pk, inputs, case.public_values)
+        ok, err = om.verify_shard(got)
+        assert ok, err
+        assert np.array_equal(got, want)
+        with pytest.raises(ZkbError, match="bad zkb200_trace.flags"):
+            prover.commit(inputs, case.public_values)
+        pk.free()
+    finally:
+        prover.close()

@@ -17,7 +17,7 @@ class Trace(C.Structure):
                 ("flags", C.c_uint32), ("n_events", C.c_size_t)]
 
 
-TRACE_COL_MAJOR, TRACE_EVENTS = 1, 2
+TRACE_COL_MAJOR, TRACE_EVENTS, TRACE_DERIVED = 1, 2, 4
 
 
 class Table(C.Structure):

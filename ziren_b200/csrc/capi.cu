@@ -181,7 +181,24 @@ int zkb200_open(zkb200_ctx* ctx, const zkb200_pk* pk, zkb200_shard* shard, uint3
 int zkb200_prove_shard(zkb200_ctx* ctx, const zkb200_pk* pk, const zkb200_trace* traces, int n, const uint32_t* pv, size_t npv,
                        uint32_t challenger[34], uint32_t** proof_words, size_t* n_words) {
   zkb200_shard* sh = nullptr;
-  int rc = zkb200_commit(ctx, traces, n, pv, npv, nullptr, &sh);
+  bool derived = false;
+  for (int i = 0; i < n; i++) derived = derived || (traces[i].flags & TRACE_DERIVED);
+  int rc;
+  if (derived) {       // ZKB200_TRACE_DERIVED: the commit needs the proving key's preprocessed tables (prover.cu: prover_commit_derived)
+    rc = guarded(ctx, [&] {
+      if (pk->per_dev.size() != ctx->devs.size()) throw std::runtime_error("zkb200: prove_shard: the proving key belongs to another context");
+      const int k = ctx->pick(traces, n);
+      ctx->inflight[k]++;
+      Shard* s = nullptr;
+      try {
+        s = prover_commit_derived(*ctx->devs[k], *pk->per_dev[k], to_traces(traces, n), pv, npv);
+      } catch (...) {
+        ctx->inflight[k]--;
+        throw;
+      }
+      sh = new zkb200_shard{s, ctx, k};
+    });
+  } else rc = zkb200_commit(ctx, traces, n, pv, npv, nullptr, &sh);
   if (rc) return rc;
   rc = zkb200_open(ctx, pk, sh, challenger, proof_words, n_words);
   zkb200_shard_free(sh);

@@ -3,6 +3,7 @@
 // context stream, runs the duplex challenger on the host between stages (the transcript order of
 // crates/stark/src/prover.rs:298-653) and packs the "ZKPF" proof.
 #include "prover.h"
+#include "derive.h"
 #include "tracegen.h"
 #include <algorithm>
 #include <array>
@@ -642,6 +643,78 @@ Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces_in, const u32*
   pcs_merkle(ctx, L, out, &pre, "commit_main_merkle");
   sh->public_values.assign(pv, pv + npv);
   return sh.release();
+}
+
+// ZKB200_TRACE_DERIVED: a table that only receives lookups (Byte, Program) is not handed over at all; its multiplicity columns
+// are counted from the rows of the shard's other tables (csrc/derive.cuh) - in the reference the host accumulates them while
+// it generates those tables (bytes/trace.rs:46-67, program/mod.rs:115-158).  Every other table is first made resident in its
+// column-major form (row fillers for event records, the layout change for uploaded rows), then the derived tables are
+// counted, then the ordinary commit runs over device-resident column-major tables.  An optional path: it holds the traces
+// twice for the duration of the call and drains the device before it returns.
+Shard* prover_commit_derived(Ctx& ctx, const Pk& pk, const std::vector<TraceIn>& traces_in, const u32* pv, size_t npv) {
+  ZKB_CUDA(cudaSetDevice(ctx.device));
+  std::vector<TraceIn> resident = traces_in;
+  std::vector<DevMat> owned;
+  std::vector<DevBuf> event_bufs;
+  owned.reserve(resident.size());
+  event_bufs.reserve(resident.size());
+  struct Drain { ~Drain() { cudaDeviceSynchronize(); } } drain;     // before `owned` goes: the commit's copies read it (declared last = runs first)
+  {
+    LaneGuard guard(ctx);
+    Lane& L = *guard.lane;
+    L.begin();
+    cudaStream_t s = L.stream;
+    for (auto& t : resident) {
+      const ChipInfo* c = ctx.machine.find(t.name);
+      if (!c) throw std::runtime_error("zkb200: commit: unknown chip " + t.name);
+      if (c->main_width != t.width) throw std::runtime_error("zkb200: commit: main width mismatch for " + t.name);
+      if (t.flags & ~(TRACE_EVENTS | TRACE_COL_MAJOR | TRACE_DERIVED)) throw std::runtime_error("zkb200: commit: bad zkb200_trace.flags for " + t.name);
+      if ((t.flags & TRACE_DERIVED) && t.flags != TRACE_DERIVED) throw std::runtime_error("zkb200: commit: ZKB200_TRACE_DERIVED excludes the other flags: " + t.name);
+      if ((t.flags & TRACE_EVENTS) && (t.flags & TRACE_COL_MAJOR)) throw std::runtime_error("zkb200: commit: bad zkb200_trace.flags for " + t.name);
+      if (t.flags & (TRACE_DERIVED | TRACE_COL_MAJOR)) continue;
+      if (t.height * t.width == 0) continue;
+      if (t.flags & TRACE_EVENTS) {
+        const size_t rec = event_record_words(t.name);
+        const size_t rows_needed = t.name == "KeccakSponge" ? t.n_events * KS_ROUNDS : t.name == "Global" ? t.n_events
+                                   : ceil_div(t.n_events, (size_t)alu_events_per_row(alu_chip_by_name(t.name.c_str())));
+        if (rows_needed > t.height) throw std::runtime_error("zkb200: commit: more event rows than the table holds: " + t.name);
+        const u32* ev = t.data;
+        if (t.n_events && !is_device_pointer(t.data)) {
+          event_bufs.emplace_back(t.n_events * rec, s);
+          ZKB_CUDA(cudaMemcpyAsync(event_bufs.back().p, t.data, t.n_events * rec * sizeof(u32), cudaMemcpyHostToDevice, s));
+          ev = event_bufs.back().p;
+        }
+        owned.emplace_back(t.height, t.width, s);
+        generate_trace_colmajor(t.name, ev, t.n_events, t.height, owned.back().d(), s);
+      } else {
+        owned.push_back(upload_colmajor(ctx, t.data, t.height, t.width, s, s));
+      }
+      t.data = owned.back().d();
+      t.flags = TRACE_COL_MAJOR;
+      t.n_events = 0;
+    }
+    std::vector<std::pair<size_t, const u32*>> derived;
+    for (size_t i = 0; i < resident.size(); i++) {
+      TraceIn& t = resident[i];
+      if (!(t.flags & TRACE_DERIVED)) continue;
+      const ChipInfo* r = ctx.machine.find(t.name);
+      const int pi = pk.index_of(t.name);
+      if (pi < 0 || pk.traces[pi].height != t.height) throw std::runtime_error("zkb200: commit: ZKB200_TRACE_DERIVED needs the table's preprocessed trace at this height: " + t.name);
+      std::vector<DeriveSender> snd;
+      for (auto& o : resident) {
+        if ((o.flags & TRACE_DERIVED) || o.height * o.width == 0) continue;
+        const int qi = pk.index_of(o.name);
+        if (qi >= 0 && pk.traces[qi].height != o.height) throw std::runtime_error("zkb200: commit: preprocessed and main height differ for " + o.name);
+        snd.push_back({ctx.machine.find(o.name), DeriveTable{qi >= 0 ? pk.traces[qi].d() : nullptr, o.data, o.height}});
+      }
+      owned.emplace_back(t.height, t.width, s);
+      derive_multiplicities(ctx.machine, *r, pk.traces[pi].d(), t.height, snd, owned.back().d(), s);
+      derived.push_back({i, owned.back().d()});
+    }
+    for (auto& d : derived) { resident[d.first].data = d.second; resident[d.first].flags = TRACE_COL_MAJOR; }
+    ZKB_CUDA(cudaStreamSynchronize(s));
+  }
+  return prover_commit(ctx, resident, pv, npv);
 }
 
 // ---- proof packing ------------------------------------------------------------------------------

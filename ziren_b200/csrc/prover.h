@@ -124,7 +124,7 @@ struct Ctx {
 // row-major Montgomery, host or device pointer (flags 0); device column-major (flags 1); event records (flags 2:
 // include/zkb200.h ZKB200_TRACE_COL_MAJOR / ZKB200_TRACE_EVENTS)
 struct TraceIn { std::string name; const u32* data; size_t height, width; u32 flags = 0; size_t n_events = 0; };
-constexpr u32 TRACE_COL_MAJOR = 1u, TRACE_EVENTS = 2u;
+constexpr u32 TRACE_COL_MAJOR = 1u, TRACE_EVENTS = 2u, TRACE_DERIVED = 4u;
 
 struct Pk {
   Ctx* ctx = nullptr;
@@ -151,6 +151,9 @@ struct Shard {
 
 Pk* prover_setup(Ctx& ctx, const std::vector<TraceIn>& prep, u32 pc_start, const u32* init_gsum);
 Shard* prover_commit(Ctx& ctx, const std::vector<TraceIn>& traces, const u32* pv, size_t npv);
+// commit of a shard with ZKB200_TRACE_DERIVED tables (multiplicity columns derived from the shard's other tables, K7): needs the
+// proving key for the preprocessed tables, so only zkb200_prove_shard reaches it
+Shard* prover_commit_derived(Ctx& ctx, const Pk& pk, const std::vector<TraceIn>& traces, const u32* pv, size_t npv);
 // consumes nothing; caller frees the shard.  challenger34: canonical image, in/out.
 std::vector<u32> prover_open(Ctx& ctx, const Pk& pk, Shard& shard, u32* challenger34);
 

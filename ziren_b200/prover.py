@@ -103,6 +103,14 @@ class EventTrace:
         self.n_events = int(shp[0]) if len(shp) else 0
 
 
+class DerivedTrace:
+    """A receive-only table (Byte, Program) that is NOT handed over (ZKB200_TRACE_DERIVED): `prove_shard` counts its
+    multiplicity columns on the device from the shard's other tables (K7).  `height`: the height of its preprocessed trace."""
+
+    def __init__(self, height: int, width: int):
+        self.height, self.width = int(height), int(width)
+
+
 class ColMajorTrace:
     """A device-resident COLUMN-MAJOR table (ZKB200_TRACE_COL_MAJOR): `data` is a CUDA tensor of width x height words."""
 
@@ -145,6 +153,8 @@ class B200Prover:
             if isinstance(t, EventTrace):
                 arr[i] = _ffi.Trace(b, _data_ptr(t.events) if t.n_events else None, 1 << t.log_height, t.width,
                                     _ffi.TRACE_EVENTS, t.n_events)
+            elif isinstance(t, DerivedTrace):
+                arr[i] = _ffi.Trace(b, None, t.height, t.width, _ffi.TRACE_DERIVED, 0)
             elif isinstance(t, ColMajorTrace):
                 arr[i] = _ffi.Trace(b, _data_ptr(t.data), t.height, t.width, _ffi.TRACE_COL_MAJOR, 0)
             else:
@@ -201,6 +211,16 @@ class B200Prover:
 
     def prove_shard(self, pk: ProvingKey, traces: dict, public_values, challenger: np.ndarray | None = None):
         """commit + open for one record: the loop body of `prove` (prover.rs:681-688)."""
+        if any(isinstance(t, DerivedTrace) for t in traces.values()):
+            # the commit of derived tables reads the proving key's preprocessed traces: one call (zkb200_prove_shard)
+            arr, keep = self._traces(traces)
+            pv = _np32(public_values)
+            st = _np32(challenger).copy() if challenger is not None else pk.observe_into()
+            out, n = u32p(), C.c_size_t()
+            self._check(_ffi.lib().zkb200_prove_shard(self._h, pk._h, arr, len(traces), _p(pv), pv.size, _p(st), C.byref(out), C.byref(n)))
+            proof = np.ctypeslib.as_array(out, shape=(n.value,)).copy()
+            _ffi.lib().zkb200_free(out)
+            return proof, st
         data = self.commit(traces, public_values)
         try:
             return self.open(pk, data, challenger)
