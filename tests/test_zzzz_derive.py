@@ -271,3 +271,31 @@ def test_shard_proves_with_derived_tables(oracle, which):
         pk.free()
     finally:
         prover.close()
+
+
+@pytest.mark.gpu
+def test_real_keccak_shard_proves_from_events_with_a_derived_byte_table(oracle):
+    """The shard of the real KeccakSponge chip (357 lookups per row) with the chip's table handed over as EVENT RECORDS and the
+    65536-row Byte table not handed over at all: rows from the row filler, Byte multiplicities counted from them and from the
+    other tables inside zkb200_prove_shard - the oracle's proof over the oracle's tables, word for word."""
+    from ziren_b200 import keccak_sponge as ks
+    from ziren_b200.prover import B200Prover, DerivedTrace, EventTrace
+    b = ks.synthetic_blocks(3, [1, 2, 1], seed=5, shard=1)
+    log_h = ks.padded_log_height(len(b))
+    case = synthetic.keccak_real_case(b, oracle.keccak_sponge_trace(b, 1 << log_h), log_cpu=10, num_queries=4, pow_bits=2)
+    om = oracle.OracleMachine(case.machine)
+    om.setup(case.prep)
+    want, _ = om.prove_shard(case.traces, case.public_values)
+    prover = B200Prover(case.machine, device=0)
+    try:
+        pk = prover.setup({k: kb.to_monty(v) for k, v in case.prep.items()})
+        inputs = {k: kb.to_monty(v) for k, v in case.traces.items()}
+        inputs["KeccakSponge"] = EventTrace(b.reshape(len(b), -1), log_h, ks.WIDTH)
+        inputs["Byte"] = DerivedTrace(*case.traces["Byte"].shape)
+        got, _ = prover.prove_shard(pk, inputs, case.public_values)
+        ok, err = om.verify_shard(got)
+        assert ok, err
+        assert np.array_equal(got, want)
+        pk.free()
+    finally:
+        prover.close()
